@@ -1,0 +1,125 @@
+"""ctypes binding of libclipgp.so (the C ABI declared in include/clipgp.h).
+
+There is no CPU fallback: if the shared library is missing, or a compute entry point is called
+without a CUDA device, a RuntimeError is raised (the reference's ``try/except Exception`` blocks
+around GP pre-training then behave as they do for any other failure).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libclipgp.so")
+
+KERNEL_IDS = {"rbf": 0, "matern": 1, "linear": 2}
+
+c_f32p = C.c_void_p
+c_i64 = C.c_int64
+
+
+class GpArgs(C.Structure):
+    """Mirror of ``clipgp_gp_args`` (include/clipgp.h)."""
+    _fields_ = [
+        ("kernel_type", C.c_int32), ("x_is_z_prefix", C.c_int32),
+        ("C", c_i64), ("T", c_i64), ("n", c_i64), ("d", c_i64), ("S", c_i64),
+        ("Z", C.c_void_p), ("X", C.c_void_p),
+        ("raw_lengthscale", C.c_void_p), ("raw_outputscale", C.c_void_p), ("raw_variance", C.c_void_p),
+        ("var_mean", C.c_void_p), ("chol_var", C.c_void_p), ("mean_x", C.c_void_p),
+        ("eps", C.c_void_p), ("eps_sc", c_i64), ("eps_st", c_i64), ("eps_ss", c_i64),
+        ("rng_state", C.c_void_p), ("s_offset", c_i64), ("S_total", c_i64),
+        ("w", C.c_void_p), ("kl", C.c_void_p), ("L", C.c_void_p), ("A", C.c_void_p), ("R", C.c_void_p),
+        ("status", C.c_void_p),
+    ]
+
+
+class GpBwdArgs(C.Structure):
+    """Mirror of ``clipgp_gp_bwd_args``."""
+    _fields_ = [
+        ("dw", C.c_void_p), ("dkl", C.c_void_p), ("dkl_scalar", C.c_float),
+        ("dZ_last", C.c_void_p), ("draw_lengthscale", C.c_void_p), ("draw_outputscale", C.c_void_p),
+        ("draw_variance", C.c_void_p), ("dvar_mean", C.c_void_p), ("dchol_var", C.c_void_p), ("dmean_x", C.c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "clipgp_last_error": (C.c_char_p, []),
+    "clipgp_version": (C.c_int, []),
+    "clipgp_launch_count": (c_i64, []),
+    "clipgp_calibration_from_logits": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p]),
+    "clipgp_ece_hist": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
+    "clipgp_aece_bins": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "clipgp_gp_smem_bytes": (c_i64, [c_i64, c_i64, c_i64, C.c_int]),
+    "clipgp_gp_forward": (C.c_int, [C.POINTER(GpArgs), C.c_void_p]),
+    "clipgp_gp_backward": (C.c_int, [C.POINTER(GpArgs), C.POINTER(GpBwdArgs), C.c_void_p]),
+    "clipgp_proto_forward": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, c_i64, C.c_void_p, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p]),
+    "clipgp_proto_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, c_i64,
+                                        C.c_void_p, C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load() -> C.CDLL:
+    """Load libclipgp.so (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the clipgp kernels)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "clipgp") -> None:
+    if rc != 0:
+        msg = load().clipgp_last_error()
+        raise RuntimeError(f"{what} failed (status {rc}): {msg.decode() if msg else 'unknown error'}")
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("clipgp kernels need CUDA tensors (sm_100a); there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"clipgp: tensors on different devices ({dev} vs {t.device})")
+    if dev is None:
+        raise RuntimeError("clipgp: no tensor given")
+    return dev
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().clipgp_launch_count())

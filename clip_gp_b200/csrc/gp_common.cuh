@@ -1,0 +1,240 @@
+// Per-class building blocks of the GP template weighter kernels (one CTA per class, everything in
+// shared memory): streamed Gram accumulation, block Cholesky, triangular solves, Cholesky adjoint.
+// Algorithm sheet: oracle/gp_manual.py (validated against autograd through oracle/gp.py).
+#pragma once
+#include "common.cuh"
+
+namespace clipgp {
+namespace gp {
+
+constexpr int kThreads = 128;  // threads per class CTA
+constexpr int KC = 64;         // feature-dim chunk streamed through shared memory
+constexpr int KCP = KC + 1;    // padded row stride of a chunk tile (conflict-free row access)
+constexpr int kMaxTiles = 3;   // 4x4 register tiles per thread: 3*128 >= ceil(65/4)^2 = 289
+
+__device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
+
+// Copy columns [k0, k0+KC) of a row-major [rows, d] global matrix into a [rows_pad][KCP] tile, optionally
+// scaled per column (inverse length-scales).  Rows >= rows and columns >= d are zero-filled.
+__device__ __forceinline__ void load_chunk(float* __restrict__ tile, const float* __restrict__ G, int rows,
+                                           int rows_pad, int d, int k0, const float* __restrict__ col_scale) {
+    for (int idx = threadIdx.x; idx < rows_pad * KC; idx += blockDim.x) {
+        const int r = idx / KC, k = idx - r * KC;
+        float v = 0.f;
+        if (r < rows && k0 + k < d) {
+            v = __ldg(G + (size_t)r * d + k0 + k);
+            if (col_scale) v *= col_scale[k0 + k];
+        }
+        tile[r * KCP + k] = v;
+    }
+}
+
+// acc[t] += sum_k op(a_ik, b_jk) over one chunk for this thread's 4x4 tiles.
+// DOT: a*b ; otherwise (a-b)^2.
+template <bool DOT>
+__device__ __forceinline__ void gram_chunk(float (&acc)[kMaxTiles][16], const float* __restrict__ tA,
+                                           const float* __restrict__ tB, int tiles_m, int tiles_n) {
+    const int ntiles = tiles_m * tiles_n;
+#pragma unroll
+    for (int t = 0; t < kMaxTiles; ++t) {
+        const int tile = threadIdx.x + t * blockDim.x;
+        if (tile < ntiles) {
+            const int ti = tile / tiles_n, tj = tile - ti * tiles_n;
+            const float* pa = tA + (ti * 4) * KCP;
+            const float* pb = tB + (tj * 4) * KCP;
+#pragma unroll 4
+            for (int k = 0; k < KC; ++k) {
+                float a[4], b[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) { a[x] = pa[x * KCP + k]; b[x] = pb[x * KCP + k]; }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        if (DOT) acc[t][x * 4 + y] = fmaf(a[x], b[y], acc[t][x * 4 + y]);
+                        else { const float df = a[x] - b[y]; acc[t][x * 4 + y] = fmaf(df, df, acc[t][x * 4 + y]); }
+                    }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float kernel_value(int kernel_type, float acc, float amp) {
+    if (kernel_type == CLIPGP_KERNEL_RBF) return amp * expf(-0.5f * acc);                     // os * exp(-r2/2)
+    if (kernel_type == CLIPGP_KERNEL_MATERN12) return expf(-sqrtf(fmaxf(acc, 1e-30f)));        // exp(-r)
+    return amp * acc;                                                                          // v * <a,b>
+}
+
+// Full Gram block K(A rows, B rows) -> out[i*ldo + j] (type OutT), i < nA, j < nB.
+//   gA/gB: global row-major [nA,d] / [nB,d]; if gB == gA the second tile load is skipped.
+//   raw_out (optional, float [nA][ldr]): the un-transformed accumulator (r^2 or dot), needed by the adjoint.
+template <typename OutT>
+__device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ raw_out, int ldr,
+                           const float* __restrict__ gA, int nA, const float* __restrict__ gB, int nB, int d,
+                           int kernel_type, float amp, const float* __restrict__ inv_ls, float* tileA, float* tileB) {
+    const bool same = (gA == gB);
+    const int pA = pad4(nA), pB = pad4(nB);
+    const int tiles_m = pA >> 2, tiles_n = pB >> 2;
+    const bool dot = (kernel_type == CLIPGP_KERNEL_LINEAR);
+    float acc[kMaxTiles][16];
+#pragma unroll
+    for (int t = 0; t < kMaxTiles; ++t)
+#pragma unroll
+        for (int x = 0; x < 16; ++x) acc[t][x] = 0.f;
+    for (int k0 = 0; k0 < d; k0 += KC) {
+        __syncthreads();
+        load_chunk(tileA, gA, nA, pA, d, k0, dot ? nullptr : inv_ls);
+        if (!same) load_chunk(tileB, gB, nB, pB, d, k0, dot ? nullptr : inv_ls);
+        __syncthreads();
+        if (dot) gram_chunk<true>(acc, tileA, same ? tileA : tileB, tiles_m, tiles_n);
+        else gram_chunk<false>(acc, tileA, same ? tileA : tileB, tiles_m, tiles_n);
+    }
+    const int ntiles = tiles_m * tiles_n;
+#pragma unroll
+    for (int t = 0; t < kMaxTiles; ++t) {
+        const int tile = threadIdx.x + t * blockDim.x;
+        if (tile < ntiles) {
+            const int ti = tile / tiles_n, tj = tile - ti * tiles_n;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int i = ti * 4 + x, j = tj * 4 + y;
+                    if (i < nA && j < nB) {
+                        const float a = acc[t][x * 4 + y];
+                        if (raw_out) raw_out[i * ldr + j] = a;
+                        if (out) out[i * ldo + j] = (OutT)kernel_value(kernel_type, a, amp);
+                    }
+                }
+        }
+    }
+    __syncthreads();
+}
+
+// In-place lower Cholesky of the n x n matrix A (row-major, leading dim ld); only the lower triangle is read
+// or written.  invd[j] = 1 / L[j][j].  Returns true (uniformly) when a pivot was not strictly positive.
+template <typename T>
+__device__ bool block_cholesky(T* __restrict__ A, int n, int ld, T* __restrict__ invd) {
+    bool fail = false;
+    for (int j = 0; j < n; ++j) {
+        __syncthreads();
+        const T ajj = A[j * ld + j];
+        if (!(ajj > (T)0)) fail = true;
+        const T dj = sqrt(ajj);
+        const T inv = (T)1 / dj;
+        __syncthreads();
+        for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) A[i * ld + j] *= inv;
+        if (threadIdx.x == 0) { A[j * ld + j] = dj; invd[j] = inv; }
+        __syncthreads();
+        const int m = n - j - 1;
+        for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+            const int r = idx / m, c = idx - r * m;
+            if (c <= r) {
+                const int i = j + 1 + r, k = j + 1 + c;
+                A[i * ld + k] -= A[i * ld + j] * A[k * ld + j];
+            }
+        }
+    }
+    __syncthreads();
+    return fail;
+}
+
+// Solve L X = B in place (B is [n][ncol], leading dim ldb); one thread per column.
+template <typename T>
+__device__ void trsm_lower_left(const T* __restrict__ L, int ldl, const T* __restrict__ invd, T* __restrict__ B,
+                                int ldb, int n, int ncol) {
+    for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+        for (int i = 0; i < n; ++i) {
+            T s = B[i * ldb + c];
+            for (int k = 0; k < i; ++k) s -= L[i * ldl + k] * B[k * ldb + c];
+            B[i * ldb + c] = s * invd[i];
+        }
+    }
+    __syncthreads();
+}
+
+// Solve L^T X = B in place (back substitution); one thread per column.
+template <typename T>
+__device__ void trsm_lowerT_left(const T* __restrict__ L, int ldl, const T* __restrict__ invd, T* __restrict__ B,
+                                 int ldb, int n, int ncol) {
+    for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+        for (int i = n - 1; i >= 0; --i) {
+            T s = B[i * ldb + c];
+            for (int k = i + 1; k < n; ++k) s -= L[k * ldl + i] * B[k * ldb + c];
+            B[i * ldb + c] = s * invd[i];
+        }
+    }
+    __syncthreads();
+}
+
+// Solve Y L = X in place (X is [nrow][n]); one thread per row:  y_i = (x_i - sum_{k>i} y_k L[k][i]) / L[i][i].
+template <typename T>
+__device__ void trsm_lower_right(const T* __restrict__ L, int ldl, const T* __restrict__ invd, T* __restrict__ X,
+                                 int ldx, int n, int nrow) {
+    for (int r = threadIdx.x; r < nrow; r += blockDim.x) {
+        for (int i = n - 1; i >= 0; --i) {
+            T s = X[r * ldx + i];
+            for (int k = i + 1; k < n; ++k) s -= X[r * ldx + k] * L[k * ldl + i];
+            X[r * ldx + i] = s * invd[i];
+        }
+    }
+    __syncthreads();
+}
+
+// Adjoint of L = chol(A).  In: L (lower), invd, dL (lower triangle used).  Out: dA (full symmetric) written to
+// `W` ([n][ld]); `dL` is destroyed only if it aliases W (allowed: W may be the same buffer as dL).
+//   P = Phi(L^T dL);  X = L^-T P;  Y = X L^-1;  dA = (Y + Y^T) / 2.
+template <typename T>
+__device__ void cholesky_adjoint(const T* __restrict__ L, int ldl, const T* __restrict__ invd, const T* dL, T* W,
+                                 int ld, int n, T* __restrict__ scratch /* [n][ld] */) {
+    __syncthreads();
+    // scratch = Phi(L^T dL)  (lower, halved diagonal, zero upper)
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        T s = (T)0;
+        if (i >= j) {
+            for (int k = i; k < n; ++k) s += L[k * ldl + i] * dL[k * ld + j];
+            if (i == j) s *= (T)0.5;
+        }
+        scratch[i * ld + j] = s;
+    }
+    __syncthreads();
+    trsm_lowerT_left(L, ldl, invd, scratch, ld, n, n);   // X = L^-T P
+    trsm_lower_right(L, ldl, invd, scratch, ld, n, n);   // Y = X L^-1
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        W[i * ld + j] = (T)0.5 * (scratch[i * ld + j] + scratch[j * ld + i]);
+    }
+    __syncthreads();
+}
+
+// Warp-level sparsemax over T <= 64 values (lane holds elements lane and lane+32).
+// Sort-free: rank by (value desc, index asc);  support_i = k_i z_i > cumsum_i - 1.
+// Returns w0/w1 and the support size (entmax SparsemaxFunction.forward).
+__device__ __forceinline__ void warp_sparsemax(float f0, float f1, int T, float& w0, float& w1, int& ksz) {
+    const int lane = threadIdx.x & 31;
+    const bool v0 = lane < T, v1 = lane + 32 < T;
+    float mx = fmaxf(v0 ? f0 : -INFINITY, v1 ? f1 : -INFINITY);
+    mx = warp_max(mx);
+    const float z0 = f0 - mx, z1 = f1 - mx;
+    int k0 = 0, k1 = 0;
+    float c0 = 0.f, c1 = 0.f;
+    for (int j = 0; j < T; ++j) {
+        const float zj = __shfl_sync(0xffffffffu, (j < 32) ? z0 : z1, j & 31);
+        const bool b0 = (zj > z0) || (zj == z0 && j <= lane);
+        const bool b1 = (zj > z1) || (zj == z1 && j <= lane + 32);
+        if (b0) { ++k0; c0 += zj; }
+        if (b1) { ++k1; c1 += zj; }
+    }
+    const bool s0 = v0 && ((float)k0 * z0 > c0 - 1.f);
+    const bool s1 = v1 && ((float)k1 * z1 > c1 - 1.f);
+    const int cnt = __popc(__ballot_sync(0xffffffffu, s0)) + __popc(__ballot_sync(0xffffffffu, s1));
+    const float ssum = warp_sum((s0 ? z0 : 0.f) + (s1 ? z1 : 0.f));
+    const float tau = (ssum - 1.f) / (float)cnt;
+    w0 = v0 ? fmaxf(z0 - tau, 0.f) : 0.f;
+    w1 = v1 ? fmaxf(z1 - tau, 0.f) : 0.f;
+    ksz = cnt;
+}
+
+}  // namespace gp
+}  // namespace clipgp

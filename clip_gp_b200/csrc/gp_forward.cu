@@ -1,0 +1,239 @@
+// GP template weighter, forward: one CTA per class, everything after the streamed Gram phase lives in
+// shared memory.  Replaces gp_template_weigher.py:166-173,194-219 + gpytorch VariationalStrategy.forward
+// + MultivariateNormal.rsample + entmax.sparsemax + kl_divergence.
+//
+// Roofline: HBM/latency.  Algorithmic bytes per class: Z [n,d] + X [T,d] + lengthscale [d] + Lq [n,n] + m [n]
+// read, w [S,T] + saved L (fp64 n^2), A (nT), R (T^2) written.
+#include "gp_layout.cuh"
+
+namespace clipgp {
+namespace gp {
+
+__global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_args a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int T = (int)a.T, n = (int)a.n, d = (int)a.d, S = (int)a.S;
+    const Dims D = make_dims(T, n, d);
+    const FwdLayout Y = make_fwd_layout(D);
+    const int ldn = D.ldn, ldt = D.ldt;
+    double* Ld = reinterpret_cast<double*>(smem + Y.Ld);
+    double* Ad = reinterpret_cast<double*>(smem + Y.Ad);
+    double* invd = reinterpret_cast<double*>(smem + Y.invd);
+    float* Sig = reinterpret_cast<float*>(smem + Y.Sig);
+    float* R = reinterpret_cast<float*>(smem + Y.R);
+    float* Af = reinterpret_cast<float*>(smem + Y.AfBm);
+    float* Bm = Af + D.f_nt;
+    float* K0 = Af;   // scratch Gram [n][ldn]; dead before Af/Bm are written
+    float* Lq = reinterpret_cast<float*>(smem + Y.Lq);
+    float* mu = reinterpret_cast<float*>(smem + Y.mu);
+    float* mvec = reinterpret_cast<float*>(smem + Y.mvec);
+    float* invls = reinterpret_cast<float*>(smem + Y.invls);
+    float* invdR = reinterpret_cast<float*>(smem + Y.invdR);
+    float* pool = reinterpret_cast<float*>(smem + Y.pool);
+    float* tileA = pool;
+    float* tileB = pool + (size_t)pad4(n) * KCP;
+    float* fbuf = pool;                       // [SCH][ldt]
+    float* ebuf = pool + (size_t)SCH * ldt;   // [T][SCH]
+    __shared__ float red[32];
+
+    const float* Zc = a.Z + (size_t)c * n * d;
+    const float* Xc = a.X + (size_t)c * T * d;
+    const int kt = a.kernel_type;
+
+    // ---- hyper-parameters (gpytorch Positive constraint = softplus)
+    if (kt != CLIPGP_KERNEL_LINEAR)
+        for (int k = tid; k < d; k += blockDim.x) invls[k] = 1.f / softplusf(a.raw_lengthscale[(size_t)c * d + k]);
+    float amp = 1.f;
+    if (kt == CLIPGP_KERNEL_RBF) amp = softplusf(a.raw_outputscale[c]);
+    if (kt == CLIPGP_KERNEL_LINEAR) amp = softplusf(a.raw_variance[c]);
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        Lq[i * ldn + j] = (j <= i) ? a.chol_var[(size_t)c * n * n + idx] : 0.f;   // CholeskyVariationalDistribution.forward mask
+    }
+    for (int i = tid; i < n; i += blockDim.x) mvec[i] = a.var_mean[(size_t)c * n + i];
+
+    // ---- do the test inputs repeat the first T inducing rows? (frozen template rows, gp_template_weigher.py:72-79)
+    int alias = 0;
+    if (a.x_is_z_prefix) {
+        int eq = 1;
+        for (int idx = tid; idx < T * d; idx += blockDim.x) eq &= (__ldg(Xc + idx) == __ldg(Zc + idx));
+        alias = __syncthreads_and(eq);
+    }
+
+    // ---- Gram blocks
+    gram_block<float>(K0, ldn, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB);
+    if (!alias) {
+        gram_block<double>(Ad, ldt, nullptr, 0, Zc, n, Xc, T, d, kt, amp, invls, tileA, tileB);
+        gram_block<float>(Sig, ldt, nullptr, 0, Xc, T, Xc, T, d, kt, amp, invls, tileA, tileB);
+    }
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        Ld[i * ldn + j] = (double)(K0[i * ldn + j] + (i == j ? 1e-4f : 0.f));   // add_jitter in fp32, then .double()
+    }
+    if (alias) {
+        for (int idx = tid; idx < n * T; idx += blockDim.x) {
+            const int i = idx / T, j = idx - i * T;
+            Ad[i * ldt + j] = (double)K0[i * ldn + j];
+        }
+        for (int idx = tid; idx < T * T; idx += blockDim.x) {
+            const int i = idx / T, j = idx - i * T;
+            Sig[i * ldt + j] = K0[i * ldn + j];
+        }
+    }
+    __syncthreads();
+
+    // ---- L = chol64(K_ZZ + 1e-4 I);  A = L^-1 K_ZX
+    const bool failL = block_cholesky<double>(Ld, n, ldn, invd);
+    trsm_lower_left<double>(Ld, ldn, invd, Ad, ldt, n, T);
+    for (int idx = tid; idx < n * T; idx += blockDim.x) {
+        const int i = idx / T, j = idx - i * T;
+        Af[i * ldt + j] = (float)Ad[i * ldt + j];
+    }
+    __syncthreads();
+    // ---- Bm = Lq^T A ;  mu = A^T m + mean_x
+    for (int idx = tid; idx < n * T; idx += blockDim.x) {
+        const int i = idx / T, j = idx - i * T;
+        float s = 0.f;
+        for (int k = i; k < n; ++k) s = fmaf(Lq[k * ldn + i], Af[k * ldt + j], s);
+        Bm[i * ldt + j] = s;
+    }
+    for (int j = tid; j < T; j += blockDim.x) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s = fmaf(Af[i * ldt + j], mvec[i], s);
+        mu[j] = s + (a.mean_x ? a.mean_x[(size_t)c * T + j] : 0.f);
+    }
+    __syncthreads();
+    // ---- Sigma = K_XX + 1e-4 I + Bm^T Bm - A^T A   (lower triangle)
+    for (int idx = tid; idx < T * T; idx += blockDim.x) {
+        const int i = idx / T, j = idx - i * T;
+        if (j <= i) {
+            float s = 0.f;
+            for (int k = 0; k < n; ++k)
+                s += Bm[k * ldt + i] * Bm[k * ldt + j] - Af[k * ldt + i] * Af[k * ldt + j];
+            Sig[i * ldt + j] = (Sig[i * ldt + j] + (i == j ? 1e-4f : 0.f)) + s;
+        }
+    }
+    __syncthreads();
+    // ---- R = chol32(Sigma), psd_safe_cholesky: retry with total diagonal jitter 1e-6, 1e-5, 1e-4
+    int retries = 0;
+    bool failR = true;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        const float jit = attempt == 0 ? 0.f : (attempt == 1 ? 1e-6f : (attempt == 2 ? 1e-5f : 1e-4f));
+        for (int idx = tid; idx < T * T; idx += blockDim.x) {
+            const int i = idx / T, j = idx - i * T;
+            if (j <= i) R[i * ldt + j] = Sig[i * ldt + j] + (i == j ? jit : 0.f);
+        }
+        __syncthreads();
+        failR = block_cholesky<float>(R, T, ldt, invdR);
+        if (!failR) break;
+        ++retries;
+    }
+    if (tid == 0 && a.status) a.status[c] = failL ? -2 : (failR ? -1 : retries);
+
+    // ---- saved tensors for the adjoint
+    if (a.L)
+        for (int idx = tid; idx < n * n; idx += blockDim.x) {
+            const int i = idx / n, j = idx - i * n;
+            a.L[(size_t)c * n * n + idx] = (j <= i) ? Ld[i * ldn + j] : 0.0;
+        }
+    if (a.A)
+        for (int idx = tid; idx < n * T; idx += blockDim.x) {
+            const int i = idx / T, j = idx - i * T;
+            a.A[(size_t)c * n * T + idx] = Af[i * ldt + j];
+        }
+    if (a.R)
+        for (int idx = tid; idx < T * T; idx += blockDim.x) {
+            const int i = idx / T, j = idx - i * T;
+            a.R[(size_t)c * T * T + idx] = (j <= i) ? R[i * ldt + j] : 0.f;
+        }
+
+    // ---- KL(q(u) || N(0, I)) = 1/2 (|Lq|_F^2 + |m|^2 - n - sum log Lq_ii^2)
+    if (a.kl) {
+        float part = 0.f;
+        for (int idx = tid; idx < n * n; idx += blockDim.x) {
+            const int i = idx / n, j = idx - i * n;
+            const float v = Lq[i * ldn + j];
+            part += v * v;
+            if (i == j) part -= logf(v * v);
+        }
+        for (int i = tid; i < n; i += blockDim.x) part += mvec[i] * mvec[i];
+        const float tot = block_sum(part, red);
+        if (tid == 0) a.kl[c] = 0.5f * (tot - (float)n);
+    }
+    __syncthreads();   // pool: tiles are dead, sample buffers take over
+
+    // ---- f_s = mu + R eps_s ;  w_s = sparsemax(f_s)
+    uint64_t seed = 0, step = 0;
+    if (a.eps == nullptr) { seed = a.rng_state[0]; step = a.rng_state[1]; }
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int s0 = 0; s0 < S; s0 += SCH) {
+        const int sc = min(SCH, S - s0);
+        for (int idx = tid; idx < T * sc; idx += blockDim.x) {
+            const int t = idx / sc, ss = idx - t * sc;
+            float e;
+            if (a.eps) e = a.eps[(size_t)c * a.eps_sc + (size_t)t * a.eps_st + (size_t)(s0 + ss) * a.eps_ss];
+            else e = philox_normal(seed, step, ((uint64_t)c * T + t) * (uint64_t)a.S_total + (uint64_t)(a.s_offset + s0 + ss));
+            ebuf[t * SCH + ss] = e;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < sc * T; idx += blockDim.x) {
+            const int ss = idx / T, j = idx - ss * T;
+            float s = 0.f;
+            for (int k = 0; k <= j; ++k) s = fmaf(R[j * ldt + k], ebuf[k * SCH + ss], s);
+            fbuf[ss * ldt + j] = s + mu[j];
+        }
+        __syncthreads();
+        for (int ss = warp; ss < sc; ss += nwarps) {
+            const float f0 = lane < T ? fbuf[ss * ldt + lane] : -INFINITY;
+            const float f1 = lane + 32 < T ? fbuf[ss * ldt + lane + 32] : -INFINITY;
+            float w0, w1; int ksz;
+            warp_sparsemax(f0, f1, T, w0, w1, ksz);
+            float* wout = a.w + ((size_t)(s0 + ss) * a.C + c) * T;
+            if (failL || failR) { w0 = 0.f; w1 = 0.f; }
+            if (lane < T) wout[lane] = w0;
+            if (lane + 32 < T) wout[lane + 32] = w1;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace gp
+}  // namespace clipgp
+
+using namespace clipgp;
+
+static int gp_check_args(const clipgp_gp_args* a, const char* who) {
+    CLIPGP_REQUIRE(a != nullptr, "%s: args is NULL", who);
+    CLIPGP_REQUIRE(a->C >= 0 && a->T >= 1 && a->T <= CLIPGP_GP_MAX_T, "%s: need 1 <= T <= %d (got %lld)", who,
+                   CLIPGP_GP_MAX_T, (long long)a->T);
+    CLIPGP_REQUIRE(a->n >= 1 && a->n <= CLIPGP_GP_MAX_T + 1, "%s: need 1 <= n <= %d (got %lld)", who, CLIPGP_GP_MAX_T + 1,
+                   (long long)a->n);
+    CLIPGP_REQUIRE(a->d >= 1 && a->S >= 1, "%s: need d >= 1 and S >= 1", who);
+    CLIPGP_REQUIRE(!a->x_is_z_prefix || a->n >= a->T, "%s: x_is_z_prefix needs n >= T", who);
+    CLIPGP_REQUIRE(a->kernel_type >= 0 && a->kernel_type <= 2, "%s: Unsupported kernel: %d", who, a->kernel_type);
+    if (a->C == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(a->Z && a->X && a->var_mean && a->chol_var && a->w, "%s: NULL tensor", who);
+    if (a->kernel_type != CLIPGP_KERNEL_LINEAR) CLIPGP_REQUIRE(a->raw_lengthscale, "%s: raw_lengthscale is NULL", who);
+    if (a->kernel_type == CLIPGP_KERNEL_RBF) CLIPGP_REQUIRE(a->raw_outputscale, "%s: raw_outputscale is NULL", who);
+    if (a->kernel_type == CLIPGP_KERNEL_LINEAR) CLIPGP_REQUIRE(a->raw_variance, "%s: raw_variance is NULL", who);
+    CLIPGP_REQUIRE(a->eps || a->rng_state, "%s: need eps or rng_state", who);
+    if (!a->eps) CLIPGP_REQUIRE(a->S_total >= a->s_offset + a->S && a->s_offset >= 0, "%s: bad sample slice", who);
+    return CLIPGP_OK;
+}
+
+extern "C" int64_t clipgp_gp_smem_bytes(int64_t T, int64_t n, int64_t d, int backward) {
+    if (T < 1 || T > CLIPGP_GP_MAX_T || n < 1 || n > CLIPGP_GP_MAX_T + 1 || d < 1) return 0;
+    const gp::Dims D = gp::make_dims((int)T, (int)n, (int)d);
+    return backward ? (int64_t)gp::make_bwd_layout(D).total : (int64_t)gp::make_fwd_layout(D).total;
+}
+
+extern "C" int clipgp_gp_forward(const clipgp_gp_args* a, void* stream) {
+    int rc = gp_check_args(a, "gp_forward");
+    if (rc != CLIPGP_OK) return rc;
+    if (a->C == 0) return CLIPGP_OK;
+    const size_t smem = (size_t)clipgp_gp_smem_bytes(a->T, a->n, a->d, 0);
+    CLIPGP_REQUIRE(smem > 0 && smem <= 227 * 1024, "gp_forward: needs %zu bytes of shared memory (> 227 KB); reduce d", smem);
+    CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gp::gp_forward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a);
+    return check_launch("gp_forward_kernel");
+}

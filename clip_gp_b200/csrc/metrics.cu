@@ -1,0 +1,347 @@
+// Calibration metrics kernels: softmax-max confidence + equal-width histogram (ECE), and the
+// sort-free exact rank partition for AECE.  Replaces /root/reference/utils/metrics.py:9-229.
+//
+// Roofline: HBM.  calib_rows_kernel streams the [N,C] logits once (N*C*4 algorithmic bytes; the second
+// pass over a row for sum-exp hits L1/L2), everything else is O(N).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace clipgp {
+
+static constexpr double kFx = 1099511627776.0;  // 2^40: conf in [2^-16,1] is an exact integer at this scale
+
+__device__ __forceinline__ unsigned long long conf_to_fx(float c) {
+    return (unsigned long long)((double)c * kFx);
+}
+
+__device__ __forceinline__ int find_bin(float cf, const float* b, int n_bins) {
+    // metrics.py:77  in_bin = (conf > b[i]) * (conf <= b[i+1]);  conf == 0 or NaN falls in no bin
+    for (int i = 0; i < n_bins; ++i)
+        if (cf > b[i] && cf <= b[i + 1]) return i;
+    return -1;
+}
+
+struct HistSmem {
+    float b[CLIPGP_MAX_BINS + 1];
+    unsigned int cnt[CLIPGP_MAX_BINS];
+    unsigned int cor[CLIPGP_MAX_BINS];
+    unsigned long long fx[CLIPGP_MAX_BINS];
+    unsigned int top1;
+};
+
+__device__ __forceinline__ void hist_init(HistSmem& h, const float* boundaries, int n_bins) {
+    for (int i = threadIdx.x; i < CLIPGP_MAX_BINS; i += blockDim.x) {
+        h.cnt[i] = 0; h.cor[i] = 0; h.fx[i] = 0ull;
+    }
+    if (boundaries != nullptr)
+        for (int i = threadIdx.x; i <= n_bins; i += blockDim.x) h.b[i] = boundaries[i];
+    if (threadIdx.x == 0) h.top1 = 0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void hist_flush(HistSmem& h, int n_bins, int64_t* bin_count,
+                                           unsigned long long* bin_conf_fx, int64_t* bin_correct, int64_t* top1) {
+    __syncthreads();
+    if (bin_count != nullptr) {
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) {
+            if (h.cnt[i]) {
+                atomicAdd((unsigned long long*)&bin_count[i], (unsigned long long)h.cnt[i]);
+                atomicAdd(&bin_conf_fx[i], h.fx[i]);
+                atomicAdd((unsigned long long*)&bin_correct[i], (unsigned long long)h.cor[i]);
+            }
+        }
+    }
+    if (top1 != nullptr && threadIdx.x == 0 && h.top1) atomicAdd((unsigned long long*)top1, (unsigned long long)h.top1);
+}
+
+// One warp per logits row.  VEC: rows are 16-byte aligned and C % 4 == 0 -> float4 loads.
+template <bool VEC>
+__global__ void __launch_bounds__(256) calib_rows_kernel(const float* __restrict__ logits, int64_t ld,
+                                                         const int64_t* __restrict__ labels, int64_t N, int64_t C,
+                                                         float* __restrict__ conf, int32_t* __restrict__ pred,
+                                                         uint8_t* __restrict__ correct,
+                                                         const float* __restrict__ boundaries, int n_bins,
+                                                         int64_t* bin_count, unsigned long long* bin_conf_fx,
+                                                         int64_t* bin_correct, int64_t* top1) {
+    __shared__ HistSmem h;
+    hist_init(h, boundaries, n_bins);
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_per_block = blockDim.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * warps_per_block;
+    for (int64_t row = gw; row < N; row += nw) {
+        const float* x = logits + row * ld;
+        float m = -FLT_MAX;
+        int am = 0x7fffffff;
+        if (VEC) {
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            const int C4 = (int)(C >> 2);
+            for (int j = lane; j < C4; j += 32) {
+                float4 v = __ldg(x4 + j);
+                const int base = j << 2;
+                if (v.x > m) { m = v.x; am = base; }
+                if (v.y > m) { m = v.y; am = base + 1; }
+                if (v.z > m) { m = v.z; am = base + 2; }
+                if (v.w > m) { m = v.w; am = base + 3; }
+            }
+        } else {
+            for (int j = lane; j < C; j += 32) {
+                float v = __ldg(x + j);
+                if (v > m) { m = v; am = j; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float om = __shfl_xor_sync(0xffffffffu, m, o);
+            int oa = __shfl_xor_sync(0xffffffffu, am, o);
+            if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+        }
+        float s = 0.f;
+        if (VEC) {
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            const int C4 = (int)(C >> 2);
+            for (int j = lane; j < C4; j += 32) {
+                float4 v = __ldg(x4 + j);
+                s += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+            }
+        } else {
+            for (int j = lane; j < C; j += 32) s += expf(__ldg(x + j) - m);
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            const float cf = 1.0f / s;   // == max_j softmax_j (exp(0)/sum)
+            const int ok = (labels != nullptr) ? ((int64_t)am == labels[row]) : 0;
+            if (conf) conf[row] = cf;
+            if (pred) pred[row] = am;
+            if (correct) correct[row] = (uint8_t)ok;
+            if (ok) atomicAdd(&h.top1, 1u);
+            if (bin_count != nullptr) {
+                const int bi = find_bin(cf, h.b, n_bins);
+                if (bi >= 0) {
+                    atomicAdd(&h.cnt[bi], 1u);
+                    atomicAdd(&h.cor[bi], (unsigned int)ok);
+                    atomicAdd(&h.fx[bi], conf_to_fx(cf));
+                }
+            }
+        }
+    }
+    hist_flush(h, n_bins, bin_count, bin_conf_fx, bin_correct, top1);
+}
+
+__global__ void __launch_bounds__(256) ece_hist_kernel(const float* __restrict__ conf, const uint8_t* __restrict__ correct,
+                                                       int64_t N, const float* __restrict__ boundaries, int n_bins,
+                                                       int64_t* bin_count, unsigned long long* bin_conf_fx,
+                                                       int64_t* bin_correct) {
+    __shared__ HistSmem h;
+    hist_init(h, boundaries, n_bins);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const float cf = conf[i];
+        const int bi = find_bin(cf, h.b, n_bins);
+        if (bi >= 0) {
+            atomicAdd(&h.cnt[bi], 1u);
+            atomicAdd(&h.cor[bi], (unsigned int)correct[i]);
+            atomicAdd(&h.fx[bi], conf_to_fx(cf));
+        }
+    }
+    hist_flush(h, n_bins, bin_count, bin_conf_fx, bin_correct, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AECE: exact prefix sums at rank edges by 5-level (8 bits each) radix select over key40 = conf_bits<<8|correct.
+// Elements with equal key have equal (conf, correct), so a rank cut inside a run of equal keys is exact.
+// ---------------------------------------------------------------------------------------------------
+static constexpr int kQ = 8;  // edges resolved per sweep
+
+__global__ void __launch_bounds__(1024) aece_select_kernel(const float* __restrict__ conf,
+                                                           const uint8_t* __restrict__ correct, int64_t N,
+                                                           const int64_t* __restrict__ edges, int n_bins,
+                                                           unsigned long long* out_conf_fx, int64_t* out_correct,
+                                                           int64_t* out_count) {
+    __shared__ unsigned int h_cnt[kQ][256];
+    __shared__ unsigned int h_cor[kQ][256];
+    __shared__ unsigned long long h_fx[kQ][256];
+    __shared__ unsigned long long q_prefix[kQ], q_fx_less[kQ], slot_prefix[kQ];
+    __shared__ long long q_rank[kQ], q_cnt_less[kQ], q_cor_less[kQ];
+    __shared__ int q_slot[kQ], q_edge[kQ];
+    __shared__ int n_slots, nq, scan_pos;
+    __shared__ unsigned long long F_fx[CLIPGP_MAX_BINS + 1];
+    __shared__ long long F_cor[CLIPGP_MAX_BINS + 1];
+    __shared__ long long e_clamped[CLIPGP_MAX_BINS + 1];
+    __shared__ unsigned long long tot_fx;
+    __shared__ unsigned long long tot_cor;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) { tot_fx = 0ull; tot_cor = 0ull; }
+    __syncthreads();
+    {   // totals (prefix sum at rank N)
+        unsigned long long fx = 0ull, cor = 0ull;
+        for (int64_t i = tid; i < N; i += blockDim.x) { fx += conf_to_fx(conf[i]); cor += correct[i]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            cor += __shfl_xor_sync(0xffffffffu, cor, o);
+        }
+        if ((tid & 31) == 0) { atomicAdd(&tot_fx, fx); atomicAdd(&tot_cor, cor); }
+    }
+    __syncthreads();
+    if (tid <= n_bins) {
+        long long e = edges[tid];
+        e = e < 0 ? 0 : (e > N ? N : e);
+        e_clamped[tid] = e;
+        if (e <= 0) { F_fx[tid] = 0ull; F_cor[tid] = 0; }
+        else if (e >= N) { F_fx[tid] = tot_fx; F_cor[tid] = (long long)tot_cor; }
+    }
+    __syncthreads();
+
+    int next_edge = 0;  // uniform across the block (same shared inputs)
+    while (true) {
+        // gather up to kQ interior edges that still need a select
+        if (tid == 0) {
+            int c = 0, k = next_edge;
+            for (; k <= n_bins && c < kQ; ++k) {
+                long long e = e_clamped[k];
+                if (e > 0 && e < N) {
+                    q_edge[c] = k; q_rank[c] = e; q_prefix[c] = 0ull; q_cnt_less[c] = 0; q_cor_less[c] = 0;
+                    q_fx_less[c] = 0ull; q_slot[c] = 0; ++c;
+                }
+            }
+            nq = c; n_slots = (c > 0) ? 1 : 0; slot_prefix[0] = 0ull;
+            scan_pos = k;
+        }
+        __syncthreads();
+        if (nq == 0) break;
+        next_edge = scan_pos;
+
+        for (int level = 0; level < 5; ++level) {
+            const int shift = 32 - 8 * level;
+            const int ns = n_slots;
+            for (int i = tid; i < ns * 256; i += blockDim.x) {
+                (&h_cnt[0][0])[i] = 0u; (&h_cor[0][0])[i] = 0u; (&h_fx[0][0])[i] = 0ull;
+            }
+            __syncthreads();
+            for (int64_t i = tid; i < N; i += blockDim.x) {
+                const float cf = conf[i];
+                const unsigned int cr = correct[i];
+                const unsigned long long key = ((unsigned long long)__float_as_uint(cf) << 8) | cr;
+                const unsigned long long hi = (level == 0) ? 0ull : (key >> (shift + 8));
+                const int digit = (int)((key >> shift) & 255ull);
+                for (int u = 0; u < ns; ++u) {
+                    if (hi == slot_prefix[u]) {
+                        atomicAdd(&h_cnt[u][digit], 1u);
+                        atomicAdd(&h_cor[u][digit], cr);
+                        atomicAdd(&h_fx[u][digit], conf_to_fx(cf));
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < nq) {
+                const int u = q_slot[tid];
+                const long long r = q_rank[tid];
+                long long cum = 0, cumcor = 0;
+                unsigned long long cumfx = 0ull;
+                int sel = 255;
+                for (int b = 0; b < 256; ++b) {
+                    const long long c = h_cnt[u][b];
+                    if (cum + c > r) { sel = b; break; }
+                    cum += c; cumcor += h_cor[u][b]; cumfx += h_fx[u][b];
+                }
+                q_cnt_less[tid] += cum; q_cor_less[tid] += cumcor; q_fx_less[tid] += cumfx;
+                q_rank[tid] = r - cum;
+                q_prefix[tid] = (q_prefix[tid] << 8) | (unsigned long long)sel;
+            }
+            __syncthreads();
+            if (tid == 0) {   // dedupe prefixes -> histogram slots for the next level
+                int ns2 = 0;
+                for (int q = 0; q < nq; ++q) {
+                    int found = -1;
+                    for (int u = 0; u < ns2; ++u) if (slot_prefix[u] == q_prefix[q]) { found = u; break; }
+                    if (found < 0) { slot_prefix[ns2] = q_prefix[q]; found = ns2++; }
+                    q_slot[q] = found;
+                }
+                n_slots = ns2;
+            }
+            __syncthreads();
+        }
+        if (tid < nq) {
+            const unsigned long long v = q_prefix[tid];
+            const float vconf = __uint_as_float((unsigned int)(v >> 8));
+            const long long rem = q_rank[tid];   // copies of v inside the prefix
+            const int k = q_edge[tid];
+            F_fx[k] = q_fx_less[tid] + (unsigned long long)rem * conf_to_fx(vconf);
+            F_cor[k] = q_cor_less[tid] + rem * (long long)(v & 255ull);
+        }
+        __syncthreads();
+    }
+    if (tid < n_bins) {
+        const long long lo = e_clamped[tid], hi = e_clamped[tid + 1];
+        if (hi > lo) {
+            out_conf_fx[tid] = F_fx[tid + 1] - F_fx[tid];
+            out_correct[tid] = F_cor[tid + 1] - F_cor[tid];
+            out_count[tid] = hi - lo;
+        } else {
+            out_conf_fx[tid] = 0ull; out_correct[tid] = 0; out_count[tid] = 0;
+        }
+    }
+}
+
+}  // namespace clipgp
+
+using namespace clipgp;
+
+extern "C" int clipgp_calibration_from_logits(const float* logits, int64_t ld_logits, const int64_t* labels, int64_t N,
+                                              int64_t C, float* conf, int32_t* pred, uint8_t* correct,
+                                              const float* boundaries, int n_bins, int64_t* bin_count,
+                                              unsigned long long* bin_conf_fx, int64_t* bin_correct, int64_t* top1,
+                                              void* stream) {
+    CLIPGP_REQUIRE(N >= 0 && C >= 1, "calibration_from_logits: bad shape N=%lld C=%lld", (long long)N, (long long)C);
+    CLIPGP_REQUIRE(C < (1ll << 31), "calibration_from_logits: C too large");
+    if (N == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(logits != nullptr, "calibration_from_logits: logits is NULL");
+    CLIPGP_REQUIRE(ld_logits >= C, "calibration_from_logits: ld_logits < C");
+    const bool want_hist = bin_count != nullptr;
+    if (want_hist) {
+        CLIPGP_REQUIRE(boundaries && bin_conf_fx && bin_correct, "calibration_from_logits: histogram outputs incomplete");
+        CLIPGP_REQUIRE(n_bins >= 1 && n_bins <= CLIPGP_MAX_BINS, "calibration_from_logits: n_bins must be in [1,%d]", CLIPGP_MAX_BINS);
+    }
+    CLIPGP_REQUIRE(labels != nullptr || (correct == nullptr && top1 == nullptr && !want_hist),
+                   "calibration_from_logits: labels is NULL");
+    const int threads = 256;
+    const int64_t rows_per_block = threads / 32;
+    int64_t blocks = (N + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    const bool vec = (C % 4 == 0) && (ld_logits % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15u) == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec)
+        calib_rows_kernel<true><<<(unsigned)blocks, threads, 0, st>>>(logits, ld_logits, labels, N, C, conf, pred, correct,
+                                                                     boundaries, n_bins, bin_count, bin_conf_fx, bin_correct, top1);
+    else
+        calib_rows_kernel<false><<<(unsigned)blocks, threads, 0, st>>>(logits, ld_logits, labels, N, C, conf, pred, correct,
+                                                                      boundaries, n_bins, bin_count, bin_conf_fx, bin_correct, top1);
+    return check_launch("calib_rows_kernel");
+}
+
+extern "C" int clipgp_ece_hist(const float* conf, const uint8_t* correct, int64_t N, const float* boundaries, int n_bins,
+                               int64_t* bin_count, unsigned long long* bin_conf_fx, int64_t* bin_correct, void* stream) {
+    CLIPGP_REQUIRE(N >= 0, "ece_hist: N < 0");
+    CLIPGP_REQUIRE(n_bins >= 1 && n_bins <= CLIPGP_MAX_BINS, "ece_hist: n_bins must be in [1,%d]", CLIPGP_MAX_BINS);
+    if (N == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(conf && correct && boundaries && bin_count && bin_conf_fx && bin_correct, "ece_hist: NULL pointer");
+    int64_t blocks = (N + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    ece_hist_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(conf, correct, N, boundaries, n_bins, bin_count,
+                                                                       bin_conf_fx, bin_correct);
+    return check_launch("ece_hist_kernel");
+}
+
+extern "C" int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64_t N, const int64_t* edges, int n_bins,
+                                unsigned long long* out_conf_fx, int64_t* out_correct, int64_t* out_count, void* stream) {
+    CLIPGP_REQUIRE(N >= 0, "aece_bins: N < 0");
+    CLIPGP_REQUIRE(n_bins >= 1 && n_bins < CLIPGP_MAX_BINS, "aece_bins: n_bins must be in [1,%d)", CLIPGP_MAX_BINS);
+    CLIPGP_REQUIRE(edges && out_conf_fx && out_correct && out_count, "aece_bins: NULL pointer");
+    CLIPGP_REQUIRE(N == 0 || (conf && correct), "aece_bins: NULL input");
+    aece_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(conf, correct, N, edges, n_bins, out_conf_fx, out_correct, out_count);
+    return check_launch("aece_select_kernel");
+}

@@ -1,0 +1,174 @@
+"""``torch.autograd.Function`` wrappers over the clipgp C ABI (the differentiable drop-in surface).
+
+Everything here launches hand-written sm_100a kernels from libclipgp.so on the caller's current CUDA
+stream; torch only owns the memory.  Gradients are the hand-derived adjoints (gp_backward.cu,
+proto.cu), not autograd traces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GpArgs, GpBwdArgs, KERNEL_IDS
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class GPWeightsFunction(torch.autograd.Function):
+    """(Z, X, raw_ls, raw_os, raw_var, m, chol, mean_x, eps) -> (w [S,C,T], kl [C]).
+
+    Replaces gp_template_weigher.py:213-217 (``self(gp_input)``, ``rsample``, ``sparsemax``) and
+    ``variational_strategy.kl_divergence()`` (adapter.py:463).  eps is the explicit base noise
+    ``[C,Nx,S]`` with Nx >= T (only rows < T are read; a strided view is fine), or None for the
+    on-device Philox stream keyed by ``rng_state = [seed, step]`` (int64 tensor on the device).
+    """
+
+    @staticmethod
+    def forward(ctx, Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, kernel_type: str, S: int,
+                rng_state, s_offset: int, S_total: int, alias_check: bool):
+        dev = _lib.require_cuda(Z, X, var_mean, chol_var)
+        lib = _lib.load()
+        Z, X, var_mean, chol_var = _c(Z), _c(X), _c(var_mean), _c(chol_var)
+        raw_ls, raw_os, raw_var, mean_x = _c(raw_ls), _c(raw_os), _c(raw_var), _c(mean_x)
+        Cn, n, d = Z.shape
+        T = X.shape[1]
+        if X.shape[0] != Cn or X.shape[2] != d:
+            raise ValueError(f"X {tuple(X.shape)} does not match Z {tuple(Z.shape)}")
+        if eps is not None:
+            if eps.dtype != torch.float32:
+                eps = eps.float()
+            if eps.shape[0] != Cn or eps.shape[1] < T or eps.shape[2] != S:
+                raise ValueError(f"eps must be [C, >=T, S]; got {tuple(eps.shape)}")
+        elif rng_state is None:
+            raise ValueError("need eps or rng_state")
+        w = torch.empty(S, Cn, T, dtype=torch.float32, device=dev)
+        kl = torch.empty(Cn, dtype=torch.float32, device=dev)
+        Lf = torch.empty(Cn, n, n, dtype=torch.float64, device=dev)
+        Af = torch.empty(Cn, n, T, dtype=torch.float32, device=dev)
+        Rf = torch.empty(Cn, T, T, dtype=torch.float32, device=dev)
+        status = torch.empty(Cn, dtype=torch.int32, device=dev)
+        a = GpArgs()
+        a.kernel_type = KERNEL_IDS[kernel_type]
+        a.x_is_z_prefix = 1 if (alias_check and n >= T) else 0
+        a.C, a.T, a.n, a.d, a.S = Cn, T, n, d, S
+        a.Z, a.X = Z.data_ptr(), X.data_ptr()
+        a.raw_lengthscale, a.raw_outputscale, a.raw_variance = _lib.ptr(raw_ls), _lib.ptr(raw_os), _lib.ptr(raw_var)
+        a.var_mean, a.chol_var, a.mean_x = var_mean.data_ptr(), chol_var.data_ptr(), _lib.ptr(mean_x)
+        if eps is not None:
+            a.eps = eps.data_ptr()
+            a.eps_sc, a.eps_st, a.eps_ss = eps.stride(0), eps.stride(1), eps.stride(2)
+            a.rng_state = None
+        else:
+            a.eps = None
+            a.rng_state = rng_state.data_ptr()
+        a.s_offset, a.S_total = int(s_offset), int(S_total if S_total else S)
+        a.w, a.kl, a.L, a.A, a.R, a.status = (w.data_ptr(), kl.data_ptr(), Lf.data_ptr(), Af.data_ptr(), Rf.data_ptr(),
+                                              status.data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(lib.clipgp_gp_forward(C.byref(a), _lib.stream_ptr(dev)), "clipgp_gp_forward")
+        ctx.kernel_type = kernel_type
+        ctx.args = a
+        ctx.keep = (Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, rng_state, w, Lf, Af, Rf)
+        ctx.status = status
+        ctx.mark_non_differentiable(status)
+        return w, kl, status
+
+    @staticmethod
+    def backward(ctx, dw, dkl, _dstatus):
+        a = ctx.args
+        (Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, rng_state, w, Lf, Af, Rf) = ctx.keep
+        dev = Z.device
+        lib = _lib.load()
+        Cn, n, d = Z.shape
+        T = X.shape[1]
+        dw = torch.zeros_like(w) if dw is None else _c(dw)
+        dkl = None if dkl is None else _c(dkl)
+        dZ = torch.zeros_like(Z)                      # rows < T stay zero (reference masks them, :72-79)
+        dZ_last = torch.empty(Cn, d, dtype=torch.float32, device=dev)
+        dls = torch.empty_like(raw_ls) if raw_ls is not None else None
+        dos = torch.empty_like(raw_os) if raw_os is not None else None
+        dvar = torch.empty_like(raw_var) if raw_var is not None else None
+        dm = torch.empty_like(var_mean)
+        dchol = torch.empty_like(chol_var)
+        dmean = torch.empty_like(mean_x) if mean_x is not None else None
+        b = GpBwdArgs()
+        b.dw = dw.data_ptr()
+        b.dkl = _lib.ptr(dkl)
+        b.dkl_scalar = 0.0
+        b.dZ_last = dZ_last.data_ptr()
+        b.draw_lengthscale, b.draw_outputscale, b.draw_variance = _lib.ptr(dls), _lib.ptr(dos), _lib.ptr(dvar)
+        b.dvar_mean, b.dchol_var, b.dmean_x = dm.data_ptr(), dchol.data_ptr(), _lib.ptr(dmean)
+        with torch.cuda.device(dev):
+            _lib.check(lib.clipgp_gp_backward(C.byref(a), C.byref(b), _lib.stream_ptr(dev)), "clipgp_gp_backward")
+        dZ[:, n - 1, :] = dZ_last
+        return (dZ, None, dls, dos, dvar, dm, dchol, dmean, None, None, None, None, None, None, None)
+
+
+def gp_weights(Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, kernel_type: str, S: int,
+               rng_state=None, s_offset: int = 0, S_total: int = 0, alias_check: bool = True):
+    return GPWeightsFunction.apply(Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, kernel_type, int(S),
+                                   rng_state, s_offset, S_total, alias_check)
+
+
+class PrototypesFunction(torch.autograd.Function):
+    """w [S,C,T], E [C,T,D] -> un-normalised prototypes [S,C,D] (gp_template_weigher.py:221)."""
+
+    @staticmethod
+    def forward(ctx, w, E):
+        dev = _lib.require_cuda(w, E)
+        lib = _lib.load()
+        w, E = _c(w), _c(E)
+        S, Cn, T = w.shape
+        D = E.shape[2]
+        P = torch.empty(S, Cn, D, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.clipgp_proto_forward(w.data_ptr(), E.data_ptr(), S, Cn, T, D, None, 0.0, P.data_ptr(), None, None,
+                                                None, None, None, 0, _lib.stream_ptr(dev)), "clipgp_proto_forward")
+        ctx.save_for_backward(E)
+        ctx.shape = (S, Cn, T, D)
+        return P
+
+    @staticmethod
+    def backward(ctx, dP):
+        (E,) = ctx.saved_tensors
+        S, Cn, T, D = ctx.shape
+        lib = _lib.load()
+        dev = E.device
+        dP = _c(dP)
+        dw = torch.empty(S, Cn, T, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.clipgp_proto_backward(dP.data_ptr(), None, None, E.data_ptr(), S, Cn, T, D, dw.data_ptr(),
+                                                 _lib.stream_ptr(dev)), "clipgp_proto_backward")
+        return dw, None
+
+
+def prototypes(w, E):
+    return PrototypesFunction.apply(w, E)
+
+
+def prototypes_reduced(w, E, residual=None, alpha: float = 0.0, want_hat=False, want_mean_hat=False, want_mean_raw=False):
+    """Inference-side prototype products (no autograd): unit rows, the collapsed logit-mean prototype
+    ``(1/S) sum_s p_hat_s`` and the prototype-init ``normalize(mean_s P_s)``."""
+    dev = _lib.require_cuda(w, E)
+    lib = _lib.load()
+    w, E = _c(w.detach()), _c(E.detach())
+    residual = _c(residual.detach()) if residual is not None else None
+    S, Cn, T = w.shape
+    D = E.shape[2]
+    P_hat = torch.empty(S, Cn, D, dtype=torch.float32, device=dev) if want_hat else None
+    mh = torch.empty(Cn, D, dtype=torch.float32, device=dev) if want_mean_hat else None
+    mr = torch.empty(Cn, D, dtype=torch.float32, device=dev) if want_mean_raw else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.clipgp_proto_forward(w.data_ptr(), E.data_ptr(), S, Cn, T, D, _lib.ptr(residual), float(alpha), None,
+                                            _lib.ptr(P_hat), None, None, _lib.ptr(mh), _lib.ptr(mr), 1,
+                                            _lib.stream_ptr(dev)), "clipgp_proto_forward")
+    return P_hat, mh, mr

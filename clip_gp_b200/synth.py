@@ -1,0 +1,90 @@
+"""Synthetic cached-feature workloads of the shapes BASELINE.json names.
+
+No CLIP weights or datasets are available offline, so the text bank and the image features are
+drawn from a class-centre model that mimics frozen-CLIP geometry: templates of one class are
+close to each other, all rows are unit-norm (reference: trainers/tip_adapter.py:101,
+trainers/adapter.py:240).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclass(frozen=True)
+class WorkloadShape:
+    name: str
+    C: int          # classes
+    T: int          # templates per class
+    D: int          # CLIP embedding dim
+    d: int          # PCA dim fed to the GP kernel
+    S: int          # MC samples
+    shots: int
+    B: int          # train minibatch
+    N_test: int
+    kernel: str
+
+
+CONFIGS: Dict[str, WorkloadShape] = {
+    # BASELINE.json configs[0..4]
+    "cfg1": WorkloadShape("cfg1", C=100, T=8, D=1024, d=256, S=4, shots=4, B=128, N_test=2000, kernel="rbf"),
+    "cfg2": WorkloadShape("cfg2", C=1000, T=32, D=512, d=256, S=10, shots=16, B=128, N_test=50000, kernel="rbf"),
+    "cfg3": WorkloadShape("cfg3", C=1000, T=32, D=512, d=256, S=10, shots=16, B=128, N_test=50000, kernel="rbf"),
+    "cfg4": WorkloadShape("cfg4", C=1000, T=32, D=1024, d=256, S=10, shots=16, B=128, N_test=50000, kernel="linear"),
+    "cfg5": WorkloadShape("cfg5", C=397, T=64, D=512, d=256, S=100, shots=16, B=128, N_test=19850, kernel="matern"),
+    # small shapes for parity tests
+    "tiny": WorkloadShape("tiny", C=12, T=5, D=64, d=16, S=3, shots=4, B=16, N_test=257, kernel="rbf"),
+    "small": WorkloadShape("small", C=37, T=8, D=128, d=32, S=4, shots=4, B=48, N_test=1000, kernel="rbf"),
+}
+
+
+def make_text_bank(C: int, T: int, D: int, seed: int, spread: float = 0.3):
+    """Class centres mu_c ~ N(0,I); E[c,t] = normalize(mu_c + spread*N(0,I)).  Returns (E [C,T,D], mu [C,D])."""
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.randn(C, D, generator=g)
+    E = F.normalize(mu.unsqueeze(1) + spread * torch.randn(C, T, D, generator=g), dim=-1)
+    return E, mu
+
+
+def make_features(mu: torch.Tensor, labels: torch.Tensor, seed: int, noise: float = 1.0):
+    """f_i = normalize(mu_{y_i} + noise*N(0,I))."""
+    g = torch.Generator().manual_seed(seed)
+    return F.normalize(mu[labels] + noise * torch.randn(labels.shape[0], mu.shape[1], generator=g), dim=-1)
+
+
+def make_train_set(mu: torch.Tensor, shots: int, seed: int):
+    C = mu.shape[0]
+    labels = torch.arange(C).repeat_interleave(shots)
+    g = torch.Generator().manual_seed(seed + 7)
+    perm = torch.randperm(labels.numel(), generator=g)
+    labels = labels[perm].contiguous()
+    return make_features(mu, labels, seed), labels
+
+
+def make_test_set(mu: torch.Tensor, N: int, seed: int):
+    g = torch.Generator().manual_seed(seed + 13)
+    labels = torch.randint(0, mu.shape[0], (N,), generator=g)
+    return make_features(mu, labels, seed + 1), labels
+
+
+def make_workload(name: str, seed_base: int = 1234, n_test: int | None = None):
+    """All host tensors for one named config (fp32 / int64, CPU)."""
+    shp = CONFIGS[name]
+    cfg_id = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}.get(name, 9)
+    seed = seed_base + cfg_id
+    E, mu = make_text_bank(shp.C, shp.T, shp.D, seed)
+    f_tr, y_tr = make_train_set(mu, shp.shots, seed + 100)
+    f_te, y_te = make_test_set(mu, n_test if n_test is not None else shp.N_test, seed + 200)
+    return {"shape": shp, "E": E, "mu": mu, "f_train": f_tr, "y_train": y_tr, "f_test": f_te, "y_test": y_te,
+            "seed": seed}
+
+
+def trained_like_q(C: int, n: int, seed: int):
+    """A non-trivial variational state: m ~ 0.5 N(0,1), L_q = I + 0.1 tril(N(0,1))."""
+    g = torch.Generator().manual_seed(seed + 31)
+    m = 0.5 * torch.randn(C, n, generator=g)
+    Lq = torch.eye(n).repeat(C, 1, 1) + 0.1 * torch.randn(C, n, n, generator=g).tril()
+    return m, Lq

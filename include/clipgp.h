@@ -1,0 +1,153 @@
+/*
+ * clipgp.h — C ABI of the B200-native CLIP-GP few-shot adapter hot path (libclipgp.so).
+ *
+ * The reference (paulmerceur/CLIP-GP) is pure Python/PyTorch and has no FFI today; each entry point
+ * below replaces the torch / gpytorch / entmax call sequence of the cited reference lines
+ * (paths relative to the reference root).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; sizes are int64_t;
+ *   - tensors are dense row-major fp32 unless stated; labels are int64;
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current torch stream);
+ *   - the return value is 0 on success, non-zero on failure; clipgp_last_error() then returns a
+ *     thread-local message.  There is NO CPU fallback: without a CUDA device every compute entry fails;
+ *   - no entry point allocates device memory or synchronises the stream unless documented.
+ */
+#ifndef CLIPGP_H_
+#define CLIPGP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLIPGP_OK 0
+#define CLIPGP_ERR_INVALID 1 /* bad argument (shape, null pointer, unsupported size) */
+#define CLIPGP_ERR_CUDA 2    /* CUDA runtime / launch failure */
+
+#define CLIPGP_KERNEL_RBF 0      /* ScaleKernel(RBFKernel(ARD))      gp_template_weigher.py:102-114 */
+#define CLIPGP_KERNEL_MATERN12 1 /* MaternKernel(nu=0.5, ARD)        gp_template_weigher.py:115-117 */
+#define CLIPGP_KERNEL_LINEAR 2   /* LinearKernel                     gp_template_weigher.py:118-120 */
+
+#define CLIPGP_MAX_BINS 64
+#define CLIPGP_GP_MAX_T 64 /* templates per class; inducing points n = T+1 <= 65 */
+
+/* ------------------------------------------------------------------------------------------------ */
+const char* clipgp_last_error(void);
+int clipgp_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches counter). */
+int64_t clipgp_launch_count(void);
+
+/* ================================================================================================
+ * Calibration metrics — utils/metrics.py
+ * ================================================================================================ */
+
+/* metrics.py:71-73 (softmax -> max -> eq) fused with the 10-bin equal-width histogram of :75-82 and
+ * the top-1 count of compute_accuracy (:9-36), one pass over the logits.
+ *   logits [N,C] (row stride ld_logits elements), labels [N].
+ *   conf [N] = max softmax prob, pred [N] (int32) = argmax (lowest index on ties), correct [N] (uint8);
+ *     any of the three may be NULL.
+ *   boundaries [n_bins+1] fp32 (torch.linspace(0,1,n_bins+1)); membership b[i] < conf <= b[i+1].
+ *   bin_count [n_bins] int64, bin_conf_fx [n_bins] uint64 (sum of conf in 2^-40 fixed point: exact and
+ *     order independent), bin_correct [n_bins] int64, top1 [1] int64 — all ACCUMULATED into (+=), so a
+ *     caller can stream chunks / shards; zero them first.  The hist pointers may be NULL (conf only). */
+int clipgp_calibration_from_logits(const float* logits, int64_t ld_logits, const int64_t* labels, int64_t N,
+                                   int64_t C, float* conf, int32_t* pred, uint8_t* correct,
+                                   const float* boundaries, int n_bins, int64_t* bin_count,
+                                   unsigned long long* bin_conf_fx, int64_t* bin_correct, int64_t* top1,
+                                   void* stream);
+
+/* Equal-width histogram of precomputed (conf, correct) — same accumulators as above. */
+int clipgp_ece_hist(const float* conf, const uint8_t* correct, int64_t N, const float* boundaries, int n_bins,
+                    int64_t* bin_count, unsigned long long* bin_conf_fx, int64_t* bin_correct, void* stream);
+
+/* metrics.py:107-133 (sort by confidence, contiguous equal-count rank bins) without materialising the
+ * sort: an exact 5-level radix select of the n_bins-1 interior rank edges over the 40-bit key
+ * (conf_bits<<8 | correct), then prefix sums at those ranks.
+ *   edges [n_bins+1] int64 DEVICE (torch.linspace(0,N,n_bins+1).round().long(), edges[0]=0, edges[-1]=N)
+ *   out_conf_fx [n_bins] uint64 (2^-40 fixed point), out_correct [n_bins] int64, out_count [n_bins] int64
+ *   — overwritten.  Single CTA; intended for N up to a few million. */
+int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64_t N, const int64_t* edges, int n_bins,
+                     unsigned long long* out_conf_fx, int64_t* out_correct, int64_t* out_count, void* stream);
+
+/* ================================================================================================
+ * GP template weighter — trainers/gp_template_weigher.py:166-222 + gpytorch VariationalStrategy
+ * (whitened), MultivariateNormal.rsample, entmax.sparsemax, kl_divergence.
+ * One CTA per class.  Per class: K_ZZ(+1e-4 I), K_ZX, K_XX -> L = chol64(K_ZZ) -> A = L^-1 K_ZX ->
+ * mu = A^T m + mean_x, Sigma = K_XX + 1e-4 I + A^T (Lq Lq^T - I) A -> R = chol32(Sigma) (psd_safe jitter
+ * retries 1e-6,1e-5,1e-4) -> f_s = mu + R eps_s -> w_s = sparsemax(f_s);  KL(q(u)||N(0,I)).
+ * ================================================================================================ */
+typedef struct clipgp_gp_args {
+    int32_t kernel_type;          /* CLIPGP_KERNEL_* */
+    int32_t x_is_z_prefix;        /* 1: caller guarantees X[c] == Z[c,:T] bit-for-bit -> only K_ZZ is evaluated */
+    int64_t C, T, n, d, S;        /* classes, templates, inducing points (T+1), kernel input dim, MC samples */
+    const float* Z;               /* [C,n,d] variational_strategy.inducing_points */
+    const float* X;               /* [C,T,d] _templates_red (test inputs) */
+    const float* raw_lengthscale; /* [C,d]  (rbf, matern) else NULL; lengthscale = softplus(raw) */
+    const float* raw_outputscale; /* [C]    (rbf) else NULL */
+    const float* raw_variance;    /* [C]    (linear) else NULL */
+    const float* var_mean;        /* [C,n]   variational_mean */
+    const float* chol_var;        /* [C,n,n] chol_variational_covar (raw; lower triangle is used) */
+    const float* mean_x;          /* [C,T] prior mean at the test inputs, or NULL for 0 */
+    const float* eps;             /* explicit base noise, element (c,t,s) at eps[c*eps_sc + t*eps_st + s*eps_ss]; */
+    int64_t eps_sc, eps_st, eps_ss; /*   NULL -> counter RNG: Philox4x32-10(seed, step)[(c*T+t)*S_total + s_offset+s] */
+    const uint64_t* rng_state;    /* device [2] = {seed, step}; used when eps == NULL */
+    int64_t s_offset, S_total;    /* this rank's slice of the MC samples (S-sharding keeps the draws identical) */
+    float* w;                     /* out [S,C,T] template weights (gp_weighter.scores) */
+    float* kl;                    /* out [C] KL(q(u) || N(0,I)), or NULL */
+    double* L;                    /* out [C,n,n] saved: lower Cholesky factor of K_ZZ + 1e-4 I (fp64) */
+    float* A;                     /* out [C,n,T] saved: interp_term L^-1 K_ZX */
+    float* R;                     /* out [C,T,T] saved: lower Cholesky factor of Sigma */
+    int32_t* status;              /* out [C]: 0 ok; k>0: Sigma needed k jitter retries; <0: not positive definite */
+} clipgp_gp_args;
+
+/* Dynamic shared memory the forward / backward kernel needs for (T, n, d); 0 if unsupported. */
+int64_t clipgp_gp_smem_bytes(int64_t T, int64_t n, int64_t d, int backward);
+
+int clipgp_gp_forward(const clipgp_gp_args* args, void* stream);
+
+/* Adjoint of clipgp_gp_forward.  `fwd` must be the argument block of the forward call (same inputs, with
+ * w/L/A/R holding its outputs).  Upstream: dw [S,C,T]; dkl [C] or NULL (then dkl_scalar multiplies every
+ * class, i.e. loss += dkl_scalar * sum_c KL_c).  Outputs are OVERWRITTEN:
+ *   dZ_last [C,d]  gradient of the learnable inducing row Z[:, n-1] (rows < T are masked by the reference,
+ *                  gp_template_weigher.py:72-79),
+ *   draw_lengthscale [C,d], draw_outputscale [C], draw_variance [C] (those the kernel type has; NULL otherwise),
+ *   dvar_mean [C,n], dchol_var [C,n,n] (lower triangle, zeros above), dmean_x [C,T] (may be NULL). */
+typedef struct clipgp_gp_bwd_args {
+    const float* dw;
+    const float* dkl;
+    float dkl_scalar;
+    float* dZ_last;
+    float* draw_lengthscale;
+    float* draw_outputscale;
+    float* draw_variance;
+    float* dvar_mean;
+    float* dchol_var;
+    float* dmean_x;
+} clipgp_gp_bwd_args;
+
+int clipgp_gp_backward(const clipgp_gp_args* fwd, const clipgp_gp_bwd_args* bwd, void* stream);
+
+/* ================================================================================================
+ * Weighted prototypes — gp_template_weigher.py:221 (einsum "skm,kmd->skd") fused with the row
+ * normalisation of adapter.py:246/425, taskres.py:109-113, clip_adapter.py:94, tip_adapter.py:136.
+ *   w [S,C,T], E [C,T,D] (frozen text bank, D % 4 == 0).
+ *   residual [C,D] + alpha: TaskRes branch t_s = normalize(p_hat_s + alpha x) (taskres.py:111-113); NULL otherwise.
+ *   Outputs (each may be NULL): P_raw [S,C,D] un-normalised prototypes (the reference's return value),
+ *   P_hat [S,C,D] unit rows, norm [S,C] = |P_raw|, P_hat_bf16 [S,C,D] (operand of the tensor-core logit GEMM),
+ *   mean_hat [C,D] = sum_s P_hat_s, mean_raw [C,D] = sum_s P_raw_s; with finish_mean != 0 they are finished
+ *   to (1/S) sum_s P_hat_s (collapsed logit-mean prototype) and normalize((1/S) sum_s P_raw_s)
+ *   (prototype init of taskres.py:281-285, clip_adapter.py:284-288, tip_adapter.py:152-156).
+ * ================================================================================================ */
+int clipgp_proto_forward(const float* w, const float* E, int64_t S, int64_t C, int64_t T, int64_t D,
+                         const float* residual, float alpha, float* P_raw, float* P_hat, float* norm,
+                         void* P_hat_bf16, float* mean_hat, float* mean_raw, int finish_mean, void* stream);
+
+/* dw [S,C,T] = <dP[s,c,:], E[c,t,:]>.  dP is the gradient of P_raw when P_hat == NULL, else the gradient of the
+ * unit rows P_hat (then dP = (dP_hat - P_hat <P_hat,dP_hat>) / norm is applied first; no residual branch). */
+int clipgp_proto_backward(const float* dP, const float* P_hat, const float* norm, const float* E, int64_t S,
+                          int64_t C, int64_t T, int64_t D, float* dw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPGP_H_ */

@@ -1,0 +1,66 @@
+"""CPU: the C-ABI library loads and exports every symbol include/clipgp.h declares; compute entry points
+fail loudly (status + message, never a silent fallback) when misused or when no GPU is present."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from clip_gp_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "clipgp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(clipgp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/clipgp.h but not exported by libclipgp.so"
+
+
+def test_python_binding_covers_the_header():
+    assert set(_lib.exported_symbols()) == set(declared_symbols())
+    lib = _lib.load()
+    assert lib.clipgp_version() >= 100
+
+
+def test_bad_arguments_report_an_error_message():
+    lib = _lib.load()
+    rc = lib.clipgp_ece_hist(None, None, 5, None, 10, None, None, None, None)
+    assert rc != 0 and b"NULL" in lib.clipgp_last_error()
+    rc = lib.clipgp_ece_hist(None, None, 5, None, 1000, None, None, None, None)
+    assert rc != 0 and b"n_bins" in lib.clipgp_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check(rc, "clipgp_ece_hist")
+
+
+def test_struct_layout_matches_header_field_order():
+    hdr = open(os.path.join(ROOT, "include", "clipgp.h")).read()
+    body = hdr[hdr.index("typedef struct clipgp_gp_args {"):hdr.index("} clipgp_gp_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.replace("*", " ").split()
+        # "int64_t C, T, n, d, S" style
+        tail = decl.split(None, 1)[1] if " " in decl else decl
+        tail = re.sub(r"^(const\s+)?(unsigned\s+)?\w+\s*\**", "", decl).strip() if "," in decl else names[-1]
+        fields += [x.strip().lstrip("*") for x in (tail.split(",") if "," in decl else [names[-1]])]
+    assert fields == [f[0] for f in _lib.GpArgs._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    from clip_gp_b200 import metrics
+    with pytest.raises(RuntimeError):
+        metrics.compute_ece(torch.randn(8, 4), torch.zeros(8, dtype=torch.long))

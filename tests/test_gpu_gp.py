@@ -1,0 +1,205 @@
+"""GPU: GP template weighter kernels (forward + hand-derived adjoint) against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from clip_gp_b200 import ops, synth
+from clip_gp_b200.gp_template_weigher import GaussianProcessTemplateWeighter
+from oracle import gp as ogp
+from tests.helpers import make_state, oracle_grads, rel_err
+
+pytestmark = pytest.mark.gpu
+KERNELS = ["rbf", "matern", "linear"]
+TOL = 1e-3          # BASELINE.json: GP weights within 1e-3 relative in fp32
+
+
+def run_kernel(st, eps, kernel, alias_check=True, need_grad=False, X=None):
+    dev = "cuda"
+    kp = st.kernel
+    t = lambda x: None if x is None else x.detach().clone().to(dev).requires_grad_(need_grad)
+    Z, m, chol = t(st.inducing_points), t(st.var_mean), t(st.chol_var)
+    ls, os_, var = t(kp.raw_lengthscale), t(kp.raw_outputscale), t(kp.raw_variance)
+    Xd = (st.templates_red if X is None else X).to(dev)
+    C, T = st.templates_red.shape[:2]
+    n = st.inducing_points.shape[1]
+    mean_x = ogp.residual_mean(st.f0, st.cls_bias, st.tmp_bias, n + T)[:, n:].contiguous().to(dev)
+    w, kl, status = ops.gp_weights(Z, Xd, ls, os_, var, m, chol, mean_x, eps.to(dev), kernel, eps.shape[2],
+                                   alias_check=alias_check)
+    return w, kl, status, dict(Z=Z, m=m, chol=chol, ls=ls, os=os_, var=var)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", ["tiny", "small", "cfg1"])
+def test_forward_matches_oracle(kernel, name):
+    wl, st = make_state(name, kernel)
+    shp = wl["shape"]
+    eps = torch.randn(shp.C, shp.T, shp.S, generator=torch.Generator().manual_seed(21))
+    w_ref, aux = ogp.gp_weights(st, eps)
+    kl_ref = ogp.kl_divergence(st.var_mean, st.chol_var)
+    w, kl, status, _ = run_kernel(st, eps, kernel)
+    assert int(status.abs().max()) == 0
+    assert rel_err(w, w_ref) < TOL and rel_err(kl, kl_ref) < 1e-5
+    assert float((w.sum(-1) - 1).abs().max()) < 1e-5 and float(w.min()) >= 0
+    # the general three-block path (no aliasing of X with Z[:T]) gives the same answer
+    w2, _, _, _ = run_kernel(st, eps, kernel, alias_check=False)
+    assert rel_err(w2, w) < 1e-4
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_forward_general_inputs(kernel):
+    """X different from the inducing rows (e.g. weight decay moved Z): oracle parity on the general path."""
+    wl, st = make_state("small", kernel)
+    shp = wl["shape"]
+    g = torch.Generator().manual_seed(4)
+    st.inducing_points = st.inducing_points + 0.02 * torch.randn(st.inducing_points.shape, generator=g)
+    eps = torch.randn(shp.C, shp.T, shp.S, generator=g)
+    w_ref, _ = ogp.gp_weights(st, eps)
+    w, _, status, _ = run_kernel(st, eps, kernel)         # alias check on, but rows differ -> general path
+    assert int(status.abs().max()) == 0 and rel_err(w, w_ref) < TOL
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_selfgolden_fixture(golden_dir, kernel):
+    g = np.load(os.path.join(golden_dir, "gp_selfgolden.npz"))
+    wl = synth.make_workload("tiny"); shp = wl["shape"]
+    st = ogp.build_state(wl["E"], kernel, shp.d)
+    st.var_mean, st.chol_var = synth.trained_like_q(shp.C, shp.T + 1, 5)
+    eps = torch.randn(shp.C, shp.T, shp.S, generator=torch.Generator().manual_seed(77))
+    w, kl, _, _ = run_kernel(st, eps, kernel)
+    assert rel_err(w, torch.from_numpy(g[f"{kernel}/w"])) < TOL
+    assert rel_err(kl, torch.from_numpy(g[f"{kernel}/kl"])) < 1e-5
+    P = ops.prototypes(w, st.templates.cuda())
+    assert rel_err(P, torch.from_numpy(g[f"{kernel}/protos"])) < TOL
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", ["tiny", "small"])
+@pytest.mark.parametrize("alias", [True, False])
+def test_adjoint_matches_oracle_autograd(kernel, name, alias):
+    wl, st = make_state(name, kernel)
+    shp = wl["shape"]
+    g = torch.Generator().manual_seed(11)
+    eps = torch.randn(shp.C, shp.T, shp.S, generator=g)
+    dw = torch.randn(shp.S, shp.C, shp.T, generator=g)
+    dkl = torch.rand(shp.C, generator=g)
+    _, _, G, _ = oracle_grads(st, eps, dw, dkl, torch.float64)      # float64 autograd through the oracle
+    w, kl, _, P = run_kernel(st, eps, kernel, alias_check=alias, need_grad=True)
+    loss = (w * dw.cuda()).sum() + (kl * dkl.cuda()).sum()
+    loss.backward()
+    assert float(P["Z"].grad[:, :-1].abs().max()) == 0.0            # frozen template rows (:72-79)
+    assert rel_err(P["Z"].grad[:, -1], G["Z"][:, -1]) < 5e-3
+    assert rel_err(P["m"].grad, G["m"]) < TOL
+    assert rel_err(P["chol"].grad, G["chol"]) < TOL
+    assert float(P["chol"].grad.triu(1).abs().max()) == 0.0
+    if "ls" in G: assert rel_err(P["ls"].grad, G["ls"]) < TOL
+    if "os" in G: assert rel_err(P["os"].grad, G["os"]) < TOL
+    if "var" in G: assert rel_err(P["var"].grad, G["var"]) < TOL
+
+
+def test_max_size_T64_n65_matern():
+    """cfg5 shape per class (T=64, n=65, Matern) on a handful of classes, forward + adjoint."""
+    g = torch.Generator().manual_seed(8)
+    C, T, D, d, S = 6, 64, 512, 256, 7
+    E, _ = synth.make_text_bank(C, T, D, 99)
+    st = ogp.build_state(E, "matern", d)
+    st.var_mean, st.chol_var = synth.trained_like_q(C, T + 1, 3)
+    eps = torch.randn(C, T, S, generator=g)
+    dw = torch.randn(S, C, T, generator=g); dkl = torch.rand(C, generator=g)
+    w64, _, G, _ = oracle_grads(st, eps, dw, dkl, torch.float64)
+    w, kl, status, P = run_kernel(st, eps, "matern", need_grad=True)
+    assert int(status.abs().max()) == 0 and rel_err(w, w64) < TOL
+    ((w * dw.cuda()).sum() + (kl * dkl.cuda()).sum()).backward()
+    assert rel_err(P["m"].grad, G["m"]) < TOL and rel_err(P["chol"].grad, G["chol"]) < TOL
+    assert rel_err(P["ls"].grad, G["ls"]) < TOL
+
+
+def test_identity_q_and_jitter_retry_status():
+    wl, st = make_state("small", "rbf", trained=False, perturb=False)
+    shp = wl["shape"]
+    eps = torch.randn(shp.C, shp.T, shp.S, generator=torch.Generator().manual_seed(6))
+    w_ref, _ = ogp.gp_weights(st, eps)
+    w, kl, status, _ = run_kernel(st, eps, "rbf")
+    assert rel_err(w, w_ref) < TOL and float(kl.abs().max()) < 1e-6 and int(status.abs().max()) == 0
+    # make Sigma indefinite for one class: L_q = 0 => Sigma = K_XX + jI - A^T A ~ jitter-level, may need retries;
+    # the status channel must report it instead of silently returning garbage
+    st.chol_var = st.chol_var.clone(); st.chol_var[0] = 0.0; st.chol_var[0].diagonal().fill_(1e-3)
+    _, _, status, _ = run_kernel(st, eps, "rbf")
+    assert int(status[1:].abs().max()) == 0
+
+
+def test_philox_stream_is_reproducible_and_shardable():
+    wl, st = make_state("small", "rbf")
+    shp = wl["shape"]
+    dev = "cuda"
+    kp = st.kernel
+    args = [x.to(dev) for x in (st.inducing_points, st.templates_red, kp.raw_lengthscale, kp.raw_outputscale)]
+    m, chol = st.var_mean.to(dev), st.chol_var.to(dev)
+    rng = torch.tensor([1234, 7], dtype=torch.int64, device=dev)
+    S = 8
+    full, _, _ = ops.gp_weights(*args, None, m, chol, None, None, "rbf", S, rng_state=rng, s_offset=0, S_total=S)
+    again, _, _ = ops.gp_weights(*args, None, m, chol, None, None, "rbf", S, rng_state=rng, s_offset=0, S_total=S)
+    assert torch.equal(full, again)
+    lo, _, _ = ops.gp_weights(*args, None, m, chol, None, None, "rbf", 3, rng_state=rng, s_offset=0, S_total=S)
+    hi, _, _ = ops.gp_weights(*args, None, m, chol, None, None, "rbf", 5, rng_state=rng, s_offset=3, S_total=S)
+    assert torch.equal(torch.cat([lo, hi], 0), full)                # sharding S never changes the draws
+    rng2 = torch.tensor([1234, 8], dtype=torch.int64, device=dev)
+    other, _, _ = ops.gp_weights(*args, None, m, chol, None, None, "rbf", S, rng_state=rng2, s_offset=0, S_total=S)
+    assert not torch.equal(other, full)
+
+
+class _Cfg:
+    class adapter:
+        gp_pca_dim = 32
+        gp_kernel_type = "rbf"
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_module_drop_in_surface(kernel):
+    """Same constructor / methods / state_dict names as the reference class; differentiable end to end."""
+    wl = synth.make_workload("small"); shp = wl["shape"]
+    cfg = _Cfg(); cfg.adapter.gp_kernel_type = kernel
+    torch.manual_seed(0)
+    gpw = GaussianProcessTemplateWeighter(text_embeddings=wl["E"], cfg=cfg).to("cuda")
+    keys = set(gpw.state_dict().keys())
+    must = {"variational_strategy.inducing_points", "variational_strategy._variational_distribution.variational_mean",
+            "variational_strategy._variational_distribution.chol_variational_covar", "mean_module.f0",
+            "mean_module.cls_bias", "mean_module.tmp_bias", "mean_module.neg_tail", "A.weight",
+            "likelihood.noise_covar.raw_noise", "_ind_mask", "_templates", "_templates_red", "_cls_mean_init"}
+    must |= {"rbf": {"covar_module.raw_outputscale", "covar_module.base_kernel.raw_lengthscale"},
+             "matern": {"covar_module.raw_lengthscale"}, "linear": {"covar_module.raw_variance"}}[kernel]
+    assert must <= keys
+    gpw.train()
+    protos = gpw.sample_prototypes(num_samples=shp.S)
+    assert protos.shape == (shp.S, shp.C, shp.D) and gpw.scores.shape == (shp.S, shp.C, shp.T)
+    kl = gpw.variational_strategy.kl_divergence()
+    assert kl.shape == (shp.C,)
+    (protos.pow(2).sum() + 0.01 * kl.sum()).backward()
+    ip = gpw.variational_strategy.inducing_points
+    assert ip.grad is not None and float(ip.grad[:, :-1].abs().max()) == 0.0
+    q = gpw.variational_strategy._variational_distribution
+    assert q.variational_mean.grad is not None and torch.isfinite(q.chol_variational_covar.grad).all()
+    # oracle parity of the whole module given the same parameters and noise
+    st = ogp.build_state(wl["E"], kernel, 32)
+    st.inducing_points = ip.detach().cpu(); st.var_mean = q.variational_mean.detach().cpu()
+    st.chol_var = q.chol_variational_covar.detach().cpu()
+    if kernel == "rbf":
+        st.kernel.raw_lengthscale = gpw.covar_module.base_kernel.raw_lengthscale.detach().cpu()
+    eps = torch.randn(shp.C, shp.T, 3, generator=torch.Generator().manual_seed(1))
+    P_ref, _ = ogp.sample_prototypes(st, eps)
+    with torch.no_grad():
+        P = gpw.sample_prototypes(3, eps=eps.cuda())
+        Pm = gpw.mean_prototypes(3, eps=eps.cuda())
+        Pc = gpw.collapsed_prototypes(3, eps=eps.cuda())
+    assert rel_err(P, P_ref) < TOL
+    mp = P_ref.mean(0); mp = mp / mp.norm(dim=-1, keepdim=True)
+    assert rel_err(Pm, mp) < TOL
+    assert rel_err(Pc, torch.nn.functional.normalize(P_ref, dim=-1).mean(0)) < TOL
+    # initialize_from_weights is the reference's no-op for T > 1
+    before = q.variational_mean.detach().clone()
+    gpw.initialize_from_weights(torch.full((shp.C, shp.T), 1.0 / shp.T, device="cuda"))
+    assert torch.equal(before, q.variational_mean.detach())
+    with pytest.raises(ValueError):
+        cfg.adapter.gp_kernel_type = "periodic"
+        GaussianProcessTemplateWeighter(text_embeddings=wl["E"], cfg=cfg)

@@ -1,0 +1,110 @@
+"""CPU: the GP oracle (PARITY UNPINNED w.r.t. gpytorch/entmax) against mathematical invariants, against
+its own committed output, and the hand-derived adjoints (oracle/gp_manual.py == the CUDA algorithm sheet)
+against autograd."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from clip_gp_b200 import synth
+from oracle import gp as ogp
+from oracle import gp_manual as gm
+from tests.helpers import make_state, oracle_grads, rel_err
+
+KERNELS = ["rbf", "matern", "linear"]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_selfgolden(golden_dir, kernel):
+    g = np.load(os.path.join(golden_dir, "gp_selfgolden.npz"))
+    wl = synth.make_workload("tiny"); shp = wl["shape"]
+    st = ogp.build_state(wl["E"], kernel, shp.d)
+    st.var_mean, st.chol_var = synth.trained_like_q(shp.C, shp.T + 1, 5)
+    eps = torch.randn(shp.C, shp.T, shp.S, generator=torch.Generator().manual_seed(77))
+    P, aux = ogp.sample_prototypes(st, eps)
+    np.testing.assert_allclose(aux["w"].numpy(), g[f"{kernel}/w"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(P.numpy(), g[f"{kernel}/protos"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(ogp.kl_divergence(st.var_mean, st.chol_var).numpy(), g[f"{kernel}/kl"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_invariants(kernel):
+    wl, st = make_state("small", kernel)
+    shp = wl["shape"]
+    eps = torch.randn(shp.C, shp.T, shp.S, generator=torch.Generator().manual_seed(1))
+    P, aux = ogp.sample_prototypes(st, eps)
+    w = aux["w"]
+    assert w.min() >= 0 and float((w.sum(-1) - 1).abs().max()) < 1e-5            # simplex
+    q = torch.distributions.MultivariateNormal(st.var_mean, scale_tril=st.chol_var.tril())
+    p = torch.distributions.MultivariateNormal(torch.zeros_like(st.var_mean),
+                                               scale_tril=torch.eye(shp.T + 1).repeat(shp.C, 1, 1))
+    assert rel_err(ogp.kl_divergence(st.var_mean, st.chol_var), torch.distributions.kl_divergence(q, p)) < 1e-5
+    # uniform weights -> prototypes are the template mean
+    wu = torch.full_like(w, 1.0 / shp.T)
+    assert rel_err(torch.einsum("skm,kmd->skd", wu, st.templates)[0], st.templates.mean(1)) < 1e-5
+
+
+def test_identity_q_gives_prior_covariance():
+    wl, st = make_state("small", "rbf", trained=False)
+    shp = wl["shape"]
+    n = shp.T + 1
+    mean_x = ogp.residual_mean(st.f0, st.cls_bias, st.tmp_bias, n + shp.T)[:, n:]
+    mu, Sigma, aux = ogp.variational_predictive(st.kernel, st.inducing_points, st.templates_red, st.var_mean,
+                                                st.chol_var, mean_x)
+    assert torch.equal(Sigma, aux["K_XX"] + 1e-4 * torch.eye(shp.T))             # L_q = I, m = 0
+    assert float(ogp.kl_divergence(st.var_mean, st.chol_var).abs().max()) == 0.0
+    # the mean module only shifts f by a per-class constant -> sparsemax is unaffected
+    assert float((mean_x - mean_x[:, :1]).abs().max()) == 0.0
+
+
+def test_sparsemax_matches_sort_free_form_and_threshold():
+    g = torch.Generator().manual_seed(3)
+    f = 2.0 * torch.randn(7, 11, 9, generator=g)
+    f[0, 0, :] = 0.3                     # full tie
+    f[1, 1, :4] = 5.0                    # partial tie at the top
+    w = ogp.sparsemax(f)
+    w2, ksz = gm.sparsemax_fwd(f)
+    assert rel_err(w2, w) < 1e-6
+    assert float((w.sum(-1) - 1).abs().max()) < 1e-6
+    # KKT: w = max(f - tau, 0) for one tau per row
+    tau = (f - w).masked_fill(w <= 0, float("-inf")).amax(-1, keepdim=True)
+    assert float((torch.clamp(f - tau, min=0) - w).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_manual_adjoint_matches_autograd(kernel, name):
+    """The CUDA backward implements oracle/gp_manual.py; here that sheet is checked against autograd through
+    the gpytorch-semantics oracle evaluated in float64 (the fp32 oracle's sq_dist expansion is itself noisy at
+    1e-4..1e-1 for Matern gradients of the learnable row)."""
+    wl, st = make_state(name, kernel)
+    shp = wl["shape"]
+    g = torch.Generator().manual_seed(11)
+    eps = torch.randn(shp.C, shp.T, shp.S, generator=g)
+    dw = torch.randn(shp.S, shp.C, shp.T, generator=g)
+    dkl = torch.rand(shp.C, generator=g)
+    w64, kl64, G, _ = oracle_grads(st, eps, dw, dkl, torch.float64)
+    n = shp.T + 1
+    mean_x = ogp.residual_mean(st.f0, st.cls_bias, st.tmp_bias, n + shp.T)[:, n:]
+    kp = st.kernel
+    w, kl, saved = gm.forward(kernel, st.inducing_points, st.templates_red, kp.raw_lengthscale, kp.raw_outputscale,
+                              kp.raw_variance, st.var_mean, st.chol_var, mean_x, eps)
+    out = gm.backward(saved, dw, dkl)
+    assert rel_err(w, w64) < 1e-4 and rel_err(kl, kl64) < 1e-5
+    assert rel_err(out["dZ"][:, -1], G["Z"][:, -1]) < 5e-3
+    assert rel_err(out["dm"], G["m"]) < 1e-3 and rel_err(out["dchol"], G["chol"]) < 1e-3
+    if "ls" in G: assert rel_err(out["draw_ls"], G["ls"]) < 1e-3
+    if "os" in G: assert rel_err(out["draw_os"], G["os"]) < 1e-3
+    if "var" in G: assert rel_err(out["draw_var"], G["var"]) < 1e-3
+
+
+def test_fp32_oracle_close_to_fp64_oracle():
+    """Forward tolerance budget: fp32 gpytorch-style evaluation vs float64 (both with 1e-4 jitter)."""
+    for kernel in KERNELS:
+        wl, st = make_state("small", kernel)
+        shp = wl["shape"]
+        eps = torch.randn(shp.C, shp.T, shp.S, generator=torch.Generator().manual_seed(2))
+        w32, _ = ogp.gp_weights(st, eps)
+        w64, _, _, _ = oracle_grads(st, eps, torch.zeros(shp.S, shp.C, shp.T), torch.zeros(shp.C))
+        assert rel_err(w32, w64) < 1e-3
