@@ -65,6 +65,16 @@ _SIGNATURES = {
                                        C.c_void_p]),
     "clipgp_proto_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, c_i64,
                                         C.c_void_p, C.c_void_p]),
+    "clipgp_gemm_f32": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, c_i64, c_i64,
+                                  C.c_float, C.c_int, C.c_void_p]),
+    "clipgp_rownorm_forward": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "clipgp_rownorm_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p]),
+    "clipgp_softmax_ce": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_float,
+                                    C.c_void_p, c_i64, C.c_float, C.c_void_p]),
+    "clipgp_l2_identity": (C.c_int, [C.c_void_p, c_i64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "clipgp_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "clipgp_increment": (C.c_int, [C.c_void_p, c_i64, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

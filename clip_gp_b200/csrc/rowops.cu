@@ -1,0 +1,188 @@
+// Row-wise kernels around the logit GEMMs: L2 row normalisation (forward / adjoint), softmax
+// cross-entropy (forward + gradient in one pass), the ||W - I||_F^2 regulariser, and the fused AdamW
+// update.  All HBM-bound streaming kernels (one warp per row / grid-stride, float4 where aligned).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace clipgp {
+
+// y = x / max(|x|, eps) per row (F.normalize, adapter.py:240,246); inv_norm[r] = 1 / max(|x|, eps).
+__global__ void __launch_bounds__(256) rownorm_fwd_kernel(const float* __restrict__ x, int64_t R, int D,
+                                                          float* __restrict__ y, float* __restrict__ inv_norm,
+                                                          __nv_bfloat16* __restrict__ y_bf16) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const float* xr = x + row * D;
+    float q = 0.f;
+    for (int k = lane; k < D; k += 32) { const float v = xr[k]; q = fmaf(v, v, q); }
+    q = warp_sum(q);
+    const float inv = 1.f / fmaxf(sqrtf(q), 1e-12f);
+    for (int k = lane; k < D; k += 32) {
+        const float v = xr[k] * inv;
+        if (y) y[row * D + k] = v;
+        if (y_bf16) y_bf16[row * D + k] = __float2bfloat16_rn(v);
+    }
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+}
+
+// dx = (dy - y <y, dy>) * inv_norm
+__global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                          const float* __restrict__ inv_norm, int64_t R, int D,
+                                                          float* __restrict__ dx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= R) return;
+    float dt = 0.f;
+    for (int k = lane; k < D; k += 32) dt = fmaf(y[row * D + k], dy[row * D + k], dt);
+    dt = warp_sum(dt);
+    const float inv = inv_norm[row];
+    for (int k = lane; k < D; k += 32) dx[row * D + k] = (dy[row * D + k] - y[row * D + k] * dt) * inv;
+}
+
+// One warp per logits row r (label index r / rows_per_label).  loss_sum += loss_scale * sum_r CE_r;
+// dlogits = grad_scale * (softmax - onehot), may alias logits.
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const float* logits, int64_t ld, const int64_t* __restrict__ labels,
+                                                         int64_t R, int64_t rows_per_label, int C, float* __restrict__ loss_rows,
+                                                         float* loss_sum, float loss_scale, float* dlogits, int64_t ldd,
+                                                         float grad_scale) {
+    __shared__ float part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    float my_loss = 0.f;
+    if (row < R) {
+        const float* x = logits + row * ld;
+        const int lab = (int)labels[row / rows_per_label];
+        float m = -FLT_MAX;
+        for (int j = lane; j < C; j += 32) m = fmaxf(m, x[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < C; j += 32) s += expf(x[j] - m);
+        s = warp_sum(s);
+        const float lse = m + logf(s);
+        const float xl = x[lab];
+        my_loss = lse - xl;
+        if (loss_rows && lane == 0) loss_rows[row] = my_loss;
+        if (dlogits) {
+            const float invs = 1.f / s;
+            float* g = dlogits + row * ldd;
+            for (int j = lane; j < C; j += 32) {
+                const float p = expf(x[j] - m) * invs;
+                g[j] = grad_scale * (p - (j == lab ? 1.f : 0.f));
+            }
+        }
+    }
+    if (loss_sum) {
+        if (lane == 0) part[warp] = (row < R) ? my_loss : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += part[k];
+            atomicAdd(loss_sum, t * loss_scale);
+        }
+    }
+}
+
+// loss += coef * ||W - I||_F^2 ; dW += 2 coef (W - I)      (adapter.py:468-476)
+__global__ void __launch_bounds__(256) l2_identity_kernel(const float* __restrict__ W, int D, float coef,
+                                                          float* __restrict__ dW, float* loss_sum) {
+    __shared__ float red[32];
+    float q = 0.f;
+    const int64_t n = (int64_t)D * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / D), c = (int)(i - (int64_t)r * D);
+        const float v = W[i] - (r == c ? 1.f : 0.f);
+        q = fmaf(v, v, q);
+        if (dW) dW[i] += 2.f * coef * v;
+    }
+    const float tot = block_sum(q, red);
+    if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, coef * tot);
+}
+
+// torch.optim.AdamW semantics (decoupled weight decay, bias correction, eps added after sqrt):
+//   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+//   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// `step` is read from device memory (so a captured CUDA graph advances it); row_mask (optional) restricts the
+// update to elements with mask != 0 semantics-free (mask multiplies the gradient first, gp_template_weigher.py:76-79).
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                    float wd, const int64_t* __restrict__ step_ptr) {
+    const float t = (float)(*step_ptr);
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+        p[i] = pi;
+    }
+}
+
+__global__ void increment_kernel(int64_t* p, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) *p += by; }
+
+}  // namespace clipgp
+
+using namespace clipgp;
+
+extern "C" int clipgp_rownorm_forward(const float* x, int64_t R, int64_t D, float* y, float* inv_norm, void* y_bf16, void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && D >= 1 && D < (1ll << 31), "rownorm_forward: bad shape");
+    if (R == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(x && (y || y_bf16), "rownorm_forward: NULL pointer");
+    const int64_t blocks = (R + 7) / 8;
+    rownorm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)D, y, inv_norm, (__nv_bfloat16*)y_bf16);
+    return check_launch("rownorm_fwd_kernel");
+}
+
+extern "C" int clipgp_rownorm_backward(const float* dy, const float* y, const float* inv_norm, int64_t R, int64_t D, float* dx,
+                                       void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && D >= 1 && D < (1ll << 31), "rownorm_backward: bad shape");
+    if (R == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(dy && y && inv_norm && dx, "rownorm_backward: NULL pointer");
+    const int64_t blocks = (R + 7) / 8;
+    rownorm_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, y, inv_norm, R, (int)D, dx);
+    return check_launch("rownorm_bwd_kernel");
+}
+
+extern "C" int clipgp_softmax_ce(const float* logits, int64_t ld, const int64_t* labels, int64_t R, int64_t rows_per_label,
+                                 int64_t C, float* loss_rows, float* loss_sum, float loss_scale, float* dlogits, int64_t ldd,
+                                 float grad_scale, void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && C >= 1 && C < (1ll << 31) && rows_per_label >= 1, "softmax_ce: bad shape");
+    if (R == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(logits && labels && ld >= C, "softmax_ce: bad input");
+    CLIPGP_REQUIRE(!dlogits || ldd >= C, "softmax_ce: ldd < C");
+    const int64_t blocks = (R + 7) / 8;
+    softmax_ce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, R, rows_per_label, (int)C, loss_rows,
+                                                                         loss_sum, loss_scale, dlogits, ldd, grad_scale);
+    return check_launch("softmax_ce_kernel");
+}
+
+extern "C" int clipgp_l2_identity(const float* W, int64_t D, float coef, float* dW, float* loss_sum, void* stream) {
+    CLIPGP_REQUIRE(D >= 1 && W, "l2_identity: bad input");
+    int64_t blocks = (D * D + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    l2_identity_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(W, (int)D, coef, dW, loss_sum);
+    return check_launch("l2_identity_kernel");
+}
+
+extern "C" int clipgp_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                                 float eps, float weight_decay, const int64_t* step, void* stream) {
+    CLIPGP_REQUIRE(n >= 0, "adamw_step: n < 0");
+    if (n == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(p && g && m && v && step, "adamw_step: NULL pointer");
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step);
+    return check_launch("adamw_kernel");
+}
+
+extern "C" int clipgp_increment(int64_t* counter, int64_t by, void* stream) {
+    CLIPGP_REQUIRE(counter, "increment: NULL pointer");
+    increment_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, by);
+    return check_launch("increment_kernel");
+}

@@ -147,6 +147,40 @@ int clipgp_proto_forward(const float* w, const float* E, int64_t S, int64_t C, i
 int clipgp_proto_backward(const float* dP, const float* P_hat, const float* norm, const float* E, int64_t S,
                           int64_t C, int64_t T, int64_t D, float* dw, void* stream);
 
+/* ================================================================================================
+ * Cosine-logit heads — adapter.py:230-252 (forward_features), :401-428 (per-sample MC cross-entropy),
+ * taskres.py:96-123, clip_adapter.py:85-100, tip_adapter.py:250-260 — exact-fp32 building blocks.
+ * (The tensor-core path with fused epilogues is clipgp_tc_*.)
+ * ================================================================================================ */
+
+/* C[M,N] = alpha * op(A) op(B) (+ C if accumulate), fp32 FFMA.  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn];
+ * each operand needs one unit stride.  Covers f W^T (adapter.py:239), f_hat P_hat^T (:248,:426), f keys^T
+ * (tip_adapter.py:250) and their adjoints dlogits^T f_hat, dlogits P_hat. */
+int clipgp_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
+                    int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha, int accumulate, void* stream);
+
+/* F.normalize(x, dim=-1) (adapter.py:240): y = x / max(|x|, 1e-12); inv_norm [R]; optional bf16 copy of y. */
+int clipgp_rownorm_forward(const float* x, int64_t R, int64_t D, float* y, float* inv_norm, void* y_bf16, void* stream);
+/* dx = (dy - y <y,dy>) * inv_norm. */
+int clipgp_rownorm_backward(const float* dy, const float* y, const float* inv_norm, int64_t R, int64_t D, float* dx,
+                            void* stream);
+
+/* F.cross_entropy over R logits rows of C classes (adapter.py:427, taskres.py:270); row r uses labels[r / rows_per_label]
+ * (rows_per_label = S for the [B,S,C] per-sample layout).  loss_rows [R] (may be NULL); loss_sum[0] += loss_scale * sum_r CE_r
+ * (may be NULL); dlogits (may be NULL, may alias logits) = grad_scale * (softmax - onehot). */
+int clipgp_softmax_ce(const float* logits, int64_t ld, const int64_t* labels, int64_t R, int64_t rows_per_label, int64_t C,
+                      float* loss_rows, float* loss_sum, float loss_scale, float* dlogits, int64_t ldd, float grad_scale,
+                      void* stream);
+
+/* adapter.py:468-476: loss_sum[0] += coef * ||W - I||_F^2 ; dW += 2 coef (W - I)  (dW / loss_sum may be NULL). */
+int clipgp_l2_identity(const float* W, int64_t D, float coef, float* dW, float* loss_sum, void* stream);
+
+/* torch.optim.AdamW update (utils/optimization.py:57-216 builds it; adapter.py:549 steps it) on one flat fp32 buffer.
+ * `step` is a DEVICE int64 (1-based) so captured CUDA graphs advance it with clipgp_increment. */
+int clipgp_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, const int64_t* step, void* stream);
+int clipgp_increment(int64_t* counter, int64_t by, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
