@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py — GP-adapter train steps/s (and eval img/s) on synthetic cached features of BASELINE.json's cfg2
+shape (ViT-B/16 D=512, ImageNet-1k C=1000, T=32 templates, 16-shot, S=10 MC samples, B=128).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one GP-Adapter optimisation step over one batch of cached features (engine.py): GP forward,
+prototypes, projection, logits for every MC sample, per-sample CE, all adjoints, L2 regulariser, AdamW.
+`value` = steps/s with inputs resident in HBM (CUDA events around each step, L2 flushed between steps, max over
+ranks); `e2e` = the same step driven from pinned HOST batches (H2D copy of the batch and D2H read of the loss inside
+the timed region).  N > 1: the S MC samples are sharded over ranks (strong scaling of one optimisation step; S=10 over 8 ranks
+splits 2,2,1,1,1,1,1,1), gradients + loss go through ONE NCCL all-reduce; eval images are sharded over ranks.
+`--impl reference` times the CPU oracle (the restated reference path: torch CPU + autograd + AdamW) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "cfg2"
+METRIC = "gp_adapter_train_steps_per_s"
+UNIT = "steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--eval-n", type=int, default=50000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="also print the per-kernel time table")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def bench_lengthscale(E, d):
+    """Median-heuristic length-scale (gp_template_weigher.py:103-107) on the templates of the first 64 classes; the full
+    C*T = 32 000-point cdist is one-time setup outside the step and both arms use this same value."""
+    from oracle import gp as ogp
+    _, _, tr, _, _ = ogp.pca_setup(E, d)
+    return ogp.median_lengthscale(tr[:64])
+
+
+class _Cfg:
+    def __init__(self, kernel, pca, ls=None):
+        self.adapter = type("A", (), {"gp_pca_dim": pca, "gp_kernel_type": kernel})()
+
+
+# ======================================================================================================= reference arm
+def run_reference(args):
+    """The reference's CPU path for the same step (oracle restatement: the reference itself cannot run offline without
+    gpytorch/entmax).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from clip_gp_b200 import synth
+    from oracle import gp as ogp
+    from oracle.train_step import OracleAdapter
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = synth.make_workload(args.workload)
+    shp = wl["shape"]
+    S = shp.S
+    ls = bench_lengthscale(wl["E"], shp.d) if shp.kernel == "rbf" else None
+    st = ogp.build_state(wl["E"], shp.kernel, shp.d, lengthscale=ls)
+    g = torch.Generator().manual_seed(1)
+    st.var_mean = 1e-3 * torch.randn(shp.C, shp.T + 1, generator=g)
+    orc = OracleAdapter(st, shp.D, shots=shp.shots)
+    f, y = wl["f_train"], wl["y_train"]
+    nb = f.shape[0] // shp.B
+
+    def one(it):
+        lo = (it % nb) * shp.B
+        eps = torch.randn(shp.C, shp.T, S, generator=g)
+        return orc.step(f[lo:lo + shp.B], y[lo:lo + shp.B], eps)
+
+    for it in range(args.warmup):
+        one(it)
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        one(args.warmup + it)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: C={shp.C} T={shp.T} D={shp.D} d={shp.d} S={S} B={shp.B} {shp.kernel} (CPU oracle of the reference path)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full optimisation steps (fwd + autograd bwd + AdamW) of the same workload"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================= our arm
+def algorithmic_bytes(shp, S, kernel_name):
+    """Algorithmic HBM bytes per launch of the step's kernels (DESIGN.md section 'kernels')."""
+    C, T, D, d, n, B = shp.C, shp.T, shp.D, shp.d, shp.T + 1, shp.B
+    f = 4
+    table = {
+        # reads Z [C,n,d], X [C,T,d] (alias check), lengthscale, Lq, m; writes w, L (fp64), A, R, kl
+        "gp_forward": f * (C * n * d + C * T * d + C * d + C * n * n + C * n + S * C * T + C * n * T + C * T * T) + 8 * C * n * n,
+        # reads the saved L/A/R, w, dw, Z and X twice (r^2 pass + adjoint pass), Lq, m; writes all parameter gradients
+        "gp_backward": f * (2 * (C * n * d + C * T * d) + C * d + 2 * C * n * n + 2 * C * n + 2 * S * C * T + C * n * T + C * T * T + 2 * C * d) + 8 * C * n * n,
+        # reads E [C,T,D] + w; writes P_hat [S,C,D] + norms
+        "proto_forward": f * (C * T * D + S * C * T + S * C * D + S * C),
+        # reads dP, P_hat [S,C,D], E [C,T,D]; writes dw
+        "proto_backward": f * (2 * S * C * D + C * T * D + S * C * T + S * C),
+    }
+    return table.get(kernel_name)
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the clipgp kernels have no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        torch.distributed.barrier()
+    from clip_gp_b200 import _lib, metrics, synth
+    from clip_gp_b200.engine import EngineConfig, GPAdapterEngine
+    from clip_gp_b200.gp_template_weigher import GaussianProcessTemplateWeighter
+
+    wl = synth.make_workload(args.workload)
+    shp = wl["shape"]
+    S = shp.S                                            # S=10 over 8 ranks splits 2,2,1,1,1,1,1,1
+    ls = bench_lengthscale(wl["E"], shp.d) if shp.kernel == "rbf" else None
+    torch.manual_seed(1)
+    gpw = GaussianProcessTemplateWeighter(wl["E"].to(dev), _Cfg(shp.kernel, shp.d), lengthscale=ls).to(dev)
+    cfg = EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world)
+    eng = GPAdapterEngine(gpw, cfg)
+    f_all = wl["f_train"].to(dev)
+    y_all = wl["y_train"].to(dev)
+    nb = f_all.shape[0] // shp.B
+    f_host = wl["f_train"].pin_memory()
+    y_host = wl["y_train"].pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
+
+    def batch(it):
+        lo = (it % nb) * shp.B
+        return lo, lo + shp.B
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident timing
+    for it in range(max(args.warmup, 3)):
+        lo, hi = batch(it)
+        eng.train_step(f_all[lo:hi], y_all[lo:hi])
+    sync_all()
+    launches0 = _lib.launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    for it in range(args.steps):
+        lo, hi = batch(args.warmup + it)
+        flush.fill_(0.0)                                   # L2 flush between timed iterations (outside the events)
+        eng.in_feat.copy_(f_all[lo:hi]); eng.in_lab.copy_(y_all[lo:hi])
+        evs[it][0].record()
+        if eng._graph is not None:
+            eng._graph.replay()
+        else:
+            eng._launch_step()
+        evs[it][1].record()
+    sync_all()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(t.item())
+    loss_last = float(eng.loss.item())
+    # kernels per step: counted from one eager (un-graphed) step: graph replays do not pass through the C ABI
+    eng_launch0 = _lib.launch_count()
+    eng.skip_update = False
+    lo, hi = batch(0)
+    eng.in_feat.copy_(f_all[lo:hi]); eng.in_lab.copy_(y_all[lo:hi])
+    eng._launch_step()
+    torch.cuda.synchronize(dev)
+    launches_per_step = _lib.launch_count() - eng_launch0
+
+    # ---------------- e2e: pinned host batches in, loss out, every step
+    sync_all()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        lo, hi = batch(args.warmup + it)
+        loss = eng.train_step(f_host[lo:hi], y_host[lo:hi])
+        _ = float(loss.item())
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------- per-kernel times (CUDA events on the launching stream, eager launches, L2 flushed)
+    ktimes = profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5)
+
+    # ---------------- eval leg: MC-averaged logits + acc/ECE/AECE over this rank's shard of the test features
+    n_eval = args.eval_n
+    f_te, y_te = wl["f_test"][:n_eval], wl["y_test"][:n_eval]
+    per = (n_eval + world - 1) // world
+    sl = slice(rank * per, min(n_eval, (rank + 1) * per))
+    f_sh, y_sh = f_te[sl].to(dev), y_te[sl].to(dev)
+    for _ in range(2):
+        res = eng.evaluate(f_sh, y_sh)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    ev_ms = 0.0
+    for _ in range(reps):
+        flush.fill_(0.0)
+        e0.record()
+        logits = eng.eval_logits(f_sh)
+        conf, correct, hist = metrics.calibration_pass(logits, y_sh, 10)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ev_ms += e0.elapsed_time(e1)
+    t = torch.tensor([ev_ms / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    eval_ms = float(t.item())
+    # global metrics: all-reduce only the integer counters; AECE needs the gathered confidences
+    if world > 1:
+        h = hist.clone()
+        torch.distributed.all_reduce(h)
+        cnt = metrics.counters_from_hist(h, n_eval)
+        confs = [torch.empty(per, device=dev) for _ in range(world)]
+        cors = [torch.empty(per, dtype=torch.uint8, device=dev) for _ in range(world)]
+        pad = per - conf.numel()
+        torch.distributed.all_gather(confs, torch.cat([conf, conf.new_zeros(pad)]))
+        torch.distributed.all_gather(cors, torch.cat([correct, correct.new_zeros(pad)]))
+        conf_g = torch.cat([c[: min(per, n_eval - i * per)] for i, c in enumerate(confs)])
+        cor_g = torch.cat([c[: min(per, n_eval - i * per)] for i, c in enumerate(cors)])
+    else:
+        cnt = metrics.counters_from_hist(hist, n_eval)
+        conf_g, cor_g = conf, correct
+    ece, _ = metrics.ece_from_counters(cnt)
+    _, out = metrics.aece_pass(conf_g, cor_g, 10)
+    aece, _ = metrics.aece_from_bins(out, n_eval, 10)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    pk = peaks()
+    steps_per_s = args.steps / (ms_total * 1e-3)
+    # dominant kernel of the step -> roofline
+    dom = max(ktimes, key=lambda k: ktimes[k]["ms"]) if ktimes else None
+    roof = None
+    if dom is not None:
+        base = dom.split("(")[0]
+        ab = algorithmic_bytes(shp, eng.S_local, base)
+        dur = ktimes[dom]["ms"] * 1e-3 / max(1, ktimes[dom]["calls"])
+        if ab is not None:
+            ach = ab / dur / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": None, "algorithmic_bytes": ab, "avg_launch_us": dur * 1e6, "share_of_step": ktimes[dom]["ms"] / sum(v["ms"] for v in ktimes.values()),
+                    "peak_source": pk["source"]}
+        else:
+            C_, D_, B_ = shp.C, shp.D, shp.B
+            fl = 2.0 * B_ * eng.S_local * C_ * D_
+            roof = {"kernel": dom, "bound": "tensor", "achieved": fl / dur / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": fl / dur / 1e12 / pk["bf16_tflops"], "traffic": None, "avg_launch_us": dur * 1e6,
+                    "share_of_step": ktimes[dom]["ms"] / sum(v["ms"] for v in ktimes.values()), "peak_source": pk["source"],
+                    "note": "fp32 FFMA GEMM (exact mode) reported against the bf16 tensor peak"}
+    line = {
+        "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: C={shp.C} T={shp.T} D={shp.D} d={shp.d} S={S} B={shp.B} shots={shp.shots} kernel={shp.kernel}, "
+                               f"per-sample MC cross-entropy + KL + L2, AdamW; MC samples sharded over {world} rank(s)",
+                   "l2_flush": "256 MB device buffer written between timed steps", "precision": "fp32 (FFMA GEMMs, fp64 K_ZZ Cholesky)",
+                   "cuda_graph": eng._graph is not None, "loss_last": loss_last},
+        "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": shp.B * shp.D * 4 + shp.B * 8, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches_per_step) * args.steps,
+        "gpu_launches_per_step": int(launches_per_step),
+        "clocks": clk,
+        "roofline": roof,
+        "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in ktimes.items()},
+        "eval": {"metric": "eval_img_per_s (MC-averaged logits + acc/ECE histogram, device resident)", "value": n_eval / (eval_ms * 1e-3),
+                 "unit": "img/s", "n_images": n_eval, "ms": eval_ms, "S_eval": S, "top1_acc": cnt.top1 * 100.0 / n_eval, "ece": ece, "aece": aece,
+                 "form": "collapsed logit-mean (exact): one [N,D]x[C,D]^T GEMM"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(wl, shp, S, ls)
+    print(json.dumps(line), flush=True)
+    if args.profile_kernels:
+        for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["ms"]):
+            print(f"# {k:28s} {v['ms']*1e3:9.1f} us/step  ({v['calls']} launches)", file=sys.stderr)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5):
+    """Average device time of every kernel of one step, from CUDA events around each C-ABI launch (eager mode)."""
+    from clip_gp_b200 import _lib
+    lib = eng.lib
+    names = ["clipgp_gemm_f32", "clipgp_rownorm_forward", "clipgp_gp_forward", "clipgp_proto_forward", "clipgp_softmax_ce",
+             "clipgp_rownorm_backward", "clipgp_l2_identity", "clipgp_proto_backward", "clipgp_gp_backward", "clipgp_sum_accumulate",
+             "clipgp_adamw_step", "clipgp_increment"]
+    records = []
+
+    class Wrap:
+        def __init__(self, fn, name):
+            self.fn, self.name = fn, name
+
+        def __call__(self, *a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = self.fn(*a)
+            e1.record()
+            records.append((self.name, e0, e1))
+            return rc
+
+    class Proxy:
+        def __getattr__(self, n):
+            fn = getattr(lib, n)
+            return Wrap(fn, n) if n in names else fn
+
+    if eng.cfg.world > 1:
+        return {}
+    eng.lib = Proxy()
+    out = {}
+    try:
+        for r in range(reps):
+            records.clear()
+            flush.fill_(0.0)
+            eng.in_feat.copy_(f_all[: shp.B]); eng.in_lab.copy_(y_all[: shp.B])
+            eng._launch_step()
+            torch.cuda.synchronize()
+            seen = {}
+            for name, e0, e1 in records:
+                short = name.replace("clipgp_", "")
+                k = seen.get(short, 0); seen[short] = k + 1
+                key = f"{short}({k})" if short in ("gemm_f32", "adamw_step", "increment") else short
+                d = out.setdefault(key, {"ms": 0.0, "calls": 0})
+                d["ms"] += e0.elapsed_time(e1) / reps
+                d["calls"] = 1
+    finally:
+        eng.lib = lib
+    return out
+
+
+def cpu_baseline(wl, shp, S, ls, budget_s=20.0):
+    from oracle import gp as ogp
+    from oracle.train_step import OracleAdapter
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = ogp.build_state(wl["E"], shp.kernel, shp.d, lengthscale=ls)
+    g = torch.Generator().manual_seed(1)
+    st.var_mean = 1e-3 * torch.randn(shp.C, shp.T + 1, generator=g)
+    orc = OracleAdapter(st, shp.D, shots=shp.shots)
+    f, y = wl["f_train"], wl["y_train"]
+    orc.step(f[: shp.B], y[: shp.B], torch.randn(shp.C, shp.T, S, generator=g))   # warm-up
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 50):
+        lo = (n % (f.shape[0] // shp.B)) * shp.B
+        orc.step(f[lo:lo + shp.B], y[lo:lo + shp.B], torch.randn(shp.C, shp.T, S, generator=g))
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} full steps (fwd + autograd bwd + AdamW) of the same {shp.name} workload on the host CPU, torch {torch.__version__}"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -63,8 +63,8 @@ _SIGNATURES = {
     "clipgp_proto_forward": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, c_i64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p]),
-    "clipgp_proto_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, c_i64,
-                                        C.c_void_p, C.c_void_p]),
+    "clipgp_proto_backward": (C.c_int, [C.c_void_p, c_i64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64,
+                                        c_i64, C.c_void_p, C.c_void_p]),
     "clipgp_gemm_f32": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, c_i64, c_i64,
                                   C.c_float, C.c_int, C.c_void_p]),
     "clipgp_rownorm_forward": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -75,6 +75,7 @@ _SIGNATURES = {
     "clipgp_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_float, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "clipgp_increment": (C.c_int, [C.c_void_p, c_i64, C.c_void_p]),
+    "clipgp_sum_accumulate": (C.c_int, [C.c_void_p, c_i64, C.c_float, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

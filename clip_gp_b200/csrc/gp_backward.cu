@@ -327,7 +327,11 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
     if (a->kernel_type == CLIPGP_KERNEL_LINEAR) CLIPGP_REQUIRE(a->raw_variance, "gp_backward: raw_variance is NULL");
     const size_t smem = (size_t)clipgp_gp_smem_bytes(a->T, a->n, a->d, 1);
     CLIPGP_REQUIRE(smem > 0 && smem <= 227 * 1024, "gp_backward: needs %zu bytes of shared memory (> 227 KB); reduce d", smem);
-    CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     gp::gp_backward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b);
     return check_launch("gp_backward_kernel");
 }

@@ -233,7 +233,11 @@ extern "C" int clipgp_gp_forward(const clipgp_gp_args* a, void* stream) {
     if (a->C == 0) return CLIPGP_OK;
     const size_t smem = (size_t)clipgp_gp_smem_bytes(a->T, a->n, a->d, 0);
     CLIPGP_REQUIRE(smem > 0 && smem <= 227 * 1024, "gp_forward: needs %zu bytes of shared memory (> 227 KB); reduce d", smem);
-    CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set = 0;   // raise the opt-in limit only when needed (keeps the call out of graph captures)
+    if (smem > smem_set) {
+        CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     gp::gp_forward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a);
     return check_launch("gp_forward_kernel");
 }

@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(128) scale_normalize_rows_kernel(float* __rest
 // gradient of the normalised rows:  dP = (dP_hat - P_hat <P_hat, dP_hat>) / |P|.
 template <int SB>
 __global__ void __launch_bounds__(kProtoThreads) proto_backward_kernel(
-    const float* __restrict__ dP, const float* __restrict__ P_hat, const float* __restrict__ norm,
-    const float* __restrict__ E, int64_t S, int64_t C, int T, int D, float* __restrict__ dw) {
+    const float* __restrict__ dP, int64_t dP_stride_s, float dP_scale, const float* __restrict__ P_hat,
+    const float* __restrict__ norm, const float* __restrict__ E, int64_t S, int64_t C, int T, int D, float* __restrict__ dw) {
     extern __shared__ __align__(16) float g[];   // [SB][D]
     __shared__ float red[SB][kProtoThreads / 32];
     __shared__ float dots[SB];
@@ -192,8 +192,10 @@ __global__ void __launch_bounds__(kProtoThreads) proto_backward_kernel(
         float q = 0.f;
         if (s < sb) {
             const size_t row = ((size_t)(s0 + s) * C + c) * D;
+            const size_t grow = (size_t)(s0 + s) * dP_stride_s + (size_t)c * D;
             for (int col = tid; col < D4; col += blockDim.x) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(dP + row) + col);
+                float4 v = __ldg(reinterpret_cast<const float4*>(dP + grow) + col);
+                v.x *= dP_scale; v.y *= dP_scale; v.z *= dP_scale; v.w *= dP_scale;
                 reinterpret_cast<float4*>(g + (size_t)s * D)[col] = v;
                 if (P_hat) {
                     const float4 h = __ldg(reinterpret_cast<const float4*>(P_hat + row) + col);
@@ -313,17 +315,22 @@ extern "C" int clipgp_proto_forward(const float* w, const float* E, int64_t S, i
     return CLIPGP_OK;
 }
 
-extern "C" int clipgp_proto_backward(const float* dP, const float* P_hat, const float* norm, const float* E, int64_t S,
-                                     int64_t C, int64_t T, int64_t D, float* dw, void* stream) {
+extern "C" int clipgp_proto_backward(const float* dP, int64_t dP_stride_s, float dP_scale, const float* P_hat, const float* norm,
+                                     const float* E, int64_t S, int64_t C, int64_t T, int64_t D, float* dw, void* stream) {
     CLIPGP_REQUIRE(S >= 1 && C >= 0 && T >= 1 && T <= CLIPGP_GP_MAX_T, "proto_backward: bad shape");
     CLIPGP_REQUIRE(D >= 4 && D % 4 == 0 && D <= 2048, "proto_backward: D must be a multiple of 4 in [4,2048]");
     if (C == 0) return CLIPGP_OK;
     CLIPGP_REQUIRE(dP && E && dw, "proto_backward: NULL pointer");
     CLIPGP_REQUIRE((P_hat == nullptr) == (norm == nullptr), "proto_backward: P_hat and norm go together");
+    CLIPGP_REQUIRE(dP_stride_s == 0 || dP_stride_s >= C * D, "proto_backward: dP_stride_s must be 0 (broadcast over samples) or >= C*D");
     constexpr int SB = 8;
     const size_t smem = sizeof(float) * SB * (size_t)D;
-    CLIPGP_CUDA(cudaFuncSetAttribute(proto_backward_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CLIPGP_CUDA(cudaFuncSetAttribute(proto_backward_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     dim3 grid((unsigned)C, (unsigned)((S + SB - 1) / SB));
-    proto_backward_kernel<SB><<<grid, kProtoThreads, smem, (cudaStream_t)stream>>>(dP, P_hat, norm, E, S, C, (int)T, (int)D, dw);
+    proto_backward_kernel<SB><<<grid, kProtoThreads, smem, (cudaStream_t)stream>>>(dP, dP_stride_s, dP_scale, P_hat, norm, E, S, C, (int)T, (int)D, dw);
     return check_launch("proto_backward_kernel");
 }

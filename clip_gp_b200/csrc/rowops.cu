@@ -123,6 +123,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     }
 }
 
+__global__ void __launch_bounds__(256) sum_accumulate_kernel(const float* __restrict__ x, int64_t n, float scale, float* out) {
+    __shared__ float red[32];
+    float q = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) q += x[i];
+    const float tot = block_sum(q, red);
+    if (threadIdx.x == 0) atomicAdd(out, tot * scale);
+}
+
 __global__ void increment_kernel(int64_t* p, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) *p += by; }
 
 }  // namespace clipgp
@@ -185,4 +193,14 @@ extern "C" int clipgp_increment(int64_t* counter, int64_t by, void* stream) {
     CLIPGP_REQUIRE(counter, "increment: NULL pointer");
     increment_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, by);
     return check_launch("increment_kernel");
+}
+
+extern "C" int clipgp_sum_accumulate(const float* x, int64_t n, float scale, float* out, void* stream) {
+    CLIPGP_REQUIRE(n >= 0 && out, "sum_accumulate: bad input");
+    if (n == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(x, "sum_accumulate: NULL input");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148) blocks = 148;
+    sum_accumulate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, scale, out);
+    return check_launch("sum_accumulate_kernel");
 }

@@ -1,0 +1,343 @@
+"""Fused GP-Adapter engine: the reference's training step (trainers/adapter.py:328-549, compute_loss
+:387-476) and MC-averaged evaluation (:230-252 + utils/metrics.py) as a fixed sequence of clipgp kernel
+launches on device-resident buffers — no autograd graph, no per-step allocation, CUDA-graph capturable.
+
+One step = GP forward (kernel build, chol64, predictive, chol32, Philox MC sampling, sparsemax, KL) ->
+weighted unit prototypes -> visual projection + normalisation -> logits for every MC sample ->
+per-sample cross-entropy -> adjoints of all of the above -> ||W-I||^2 regulariser -> AdamW on both
+parameter groups (adapter.py:290-311).  The three logging-only GP passes and the per-step full test
+evaluation of the reference are not part of the step.
+
+Multi-GPU: MC samples are sharded across ranks for training (every rank draws its slice of
+the same Philox stream), gradients are summed with ONE all-reduce of the flat gradient buffer; evaluation
+shards the images and all-reduces only the integer counters.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, metrics
+from ._lib import GpArgs, GpBwdArgs, KERNEL_IDS
+from .gp_template_weigher import GaussianProcessTemplateWeighter
+
+
+@dataclass
+class EngineConfig:
+    S_train: int = 10
+    S_eval: int = 10
+    batch_size: int = 128
+    logit_scale: float = 100.0          # logit_scale.exp() of CLIP (adapter.py:241)
+    gp_beta: float = 0.01               # configs/trainers/gp.yaml GP_BETA
+    l2_lambda: float = 0.5              # default.yaml L2_LAMBDA
+    shots: int = 16
+    lr: float = 0.01                    # OPTIM.LR (visual_proj group)
+    gp_lr: float = 1e-3                 # GP_LR (gp_weighter group)
+    weight_decay: float = 0.0
+    betas: tuple = (0.9, 0.999)
+    adam_eps: float = 1e-8
+    loss_mode: str = "per_sample"       # "per_sample" (adapter.py:422-428) | "logit_mean" (taskres.py:268-270)
+    train_visual_proj: bool = True      # FREEZE_VISUAL_PROJ False
+    seed: int = 0
+    rank: int = 0
+    world: int = 1
+
+
+class GPAdapterEngine:
+    def __init__(self, gpw: GaussianProcessTemplateWeighter, cfg: EngineConfig, visual_proj_weight: Optional[torch.Tensor] = None):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        dev = gpw._templates.device
+        if dev.type != "cuda":
+            raise RuntimeError("GPAdapterEngine needs the weighter on a CUDA device (no CPU fallback)")
+        self.dev = dev
+        self.kernel_type = gpw.kernel_type
+        gpw.variational_strategy._maybe_init()
+        self.C, self.T, self.D = gpw.num_classes, gpw.num_templates, gpw.dim
+        self.n, self.d = self.T + 1, gpw.red_dim
+        Cn, T, D, n, d = self.C, self.T, self.D, self.n, self.d
+        # MC samples of this rank: an even split, the first S % world ranks take one more (S=10 over 8 ranks
+        # is 2,2,1,1,1,1,1,1); every rank draws its slice [s_offset, s_offset + S_local) of the same Philox stream
+        if cfg.S_train < cfg.world:
+            raise ValueError(f"S_train={cfg.S_train} < world={cfg.world}: shard the batch instead")
+        base, extra = divmod(cfg.S_train, cfg.world)
+        self.S_local = base + (1 if cfg.rank < extra else 0)
+        self.s_offset = cfg.rank * base + min(cfg.rank, extra)
+        self.E = gpw._templates.detach().contiguous()
+        self.X = gpw._templates_red.detach().contiguous()
+        self.Z = gpw.variational_strategy.inducing_points.detach().clone().contiguous()
+        q = gpw.variational_strategy._variational_distribution
+        raw_ls, raw_os, raw_var = gpw._kernel_raw()
+        # ---- flat parameter / gradient / Adam buffers: [W | z_last | m | Lq | hyper...]
+        segs = [("W", D * D), ("z_last", Cn * d), ("m", Cn * n), ("Lq", Cn * n * n)]
+        if raw_ls is not None: segs.append(("ls", Cn * d))
+        if raw_os is not None: segs.append(("os", Cn))
+        if raw_var is not None: segs.append(("var", Cn))
+        self.offsets: Dict[str, tuple] = {}
+        off = 0
+        for name, sz in segs:
+            self.offsets[name] = (off, sz)
+            off += sz
+        self.n_params = off
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(off + 1, dtype=torch.float32, device=dev)     # last slot: the loss (all-reduced with the grads)
+        self.flat_m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(off, dtype=torch.float32, device=dev)
+        W0 = torch.eye(D, device=dev) if visual_proj_weight is None else visual_proj_weight.detach().to(dev).float()
+        self.p("W").copy_(W0.reshape(-1))
+        self.p("z_last").copy_(self.Z[:, n - 1, :].reshape(-1))
+        self.p("m").copy_(q.variational_mean.detach().reshape(-1))
+        self.p("Lq").copy_(q.chol_variational_covar.detach().reshape(-1))
+        if raw_ls is not None: self.p("ls").copy_(raw_ls.detach().reshape(-1))
+        if raw_os is not None: self.p("os").copy_(raw_os.detach().reshape(-1))
+        if raw_var is not None: self.p("var").copy_(raw_var.detach().reshape(-1))
+        self.mean_x = gpw.mean_module.test_mean(T).detach().contiguous()      # per-class constant: no effect on w
+        # ---- device scalars
+        self.rng_state = torch.tensor([int(cfg.seed), 0], dtype=torch.int64, device=dev)
+        self.adam_step = torch.ones(1, dtype=torch.int64, device=dev)
+        self._alloc_train(cfg.batch_size)
+        self._graph = None
+
+    # ------------------------------------------------------------------ views
+    def p(self, name):
+        o, s = self.offsets[name]
+        return self.flat_p[o:o + s]
+
+    def g(self, name):
+        o, s = self.offsets[name]
+        return self.flat_g[o:o + s]
+
+    @property
+    def loss(self) -> torch.Tensor:
+        return self.flat_g[self.n_params:self.n_params + 1]
+
+    def _ptr(self, buf, name):
+        o, _ = self.offsets[name]
+        return buf.data_ptr() + 4 * o
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_train(self, B):
+        dev, Cn, T, D, n, d, S = self.dev, self.C, self.T, self.D, self.n, self.d, self.S_local
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.B = B
+        self.in_feat = torch.zeros(B, D, **f32)
+        self.in_lab = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.Y = torch.empty(B, D, **f32)
+        self.f_hat = torch.empty(B, D, **f32)
+        self.f_inv = torch.empty(B, **f32)
+        self.w = torch.empty(S, Cn, T, **f32)
+        self.kl = torch.empty(Cn, **f32)
+        self.Lsave = torch.empty(Cn, n, n, dtype=torch.float64, device=dev)
+        self.Asave = torch.empty(Cn, n, T, **f32)
+        self.Rsave = torch.empty(Cn, T, T, **f32)
+        self.status = torch.zeros(Cn, dtype=torch.int32, device=dev)
+        self.P_hat = torch.empty(S, Cn, D, **f32)
+        self.P_norm = torch.empty(S, Cn, **f32)
+        self.P_mean = torch.empty(Cn, D, **f32)
+        self.logits = torch.empty(B, (S if self.cfg.loss_mode == "per_sample" else 1) * Cn, **f32)
+        self.dP = torch.empty((S if self.cfg.loss_mode == "per_sample" else 1), Cn, D, **f32)
+        self.df_hat = torch.empty(B, D, **f32)
+        self.dY = torch.empty(B, D, **f32)
+        self.dw = torch.empty(S, Cn, T, **f32)
+        a = GpArgs()
+        a.kernel_type = KERNEL_IDS[self.kernel_type]
+        a.x_is_z_prefix = 1
+        a.C, a.T, a.n, a.d, a.S = Cn, T, n, d, S
+        a.Z, a.X = self.Z.data_ptr(), self.X.data_ptr()
+        a.raw_lengthscale = self._ptr(self.flat_p, "ls") if "ls" in self.offsets else None
+        a.raw_outputscale = self._ptr(self.flat_p, "os") if "os" in self.offsets else None
+        a.raw_variance = self._ptr(self.flat_p, "var") if "var" in self.offsets else None
+        a.var_mean, a.chol_var = self._ptr(self.flat_p, "m"), self._ptr(self.flat_p, "Lq")
+        a.mean_x = self.mean_x.data_ptr()
+        a.eps = None
+        a.rng_state = self.rng_state.data_ptr()
+        a.s_offset, a.S_total = self.s_offset, self.cfg.S_train
+        a.w, a.kl, a.L, a.A, a.R, a.status = (self.w.data_ptr(), self.kl.data_ptr(), self.Lsave.data_ptr(),
+                                              self.Asave.data_ptr(), self.Rsave.data_ptr(), self.status.data_ptr())
+        self.gp_args = a
+        b = GpBwdArgs()
+        b.dw = self.dw.data_ptr()
+        b.dkl = None
+        b.dkl_scalar = float(self.cfg.gp_beta) / self.cfg.world
+        b.dZ_last = self._ptr(self.flat_g, "z_last")
+        b.draw_lengthscale = self._ptr(self.flat_g, "ls") if "ls" in self.offsets else None
+        b.draw_outputscale = self._ptr(self.flat_g, "os") if "os" in self.offsets else None
+        b.draw_variance = self._ptr(self.flat_g, "var") if "var" in self.offsets else None
+        b.dvar_mean, b.dchol_var, b.dmean_x = self._ptr(self.flat_g, "m"), self._ptr(self.flat_g, "Lq"), None
+        self.gp_bwd_args = b
+
+    # ------------------------------------------------------------------ one training step (launch only)
+    def _launch_step(self):
+        lib, cfg = self.lib, self.cfg
+        st = _lib.stream_ptr(self.dev)
+        ck = _lib.check
+        B, Cn, T, D, S = self.B, self.C, self.T, self.D, self.S_local
+        S_tot = cfg.S_train
+        per_sample = cfg.loss_mode == "per_sample"
+        SC = (S if per_sample else 1) * Cn
+        self.flat_g.zero_()
+        W = self._ptr(self.flat_p, "W")
+        # visual projection + normalisation (adapter.py:419-420)
+        ck(lib.clipgp_gemm_f32(self.in_feat.data_ptr(), D, 1, W, 1, D, self.Y.data_ptr(), D, B, D, D, 1.0, 0, st), "gemm(proj)")
+        ck(lib.clipgp_rownorm_forward(self.Y.data_ptr(), B, D, self.f_hat.data_ptr(), self.f_inv.data_ptr(), None, st), "rownorm")
+        # GP weights + unit prototypes (adapter.py:404, 424-425)
+        ck(lib.clipgp_gp_forward(C.byref(self.gp_args), st), "gp_forward")
+        ck(lib.clipgp_proto_forward(self.w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, self.P_hat.data_ptr(),
+                                    self.P_norm.data_ptr(), None, None if per_sample else self.P_mean.data_ptr(), None, 0, st), "proto_forward")
+        Bmat = self.P_hat if per_sample else self.P_mean
+        # logits (adapter.py:426) -> cross-entropy + gradient (adapter.py:427-428)
+        ck(lib.clipgp_gemm_f32(self.f_hat.data_ptr(), D, 1, Bmat.data_ptr(), 1, D, self.logits.data_ptr(), SC, B, SC, D,
+                               cfg.logit_scale * (1.0 if per_sample else 1.0 / S), 0, st), "gemm(logits)")
+        if per_sample:
+            rows, rpl = B * S, S
+            loss_scale = 1.0 / (B * S_tot)
+        else:
+            rows, rpl = B, 1
+            loss_scale = 1.0 / (B * cfg.world)
+            if cfg.world > 1:
+                raise NotImplementedError("logit_mean loss is not S-sharded (it is not a sum over samples)")
+        ck(lib.clipgp_softmax_ce(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, None, self.loss.data_ptr(),
+                                 loss_scale, self.logits.data_ptr(), Cn, loss_scale, st), "softmax_ce")
+        # adjoints of the logit GEMM: dP_hat = scale * dlogits^T f_hat ; df_hat = scale * dlogits P_hat
+        alpha = cfg.logit_scale * (1.0 if per_sample else 1.0 / S)
+        ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), 1, SC, self.f_hat.data_ptr(), D, 1, self.dP.data_ptr(), D, SC, D, B,
+                               alpha, 0, st), "gemm(dP)")
+        if cfg.train_visual_proj:
+            ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), SC, 1, Bmat.data_ptr(), D, 1, self.df_hat.data_ptr(), D, B, D, SC,
+                                   alpha, 0, st), "gemm(df)")
+            ck(lib.clipgp_rownorm_backward(self.df_hat.data_ptr(), self.f_hat.data_ptr(), self.f_inv.data_ptr(), B, D,
+                                           self.dY.data_ptr(), st), "rownorm_bwd")
+            # dW = dY^T f (+ L2 regulariser, adapter.py:468-476)
+            ck(lib.clipgp_gemm_f32(self.dY.data_ptr(), 1, D, self.in_feat.data_ptr(), D, 1, self._ptr(self.flat_g, "W"), D, D, D, B,
+                                   1.0, 0, st), "gemm(dW)")
+            coef = float(cfg.l2_lambda) / float(cfg.shots) / cfg.world
+            ck(lib.clipgp_l2_identity(W, D, coef, self._ptr(self.flat_g, "W"), self.loss.data_ptr(), st), "l2_identity")
+        # prototype + GP adjoints (dkl_scalar = gp_beta: adapter.py:462-465)
+        if per_sample:
+            ck(lib.clipgp_proto_backward(self.dP.data_ptr(), Cn * D, 1.0, self.P_hat.data_ptr(), self.P_norm.data_ptr(),
+                                         self.E.data_ptr(), S, Cn, T, D, self.dw.data_ptr(), st), "proto_backward")
+        else:
+            # mean over samples happened on unit rows: every sample receives dP_mean (the 1/S is inside alpha)
+            ck(lib.clipgp_proto_backward(self.dP.data_ptr(), 0, 1.0, self.P_hat.data_ptr(), self.P_norm.data_ptr(),
+                                         self.E.data_ptr(), S, Cn, T, D, self.dw.data_ptr(), st), "proto_backward")
+        ck(lib.clipgp_gp_backward(C.byref(self.gp_args), C.byref(self.gp_bwd_args), st), "gp_backward")
+        ck(lib.clipgp_sum_accumulate(self.kl.data_ptr(), Cn, float(cfg.gp_beta) / cfg.world, self.loss.data_ptr(), st), "kl_sum")
+        if cfg.world > 1:
+            torch.distributed.all_reduce(self.flat_g)         # ONE fused all-reduce: gradients + loss
+        if not getattr(self, "skip_update", False):
+            self._launch_update()
+
+    def _launch_update(self):
+        lib, cfg, st = self.lib, self.cfg, _lib.stream_ptr(self.dev)
+        ck = _lib.check
+        oW, nW = self.offsets["W"]
+        b1, b2 = cfg.betas
+        if cfg.train_visual_proj:
+            ck(lib.clipgp_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                                     nW, cfg.lr, b1, b2, cfg.adam_eps, cfg.weight_decay, self.adam_step.data_ptr(), st), "adamw(W)")
+        rest = self.n_params - nW
+        ck(lib.clipgp_adamw_step(self.flat_p.data_ptr() + 4 * nW, self.flat_g.data_ptr() + 4 * nW, self.flat_m.data_ptr() + 4 * nW,
+                                 self.flat_v.data_ptr() + 4 * nW, rest, cfg.gp_lr, b1, b2, cfg.adam_eps, cfg.weight_decay,
+                                 self.adam_step.data_ptr(), st), "adamw(gp)")
+        self.Z[:, self.n - 1, :].copy_(self.p("z_last").view(self.C, self.d))
+        ck(lib.clipgp_increment(self.adam_step.data_ptr(), 1, st), "increment")
+        ck(lib.clipgp_increment(self.rng_state.data_ptr() + 8, 1, st), "increment")
+
+    # ------------------------------------------------------------------ public API
+    def train_step(self, features: torch.Tensor, labels: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
+        """One optimisation step on a [B,D] feature batch (host or device tensors).  Returns the device scalar loss."""
+        if features.shape[0] != self.B:
+            self._alloc_train(features.shape[0])
+            self._graph = None
+        self.in_feat.copy_(features, non_blocking=True)
+        self.in_lab.copy_(labels, non_blocking=True)
+        with torch.cuda.device(self.dev):
+            if use_graph and self.cfg.world == 1:
+                if self._graph is None:
+                    self._capture()
+                self._graph.replay()
+            else:
+                self._launch_step()
+        return self.loss
+
+    def _capture(self):
+        # warm-up outside capture (sets kernel attributes), with all state restored afterwards
+        snap = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.Z.clone(), self.adam_step.clone(),
+                self.rng_state.clone())
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self._launch_step()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.Z, self.adam_step, self.rng_state), snap):
+            dst.copy_(src)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch_step()
+        # the capture did not execute anything; state is still the snapshot
+        self._graph = g
+
+    @torch.no_grad()
+    def eval_prototypes(self, S: Optional[int] = None) -> torch.Tensor:
+        """(1/S) sum_s p_hat_s [C,D] with the current parameters (collapsed form of adapter.py:243-249)."""
+        S = int(S or self.cfg.S_eval)
+        lib, st = self.lib, _lib.stream_ptr(self.dev)
+        Cn, T, D, n = self.C, self.T, self.D, self.n
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        w = torch.empty(S, Cn, T, **f32)
+        a = GpArgs.from_buffer_copy(self.gp_args)
+        a.S, a.s_offset, a.S_total = S, 0, S
+        a.w, a.kl = w.data_ptr(), None
+        a.L = a.A = a.R = None
+        Pm = torch.empty(Cn, D, **f32)
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.clipgp_gp_forward(C.byref(a), st), "gp_forward(eval)")
+            _lib.check(lib.clipgp_proto_forward(w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, None, None, None,
+                                                Pm.data_ptr(), None, 1, st), "proto_forward(eval)")
+        self.last_eval_w = w
+        return Pm
+
+    @torch.no_grad()
+    def eval_logits(self, features: torch.Tensor, prototypes_mean: Optional[torch.Tensor] = None, S: Optional[int] = None):
+        """MC-averaged logits [N,C] = scale * normalize(f W^T) . mean_s p_hat_s  (adapter.py:239-249)."""
+        lib, st = self.lib, _lib.stream_ptr(self.dev)
+        Pm = prototypes_mean if prototypes_mean is not None else self.eval_prototypes(S)
+        f = features.to(self.dev, non_blocking=True).float().contiguous()
+        N, D, Cn = f.shape[0], self.D, self.C
+        Y = torch.empty(N, D, dtype=torch.float32, device=self.dev)
+        logits = torch.empty(N, Cn, dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            for lo in range(0, N, 32768):                      # grid.y limit of the fp32 GEMM
+                hi = min(N, lo + 32768)
+                _lib.check(lib.clipgp_gemm_f32(f[lo:hi].data_ptr(), D, 1, self._ptr(self.flat_p, "W"), 1, D, Y[lo:hi].data_ptr(), D,
+                                               hi - lo, D, D, 1.0, 0, st), "gemm(proj)")
+            _lib.check(lib.clipgp_rownorm_forward(Y.data_ptr(), N, D, Y.data_ptr(), None, None, st), "rownorm")
+            for lo in range(0, N, 32768):
+                hi = min(N, lo + 32768)
+                _lib.check(lib.clipgp_gemm_f32(Y[lo:hi].data_ptr(), D, 1, Pm.data_ptr(), 1, D, logits[lo:hi].data_ptr(), Cn,
+                                               hi - lo, Cn, D, self.cfg.logit_scale, 0, st), "gemm(logits)")
+        return logits
+
+    @torch.no_grad()
+    def evaluate(self, features: torch.Tensor, labels: torch.Tensor, S: Optional[int] = None, n_bins: int = 10):
+        """Accuracy / ECE / AECE of the MC-averaged logits for this rank's shard (metrics.evaluate_calibration)."""
+        logits = self.eval_logits(features, S=S)
+        return metrics.evaluate_calibration(logits, labels.to(self.dev), n_bins)
+
+    # ------------------------------------------------------------------ sync back to the nn.Module
+    @torch.no_grad()
+    def export_to_module(self, gpw: GaussianProcessTemplateWeighter, visual_proj: Optional[torch.nn.Linear] = None):
+        gpw.variational_strategy.inducing_points.copy_(self.Z)
+        q = gpw.variational_strategy._variational_distribution
+        q.variational_mean.copy_(self.p("m").view_as(q.variational_mean))
+        q.chol_variational_covar.copy_(self.p("Lq").view_as(q.chol_variational_covar))
+        raw_ls, raw_os, raw_var = gpw._kernel_raw()
+        if raw_ls is not None: raw_ls.copy_(self.p("ls").view_as(raw_ls))
+        if raw_os is not None: raw_os.copy_(self.p("os").view_as(raw_os))
+        if raw_var is not None: raw_var.copy_(self.p("var").view_as(raw_var))
+        if visual_proj is not None:
+            visual_proj.weight.copy_(self.p("W").view(self.D, self.D))

@@ -192,7 +192,8 @@ class GaussianProcessTemplateWeighter(nn.Module):
     reference does (MultivariateNormal.rsample), ``"philox"`` uses the on-device counter RNG (no eps tensor).
     """
 
-    def __init__(self, text_embeddings: torch.Tensor, cfg: Any, rng: str = "torch", seed: int = 0, **kwargs) -> None:
+    def __init__(self, text_embeddings: torch.Tensor, cfg: Any, rng: str = "torch", seed: int = 0,
+                 lengthscale: Optional[float] = None, **kwargs) -> None:
         super().__init__()
         self.orig_device = text_embeddings.device
         self.num_classes, self.num_templates, self.dim = text_embeddings.shape
@@ -244,7 +245,8 @@ class GaussianProcessTemplateWeighter(nn.Module):
         kernel_type = getattr(adapter_cfg, "gp_kernel_type", "rbf")
         self.kernel_type = kernel_type
         if kernel_type == "rbf":
-            ls_cfg = self._median_lengthscale(templates_red)
+            # `lengthscale` (extension) skips the O((C*T)^2) median heuristic when the caller already knows the value
+            ls_cfg = float(lengthscale) if lengthscale is not None else self._median_lengthscale(templates_red)
             print(f"[GP] Auto length-scale (normalised median): {ls_cfg:.4f}")
             base = _RBFKernel(K, self.red_dim).initialize(lengthscale=ls_cfg)
             self.covar_module = _ScaleKernel(base, K)

@@ -146,8 +146,8 @@ class PrototypesFunction(torch.autograd.Function):
         dP = _c(dP)
         dw = torch.empty(S, Cn, T, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.clipgp_proto_backward(dP.data_ptr(), None, None, E.data_ptr(), S, Cn, T, D, dw.data_ptr(),
-                                                 _lib.stream_ptr(dev)), "clipgp_proto_backward")
+            _lib.check(lib.clipgp_proto_backward(dP.data_ptr(), Cn * D, 1.0, None, None, E.data_ptr(), S, Cn, T, D,
+                                                 dw.data_ptr(), _lib.stream_ptr(dev)), "clipgp_proto_backward")
         return dw, None
 
 

@@ -142,10 +142,12 @@ int clipgp_proto_forward(const float* w, const float* E, int64_t S, int64_t C, i
                          const float* residual, float alpha, float* P_raw, float* P_hat, float* norm,
                          void* P_hat_bf16, float* mean_hat, float* mean_raw, int finish_mean, void* stream);
 
-/* dw [S,C,T] = <dP[s,c,:], E[c,t,:]>.  dP is the gradient of P_raw when P_hat == NULL, else the gradient of the
- * unit rows P_hat (then dP = (dP_hat - P_hat <P_hat,dP_hat>) / norm is applied first; no residual branch). */
-int clipgp_proto_backward(const float* dP, const float* P_hat, const float* norm, const float* E, int64_t S,
-                          int64_t C, int64_t T, int64_t D, float* dw, void* stream);
+/* dw [S,C,T] = <dP[s,c,:], E[c,t,:]>.  Row (s,c) of the upstream gradient is dP_scale * dP[s*dP_stride_s + c*D ...]
+ * (dP_stride_s = C*D for a dense [S,C,D] gradient, 0 to broadcast one [C,D] gradient over the samples, which with
+ * dP_scale = 1/S is the adjoint of the logit-mean heads).  It is the gradient of P_raw when P_hat == NULL, else the
+ * gradient of the unit rows P_hat (then dP = (dP_hat - P_hat <P_hat,dP_hat>) / norm is applied first). */
+int clipgp_proto_backward(const float* dP, int64_t dP_stride_s, float dP_scale, const float* P_hat, const float* norm,
+                          const float* E, int64_t S, int64_t C, int64_t T, int64_t D, float* dw, void* stream);
 
 /* ================================================================================================
  * Cosine-logit heads — adapter.py:230-252 (forward_features), :401-428 (per-sample MC cross-entropy),
@@ -180,6 +182,8 @@ int clipgp_l2_identity(const float* W, int64_t D, float coef, float* dW, float* 
 int clipgp_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                       float weight_decay, const int64_t* step, void* stream);
 int clipgp_increment(int64_t* counter, int64_t by, void* stream);
+/* out[0] += scale * sum(x[0..n))   (e.g. gp_beta * sum_c KL_c, adapter.py:462-465). */
+int clipgp_sum_accumulate(const float* x, int64_t n, float scale, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,110 @@
+"""GPU: the fused GP-Adapter engine (train step + MC-averaged eval) against the CPU oracle step."""
+import copy
+
+import pytest
+import torch
+
+from clip_gp_b200 import synth
+from clip_gp_b200.engine import EngineConfig, GPAdapterEngine
+from clip_gp_b200.gp_template_weigher import GaussianProcessTemplateWeighter
+from oracle import gp as ogp
+from oracle import metrics as om
+from oracle import philox
+from oracle.train_step import OracleAdapter
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+class _Cfg:
+    def __init__(self, kernel, pca):
+        self.adapter = type("A", (), {"gp_pca_dim": pca, "gp_kernel_type": kernel})()
+
+
+def build(kernel, name="small", loss_mode="per_sample", S=4, seed=3):
+    wl = synth.make_workload(name); shp = wl["shape"]
+    torch.manual_seed(0)
+    gpw = GaussianProcessTemplateWeighter(wl["E"], _Cfg(kernel, shp.d)).to("cuda")
+    q = gpw.variational_strategy._variational_distribution
+    m, Lq = synth.trained_like_q(shp.C, shp.T + 1, 5)
+    gpw.variational_strategy._maybe_init()
+    with torch.no_grad():
+        q.variational_mean.copy_(m); q.chol_variational_covar.copy_(Lq)
+    cfg = EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, loss_mode=loss_mode, seed=seed)
+    eng = GPAdapterEngine(gpw, cfg)
+    # the oracle twin
+    st = ogp.build_state(wl["E"], kernel, shp.d)
+    st.inducing_points = gpw.variational_strategy.inducing_points.detach().cpu().clone()
+    st.var_mean, st.chol_var = m.clone(), Lq.clone()
+    raw_ls, raw_os, raw_var = gpw._kernel_raw()
+    if raw_ls is not None: st.kernel.raw_lengthscale = raw_ls.detach().cpu().clone()
+    if raw_os is not None: st.kernel.raw_outputscale = raw_os.detach().cpu().clone()
+    if raw_var is not None: st.kernel.raw_variance = raw_var.detach().cpu().clone()
+    orc = OracleAdapter(st, shp.D, scale=cfg.logit_scale, gp_beta=cfg.gp_beta, l2_lambda=cfg.l2_lambda, shots=cfg.shots,
+                        lr=cfg.lr, gp_lr=cfg.gp_lr, loss_mode=loss_mode)
+    return wl, shp, eng, orc, cfg
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "matern", "linear"])
+@pytest.mark.parametrize("loss_mode", ["per_sample", "logit_mean"])
+def test_step_loss_and_gradients(kernel, loss_mode):
+    wl, shp, eng, orc, cfg = build(kernel, loss_mode=loss_mode)
+    f, y = wl["f_train"][: shp.B], wl["y_train"][: shp.B]
+    eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, cfg.S_train)
+    loss_ref = orc.loss(f, y, eps)
+    loss_ref.backward()
+    eng.skip_update = True
+    loss = eng.train_step(f.cuda(), y.cuda(), use_graph=False)
+    assert float(loss) == pytest.approx(float(loss_ref), rel=1e-3)
+    n = shp.T + 1
+    tol = 2e-3
+    assert rel_err(eng.g("W").view(shp.D, shp.D), orc.W.grad) < tol
+    assert rel_err(eng.g("m").view(shp.C, n), orc.st.var_mean.grad) < tol
+    assert rel_err(eng.g("Lq").view(shp.C, n, n), orc.st.chol_var.grad) < tol
+    if kernel != "matern":      # fp32 oracle gradient of the learnable row is expansion-noise dominated for Matern
+        assert rel_err(eng.g("z_last").view(shp.C, -1), orc.st.inducing_points.grad[:, -1]) < 2e-2
+    if kernel in ("rbf", "matern"): assert rel_err(eng.g("ls").view(shp.C, 1, -1), orc.st.kernel.raw_lengthscale.grad) < tol
+    if kernel == "rbf": assert rel_err(eng.g("os"), orc.st.kernel.raw_outputscale.grad) < tol
+    if kernel == "linear": assert rel_err(eng.g("var").view(shp.C, 1, 1), orc.st.kernel.raw_variance.grad) < tol
+    assert int(eng.status.abs().max()) == 0
+
+
+def test_adamw_update_and_graph_replay_match_eager():
+    wl, shp, eng_a, orc, cfg = build("rbf")
+    _, _, eng_b, _, _ = build("rbf")
+    f, y = wl["f_train"], wl["y_train"]
+    losses_ref = []
+    for it in range(3):
+        fb, yb = f[it * shp.B:(it + 1) * shp.B], y[it * shp.B:(it + 1) * shp.B]
+        eps = philox.eps_tensor(cfg.seed, it, shp.C, shp.T, cfg.S_train)
+        losses_ref.append(orc.step(fb, yb, eps))
+        la = float(eng_a.train_step(fb.cuda(), yb.cuda(), use_graph=False))
+        lb = float(eng_b.train_step(fb.cuda(), yb.cuda(), use_graph=True))
+        assert la == pytest.approx(losses_ref[-1], rel=2e-3)
+        assert lb == pytest.approx(la, rel=1e-5)
+    assert torch.allclose(eng_a.flat_p, eng_b.flat_p, rtol=1e-5, atol=1e-6)
+    # parameters after three AdamW steps (sign-like first steps: compare with an absolute budget of one lr step)
+    W = eng_a.p("W").view(shp.D, shp.D).cpu()
+    assert float((W - orc.W.detach()).abs().max()) < 0.5 * cfg.lr
+    m = eng_a.p("m").view(shp.C, -1).cpu()
+    bad = ((m - orc.st.var_mean.detach()).abs() > 0.5 * cfg.gp_lr).float().mean()
+    assert float(bad) < 0.01
+    assert int(eng_a.adam_step) == 4 and int(eng_a.rng_state[1]) == 3
+    assert torch.equal(eng_a.Z[:, :-1].cpu(), orc.st.inducing_points.detach()[:, :-1])     # frozen rows untouched
+
+
+def test_eval_matches_oracle_logit_mean_and_metrics():
+    wl, shp, eng, orc, cfg = build("rbf", S=6)
+    f, y = wl["f_test"], wl["y_test"]
+    eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, 6)
+    logits_ref = orc.eval_logits(f, eps)                       # materialised [B,S,C] mean (adapter.py:247-249)
+    logits = eng.eval_logits(f.cuda(), S=6)                    # collapsed: one GEMM against mean_s p_hat_s
+    assert float((logits.cpu() - logits_ref).abs().max()) < 1e-3 * float(logits_ref.abs().max())
+    res = eng.evaluate(f.cuda(), y.cuda(), S=6)
+    assert res["top1_count"] == om.top1_count(logits_ref, y)
+    e, b = om.compute_ece_with_bins(logits_ref, y)
+    conf, _, _ = om.confidence(logits_ref, y)
+    gap = float((conf[:, None] - torch.linspace(0, 1, 11)[None]).abs().min())
+    assert res["calibration"]["bin_count"] == b["bin_count"], f"min |conf-boundary| = {gap:.2e}"
+    assert res["ece"] == pytest.approx(e, rel=1e-3, abs=1e-3)
+    assert res["aece"] == pytest.approx(om.compute_aece(logits_ref, y), rel=1e-3, abs=1e-3)
