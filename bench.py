@@ -430,6 +430,16 @@ def cpu_baseline(wl, shp, S, ls, budget_s=20.0):
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly ONE JSON line; everything else (build log, module prints) goes to stderr
+    _real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001
+        if "file" not in kw:
+            kw["file"] = _real_stdout
+        _print(*args, **kw)
+
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -16,7 +16,7 @@ template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(GTHREADS) gemm_f32_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                             const float* __restrict__ B, int64_t sbk, int64_t sbn,
                                                             float* __restrict__ Cm, int64_t ldc, int M, int N, int K,
-                                                            float alpha, int accumulate) {
+                                                            float alpha, int accumulate, int k_per_split) {
     __shared__ __align__(16) float As[GBK][GBM + 4];
     __shared__ __align__(16) float Bs[GBK][GBN + 4];
     const int tid = threadIdx.x;
@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(GTHREADS) gemm_f32_kernel(const float* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < K; k0 += GBK) {
+    const int k_begin = blockIdx.z * k_per_split;
+    const int k_end = min(K, k_begin + k_per_split);
+    for (int k0 = k_begin; k0 < k_end; k0 += GBK) {
         // ---- load A tile [GBM x GBK] -> As[k][m]
 #pragma unroll
         for (int it = 0; it < (GBM * GBK) / GTHREADS; ++it) {
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(GTHREADS) gemm_f32_kernel(const float* __restr
             int m, k;
             if (A_KMAJOR) { k = idx % GBK; m = idx / GBK; } else { m = idx % GBM; k = idx / GBM; }
             const int gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < M && gk < K) ? __ldg(A + (int64_t)gm * sam + (int64_t)gk * sak) : 0.f;
+            As[k][m] = (gm < M && gk < k_end) ? __ldg(A + (int64_t)gm * sam + (int64_t)gk * sak) : 0.f;
         }
 #pragma unroll
         for (int it = 0; it < (GBN * GBK) / GTHREADS; ++it) {
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(GTHREADS) gemm_f32_kernel(const float* __restr
             int n, k;
             if (B_KMAJOR) { k = idx % GBK; n = idx / GBK; } else { n = idx % GBN; k = idx / GBN; }
             const int gn = n0 + n, gk = k0 + k;
-            Bs[k][n] = (gn < N && gk < K) ? __ldg(B + (int64_t)gk * sbk + (int64_t)gn * sbn) : 0.f;
+            Bs[k][n] = (gn < N && gk < k_end) ? __ldg(B + (int64_t)gk * sbk + (int64_t)gn * sbn) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -73,7 +75,8 @@ __global__ void __launch_bounds__(GTHREADS) gemm_f32_kernel(const float* __restr
             if (gn < N) {
                 float* p = Cm + (int64_t)gm * ldc + gn;
                 const float v = alpha * acc[i][j];
-                *p = accumulate ? (*p + v) : v;
+                if (gridDim.z > 1) atomicAdd(p, v);            // split-K: C was zeroed (or holds the accumulate base)
+                else *p = accumulate ? (*p + v) : v;
             }
         }
     }
@@ -96,10 +99,27 @@ extern "C" int clipgp_gemm_f32(const float* A, int64_t sam, int64_t sak, const f
     dim3 grid((unsigned)((N + GBN - 1) / GBN), (unsigned)((M + GBM - 1) / GBM));
     CLIPGP_REQUIRE(grid.y <= 65535, "gemm_f32: M too large for one launch (chunk the rows)");
     cudaStream_t st = (cudaStream_t)stream;
+    // split-K when the output grid cannot fill the SMs (skinny adjoint GEMMs: K = S*C or B is the long axis)
+    int splits = 1;
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    if (tiles < num_sms() && K >= 8 * GBK) {
+        splits = (int)((2 * num_sms() + tiles - 1) / tiles);
+        const int max_splits = (int)(K / (4 * GBK));
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 64) splits = 64;
+        if (splits < 1) splits = 1;
+    }
+    int k_per_split = (int)K;
+    if (splits > 1) {
+        k_per_split = (int)(((K + splits - 1) / splits + GBK - 1) / GBK * GBK);
+        splits = (int)((K + k_per_split - 1) / k_per_split);
+        grid.z = (unsigned)splits;
+        if (!accumulate) CLIPGP_CUDA(cudaMemset2DAsync(Cm, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+    }
     const bool ak = (sak == 1), bk = (sbk == 1);
-    if (ak && bk) gemm_f32_kernel<true, true><<<grid, GTHREADS, 0, st>>>(A, sam, sak, B, sbk, sbn, Cm, ldc, (int)M, (int)N, (int)K, alpha, accumulate);
-    else if (ak && !bk) gemm_f32_kernel<true, false><<<grid, GTHREADS, 0, st>>>(A, sam, sak, B, sbk, sbn, Cm, ldc, (int)M, (int)N, (int)K, alpha, accumulate);
-    else if (!ak && bk) gemm_f32_kernel<false, true><<<grid, GTHREADS, 0, st>>>(A, sam, sak, B, sbk, sbn, Cm, ldc, (int)M, (int)N, (int)K, alpha, accumulate);
-    else gemm_f32_kernel<false, false><<<grid, GTHREADS, 0, st>>>(A, sam, sak, B, sbk, sbn, Cm, ldc, (int)M, (int)N, (int)K, alpha, accumulate);
+    if (ak && bk) gemm_f32_kernel<true, true><<<grid, GTHREADS, 0, st>>>(A, sam, sak, B, sbk, sbn, Cm, ldc, (int)M, (int)N, (int)K, alpha, accumulate, k_per_split);
+    else if (ak && !bk) gemm_f32_kernel<true, false><<<grid, GTHREADS, 0, st>>>(A, sam, sak, B, sbk, sbn, Cm, ldc, (int)M, (int)N, (int)K, alpha, accumulate, k_per_split);
+    else if (!ak && bk) gemm_f32_kernel<false, true><<<grid, GTHREADS, 0, st>>>(A, sam, sak, B, sbk, sbn, Cm, ldc, (int)M, (int)N, (int)K, alpha, accumulate, k_per_split);
+    else gemm_f32_kernel<false, false><<<grid, GTHREADS, 0, st>>>(A, sam, sak, B, sbk, sbn, Cm, ldc, (int)M, (int)N, (int)K, alpha, accumulate, k_per_split);
     return check_launch("gemm_f32_kernel");
 }

@@ -1,0 +1,382 @@
+// Tensor-core path of the logit / projection / cache-affinity contractions:  D[M,N] = alpha * A[M,K] B[N,K]^T with
+// bf16 operands (K-major, i.e. plain row-major [rows, K]) and fp32 accumulation in TMEM.
+//
+//   * operands are staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a 4-stage shared-memory ring,
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x 256 x 16), accumulators live in TMEM
+//     (2 x 256 columns, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1),
+//   * four epilogue warps read the accumulator with tcgen05.ld (thread <-> TMEM lane <-> output row) and either
+//     store alpha*D (EPI_STORE) or reduce it on the fly (EPI_ROWSTATS): running softmax max / arg-max / sum-exp per
+//     row across all class tiles -> confidence, hit flag, top-1 count and the ECE histogram (utils/metrics.py:71-82),
+//     so the [N_img, C] logits of the eval path never touch HBM.
+//   * `Ka` < K makes A wrap along K (A column = k mod Ka): with B = [p_hat_1 | ... | p_hat_S] along K this
+//     accumulates sum_s f_hat . p_hat_s in TMEM, i.e. the MC-averaged logits of adapter.py:247-249 as ONE GEMM of
+//     2*N*S*C*D flops without materialising [N,S,C].
+//
+// Persistent kernel: grid = min(#SMs, #work items); warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator,
+// warps 2..5 = epilogue.  Roofline: tensor pipe (bf16) for large M; HBM/latency for M = 128.
+#include <cuda.h>
+#include <float.h>
+
+#include "common.cuh"
+
+namespace clipgp {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;
+constexpr int ACC_COLS = BN;       // fp32 accumulator columns per tile
+constexpr int TMEM_COLS = 512;     // two accumulator stages
+
+constexpr int EPI_STORE = 0, EPI_ROWSTATS = 1;
+
+struct Params {
+    int M, N, K, Ka;
+    int num_m, num_n, num_k;
+    int n_per_item;             // consecutive n tiles one work item covers (num_n for ROWSTATS, 1 for STORE)
+    int mode;
+    float alpha;
+    float* C; long long ldc;    // STORE target / optional logits copy in ROWSTATS
+    const long long* labels; float* conf; int* pred; unsigned char* correct;
+    const float* boundaries; int n_bins;
+    long long* bin_count; unsigned long long* bin_conf_fx; long long* bin_correct; long long* top1;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
+// [0,14), LBO = 1 (ignored for swizzled K-major) in [16,30), SBO = 1024 B >> 4 (8 rows x 128 B) in [32,46),
+// version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major,
+// N >> 3 in [17,23), M >> 4 in [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ unsigned long long conf_to_fx(float c) { return (unsigned long long)((double)c * 1099511627776.0); }
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_b, const Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_b[CLIPGP_MAX_BINS + 1];
+    __shared__ unsigned int s_cnt[CLIPGP_MAX_BINS], s_cor[CLIPGP_MAX_BINS], s_top1;
+    __shared__ unsigned long long s_fx[CLIPGP_MAX_BINS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    }
+    if (p.mode == EPI_ROWSTATS) {
+        for (int i = threadIdx.x; i < CLIPGP_MAX_BINS; i += blockDim.x) { s_cnt[i] = 0; s_cor[i] = 0; s_fx[i] = 0ull; }
+        for (int i = threadIdx.x; i <= p.n_bins; i += blockDim.x) s_b[i] = p.boundaries ? p.boundaries[i] : 0.f;
+        if (threadIdx.x == 0) s_top1 = 0;
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int groups = p.num_n / p.n_per_item;              // work items per m block
+    const int num_items = p.num_m * groups;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int m_blk = item / groups, n_first = (item - m_blk * groups) * p.n_per_item;
+                for (int nn = 0; nn < p.n_per_item; ++nn) {
+                    const int n_blk = n_first + nn;
+                    for (int kb = 0; kb < p.num_k; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        unsigned char* sa = smem + stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(sa, &map_a, &full_bar[stage], (kb * BK) % p.Ka, m_blk * BM);
+                        tma_load_2d(sa + A_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                for (int nn = 0; nn < p.n_per_item; ++nn) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
+                    for (int kb = 0; kb < p.num_k; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k)
+                            umma_bf16(tmem_d, adesc + (uint64_t)(k * (UK * 2 / 16)), bdesc + (uint64_t)(k * (UK * 2 / 16)), kIdesc,
+                                      (kb | k) != 0 ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
+                        if (kb == p.num_k - 1) umma_commit(&tmem_full[acc]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================== epilogue (4 warps; thread <-> TMEM lane <-> row)
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int m_blk = item / groups, n_first = (item - m_blk * groups) * p.n_per_item;
+            const int row = m_blk * BM + q * 32 + lane;
+            float run_m = -FLT_MAX, run_s = 0.f; int run_am = 0x7fffffff;
+            for (int nn = 0; nn < p.n_per_item; ++nn) {
+                const int n_blk = n_first + nn;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int col0 = n_blk * BN + c0;
+                    if (col0 >= p.N) break;                              // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)c0, r);
+                    const int ncols = min(32, p.N - col0);
+                    if (p.C != nullptr && row < p.M) {
+                        float* dst = p.C + (long long)row * p.ldc + col0;
+                        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(p.alpha * __uint_as_float(r[j]), p.alpha * __uint_as_float(r[j + 1]),
+                                                                                   p.alpha * __uint_as_float(r[j + 2]), p.alpha * __uint_as_float(r[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < ncols) dst[j] = p.alpha * __uint_as_float(r[j]);
+                        }
+                    }
+                    if (p.mode == EPI_ROWSTATS) {
+                        // chunk max / arg-max (lowest index on ties), then one rescale of the running sum
+                        float cm = -FLT_MAX; int cam = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = p.alpha * __uint_as_float(r[j]);
+                            if (j < ncols && v > cm) { cm = v; cam = j; }
+                        }
+                        if (cm > run_m) {
+                            run_s *= exp2f((run_m - cm) * 1.4426950408889634f);
+                            run_m = cm; run_am = col0 + cam;
+                        }
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = p.alpha * __uint_as_float(r[j]);
+                            if (j < ncols) s += exp2f((v - run_m) * 1.4426950408889634f);
+                        }
+                        run_s += s;
+                    }
+                }
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (p.mode == EPI_ROWSTATS && row < p.M) {
+                const float cf = 1.0f / run_s;
+                const int ok = (p.labels != nullptr) ? ((long long)run_am == p.labels[row]) : 0;
+                if (p.conf) p.conf[row] = cf;
+                if (p.pred) p.pred[row] = run_am;
+                if (p.correct) p.correct[row] = (unsigned char)ok;
+                if (ok) atomicAdd(&s_top1, 1u);
+                if (p.bin_count != nullptr) {
+                    int bi = -1;
+                    for (int i = 0; i < p.n_bins; ++i)
+                        if (cf > s_b[i] && cf <= s_b[i + 1]) { bi = i; break; }
+                    if (bi >= 0) { atomicAdd(&s_cnt[bi], 1u); atomicAdd(&s_cor[bi], (unsigned int)ok); atomicAdd(&s_fx[bi], conf_to_fx(cf)); }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (p.mode == EPI_ROWSTATS) {
+        if (p.bin_count != nullptr)
+            for (int i = threadIdx.x; i < p.n_bins; i += blockDim.x)
+                if (s_cnt[i]) {
+                    atomicAdd((unsigned long long*)&p.bin_count[i], (unsigned long long)s_cnt[i]);
+                    atomicAdd(&p.bin_conf_fx[i], s_fx[i]);
+                    atomicAdd((unsigned long long*)&p.bin_correct[i], (unsigned long long)s_cor[i]);
+                }
+        if (p.top1 != nullptr && threadIdx.x == 0 && s_top1) atomicAdd((unsigned long long*)p.top1, (unsigned long long)s_top1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// bf16 row-major [rows, cols] -> 2D tensor map with a [box_rows, 64] box, 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver"); return CLIPGP_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc_gemm: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return CLIPGP_ERR_CUDA; }
+    return CLIPGP_OK;
+}
+
+static int launch(const void* A, long long M, long long Ka, const void* B, long long N, long long K, Params& p, cudaStream_t st) {
+    CLIPGP_REQUIRE(M >= 1 && N >= 1 && K >= 1 && Ka >= 1, "tc_gemm: empty problem");
+    CLIPGP_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "tc_gemm: size too large");
+    CLIPGP_REQUIRE(A && B, "tc_gemm: NULL operand");
+    CLIPGP_REQUIRE(Ka % 8 == 0 && K % 8 == 0, "tc_gemm: K (%lld) and Ka (%lld) must be multiples of 8 (16-byte TMA row pitch)", K, Ka);
+    CLIPGP_REQUIRE(K % Ka == 0 && (Ka == K || Ka % BK == 0), "tc_gemm: K must be a multiple of Ka, and Ka a multiple of %d when A wraps", BK);
+    CLIPGP_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) == 0, "tc_gemm: operands must be 16-byte aligned");
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, A, M, Ka, BM);
+    if (rc != CLIPGP_OK) return rc;
+    rc = make_map(&mb, B, N, K, BN);
+    if (rc != CLIPGP_OK) return rc;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.Ka = (int)Ka;
+    p.num_m = (int)((M + BM - 1) / BM); p.num_n = (int)((N + BN - 1) / BN); p.num_k = (int)((K + BK - 1) / BK);
+    p.n_per_item = (p.mode == EPI_ROWSTATS) ? p.num_n : 1;
+    const int items = p.num_m * (p.num_n / p.n_per_item);
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CLIPGP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int grid = items < num_sms() ? items : num_sms();
+    tc_gemm_kernel<<<grid, THREADS, smem, st>>>(ma, mb, p);
+    return check_launch("tc_gemm_kernel");
+}
+
+}  // namespace tc
+}  // namespace clipgp
+
+using namespace clipgp;
+
+extern "C" int clipgp_tc_gemm_store(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K,
+                                    float alpha, float* C, int64_t ldc, void* stream) {
+    CLIPGP_REQUIRE(C != nullptr && ldc >= N, "tc_gemm_store: bad output");
+    tc::Params p = {};
+    p.mode = tc::EPI_STORE; p.alpha = alpha; p.C = C; p.ldc = ldc;
+    return tc::launch(A_bf16, M, Ka, B_bf16, N, K, p, (cudaStream_t)stream);
+}
+
+extern "C" int clipgp_tc_logits_calibration(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K,
+                                            float alpha, const int64_t* labels, float* conf, int32_t* pred, uint8_t* correct,
+                                            const float* boundaries, int n_bins, int64_t* bin_count,
+                                            unsigned long long* bin_conf_fx, int64_t* bin_correct, int64_t* top1,
+                                            float* logits_out, int64_t ld_logits, void* stream) {
+    if (M == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(n_bins >= 0 && n_bins <= CLIPGP_MAX_BINS, "tc_logits_calibration: n_bins must be in [0,%d]", CLIPGP_MAX_BINS);
+    CLIPGP_REQUIRE(bin_count == nullptr || (boundaries && bin_conf_fx && bin_correct && n_bins >= 1), "tc_logits_calibration: histogram outputs incomplete");
+    CLIPGP_REQUIRE(labels != nullptr || (correct == nullptr && top1 == nullptr && bin_count == nullptr), "tc_logits_calibration: labels is NULL");
+    CLIPGP_REQUIRE(logits_out == nullptr || ld_logits >= N, "tc_logits_calibration: ld_logits < N");
+    tc::Params p = {};
+    p.mode = tc::EPI_ROWSTATS; p.alpha = alpha; p.C = logits_out; p.ldc = ld_logits;
+    p.labels = reinterpret_cast<const long long*>(labels); p.conf = conf; p.pred = pred; p.correct = correct;
+    p.boundaries = boundaries; p.n_bins = n_bins;
+    p.bin_count = reinterpret_cast<long long*>(bin_count); p.bin_conf_fx = bin_conf_fx;
+    p.bin_correct = reinterpret_cast<long long*>(bin_correct); p.top1 = reinterpret_cast<long long*>(top1);
+    return tc::launch(A_bf16, M, Ka, B_bf16, N, K, p, (cudaStream_t)stream);
+}

@@ -53,25 +53,37 @@ __device__ float kernel_adjoint_block(const float* dK, int ld, float* raw, const
         const float* tB = same ? tileA : tileB;
         const int k = k0 + kk;
         if (k < d && part < nparts) {
-            float qk = 0.f, dz = 0.f;
-            for (int i = part; i < nA; i += nparts) {
-                const float ui = tileA[i * KCP + kk];
-                for (int j = 0; j < nB; ++j) {
-                    const float wv = raw[i * ld + j];
-                    const float uj = tB[j * KCP + kk];
-                    if (dot) {
-                        if (i == rowA) dz = fmaf(wv, uj, dz);
-                        if (j == rowB) dz = fmaf(wv, ui, dz);
-                    } else {
-                        const float df = ui - uj;
-                        qk = fmaf(wv * df, df, qk);
-                        if (i == rowA) dz = fmaf(wv, df, dz);
-                        if (j == rowB) dz = fmaf(-wv, df, dz);
+            if (!dot) {
+                float qk = 0.f;
+                for (int i = part; i < nA; i += nparts) {
+                    const float ui = tileA[i * KCP + kk];
+                    const float* wrow = raw + i * ld;
+                    for (int j = 0; j < nB; ++j) {
+                        const float df = ui - tB[j * KCP + kk];
+                        qk = fmaf(wrow[j] * df, df, qk);
                     }
                 }
+                atomicAdd(&q[k], qk);
             }
-            if (!dot) { atomicAdd(&q[k], qk); dz *= 2.f * invls[k]; }
-            if (rowA >= 0 || rowB >= 0) atomicAdd(&dzl[k], dz);
+            if (part == 0 && (rowA >= 0 || rowB >= 0)) {       // the one learnable row: O(nA + nB) per column
+                float dz = 0.f;
+                if (rowA >= 0) {
+                    const float ui = tileA[rowA * KCP + kk];
+                    for (int j = 0; j < nB; ++j) {
+                        const float uj = tB[j * KCP + kk];
+                        dz = fmaf(raw[rowA * ld + j], dot ? uj : (ui - uj), dz);
+                    }
+                }
+                if (rowB >= 0) {
+                    const float uj = tB[rowB * KCP + kk];
+                    for (int i = 0; i < nA; ++i) {
+                        const float ui = tileA[i * KCP + kk];
+                        dz = fmaf(raw[i * ld + rowB], dot ? ui : (uj - ui), dz);
+                    }
+                }
+                if (!dot) dz *= 2.f * invls[k];
+                dzl[k] += dz;
+            }
         }
     }
     __syncthreads();
@@ -263,11 +275,8 @@ __global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_a
         float* tileA = reinterpret_cast<float*>(smem + Y.p_tiles);
         float* tileB = tileA + (size_t)pad4(n) * KCP;
         int alias = 0;
-        if (a.x_is_z_prefix) {
-            int eq = 1;
-            for (int idx = tid; idx < T * d; idx += blockDim.x) eq &= (__ldg(Xc + idx) == __ldg(Zc + idx));
-            alias = __syncthreads_and(eq);
-        }
+        if (a.x_is_z_prefix == 2) alias = 1;
+        else if (a.x_is_z_prefix == 1) alias = rows_identical(Xc, Zc, T * d);
         float damp = 0.f;
         if (alias) {
             // one block: K(Z,Z) carries dK_ZZ + [dK_ZX | 0] + [[dK_XX, 0],[0, 0]]

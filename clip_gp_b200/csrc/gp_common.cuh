@@ -8,7 +8,7 @@ namespace clipgp {
 namespace gp {
 
 constexpr int kThreads = 128;  // threads per class CTA
-constexpr int KC = 64;         // feature-dim chunk streamed through shared memory
+constexpr int KC = 32;         // feature-dim chunk streamed through shared memory
 constexpr int KCP = KC + 1;    // padded row stride of a chunk tile (conflict-free row access)
 constexpr int kMaxTiles = 3;   // 4x4 register tiles per thread: 3*128 >= ceil(65/4)^2 = 289
 
@@ -16,8 +16,36 @@ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
 
 // Copy columns [k0, k0+KC) of a row-major [rows, d] global matrix into a [rows_pad][KCP] tile, optionally
 // scaled per column (inverse length-scales).  Rows >= rows and columns >= d are zero-filled.
+// Loads are issued four-deep per thread (128-bit when d % 4 == 0) before any is consumed, so a thread keeps
+// 64 bytes in flight instead of stalling on every element.
 __device__ __forceinline__ void load_chunk(float* __restrict__ tile, const float* __restrict__ G, int rows,
                                            int rows_pad, int d, int k0, const float* __restrict__ col_scale) {
+    constexpr int V = KC / 4;
+    if (((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15u) == 0)) {
+        const int total = rows_pad * V;
+        for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * blockDim.x;
+                const int r = idx / V, k = k0 + (idx - r * V) * 4;
+                v[u] = (idx < total && r < rows && k < d) ? __ldg(reinterpret_cast<const float4*>(G + (size_t)r * d + k))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * blockDim.x;
+                if (idx < total) {
+                    const int r = idx / V, q = (idx - r * V) * 4, k = k0 + q;
+                    float4 x = v[u];
+                    if (col_scale && k < d) { x.x *= col_scale[k]; x.y *= col_scale[k + 1]; x.z *= col_scale[k + 2]; x.w *= col_scale[k + 3]; }
+                    float* t = tile + r * KCP + q;
+                    t[0] = x.x; t[1] = x.y; t[2] = x.z; t[3] = x.w;
+                }
+            }
+        }
+        return;
+    }
     for (int idx = threadIdx.x; idx < rows_pad * KC; idx += blockDim.x) {
         const int r = idx / KC, k = idx - r * KC;
         float v = 0.f;
@@ -27,6 +55,31 @@ __device__ __forceinline__ void load_chunk(float* __restrict__ tile, const float
         }
         tile[r * KCP + k] = v;
     }
+}
+
+// All-threads test X[0 .. count) == Z[0 .. count) (bitwise as floats), with four 128-bit loads in flight per array.
+__device__ __forceinline__ int rows_identical(const float* __restrict__ X, const float* __restrict__ Z, int count) {
+    int eq = 1;
+    if (((count & 3) == 0) && (((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Z)) & 15u) == 0)) {
+        const int c4 = count >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(X);
+        const float4* z4 = reinterpret_cast<const float4*>(Z);
+        for (int base = threadIdx.x; base < c4; base += 4 * blockDim.x) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * blockDim.x;
+                a[u] = (i < c4) ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                b[u] = (i < c4) ? __ldg(z4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                eq &= (a[u].x == b[u].x) & (a[u].y == b[u].y) & (a[u].z == b[u].z) & (a[u].w == b[u].w);
+        }
+    } else {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) eq &= (__ldg(X + i) == __ldg(Z + i));
+    }
+    return __syncthreads_and(eq);
 }
 
 // acc[t] += sum_k op(a_ik, b_jk) over one chunk for this thread's 4x4 tiles.
@@ -116,24 +169,22 @@ __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ 
 template <typename T>
 __device__ bool block_cholesky(T* __restrict__ A, int n, int ld, T* __restrict__ invd) {
     bool fail = false;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __syncthreads();
     for (int j = 0; j < n; ++j) {
-        __syncthreads();
+        // every thread derives the pivot itself (broadcast read); column j below the diagonal is scaled on the fly
         const T ajj = A[j * ld + j];
         if (!(ajj > (T)0)) fail = true;
-        const T dj = sqrt(ajj);
-        const T inv = (T)1 / dj;
-        __syncthreads();
-        for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) A[i * ld + j] *= inv;
-        if (threadIdx.x == 0) { A[j * ld + j] = dj; invd[j] = inv; }
-        __syncthreads();
-        const int m = n - j - 1;
-        for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
-            const int r = idx / m, c = idx - r * m;
-            if (c <= r) {
-                const int i = j + 1 + r, k = j + 1 + c;
-                A[i * ld + k] -= A[i * ld + j] * A[k * ld + j];
-            }
+        const T inv = (T)1 / sqrt(ajj);
+        // trailing update with the scaled column: A[i][k] -= (A[i][j] inv) (A[k][j] inv), j < k <= i
+        for (int i = j + 1 + warp; i < n; i += nwarps) {
+            const T lij = A[i * ld + j] * inv;
+            for (int k = j + 1 + lane; k <= i; k += 32) A[i * ld + k] -= lij * (A[k * ld + j] * inv);
         }
+        __syncthreads();
+        // column j is final now; later columns never touch it again, so no second barrier is needed here
+        for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) A[i * ld + j] *= inv;
+        if (threadIdx.x == 0) { A[j * ld + j] = ajj * inv; invd[j] = inv; }
     }
     __syncthreads();
     return fail;

@@ -131,6 +131,28 @@ __global__ void __launch_bounds__(256) sum_accumulate_kernel(const float* __rest
     if (threadIdx.x == 0) atomicAdd(out, tot * scale);
 }
 
+// fp32 -> bf16 operand for the tensor-core GEMMs.  mode 0: out[r, K] = bf16(x).  Split modes emulate fp32 products
+// with three bf16 MMAs (x = hi + lo, a.b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi, relative error ~2^-16):
+// mode 1 (A side): out[r, 3K] = [hi | hi | lo];  mode 2 (B side): out[r, 3K] = [hi | lo | hi].
+// out row r, segment g, column k lives at out[r*out_ld + g*seg_stride + k] (seg_stride = K for the layouts above;
+// callers that interleave MC samples along K pass their own strides).
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, int64_t R, int K, int64_t ldx,
+                                                        __nv_bfloat16* __restrict__ out, int64_t out_ld, int64_t seg_stride, int mode) {
+    const int64_t total = R * (int64_t)K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K; const int k = (int)(i - r * K);
+        const float v = x[r * ldx + k];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        __nv_bfloat16* o = out + r * out_ld + k;
+        o[0] = hi;
+        if (mode != 0) {
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            o[seg_stride] = (mode == 1) ? hi : lo;
+            o[2 * seg_stride] = (mode == 1) ? lo : hi;
+        }
+    }
+}
+
 __global__ void increment_kernel(int64_t* p, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) *p += by; }
 
 }  // namespace clipgp
@@ -203,4 +225,17 @@ extern "C" int clipgp_sum_accumulate(const float* x, int64_t n, float scale, flo
     if (blocks > 148) blocks = 148;
     sum_accumulate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, scale, out);
     return check_launch("sum_accumulate_kernel");
+}
+
+extern "C" int clipgp_cast_bf16(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld, int64_t seg_stride,
+                                int mode, void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && K >= 1 && K < (1ll << 31) && ldx >= K, "cast_bf16: bad shape");
+    CLIPGP_REQUIRE(mode >= 0 && mode <= 2, "cast_bf16: mode must be 0 (plain), 1 (A split) or 2 (B split)");
+    if (R == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(x && out, "cast_bf16: NULL pointer");
+    int64_t blocks = (R * K + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)K, ldx, (__nv_bfloat16*)out, out_ld, seg_stride, mode);
+    return check_launch("cast_bf16_kernel");
 }

@@ -144,7 +144,7 @@ class GPAdapterEngine:
         self.dw = torch.empty(S, Cn, T, **f32)
         a = GpArgs()
         a.kernel_type = KERNEL_IDS[self.kernel_type]
-        a.x_is_z_prefix = 1
+        a.x_is_z_prefix = 2     # the engine never writes the frozen template rows of Z (only z_last is scattered back)
         a.C, a.T, a.n, a.d, a.S = Cn, T, n, d, S
         a.Z, a.X = self.Z.data_ptr(), self.X.data_ptr()
         a.raw_lengthscale = self._ptr(self.flat_p, "ls") if "ls" in self.offsets else None

@@ -78,7 +78,8 @@ int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64_t N, const
  * ================================================================================================ */
 typedef struct clipgp_gp_args {
     int32_t kernel_type;          /* CLIPGP_KERNEL_* */
-    int32_t x_is_z_prefix;        /* 1: caller guarantees X[c] == Z[c,:T] bit-for-bit -> only K_ZZ is evaluated */
+    int32_t x_is_z_prefix;        /* X[c] == Z[c,:T] bit-for-bit lets the kernel evaluate only K_ZZ: 0 never assume it,
+                                     1 test it on the device per class, 2 the caller guarantees it (no test) */
     int64_t C, T, n, d, S;        /* classes, templates, inducing points (T+1), kernel input dim, MC samples */
     const float* Z;               /* [C,n,d] variational_strategy.inducing_points */
     const float* X;               /* [C,T,d] _templates_red (test inputs) */
@@ -184,6 +185,30 @@ int clipgp_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, f
 int clipgp_increment(int64_t* counter, int64_t by, void* stream);
 /* out[0] += scale * sum(x[0..n))   (e.g. gp_beta * sum_c KL_c, adapter.py:462-465). */
 int clipgp_sum_accumulate(const float* x, int64_t n, float scale, float* out, void* stream);
+
+/* ================================================================================================
+ * Tensor-core (tcgen05 / TMEM / TMA) path of the same contractions: D[M,N] = alpha * A[M,K] B[N,K]^T, bf16 operands in
+ * plain row-major [rows, K] (K % 8 == 0, 16-byte aligned), fp32 accumulation.  Ka <= K with K % Ka == 0 makes A wrap
+ * along K (A column = k mod Ka, Ka % 64 == 0): with B = [p_hat_1 | ... | p_hat_S] along K the MC sum over samples
+ * (adapter.py:247-249) accumulates inside TMEM.  fp32-grade products: feed the split operands of clipgp_cast_bf16.
+ * ================================================================================================ */
+
+/* fp32 [R,K] (row stride ldx) -> bf16.  mode 0: out[r*out_ld + k].  mode 1 / 2: three segments at out[r*out_ld + g*seg_stride + k]
+ * holding [hi|hi|lo] (A side) / [hi|lo|hi] (B side), so that one K-tripled GEMM yields a_hi b_hi + a_hi b_lo + a_lo b_hi. */
+int clipgp_cast_bf16(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld, int64_t seg_stride, int mode,
+                     void* stream);
+
+/* C[M,N] (fp32, row stride ldc) = alpha * A B^T. */
+int clipgp_tc_gemm_store(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K, float alpha,
+                         float* C, int64_t ldc, void* stream);
+
+/* Logits alpha * A B^T reduced on the fly per row: max-softmax confidence, arg-max, hit flag, top-1 count and the equal-width
+ * ECE histogram (utils/metrics.py:9-36,71-82) -- same outputs / accumulate semantics as clipgp_calibration_from_logits, but the
+ * [M,N] logits never reach HBM unless logits_out != NULL. */
+int clipgp_tc_logits_calibration(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K, float alpha,
+                                 const int64_t* labels, float* conf, int32_t* pred, uint8_t* correct, const float* boundaries,
+                                 int n_bins, int64_t* bin_count, unsigned long long* bin_conf_fx, int64_t* bin_correct,
+                                 int64_t* top1, float* logits_out, int64_t ld_logits, void* stream);
 
 #ifdef __cplusplus
 }
