@@ -267,24 +267,43 @@ def run_ours(args):
     per = (n_eval + world - 1) // world
     sl = slice(rank * per, min(n_eval, (rank + 1) * per))
     f_sh, y_sh = f_te[sl].to(dev), y_te[sl].to(dev)
-    for _ in range(2):
-        res = eng.evaluate(f_sh, y_sh)
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    ev_ms = 0.0
-    for _ in range(reps):
-        flush.fill_(0.0)
-        e0.record()
+    def time_eval(fn, reps=5):
+        for _ in range(2):
+            out = fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(reps):
+            flush.fill_(0.0)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            tot += e0.elapsed_time(e1)
+        tt = torch.tensor([tot / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        return float(tt.item()), out
+
+    def eval_fp32():
         logits = eng.eval_logits(f_sh)
-        conf, correct, hist = metrics.calibration_pass(logits, y_sh, 10)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ev_ms += e0.elapsed_time(e1)
-    t = torch.tensor([ev_ms / reps], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    eval_ms = float(t.item())
+        return metrics.calibration_pass(logits, y_sh, 10)
+
+    # headline eval: tcgen05 GEMMs with split-bf16 operands (fp32-grade products, >= the reference's TF32), collapsed MC form
+    eval_ms, (conf, correct, hist) = time_eval(lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16x3", mc="collapsed"))
+    eval_variants = {}
+    for nm, fn in (("fp32_ffma_collapsed", eval_fp32),
+                   ("bf16_collapsed", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16", mc="collapsed")),
+                   ("bf16_materialised", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16", mc="materialised")),
+                   ("bf16x3_materialised", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16x3", mc="materialised"))):
+        ms_v, _ = time_eval(fn, reps=3)
+        eval_variants[nm] = {"ms": ms_v, "img_per_s": n_eval / (ms_v * 1e-3)}
+    # the fused logit GEMM alone, materialised MC form (north star: [N,D] x [S*C,D]^T), against the tensor peak
+    from clip_gp_b200 import tc as _tc
+    Bop, mcs = eng.eval_operands_tc(S, "bf16", "materialised")
+    fb = _tc.cast_bf16(f_sh)
+    gemm_ms, _ = time_eval(lambda: _tc.logits_calibration(fb, Bop, 100.0 * mcs, y_sh, 10), reps=5)
+    gemm_flops = 2.0 * f_sh.shape[0] * shp.C * shp.D * S
     # global metrics: all-reduce only the integer counters; AECE needs the gathered confidences
     if world > 1:
         h = hist.clone()
@@ -343,9 +362,15 @@ def run_ours(args):
         "clocks": clk,
         "roofline": roof,
         "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in ktimes.items()},
-        "eval": {"metric": "eval_img_per_s (MC-averaged logits + acc/ECE histogram, device resident)", "value": n_eval / (eval_ms * 1e-3),
-                 "unit": "img/s", "n_images": n_eval, "ms": eval_ms, "S_eval": S, "top1_acc": cnt.top1 * 100.0 / n_eval, "ece": ece, "aece": aece,
-                 "form": "collapsed logit-mean (exact): one [N,D]x[C,D]^T GEMM"},
+        "eval": {"metric": "eval_img_per_s (projection + MC-averaged logits + acc/ECE histogram, device resident)",
+                 "value": n_eval / (eval_ms * 1e-3), "unit": "img/s", "n_images": n_eval, "ms": eval_ms, "S_eval": S,
+                 "top1_acc": cnt.top1 * 100.0 / n_eval, "ece": ece, "aece": aece,
+                 "form": "tcgen05 GEMMs, split-bf16 (bf16x3) operands, collapsed logit-mean (exact): [N,D]x[C,D]^T, calibration fused in the epilogue",
+                 "variants": eval_variants},
+        "roofline_eval_gemm": {"kernel": "tc_gemm_kernel (EPI_ROWSTATS), materialised MC logits [N,D]x[S*C,D]^T accumulated over s in TMEM",
+                               "bound": "tensor", "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                               "frac": gemm_flops / (gemm_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None, "avg_launch_us": gemm_ms * 1e3,
+                               "flops_per_launch": gemm_flops, "peak_source": pk["source"]},
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(wl, shp, S, ls)

@@ -323,10 +323,79 @@ class GPAdapterEngine:
         return logits
 
     @torch.no_grad()
-    def evaluate(self, features: torch.Tensor, labels: torch.Tensor, S: Optional[int] = None, n_bins: int = 10):
-        """Accuracy / ECE / AECE of the MC-averaged logits for this rank's shard (metrics.evaluate_calibration)."""
-        logits = self.eval_logits(features, S=S)
-        return metrics.evaluate_calibration(logits, labels.to(self.dev), n_bins)
+    def evaluate(self, features: torch.Tensor, labels: torch.Tensor, S: Optional[int] = None, n_bins: int = 10,
+                 precision: str = "fp32", mc: str = "collapsed"):
+        """Accuracy / ECE / AECE of the MC-averaged logits for this rank's shard.
+
+        precision: "fp32" (FFMA GEMMs, logits materialised, exact-mode comparator) | "bf16" | "bf16x3" (tcgen05 GEMMs with the
+        calibration epilogue fused; bf16x3 = split operands, fp32-grade products).  mc: "collapsed" (one [N,D]x[C,D]^T GEMM
+        against mean_s p_hat_s, exact for the reference's logit-mean) | "materialised" (all S samples: [N,D]x[S*C,D]^T flops,
+        accumulated over s inside TMEM; tensor modes only)."""
+        labels = labels.to(self.dev)
+        if precision == "fp32":
+            logits = self.eval_logits(features, S=S)
+            return metrics.evaluate_calibration(logits, labels, n_bins)
+        conf, correct, hist = self.eval_calibration_tc(features, labels, S=S, n_bins=n_bins, precision=precision, mc=mc)
+        n = int(labels.numel())
+        cnt = metrics.counters_from_hist(hist, n)
+        ece, calib = metrics.ece_from_counters(cnt)
+        _, out = metrics.aece_pass(conf, correct, n_bins)
+        aece, acalib = metrics.aece_from_bins(out, n, n_bins)
+        return {"top1_acc": cnt.top1 * (100.0 / max(n, 1)), "ece": ece, "aece": aece, "calibration": calib,
+                "adaptive_calibration": acalib, "n": n, "top1_count": cnt.top1, "counters": cnt}
+
+    @torch.no_grad()
+    def eval_operands_tc(self, S: Optional[int] = None, precision: str = "bf16", mc: str = "collapsed"):
+        """bf16 B operand of the eval GEMM: mean_s p_hat_s [C, D] (collapsed) or [C, S*D] with the samples along K."""
+        from . import tc
+        S = int(S or self.cfg.S_eval)
+        split = precision == "bf16x3"
+        lib, st = self.lib, _lib.stream_ptr(self.dev)
+        Cn, T, D = self.C, self.T, self.D
+        if mc == "collapsed":
+            Pm = self.eval_prototypes(S)
+            return tc.cast_bf16(Pm, tc.SPLIT_B if split else tc.PLAIN), 1.0
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        w = torch.empty(S, Cn, T, **f32)
+        a = GpArgs.from_buffer_copy(self.gp_args)
+        a.S, a.s_offset, a.S_total = S, 0, S
+        a.w, a.kl = w.data_ptr(), None
+        a.L = a.A = a.R = None
+        P_hat = torch.empty(S, Cn, D, **f32)
+        seg = 3 if split else 1
+        Bop = torch.empty(Cn, S * seg * D, dtype=torch.bfloat16, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.clipgp_gp_forward(C.byref(a), st), "gp_forward(eval)")
+            _lib.check(lib.clipgp_proto_forward(w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, P_hat.data_ptr(), None,
+                                                None, None, None, 0, st), "proto_forward(eval)")
+            for s_ in range(S):     # row c of the operand = [p_hat_1c | ... | p_hat_Sc] (each optionally [hi|lo|hi])
+                _lib.check(lib.clipgp_cast_bf16(P_hat[s_].data_ptr(), Cn, D, D, Bop.data_ptr() + 2 * s_ * seg * D, S * seg * D, D,
+                                                2 if split else 0, st), "cast_bf16(P)")
+        return Bop, 1.0 / S
+
+    @torch.no_grad()
+    def eval_calibration_tc(self, features, labels, S=None, n_bins=10, precision="bf16", mc="collapsed", want_logits=False):
+        """Tensor-core eval: cast -> projection GEMM -> row normalise -> fused logits + softmax-max + histogram GEMM."""
+        from . import tc
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError(f"unknown precision {precision}")
+        split = precision == "bf16x3"
+        lib, st = self.lib, _lib.stream_ptr(self.dev)
+        f = features.to(self.dev, non_blocking=True).float().contiguous()
+        N, D = f.shape
+        Bop, mc_scale = self.eval_operands_tc(S, precision, mc)
+        Wb = tc.cast_bf16(self.p("W").view(D, D), tc.SPLIT_B if split else tc.PLAIN)
+        fb = tc.cast_bf16(f, tc.SPLIT_A if split else tc.PLAIN)
+        Y = tc.gemm_store(fb, Wb, 1.0)                                              # adapter.py:239
+        seg = 3 if split else 1
+        fhat_b = torch.empty(N, seg * D, dtype=torch.bfloat16, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.clipgp_rownorm_forward(Y.data_ptr(), N, D, Y.data_ptr(), None, None, st), "rownorm")      # adapter.py:240
+            _lib.check(lib.clipgp_cast_bf16(Y.data_ptr(), N, D, D, fhat_b.data_ptr(), seg * D, D, 1 if split else 0, st), "cast_bf16(f_hat)")
+        conf, correct, hist, logits = tc.logits_calibration(fhat_b, Bop, self.cfg.logit_scale * mc_scale, labels, n_bins,
+                                                            want_conf=True, want_logits=want_logits)
+        self.last_eval_logits = logits
+        return conf, correct, hist
 
     # ------------------------------------------------------------------ sync back to the nn.Module
     @torch.no_grad()
