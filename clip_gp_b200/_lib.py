@@ -76,6 +76,12 @@ _SIGNATURES = {
                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "clipgp_increment": (C.c_int, [C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_sum_accumulate": (C.c_int, [C.c_void_p, c_i64, C.c_float, C.c_void_p, C.c_void_p]),
+    "clipgp_tip_forward": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, c_i64, C.c_float, C.c_float, C.c_void_p, c_i64,
+                                     C.c_void_p, c_i64, C.c_int, C.c_void_p]),
+    "clipgp_tip_backward": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, C.c_float, C.c_float,
+                                      C.c_void_p]),
+    "clipgp_tc_tip_logits": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                       c_i64, C.c_void_p]),
     "clipgp_cast_bf16": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
     "clipgp_tc_gemm_store": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_float, C.c_void_p, c_i64,
                                        C.c_void_p]),

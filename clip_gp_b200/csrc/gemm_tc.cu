@@ -29,7 +29,7 @@ constexpr int THREADS = 192;
 constexpr int ACC_COLS = BN;       // fp32 accumulator columns per tile
 constexpr int TMEM_COLS = 512;     // two accumulator stages
 
-constexpr int EPI_STORE = 0, EPI_ROWSTATS = 1;
+constexpr int EPI_STORE = 0, EPI_ROWSTATS = 1, EPI_TIP = 2;
 
 struct Params {
     int M, N, K, Ka;
@@ -41,6 +41,7 @@ struct Params {
     const long long* labels; float* conf; int* pred; unsigned char* correct;
     const float* boundaries; int n_bins;
     long long* bin_count; unsigned long long* bin_conf_fx; long long* bin_correct; long long* top1;
+    const int* key_class; float beta; float tip_alpha;   // EPI_TIP: class of every key (column), exp(-beta(1-aff)), alpha
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -220,7 +221,26 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     uint32_t r[32];
                     tmem_ld32(taddr + (uint32_t)c0, r);
                     const int ncols = min(32, p.N - col0);
-                    if (p.C != nullptr && row < p.M) {
+                    if (p.mode == EPI_TIP) {
+                        // cache_logits[b, class(j)] += exp(-beta (1 - aff[b,j])): run-length sums over equal classes (keys are
+                        // sorted by class on the host, so a 32-column chunk flushes only a few atomics per row)
+                        if (row < p.M) {
+                            float* orow = p.C + (long long)row * p.ldc;
+                            int cur = p.key_class[col0];
+                            float sum = 0.f;
+                            const float bl = p.beta * 1.4426950408889634f;
+#pragma unroll 4
+                            for (int j = 0; j < 32; ++j) {
+                                if (j < ncols) {
+                                    const int cls = p.key_class[col0 + j];
+                                    const float e = exp2f(bl * (p.alpha * __uint_as_float(r[j]) - 1.f));
+                                    if (cls != cur) { atomicAdd(orow + cur, p.tip_alpha * sum); cur = cls; sum = 0.f; }
+                                    sum += e;
+                                }
+                            }
+                            atomicAdd(orow + cur, p.tip_alpha * sum);
+                        }
+                    } else if (p.C != nullptr && row < p.M) {
                         float* dst = p.C + (long long)row * p.ldc + col0;
                         if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
@@ -379,4 +399,14 @@ extern "C" int clipgp_tc_logits_calibration(const void* A_bf16, int64_t M, int64
     p.bin_count = reinterpret_cast<long long*>(bin_count); p.bin_conf_fx = bin_conf_fx;
     p.bin_correct = reinterpret_cast<long long*>(bin_correct); p.top1 = reinterpret_cast<long long*>(top1);
     return tc::launch(A_bf16, M, Ka, B_bf16, N, K, p, (cudaStream_t)stream);
+}
+
+extern "C" int clipgp_tc_tip_logits(const void* F_bf16, int64_t M, const void* keys_bf16, int64_t N_tr, int64_t K,
+                                    const int32_t* key_class, float beta, float alpha, float* out, int64_t ldo, void* stream) {
+    if (M == 0 || N_tr == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(key_class && out, "tc_tip_logits: NULL pointer");
+    tc::Params p = {};
+    p.mode = tc::EPI_TIP; p.alpha = 1.0f; p.C = out; p.ldc = ldo;
+    p.key_class = key_class; p.beta = beta; p.tip_alpha = alpha;
+    return tc::launch(F_bf16, M, K, keys_bf16, N_tr, K, p, (cudaStream_t)stream);
 }

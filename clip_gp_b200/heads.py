@@ -1,0 +1,207 @@
+"""Cosine-logit heads of the reference trainers, on CACHED frozen-CLIP features (the hot path starts after feature
+extraction).  Same class / method names and argument meaning as the reference's ``CustomCLIP``
+variants; every tensor op on the path is a clipgp kernel (ops.py), torch only owns parameters and autograd plumbing.
+
+* ``AdapterHead``      — trainers/adapter.py:145-259 (visual_proj + GP / uniform template weighting)
+* ``TaskResHead``      — trainers/taskres.py:35-47, 96-123
+* ``ClipAdapterHead``  — trainers/clip_adapter.py:16-32, 77-100
+* ``tip_*``            — trainers/tip_adapter.py:43-80, 250-260
+* ``gp_pretrain``      — the full-batch ELBO loop of taskres.py:254-289 == clip_adapter.py:257-290 == tip_adapter.py:122-157
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import metrics, ops
+from .gp_template_weigher import GaussianProcessTemplateWeighter
+
+
+def _cosine_logits(feats_hat: torch.Tensor, prototypes: torch.Tensor, scale) -> torch.Tensor:
+    """scale * f_hat . normalize(p): [B,C] for 2-D prototypes, mean over samples for [S,C,D] (adapter.py:246-251)."""
+    if prototypes.dim() == 3:
+        S, C, D = prototypes.shape
+        p_hat = ops.row_normalize(prototypes).reshape(S * C, D)
+        logits = ops.matmul_nt(feats_hat, p_hat, 1.0).view(feats_hat.shape[0], S, C)
+        return logits.mean(dim=1) * scale
+    return ops.matmul_nt(feats_hat, ops.row_normalize(prototypes), 1.0) * scale
+
+
+class AdapterHead(nn.Module):
+    """``CustomCLIP`` of trainers/adapter.py without the encoders: text_embeddings [K,M,D] are given."""
+
+    def __init__(self, config: Any, text_embeddings: torch.Tensor, logit_scale: float = math.log(100.0)):
+        super().__init__()
+        self.config = config
+        a = getattr(config, "adapter", config)
+        self.register_buffer("text_embeddings", text_embeddings.detach().float())
+        self.logit_scale = nn.Parameter(torch.tensor(float(logit_scale)), requires_grad=False)
+        self.gp_num_mc_samples_train = int(getattr(a, "gp_num_mc_samples_train", 1) or 1)
+        self.gp_num_mc_samples_eval = int(getattr(a, "gp_num_mc_samples_eval", 1) or 1)
+        self.gp_weighter = GaussianProcessTemplateWeighter(text_embeddings, config) if bool(getattr(a, "use_gp", False)) else None
+        dim = int(text_embeddings.shape[-1])
+        self.visual_proj = nn.Linear(dim, dim, bias=False)
+        with torch.no_grad():
+            self.visual_proj.weight.copy_(torch.eye(dim))                      # adapter.py:187-192
+
+    def get_prototypes(self, num_samples: int = 1, visual_embeddings: Optional[torch.Tensor] = None):
+        if self.gp_weighter is not None:                                        # adapter.py:206-208
+            return self.gp_weighter.sample_prototypes(max(1, num_samples), visual_embeddings)
+        return self.text_embeddings.mean(dim=1)                                 # adapter.py:225 (uniform template weights)
+
+    def forward_features(self, features: torch.Tensor, num_samples: Optional[int] = None) -> torch.Tensor:
+        projected = ops.matmul_nt(features, self.visual_proj.weight, 1.0)       # adapter.py:239
+        f_hat = ops.row_normalize(projected)
+        scale = self.logit_scale.exp()
+        S = self.gp_num_mc_samples_train if self.training else self.gp_num_mc_samples_eval     # adapter.py:242
+        return _cosine_logits(f_hat, self.get_prototypes(S, projected), scale)
+
+    forward = forward_features
+
+    def compute_loss(self, features, labels, num_samples: int, gp_beta: float, l2_lambda: float, shots: int):
+        """Trainer.compute_loss, adapter.py:387-476."""
+        f_hat = ops.row_normalize(ops.matmul_nt(features, self.visual_proj.weight, 1.0))
+        scale = float(self.logit_scale.exp())
+        if self.gp_weighter is not None and num_samples > 1:
+            protos = self.gp_weighter.sample_prototypes(num_samples)            # adapter.py:404
+            S, C, D = protos.shape
+            p_hat = ops.row_normalize(protos).reshape(S * C, D)
+            logits = ops.matmul_nt(f_hat, p_hat, scale).view(-1, C)             # rows (b, s)
+            ce = ops.cross_entropy(logits, labels, rows_per_label=S)            # mean_s mean_b CE (adapter.py:422-428)
+        else:
+            ce = ops.cross_entropy(_cosine_logits(f_hat, self.get_prototypes(num_samples), scale), labels)
+        total = ce
+        if self.gp_weighter is not None:
+            total = total + self.gp_weighter.variational_strategy.kl_divergence().sum() * float(gp_beta)
+        W = self.visual_proj.weight
+        if W.requires_grad:
+            eye = torch.eye(W.shape[0], device=W.device, dtype=W.dtype)
+            total = total + (W - eye).pow(2).sum() * (float(l2_lambda) / shots)
+        return total
+
+
+class TaskResHead(nn.Module):
+    """``TaskResLearner`` + ``CustomCLIP.forward`` of trainers/taskres.py on cached features."""
+
+    def __init__(self, config: Any, base_text_features: torch.Tensor, logit_scale: float = math.log(100.0)):
+        super().__init__()
+        self.config = config
+        a = getattr(config, "adapter", config)
+        self.alpha = float(getattr(a, "taskres_residual_scale", 0.5))
+        self.register_buffer("base_text_features", base_text_features.detach().float().clone())
+        self.text_feature_residuals = nn.Parameter(torch.zeros_like(self.base_text_features))
+        self.logit_scale = nn.Parameter(torch.tensor(float(logit_scale)), requires_grad=False)
+        self.gp_weighter: Optional[GaussianProcessTemplateWeighter] = None
+        self.gp_num_mc_samples_train = int(getattr(a, "gp_num_mc_samples_train", 1) or 1)
+        self.gp_num_mc_samples_eval = int(getattr(a, "gp_num_mc_samples_eval", 1) or 1)
+
+    def forward(self, image_features: torch.Tensor) -> torch.Tensor:
+        f_hat = ops.row_normalize(image_features)                               # taskres.py:99
+        scale = self.logit_scale.exp()
+        if self.gp_weighter is not None and bool(getattr(getattr(self.config, "adapter", self.config), "use_gp", False)):
+            S = max(1, self.gp_num_mc_samples_train if self.training else self.gp_num_mc_samples_eval)
+            protos = self.gp_weighter.sample_prototypes(S)                      # taskres.py:107-109
+            p_hat = ops.row_normalize(protos)
+            text_s = p_hat + (self.alpha * self.text_feature_residuals).unsqueeze(0)       # :111-112
+            return _cosine_logits(f_hat, text_s, scale)                         # :113-116
+        return _cosine_logits(f_hat, self.base_text_features + self.alpha * self.text_feature_residuals, scale)   # :119-121
+
+
+class AdapterMLP(nn.Module):
+    """trainers/clip_adapter.py:16-32 (bias-free 2-layer MLP with ReLU); the linears run on the clipgp fp32 GEMM."""
+
+    def __init__(self, in_dim: int, reduction: int = 4):
+        super().__init__()
+        hidden = max(1, in_dim // max(1, int(reduction)))
+        self.fc1 = nn.Linear(in_dim, hidden, bias=False)
+        self.fc2 = nn.Linear(hidden, in_dim, bias=False)
+
+    def forward(self, x):
+        x = torch.relu(ops.matmul_nt(x, self.fc1.weight, 1.0))
+        return torch.relu(ops.matmul_nt(x, self.fc2.weight, 1.0))
+
+
+class ClipAdapterHead(nn.Module):
+    """``CustomCLIP`` of trainers/clip_adapter.py on cached features; clip_weights is [D,K] as in the reference."""
+
+    def __init__(self, config: Any, clip_weights: torch.Tensor, logit_scale: float = math.log(100.0)):
+        super().__init__()
+        self.config = config
+        a = getattr(config, "adapter", config)
+        in_dim = int(clip_weights.shape[0])
+        self.adapter = AdapterMLP(in_dim, int(getattr(a, "clip_adapter_reduction", 4)))
+        self.register_buffer("_blend_ratio", torch.tensor(float(getattr(a, "clip_adapter_ratio", 0.2))))
+        self.register_buffer("clip_weights", clip_weights.detach().float().clone())
+        self.logit_scale = nn.Parameter(torch.tensor(float(logit_scale)), requires_grad=False)
+        self.gp_weighter: Optional[GaussianProcessTemplateWeighter] = None
+        self.gp_num_mc_samples_train = int(getattr(a, "gp_num_mc_samples_train", 1) or 1)
+        self.gp_num_mc_samples_eval = int(getattr(a, "gp_num_mc_samples_eval", 1) or 1)
+
+    def _apply_adapter(self, feats):
+        ratio = float(self._blend_ratio.item())
+        return ratio * self.adapter(feats) + (1.0 - ratio) * feats            # clip_adapter.py:77-80
+
+    def logits_from_features(self, features: torch.Tensor, training: bool = False) -> torch.Tensor:
+        feats = self._apply_adapter(features.float())
+        f_hat = ops.row_normalize(feats)
+        scale = self.logit_scale.exp()
+        if self.gp_weighter is not None and bool(getattr(getattr(self.config, "adapter", self.config), "use_gp", False)):
+            S = max(1, self.gp_num_mc_samples_train if training else self.gp_num_mc_samples_eval)
+            return _cosine_logits(f_hat, self.gp_weighter.sample_prototypes(S), scale)       # clip_adapter.py:90-96
+        return _cosine_logits(f_hat, self.clip_weights.t().contiguous(), scale)                # :97-100 (normalize(dim=0) of [D,K])
+
+    def forward(self, features):
+        return self.logits_from_features(features, training=self.training)
+
+
+# ---------------------------------------------------------------------------------------------------- Tip-Adapter
+def tip_build_cache(features_hat: torch.Tensor, labels: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """_build_cache (tip_adapter.py:43-50) with the keys sorted by class so that label-segmented sums are contiguous;
+    the one-hot value matrix is never formed (the labels are the values)."""
+    order = torch.argsort(labels, stable=True)
+    return features_hat[order].contiguous(), labels[order].contiguous()
+
+
+def tip_search(feats_hat, labels, keys, key_labels, clip_logits, num_classes: int, init_beta: float, init_alpha: float,
+               betas=(1.0, 2.0, 5.0), alphas=(1.0, 5.0, 10.0, 20.0, 50.0)):
+    """_search_hyperparams (tip_adapter.py:52-80): first (beta, alpha) with the strictly best top-1.  One affinity GEMM is shared
+    by all 15 pairs."""
+    best_acc, best_beta, best_alpha = -1.0, float(init_beta), float(init_alpha)
+    with torch.no_grad():
+        for beta in betas:
+            for alpha in alphas:
+                tl = ops.tip_logits(feats_hat, keys, key_labels, clip_logits, beta, alpha, num_classes)
+                acc = metrics.compute_accuracy(tl, labels)[0]
+                if acc > best_acc:
+                    best_acc, best_beta, best_alpha = float(acc), float(beta), float(alpha)
+    return best_beta, best_alpha, best_acc
+
+
+# ---------------------------------------------------------------------------------------------------- GP pre-training
+def gp_pretrain(gp_weighter: GaussianProcessTemplateWeighter, feats_hat: torch.Tensor, labels: torch.Tensor, epochs: int,
+                gp_lr: float, beta_kl: float, num_samples: int, weight_decay: float = 0.0, scale: float = 100.0, log_every: int = 10):
+    """Full-batch ELBO optimisation of the weighter (taskres.py:254-280; identical in clip_adapter.py / tip_adapter.py):
+    CE(mean_s 100 f . normalize(protos_s), y) + beta * sum KL, AdamW + cosine annealing.  Returns the loss history."""
+    opt = torch.optim.AdamW(gp_weighter.parameters(), lr=gp_lr, weight_decay=weight_decay)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, epochs)
+    hist = []
+    for ep in range(epochs):
+        gp_weighter.train()
+        prot = gp_weighter.sample_prototypes(num_samples=max(1, num_samples))
+        logits = _cosine_logits(feats_hat, prot, scale)
+        ce = ops.cross_entropy(logits, labels)
+        kl = gp_weighter.variational_strategy.kl_divergence().sum()
+        loss = ce + beta_kl * kl
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sched.step()
+        hist.append(float(loss.detach()))
+        if log_every and ((ep == 0) or ((ep + 1) % log_every == 0)):
+            with torch.no_grad():
+                acc = metrics.compute_accuracy(logits.detach(), labels)[0]
+            print(f"[GP] epoch {ep + 1}/{epochs} loss={hist[-1]:.4f} CE={float(ce):.4f} KL={float(kl):.4f} acc={acc:.2f}")
+    return hist

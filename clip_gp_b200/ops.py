@@ -172,3 +172,160 @@ def prototypes_reduced(w, E, residual=None, alpha: float = 0.0, want_hat=False, 
                                             _lib.ptr(P_hat), None, None, _lib.ptr(mh), _lib.ptr(mr), 1,
                                             _lib.stream_ptr(dev)), "clipgp_proto_forward")
     return P_hat, mh, mr
+
+
+# =====================================================================================================
+# Generic differentiable building blocks of the cosine-logit heads (exact-fp32 kernels)
+# =====================================================================================================
+def _gemm(A, sam, sak, B, sbk, sbn, out, M, N, K, alpha, accumulate=0):
+    dev = out.device
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().clipgp_gemm_f32(A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, out.data_ptr(), out.stride(0), M, N, K,
+                                               float(alpha), accumulate, _lib.stream_ptr(dev)), "clipgp_gemm_f32")
+
+
+class MatmulNT(torch.autograd.Function):
+    """C = alpha * A @ B^T for A [M,K], B [N,K] (adapter.py:239 f W^T; :251 / :426 f_hat p_hat^T; tip_adapter.py:250)."""
+
+    @staticmethod
+    def forward(ctx, A, B, alpha: float):
+        dev = _lib.require_cuda(A, B)
+        A, B = _c(A), _c(B)
+        M, K = A.shape
+        N = B.shape[0]
+        if B.shape[1] != K:
+            raise ValueError(f"matmul_nt: {tuple(A.shape)} x {tuple(B.shape)}^T")
+        out = torch.empty(M, N, dtype=torch.float32, device=dev)
+        if M and N:
+            _gemm(A, K, 1, B, 1, K, out, M, N, K, alpha)
+        ctx.save_for_backward(A, B)
+        ctx.alpha = float(alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B = ctx.saved_tensors
+        dC = _c(dC)
+        M, K = A.shape
+        N = B.shape[0]
+        dA = dB = None
+        if ctx.needs_input_grad[0]:
+            dA = torch.empty_like(A)
+            _gemm(dC, N, 1, B, K, 1, dA, M, K, N, ctx.alpha)          # dA = alpha dC B
+        if ctx.needs_input_grad[1]:
+            dB = torch.empty_like(B)
+            _gemm(dC, 1, N, A, K, 1, dB, N, K, M, ctx.alpha)          # dB = alpha dC^T A
+        return dA, dB, None
+
+
+def matmul_nt(A, B, alpha: float = 1.0):
+    return MatmulNT.apply(A, B, alpha)
+
+
+class RowNormalize(torch.autograd.Function):
+    """F.normalize(x, p=2, dim=-1) for a 2-D tensor (adapter.py:240,246)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        dev = _lib.require_cuda(x)
+        x = _c(x)
+        R, D = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(R, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().clipgp_rownorm_forward(x.data_ptr(), R, D, y.data_ptr(), inv.data_ptr(), None, _lib.stream_ptr(dev)),
+                       "clipgp_rownorm_forward")
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            _lib.check(_lib.load().clipgp_rownorm_backward(dy.data_ptr(), y.data_ptr(), inv.data_ptr(), y.shape[0], y.shape[1], dx.data_ptr(),
+                                                           _lib.stream_ptr(y.device)), "clipgp_rownorm_backward")
+        return dx
+
+
+def row_normalize(x):
+    shp = x.shape
+    return RowNormalize.apply(x.reshape(-1, shp[-1])).reshape(shp)
+
+
+class SoftmaxCrossEntropy(torch.autograd.Function):
+    """mean over rows of F.cross_entropy(logits [R,C], labels[r // rows_per_label])  (adapter.py:427, taskres.py:270)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, rows_per_label: int):
+        dev = _lib.require_cuda(logits, labels)
+        logits = _c(logits)
+        labels = labels.to(torch.int64).contiguous()
+        R, Cn = logits.shape
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        dlogits = torch.empty_like(logits)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().clipgp_softmax_ce(logits.data_ptr(), Cn, labels.data_ptr(), R, int(rows_per_label), Cn, None, loss.data_ptr(),
+                                                     1.0 / max(R, 1), dlogits.data_ptr(), Cn, 1.0 / max(R, 1), _lib.stream_ptr(dev)),
+                       "clipgp_softmax_ce")
+        ctx.save_for_backward(dlogits)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * dloss, None, None
+
+
+def cross_entropy(logits, labels, rows_per_label: int = 1):
+    return SoftmaxCrossEntropy.apply(logits, labels, rows_per_label)
+
+
+class TipCacheLogits(torch.autograd.Function):
+    """tip_logits = clip_logits + alpha * exp(-(beta - beta * f keys^T)) @ one_hot(labels_tr)   (tip_adapter.py:250-260).
+    Differentiable w.r.t. the cache keys (Tip-Adapter-F's nn.Linear weight) and clip_logits."""
+
+    @staticmethod
+    def forward(ctx, feats, keys, labels_tr, clip_logits, beta: float, alpha: float, num_classes: int):
+        dev = _lib.require_cuda(feats, keys, labels_tr)
+        lib = _lib.load()
+        feats, keys = _c(feats), _c(keys)
+        labels_tr = labels_tr.to(torch.int64).contiguous()
+        clip_logits = _c(clip_logits) if clip_logits is not None else None
+        B, D = feats.shape
+        N_tr = keys.shape[0]
+        aff = torch.empty(B, N_tr, dtype=torch.float32, device=dev)
+        out = torch.empty(B, num_classes, dtype=torch.float32, device=dev)
+        if B and N_tr:
+            _gemm(feats, D, 1, keys, 1, D, aff, B, N_tr, D, 1.0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.clipgp_tip_forward(aff.data_ptr(), N_tr, labels_tr.data_ptr(), B, N_tr, num_classes, float(beta), float(alpha),
+                                              _lib.ptr(clip_logits), num_classes, out.data_ptr(), num_classes, 1, _lib.stream_ptr(dev)),
+                       "clipgp_tip_forward")
+        ctx.save_for_backward(aff, feats, labels_tr)
+        ctx.consts = (float(beta), float(alpha))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        e, feats, labels_tr = ctx.saved_tensors
+        beta, alpha = ctx.consts
+        dev = e.device
+        dout = _c(dout)
+        B, N_tr = e.shape
+        D = feats.shape[1]
+        dkeys = None
+        if ctx.needs_input_grad[1]:
+            G = e.clone()
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().clipgp_tip_backward(G.data_ptr(), N_tr, labels_tr.data_ptr(), B, N_tr, dout.data_ptr(), dout.shape[1],
+                                                           beta, alpha, _lib.stream_ptr(dev)), "clipgp_tip_backward")
+            dkeys = torch.empty(N_tr, D, dtype=torch.float32, device=dev)
+            _gemm(G, 1, N_tr, feats, D, 1, dkeys, N_tr, D, B, 1.0)      # dkeys = G^T f
+        dclip = dout if ctx.needs_input_grad[3] else None
+        return None, dkeys, None, dclip, None, None, None
+
+
+def tip_logits(feats, keys, labels_tr, clip_logits, beta: float, alpha: float, num_classes: int):
+    return TipCacheLogits.apply(feats, keys, labels_tr, clip_logits, beta, alpha, num_classes)

@@ -210,6 +210,29 @@ int clipgp_tc_logits_calibration(const void* A_bf16, int64_t M, int64_t Ka, cons
                                  int n_bins, int64_t* bin_count, unsigned long long* bin_conf_fx, int64_t* bin_correct,
                                  int64_t* top1, float* logits_out, int64_t ld_logits, void* stream);
 
+/* ================================================================================================
+ * Tip-Adapter cache model — trainers/tip_adapter.py:43-80 (_build_cache, _search_hyperparams), :250-260 (train),
+ * :281-290, :309-318, :331-333, :371-383 (eval):  affinity = f keys^T; cache = exp(-(beta - beta*affinity)) @ one_hot(labels_tr);
+ * tip = clip_logits + alpha * cache.  The one-hot GEMM is a label-segmented sum here.
+ * ================================================================================================ */
+
+/* Exact-fp32 row pass over a materialised affinity block [B, N_tr] (row stride lda, from clipgp_gemm_f32):
+ * out[b,c] = clip_logits[b,c] (0 if NULL) + alpha * sum_{j: labels_tr[j]==c} exp(-(beta - beta*aff[b,j])).
+ * store_e != 0 overwrites the block with the exponentials (saved for the adjoint). */
+int clipgp_tip_forward(float* affinity, int64_t lda, const int64_t* labels_tr, int64_t B, int64_t N_tr, int64_t C, float beta,
+                       float alpha, const float* clip_logits, int64_t ldc, float* out, int64_t ldo, int store_e, void* stream);
+
+/* In place over the saved exponentials: G[b,j] = dout[b, labels_tr[j]] * alpha * beta * e[b,j] = d loss / d affinity[b,j].
+ * (The key gradient of Tip-Adapter-F, tip_adapter.py:229-269, is then G^T f via clipgp_gemm_f32.) */
+int clipgp_tip_backward(float* e, int64_t lda, const int64_t* labels_tr, int64_t B, int64_t N_tr, const float* dout, int64_t ldd,
+                        float beta, float alpha, void* stream);
+
+/* Tensor-core fused form for evaluation: out[b, key_class[j]] += alpha * exp(-beta (1 - f_b . key_j)) for every key j, computed in
+ * the epilogue of the tcgen05 affinity GEMM ([M,K] x [N_tr,K]^T, bf16 or split operands): the [M, N_tr] affinity never reaches
+ * HBM.  `out` [M, C] must already hold clip_logits; key_class [N_tr] int32 (sorting the cache by class minimises atomics). */
+int clipgp_tc_tip_logits(const void* F_bf16, int64_t M, const void* keys_bf16, int64_t N_tr, int64_t K, const int32_t* key_class,
+                         float beta, float alpha, float* out, int64_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,89 @@
+"""GPU: differentiable head building blocks (fp32 GEMM, row-normalise, softmax-CE, Tip cache logits) against torch
+autograd through the oracle's restatement of the reference heads."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from clip_gp_b200 import ops, tc
+from oracle import heads as oh
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (48, 37, 128), (128, 1000, 512), (130, 10000, 77), (700, 300, 1024), (128, 512, 10000)])
+def test_matmul_nt_forward_backward(M, N, K):
+    g = torch.Generator().manual_seed(M * N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    dC = torch.randn(M, N, generator=g)
+    Ar, Br = A.clone().requires_grad_(True), B.clone().requires_grad_(True)
+    (0.7 * Ar @ Br.t()).backward(dC)
+    Ad, Bd = A.cuda().requires_grad_(True), B.cuda().requires_grad_(True)
+    C = ops.matmul_nt(Ad, Bd, 0.7)
+    C.backward(dC.cuda())
+    assert rel_err(C, (0.7 * A @ B.t())) < 1e-5
+    assert rel_err(Ad.grad, Ar.grad) < 1e-5 and rel_err(Bd.grad, Br.grad) < 1e-5
+
+
+def test_adapter_head_loss_and_grads_match_oracle():
+    """adapter.py:401-428 composed from clipgp ops == oracle.heads.adapter_mc_ce (autograd)."""
+    g = torch.Generator().manual_seed(1)
+    B, D, C, S = 48, 128, 37, 4
+    f = torch.randn(B, D, generator=g); y = torch.randint(0, C, (B,), generator=g)
+    W = (torch.eye(D) + 0.05 * torch.randn(D, D, generator=g))
+    P = torch.randn(S, C, D, generator=g)
+    Wr, Pr = W.clone().requires_grad_(True), P.clone().requires_grad_(True)
+    ref = oh.adapter_mc_ce(f, y, Wr, Pr, 30.0)
+    ref.backward()
+    Wd, Pd = W.cuda().requires_grad_(True), P.cuda().requires_grad_(True)
+    f_hat = ops.row_normalize(ops.matmul_nt(f.cuda(), Wd))
+    p_hat = ops.row_normalize(Pd).reshape(S * C, D)
+    logits = ops.matmul_nt(f_hat, p_hat, 30.0).view(B * S, C)           # row (b, s)
+    loss = ops.cross_entropy(logits, y.cuda(), rows_per_label=S)
+    loss.backward()
+    assert float(loss) == pytest.approx(float(ref), rel=1e-5)
+    assert rel_err(Wd.grad, Wr.grad) < 1e-4 and rel_err(Pd.grad, Pr.grad) < 1e-4
+    # logit-mean form (adapter.py:247-249)
+    lm = ops.matmul_nt(f_hat, p_hat, 30.0).view(B, S, C).mean(1)
+    assert rel_err(lm, oh.adapter_logits(f, W, P, 30.0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,N_tr,C,D", [(16, 48, 12, 64), (128, 1600, 100, 1024), (33, 407, 37, 128)])
+def test_tip_cache_logits_forward_backward(B, N_tr, C, D):
+    g = torch.Generator().manual_seed(B + N_tr)
+    f = F.normalize(torch.randn(B, D, generator=g), dim=-1)
+    keys = F.normalize(torch.randn(N_tr, D, generator=g), dim=-1)
+    lab = torch.randint(0, C, (N_tr,), generator=g)
+    clip = 5.0 * torch.randn(B, C, generator=g)
+    dout = torch.randn(B, C, generator=g)
+    kr = keys.clone().requires_grad_(True)
+    ref = oh.tip_logits(f, kr, oh.tip_cache_vals(lab, C), clip, 2.0, 20.0)
+    ref.backward(dout)
+    kd = keys.cuda().requires_grad_(True)
+    out = ops.tip_logits(f.cuda(), kd, lab.cuda(), clip.cuda(), 2.0, 20.0, C)
+    out.backward(dout.cuda())
+    assert rel_err(out, ref) < 1e-5 and rel_err(kd.grad, kr.grad) < 1e-4
+    # fused tensor-core evaluation form (affinity never materialised); split operands -> fp32-grade
+    order = torch.argsort(lab, stable=True)
+    ks, ls = keys[order].cuda(), lab[order].cuda()
+    o3 = clip.cuda().clone()
+    from clip_gp_b200 import _lib
+    _lib.check(_lib.load().clipgp_tc_tip_logits(tc.cast_bf16(f.cuda(), tc.SPLIT_A).data_ptr(), B, tc.cast_bf16(ks, tc.SPLIT_B).data_ptr(), N_tr,
+                                                3 * D, ls.to(torch.int32).contiguous().data_ptr(), 2.0, 20.0, o3.data_ptr(), C,
+                                                _lib.stream_ptr(o3.device)), "clipgp_tc_tip_logits")
+    assert rel_err(o3, ref) < 1e-3
+
+
+def test_tip_hyperparameter_search_matches_oracle():
+    from clip_gp_b200 import heads
+    g = torch.Generator().manual_seed(7)
+    B, N_tr, C, D = 200, 160, 10, 64
+    mu = torch.randn(C, D, generator=g)
+    lab = torch.arange(C).repeat_interleave(16)
+    keys = F.normalize(mu[lab] + 2.0 * torch.randn(N_tr, D, generator=g), dim=-1)
+    y = torch.randint(0, C, (B,), generator=g)
+    f = F.normalize(mu[y] + 3.0 * torch.randn(B, D, generator=g), dim=-1)
+    clip = 100.0 * f @ F.normalize(mu, dim=-1).t()
+    bb, ba, acc = oh.tip_search(f, y, keys, oh.tip_cache_vals(lab, C), clip, 2.0, 20.0)
+    b2, a2, acc2 = heads.tip_search(f.cuda(), y.cuda(), keys.cuda(), lab.cuda(), clip.cuda(), C, 2.0, 20.0)
+    assert (b2, a2) == (bb, ba) and acc2 == pytest.approx(acc)
