@@ -68,8 +68,8 @@ def test_tip_cache_logits_forward_backward(B, N_tr, C, D):
     ks, ls = keys[order].cuda(), lab[order].cuda()
     o3 = clip.cuda().clone()
     from clip_gp_b200 import _lib
-    _lib.check(_lib.load().clipgp_tc_tip_logits(tc.cast_bf16(f.cuda(), tc.SPLIT_A).data_ptr(), B, tc.cast_bf16(ks, tc.SPLIT_B).data_ptr(), N_tr,
-                                                3 * D, ls.to(torch.int32).contiguous().data_ptr(), 2.0, 20.0, o3.data_ptr(), C,
+    fa, kb, li = tc.cast_bf16(f.cuda(), tc.SPLIT_A), tc.cast_bf16(ks, tc.SPLIT_B), ls.to(torch.int32).contiguous()   # keep alive
+    _lib.check(_lib.load().clipgp_tc_tip_logits(fa.data_ptr(), B, kb.data_ptr(), N_tr, 3 * D, li.data_ptr(), 2.0, 20.0, o3.data_ptr(), C,
                                                 _lib.stream_ptr(o3.device)), "clipgp_tc_tip_logits")
     assert rel_err(o3, ref) < 1e-3
 
