@@ -264,8 +264,9 @@ def run_ours(args):
     # ---------------- eval leg: MC-averaged logits + acc/ECE/AECE over this rank's shard of the test features
     n_eval = args.eval_n
     f_te, y_te = wl["f_test"][:n_eval], wl["y_test"][:n_eval]
-    per = (n_eval + world - 1) // world
-    sl = slice(rank * per, min(n_eval, (rank + 1) * per))
+    from clip_gp_b200 import dist as cdist
+    lo_e, hi_e = cdist.shard_range(n_eval, rank, world)
+    sl = slice(lo_e, hi_e)
     f_sh, y_sh = f_te[sl].to(dev), y_te[sl].to(dev)
     def time_eval(fn, reps=5):
         for _ in range(2):
@@ -305,20 +306,8 @@ def run_ours(args):
     gemm_ms, _ = time_eval(lambda: _tc.logits_calibration(fb, Bop, 100.0 * mcs, y_sh, 10), reps=5)
     gemm_flops = 2.0 * f_sh.shape[0] * shp.C * shp.D * S
     # global metrics: all-reduce only the integer counters; AECE needs the gathered confidences
-    if world > 1:
-        h = hist.clone()
-        torch.distributed.all_reduce(h)
-        cnt = metrics.counters_from_hist(h, n_eval)
-        confs = [torch.empty(per, device=dev) for _ in range(world)]
-        cors = [torch.empty(per, dtype=torch.uint8, device=dev) for _ in range(world)]
-        pad = per - conf.numel()
-        torch.distributed.all_gather(confs, torch.cat([conf, conf.new_zeros(pad)]))
-        torch.distributed.all_gather(cors, torch.cat([correct, correct.new_zeros(pad)]))
-        conf_g = torch.cat([c[: min(per, n_eval - i * per)] for i, c in enumerate(confs)])
-        cor_g = torch.cat([c[: min(per, n_eval - i * per)] for i, c in enumerate(cors)])
-    else:
-        cnt = metrics.counters_from_hist(hist, n_eval)
-        conf_g, cor_g = conf, correct
+    hist_g, conf_g, cor_g = cdist.global_calibration(hist, conf, correct, n_eval, world)
+    cnt = metrics.counters_from_hist(hist_g, n_eval)
     ece, _ = metrics.ece_from_counters(cnt)
     _, out = metrics.aece_pass(conf_g, cor_g, 10)
     aece, _ = metrics.aece_from_bins(out, n_eval, 10)

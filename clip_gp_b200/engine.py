@@ -20,7 +20,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import _lib, metrics
+from . import _lib, dist, metrics
 from ._lib import GpArgs, GpBwdArgs, KERNEL_IDS
 from .gp_template_weigher import GaussianProcessTemplateWeighter
 
@@ -63,9 +63,7 @@ class GPAdapterEngine:
         # is 2,2,1,1,1,1,1,1); every rank draws its slice [s_offset, s_offset + S_local) of the same Philox stream
         if cfg.S_train < cfg.world:
             raise ValueError(f"S_train={cfg.S_train} < world={cfg.world}: shard the batch instead")
-        base, extra = divmod(cfg.S_train, cfg.world)
-        self.S_local = base + (1 if cfg.rank < extra else 0)
-        self.s_offset = cfg.rank * base + min(cfg.rank, extra)
+        self.s_offset, self.S_local = dist.sample_split(cfg.S_train, cfg.rank, cfg.world)
         self.E = gpw._templates.detach().contiguous()
         self.X = gpw._templates_red.detach().contiguous()
         self.Z = gpw.variational_strategy.inducing_points.detach().clone().contiguous()
