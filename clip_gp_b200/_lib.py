@@ -32,7 +32,7 @@ class GpArgs(C.Structure):
         ("eps", C.c_void_p), ("eps_sc", c_i64), ("eps_st", c_i64), ("eps_ss", c_i64),
         ("rng_state", C.c_void_p), ("s_offset", c_i64), ("S_total", c_i64),
         ("w", C.c_void_p), ("kl", C.c_void_p), ("L", C.c_void_p), ("A", C.c_void_p), ("R", C.c_void_p),
-        ("status", C.c_void_p),
+        ("status", C.c_void_p), ("Ksave", C.c_void_p),
     ]
 
 
@@ -59,6 +59,7 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_void_p]),
     "clipgp_gp_smem_bytes": (c_i64, [c_i64, c_i64, c_i64, C.c_int]),
     "clipgp_gp_forward": (C.c_int, [C.POINTER(GpArgs), C.c_void_p]),
+    "clipgp_gp_warp_path_ok": (C.c_int, [c_i64, c_i64, c_i64]),
     "clipgp_gp_backward": (C.c_int, [C.POINTER(GpArgs), C.POINTER(GpBwdArgs), C.c_void_p]),
     "clipgp_proto_forward": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, c_i64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

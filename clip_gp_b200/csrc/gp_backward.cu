@@ -10,75 +10,112 @@
 namespace clipgp {
 namespace gp {
 
-// One Gram block's contribution to the kernel adjoints.
+// One Gram block's contribution to the kernel adjoints, from the kernel values the forward pass saved.
 //   dK   : [nA][ld] float (smem) upstream gradient of K(A rows, B rows)
-//   raw  : [nA][ld] float scratch (receives r^2 / dot, then W = d loss / d raw)
-//   q    : [d] accumulates sum_ij W_ij (u_ik - u_jk)^2      (rbf / matern; u = z * invls)
-//   dzl  : [d] accumulates the gradient of one designated row (rowA as A-row and/or rowB as B-row), or -1
+//   Wm   : [nA][ld] float (smem) in: K values of the block; out: W = d loss / d raw  (raw = r^2 or <a,b>)
+//   q    : [d] accumulates sum_ij W_ij (u_ik - u_jk)^2 (rbf / matern; u = z / lengthscale), evaluated in expanded form
+//          sum_i r_i u_ik^2 + sum_j c_j u_jk^2 - 2 sum_i u_ik (W U_B)_ik  with 4x4 register tiles for W U_B
+//   dzl  : [d] accumulates the gradient of one designated row (rowA as an A row and/or rowB as a B row; -1 = none)
+//   rs/cs: [>= nA] / [>= nB] scratch for the row / column sums of W
 // Returns this thread's partial of d loss / d amp (outputscale or variance).
-__device__ float kernel_adjoint_block(const float* dK, int ld, float* raw, const float* gA, int nA, const float* gB,
+__device__ float kernel_adjoint_block(const float* dK, int ld, float* Wm, const float* gA, int nA, const float* gB,
                                       int nB, int d, int kt, float amp, const float* invls, float* tileA, float* tileB,
-                                      float* q, float* dzl, int rowA, int rowB) {
-    gram_block<float>(nullptr, 0, raw, ld, gA, nA, gB, nB, d, kt, amp, invls, tileA, tileB);
+                                      float* q, float* dzl, int rowA, int rowB, float* rs, float* cs) {
     float damp = 0.f;
+    const float inv_amp = 1.f / amp;
     for (int idx = threadIdx.x; idx < nA * nB; idx += blockDim.x) {
         const int i = idx / nB, j = idx - i * nB;
-        const float r = raw[i * ld + j];
+        const float kv = Wm[i * ld + j];
         const float g = dK[i * ld + j];
         float wv;
         if (kt == CLIPGP_KERNEL_RBF) {
-            const float e = expf(-0.5f * r);
-            damp += g * e;                         // dK/d os = exp(-r2/2)
-            wv = -0.5f * g * amp * e;              // dK/d r2 = -K/2
+            damp += g * kv * inv_amp;              // dK/d os = exp(-r2/2) = K / os
+            wv = -0.5f * g * kv;                   // dK/d r2 = -K/2
         } else if (kt == CLIPGP_KERNEL_MATERN12) {
-            const float rr = sqrtf(fmaxf(r, 1e-30f));
-            wv = (r > 1e-30f) ? (-0.5f * g * expf(-rr) / rr) : 0.f;   // clamp_min(1e-30) kills the gradient
+            const float rr = -logf(kv);            // K = exp(-r)
+            wv = (kv < 1.f && rr > 0.f) ? (-0.5f * g * kv / rr) : 0.f;   // r2 <= 1e-30 (K == 1): clamp kills the gradient
         } else {
-            damp += g * r;                         // dK/d v = <a,b>
+            damp += g * kv * inv_amp;              // dK/d v = <a,b> = K / v
             wv = g * amp;                          // dK/d dot = v
         }
-        raw[i * ld + j] = wv;
+        Wm[i * ld + j] = wv;
     }
     __syncthreads();
     const bool same = (gA == gB);
     const bool dot = (kt == CLIPGP_KERNEL_LINEAR);
+    if (!dot) {
+        for (int i = threadIdx.x; i < nA; i += blockDim.x) { float t = 0.f; for (int j = 0; j < nB; ++j) t += Wm[i * ld + j]; rs[i] = t; }
+        for (int j = threadIdx.x; j < nB; j += blockDim.x) { float t = 0.f; for (int i = 0; i < nA; ++i) t += Wm[i * ld + j]; cs[j] = t; }
+    }
     const int pA = pad4(nA), pB = pad4(nB);
-    // thread -> (column k of the chunk, slice of the A rows)
-    const int kk = threadIdx.x % KC, part = threadIdx.x / KC, nparts = blockDim.x / KC;
+    constexpr int KQ = KC / 4;
+    const int vtiles = (pA >> 2) * KQ;
     for (int k0 = 0; k0 < d; k0 += KC) {
         __syncthreads();
         load_chunk(tileA, gA, nA, pA, d, k0, dot ? nullptr : invls);
         if (!same) load_chunk(tileB, gB, nB, pB, d, k0, dot ? nullptr : invls);
         __syncthreads();
         const float* tB = same ? tileA : tileB;
-        const int k = k0 + kk;
-        if (k < d && part < nparts) {
-            if (!dot) {
-                float qk = 0.f;
-                for (int i = part; i < nA; i += nparts) {
-                    const float ui = tileA[i * KCP + kk];
-                    const float* wrow = raw + i * ld;
-                    for (int j = 0; j < nB; ++j) {
-                        const float df = ui - tB[j * KCP + kk];
-                        qk = fmaf(wrow[j] * df, df, qk);
+        if (!dot) {
+            for (int tile = threadIdx.x; tile < vtiles; tile += blockDim.x) {
+                const int it = tile / KQ, kq = tile - it * KQ;
+                const int i0 = it * 4;
+                float v[4][4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) v[x][y] = 0.f;
+                const float* w0 = Wm + (i0 + 0 < nA ? i0 + 0 : 0) * ld;
+                const float* w1 = Wm + (i0 + 1 < nA ? i0 + 1 : 0) * ld;
+                const float* w2 = Wm + (i0 + 2 < nA ? i0 + 2 : 0) * ld;
+                const float* w3 = Wm + (i0 + 3 < nA ? i0 + 3 : 0) * ld;
+                const float* ub = tB + kq * 4;
+                for (int j = 0; j < nB; ++j) {
+                    const float w[4] = {w0[j], w1[j], w2[j], w3[j]};
+                    const float u[4] = {ub[j * KCP], ub[j * KCP + 1], ub[j * KCP + 2], ub[j * KCP + 3]};
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) v[x][y] = fmaf(w[x], u[y], v[x][y]);
+                }
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int k = k0 + kq * 4 + y;
+                    if (k < d) {
+                        float accq = 0.f;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const int i = i0 + x;
+                            if (i < nA) { const float ua = tileA[i * KCP + kq * 4 + y]; accq += ua * (rs[i] * ua - 2.f * v[x][y]); }
+                        }
+                        atomicAdd(&q[k], accq);
                     }
                 }
-                atomicAdd(&q[k], qk);
             }
-            if (part == 0 && (rowA >= 0 || rowB >= 0)) {       // the one learnable row: O(nA + nB) per column
+            if (threadIdx.x < KC && k0 + threadIdx.x < d) {            // column term sum_j c_j u_jk^2
+                const int kk = threadIdx.x;
+                float accq = 0.f;
+                for (int j = 0; j < nB; ++j) { const float uj = tB[j * KCP + kk]; accq = fmaf(cs[j] * uj, uj, accq); }
+                atomicAdd(&q[k0 + kk], accq);
+            }
+        }
+        if ((rowA >= 0 || rowB >= 0) && threadIdx.x >= blockDim.x - KC) {   // the one learnable row: O(nA + nB) per column
+            const int kk = threadIdx.x - (blockDim.x - KC);
+            const int k = k0 + kk;
+            if (k < d) {
                 float dz = 0.f;
                 if (rowA >= 0) {
                     const float ui = tileA[rowA * KCP + kk];
                     for (int j = 0; j < nB; ++j) {
                         const float uj = tB[j * KCP + kk];
-                        dz = fmaf(raw[rowA * ld + j], dot ? uj : (ui - uj), dz);
+                        dz = fmaf(Wm[rowA * ld + j], dot ? uj : (ui - uj), dz);
                     }
                 }
                 if (rowB >= 0) {
                     const float uj = tB[rowB * KCP + kk];
                     for (int i = 0; i < nA; ++i) {
                         const float ui = tileA[i * KCP + kk];
-                        dz = fmaf(raw[i * ld + rowB], dot ? ui : (uj - ui), dz);
+                        dz = fmaf(Wm[i * ld + rowB], dot ? ui : (uj - ui), dz);
                     }
                 }
                 if (!dot) dz *= 2.f * invls[k];
@@ -189,7 +226,14 @@ __global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_a
             }
         }
         __syncthreads();
-        cholesky_adjoint<float>(R, ldt, invdR, dSig, dSig, ldt, T, scrF);   // dSig <- dSigma (full, symmetric)
+        if ((tid >> 5) == 0) warp_cholesky_rev<float>(R, ldt, invdR, dSig, ldt, T);
+        __syncthreads();
+        for (int idx = tid; idx < T * T; idx += blockDim.x) {                // dSig <- dSigma (full, symmetric)
+            const int i = idx / T, j = idx - i * T;
+            if (i > j) { const float v = 0.5f * dSig[i * ldt + j]; dSig[i * ldt + j] = v; dSig[j * ldt + i] = v; }
+        }
+        __syncthreads();
+        (void)scrF;
     }
 
     // =========================== B3 ===========================
@@ -260,12 +304,14 @@ __global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_a
             dLd[i * ldn + j] = -s;
         }
         __syncthreads();
-        cholesky_adjoint<double>(Ld, ldn, invd, dLd, dLd, ldn, n, scrD);
+        if ((tid >> 5) == 0) warp_cholesky_rev<double>(Ld, ldn, invd, dLd, ldn, n);
+        __syncthreads();
         for (int idx = tid; idx < n * n; idx += blockDim.x) {
             const int i = idx / n, j = idx - i * n;
-            dKzz[i * ldn + j] = (float)dLd[i * ldn + j];
+            dKzz[i * ldn + j] = (float)sym_from_rev<double>(dLd, ldn, i, j);
         }
         __syncthreads();
+        (void)scrD;
     }
 
     // =========================== B5 ===========================
@@ -274,9 +320,10 @@ __global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_a
         float* raw = reinterpret_cast<float*>(smem + Y.p_raw);
         float* tileA = reinterpret_cast<float*>(smem + Y.p_tiles);
         float* tileB = tileA + (size_t)pad4(n) * KCP;
-        int alias = 0;
-        if (a.x_is_z_prefix == 2) alias = 1;
-        else if (a.x_is_z_prefix == 1) alias = rows_identical(Xc, Zc, T * d);
+        const float* ks = a.Ksave + (size_t)c * (1 + n * n + n * T + T * T);
+        const int alias = ks[0] != 0.f;
+        float* rs = reinterpret_cast<float*>(smem + Y.rs);
+        float* cs = reinterpret_cast<float*>(smem + Y.cs);
         float damp = 0.f;
         if (alias) {
             // one block: K(Z,Z) carries dK_ZZ + [dK_ZX | 0] + [[dK_XX, 0],[0, 0]]
@@ -286,18 +333,24 @@ __global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_a
                 if (j < T) v += (float)dAd[i * ldt + j];
                 if (i < T && j < T) v += dSig[i * ldt + j];
                 dKzz[i * ldn + j] = v;
+                raw[i * ldn + j] = ks[1 + idx];
             }
             __syncthreads();
-            damp += kernel_adjoint_block(dKzz, ldn, raw, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB, qls, dzl, n - 1, n - 1);
+            damp += kernel_adjoint_block(dKzz, ldn, raw, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB, qls, dzl, n - 1, n - 1, rs, cs);
         } else {
             for (int idx = tid; idx < n * T; idx += blockDim.x) {
                 const int i = idx / T, j = idx - i * T;
                 dKzx[i * ldt + j] = (float)dAd[i * ldt + j];
             }
+            for (int idx = tid; idx < n * n; idx += blockDim.x) { const int i = idx / n, j = idx - i * n; raw[i * ldn + j] = ks[1 + idx]; }
             __syncthreads();
-            damp += kernel_adjoint_block(dKzz, ldn, raw, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB, qls, dzl, n - 1, n - 1);
-            damp += kernel_adjoint_block(dKzx, ldt, raw, Zc, n, Xc, T, d, kt, amp, invls, tileA, tileB, qls, dzl, n - 1, -1);
-            damp += kernel_adjoint_block(dSig, ldt, raw, Xc, T, Xc, T, d, kt, amp, invls, tileA, tileB, qls, dzl, -1, -1);
+            damp += kernel_adjoint_block(dKzz, ldn, raw, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB, qls, dzl, n - 1, n - 1, rs, cs);
+            for (int idx = tid; idx < n * T; idx += blockDim.x) { const int i = idx / T, j = idx - i * T; raw[i * ldt + j] = ks[1 + n * n + idx]; }
+            __syncthreads();
+            damp += kernel_adjoint_block(dKzx, ldt, raw, Zc, n, Xc, T, d, kt, amp, invls, tileA, tileB, qls, dzl, n - 1, -1, rs, cs);
+            for (int idx = tid; idx < T * T; idx += blockDim.x) { const int i = idx / T, j = idx - i * T; raw[i * ldt + j] = ks[1 + n * n + n * T + idx]; }
+            __syncthreads();
+            damp += kernel_adjoint_block(dSig, ldt, raw, Xc, T, Xc, T, d, kt, amp, invls, tileA, tileB, qls, dzl, -1, -1, rs, cs);
         }
         const float damp_tot = block_sum(damp, red);
         if (tid == 0) {
@@ -327,8 +380,8 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
                        a->d >= 1 && a->S >= 1, "gp_backward: unsupported shape");
     CLIPGP_REQUIRE(a->kernel_type >= 0 && a->kernel_type <= 2, "gp_backward: Unsupported kernel: %d", a->kernel_type);
     if (a->C == 0) return CLIPGP_OK;
-    CLIPGP_REQUIRE(a->Z && a->X && a->var_mean && a->chol_var && a->w && a->L && a->A && a->R,
-                   "gp_backward: forward tensors missing (Z, X, var_mean, chol_var, w, L, A, R)");
+    CLIPGP_REQUIRE(a->Z && a->X && a->var_mean && a->chol_var && a->w && a->L && a->A && a->R && a->Ksave,
+                   "gp_backward: forward tensors missing (Z, X, var_mean, chol_var, w, L, A, R, Ksave)");
     CLIPGP_REQUIRE(a->eps || a->rng_state, "gp_backward: need eps or rng_state");
     CLIPGP_REQUIRE(b->dw && b->dvar_mean && b->dchol_var, "gp_backward: dw / dvar_mean / dchol_var is NULL");
     if (a->kernel_type != CLIPGP_KERNEL_LINEAR) CLIPGP_REQUIRE(a->raw_lengthscale, "gp_backward: raw_lengthscale is NULL");

@@ -12,7 +12,7 @@ constexpr int KC = 32;         // feature-dim chunk streamed through shared memo
 constexpr int KCP = KC + 1;    // padded row stride of a chunk tile (conflict-free row access)
 constexpr int kMaxTiles = 3;   // 4x4 register tiles per thread: 3*128 >= ceil(65/4)^2 = 289
 
-__device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
+__host__ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
 
 // Copy columns [k0, k0+KC) of a row-major [rows, d] global matrix into a [rows_pad][KCP] tile, optionally
 // scaled per column (inverse length-scales).  Rows >= rows and columns >= d are zero-filled.
@@ -84,15 +84,25 @@ __device__ __forceinline__ int rows_identical(const float* __restrict__ X, const
 
 // acc[t] += sum_k op(a_ik, b_jk) over one chunk for this thread's 4x4 tiles.
 // DOT: a*b ; otherwise (a-b)^2.
+// Tile enumeration.  General blocks: row-major over (ti, tj).  Symmetric blocks (A rows == B rows): only the
+// tiles with tj >= ti, enumerated row by row; the lower part is mirrored when the block is written out.
+__device__ __forceinline__ int num_tiles(int tiles_m, int tiles_n, bool sym) {
+    return sym ? (tiles_m * (tiles_m + 1)) / 2 : tiles_m * tiles_n;
+}
+__device__ __forceinline__ void tile_coords(int tile, int tiles_n, bool sym, int& ti, int& tj) {
+    if (!sym) { ti = tile / tiles_n; tj = tile - ti * tiles_n; return; }
+    int row = 0, left = tile, len = tiles_n;
+    while (left >= len) { left -= len; --len; ++row; }
+    ti = row; tj = row + left;
+}
+
 template <bool DOT>
 __device__ __forceinline__ void gram_chunk(float (&acc)[kMaxTiles][16], const float* __restrict__ tA,
-                                           const float* __restrict__ tB, int tiles_m, int tiles_n) {
-    const int ntiles = tiles_m * tiles_n;
+                                           const float* __restrict__ tB, const int (&tis)[kMaxTiles], const int (&tjs)[kMaxTiles]) {
 #pragma unroll
     for (int t = 0; t < kMaxTiles; ++t) {
-        const int tile = threadIdx.x + t * blockDim.x;
-        if (tile < ntiles) {
-            const int ti = tile / tiles_n, tj = tile - ti * tiles_n;
+        if (tis[t] >= 0) {
+            const int ti = tis[t], tj = tjs[t];
             const float* pa = tA + (ti * 4) * KCP;
             const float* pb = tB + (tj * 4) * KCP;
 #pragma unroll 4
@@ -126,28 +136,33 @@ __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ 
                            const float* __restrict__ gA, int nA, const float* __restrict__ gB, int nB, int d,
                            int kernel_type, float amp, const float* __restrict__ inv_ls, float* tileA, float* tileB) {
     const bool same = (gA == gB);
+    const bool sym = same && (nA == nB);
     const int pA = pad4(nA), pB = pad4(nB);
     const int tiles_m = pA >> 2, tiles_n = pB >> 2;
     const bool dot = (kernel_type == CLIPGP_KERNEL_LINEAR);
     float acc[kMaxTiles][16];
+    int tis[kMaxTiles], tjs[kMaxTiles];
+    const int ntiles = num_tiles(tiles_m, tiles_n, sym);
 #pragma unroll
-    for (int t = 0; t < kMaxTiles; ++t)
+    for (int t = 0; t < kMaxTiles; ++t) {
+        const int tile = threadIdx.x + t * blockDim.x;
+        tis[t] = -1; tjs[t] = 0;
+        if (tile < ntiles) tile_coords(tile, tiles_n, sym, tis[t], tjs[t]);
 #pragma unroll
         for (int x = 0; x < 16; ++x) acc[t][x] = 0.f;
+    }
     for (int k0 = 0; k0 < d; k0 += KC) {
         __syncthreads();
         load_chunk(tileA, gA, nA, pA, d, k0, dot ? nullptr : inv_ls);
         if (!same) load_chunk(tileB, gB, nB, pB, d, k0, dot ? nullptr : inv_ls);
         __syncthreads();
-        if (dot) gram_chunk<true>(acc, tileA, same ? tileA : tileB, tiles_m, tiles_n);
-        else gram_chunk<false>(acc, tileA, same ? tileA : tileB, tiles_m, tiles_n);
+        if (dot) gram_chunk<true>(acc, tileA, same ? tileA : tileB, tis, tjs);
+        else gram_chunk<false>(acc, tileA, same ? tileA : tileB, tis, tjs);
     }
-    const int ntiles = tiles_m * tiles_n;
 #pragma unroll
     for (int t = 0; t < kMaxTiles; ++t) {
-        const int tile = threadIdx.x + t * blockDim.x;
-        if (tile < ntiles) {
-            const int ti = tile / tiles_n, tj = tile - ti * tiles_n;
+        if (tis[t] >= 0) {
+            const int ti = tis[t], tj = tjs[t];
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -155,8 +170,13 @@ __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ 
                     const int i = ti * 4 + x, j = tj * 4 + y;
                     if (i < nA && j < nB) {
                         const float a = acc[t][x * 4 + y];
+                        const OutT kv = (OutT)kernel_value(kernel_type, a, amp);
                         if (raw_out) raw_out[i * ldr + j] = a;
-                        if (out) out[i * ldo + j] = (OutT)kernel_value(kernel_type, a, amp);
+                        if (out) out[i * ldo + j] = kv;
+                        if (sym && tj > ti) {      // mirror (diagonal tiles hold both halves already)
+                            if (raw_out) raw_out[j * ldr + i] = a;
+                            if (out) out[j * ldo + i] = kv;
+                        }
                     }
                 }
         }
@@ -188,6 +208,79 @@ __device__ bool block_cholesky(T* __restrict__ A, int n, int ld, T* __restrict__
     }
     __syncthreads();
     return fail;
+}
+
+// Left-looking lower Cholesky executed by ONE warp (call from a single warp; lanes own rows lane, lane+32, lane+64),
+// in place on the lower triangle, __syncwarp only.  invd[j] = 1 / L[j][j].  Returns true (warp-uniformly) when a
+// pivot was not strictly positive.  n <= 96.
+template <typename T>
+__device__ bool warp_cholesky(T* __restrict__ A, int n, int ld, T* __restrict__ invd) {
+    const int lane = threadIdx.x & 31;
+    bool fail = false;
+    for (int j = 0; j < n; ++j) {
+        T s[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int i = lane + 32 * u;
+            T acc = (T)0;
+            if (i >= j && i < n) {
+                acc = A[i * ld + j];
+                const T* ri = A + i * ld;
+                const T* rj = A + j * ld;
+                for (int k = 0; k < j; ++k) acc -= ri[k] * rj[k];
+            }
+            s[u] = acc;
+        }
+        const int slot = j >> 5;
+        const T sj = __shfl_sync(0xffffffffu, slot == 0 ? s[0] : (slot == 1 ? s[1] : s[2]), j & 31);
+        if (!(sj > (T)0)) fail = true;
+        const T inv = (T)1 / sqrt(sj);
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int i = lane + 32 * u;
+            if (i > j && i < n) A[i * ld + j] = s[u] * inv;
+        }
+        if (lane == 0) { A[j * ld + j] = sj * inv; invd[j] = inv; }
+        __syncwarp();
+    }
+    return fail;
+}
+
+// Adjoint of L = chol(A) by ONE warp: Murray's level-2 reverse sweep ("Differentiation of the Cholesky decomposition",
+// 2016).  In: L (lower), invd, G = dL (lower triangle; destroyed).  Out (in G): the strict lower triangle holds the SUM of
+// the sensitivities of A_ij and A_ji, the diagonal the sensitivity of A_ii; i.e. the symmetric gradient is
+// dA = (tril(G,-1) + tril(G,-1)^T) / 2 + diag(G)   (use sym_from_rev below).
+template <typename T>
+__device__ void warp_cholesky_rev(const T* __restrict__ L, int ldl, const T* __restrict__ invd, T* __restrict__ G, int ld, int n) {
+    const int lane = threadIdx.x & 31;
+    for (int j = n - 1; j >= 0; --j) {
+        const T inv = invd[j];
+        T part = (T)0;
+        for (int i = j + 1 + lane; i < n; i += 32) part += L[i * ldl + j] * G[i * ld + j];
+        part = warp_sum(part);
+        const T db = (G[j * ld + j] - part * inv) * inv;            // (d_bar - c^T c_bar / d) / d
+        __syncwarp();
+        for (int i = j + 1 + lane; i < n; i += 32) G[i * ld + j] *= inv;   // c_bar /= d
+        __syncwarp();
+        for (int k = lane; k < j; k += 32) {                            // r_bar -= d_bar r + c_bar^T B
+            T sacc = G[j * ld + k] - db * L[j * ldl + k];
+            for (int i = j + 1; i < n; ++i) sacc -= G[i * ld + j] * L[i * ldl + k];
+            G[j * ld + k] = sacc;
+        }
+        for (int i = j + 1 + lane; i < n; i += 32) {                    // B_bar -= c_bar r
+            const T cbi = G[i * ld + j];
+            T* gi = G + i * ld;
+            const T* rj = L + j * ldl;
+            for (int k = 0; k < j; ++k) gi[k] -= cbi * rj[k];
+        }
+        if (lane == 0) G[j * ld + j] = db * (T)0.5;
+        __syncwarp();
+    }
+}
+template <typename T>
+__device__ __forceinline__ T sym_from_rev(const T* __restrict__ G, int ld, int i, int j) {
+    return i == j ? G[i * ld + i] : (T)0.5 * (i > j ? G[i * ld + j] : G[j * ld + i]);
 }
 
 // Solve L X = B in place (B is [n][ncol], leading dim ldb); one thread per column.

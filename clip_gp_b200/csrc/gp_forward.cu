@@ -4,12 +4,16 @@
 //
 // Roofline: HBM/latency.  Algorithmic bytes per class: Z [n,d] + X [T,d] + lengthscale [d] + Lq [n,n] + m [n]
 // read, w [S,T] + saved L (fp64 n^2), A (nT), R (T^2) written.
+#include <stdlib.h>
+
 #include "gp_layout.cuh"
 
 namespace clipgp {
 namespace gp {
 
-__global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_args a) {
+// gram_only != 0: classes whose test inputs alias the inducing rows only get their kernel block K_ZZ computed and saved
+// (the register-resident warp kernel of gp_warp_forward.cu continues from it); un-aliased classes run the whole path here.
+__global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_args a, const int gram_only) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int c = blockIdx.x, tid = threadIdx.x;
     const int T = (int)a.T, n = (int)a.n, d = (int)a.d, S = (int)a.S;
@@ -35,22 +39,27 @@ __global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_ar
     float* fbuf = pool;                       // [SCH][ldt]
     float* ebuf = pool + (size_t)SCH * ldt;   // [T][SCH]
     __shared__ float red[32];
+    __shared__ int s_flag;
+    const int warp_id = tid >> 5;
 
     const float* Zc = a.Z + (size_t)c * n * d;
     const float* Xc = a.X + (size_t)c * T * d;
     const int kt = a.kernel_type;
 
     // ---- hyper-parameters (gpytorch Positive constraint = softplus)
-    if (kt != CLIPGP_KERNEL_LINEAR)
-        for (int k = tid; k < d; k += blockDim.x) invls[k] = 1.f / softplusf(a.raw_lengthscale[(size_t)c * d + k]);
+    const bool compact = gram_only && a.x_is_z_prefix == 2;      // small launch: only the Gram scratch exists in smem
     float amp = 1.f;
     if (kt == CLIPGP_KERNEL_RBF) amp = softplusf(a.raw_outputscale[c]);
     if (kt == CLIPGP_KERNEL_LINEAR) amp = softplusf(a.raw_variance[c]);
-    for (int idx = tid; idx < n * n; idx += blockDim.x) {
-        const int i = idx / n, j = idx - i * n;
-        Lq[i * ldn + j] = (j <= i) ? a.chol_var[(size_t)c * n * n + idx] : 0.f;   // CholeskyVariationalDistribution.forward mask
+    if (!compact) {
+        if (kt != CLIPGP_KERNEL_LINEAR)
+            for (int k = tid; k < d; k += blockDim.x) invls[k] = 1.f / softplusf(a.raw_lengthscale[(size_t)c * d + k]);
+        for (int idx = tid; idx < n * n; idx += blockDim.x) {
+            const int i = idx / n, j = idx - i * n;
+            Lq[i * ldn + j] = (j <= i) ? a.chol_var[(size_t)c * n * n + idx] : 0.f;   // CholeskyVariationalDistribution.forward mask
+        }
+        for (int i = tid; i < n; i += blockDim.x) mvec[i] = a.var_mean[(size_t)c * n + i];
     }
-    for (int i = tid; i < n; i += blockDim.x) mvec[i] = a.var_mean[(size_t)c * n + i];
 
     // ---- do the test inputs repeat the first T inducing rows? (frozen template rows, gp_template_weigher.py:72-79)
     int alias = 0;
@@ -58,10 +67,34 @@ __global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_ar
     else if (a.x_is_z_prefix == 1) alias = rows_identical(Xc, Zc, T * d);  // verify on the device
 
     // ---- Gram blocks
+    if (gram_only && alias) {
+        // compact carve-up (the launch only provides K0 + invls + one tile when aliasing is guaranteed by the caller)
+        float* K0c = reinterpret_cast<float*>(smem);
+        float* ilsc = K0c + D.f_nn;
+        float* tilec = ilsc + ((d + 3) & ~3);
+        if (kt != CLIPGP_KERNEL_LINEAR)
+            for (int k = tid; k < d; k += blockDim.x) ilsc[k] = 1.f / softplusf(a.raw_lengthscale[(size_t)c * d + k]);
+        __syncthreads();
+        gram_block<float>(K0c, ldn, nullptr, 0, Zc, n, Zc, n, d, kt, amp, ilsc, tilec, tilec);
+        float* ks = a.Ksave + (size_t)c * (1 + n * n + n * T + T * T);
+        if (tid == 0) { ks[0] = 1.f; if (a.status) a.status[c] = 0; }
+        for (int idx = tid; idx < n * n; idx += blockDim.x) { const int i = idx / n, j = idx - i * n; ks[1 + idx] = K0c[i * ldn + j]; }
+        return;
+    }
     gram_block<float>(K0, ldn, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB);
     if (!alias) {
         gram_block<double>(Ad, ldt, nullptr, 0, Zc, n, Xc, T, d, kt, amp, invls, tileA, tileB);
         gram_block<float>(Sig, ldt, nullptr, 0, Xc, T, Xc, T, d, kt, amp, invls, tileA, tileB);
+    }
+    // ---- kernel blocks saved for the adjoint (it then needs no second pass over Z / X for the kernel values)
+    if (a.Ksave) {
+        float* ks = a.Ksave + (size_t)c * (1 + n * n + n * T + T * T);
+        if (tid == 0) ks[0] = alias ? 1.f : 0.f;
+        for (int idx = tid; idx < n * n; idx += blockDim.x) { const int i = idx / n, j = idx - i * n; ks[1 + idx] = K0[i * ldn + j]; }
+        if (!alias) {
+            for (int idx = tid; idx < n * T; idx += blockDim.x) { const int i = idx / T, j = idx - i * T; ks[1 + n * n + idx] = (float)Ad[i * ldt + j]; }
+            for (int idx = tid; idx < T * T; idx += blockDim.x) { const int i = idx / T, j = idx - i * T; ks[1 + n * n + n * T + idx] = Sig[i * ldt + j]; }
+        }
     }
     for (int idx = tid; idx < n * n; idx += blockDim.x) {
         const int i = idx / n, j = idx - i * n;
@@ -80,7 +113,12 @@ __global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_ar
     __syncthreads();
 
     // ---- L = chol64(K_ZZ + 1e-4 I);  A = L^-1 K_ZX
-    const bool failL = block_cholesky<double>(Ld, n, ldn, invd);
+    if (warp_id == 0) {
+        const bool f = warp_cholesky<double>(Ld, n, ldn, invd);
+        if (tid == 0) s_flag = f ? 1 : 0;
+    }
+    __syncthreads();
+    const bool failL = s_flag != 0;
     trsm_lower_left<double>(Ld, ldn, invd, Ad, ldt, n, T);
     for (int idx = tid; idx < n * T; idx += blockDim.x) {
         const int i = idx / T, j = idx - i * T;
@@ -100,14 +138,38 @@ __global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_ar
         mu[j] = s + (a.mean_x ? a.mean_x[(size_t)c * T + j] : 0.f);
     }
     __syncthreads();
-    // ---- Sigma = K_XX + 1e-4 I + Bm^T Bm - A^T A   (lower triangle)
-    for (int idx = tid; idx < T * T; idx += blockDim.x) {
-        const int i = idx / T, j = idx - i * T;
-        if (j <= i) {
-            float s = 0.f;
-            for (int k = 0; k < n; ++k)
-                s += Bm[k * ldt + i] * Bm[k * ldt + j] - Af[k * ldt + i] * Af[k * ldt + j];
-            Sig[i * ldt + j] = (Sig[i * ldt + j] + (i == j ? 1e-4f : 0.f)) + s;
+    // ---- Sigma = K_XX + 1e-4 I + Bm^T Bm - A^T A   (lower triangle; 4x4 register tiles over (i, j), k = inducing index)
+    {
+        const int tt = pad4(T) >> 2;
+        const int ntl = (tt * (tt + 1)) / 2;
+        for (int tile = tid; tile < ntl; tile += blockDim.x) {
+            int tj, ti;
+            tile_coords(tile, tt, true, tj, ti);          // tj <= ti  (lower-triangular tiles)
+            float accs[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) accs[x][y] = 0.f;
+            for (int k = 0; k < n; ++k) {
+                float bi[4], bj[4], ai[4], aj[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int ci = ti * 4 + x, cj = tj * 4 + x;
+                    bi[x] = ci < T ? Bm[k * ldt + ci] : 0.f; ai[x] = ci < T ? Af[k * ldt + ci] : 0.f;
+                    bj[x] = cj < T ? Bm[k * ldt + cj] : 0.f; aj[x] = cj < T ? Af[k * ldt + cj] : 0.f;
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) accs[x][y] += bi[x] * bj[y] - ai[x] * aj[y];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int i = ti * 4 + x, j = tj * 4 + y;
+                    if (i < T && j <= i) Sig[i * ldt + j] = (Sig[i * ldt + j] + (i == j ? 1e-4f : 0.f)) + accs[x][y];
+                }
         }
     }
     __syncthreads();
@@ -121,9 +183,15 @@ __global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_ar
             if (j <= i) R[i * ldt + j] = Sig[i * ldt + j] + (i == j ? jit : 0.f);
         }
         __syncthreads();
-        failR = block_cholesky<float>(R, T, ldt, invdR);
+        if (warp_id == 0) {
+            const bool f = warp_cholesky<float>(R, T, ldt, invdR);
+            if (tid == 0) s_flag = f ? 1 : 0;
+        }
+        __syncthreads();
+        failR = s_flag != 0;
         if (!failR) break;
         ++retries;
+        __syncthreads();     // everyone has read s_flag before the next attempt overwrites it
     }
     if (tid == 0 && a.status) a.status[c] = failL ? -2 : (failR ? -1 : retries);
 
@@ -224,17 +292,42 @@ extern "C" int64_t clipgp_gp_smem_bytes(int64_t T, int64_t n, int64_t d, int bac
     return backward ? (int64_t)gp::make_bwd_layout(D).total : (int64_t)gp::make_fwd_layout(D).total;
 }
 
+int clipgp_gp_forward_warp_launch(const clipgp_gp_args* a, cudaStream_t st);   // gp_warp_forward.cu
+extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
+
+static bool use_warp_path(const clipgp_gp_args* a) {
+    static const bool disabled = (getenv("CLIPGP_GP_BLOCK_ONLY") != nullptr);
+    if (disabled || !clipgp_gp_warp_path_ok(a->T, a->n, a->d) || a->x_is_z_prefix == 0) return false;
+    if (a->Ksave == nullptr) return false;                                  // the two kernels hand over through the saved K block
+    if ((reinterpret_cast<uintptr_t>(a->Z) | reinterpret_cast<uintptr_t>(a->X)) & 15u) return false;
+    return true;
+}
+
 extern "C" int clipgp_gp_forward(const clipgp_gp_args* a, void* stream) {
     int rc = gp_check_args(a, "gp_forward");
     if (rc != CLIPGP_OK) return rc;
     if (a->C == 0) return CLIPGP_OK;
-    const size_t smem = (size_t)clipgp_gp_smem_bytes(a->T, a->n, a->d, 0);
+    const bool warp_path = use_warp_path(a);
+    size_t smem = (size_t)clipgp_gp_smem_bytes(a->T, a->n, a->d, 0);
     CLIPGP_REQUIRE(smem > 0 && smem <= 227 * 1024, "gp_forward: needs %zu bytes of shared memory (> 227 KB); reduce d", smem);
     static size_t smem_set = 0;   // raise the opt-in limit only when needed (keeps the call out of graph captures)
     if (smem > smem_set) {
         CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    gp::gp_forward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a);
+    if (warp_path) {
+        // two-kernel fast path: (1) block-per-class streamed Gram -> K_ZZ saved; (2) warp-per-class register-resident
+        // factorisations / sampling / sparsemax from the saved block.  Classes whose test inputs do not alias the inducing
+        // rows (x_is_z_prefix == 1 and the device check fails) are completed by kernel (1) itself.
+        if (a->x_is_z_prefix == 2) {
+            const gp::Dims D = gp::make_dims((int)a->T, (int)a->n, (int)a->d);
+            smem = sizeof(float) * (D.f_nn + (size_t)((a->d + 3) & ~3) + (size_t)gp::pad4((int)a->n) * gp::KCP) + 16;
+        }
+        gp::gp_forward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 1);
+        rc = check_launch("gp_forward_kernel(gram)");
+        if (rc != CLIPGP_OK) return rc;
+        return clipgp_gp_forward_warp_launch(a, (cudaStream_t)stream);
+    }
+    gp::gp_forward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 0);
     return check_launch("gp_forward_kernel");
 }

@@ -60,7 +60,7 @@ __host__ __device__ inline FwdLayout make_fwd_layout(const Dims& D) {
 //   B5 (kernel adjoint)                      : dKzx | raw | tiles        (dKzz stays where B4 left it)
 struct BwdLayout {
     size_t Ld, invd, dAd;                                   // double
-    size_t Af, dSig, mvec, dmu, invls, invdR, dls, dzl, pool;
+    size_t Af, dSig, mvec, dmu, invls, invdR, dls, dzl, rs, cs, pool;
     size_t p_R, p_scrF, p_df, p_eps;                        // B1 (offsets from start of smem)
     size_t p_Lq, p_Bm, p_dBm, p_dAf;                        // B3
     size_t p_scrD, p_dLd, p_dKzz;                           // B4
@@ -82,6 +82,8 @@ __host__ __device__ inline BwdLayout make_bwd_layout(const Dims& D) {
     L.invdR = o; o = align16(o + 4 * (size_t)D.T);
     L.dls = o;   o = align16(o + 4 * (size_t)(D.d > 0 ? D.d : 1));
     L.dzl = o;   o = align16(o + 4 * (size_t)(D.d > 0 ? D.d : 1));
+    L.rs = o;    o = align16(o + 4 * (size_t)(D.n + 3));
+    L.cs = o;    o = align16(o + 4 * (size_t)(D.n + 3));
     L.pool = o;
     size_t p = o;
     L.p_R = p;     p = align16(p + 4 * D.f_tt);

@@ -132,6 +132,7 @@ class GPAdapterEngine:
         self.Asave = torch.empty(Cn, n, T, **f32)
         self.Rsave = torch.empty(Cn, T, T, **f32)
         self.status = torch.zeros(Cn, dtype=torch.int32, device=dev)
+        self.Ksave = torch.empty(Cn, 1 + n * n + n * T + T * T, **f32)
         self.P_hat = torch.empty(S, Cn, D, **f32)
         self.P_norm = torch.empty(S, Cn, **f32)
         self.P_mean = torch.empty(Cn, D, **f32)
@@ -155,6 +156,7 @@ class GPAdapterEngine:
         a.s_offset, a.S_total = self.s_offset, self.cfg.S_train
         a.w, a.kl, a.L, a.A, a.R, a.status = (self.w.data_ptr(), self.kl.data_ptr(), self.Lsave.data_ptr(),
                                               self.Asave.data_ptr(), self.Rsave.data_ptr(), self.status.data_ptr())
+        a.Ksave = self.Ksave.data_ptr()
         self.gp_args = a
         b = GpBwdArgs()
         b.dw = self.dw.data_ptr()
@@ -291,6 +293,7 @@ class GPAdapterEngine:
         a.S, a.s_offset, a.S_total = S, 0, S
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
+        a.Ksave = None
         Pm = torch.empty(Cn, D, **f32)
         with torch.cuda.device(self.dev):
             _lib.check(lib.clipgp_gp_forward(C.byref(a), st), "gp_forward(eval)")
@@ -359,6 +362,7 @@ class GPAdapterEngine:
         a.S, a.s_offset, a.S_total = S, 0, S
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
+        a.Ksave = None
         P_hat = torch.empty(S, Cn, D, **f32)
         seg = 3 if split else 1
         Bop = torch.empty(Cn, S * seg * D, dtype=torch.bfloat16, device=self.dev)

@@ -56,6 +56,7 @@ class GPWeightsFunction(torch.autograd.Function):
         Af = torch.empty(Cn, n, T, dtype=torch.float32, device=dev)
         Rf = torch.empty(Cn, T, T, dtype=torch.float32, device=dev)
         status = torch.empty(Cn, dtype=torch.int32, device=dev)
+        Ksave = torch.empty(Cn, 1 + n * n + n * T + T * T, dtype=torch.float32, device=dev)
         a = GpArgs()
         a.kernel_type = KERNEL_IDS[kernel_type]
         a.x_is_z_prefix = 1 if (alias_check and n >= T) else 0
@@ -73,11 +74,13 @@ class GPWeightsFunction(torch.autograd.Function):
         a.s_offset, a.S_total = int(s_offset), int(S_total if S_total else S)
         a.w, a.kl, a.L, a.A, a.R, a.status = (w.data_ptr(), kl.data_ptr(), Lf.data_ptr(), Af.data_ptr(), Rf.data_ptr(),
                                               status.data_ptr())
+        a.Ksave = Ksave.data_ptr()
         with torch.cuda.device(dev):
             _lib.check(lib.clipgp_gp_forward(C.byref(a), _lib.stream_ptr(dev)), "clipgp_gp_forward")
         ctx.kernel_type = kernel_type
         ctx.args = a
         ctx.keep = (Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, rng_state, w, Lf, Af, Rf)
+        ctx.ksave = Ksave
         ctx.status = status
         ctx.mark_non_differentiable(status)
         return w, kl, status

@@ -99,12 +99,16 @@ typedef struct clipgp_gp_args {
     float* A;                     /* out [C,n,T] saved: interp_term L^-1 K_ZX */
     float* R;                     /* out [C,T,T] saved: lower Cholesky factor of Sigma */
     int32_t* status;              /* out [C]: 0 ok; k>0: Sigma needed k jitter retries; <0: not positive definite */
+    float* Ksave;                 /* out [C, 1 + n*n + n*T + T*T] saved kernel blocks: [alias flag | K_ZZ (no jitter) | K_ZX | K_XX];
+                                     K_ZX / K_XX are written only when the alias flag is 0.  Required by clipgp_gp_backward */
 } clipgp_gp_args;
 
 /* Dynamic shared memory the forward / backward kernel needs for (T, n, d); 0 if unsupported. */
 int64_t clipgp_gp_smem_bytes(int64_t T, int64_t n, int64_t d, int backward);
 
 int clipgp_gp_forward(const clipgp_gp_args* args, void* stream);
+/* 1 if (T, n, d) is served by the warp-per-class register-resident fast path (T <= 32, n == T+1, d % 4 == 0). */
+int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
 
 /* Adjoint of clipgp_gp_forward.  `fwd` must be the argument block of the forward call (same inputs, with
  * w/L/A/R holding its outputs).  Upstream: dw [S,C,T]; dkl [C] or NULL (then dkl_scalar multiplies every
