@@ -84,6 +84,7 @@ _SIGNATURES = {
     "clipgp_tc_tip_logits": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
                                        c_i64, C.c_void_p]),
     "clipgp_cast_bf16": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
+    "clipgp_cast_bf16_transpose": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
     "clipgp_tc_gemm_store": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_float, C.c_void_p, c_i64,
                                        C.c_void_p]),
     "clipgp_tc_logits_calibration": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_float, C.c_void_p,

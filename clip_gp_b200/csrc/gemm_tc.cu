@@ -35,6 +35,7 @@ struct Params {
     int M, N, K, Ka;
     int num_m, num_n, num_k;
     int n_per_item;             // consecutive n tiles one work item covers (num_n for ROWSTATS, 1 for STORE)
+    int k_splits, kb_per_split; // EPI_STORE only: the K blocks are split over k_splits work items that accumulate atomically
     int mode;
     float alpha;
     float* C; long long ldc;    // STORE target / optional logits copy in ROWSTATS
@@ -150,18 +151,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    const int groups = p.num_n / p.n_per_item;              // work items per m block
-    const int num_items = p.num_m * groups;
+    const int groups = p.num_n / p.n_per_item;              // work items per (m block, k split)
+    const int num_items = p.num_m * groups * p.k_splits;
 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                const int m_blk = item / groups, n_first = (item - m_blk * groups) * p.n_per_item;
+                const int ks = item % p.k_splits, mg = item / p.k_splits;
+                const int m_blk = mg / groups, n_first = (mg - m_blk * groups) * p.n_per_item;
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_k, kb0 + p.kb_per_split);
                 for (int nn = 0; nn < p.n_per_item; ++nn) {
                     const int n_blk = n_first + nn;
-                    for (int kb = 0; kb < p.num_k; ++kb) {
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         unsigned char* sa = smem + stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -179,11 +182,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int ks = item % p.k_splits;
+                const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_k, kb0 + p.kb_per_split);
                 for (int nn = 0; nn < p.n_per_item; ++nn) {
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
-                    for (int kb = 0; kb < p.num_k; ++kb) {
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         fence_after();
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -191,9 +196,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
                         for (int k = 0; k < BK / UK; ++k)
                             umma_bf16(tmem_d, adesc + (uint64_t)(k * (UK * 2 / 16)), bdesc + (uint64_t)(k * (UK * 2 / 16)), kIdesc,
-                                      (kb | k) != 0 ? 1u : 0u);
+                                      (kb > kb0 || k != 0) ? 1u : 0u);
                         umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
-                        if (kb == p.num_k - 1) umma_commit(&tmem_full[acc]);
+                        if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -206,7 +211,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            const int m_blk = item / groups, n_first = (item - m_blk * groups) * p.n_per_item;
+            const int mg = item / p.k_splits;
+            const int m_blk = mg / groups, n_first = (mg - m_blk * groups) * p.n_per_item;
             const int row = m_blk * BM + q * 32 + lane;
             float run_m = -FLT_MAX, run_s = 0.f; int run_am = 0x7fffffff;
             for (int nn = 0; nn < p.n_per_item; ++nn) {
@@ -242,7 +248,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         }
                     } else if (p.C != nullptr && row < p.M) {
                         float* dst = p.C + (long long)row * p.ldc + col0;
-                        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                        if (p.k_splits > 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < ncols) atomicAdd(dst + j, p.alpha * __uint_as_float(r[j]));
+                        } else if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
                                 *reinterpret_cast<float4*>(dst + j) = make_float4(p.alpha * __uint_as_float(r[j]), p.alpha * __uint_as_float(r[j + 1]),
@@ -357,7 +367,21 @@ static int launch(const void* A, long long M, long long Ka, const void* B, long 
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.Ka = (int)Ka;
     p.num_m = (int)((M + BM - 1) / BM); p.num_n = (int)((N + BN - 1) / BN); p.num_k = (int)((K + BK - 1) / BK);
     p.n_per_item = (p.mode == EPI_ROWSTATS) ? p.num_n : 1;
-    const int items = p.num_m * (p.num_n / p.n_per_item);
+    p.k_splits = 1; p.kb_per_split = p.num_k;
+    if (p.mode == EPI_STORE) {
+        // split K when the output grid cannot fill the SMs and K is long (skinny adjoint GEMMs, e.g. d f_hat = dlogits P_hat)
+        const int tiles = p.num_m * p.num_n;
+        if (tiles * 2 <= num_sms() && p.num_k >= 16) {
+            int want = num_sms() / tiles;
+            if (want > p.num_k / 4) want = p.num_k / 4;
+            if (want > 1) {
+                p.kb_per_split = (p.num_k + want - 1) / want;
+                p.k_splits = (p.num_k + p.kb_per_split - 1) / p.kb_per_split;
+                CLIPGP_CUDA(cudaMemset2DAsync(p.C, sizeof(float) * p.ldc, 0, sizeof(float) * N, M, st));
+            }
+        }
+    }
+    const int items = p.num_m * (p.num_n / p.n_per_item) * p.k_splits;
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     static bool attr_set = false;
     if (!attr_set) {

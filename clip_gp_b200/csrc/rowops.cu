@@ -153,6 +153,36 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     }
 }
 
+// Transposing variant: x fp32 [R, K] (row stride ldx) -> out bf16 [K, segs*R] with out[k*out_ld + g*seg_stride + r];
+// 32x32 shared-memory tiles keep both the global read and the global write coalesced.  Modes as cast_bf16_kernel.
+__global__ void __launch_bounds__(256) cast_bf16_t_kernel(const float* __restrict__ x, int64_t R, int64_t K, int64_t ldx,
+                                                          __nv_bfloat16* __restrict__ out, int64_t out_ld, int64_t seg_stride, int mode) {
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = r0 + ty + 8 * i, k = k0 + tx;
+        tile[ty + 8 * i][tx] = (r < R && k < K) ? x[r * ldx + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t k = k0 + ty + 8 * i, r = r0 + tx;
+        if (k < K && r < R) {
+            const float v = tile[tx][ty + 8 * i];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            __nv_bfloat16* o = out + k * out_ld + r;
+            o[0] = hi;
+            if (mode != 0) {
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                o[seg_stride] = (mode == 1) ? hi : lo;
+                o[2 * seg_stride] = (mode == 1) ? lo : hi;
+            }
+        }
+    }
+}
+
 __global__ void increment_kernel(int64_t* p, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) *p += by; }
 
 }  // namespace clipgp
@@ -238,4 +268,16 @@ extern "C" int clipgp_cast_bf16(const float* x, int64_t R, int64_t K, int64_t ld
     if (blocks > cap) blocks = cap;
     cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)K, ldx, (__nv_bfloat16*)out, out_ld, seg_stride, mode);
     return check_launch("cast_bf16_kernel");
+}
+
+extern "C" int clipgp_cast_bf16_transpose(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld,
+                                          int64_t seg_stride, int mode, void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && K >= 0 && ldx >= K, "cast_bf16_transpose: bad shape");
+    CLIPGP_REQUIRE(mode >= 0 && mode <= 2, "cast_bf16_transpose: mode must be 0, 1 or 2");
+    if (R == 0 || K == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(x && out, "cast_bf16_transpose: NULL pointer");
+    dim3 grid((unsigned)((K + 31) / 32), (unsigned)((R + 31) / 32));
+    CLIPGP_REQUIRE(grid.y <= 65535, "cast_bf16_transpose: R too large");
+    cast_bf16_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, K, ldx, (__nv_bfloat16*)out, out_ld, seg_stride, mode);
+    return check_launch("cast_bf16_t_kernel");
 }

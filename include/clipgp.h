@@ -202,7 +202,12 @@ int clipgp_sum_accumulate(const float* x, int64_t n, float scale, float* out, vo
 int clipgp_cast_bf16(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld, int64_t seg_stride, int mode,
                      void* stream);
 
-/* C[M,N] (fp32, row stride ldc) = alpha * A B^T. */
+/* Transposing form: fp32 [R,K] -> bf16 [K, R] (or the split [K, 3R] layouts) with out[k*out_ld + g*seg_stride + r]; produces the
+ * K-major operands of the adjoint GEMMs (dlogits^T, f_hat^T, P_hat^T) without an fp32 transpose. */
+int clipgp_cast_bf16_transpose(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld, int64_t seg_stride,
+                               int mode, void* stream);
+
+/* C[M,N] (fp32, row stride ldc) = alpha * A B^T.  Skinny outputs with long K are split over K (atomic accumulation). */
 int clipgp_tc_gemm_store(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K, float alpha,
                          float* C, int64_t ldc, void* stream);
 
