@@ -40,6 +40,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--eval-n", type=int, default=50000)
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
+                    help="GEMMs of the train step: fp32 FFMA | tcgen05 split-bf16 (fp32-grade) | tcgen05 bf16")
+    ap.add_argument("--no-fullbatch", action="store_true", help="skip the B = N_train full-batch (tensor-bound) leg")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other-precision timings of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="also print the per-kernel time table")
     return ap.parse_args()
@@ -188,7 +192,8 @@ def run_ours(args):
     ls = bench_lengthscale(wl["E"], shp.d) if shp.kernel == "rbf" else None
     torch.manual_seed(1)
     gpw = GaussianProcessTemplateWeighter(wl["E"].to(dev), _Cfg(shp.kernel, shp.d), lengthscale=ls).to(dev)
-    cfg = EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world)
+    cfg = EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world,
+                       precision=args.precision)
     eng = GPAdapterEngine(gpw, cfg)
     f_all = wl["f_train"].to(dev)
     y_all = wl["y_train"].to(dev)
@@ -206,33 +211,38 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
+    def time_steps(e, steps, warmup):
+        """Device time of `steps` optimisation steps (CUDA events around each step on the launching stream, L2 flushed
+        between steps outside the events, max over ranks).  Returns total ms."""
+        Bsz = e.B
+        nbb = max(1, f_all.shape[0] // Bsz)
+        for it in range(max(warmup, 3)):
+            lo = (it % nbb) * Bsz
+            e.train_step(f_all[lo:lo + Bsz], y_all[lo:lo + Bsz])
+        sync_all()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        sync_all()
+        for it in range(steps):
+            lo = ((warmup + it) % nbb) * Bsz
+            flush.fill_(0.0)                               # L2 flush between timed iterations (outside the events)
+            e.in_feat.copy_(f_all[lo:lo + Bsz]); e.in_lab.copy_(y_all[lo:lo + Bsz])
+            evs[it][0].record()
+            if e._graph is not None:
+                e._graph.replay()
+            else:
+                e._launch_step()
+            evs[it][1].record()
+        sync_all()
+        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        return float(tt.item())
+
     # ---------------- device-resident timing
-    for it in range(max(args.warmup, 3)):
-        lo, hi = batch(it)
-        eng.train_step(f_all[lo:hi], y_all[lo:hi])
-    sync_all()
-    launches0 = _lib.launch_count()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
-    for it in range(args.steps):
-        lo, hi = batch(args.warmup + it)
-        flush.fill_(0.0)                                   # L2 flush between timed iterations (outside the events)
-        eng.in_feat.copy_(f_all[lo:hi]); eng.in_lab.copy_(y_all[lo:hi])
-        evs[it][0].record()
-        if eng._graph is not None:
-            eng._graph.replay()
-        else:
-            eng._launch_step()
-        evs[it][1].record()
-    sync_all()
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = time_steps(eng, args.steps, args.warmup)
     loss_last = float(eng.loss.item())
     # kernels per step: counted from one eager (un-graphed) step: graph replays do not pass through the C ABI
     eng_launch0 = _lib.launch_count()
@@ -260,6 +270,45 @@ def run_ours(args):
 
     # ---------------- per-kernel times (CUDA events on the launching stream, eager launches, L2 flushed)
     ktimes = profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5)
+
+    # ---------------- the same step at the other GEMM precisions (short runs)
+    train_variants = {}
+    if not args.no_variants:
+        for prec in ("fp32", "bf16x3", "bf16"):
+            if prec == args.precision:
+                train_variants[prec] = {"ms_per_step": ms_total / args.steps, "steps_per_s": args.steps / (ms_total * 1e-3)}
+                continue
+            ev = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank,
+                                                   world=world, precision=prec))
+            msv = time_steps(ev, 10, 3)
+            train_variants[prec] = {"ms_per_step": msv / 10, "steps_per_s": 10 / (msv * 1e-3)}
+            del ev
+
+    # ---------------- full-batch leg (B = N_train = C * shots): the tensor-bound form of the same step
+    fullbatch = None
+    if not args.no_fullbatch and args.precision != "fp32":
+        Bf = f_all.shape[0]
+        fullbatch = {"B": Bf, "note": "per-sample MC cross-entropy over the whole cached training set; logits [B, S*C] materialised in fp32"}
+        for prec in ("bf16", "bf16x3"):
+            ef = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=Bf, shots=shp.shots, seed=1234, rank=rank,
+                                                   world=world, precision=prec))
+            msf = time_steps(ef, 5, 3) / 5
+            kt = profile_step_kernels(ef, f_all, y_all, shp, flush, reps=2, B=Bf)
+            entry = {"ms_per_step": msf, "steps_per_s": 1e3 / msf, "img_per_s": Bf * 1e3 / msf}
+            gem = {k: v for k, v in kt.items() if k.startswith("tc_gemm_store") and v.get("flops")}
+            if gem:
+                # the three logit contractions: logits, d P_hat, d f_hat  (2*B*S*C*D algorithmic flops each)
+                big = sorted(gem.items(), key=lambda kv: -kv[1]["flops"])[:3]
+                fl = sum(v["flops"] for _, v in big); tm = sum(v["ms"] for _, v in big) * 1e-3
+                pk_ = peaks()
+                entry["logit_gemms"] = {"bound": "tensor", "flops": fl, "ms": tm * 1e3, "achieved": fl / tm / 1e12, "unit": "TFLOP/s",
+                                        "peak": pk_["bf16_tflops"], "frac": fl / tm / 1e12 / pk_["bf16_tflops"],
+                                        "hw_flops_factor": 3 if prec == "bf16x3" else 1,
+                                        "per_gemm": {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} for k, v in big}}
+                entry["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in kt.items()}
+            fullbatch[prec] = entry
+            del ef
+        torch.cuda.empty_cache()
 
     # ---------------- eval leg: MC-averaged logits + acc/ECE/AECE over this rank's shard of the test features
     n_eval = args.eval_n
@@ -332,18 +381,22 @@ def run_ours(args):
                     "peak_source": pk["source"]}
         else:
             C_, D_, B_ = shp.C, shp.D, shp.B
-            fl = 2.0 * B_ * eng.S_local * C_ * D_
+            fl = ktimes[dom].get("flops") or 2.0 * B_ * eng.S_local * C_ * D_
             roof = {"kernel": dom, "bound": "tensor", "achieved": fl / dur / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": fl / dur / 1e12 / pk["bf16_tflops"], "traffic": None, "avg_launch_us": dur * 1e6,
                     "share_of_step": ktimes[dom]["ms"] / sum(v["ms"] for v in ktimes.values()), "peak_source": pk["source"],
-                    "note": "fp32 FFMA GEMM (exact mode) reported against the bf16 tensor peak"}
+                    "note": ("tcgen05 GEMM, algorithmic flops (split operands issue 3x the MMAs)" if "tc_gemm" in dom else
+                             "fp32 FFMA GEMM (exact mode) reported against the bf16 tensor peak")}
     line = {
         "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+        "data": "synthetic",
         "config": {"workload": f"{args.workload}: C={shp.C} T={shp.T} D={shp.D} d={shp.d} S={S} B={shp.B} shots={shp.shots} kernel={shp.kernel}, "
                                f"per-sample MC cross-entropy + KL + L2, AdamW; MC samples sharded over {world} rank(s)",
-                   "l2_flush": "256 MB device buffer written between timed steps", "precision": "fp32 (FFMA GEMMs, fp64 K_ZZ Cholesky)",
+                   "l2_flush": "256 MB device buffer written between timed steps", "precision": {"fp32": "fp32 (FFMA GEMMs, fp64 K_ZZ Cholesky)",
+                                 "bf16x3": "tcgen05 GEMMs on split-bf16 operands (fp32-grade products; the reference's GPU path is TF32), fp32 everywhere else, fp64 K_ZZ Cholesky",
+                                 "bf16": "tcgen05 bf16 GEMMs, fp32 everywhere else, fp64 K_ZZ Cholesky"}[args.precision],
                    "cuda_graph": eng._graph is not None, "loss_last": loss_last},
         "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": shp.B * shp.D * 4 + shp.B * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches_per_step) * args.steps,
@@ -351,6 +404,8 @@ def run_ours(args):
         "clocks": clk,
         "roofline": roof,
         "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in ktimes.items()},
+        "train_variants": train_variants,
+        "train_fullbatch": fullbatch,
         "eval": {"metric": "eval_img_per_s (projection + MC-averaged logits + acc/ECE histogram, device resident)",
                  "value": n_eval / (eval_ms * 1e-3), "unit": "img/s", "n_images": n_eval, "ms": eval_ms, "S_eval": S,
                  "top1_acc": cnt.top1 * 100.0 / n_eval, "ece": ece, "aece": aece,
@@ -371,13 +426,16 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
-def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5):
+def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
     """Average device time of every kernel of one step, from CUDA events around each C-ABI launch (eager mode)."""
     from clip_gp_b200 import _lib
     lib = eng.lib
     names = ["clipgp_gemm_f32", "clipgp_rownorm_forward", "clipgp_gp_forward", "clipgp_proto_forward", "clipgp_softmax_ce",
              "clipgp_rownorm_backward", "clipgp_l2_identity", "clipgp_proto_backward", "clipgp_gp_backward", "clipgp_sum_accumulate",
-             "clipgp_adamw_step", "clipgp_increment"]
+             "clipgp_adamw_step", "clipgp_increment", "clipgp_tc_gemm_store", "clipgp_cast_bf16", "clipgp_cast_bf16_transpose"]
+    multi = ("gemm_f32", "adamw_step", "increment", "tc_gemm_store", "cast_bf16", "cast_bf16_transpose")
+    seg = getattr(eng, "tc_seg", 1)
+    B = B or shp.B
     records = []
 
     class Wrap:
@@ -389,7 +447,8 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5):
             e0.record()
             rc = self.fn(*a)
             e1.record()
-            records.append((self.name, e0, e1))
+            fl = 2.0 * a[1] * a[4] * a[5] / seg if self.name == "clipgp_tc_gemm_store" else None
+            records.append((self.name, e0, e1, fl))
             return rc
 
     class Proxy:
@@ -405,17 +464,18 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5):
         for r in range(reps):
             records.clear()
             flush.fill_(0.0)
-            eng.in_feat.copy_(f_all[: shp.B]); eng.in_lab.copy_(y_all[: shp.B])
+            eng.in_feat.copy_(f_all[:B]); eng.in_lab.copy_(y_all[:B])
             eng._launch_step()
             torch.cuda.synchronize()
             seen = {}
-            for name, e0, e1 in records:
+            for name, e0, e1, fl in records:
                 short = name.replace("clipgp_", "")
                 k = seen.get(short, 0); seen[short] = k + 1
-                key = f"{short}({k})" if short in ("gemm_f32", "adamw_step", "increment") else short
+                key = f"{short}({k})" if short in multi else short
                 d = out.setdefault(key, {"ms": 0.0, "calls": 0})
                 d["ms"] += e0.elapsed_time(e1) / reps
                 d["calls"] = 1
+                if fl: d["flops"] = fl
     finally:
         eng.lib = lib
     return out

@@ -5,6 +5,8 @@
 //   B3  Sigma = K_XX + jI + Bm^T Bm - A^T A, Bm = Lq^T A, mu = A^T m + mean_x  ->  dA, dLq, dm (+ KL terms)
 //   B4  A = L^-1 K_ZX in fp64: dK_ZX = L^-T dA, dL = -tril(dK_ZX A^T), dK_ZZ = chol64 adjoint
 //   B5  kernel adjoint: d lengthscale / outputscale / variance and the learnable inducing row Z[n-1]
+#include <stdlib.h>
+
 #include "gp_layout.cuh"
 
 namespace clipgp {
@@ -127,10 +129,60 @@ __device__ float kernel_adjoint_block(const float* dK, int ld, float* Wm, const 
     return damp;
 }
 
-__global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b) {
+// Kernel-adjoint stage of the warp path (gp_warp_backward.cu): d loss / d K block (scratch part of the class record in
+// Ksave) -> gradients of the length-scales, the output-scale / variance and the learnable inducing row, by one streamed pass
+// over Z with the 4x4 register tiles of kernel_adjoint_block.  One CTA per (aliased) class.
+__global__ void __launch_bounds__(kThreads) gp_kernel_adjoint_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int T = (int)a.T, n = (int)a.n, d = (int)a.d;
+    const int ldn = n | 1, dp = (d + 3) & ~3;
+    const float* ks = a.Ksave + (size_t)c * (1 + n * n + n * T + T * T);
+    if (ks[0] == 0.f) return;
+    float* dK = reinterpret_cast<float*>(smem);
+    float* raw = dK + n * ldn;
+    float* invls = raw + n * ldn;
+    float* qls = invls + dp;
+    float* dzl = qls + dp;
+    float* rs = dzl + dp;
+    float* cs = rs + ((n + 3) & ~3);
+    float* tileA = cs + ((n + 3) & ~3);
+    __shared__ float red[32];
+    const float* Zc = a.Z + (size_t)c * n * d;
+    const int kt = a.kernel_type;
+    if (kt != CLIPGP_KERNEL_LINEAR)
+        for (int k = tid; k < d; k += blockDim.x) invls[k] = 1.f / softplusf(a.raw_lengthscale[(size_t)c * d + k]);
+    float amp = 1.f;
+    if (kt == CLIPGP_KERNEL_RBF) amp = softplusf(a.raw_outputscale[c]);
+    if (kt == CLIPGP_KERNEL_LINEAR) amp = softplusf(a.raw_variance[c]);
+    for (int k = tid; k < d; k += blockDim.x) { qls[k] = 0.f; dzl[k] = 0.f; }
+    const float* dKt = ks + 1 + n * n;
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx - i * n;
+        dK[i * ldn + j] = dKt[idx];
+        raw[i * ldn + j] = ks[1 + idx];
+    }
+    __syncthreads();
+    const float damp = kernel_adjoint_block(dK, ldn, raw, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileA, qls, dzl, n - 1, n - 1, rs, cs);
+    const float damp_tot = block_sum(damp, red);
+    if (tid == 0) {
+        if (kt == CLIPGP_KERNEL_RBF && b.draw_outputscale) b.draw_outputscale[c] = damp_tot * sigmoidf_(a.raw_outputscale[c]);
+        if (kt == CLIPGP_KERNEL_LINEAR && b.draw_variance) b.draw_variance[c] = damp_tot * sigmoidf_(a.raw_variance[c]);
+    }
+    __syncthreads();
+    for (int k = tid; k < d; k += blockDim.x) {
+        if (kt != CLIPGP_KERNEL_LINEAR && b.draw_lengthscale)
+            b.draw_lengthscale[(size_t)c * d + k] = -2.f * qls[k] * invls[k] * sigmoidf_(a.raw_lengthscale[(size_t)c * d + k]);
+        if (b.dZ_last) b.dZ_last[(size_t)c * d + k] = dzl[k];
+    }
+}
+
+// only_unaliased != 0: classes served by the warp path (alias flag set) are skipped.
+__global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b, const int only_unaliased) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int c = blockIdx.x, tid = threadIdx.x;
     const int T = (int)a.T, n = (int)a.n, d = (int)a.d, S = (int)a.S;
+    if (only_unaliased && a.Ksave[(size_t)c * (1 + n * n + n * T + T * T)] != 0.f) return;
     const Dims D = make_dims(T, n, d);
     const BwdLayout Y = make_bwd_layout(D);
     const int ldn = D.ldn, ldt = D.ldt;
@@ -374,6 +426,8 @@ __global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_a
 
 using namespace clipgp;
 
+int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, cudaStream_t st);   // gp_warp_backward.cu
+
 extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, void* stream) {
     CLIPGP_REQUIRE(a && b, "gp_backward: NULL args");
     CLIPGP_REQUIRE(a->C >= 0 && a->T >= 1 && a->T <= CLIPGP_GP_MAX_T && a->n >= 1 && a->n <= CLIPGP_GP_MAX_T + 1 &&
@@ -394,6 +448,30 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
         CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    gp::gp_backward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b);
+    // warp path (T <= 32, aliased test inputs): dense algebra warp-per-class, then the streamed kernel adjoint; classes whose
+    // inputs are not aliased (x_is_z_prefix == 1 and the forward pass's device check failed) go through the block kernel
+    static const bool block_only = (getenv("CLIPGP_GP_BLOCK_ONLY") != nullptr);
+    const bool warp_path = !block_only && clipgp_gp_warp_path_ok(a->T, a->n, a->d) && a->x_is_z_prefix != 0 &&
+                           ((reinterpret_cast<uintptr_t>(a->Z) & 15u) == 0);
+    if (warp_path) {
+        int rc;
+        if (a->x_is_z_prefix != 2) {
+            gp::gp_backward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b, 1);
+            rc = check_launch("gp_backward_kernel(unaliased)");
+            if (rc != CLIPGP_OK) return rc;
+        }
+        rc = clipgp_gp_backward_warp_launch(a, b, (cudaStream_t)stream);
+        if (rc != CLIPGP_OK) return rc;
+        const int n = (int)a->n, d = (int)a->d, ldn = n | 1, dp = (d + 3) & ~3, np = (n + 3) & ~3;
+        const size_t sm2 = sizeof(float) * ((size_t)2 * n * ldn + 3 * dp + 2 * np + (size_t)gp::pad4(n) * gp::KCP) + 16;
+        static size_t sm2_set = 48 * 1024;
+        if (sm2 > sm2_set) {
+            CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_kernel_adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            sm2_set = sm2;
+        }
+        gp::gp_kernel_adjoint_kernel<<<(unsigned)a->C, gp::kThreads, sm2, (cudaStream_t)stream>>>(*a, *b);
+        return check_launch("gp_kernel_adjoint_kernel");
+    }
+    gp::gp_backward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b, 0);
     return check_launch("gp_backward_kernel");
 }

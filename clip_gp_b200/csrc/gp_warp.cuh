@@ -1,106 +1,91 @@
-// Warp-per-class, register-resident building blocks of the GP template weighter for T <= 32 templates
-// (n = T + 1 inducing points).  Lane i owns row i (or column i) of every T x T matrix in registers; the one
-// extra inducing row (the learnable class token) is carried as a border:
+// Warp-per-class building blocks of the GP template weighter for T <= 32 templates (n = T + 1 inducing points).
 //
-//     K_ZZ + jI = [ Kt + jI   k ]      L = [ Lt   0 ]      l = Lt^-1 k,   lam = sqrt(kappa + j - l.l)
-//                 [ k^T  kappa+j ]         [ l^T lam ]
-//
-// All loops over register arrays are fully unrolled (static register indices); cross-lane traffic is warp shuffles.
-// No shared-memory matrices, no block barriers: a CTA is just a bundle of independent warps, so many classes are in
-// flight per SM and their dependent chains (Cholesky columns, substitutions) overlap.
+// One warp owns one class; every matrix of the class (<= 33 x 33) lives in that warp's slice of shared memory and all
+// loops are run-time loops over it (compact code: a fully unrolled register-resident variant of these kernels was
+// instruction-fetch bound, ncu stall_no_inst ~ 40 %).  Conventions that keep shared-memory traffic conflict free:
+//   * row stride LD = 33 (odd): "lane = row" walks A[lane*LD + k] hit 32 distinct banks,
+//   * "lane = column" accesses A[k*LD + lane] are contiguous, the other operand of a product is a broadcast read.
+// Only __syncwarp() is used: a CTA is a single warp, so 7 classes are resident per SM (31 KB each) and the whole
+// class set of the ImageNet shape (1000 classes) is one wave on 148 SMs.
 #pragma once
-#include "common.cuh"
+#include "gp_common.cuh"
 
 namespace clipgp {
 namespace gpw {
 
-constexpr int TM = 32;            // lanes = max templates
+constexpr int LD = 33;                 // row stride (elements) of every per-class matrix
+constexpr int NN = 33 * LD + 3;        // elements per matrix slot (3 pad elements: 4-wide tiles may read past the last row)
 constexpr unsigned FULL = 0xffffffffu;
 
-template <typename T>
-__device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
+// Lane-strided walk over the elements of a dense row-major [rows, cols] array: f(idx, i, j), idx = i*cols + j.
+template <typename F>
+__device__ __forceinline__ void each(int rows, int cols, F f) {
+    const int total = rows * cols;
+    int i = 0, j = lane_id();
+    while (j >= cols) { j -= cols; ++i; }
+    for (int idx = lane_id(); idx < total; idx += 32) {
+        f(idx, i, j);
+        j += 32;
+        while (j >= cols) { j -= cols; ++i; }
+    }
 }
 
-// Row-per-lane lower Cholesky, in place: lane i holds a[0..31] = row i of a symmetric PD matrix (only columns <= i are
-// used / produced).  Right-looking, fully unrolled.  inv_diag = 1 / L[lane][lane].  Returns (uniformly) true on failure.
+// X <- L^-1 X (forward substitution), X is [n][ncol] with lane = column; two partial sums shorten the dependent chain.
 template <typename T>
-__device__ __forceinline__ bool chol_rows(T (&a)[TM], T& inv_diag) {
-    const int lane = threadIdx.x & 31;
-    bool fail = false;
-    inv_diag = (T)1;
-#pragma unroll
-    for (int j = 0; j < TM; ++j) {
-        const T ajj = bcast(a[j], j);
-        if (!(ajj > (T)0)) fail = true;
-        const T inv = rsqrt(ajj);
-        const T lij = a[j] * inv;                       // column j entry of this lane's row (valid for lane >= j)
-        if (lane == j) inv_diag = inv;
-        a[j] = (lane == j) ? ajj * inv : lij;
-#pragma unroll
-        for (int k = j + 1; k < TM; ++k) {
-            const T lkj = bcast(lij, k);                // L[k][j]
-            a[k] -= lij * lkj;                          // meaningful for lane >= k; upper part is never read
+__device__ __forceinline__ void trsm_lower_cols(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ X, int n, int ncol) {
+    const int lane = lane_id();
+    if (lane < ncol) {
+        for (int i = 0; i < n; ++i) {
+            const T* Li = L + i * LD;
+            T s0 = X[i * LD + lane], s1 = (T)0;
+            int k = 0;
+            for (; k + 1 < i; k += 2) { s0 -= Li[k] * X[k * LD + lane]; s1 -= Li[k + 1] * X[(k + 1) * LD + lane]; }
+            if (k < i) s0 -= Li[k] * X[k * LD + lane];
+            X[i * LD + lane] = (s0 + s1) * invd[i];
         }
     }
-    return fail;
+    __syncwarp();
 }
 
-// x = L^-1 b for a vector with one element per lane (b_i in lane i); L row-per-lane, inv_diag per lane.
+// X <- L^-T X (back substitution), lane = column.
 template <typename T>
-__device__ __forceinline__ T fwd_subst_vec(const T (&l)[TM], T inv_diag, T b) {
-    const int lane = threadIdx.x & 31;
-    T acc = b, x = (T)0;
-#pragma unroll
-    for (int m = 0; m < TM; ++m) {
-        if (lane == m) x = acc * inv_diag;              // finalise element m
-        const T xm = bcast(x, m);
-        if (lane > m) acc -= l[m] * xm;
-    }
-    return x;
-}
-
-// x = L^-T b (back substitution), vector with one element per lane.  Needs column access L[k][m] for k > m, i.e.
-// element m of lane k's row: broadcast per (m): each lane accumulates sum_{k>m} L[k][m] x_k by reduction over lanes.
-template <typename T>
-__device__ __forceinline__ T bwd_subst_vec(const T (&l)[TM], T inv_diag, T b) {
-    const int lane = threadIdx.x & 31;
-    T x = (T)0;
-    // x_m = (b_m - sum_{k>m} L[k][m] x_k) / L[m][m], m = 31 .. 0.  Lane k contributes l[m] * x_k once x_k is known.
-    T acc = b;                                          // lane m accumulates its own right-hand side
-#pragma unroll
-    for (int k = TM - 1; k >= 0; --k) {
-        if (lane == k) x = acc * inv_diag;
-        const T xk = bcast(x, k);
-        // lane m (< k) needs L[k][m] = element m of lane k's row: lane-dependent register index -> use a transposed copy
-        // supplied by the caller instead (see bwd_subst_cols); this vector form is only used with lt = transposed rows.
-        if (lane < k) acc -= l[k] * xk;                 // here l is the TRANSPOSED factor: l[k] = L[k][lane]
-    }
-    return x;
-}
-
-// 32 x 32 in-register transpose: lane i holds row i in a[0..31]; afterwards lane i holds column i.  5 butterfly stages.
-template <typename T>
-__device__ __forceinline__ void transpose_rows(T (&a)[TM]) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int j = 0; j < TM; ++j) {
-            if ((j & s) == 0) {
-                // exchange a[j + s] of the lower lane with a[j] of the upper lane
-                const T send = up ? a[j] : a[j + s];
-                const T recv = __shfl_xor_sync(FULL, send, s);
-                if (up) a[j] = recv; else a[j + s] = recv;
-            }
+__device__ __forceinline__ void trsm_lowerT_cols(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ X, int n, int ncol) {
+    const int lane = lane_id();
+    if (lane < ncol) {
+        for (int i = n - 1; i >= 0; --i) {
+            T s0 = X[i * LD + lane], s1 = (T)0;
+            int k = i + 1;
+            for (; k + 1 < n; k += 2) { s0 -= L[k * LD + i] * X[k * LD + lane]; s1 -= L[(k + 1) * LD + i] * X[(k + 1) * LD + lane]; }
+            if (k < n) s0 -= L[k * LD + i] * X[k * LD + lane];
+            X[i * LD + lane] = (s0 + s1) * invd[i];
         }
     }
+    __syncwarp();
 }
+
+// Sort-free sparsemax over the T <= 32 lanes (rank by value desc, index asc; entmax SparsemaxFunction.forward).
+__device__ __forceinline__ float sparsemax_lanes(float f, int T) {
+    const int lane = lane_id();
+    const bool valid = lane < T;
+    const float fm = warp_max(valid ? f : -INFINITY);
+    const float z = f - fm;
+    int kk = 0; float cs = 0.f;
+    for (int j = 0; j < T; ++j) {
+        const float zj = __shfl_sync(FULL, z, j);
+        const bool before = (zj > z) || (zj == z && j <= lane);
+        if (before) { ++kk; cs += zj; }
+    }
+    const bool sup = valid && ((float)kk * z > cs - 1.f);
+    const int cnt = __popc(__ballot_sync(FULL, sup));
+    const float tau = (warp_sum(sup ? z : 0.f) - 1.f) / (float)cnt;
+    return valid ? fmaxf(z - tau, 0.f) : 0.f;
+}
+
+// Offsets of the per-class record in Ksave ([alias flag | K_ZZ n*n | K_ZX n*T | K_XX T*T]).  For aliased classes the
+// K_ZX / K_XX part is unused by the forward pass; the adjoint uses it as scratch for d loss / d K_ZZ (n*n <= n*T + T*T for T >= 2).
+__device__ __forceinline__ size_t ksave_stride(int n, int T) { return (size_t)1 + (size_t)n * n + (size_t)n * T + (size_t)T * T; }
 
 }  // namespace gpw
 }  // namespace clipgp

@@ -1,0 +1,247 @@
+// GP template weighter, adjoint, warp-per-class dense-algebra part (T <= 32, n = T + 1, aliased test inputs).
+// Formulas: oracle/gp_manual.py::backward (validated there against torch.autograd); same results as the block kernel
+// of gp_backward.cu, which remains the general path.  Per class, from the saved L (fp64), A, R and w / dw / eps:
+//
+//   P1  sparsemax adjoint per sample -> dmu, dR = tril(sum_s df_s eps_s^T) -> dSigma (chol32 adjoint, Murray reverse sweep)
+//   P2  H = A dSigma, dBm = 2 Lq^T H, dA = -2 H + Lq dBm + m dmu^T, dLq = tril(A dBm^T) + KL term, dm = A dmu + KL term
+//       (Bm = Lq^T A is never needed: dBm = 2 Bm dSigma = 2 Lq^T (A dSigma))
+//   P3  fp64: dK_ZX = L^-T dA, dL = -tril(dK_ZX A^T), dK_ZZ = chol64 adjoint
+//   out d loss / d K_ZZ-block = dK_ZZ + [dK_ZX | 0] + [[dSigma, 0], [0, 0]]  (aliased inputs: one kernel block carries all three)
+//       written to the scratch part of the class record in Ksave; gp_kernel_adjoint_kernel (gp_backward.cu) turns it into the
+//       length-scale / output-scale / variance / learnable-row gradients with one streamed pass over Z.
+//
+// Shared memory per warp: three fp64 [33][33] regions re-used across the phases + A (fp32) = 31 KB, 7 classes per SM.
+#include "gp_warp.cuh"
+
+namespace clipgp {
+namespace gpw {
+
+struct BwdSmem {
+    double RA[NN];       // P2..P3: dA -> dK_ZX (fp64)
+    double RB[NN];       // P1: R | dR->dSigma (fp32 halves);  P2: dBm | dSigma;  P3: L (fp64)
+    double RC[NN];       // P2: Lq | H (fp32 halves);  P3: dL -> chol adjoint (fp64)
+    double invd[34];
+    float Af[NN];
+    float mvec[36];
+    float vecT[32];      // P1: 1 / R_ii;  P2: dmu
+};
+
+__global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b) {
+    extern __shared__ __align__(16) unsigned char smw[];
+    BwdSmem& s = *reinterpret_cast<BwdSmem*>(smw);
+    const int lane = threadIdx.x, c = blockIdx.x;
+    const int T = (int)a.T, n = T + 1, S = (int)a.S;
+    float* ks = a.Ksave + (size_t)c * ksave_stride(n, T);
+    if (ks[0] == 0.f) return;                      // un-aliased class: handled by the block kernel
+    float* dKt = ks + 1 + n * n;                   // scratch: d loss / d K block, [n][n]
+    const float dkl = b.dkl ? b.dkl[c] : b.dkl_scalar;
+    const int lt = lane < T ? lane : T - 1;        // clamped lane for row-per-lane walks
+
+    // =========================== P1 ===========================
+    float* R = reinterpret_cast<float*>(s.RB);
+    float* G = R + NN;
+    each(T, T, [&](int idx, int i, int j) { R[i * LD + j] = __ldg(a.R + (size_t)c * T * T + idx); G[i * LD + j] = 0.f; });
+    __syncwarp();
+    if (lane < T) s.vecT[lane] = 1.f / R[lane * LD + lane];
+    float dmu = 0.f;
+    {
+        uint64_t seed = 0, step = 0;
+        if (a.eps == nullptr) { seed = a.rng_state[0]; step = a.rng_state[1]; }
+        float* Grow = G + lt * LD;
+        for (int sidx = 0; sidx < S; ++sidx) {
+            const size_t off = ((size_t)sidx * a.C + c) * T;
+            const float wv = lane < T ? a.w[off + lane] : 0.f;
+            const bool sup = wv > 0.f;
+            const float g = sup ? b.dw[off + lane] : 0.f;
+            const int cnt = __popc(__ballot_sync(FULL, sup));
+            const float vhat = warp_sum(g) / (float)max(cnt, 1);
+            const float df = sup ? g - vhat : 0.f;              // entmax sparsemax backward
+            dmu += df;
+            float e = 0.f;
+            if (lane < T) {
+                if (a.eps) e = a.eps[(size_t)c * a.eps_sc + (size_t)lane * a.eps_st + (size_t)sidx * a.eps_ss];
+                else e = philox_normal(seed, step, ((uint64_t)c * T + lane) * (uint64_t)a.S_total + (uint64_t)(a.s_offset + sidx));
+            }
+            if (cnt == 0) continue;                             // warp-uniform
+            for (int k = 0; k < T; ++k) {                       // dR[lane][k] += df_lane eps_k (upper part is never read)
+                const float ek = __shfl_sync(FULL, e, k);
+                if (lane < T) Grow[k] = fmaf(df, ek, Grow[k]);
+            }
+        }
+    }
+    __syncwarp();
+    gp::warp_cholesky_rev<float>(R, LD, s.vecT, G, LD, T);
+    __syncwarp();
+    each(T, T, [&](int idx, int i, int j) {                     // G <- dSigma, full symmetric
+        if (i > j) { const float v = 0.5f * G[i * LD + j]; G[i * LD + j] = v; G[j * LD + i] = v; }
+    });
+    __syncwarp();
+    each(n, n, [&](int idx, int i, int j) { dKt[idx] = (i < T && j < T) ? G[i * LD + j] : 0.f; });
+    if (b.dmean_x && lane < T) b.dmean_x[(size_t)c * T + lane] = dmu;
+    if (lane < T) s.vecT[lane] = dmu;                           // 1 / R_ii is dead
+
+    // =========================== P2 ===========================
+    float* Lq = reinterpret_cast<float*>(s.RC);
+    float* H = Lq + NN;
+    float* dBm = R;                                             // R is dead
+    each(n, T, [&](int idx, int i, int j) { s.Af[i * LD + j] = __ldg(a.A + (size_t)c * n * T + idx); });
+    each(n, n, [&](int idx, int i, int j) { Lq[i * LD + j] = (j <= i) ? __ldg(a.chol_var + (size_t)c * n * n + idx) : 0.f; });
+    for (int i = lane; i < n; i += 32) s.mvec[i] = __ldg(a.var_mean + (size_t)c * n + i);
+    if (lane < 3) Lq[33 * LD + lane] = 0.f;
+    __syncwarp();
+    // H = A dSigma  (lane = column t)
+    for (int i0 = 0; i0 < n; i0 += 4) {
+        const float* a0 = s.Af + i0 * LD;
+        const float* a1 = s.Af + min(i0 + 1, n - 1) * LD;
+        const float* a2 = s.Af + min(i0 + 2, n - 1) * LD;
+        const float* a3 = s.Af + min(i0 + 3, n - 1) * LD;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int u = 0; u < T; ++u) {
+            const float ds = G[u * LD + lt];
+            acc0 = fmaf(a0[u], ds, acc0); acc1 = fmaf(a1[u], ds, acc1); acc2 = fmaf(a2[u], ds, acc2); acc3 = fmaf(a3[u], ds, acc3);
+        }
+        if (lane < T) {
+            H[i0 * LD + lane] = acc0;
+            if (i0 + 1 < n) H[(i0 + 1) * LD + lane] = acc1;
+            if (i0 + 2 < n) H[(i0 + 2) * LD + lane] = acc2;
+            if (i0 + 3 < n) H[(i0 + 3) * LD + lane] = acc3;
+        }
+    }
+    __syncwarp();
+    // dBm = 2 Lq^T H : dBm[i][t] = 2 sum_{k >= i} Lq[k][i] H[k][t]  (zeros above the diagonal of Lq make k >= i implicit)
+    for (int i0 = 0; i0 < n; i0 += 4) {
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int k = i0; k < n; ++k) {
+            const float hv = H[k * LD + lt];
+            const float* lq = Lq + k * LD + i0;
+            acc0 = fmaf(lq[0], hv, acc0); acc1 = fmaf(lq[1], hv, acc1); acc2 = fmaf(lq[2], hv, acc2); acc3 = fmaf(lq[3], hv, acc3);
+        }
+        if (lane < T) {
+            dBm[i0 * LD + lane] = 2.f * acc0;
+            if (i0 + 1 < n) dBm[(i0 + 1) * LD + lane] = 2.f * acc1;
+            if (i0 + 2 < n) dBm[(i0 + 2) * LD + lane] = 2.f * acc2;
+            if (i0 + 3 < n) dBm[(i0 + 3) * LD + lane] = 2.f * acc3;
+        }
+    }
+    __syncwarp();
+    // dA = -2 H + Lq dBm + m dmu^T  (lane = column t) -> fp64
+    for (int i0 = 0; i0 < n; i0 += 4) {
+        const float* l0 = Lq + i0 * LD;
+        const float* l1 = Lq + min(i0 + 1, n - 1) * LD;
+        const float* l2 = Lq + min(i0 + 2, n - 1) * LD;
+        const float* l3 = Lq + min(i0 + 3, n - 1) * LD;
+        const int kmax = min(i0 + 3, n - 1);
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int k = 0; k <= kmax; ++k) {
+            const float bv = dBm[k * LD + lt];
+            acc0 = fmaf(l0[k], bv, acc0); acc1 = fmaf(l1[k], bv, acc1); acc2 = fmaf(l2[k], bv, acc2); acc3 = fmaf(l3[k], bv, acc3);
+        }
+        const float accs[4] = {acc0, acc1, acc2, acc3};
+        if (lane < T) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int i = i0 + x;
+                if (i < n) s.RA[i * LD + lane] = (double)(-2.f * H[i * LD + lane] + accs[x] + s.mvec[i] * dmu);
+            }
+        }
+    }
+    // dLq = tril(A dBm^T) + dkl (Lq - diag(1 / Lq_ii))  (lane = column j < 32: row j of dBm), written straight to HBM
+    {
+        const float* brow = dBm + min(lane, n - 1) * LD;
+        float* out = b.dchol_var + (size_t)c * n * n;
+        for (int i0 = 0; i0 < n; i0 += 4) {
+            const float* a0 = s.Af + i0 * LD;
+            const float* a1 = s.Af + min(i0 + 1, n - 1) * LD;
+            const float* a2 = s.Af + min(i0 + 2, n - 1) * LD;
+            const float* a3 = s.Af + min(i0 + 3, n - 1) * LD;
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const float bv = brow[t];
+                acc0 = fmaf(a0[t], bv, acc0); acc1 = fmaf(a1[t], bv, acc1); acc2 = fmaf(a2[t], bv, acc2); acc3 = fmaf(a3[t], bv, acc3);
+            }
+            const float accs[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int i = i0 + x;
+                if (i < n && lane < n) {
+                    float v = 0.f;
+                    if (lane <= i) v = accs[x] + dkl * (Lq[i * LD + lane] - (i == lane ? 1.f / Lq[i * LD + i] : 0.f));
+                    out[(size_t)i * n + lane] = v;
+                }
+            }
+        }
+        if (n == 33) {                                          // column 32: zeros above the diagonal, one entry on it
+            float v = lane < T ? s.Af[32 * LD + lane] * dBm[32 * LD + lane] : 0.f;
+            v = warp_sum(v);
+            out[(size_t)lane * n + 32] = 0.f;
+            if (lane == 0) out[(size_t)32 * n + 32] = v + dkl * (Lq[32 * LD + 32] - 1.f / Lq[32 * LD + 32]);
+        }
+    }
+    // dm = A dmu + dkl m  (lane = row i)
+    for (int i = lane; i < n; i += 32) {
+        const float* arow = s.Af + i * LD;
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = fmaf(arow[t], s.vecT[t], acc);
+        b.dvar_mean[(size_t)c * n + i] = acc + dkl * s.mvec[i];
+    }
+    __syncwarp();
+
+    // =========================== P3 (fp64) ===========================
+    double* Ld = s.RB;
+    double* Gd = s.RC;
+    each(n, n, [&](int idx, int i, int j) { Ld[i * LD + j] = a.L[(size_t)c * n * n + idx]; });
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) s.invd[i] = 1.0 / Ld[i * LD + i];
+    __syncwarp();
+    trsm_lowerT_cols<double>(Ld, s.invd, s.RA, n, T);           // RA <- dK_ZX = L^-T dA
+    // dL = -tril(dK_ZX A^T)  (lane = column j < 32: row j of A)
+    {
+        const float* arow = s.Af + min(lane, n - 1) * LD;
+        for (int i0 = 0; i0 < n; i0 += 4) {
+            const double* d0 = s.RA + i0 * LD;
+            const double* d1 = s.RA + min(i0 + 1, n - 1) * LD;
+            const double* d2 = s.RA + min(i0 + 2, n - 1) * LD;
+            const double* d3 = s.RA + min(i0 + 3, n - 1) * LD;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            for (int t = 0; t < T; ++t) {
+                const double av = (double)arow[t];
+                acc0 += d0[t] * av; acc1 += d1[t] * av; acc2 += d2[t] * av; acc3 += d3[t] * av;
+            }
+            const double accs[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int i = i0 + x;
+                if (i < n && lane <= i && lane < n) Gd[i * LD + lane] = -accs[x];
+            }
+        }
+        if (n == 33) {
+            double v = lane < T ? s.RA[32 * LD + lane] * (double)s.Af[32 * LD + lane] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) Gd[32 * LD + 32] = -v;
+        }
+    }
+    __syncwarp();
+    gp::warp_cholesky_rev<double>(Ld, LD, s.invd, Gd, LD, n);
+    __syncwarp();
+    each(n, n, [&](int idx, int i, int j) {
+        float v = (float)gp::sym_from_rev<double>(Gd, LD, i, j);
+        if (j < T) v += (float)s.RA[i * LD + j];
+        dKt[idx] += v;                                          // same lane wrote dKt[idx] (the dSigma block) in P1
+    });
+}
+
+}  // namespace gpw
+}  // namespace clipgp
+
+using namespace clipgp;
+
+int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CLIPGP_CUDA(cudaFuncSetAttribute(gpw::gp_backward_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
+    gpw::gp_backward_warp_kernel<<<(unsigned)a->C, 32, sizeof(gpw::BwdSmem), st>>>(*a, *b);
+    return check_launch("gp_backward_warp_kernel");
+}

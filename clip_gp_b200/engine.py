@@ -41,6 +41,8 @@ class EngineConfig:
     adam_eps: float = 1e-8
     loss_mode: str = "per_sample"       # "per_sample" (adapter.py:422-428) | "logit_mean" (taskres.py:268-270)
     train_visual_proj: bool = True      # FREEZE_VISUAL_PROJ False
+    precision: str = "fp32"             # GEMMs of the step: "fp32" (FFMA, exact comparator) | "bf16x3" (tcgen05, split operands,
+                                        # fp32-grade products: the reference itself runs TF32, adapter.py:23) | "bf16" (tcgen05)
     seed: int = 0
     rank: int = 0
     world: int = 1
@@ -141,6 +143,8 @@ class GPAdapterEngine:
         self.df_hat = torch.empty(B, D, **f32)
         self.dY = torch.empty(B, D, **f32)
         self.dw = torch.empty(S, Cn, T, **f32)
+        if self.cfg.precision != "fp32":
+            self._alloc_tc()
         a = GpArgs()
         a.kernel_type = KERNEL_IDS[self.kernel_type]
         a.x_is_z_prefix = 2     # the engine never writes the frozen template rows of Z (only z_last is scattered back)
@@ -169,6 +173,34 @@ class GPAdapterEngine:
         b.dvar_mean, b.dchol_var, b.dmean_x = self._ptr(self.flat_g, "m"), self._ptr(self.flat_g, "Lq"), None
         self.gp_bwd_args = b
 
+    # ------------------------------------------------------------------ tensor-core operand buffers
+    def _alloc_tc(self):
+        """bf16 operands of the five GEMMs of the step, all K-major ([rows, K]); in split mode every operand is K-tripled
+        ([hi|hi|lo] on the A side, [hi|lo|hi] on the B side).  K is padded to a multiple of 8 (16-byte TMA row pitch) with
+        zero columns that no cast ever writes."""
+        if self.cfg.precision not in ("bf16x3", "bf16"):
+            raise ValueError(f"unknown precision {self.cfg.precision!r}")
+        if self.D % 8:
+            raise ValueError("tensor-core step needs D % 8 == 0")
+        B, Cn, D, S = self.B, self.C, self.D, self.S_local
+        SC = (S if self.cfg.loss_mode == "per_sample" else 1) * Cn
+        seg = 3 if self.cfg.precision == "bf16x3" else 1
+        self.tc_seg, self.tc_ma, self.tc_mb = seg, (1 if seg == 3 else 0), (2 if seg == 3 else 0)
+        self.Bp, self.SCp = (B + 7) // 8 * 8, (SC + 7) // 8 * 8
+        z = lambda r, k: torch.zeros(r, seg * k, dtype=torch.bfloat16, device=self.dev)
+        self.fb, self.Wb, self.fhb, self.Pb = z(B, D), z(D, D), z(B, D), z(SC, D)
+        self.dlb, self.dlTb = z(B, self.SCp), z(SC, self.Bp)
+        self.fhTb, self.PTb = z(D, self.Bp), z(D, self.SCp)
+        self.dYTb, self.fTb = z(D, self.Bp), z(D, self.Bp)
+
+    def _cast(self, src_ptr, R, K, ldx, out, Kp, mode, transpose=False):
+        fn = self.lib.clipgp_cast_bf16_transpose if transpose else self.lib.clipgp_cast_bf16
+        _lib.check(fn(src_ptr, R, K, ldx, out.data_ptr(), out.stride(0), Kp, mode, _lib.stream_ptr(self.dev)), "cast_bf16")
+
+    def _tc(self, A, Bm, alpha, out_ptr, ldc):
+        _lib.check(self.lib.clipgp_tc_gemm_store(A.data_ptr(), A.shape[0], A.shape[1], Bm.data_ptr(), Bm.shape[0], Bm.shape[1],
+                                                 float(alpha), out_ptr, ldc, _lib.stream_ptr(self.dev)), "tc_gemm_store")
+
     # ------------------------------------------------------------------ one training step (launch only)
     def _launch_step(self):
         lib, cfg = self.lib, self.cfg
@@ -181,7 +213,14 @@ class GPAdapterEngine:
         self.flat_g.zero_()
         W = self._ptr(self.flat_p, "W")
         # visual projection + normalisation (adapter.py:419-420)
-        ck(lib.clipgp_gemm_f32(self.in_feat.data_ptr(), D, 1, W, 1, D, self.Y.data_ptr(), D, B, D, D, 1.0, 0, st), "gemm(proj)")
+        tcm = cfg.precision != "fp32"
+        if tcm:
+            ma, mb = self.tc_ma, self.tc_mb
+            self._cast(self.in_feat.data_ptr(), B, D, D, self.fb, D, ma)
+            self._cast(W, D, D, D, self.Wb, D, mb)
+            self._tc(self.fb, self.Wb, 1.0, self.Y.data_ptr(), D)
+        else:
+            ck(lib.clipgp_gemm_f32(self.in_feat.data_ptr(), D, 1, W, 1, D, self.Y.data_ptr(), D, B, D, D, 1.0, 0, st), "gemm(proj)")
         ck(lib.clipgp_rownorm_forward(self.Y.data_ptr(), B, D, self.f_hat.data_ptr(), self.f_inv.data_ptr(), None, st), "rownorm")
         # GP weights + unit prototypes (adapter.py:404, 424-425)
         ck(lib.clipgp_gp_forward(C.byref(self.gp_args), st), "gp_forward")
@@ -189,8 +228,14 @@ class GPAdapterEngine:
                                     self.P_norm.data_ptr(), None, None if per_sample else self.P_mean.data_ptr(), None, 0, st), "proto_forward")
         Bmat = self.P_hat if per_sample else self.P_mean
         # logits (adapter.py:426) -> cross-entropy + gradient (adapter.py:427-428)
-        ck(lib.clipgp_gemm_f32(self.f_hat.data_ptr(), D, 1, Bmat.data_ptr(), 1, D, self.logits.data_ptr(), SC, B, SC, D,
-                               cfg.logit_scale * (1.0 if per_sample else 1.0 / S), 0, st), "gemm(logits)")
+        alpha = cfg.logit_scale * (1.0 if per_sample else 1.0 / S)
+        if tcm:
+            self._cast(self.f_hat.data_ptr(), B, D, D, self.fhb, D, ma)
+            self._cast(Bmat.data_ptr(), SC, D, D, self.Pb, D, mb)
+            self._tc(self.fhb, self.Pb, alpha, self.logits.data_ptr(), SC)
+        else:
+            ck(lib.clipgp_gemm_f32(self.f_hat.data_ptr(), D, 1, Bmat.data_ptr(), 1, D, self.logits.data_ptr(), SC, B, SC, D,
+                                   alpha, 0, st), "gemm(logits)")
         if per_sample:
             rows, rpl = B * S, S
             loss_scale = 1.0 / (B * S_tot)
@@ -202,17 +247,33 @@ class GPAdapterEngine:
         ck(lib.clipgp_softmax_ce(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, None, self.loss.data_ptr(),
                                  loss_scale, self.logits.data_ptr(), Cn, loss_scale, st), "softmax_ce")
         # adjoints of the logit GEMM: dP_hat = scale * dlogits^T f_hat ; df_hat = scale * dlogits P_hat
-        alpha = cfg.logit_scale * (1.0 if per_sample else 1.0 / S)
-        ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), 1, SC, self.f_hat.data_ptr(), D, 1, self.dP.data_ptr(), D, SC, D, B,
-                               alpha, 0, st), "gemm(dP)")
+        if tcm:
+            # K-major operands: dlogits^T [SC, B] and f_hat^T [D, B] (K = batch)
+            self._cast(self.logits.data_ptr(), B, SC, SC, self.dlTb, self.Bp, ma, transpose=True)
+            self._cast(self.f_hat.data_ptr(), B, D, D, self.fhTb, self.Bp, mb, transpose=True)
+            self._tc(self.dlTb, self.fhTb, alpha, self.dP.data_ptr(), D)
+        else:
+            ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), 1, SC, self.f_hat.data_ptr(), D, 1, self.dP.data_ptr(), D, SC, D, B,
+                                   alpha, 0, st), "gemm(dP)")
         if cfg.train_visual_proj:
-            ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), SC, 1, Bmat.data_ptr(), D, 1, self.df_hat.data_ptr(), D, B, D, SC,
-                                   alpha, 0, st), "gemm(df)")
+            if tcm:
+                # dlogits [B, SC] and P_hat^T [D, SC] (K = samples x classes; split over K inside the GEMM)
+                self._cast(self.logits.data_ptr(), B, SC, SC, self.dlb, self.SCp, ma)
+                self._cast(Bmat.data_ptr(), SC, D, D, self.PTb, self.SCp, mb, transpose=True)
+                self._tc(self.dlb, self.PTb, alpha, self.df_hat.data_ptr(), D)
+            else:
+                ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), SC, 1, Bmat.data_ptr(), D, 1, self.df_hat.data_ptr(), D, B, D, SC,
+                                       alpha, 0, st), "gemm(df)")
             ck(lib.clipgp_rownorm_backward(self.df_hat.data_ptr(), self.f_hat.data_ptr(), self.f_inv.data_ptr(), B, D,
                                            self.dY.data_ptr(), st), "rownorm_bwd")
             # dW = dY^T f (+ L2 regulariser, adapter.py:468-476)
-            ck(lib.clipgp_gemm_f32(self.dY.data_ptr(), 1, D, self.in_feat.data_ptr(), D, 1, self._ptr(self.flat_g, "W"), D, D, D, B,
-                                   1.0, 0, st), "gemm(dW)")
+            if tcm:
+                self._cast(self.dY.data_ptr(), B, D, D, self.dYTb, self.Bp, ma, transpose=True)
+                self._cast(self.in_feat.data_ptr(), B, D, D, self.fTb, self.Bp, mb, transpose=True)
+                self._tc(self.dYTb, self.fTb, 1.0, self._ptr(self.flat_g, "W"), D)
+            else:
+                ck(lib.clipgp_gemm_f32(self.dY.data_ptr(), 1, D, self.in_feat.data_ptr(), D, 1, self._ptr(self.flat_g, "W"), D, D, D, B,
+                                       1.0, 0, st), "gemm(dW)")
             coef = float(cfg.l2_lambda) / float(cfg.shots) / cfg.world
             ck(lib.clipgp_l2_identity(W, D, coef, self._ptr(self.flat_g, "W"), self.loss.data_ptr(), st), "l2_identity")
         # prototype + GP adjoints (dkl_scalar = gp_beta: adapter.py:462-465)

@@ -41,6 +41,9 @@ CONFIGS: Dict[str, WorkloadShape] = {
     # small shapes for parity tests
     "tiny": WorkloadShape("tiny", C=12, T=5, D=64, d=16, S=3, shots=4, B=16, N_test=257, kernel="rbf"),
     "small": WorkloadShape("small", C=37, T=8, D=128, d=32, S=4, shots=4, B=48, N_test=1000, kernel="rbf"),
+    # the headline per-class shape (T=32, n=33) and its neighbour (n=32) on a few classes
+    "t32": WorkloadShape("t32", C=19, T=32, D=128, d=64, S=5, shots=4, B=32, N_test=500, kernel="rbf"),
+    "t31": WorkloadShape("t31", C=7, T=31, D=128, d=48, S=3, shots=4, B=32, N_test=500, kernel="rbf"),
 }
 
 

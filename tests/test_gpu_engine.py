@@ -21,7 +21,7 @@ class _Cfg:
         self.adapter = type("A", (), {"gp_pca_dim": pca, "gp_kernel_type": kernel})()
 
 
-def build(kernel, name="small", loss_mode="per_sample", S=4, seed=3):
+def build(kernel, name="small", loss_mode="per_sample", S=4, seed=3, precision="fp32"):
     wl = synth.make_workload(name); shp = wl["shape"]
     torch.manual_seed(0)
     gpw = GaussianProcessTemplateWeighter(wl["E"], _Cfg(kernel, shp.d)).to("cuda")
@@ -30,7 +30,8 @@ def build(kernel, name="small", loss_mode="per_sample", S=4, seed=3):
     gpw.variational_strategy._maybe_init()
     with torch.no_grad():
         q.variational_mean.copy_(m); q.chol_variational_covar.copy_(Lq)
-    cfg = EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, loss_mode=loss_mode, seed=seed)
+    cfg = EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, loss_mode=loss_mode, seed=seed,
+                       precision=precision)
     eng = GPAdapterEngine(gpw, cfg)
     # the oracle twin
     st = ogp.build_state(wl["E"], kernel, shp.d)
@@ -67,6 +68,35 @@ def test_step_loss_and_gradients(kernel, loss_mode):
     if kernel == "rbf": assert rel_err(eng.g("os"), orc.st.kernel.raw_outputscale.grad) < tol
     if kernel == "linear": assert rel_err(eng.g("var").view(shp.C, 1, 1), orc.st.kernel.raw_variance.grad) < tol
     assert int(eng.status.abs().max()) == 0
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("loss_mode", ["per_sample", "logit_mean"])
+@pytest.mark.parametrize("name", ["small", "tiny"])
+def test_tensor_core_step_loss_and_gradients(precision, loss_mode, name):
+    """The same step with all five GEMMs on tcgen05: split operands (bf16x3) meet the fp32 gate; plain bf16 meets its stated
+    tolerance (2 % of the largest gradient entry; the reference's own GPU path is TF32, adapter.py:23)."""
+    wl, shp, eng, orc, cfg = build("rbf", name=name, loss_mode=loss_mode, precision=precision)
+    f, y = wl["f_train"][: shp.B], wl["y_train"][: shp.B]
+    eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, cfg.S_train)
+    loss_ref = orc.loss(f, y, eps)
+    loss_ref.backward()
+    eng.skip_update = True
+    loss = eng.train_step(f.cuda(), y.cuda(), use_graph=False)
+    n = shp.T + 1
+    tol, ltol = (2e-3, 1e-3) if precision == "bf16x3" else (3e-2, 1e-2)
+    assert float(loss) == pytest.approx(float(loss_ref), rel=ltol)
+    assert rel_err(eng.g("W").view(shp.D, shp.D), orc.W.grad) < tol
+    assert rel_err(eng.g("m").view(shp.C, n), orc.st.var_mean.grad) < tol
+    assert rel_err(eng.g("Lq").view(shp.C, n, n), orc.st.chol_var.grad) < tol
+    assert rel_err(eng.g("ls").view(shp.C, 1, -1), orc.st.kernel.raw_lengthscale.grad) < tol
+    assert rel_err(eng.g("os"), orc.st.kernel.raw_outputscale.grad) < tol
+    # graph replay of the tensor-core step reproduces the eager launch sequence
+    _, _, eng2, _, _ = build("rbf", name=name, loss_mode=loss_mode, precision=precision)
+    eng2.skip_update = True
+    loss2 = eng2.train_step(f.cuda(), y.cuda(), use_graph=True)
+    assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
+    assert torch.allclose(eng2.flat_g, eng.flat_g, rtol=1e-4, atol=1e-7)
 
 
 def test_adamw_update_and_graph_replay_match_eager():
