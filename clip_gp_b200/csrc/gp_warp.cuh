@@ -32,6 +32,57 @@ __device__ __forceinline__ void each(int rows, int cols, F f) {
     }
 }
 
+// Same walk, four elements per lane in flight: `ld(idx)` is evaluated for all four before `st(idx, i, j, v)` consumes any, so
+// the global loads of a staging copy overlap instead of being serialised by their dependent shared-memory stores.
+template <typename V, typename LD_, typename ST_>
+__device__ __forceinline__ void stage(int rows, int cols, LD_ ld, ST_ st) {
+    const int total = rows * cols;
+    for (int base = lane_id(); base < total; base += 128) {
+        V v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int idx = base + 32 * u; if (idx < total) v[u] = ld(idx); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + 32 * u;
+            if (idx < total) { const int i = idx / cols; st(idx, i, idx - i * cols, v[u]); }
+        }
+    }
+}
+
+// Left-looking lower Cholesky of an n x n matrix (n <= 33) by one warp, in place on the lower triangle.  Lane i owns row i;
+// when n == 33 the extra row 32 is carried by lane j-1 (idle in column j >= 1, because its own row is above the diagonal), so
+// the warp makes ONE pass per column instead of two.  invd[j] = 1 / L[j][j].  Returns true (uniformly) on a non-positive pivot.
+template <typename T>
+__device__ __forceinline__ bool chol33(T* __restrict__ A, int n, T* __restrict__ invd) {
+    const int lane = lane_id();
+    bool fail = false;
+    for (int j = 0; j < n; ++j) {
+        int i = lane;
+        if (n == 33 && lane == j - 1) i = 32;
+        const bool active = (i >= j) && (i < n);
+        T acc = (T)0;
+        {
+            const T* ri = A + (active ? i : j) * LD;
+            const T* rj = A + j * LD;
+            T a0 = ri[j], a1 = (T)0;
+            int k = 0;
+            for (; k + 1 < j; k += 2) { a0 -= ri[k] * rj[k]; a1 -= ri[k + 1] * rj[k + 1]; }
+            if (k < j) a0 -= ri[k] * rj[k];
+            acc = a0 + a1;
+        }
+        // the pivot is the accumulator of row j: lane j for j < 32, lane 31 (carrying row 32) for j == 32
+        const T sj = __shfl_sync(FULL, acc, j < 32 ? j : 31);
+        if (!(sj > (T)0)) fail = true;
+        const T inv = rsqrt(sj);
+        __syncwarp();
+        if (active && i > j) A[i * LD + j] = acc * inv;
+        if (n == 33 && j == 0 && lane == 0) A[32 * LD] = A[32 * LD] * inv;      // column 0 has no idle lane: row 32 by lane 0
+        if (lane == 0) { A[j * LD + j] = sj * inv; invd[j] = inv; }
+        __syncwarp();
+    }
+    return fail;
+}
+
 // X <- L^-1 X (forward substitution), X is [n][ncol] with lane = column; two partial sums shorten the dependent chain.
 template <typename T>
 __device__ __forceinline__ void trsm_lower_cols(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ X, int n, int ncol) {

@@ -40,7 +40,11 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
     // =========================== P1 ===========================
     float* R = reinterpret_cast<float*>(s.RB);
     float* G = R + NN;
-    each(T, T, [&](int idx, int i, int j) { R[i * LD + j] = __ldg(a.R + (size_t)c * T * T + idx); G[i * LD + j] = 0.f; });
+    {
+        const float* Rg = a.R + (size_t)c * T * T;
+        stage<float>(T, T, [&](int idx) { return __ldg(Rg + idx); },
+                     [&](int idx, int i, int j, float v) { R[i * LD + j] = v; G[i * LD + j] = 0.f; });
+    }
     __syncwarp();
     if (lane < T) s.vecT[lane] = 1.f / R[lane * LD + lane];
     float dmu = 0.f;
@@ -84,8 +88,12 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
     float* Lq = reinterpret_cast<float*>(s.RC);
     float* H = Lq + NN;
     float* dBm = R;                                             // R is dead
-    each(n, T, [&](int idx, int i, int j) { s.Af[i * LD + j] = __ldg(a.A + (size_t)c * n * T + idx); });
-    each(n, n, [&](int idx, int i, int j) { Lq[i * LD + j] = (j <= i) ? __ldg(a.chol_var + (size_t)c * n * n + idx) : 0.f; });
+    {
+        const float* Ag = a.A + (size_t)c * n * T;
+        const float* cv = a.chol_var + (size_t)c * n * n;
+        stage<float>(n, T, [&](int idx) { return __ldg(Ag + idx); }, [&](int idx, int i, int j, float v) { s.Af[i * LD + j] = v; });
+        stage<float>(n, n, [&](int idx) { return __ldg(cv + idx); }, [&](int idx, int i, int j, float v) { Lq[i * LD + j] = (j <= i) ? v : 0.f; });
+    }
     for (int i = lane; i < n; i += 32) s.mvec[i] = __ldg(a.var_mean + (size_t)c * n + i);
     if (lane < 3) Lq[33 * LD + lane] = 0.f;
     __syncwarp();
@@ -189,7 +197,10 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
     // =========================== P3 (fp64) ===========================
     double* Ld = s.RB;
     double* Gd = s.RC;
-    each(n, n, [&](int idx, int i, int j) { Ld[i * LD + j] = a.L[(size_t)c * n * n + idx]; });
+    {
+        const double* Lg = a.L + (size_t)c * n * n;
+        stage<double>(n, n, [&](int idx) { return Lg[idx]; }, [&](int idx, int i, int j, double v) { Ld[i * LD + j] = v; });
+    }
     __syncwarp();
     for (int i = lane; i < n; i += 32) s.invd[i] = 1.0 / Ld[i * LD + i];
     __syncwarp();

@@ -31,18 +31,21 @@ __global__ void __launch_bounds__(32) gp_forward_warp_kernel(const clipgp_gp_arg
     const float* K = ks + 1;
 
     // ---- stage K_ZZ: jitter is added in fp32 before the cast, as gpytorch does (add_jitter, then .double())
-    each(n, n, [&](int idx, int i, int j) {
-        const float v = __ldg(K + idx);
+    stage<float>(n, n, [&](int idx) { return __ldg(K + idx); }, [&](int idx, int i, int j, float v) {
         s.Ld[i * LD + j] = (double)(v + (i == j ? 1e-4f : 0.f));
         if (j < T) s.Ad[i * LD + j] = (double)v;
     });
-    each(n, n, [&](int idx, int i, int j) { s.Lq[i * LD + j] = (j <= i) ? __ldg(a.chol_var + (size_t)c * n * n + idx) : 0.f; });
+    {
+        const float* cv = a.chol_var + (size_t)c * n * n;
+        stage<float>(n, n, [&](int idx) { return __ldg(cv + idx); },
+                     [&](int idx, int i, int j, float v) { s.Lq[i * LD + j] = (j <= i) ? v : 0.f; });
+    }
     for (int i = lane; i < n; i += 32) s.mvec[i] = __ldg(a.var_mean + (size_t)c * n + i);
     if (lane < 3) s.Lq[33 * LD + lane] = 0.f;
     __syncwarp();
 
     // ---- L = chol64(K_ZZ + 1e-4 I);  A = L^-1 K_ZX
-    const bool failL = gp::warp_cholesky<double>(s.Ld, n, LD, s.invd);
+    const bool failL = chol33<double>(s.Ld, n, s.invd);
     __syncwarp();
     trsm_lower_cols<double>(s.Ld, s.invd, s.Ad, n, T);
     if (lane < T)
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(32) gp_forward_warp_kernel(const clipgp_gp_arg
         for (int t = 0; t < T; ++t)
             if (lane <= t) R[t * LD + lane] = Sig[t * LD + lane] + (t == lane ? jit : 0.f);
         __syncwarp();
-        failR = gp::warp_cholesky<float>(R, T, LD, s.invdR);
+        failR = chol33<float>(R, T, s.invdR);
         __syncwarp();
         if (!failR) break;
         ++retries;
