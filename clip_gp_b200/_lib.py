@@ -85,8 +85,17 @@ _SIGNATURES = {
                                        c_i64, C.c_void_p]),
     "clipgp_cast_bf16": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
     "clipgp_cast_bf16_transpose": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
+    "clipgp_cast_bf16_dual": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p, c_i64, c_i64,
+                                        C.c_int, C.c_void_p]),
+    "clipgp_softmax_ce_stats": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_float,
+                                          C.c_void_p]),
+    "clipgp_softmax_grad_bf16_dual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, C.c_float, C.c_void_p, c_i64,
+                                                c_i64, C.c_int, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
+    "clipgp_increment2": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_tc_gemm_store": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_float, C.c_void_p, c_i64,
                                        C.c_void_p]),
+    "clipgp_tc_gemm_store_splitk": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_float, C.c_void_p, c_i64,
+                                              C.c_void_p]),
     "clipgp_tc_logits_calibration": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_float, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),

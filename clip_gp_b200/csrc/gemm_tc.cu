@@ -249,9 +249,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     } else if (p.C != nullptr && row < p.M) {
                         float* dst = p.C + (long long)row * p.ldc + col0;
                         if (p.k_splits > 1) {
+                            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < ncols) atomicAdd(dst + j, p.alpha * __uint_as_float(r[j]));
+                                for (int j = 0; j < 32; j += 4)        // vector reduction: one L2 atomic per 16 bytes
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                                                 "f"(p.alpha * __uint_as_float(r[j])), "f"(p.alpha * __uint_as_float(r[j + 1])),
+                                                 "f"(p.alpha * __uint_as_float(r[j + 2])), "f"(p.alpha * __uint_as_float(r[j + 3])) : "memory");
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (j < ncols) atomicAdd(dst + j, p.alpha * __uint_as_float(r[j]));
+                            }
                         } else if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
@@ -352,7 +360,8 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     return CLIPGP_OK;
 }
 
-static int launch(const void* A, long long M, long long Ka, const void* B, long long N, long long K, Params& p, cudaStream_t st) {
+static int launch(const void* A, long long M, long long Ka, const void* B, long long N, long long K, Params& p, cudaStream_t st,
+                  bool allow_split_k = false) {
     CLIPGP_REQUIRE(M >= 1 && N >= 1 && K >= 1 && Ka >= 1, "tc_gemm: empty problem");
     CLIPGP_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "tc_gemm: size too large");
     CLIPGP_REQUIRE(A && B, "tc_gemm: NULL operand");
@@ -368,12 +377,12 @@ static int launch(const void* A, long long M, long long Ka, const void* B, long 
     p.num_m = (int)((M + BM - 1) / BM); p.num_n = (int)((N + BN - 1) / BN); p.num_k = (int)((K + BK - 1) / BK);
     p.n_per_item = (p.mode == EPI_ROWSTATS) ? p.num_n : 1;
     p.k_splits = 1; p.kb_per_split = p.num_k;
-    if (p.mode == EPI_STORE) {
+    if (p.mode == EPI_STORE && allow_split_k) {
         // split K when the output grid cannot fill the SMs and K is long (skinny adjoint GEMMs, e.g. d f_hat = dlogits P_hat)
         const int tiles = p.num_m * p.num_n;
-        if (tiles * 2 <= num_sms() && p.num_k >= 16) {
+        if (tiles * 2 <= num_sms() && p.num_k >= 4) {
             int want = num_sms() / tiles;
-            if (want > p.num_k / 4) want = p.num_k / 4;
+            if (want > p.num_k / 2) want = p.num_k / 2;          // at least two K blocks (2 x 48 KB of operands) per work item
             if (want > 1) {
                 p.kb_per_split = (p.num_k + want - 1) / want;
                 p.k_splits = (p.num_k + p.kb_per_split - 1) / p.kb_per_split;
@@ -404,6 +413,14 @@ extern "C" int clipgp_tc_gemm_store(const void* A_bf16, int64_t M, int64_t Ka, c
     tc::Params p = {};
     p.mode = tc::EPI_STORE; p.alpha = alpha; p.C = C; p.ldc = ldc;
     return tc::launch(A_bf16, M, Ka, B_bf16, N, K, p, (cudaStream_t)stream);
+}
+
+extern "C" int clipgp_tc_gemm_store_splitk(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K,
+                                           float alpha, float* C, int64_t ldc, void* stream) {
+    CLIPGP_REQUIRE(C != nullptr && ldc >= N, "tc_gemm_store_splitk: bad output");
+    tc::Params p = {};
+    p.mode = tc::EPI_STORE; p.alpha = alpha; p.C = C; p.ldc = ldc;
+    return tc::launch(A_bf16, M, Ka, B_bf16, N, K, p, (cudaStream_t)stream, true);
 }
 
 extern "C" int clipgp_tc_logits_calibration(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K,

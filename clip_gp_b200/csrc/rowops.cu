@@ -183,6 +183,127 @@ __global__ void __launch_bounds__(256) cast_bf16_t_kernel(const float* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dual-layout bf16 operand producer: one read of an fp32 [R, K] matrix (optionally transformed on the fly) feeds BOTH
+// K-major operands the tensor-core step needs from it: the row-major copy out[r, k] (A/B operand of the forward GEMM) and
+// the transposed copy outT[k, r] (operand of the adjoint GEMM that contracts over r).  Modes as cast_bf16_kernel
+// (0 plain, 1 A-split [hi|hi|lo], 2 B-split [hi|lo|hi]); either output may be NULL.  32 x 32 tiles through shared memory keep
+// both global writes contiguous.
+struct IdentityOp {
+    __device__ __forceinline__ float operator()(float v, int64_t, int64_t) const { return v; }
+};
+// dlogits = grad_scale * (softmax(x) - onehot) from per-row statistics (max, 1/sum); logits viewed as [B, S*C], row (b, s).
+struct SoftmaxGradOp {
+    const float2* stats; const int64_t* labels; int S, C; float grad_scale;
+    __device__ __forceinline__ float operator()(float v, int64_t r, int64_t k) const {
+        const int sidx = (int)(k / C), j = (int)(k - (int64_t)sidx * C);
+        const float2 st = stats[r * S + sidx];
+        const float p = __expf(v - st.x) * st.y;
+        return grad_scale * (p - (j == (int)labels[r] ? 1.f : 0.f));
+    }
+};
+
+__device__ __forceinline__ void store_split(__nv_bfloat16* o, int64_t seg_stride, int mode, float v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    o[0] = hi;
+    if (mode != 0) {
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        o[seg_stride] = (mode == 1) ? hi : lo;
+        o[2 * seg_stride] = (mode == 1) ? lo : hi;
+    }
+}
+
+__device__ __forceinline__ void store_split2(__nv_bfloat16* o, int64_t seg_stride, int mode, float v0, float v1) {
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+    *reinterpret_cast<__nv_bfloat162*>(o) = hi;
+    if (mode != 0) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0 - __low2float(hi), v1 - __high2float(hi));
+        *reinterpret_cast<__nv_bfloat162*>(o + seg_stride) = (mode == 1) ? hi : lo;
+        *reinterpret_cast<__nv_bfloat162*>(o + 2 * seg_stride) = (mode == 1) ? lo : hi;
+    }
+}
+
+// 64 x 64 tiles, 256 threads (32 x 8): every thread moves column pairs, so the fp32 reads are 8-byte and both bf16 writes
+// 4-byte (128 contiguous bytes per warp and row); `vec` = all strides even and bases 4-byte aligned (checked by the host).
+template <typename Op>
+__global__ void __launch_bounds__(256) cast_dual_kernel(const float* __restrict__ x, int64_t R, int64_t K, int64_t ldx, Op op,
+                                                        __nv_bfloat16* __restrict__ out, int64_t out_ld, int64_t seg_stride, int mode,
+                                                        __nv_bfloat16* __restrict__ outT, int64_t outT_ld, int64_t segT_stride, int modeT,
+                                                        int vec) {
+    __shared__ float tile[64][65];
+    const int64_t r0 = (int64_t)blockIdx.y * 64, k0 = (int64_t)blockIdx.x * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t k = k0 + 2 * tx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = ty + 8 * i;
+        const int64_t r = r0 + rr;
+        float v0 = 0.f, v1 = 0.f;
+        if (r < R) {
+            if (vec && k + 1 < K) {
+                const float2 xv = *reinterpret_cast<const float2*>(x + r * ldx + k);
+                v0 = op(xv.x, r, k); v1 = op(xv.y, r, k + 1);
+                if (out) store_split2(out + r * out_ld + k, seg_stride, mode, v0, v1);
+            } else {
+                if (k < K) { v0 = op(x[r * ldx + k], r, k); if (out) store_split(out + r * out_ld + k, seg_stride, mode, v0); }
+                if (k + 1 < K) { v1 = op(x[r * ldx + k + 1], r, k + 1); if (out) store_split(out + r * out_ld + k + 1, seg_stride, mode, v1); }
+            }
+        }
+        tile[rr][2 * tx] = v0; tile[rr][2 * tx + 1] = v1;
+    }
+    if (outT == nullptr) return;
+    __syncthreads();
+    const int64_t r = r0 + 2 * tx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int kk = ty + 8 * i;
+        const int64_t kq = k0 + kk;
+        if (kq < K) {
+            const float v0 = tile[2 * tx][kk], v1 = tile[2 * tx + 1][kk];
+            __nv_bfloat16* o = outT + kq * outT_ld + r;
+            if (vec && r + 1 < R) store_split2(o, segT_stride, modeT, v0, v1);
+            else {
+                if (r < R) store_split(o, segT_stride, modeT, v0);
+                if (r + 1 < R) store_split(o + 1, segT_stride, modeT, v1);
+            }
+        }
+    }
+}
+
+// Row statistics of the softmax cross-entropy (phase 1 of the tensor-core step's loss): stats[r] = (max, 1 / sum exp(x - max)),
+// loss_sum += loss_scale * sum_r (lse_r - x_r[label]).  One warp per row; row r uses labels[r / rows_per_label].
+__global__ void __launch_bounds__(256) softmax_stats_kernel(const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
+                                                            int64_t R, int64_t rows_per_label, int C, float2* __restrict__ stats,
+                                                            float* loss_sum, float loss_scale) {
+    __shared__ float part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    float my_loss = 0.f;
+    if (row < R) {
+        const float* x = logits + row * ld;
+        float m = -FLT_MAX;
+        for (int j = lane; j < C; j += 32) m = fmaxf(m, x[j]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < C; j += 32) sum += expf(x[j] - m);
+        sum = warp_sum(sum);
+        my_loss = m + logf(sum) - x[(int)labels[row / rows_per_label]];
+        if (lane == 0) stats[row] = make_float2(m, 1.f / sum);
+    }
+    if (loss_sum) {
+        if (lane == 0) part[warp] = (row < R) ? my_loss : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += part[k];
+            atomicAdd(loss_sum, t * loss_scale);
+        }
+    }
+}
+
+__global__ void increment2_kernel(int64_t* a, int64_t* b, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) { *a += by; *b += by; } }
+
 __global__ void increment_kernel(int64_t* p, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) *p += by; }
 
 }  // namespace clipgp
@@ -280,4 +401,65 @@ extern "C" int clipgp_cast_bf16_transpose(const float* x, int64_t R, int64_t K, 
     CLIPGP_REQUIRE(grid.y <= 65535, "cast_bf16_transpose: R too large");
     cast_bf16_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, K, ldx, (__nv_bfloat16*)out, out_ld, seg_stride, mode);
     return check_launch("cast_bf16_t_kernel");
+}
+
+static int check_dual(const char* who, int64_t R, int64_t K, int64_t ldx, const void* x, const void* out, const void* outT, int mode, int modeT) {
+    CLIPGP_REQUIRE(R >= 0 && K >= 0 && ldx >= K, "%s: bad shape", who);
+    CLIPGP_REQUIRE(mode >= 0 && mode <= 2 && modeT >= 0 && modeT <= 2, "%s: modes must be 0, 1 or 2", who);
+    CLIPGP_REQUIRE(R == 0 || K == 0 || (x && (out || outT)), "%s: NULL pointer", who);
+    CLIPGP_REQUIRE((R + 63) / 64 <= 65535, "%s: R too large", who);
+    return CLIPGP_OK;
+}
+
+static int dual_vec_ok(const void* x, int64_t ldx, const void* out, int64_t out_ld, int64_t seg, const void* outT, int64_t outT_ld,
+                       int64_t segT) {
+    if ((ldx & 1) || (reinterpret_cast<uintptr_t>(x) & 7u)) return 0;
+    if (out && ((out_ld & 1) || (seg & 1) || (reinterpret_cast<uintptr_t>(out) & 3u))) return 0;
+    if (outT && ((outT_ld & 1) || (segT & 1) || (reinterpret_cast<uintptr_t>(outT) & 3u))) return 0;
+    return 1;
+}
+
+extern "C" int clipgp_cast_bf16_dual(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld, int64_t seg_stride,
+                                     int mode, void* outT, int64_t outT_ld, int64_t segT_stride, int modeT, void* stream) {
+    int rc = check_dual("cast_bf16_dual", R, K, ldx, x, out, outT, mode, modeT);
+    if (rc != CLIPGP_OK) return rc;
+    if (R == 0 || K == 0) return CLIPGP_OK;
+    dim3 grid((unsigned)((K + 63) / 64), (unsigned)((R + 63) / 64));
+    cast_dual_kernel<IdentityOp><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, K, ldx, IdentityOp(), (__nv_bfloat16*)out, out_ld, seg_stride,
+                                                                         mode, (__nv_bfloat16*)outT, outT_ld, segT_stride, modeT,
+                                                                         dual_vec_ok(x, ldx, out, out_ld, seg_stride, outT, outT_ld, segT_stride));
+    return check_launch("cast_dual_kernel");
+}
+
+extern "C" int clipgp_softmax_ce_stats(const float* logits, int64_t ld, const int64_t* labels, int64_t R, int64_t rows_per_label,
+                                       int64_t C, float* stats, float* loss_sum, float loss_scale, void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && C >= 1 && C < (1ll << 31) && rows_per_label >= 1, "softmax_ce_stats: bad shape");
+    if (R == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(logits && labels && stats && ld >= C, "softmax_ce_stats: bad input");
+    const int64_t blocks = (R + 7) / 8;
+    softmax_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(logits, ld, labels, R, rows_per_label, (int)C,
+                                                                            reinterpret_cast<float2*>(stats), loss_sum, loss_scale);
+    return check_launch("softmax_stats_kernel");
+}
+
+extern "C" int clipgp_softmax_grad_bf16_dual(const float* logits, const float* stats, const int64_t* labels, int64_t B, int64_t S,
+                                             int64_t C, float grad_scale, void* out, int64_t out_ld, int64_t seg_stride, int mode,
+                                             void* outT, int64_t outT_ld, int64_t segT_stride, int modeT, void* stream) {
+    const int64_t K = S * C;
+    int rc = check_dual("softmax_grad_bf16_dual", B, K, K, logits, out, outT, mode, modeT);
+    if (rc != CLIPGP_OK) return rc;
+    if (B == 0 || K == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(stats && labels && S >= 1 && C >= 1 && C < (1ll << 31), "softmax_grad_bf16_dual: bad input");
+    SoftmaxGradOp op{reinterpret_cast<const float2*>(stats), labels, (int)S, (int)C, grad_scale};
+    dim3 grid((unsigned)((K + 63) / 64), (unsigned)((B + 63) / 64));
+    cast_dual_kernel<SoftmaxGradOp><<<grid, 256, 0, (cudaStream_t)stream>>>(logits, B, K, K, op, (__nv_bfloat16*)out, out_ld, seg_stride, mode,
+                                                                            (__nv_bfloat16*)outT, outT_ld, segT_stride, modeT,
+                                                                            dual_vec_ok(logits, K, out, out_ld, seg_stride, outT, outT_ld, segT_stride));
+    return check_launch("cast_dual_kernel(softmax_grad)");
+}
+
+extern "C" int clipgp_increment2(int64_t* a, int64_t* b, int64_t by, void* stream) {
+    CLIPGP_REQUIRE(a && b, "increment2: NULL pointer");
+    increment2_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a, b, by);
+    return check_launch("increment2_kernel");
 }

@@ -192,14 +192,21 @@ class GPAdapterEngine:
         self.dlb, self.dlTb = z(B, self.SCp), z(SC, self.Bp)
         self.fhTb, self.PTb = z(D, self.Bp), z(D, self.SCp)
         self.dYTb, self.fTb = z(D, self.Bp), z(D, self.Bp)
+        self.sm_stats = torch.empty(B * (S if self.cfg.loss_mode == "per_sample" else 1), 2, dtype=torch.float32, device=self.dev)
 
     def _cast(self, src_ptr, R, K, ldx, out, Kp, mode, transpose=False):
         fn = self.lib.clipgp_cast_bf16_transpose if transpose else self.lib.clipgp_cast_bf16
         _lib.check(fn(src_ptr, R, K, ldx, out.data_ptr(), out.stride(0), Kp, mode, _lib.stream_ptr(self.dev)), "cast_bf16")
 
+    def _cast2(self, src_ptr, R, K, ldx, out, Kp, mode, outT, Rp, modeT):
+        """One read of an fp32 [R,K] source -> row-major operand `out` [R, seg*Kp] and transposed operand `outT` [K, seg*Rp]."""
+        _lib.check(self.lib.clipgp_cast_bf16_dual(src_ptr, R, K, ldx, _lib.ptr(out), out.stride(0) if out is not None else 0, Kp, mode,
+                                                  _lib.ptr(outT), outT.stride(0) if outT is not None else 0, Rp, modeT,
+                                                  _lib.stream_ptr(self.dev)), "cast_bf16_dual")
+
     def _tc(self, A, Bm, alpha, out_ptr, ldc):
-        _lib.check(self.lib.clipgp_tc_gemm_store(A.data_ptr(), A.shape[0], A.shape[1], Bm.data_ptr(), Bm.shape[0], Bm.shape[1],
-                                                 float(alpha), out_ptr, ldc, _lib.stream_ptr(self.dev)), "tc_gemm_store")
+        _lib.check(self.lib.clipgp_tc_gemm_store_splitk(A.data_ptr(), A.shape[0], A.shape[1], Bm.data_ptr(), Bm.shape[0], Bm.shape[1],
+                                                        float(alpha), out_ptr, ldc, _lib.stream_ptr(self.dev)), "tc_gemm_store_splitk")
 
     # ------------------------------------------------------------------ one training step (launch only)
     def _launch_step(self):
@@ -216,7 +223,7 @@ class GPAdapterEngine:
         tcm = cfg.precision != "fp32"
         if tcm:
             ma, mb = self.tc_ma, self.tc_mb
-            self._cast(self.in_feat.data_ptr(), B, D, D, self.fb, D, ma)
+            self._cast2(self.in_feat.data_ptr(), B, D, D, self.fb, D, ma, self.fTb if cfg.train_visual_proj else None, self.Bp, mb)
             self._cast(W, D, D, D, self.Wb, D, mb)
             self._tc(self.fb, self.Wb, 1.0, self.Y.data_ptr(), D)
         else:
@@ -230,8 +237,8 @@ class GPAdapterEngine:
         # logits (adapter.py:426) -> cross-entropy + gradient (adapter.py:427-428)
         alpha = cfg.logit_scale * (1.0 if per_sample else 1.0 / S)
         if tcm:
-            self._cast(self.f_hat.data_ptr(), B, D, D, self.fhb, D, ma)
-            self._cast(Bmat.data_ptr(), SC, D, D, self.Pb, D, mb)
+            self._cast2(self.f_hat.data_ptr(), B, D, D, self.fhb, D, ma, self.fhTb, self.Bp, mb)
+            self._cast2(Bmat.data_ptr(), SC, D, D, self.Pb, D, mb, self.PTb if cfg.train_visual_proj else None, self.SCp, mb)
             self._tc(self.fhb, self.Pb, alpha, self.logits.data_ptr(), SC)
         else:
             ck(lib.clipgp_gemm_f32(self.f_hat.data_ptr(), D, 1, Bmat.data_ptr(), 1, D, self.logits.data_ptr(), SC, B, SC, D,
@@ -244,13 +251,20 @@ class GPAdapterEngine:
             loss_scale = 1.0 / (B * cfg.world)
             if cfg.world > 1:
                 raise NotImplementedError("logit_mean loss is not S-sharded (it is not a sum over samples)")
-        ck(lib.clipgp_softmax_ce(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, None, self.loss.data_ptr(),
-                                 loss_scale, self.logits.data_ptr(), Cn, loss_scale, st), "softmax_ce")
+        if tcm:
+            # two-phase softmax cross-entropy: row statistics + loss, then dlogits straight into the bf16 operands of the two
+            # adjoint GEMMs (dlogits [B, SC] and dlogits^T [SC, B]); no fp32 dlogits
+            ck(lib.clipgp_softmax_ce_stats(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, self.sm_stats.data_ptr(),
+                                           self.loss.data_ptr(), loss_scale, st), "softmax_ce_stats")
+            ck(lib.clipgp_softmax_grad_bf16_dual(self.logits.data_ptr(), self.sm_stats.data_ptr(), self.in_lab.data_ptr(), B, rpl, Cn,
+                                                 loss_scale, _lib.ptr(self.dlb) if cfg.train_visual_proj else None, self.dlb.stride(0),
+                                                 self.SCp, ma, self.dlTb.data_ptr(), self.dlTb.stride(0), self.Bp, ma, st), "softmax_grad")
+        else:
+            ck(lib.clipgp_softmax_ce(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, None, self.loss.data_ptr(),
+                                     loss_scale, self.logits.data_ptr(), Cn, loss_scale, st), "softmax_ce")
         # adjoints of the logit GEMM: dP_hat = scale * dlogits^T f_hat ; df_hat = scale * dlogits P_hat
         if tcm:
             # K-major operands: dlogits^T [SC, B] and f_hat^T [D, B] (K = batch)
-            self._cast(self.logits.data_ptr(), B, SC, SC, self.dlTb, self.Bp, ma, transpose=True)
-            self._cast(self.f_hat.data_ptr(), B, D, D, self.fhTb, self.Bp, mb, transpose=True)
             self._tc(self.dlTb, self.fhTb, alpha, self.dP.data_ptr(), D)
         else:
             ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), 1, SC, self.f_hat.data_ptr(), D, 1, self.dP.data_ptr(), D, SC, D, B,
@@ -258,8 +272,6 @@ class GPAdapterEngine:
         if cfg.train_visual_proj:
             if tcm:
                 # dlogits [B, SC] and P_hat^T [D, SC] (K = samples x classes; split over K inside the GEMM)
-                self._cast(self.logits.data_ptr(), B, SC, SC, self.dlb, self.SCp, ma)
-                self._cast(Bmat.data_ptr(), SC, D, D, self.PTb, self.SCp, mb, transpose=True)
                 self._tc(self.dlb, self.PTb, alpha, self.df_hat.data_ptr(), D)
             else:
                 ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), SC, 1, Bmat.data_ptr(), D, 1, self.df_hat.data_ptr(), D, B, D, SC,
@@ -268,8 +280,7 @@ class GPAdapterEngine:
                                            self.dY.data_ptr(), st), "rownorm_bwd")
             # dW = dY^T f (+ L2 regulariser, adapter.py:468-476)
             if tcm:
-                self._cast(self.dY.data_ptr(), B, D, D, self.dYTb, self.Bp, ma, transpose=True)
-                self._cast(self.in_feat.data_ptr(), B, D, D, self.fTb, self.Bp, mb, transpose=True)
+                self._cast2(self.dY.data_ptr(), B, D, D, None, 0, 0, self.dYTb, self.Bp, ma)
                 self._tc(self.dYTb, self.fTb, 1.0, self._ptr(self.flat_g, "W"), D)
             else:
                 ck(lib.clipgp_gemm_f32(self.dY.data_ptr(), 1, D, self.in_feat.data_ptr(), D, 1, self._ptr(self.flat_g, "W"), D, D, D, B,
@@ -304,8 +315,7 @@ class GPAdapterEngine:
                                  self.flat_v.data_ptr() + 4 * nW, rest, cfg.gp_lr, b1, b2, cfg.adam_eps, cfg.weight_decay,
                                  self.adam_step.data_ptr(), st), "adamw(gp)")
         self.Z[:, self.n - 1, :].copy_(self.p("z_last").view(self.C, self.d))
-        ck(lib.clipgp_increment(self.adam_step.data_ptr(), 1, st), "increment")
-        ck(lib.clipgp_increment(self.rng_state.data_ptr() + 8, 1, st), "increment")
+        ck(lib.clipgp_increment2(self.adam_step.data_ptr(), self.rng_state.data_ptr() + 8, 1, st), "increment2")
 
     # ------------------------------------------------------------------ public API
     def train_step(self, features: torch.Tensor, labels: torch.Tensor, use_graph: bool = True) -> torch.Tensor:

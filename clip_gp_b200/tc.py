@@ -23,6 +23,48 @@ def cast_bf16(x: torch.Tensor, mode: int = PLAIN) -> torch.Tensor:
     return out
 
 
+def _pad8(v: int) -> int:
+    return (v + 7) // 8 * 8
+
+
+def cast_bf16_dual(x: torch.Tensor, mode: int = PLAIN, modeT: int = PLAIN):
+    """One read of fp32 [R,K] -> (row-major operand [R, seg*Kp], transposed operand [K, segT*Rp]); Kp / Rp = K / R padded to 8."""
+    dev = _lib.require_cuda(x)
+    x = x.float().contiguous()
+    R, K = x.shape
+    Kp, Rp = _pad8(K), _pad8(R)
+    out = torch.zeros(R, Kp * (3 if mode else 1), dtype=torch.bfloat16, device=dev)
+    outT = torch.zeros(K, Rp * (3 if modeT else 1), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().clipgp_cast_bf16_dual(x.data_ptr(), R, K, K, out.data_ptr(), out.stride(0), Kp, mode, outT.data_ptr(),
+                                                     outT.stride(0), Rp, modeT, _lib.stream_ptr(dev)), "clipgp_cast_bf16_dual")
+    return out, outT
+
+
+def softmax_ce_operands(logits: torch.Tensor, labels: torch.Tensor, S: int, grad_scale: float, mode: int = PLAIN):
+    """logits [B, S*C] (row (b,s) uses labels[b]) -> (mean CE over the B*S rows, dlogits bf16 [B, seg*SCp], dlogits^T bf16 [S*C, seg*Bp])
+    with dlogits = grad_scale * (softmax - onehot): the two-phase tensor-core form of F.cross_entropy + its gradient."""
+    dev = _lib.require_cuda(logits, labels)
+    logits = logits.float().contiguous()
+    B, SC = logits.shape
+    Cn = SC // S
+    stats = torch.empty(B * S, 2, dtype=torch.float32, device=dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    SCp, Bp = _pad8(SC), _pad8(B)
+    seg = 3 if mode else 1
+    out = torch.zeros(B, seg * SCp, dtype=torch.bfloat16, device=dev)
+    outT = torch.zeros(SC, seg * Bp, dtype=torch.bfloat16, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        _lib.check(lib.clipgp_softmax_ce_stats(logits.data_ptr(), Cn, labels.data_ptr(), B * S, S, Cn, stats.data_ptr(), loss.data_ptr(),
+                                               1.0 / (B * S), st), "clipgp_softmax_ce_stats")
+        _lib.check(lib.clipgp_softmax_grad_bf16_dual(logits.data_ptr(), stats.data_ptr(), labels.data_ptr(), B, S, Cn, float(grad_scale),
+                                                     out.data_ptr(), out.stride(0), SCp, mode, outT.data_ptr(), outT.stride(0), Bp, mode,
+                                                     st), "clipgp_softmax_grad_bf16_dual")
+    return loss, out, outT
+
+
 def gemm_store(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C = alpha * A @ B^T for bf16 A [M,Ka], B [N,K] (K % Ka == 0: A wraps along K)."""
     dev = _lib.require_cuda(A, B)

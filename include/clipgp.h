@@ -207,9 +207,30 @@ int clipgp_cast_bf16(const float* x, int64_t R, int64_t K, int64_t ldx, void* ou
 int clipgp_cast_bf16_transpose(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld, int64_t seg_stride,
                                int mode, void* stream);
 
-/* C[M,N] (fp32, row stride ldc) = alpha * A B^T.  Skinny outputs with long K are split over K (atomic accumulation). */
+/* One read, both layouts: out[r*out_ld + g*seg_stride + k] (mode) and outT[k*outT_ld + g*segT_stride + r] (modeT); either may be
+ * NULL.  Feeds the forward GEMM and the adjoint GEMM that contracts over r from the same fp32 source. */
+int clipgp_cast_bf16_dual(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld, int64_t seg_stride, int mode,
+                          void* outT, int64_t outT_ld, int64_t segT_stride, int modeT, void* stream);
+
+/* Tensor-core form of F.cross_entropy (adapter.py:427): phase 1 reduces every logits row to stats[r] = (max, 1/sum exp(x - max))
+ * (float2) and accumulates loss_sum[0] += loss_scale * sum_r CE_r; phase 2 streams the logits [B, S*C] once more and writes
+ * dlogits = grad_scale * (softmax - onehot) directly as the two bf16 operands of the adjoint GEMMs (row (b,s) uses labels[b]):
+ * out [B, S*C] for d f_hat = dlogits P_hat and outT [S*C, B] for d P_hat = dlogits^T f_hat.  No fp32 dlogits reach HBM. */
+int clipgp_softmax_ce_stats(const float* logits, int64_t ld, const int64_t* labels, int64_t R, int64_t rows_per_label, int64_t C,
+                            float* stats, float* loss_sum, float loss_scale, void* stream);
+int clipgp_softmax_grad_bf16_dual(const float* logits, const float* stats, const int64_t* labels, int64_t B, int64_t S, int64_t C,
+                                  float grad_scale, void* out, int64_t out_ld, int64_t seg_stride, int mode, void* outT,
+                                  int64_t outT_ld, int64_t segT_stride, int modeT, void* stream);
+int clipgp_increment2(int64_t* a, int64_t* b, int64_t by, void* stream);
+
+/* C[M,N] (fp32, row stride ldc) = alpha * A B^T.  Deterministic (one accumulator per output tile). */
 int clipgp_tc_gemm_store(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K, float alpha,
                          float* C, int64_t ldc, void* stream);
+/* Same product for the small / skinny GEMMs of the training step (few output tiles, long K): when the output grid cannot fill
+ * the SMs the K blocks are split over work items that accumulate into C with vector reductions (red.global.add.v4.f32), so the
+ * fp32 summation order, and the last bits of C, vary from run to run (as with any split-K GEMM). */
+int clipgp_tc_gemm_store_splitk(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K, float alpha,
+                                float* C, int64_t ldc, void* stream);
 
 /* Logits alpha * A B^T reduced on the fly per row: max-softmax confidence, arg-max, hit flag, top-1 count and the equal-width
  * ECE histogram (utils/metrics.py:9-36,71-82) -- same outputs / accumulate semantics as clipgp_calibration_from_logits, but the

@@ -96,7 +96,7 @@ def test_tensor_core_step_loss_and_gradients(precision, loss_mode, name):
     eng2.skip_update = True
     loss2 = eng2.train_step(f.cuda(), y.cuda(), use_graph=True)
     assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
-    assert torch.allclose(eng2.flat_g, eng.flat_g, rtol=1e-4, atol=1e-7)
+    assert rel_err(eng2.flat_g, eng.flat_g) < 1e-5            # split-K reductions: fp32 summation order varies run to run
 
 
 def test_adamw_update_and_graph_replay_match_eager():

@@ -75,3 +75,51 @@ def test_fused_calibration_epilogue(M, C, D):
         assert bins["bin_count"] == b["bin_count"]
     assert sum(bins["bin_count"]) == M
     assert ece == pytest.approx(e, rel=1e-3, abs=1e-3)
+
+
+def _unsplit(op, K, Kp, mode):
+    """Reassemble the fp32 value a (split) bf16 operand represents: hi (+ lo)."""
+    op = op.float()
+    if mode == tc.PLAIN:
+        return op[:, :K]
+    hi = op[:, :K]
+    lo = op[:, 2 * Kp:2 * Kp + K] if mode == tc.SPLIT_A else op[:, Kp:Kp + K]
+    return hi + lo
+
+
+@pytest.mark.parametrize("R,K", [(128, 512), (48, 148), (33, 37), (130, 1000), (257, 64)])
+@pytest.mark.parametrize("mode,modeT", [(tc.PLAIN, tc.PLAIN), (tc.SPLIT_A, tc.SPLIT_B), (tc.SPLIT_B, tc.SPLIT_A)])
+def test_dual_layout_cast(R, K, mode, modeT):
+    g = torch.Generator().manual_seed(R * 7 + K)
+    x = _rand(R, K, g)
+    out, outT = tc.cast_bf16_dual(x, mode, modeT)
+    Kp, Rp = (K + 7) // 8 * 8, (R + 7) // 8 * 8
+    ref_o = tc.cast_bf16(x, mode)                                       # the single-layout kernel is the reference layout
+    seg = 3 if mode else 1
+    for gseg in range(seg):
+        assert torch.equal(out[:, gseg * Kp:gseg * Kp + K], ref_o[:, gseg * K:(gseg + 1) * K])
+    ref_t = tc.cast_bf16(x.t().contiguous(), modeT)
+    segT = 3 if modeT else 1
+    for gseg in range(segT):
+        assert torch.equal(outT[:, gseg * Rp:gseg * Rp + R], ref_t[:, gseg * R:(gseg + 1) * R])
+    tol = 2.0 ** -15 if mode else 2.0 ** -8
+    assert float((_unsplit(out, K, Kp, mode) - x).abs().max()) <= tol * float(x.abs().max())
+
+
+@pytest.mark.parametrize("B,S,C", [(16, 3, 12), (48, 4, 37), (128, 10, 1000), (130, 1, 1000)])
+@pytest.mark.parametrize("mode", [tc.PLAIN, tc.SPLIT_A])
+def test_two_phase_softmax_ce_operands(B, S, C, mode):
+    """Loss and dlogits (both operand layouts) of the tensor-core step against torch cross_entropy + autograd."""
+    g = torch.Generator().manual_seed(B + S + C)
+    logits = (8.0 * torch.randn(B, S * C, generator=g)).cuda().requires_grad_(True)
+    y = torch.randint(0, C, (B,), generator=g).cuda()
+    ref = torch.nn.functional.cross_entropy(logits.view(B * S, C), y.repeat_interleave(S), reduction="mean")
+    ref.backward()
+    loss, out, outT = tc.softmax_ce_operands(logits.detach(), y, S, 1.0 / (B * S), mode)
+    assert float(loss) == pytest.approx(float(ref), rel=1e-5)
+    SC = S * C
+    SCp, Bp = (SC + 7) // 8 * 8, (B + 7) // 8 * 8
+    gref = logits.grad
+    tol = (2.0 ** -15 if mode else 2.0 ** -8) * float(gref.abs().max()) + 1e-9
+    assert float((_unsplit(out, SC, SCp, mode) - gref).abs().max()) <= tol
+    assert float((_unsplit(outT, B, Bp, mode) - gref.t()).abs().max()) <= tol
