@@ -5,8 +5,9 @@
 // instruction-fetch bound, ncu stall_no_inst ~ 40 %).  Conventions that keep shared-memory traffic conflict free:
 //   * row stride LD = 33 (odd): "lane = row" walks A[lane*LD + k] hit 32 distinct banks,
 //   * "lane = column" accesses A[k*LD + lane] are contiguous, the other operand of a product is a broadcast read.
-// Only __syncwarp() is used: a CTA is a single warp, so 7 classes are resident per SM (31 KB each) and the whole
-// class set of the ImageNet shape (1000 classes) is one wave on 148 SMs.
+// A CTA is ONE class with NW = 4 warps (31 KB of shared memory, 7 classes resident per SM, so the 1000 classes of the ImageNet
+// shape are one wave on 148 SMs): the matrix products and staging copies are spread over the four warps, the inherently
+// sequential factorisations run in warp 0 (or, for the Cholesky adjoint, with the rank-1 updates split across the warps).
 #pragma once
 #include "gp_common.cuh"
 
@@ -17,7 +18,34 @@ constexpr int LD = 33;                 // row stride (elements) of every per-cla
 constexpr int NN = 33 * LD + 3;        // elements per matrix slot (3 pad elements: 4-wide tiles may read past the last row)
 constexpr unsigned FULL = 0xffffffffu;
 
+constexpr int NW = 4;                  // warps per class CTA
+constexpr int NT = NW * 32;
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// Block-strided walk over a dense row-major [rows, cols] array: f(idx, i, j).
+template <typename F>
+__device__ __forceinline__ void each_block(int rows, int cols, F f) {
+    const int total = rows * cols;
+    for (int idx = threadIdx.x; idx < total; idx += NT) { const int i = idx / cols; f(idx, i, idx - i * cols); }
+}
+
+// Staging copy with four global loads in flight per thread (block-strided).
+template <typename V, typename LD_, typename ST_>
+__device__ __forceinline__ void stage_block(int rows, int cols, LD_ ld, ST_ st) {
+    const int total = rows * cols;
+    for (int base = threadIdx.x; base < total; base += 4 * NT) {
+        V v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int idx = base + NT * u; if (idx < total) v[u] = ld(idx); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + NT * u;
+            if (idx < total) { const int i = idx / cols; st(idx, i, idx - i * cols, v[u]); }
+        }
+    }
+}
 
 // Lane-strided walk over the elements of a dense row-major [rows, cols] array: f(idx, i, j), idx = i*cols + j.
 template <typename F>
@@ -132,6 +160,50 @@ __device__ __forceinline__ float sparsemax_lanes(float f, int T) {
     const int cnt = __popc(__ballot_sync(FULL, sup));
     const float tau = (warp_sum(sup ? z : 0.f) - 1.f) / (float)cnt;
     return valid ? fmaxf(z - tau, 0.f) : 0.f;
+}
+
+// Adjoint of L = chol(A) by the whole CTA: Murray's level-2 reverse sweep (gp::warp_cholesky_rev holds the single-warp form and
+// the output convention: strict lower triangle = SUM of the sensitivities of A_ij and A_ji, diagonal = sensitivity of A_ii).
+// Per column j: warp 0 finishes the pivot terms, then -- concurrently -- warp 0 updates row j (r_bar) while warps 1..3 apply the
+// rank-1 update of the trailing rows (B_bar), each on its third of the columns k < j.  `slot` = one shared T for the pivot adjoint.
+template <typename T>
+__device__ __forceinline__ void chol_rev_block(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ G, int n, T* slot) {
+    const int lane = lane_id(), wid = warp_id();
+    for (int j = n - 1; j >= 0; --j) {
+        __syncthreads();
+        if (wid == 0) {
+            const T inv = invd[j];
+            T part = (T)0;
+            for (int i = j + 1 + lane; i < n; i += 32) part += L[i * LD + j] * G[i * LD + j];
+            part = warp_sum(part);
+            const T db = (G[j * LD + j] - part * inv) * inv;            // (d_bar - c^T c_bar / d) / d
+            __syncwarp();
+            for (int i = j + 1 + lane; i < n; i += 32) G[i * LD + j] *= inv;   // c_bar /= d
+            if (lane == 0) *slot = db;
+        }
+        __syncthreads();
+        const T db = *slot;
+        if (wid == 0) {
+            for (int k = lane; k < j; k += 32) {                        // r_bar -= d_bar r + c_bar^T B
+                T s0 = G[j * LD + k] - db * L[j * LD + k], s1 = (T)0;
+                int i = j + 1;
+                for (; i + 1 < n; i += 2) { s0 -= G[i * LD + j] * L[i * LD + k]; s1 -= G[(i + 1) * LD + j] * L[(i + 1) * LD + k]; }
+                if (i < n) s0 -= G[i * LD + j] * L[i * LD + k];
+                G[j * LD + k] = s0 + s1;
+            }
+            if (lane == 0) G[j * LD + j] = db * (T)0.5;
+        } else {
+            const int per = (j + NW - 2) / (NW - 1);
+            const int k0 = (wid - 1) * per, k1 = min(j, k0 + per);
+            for (int i = j + 1 + lane; i < n; i += 32) {                // B_bar -= c_bar r
+                const T cbi = G[i * LD + j];
+                T* gi = G + i * LD;
+                const T* rj = L + j * LD;
+                for (int k = k0; k < k1; ++k) gi[k] -= cbi * rj[k];
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // Offsets of the per-class record in Ksave ([alias flag | K_ZZ n*n | K_ZX n*T | K_XX T*T]).  For aliased classes the

@@ -10,7 +10,8 @@
 //       written to the scratch part of the class record in Ksave; gp_kernel_adjoint_kernel (gp_backward.cu) turns it into the
 //       length-scale / output-scale / variance / learnable-row gradients with one streamed pass over Z.
 //
-// Shared memory per warp: three fp64 [33][33] regions re-used across the phases + A (fp32) = 31 KB, 7 classes per SM.
+// One 4-warp CTA per class; shared memory: three fp64 [33][33] regions re-used across the phases + A (fp32) = 31 KB,
+// 7 classes per SM.
 #include "gp_warp.cuh"
 
 namespace clipgp {
@@ -21,18 +22,19 @@ struct BwdSmem {
     double RB[NN];       // P1: R | dR->dSigma (fp32 halves);  P2: dBm | dSigma;  P3: L (fp64)
     double RC[NN];       // P2: Lq | H (fp32 halves);  P3: dL -> chol adjoint (fp64)
     double invd[34];
+    double slot;         // pivot adjoint of the Cholesky reverse sweeps
     float Af[NN];
     float mvec[36];
     float vecT[32];      // P1: 1 / R_ii;  P2: dmu
 };
 
-__global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b) {
+__global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b) {
     extern __shared__ __align__(16) unsigned char smw[];
     BwdSmem& s = *reinterpret_cast<BwdSmem*>(smw);
-    const int lane = threadIdx.x, c = blockIdx.x;
+    const int lane = lane_id(), wid = warp_id(), tid = threadIdx.x, c = blockIdx.x;
     const int T = (int)a.T, n = T + 1, S = (int)a.S;
     float* ks = a.Ksave + (size_t)c * ksave_stride(n, T);
-    if (ks[0] == 0.f) return;                      // un-aliased class: handled by the block kernel
+    if (ks[0] == 0.f) return;                      // un-aliased class: handled by the block kernel (uniform per CTA)
     float* dKt = ks + 1 + n * n;                   // scratch: d loss / d K block, [n][n]
     const float dkl = b.dkl ? b.dkl[c] : b.dkl_scalar;
     const int lt = lane < T ? lane : T - 1;        // clamped lane for row-per-lane walks
@@ -42,16 +44,18 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
     float* G = R + NN;
     {
         const float* Rg = a.R + (size_t)c * T * T;
-        stage<float>(T, T, [&](int idx) { return __ldg(Rg + idx); },
-                     [&](int idx, int i, int j, float v) { R[i * LD + j] = v; G[i * LD + j] = 0.f; });
+        stage_block<float>(T, T, [&](int idx) { return __ldg(Rg + idx); },
+                           [&](int idx, int i, int j, float v) { R[i * LD + j] = v; G[i * LD + j] = 0.f; });
     }
-    __syncwarp();
-    if (lane < T) s.vecT[lane] = 1.f / R[lane * LD + lane];
+    __syncthreads();
+    if (tid < T) s.vecT[tid] = 1.f / R[tid * LD + tid];
     float dmu = 0.f;
     {
+        // every warp walks all samples (the sparsemax adjoint is a few instructions) and accumulates its own eight columns of dR
         uint64_t seed = 0, step = 0;
         if (a.eps == nullptr) { seed = a.rng_state[0]; step = a.rng_state[1]; }
         float* Grow = G + lt * LD;
+        const int kq0 = 8 * wid, kq1 = min(T, kq0 + 8);
         for (int sidx = 0; sidx < S; ++sidx) {
             const size_t off = ((size_t)sidx * a.C + c) * T;
             const float wv = lane < T ? a.w[off + lane] : 0.f;
@@ -67,22 +71,22 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
                 else e = philox_normal(seed, step, ((uint64_t)c * T + lane) * (uint64_t)a.S_total + (uint64_t)(a.s_offset + sidx));
             }
             if (cnt == 0) continue;                             // warp-uniform
-            for (int k = 0; k < T; ++k) {                       // dR[lane][k] += df_lane eps_k (upper part is never read)
+            for (int k = kq0; k < kq1; ++k) {                   // dR[lane][k] += df_lane eps_k (upper part is never read)
                 const float ek = __shfl_sync(FULL, e, k);
                 if (lane < T) Grow[k] = fmaf(df, ek, Grow[k]);
             }
         }
     }
-    __syncwarp();
-    gp::warp_cholesky_rev<float>(R, LD, s.vecT, G, LD, T);
-    __syncwarp();
-    each(T, T, [&](int idx, int i, int j) {                     // G <- dSigma, full symmetric
+    chol_rev_block<float>(R, s.vecT, G, T, reinterpret_cast<float*>(&s.slot));
+    each_block(T, T, [&](int idx, int i, int j) {               // G <- dSigma, full symmetric
         if (i > j) { const float v = 0.5f * G[i * LD + j]; G[i * LD + j] = v; G[j * LD + i] = v; }
     });
-    __syncwarp();
-    each(n, n, [&](int idx, int i, int j) { dKt[idx] = (i < T && j < T) ? G[i * LD + j] : 0.f; });
-    if (b.dmean_x && lane < T) b.dmean_x[(size_t)c * T + lane] = dmu;
-    if (lane < T) s.vecT[lane] = dmu;                           // 1 / R_ii is dead
+    __syncthreads();
+    each_block(n, n, [&](int idx, int i, int j) { dKt[idx] = (i < T && j < T) ? G[i * LD + j] : 0.f; });
+    if (wid == 0) {
+        if (b.dmean_x && lane < T) b.dmean_x[(size_t)c * T + lane] = dmu;
+        if (lane < T) s.vecT[lane] = dmu;                       // 1 / R_ii is dead
+    }
 
     // =========================== P2 ===========================
     float* Lq = reinterpret_cast<float*>(s.RC);
@@ -91,14 +95,14 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
     {
         const float* Ag = a.A + (size_t)c * n * T;
         const float* cv = a.chol_var + (size_t)c * n * n;
-        stage<float>(n, T, [&](int idx) { return __ldg(Ag + idx); }, [&](int idx, int i, int j, float v) { s.Af[i * LD + j] = v; });
-        stage<float>(n, n, [&](int idx) { return __ldg(cv + idx); }, [&](int idx, int i, int j, float v) { Lq[i * LD + j] = (j <= i) ? v : 0.f; });
+        stage_block<float>(n, T, [&](int idx) { return __ldg(Ag + idx); }, [&](int idx, int i, int j, float v) { s.Af[i * LD + j] = v; });
+        stage_block<float>(n, n, [&](int idx) { return __ldg(cv + idx); }, [&](int idx, int i, int j, float v) { Lq[i * LD + j] = (j <= i) ? v : 0.f; });
     }
-    for (int i = lane; i < n; i += 32) s.mvec[i] = __ldg(a.var_mean + (size_t)c * n + i);
-    if (lane < 3) Lq[33 * LD + lane] = 0.f;
-    __syncwarp();
+    for (int i = tid; i < n; i += NT) s.mvec[i] = __ldg(a.var_mean + (size_t)c * n + i);
+    if (tid < 3) Lq[33 * LD + tid] = 0.f;
+    __syncthreads();
     // H = A dSigma  (lane = column t)
-    for (int i0 = 0; i0 < n; i0 += 4) {
+    for (int i0 = 4 * wid; i0 < n; i0 += 4 * NW) {
         const float* a0 = s.Af + i0 * LD;
         const float* a1 = s.Af + min(i0 + 1, n - 1) * LD;
         const float* a2 = s.Af + min(i0 + 2, n - 1) * LD;
@@ -115,9 +119,9 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
             if (i0 + 3 < n) H[(i0 + 3) * LD + lane] = acc3;
         }
     }
-    __syncwarp();
+    __syncthreads();
     // dBm = 2 Lq^T H : dBm[i][t] = 2 sum_{k >= i} Lq[k][i] H[k][t]  (zeros above the diagonal of Lq make k >= i implicit)
-    for (int i0 = 0; i0 < n; i0 += 4) {
+    for (int i0 = 4 * wid; i0 < n; i0 += 4 * NW) {
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
         for (int k = i0; k < n; ++k) {
             const float hv = H[k * LD + lt];
@@ -131,25 +135,28 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
             if (i0 + 3 < n) dBm[(i0 + 3) * LD + lane] = 2.f * acc3;
         }
     }
-    __syncwarp();
+    __syncthreads();
     // dA = -2 H + Lq dBm + m dmu^T  (lane = column t) -> fp64
-    for (int i0 = 0; i0 < n; i0 += 4) {
-        const float* l0 = Lq + i0 * LD;
-        const float* l1 = Lq + min(i0 + 1, n - 1) * LD;
-        const float* l2 = Lq + min(i0 + 2, n - 1) * LD;
-        const float* l3 = Lq + min(i0 + 3, n - 1) * LD;
-        const int kmax = min(i0 + 3, n - 1);
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-        for (int k = 0; k <= kmax; ++k) {
-            const float bv = dBm[k * LD + lt];
-            acc0 = fmaf(l0[k], bv, acc0); acc1 = fmaf(l1[k], bv, acc1); acc2 = fmaf(l2[k], bv, acc2); acc3 = fmaf(l3[k], bv, acc3);
-        }
-        const float accs[4] = {acc0, acc1, acc2, acc3};
-        if (lane < T) {
+    {
+        const float dmu_t = s.vecT[lt];
+        for (int i0 = 4 * wid; i0 < n; i0 += 4 * NW) {
+            const float* l0 = Lq + i0 * LD;
+            const float* l1 = Lq + min(i0 + 1, n - 1) * LD;
+            const float* l2 = Lq + min(i0 + 2, n - 1) * LD;
+            const float* l3 = Lq + min(i0 + 3, n - 1) * LD;
+            const int kmax = min(i0 + 3, n - 1);
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+            for (int k = 0; k <= kmax; ++k) {
+                const float bv = dBm[k * LD + lt];
+                acc0 = fmaf(l0[k], bv, acc0); acc1 = fmaf(l1[k], bv, acc1); acc2 = fmaf(l2[k], bv, acc2); acc3 = fmaf(l3[k], bv, acc3);
+            }
+            const float accs[4] = {acc0, acc1, acc2, acc3};
+            if (lane < T) {
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int i = i0 + x;
-                if (i < n) s.RA[i * LD + lane] = (double)(-2.f * H[i * LD + lane] + accs[x] + s.mvec[i] * dmu);
+                for (int x = 0; x < 4; ++x) {
+                    const int i = i0 + x;
+                    if (i < n) s.RA[i * LD + lane] = (double)(-2.f * H[i * LD + lane] + accs[x] + s.mvec[i] * dmu_t);
+                }
             }
         }
     }
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
     {
         const float* brow = dBm + min(lane, n - 1) * LD;
         float* out = b.dchol_var + (size_t)c * n * n;
-        for (int i0 = 0; i0 < n; i0 += 4) {
+        for (int i0 = 4 * wid; i0 < n; i0 += 4 * NW) {
             const float* a0 = s.Af + i0 * LD;
             const float* a1 = s.Af + min(i0 + 1, n - 1) * LD;
             const float* a2 = s.Af + min(i0 + 2, n - 1) * LD;
@@ -178,37 +185,38 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
                 }
             }
         }
-        if (n == 33) {                                          // column 32: zeros above the diagonal, one entry on it
+        if (n == 33 && wid == 1) {                              // column 32: zeros above the diagonal, one entry on it
             float v = lane < T ? s.Af[32 * LD + lane] * dBm[32 * LD + lane] : 0.f;
             v = warp_sum(v);
             out[(size_t)lane * n + 32] = 0.f;
             if (lane == 0) out[(size_t)32 * n + 32] = v + dkl * (Lq[32 * LD + 32] - 1.f / Lq[32 * LD + 32]);
         }
     }
-    // dm = A dmu + dkl m  (lane = row i)
-    for (int i = lane; i < n; i += 32) {
+    // dm = A dmu + dkl m  (one thread per row i)
+    for (int i = tid; i < n; i += NT) {
         const float* arow = s.Af + i * LD;
         float acc = 0.f;
         for (int t = 0; t < T; ++t) acc = fmaf(arow[t], s.vecT[t], acc);
         b.dvar_mean[(size_t)c * n + i] = acc + dkl * s.mvec[i];
     }
-    __syncwarp();
+    __syncthreads();
 
     // =========================== P3 (fp64) ===========================
     double* Ld = s.RB;
     double* Gd = s.RC;
     {
         const double* Lg = a.L + (size_t)c * n * n;
-        stage<double>(n, n, [&](int idx) { return Lg[idx]; }, [&](int idx, int i, int j, double v) { Ld[i * LD + j] = v; });
+        stage_block<double>(n, n, [&](int idx) { return Lg[idx]; }, [&](int idx, int i, int j, double v) { Ld[i * LD + j] = v; });
     }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) s.invd[i] = 1.0 / Ld[i * LD + i];
-    __syncwarp();
-    trsm_lowerT_cols<double>(Ld, s.invd, s.RA, n, T);           // RA <- dK_ZX = L^-T dA
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) s.invd[i] = 1.0 / Ld[i * LD + i];
+    __syncthreads();
+    if (wid == 0) trsm_lowerT_cols<double>(Ld, s.invd, s.RA, n, T);   // RA <- dK_ZX = L^-T dA
+    __syncthreads();
     // dL = -tril(dK_ZX A^T)  (lane = column j < 32: row j of A)
     {
         const float* arow = s.Af + min(lane, n - 1) * LD;
-        for (int i0 = 0; i0 < n; i0 += 4) {
+        for (int i0 = 4 * wid; i0 < n; i0 += 4 * NW) {
             const double* d0 = s.RA + i0 * LD;
             const double* d1 = s.RA + min(i0 + 1, n - 1) * LD;
             const double* d2 = s.RA + min(i0 + 2, n - 1) * LD;
@@ -225,19 +233,17 @@ __global__ void __launch_bounds__(32) gp_backward_warp_kernel(const clipgp_gp_ar
                 if (i < n && lane <= i && lane < n) Gd[i * LD + lane] = -accs[x];
             }
         }
-        if (n == 33) {
+        if (n == 33 && wid == 1) {
             double v = lane < T ? s.RA[32 * LD + lane] * (double)s.Af[32 * LD + lane] : 0.0;
             v = warp_sum(v);
             if (lane == 0) Gd[32 * LD + 32] = -v;
         }
     }
-    __syncwarp();
-    gp::warp_cholesky_rev<double>(Ld, LD, s.invd, Gd, LD, n);
-    __syncwarp();
-    each(n, n, [&](int idx, int i, int j) {
+    chol_rev_block<double>(Ld, s.invd, Gd, n, &s.slot);
+    each_block(n, n, [&](int idx, int i, int j) {
         float v = (float)gp::sym_from_rev<double>(Gd, LD, i, j);
         if (j < T) v += (float)s.RA[i * LD + j];
-        dKt[idx] += v;                                          // same lane wrote dKt[idx] (the dSigma block) in P1
+        dKt[idx] += v;                                          // same thread wrote dKt[idx] (the dSigma block) in P1
     });
 }
 
@@ -253,6 +259,6 @@ int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_
                                          cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    gpw::gp_backward_warp_kernel<<<(unsigned)a->C, 32, sizeof(gpw::BwdSmem), st>>>(*a, *b);
+    gpw::gp_backward_warp_kernel<<<(unsigned)a->C, gpw::NT, sizeof(gpw::BwdSmem), st>>>(*a, *b);
     return check_launch("gp_backward_warp_kernel");
 }

@@ -4,7 +4,7 @@
 //   L = chol64(K_ZZ + 1e-4 I), A = L^-1 K_ZX, mu = A^T m + mean_x, Bm = Lq^T A, Sigma = K_XX + 1e-4 I + Bm^T Bm - A^T A,
 //   R = chol32(Sigma) (psd_safe jitter retries), KL(q(u) || N(0,I)), f_s = mu + R eps_s, w_s = sparsemax(f_s)
 // (gp_template_weigher.py:166-173,194-219 + gpytorch whitened VariationalStrategy.forward, rsample, entmax.sparsemax).
-// One warp per class, matrices in that warp's shared memory, run-time loops (see gp_warp.cuh).
+// One 4-warp CTA per class, matrices in shared memory, run-time loops (see gp_warp.cuh).
 #include "gp_warp.cuh"
 
 namespace clipgp {
@@ -19,42 +19,42 @@ struct FwdSmem {
     float Lq[NN];        // tril(chol_var); afterwards reused as R = chol32(Sigma)
     float mvec[36];
     float invdR[32];
+    float mu[32];
+    int flag[4];
 };
 
-__global__ void __launch_bounds__(32) gp_forward_warp_kernel(const clipgp_gp_args a) {
+__global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_args a) {
     extern __shared__ __align__(16) unsigned char smw[];
     FwdSmem& s = *reinterpret_cast<FwdSmem*>(smw);
-    const int lane = threadIdx.x, c = blockIdx.x;
+    const int lane = lane_id(), wid = warp_id(), tid = threadIdx.x, c = blockIdx.x;
     const int T = (int)a.T, n = T + 1, S = (int)a.S;
     const float* ks = a.Ksave + (size_t)c * ksave_stride(n, T);
-    if (ks[0] == 0.f) return;                      // un-aliased class: finished by the block kernel
+    if (ks[0] == 0.f) return;                      // un-aliased class: finished by the block kernel (uniform per CTA)
     const float* K = ks + 1;
+    const int lt = lane < T ? lane : T - 1;
 
     // ---- stage K_ZZ: jitter is added in fp32 before the cast, as gpytorch does (add_jitter, then .double())
-    stage<float>(n, n, [&](int idx) { return __ldg(K + idx); }, [&](int idx, int i, int j, float v) {
+    stage_block<float>(n, n, [&](int idx) { return __ldg(K + idx); }, [&](int idx, int i, int j, float v) {
         s.Ld[i * LD + j] = (double)(v + (i == j ? 1e-4f : 0.f));
         if (j < T) s.Ad[i * LD + j] = (double)v;
     });
     {
         const float* cv = a.chol_var + (size_t)c * n * n;
-        stage<float>(n, n, [&](int idx) { return __ldg(cv + idx); },
-                     [&](int idx, int i, int j, float v) { s.Lq[i * LD + j] = (j <= i) ? v : 0.f; });
+        stage_block<float>(n, n, [&](int idx) { return __ldg(cv + idx); },
+                           [&](int idx, int i, int j, float v) { s.Lq[i * LD + j] = (j <= i) ? v : 0.f; });
     }
-    for (int i = lane; i < n; i += 32) s.mvec[i] = __ldg(a.var_mean + (size_t)c * n + i);
-    if (lane < 3) s.Lq[33 * LD + lane] = 0.f;
-    __syncwarp();
+    for (int i = tid; i < n; i += NT) s.mvec[i] = __ldg(a.var_mean + (size_t)c * n + i);
+    if (tid < 3) s.Lq[33 * LD + tid] = 0.f;
+    __syncthreads();
 
-    // ---- L = chol64(K_ZZ + 1e-4 I);  A = L^-1 K_ZX
-    const bool failL = chol33<double>(s.Ld, n, s.invd);
-    __syncwarp();
-    trsm_lower_cols<double>(s.Ld, s.invd, s.Ad, n, T);
-    if (lane < T)
-        for (int i = 0; i < n; ++i) s.Af[i * LD + lane] = (float)s.Ad[i * LD + lane];
-    __syncwarp();
-
-    // ---- KL(q(u) || N(0,I)) = 1/2 (|Lq|_F^2 + |m|^2 - n - sum log Lq_ii^2)
-    if (a.kl) {
-        float part = 0.f;
+    // ---- warp 0: L = chol64(K_ZZ + 1e-4 I), A = L^-1 K_ZX;  warp 1 meanwhile: KL(q(u) || N(0,I))
+    if (wid == 0) {
+        const bool f = chol33<double>(s.Ld, n, s.invd);
+        if (lane == 0) s.flag[0] = f ? 1 : 0;
+        __syncwarp();
+        trsm_lower_cols<double>(s.Ld, s.invd, s.Ad, n, T);
+    } else if (wid == 1 && a.kl) {
+        float part = 0.f;                          // 1/2 (|Lq|_F^2 + |m|^2 - n - sum log Lq_ii^2)
         for (int i = lane; i < n; i += 32) {
             const float* row = s.Lq + i * LD;
             float q = 0.f;
@@ -64,18 +64,23 @@ __global__ void __launch_bounds__(32) gp_forward_warp_kernel(const clipgp_gp_arg
         part = warp_sum(part);
         if (lane == 0) a.kl[c] = 0.5f * (part - (float)n);
     }
+    __syncthreads();
+    const bool failL = s.flag[0] != 0;
+    each_block(n, T, [&](int idx, int i, int j) { s.Af[i * LD + j] = (float)s.Ad[i * LD + j]; });
+    __syncthreads();
 
-    // ---- mu = A^T m + mean_x (lane = test point)
-    float mu = 0.f;
-    if (lane < T) {
+    // ---- mu = A^T m + mean_x (warp 3, lane = test point)
+    if (wid == 3 && lane < T) {
+        float mu = 0.f;
         for (int i = 0; i < n; ++i) mu = fmaf(s.Af[i * LD + lane], s.mvec[i], mu);
         if (a.mean_x) mu += __ldg(a.mean_x + (size_t)c * T + lane);
+        s.mu[lane] = mu;
     }
     // ---- Bm = Lq^T A : Bm[i][t] = sum_{k >= i} Lq[k][i] A[k][t]  (Lq is zero above the diagonal: no k >= i test needed)
-    for (int i0 = 0; i0 < n; i0 += 4) {
+    for (int i0 = 4 * wid; i0 < n; i0 += 4 * NW) {
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
         for (int k = i0; k < n; ++k) {
-            const float av = s.Af[k * LD + lane];
+            const float av = s.Af[k * LD + lt];
             const float* lq = s.Lq + k * LD + i0;
             acc0 = fmaf(lq[0], av, acc0); acc1 = fmaf(lq[1], av, acc1); acc2 = fmaf(lq[2], av, acc2); acc3 = fmaf(lq[3], av, acc3);
         }
@@ -86,14 +91,14 @@ __global__ void __launch_bounds__(32) gp_forward_warp_kernel(const clipgp_gp_arg
             if (i0 + 3 < n) s.Bm[(i0 + 3) * LD + lane] = acc3;
         }
     }
-    __syncwarp();
+    __syncthreads();
 
     // ---- Sigma = K_XX + 1e-4 I + Bm^T Bm - A^T A (lower triangle), lane = column u, four rows t per pass
     float* Sig = reinterpret_cast<float*>(s.Ad);
-    for (int t0 = 0; t0 < T; t0 += 4) {
+    for (int t0 = 4 * wid; t0 < T; t0 += 4 * NW) {
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
         for (int k = 0; k < n; ++k) {
-            const float bu = s.Bm[k * LD + lane], au = s.Af[k * LD + lane];
+            const float bu = s.Bm[k * LD + lt], au = s.Af[k * LD + lt];
             const float* bt = s.Bm + k * LD + t0;
             const float* at = s.Af + k * LD + t0;
             acc0 += bt[0] * bu - at[0] * au; acc1 += bt[1] * bu - at[1] * au;
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(32) gp_forward_warp_kernel(const clipgp_gp_arg
             if (t < T && lane <= t) Sig[t * LD + lane] = (__ldg(K + t * n + lane) + (t == lane ? 1e-4f : 0.f)) + accs[x];
         }
     }
-    __syncwarp();
+    __syncthreads();
 
     // ---- R = chol32(Sigma), psd_safe_cholesky retries with total diagonal jitter 1e-6, 1e-5, 1e-4
     float* R = s.Lq;                                // Lq is dead (its zeros above the diagonal stay in place)
@@ -114,27 +119,32 @@ __global__ void __launch_bounds__(32) gp_forward_warp_kernel(const clipgp_gp_arg
     bool failR = true;
     for (int attempt = 0; attempt < 4; ++attempt) {
         const float jit = attempt == 0 ? 0.f : (attempt == 1 ? 1e-6f : (attempt == 2 ? 1e-5f : 1e-4f));
-        for (int t = 0; t < T; ++t)
-            if (lane <= t) R[t * LD + lane] = Sig[t * LD + lane] + (t == lane ? jit : 0.f);
-        __syncwarp();
-        failR = chol33<float>(R, T, s.invdR);
-        __syncwarp();
+        each_block(T, T, [&](int idx, int t, int u) { if (u <= t) R[t * LD + u] = Sig[t * LD + u] + (t == u ? jit : 0.f); });
+        __syncthreads();
+        if (wid == 0) {
+            const bool f = chol33<float>(R, T, s.invdR);
+            if (lane == 0) s.flag[1] = f ? 1 : 0;
+        }
+        __syncthreads();
+        failR = s.flag[1] != 0;
         if (!failR) break;
         ++retries;
+        __syncthreads();                            // everyone has read the flag before the next attempt rewrites it
     }
     const int st = failL ? -2 : (failR ? -1 : retries);
-    if (lane == 0 && a.status) a.status[c] = st;
+    if (tid == 0 && a.status) a.status[c] = st;
 
     // ---- saved factors for the adjoint
-    if (a.L) each(n, n, [&](int idx, int i, int j) { a.L[(size_t)c * n * n + idx] = (j <= i) ? s.Ld[i * LD + j] : 0.0; });
-    if (a.A) each(n, T, [&](int idx, int i, int j) { a.A[(size_t)c * n * T + idx] = s.Af[i * LD + j]; });
-    if (a.R) each(T, T, [&](int idx, int i, int j) { a.R[(size_t)c * T * T + idx] = (j <= i) ? R[i * LD + j] : 0.f; });
+    if (a.L) each_block(n, n, [&](int idx, int i, int j) { a.L[(size_t)c * n * n + idx] = (j <= i) ? s.Ld[i * LD + j] : 0.0; });
+    if (a.A) each_block(n, T, [&](int idx, int i, int j) { a.A[(size_t)c * n * T + idx] = s.Af[i * LD + j]; });
+    if (a.R) each_block(T, T, [&](int idx, int i, int j) { a.R[(size_t)c * T * T + idx] = (j <= i) ? R[i * LD + j] : 0.f; });
 
-    // ---- f_s = mu + R eps_s ; w_s = sparsemax(f_s)   (lane = template)
+    // ---- f_s = mu + R eps_s ; w_s = sparsemax(f_s)   (one sample per warp at a time, lane = template)
     uint64_t seed = 0, step = 0;
     if (a.eps == nullptr) { seed = a.rng_state[0]; step = a.rng_state[1]; }
-    const float* Rrow = R + (lane < T ? lane : 0) * LD;
-    for (int sidx = 0; sidx < S; ++sidx) {
+    const float* Rrow = R + lt * LD;
+    const float mu = s.mu[lt];
+    for (int sidx = wid; sidx < S; sidx += NW) {
         float e = 0.f;
         if (lane < T) {
             if (a.eps) e = a.eps[(size_t)c * a.eps_sc + (size_t)lane * a.eps_st + (size_t)sidx * a.eps_ss];
@@ -170,6 +180,6 @@ int clipgp_gp_forward_warp_launch(const clipgp_gp_args* a, cudaStream_t st) {
                                          cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    gpw::gp_forward_warp_kernel<<<(unsigned)a->C, 32, sizeof(gpw::FwdSmem), st>>>(*a);
+    gpw::gp_forward_warp_kernel<<<(unsigned)a->C, gpw::NT, sizeof(gpw::FwdSmem), st>>>(*a);
     return check_launch("gp_forward_warp_kernel");
 }
