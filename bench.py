@@ -397,7 +397,7 @@ def run_ours(args):
                    "l2_flush": "256 MB device buffer written between timed steps", "precision": {"fp32": "fp32 (FFMA GEMMs, fp64 K_ZZ Cholesky)",
                                  "bf16x3": "tcgen05 GEMMs on split-bf16 operands (fp32-grade products; the reference's GPU path is TF32), fp32 everywhere else, fp64 K_ZZ Cholesky",
                                  "bf16": "tcgen05 bf16 GEMMs, fp32 everywhere else, fp64 K_ZZ Cholesky"}[args.precision],
-                   "cuda_graph": eng._graph is not None, "loss_last": loss_last},
+                   "cuda_graph": eng._graph is not None, "two_stream_overlap": bool(eng.cfg.overlap), "loss_last": loss_last},
         "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": shp.B * shp.D * 4 + shp.B * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches_per_step) * args.steps,
         "gpu_launches_per_step": int(launches_per_step),
@@ -461,6 +461,8 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
         return {}
     eng.lib = Proxy()
     out = {}
+    overlap_was = eng.cfg.overlap
+    eng.cfg.overlap = False          # serialise the two branches of the step so that the per-kernel events do not overlap
     try:
         for r in range(reps):
             records.clear()
@@ -479,6 +481,7 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
                 if fl: d["flops"] = fl
     finally:
         eng.lib = lib
+        eng.cfg.overlap = overlap_was
     return out
 
 

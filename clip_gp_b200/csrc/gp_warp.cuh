@@ -24,17 +24,23 @@ constexpr int NT = NW * 32;
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
+// idx / cols for 0 <= idx < 2^20 without an integer division: (idx + 0.5) / cols is at least 0.5 / cols away from any integer,
+// far more than the fp32 rounding of the product.
+__device__ __forceinline__ int fast_div(int idx, float inv_cols) { return __float2int_rz(((float)idx + 0.5f) * inv_cols); }
+
 // Block-strided walk over a dense row-major [rows, cols] array: f(idx, i, j).
 template <typename F>
 __device__ __forceinline__ void each_block(int rows, int cols, F f) {
     const int total = rows * cols;
-    for (int idx = threadIdx.x; idx < total; idx += NT) { const int i = idx / cols; f(idx, i, idx - i * cols); }
+    const float inv = 1.f / (float)cols;
+    for (int idx = threadIdx.x; idx < total; idx += NT) { const int i = fast_div(idx, inv); f(idx, i, idx - i * cols); }
 }
 
 // Staging copy with four global loads in flight per thread (block-strided).
 template <typename V, typename LD_, typename ST_>
 __device__ __forceinline__ void stage_block(int rows, int cols, LD_ ld, ST_ st) {
     const int total = rows * cols;
+    const float inv = 1.f / (float)cols;
     for (int base = threadIdx.x; base < total; base += 4 * NT) {
         V v[4];
 #pragma unroll
@@ -42,7 +48,7 @@ __device__ __forceinline__ void stage_block(int rows, int cols, LD_ ld, ST_ st) 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int idx = base + NT * u;
-            if (idx < total) { const int i = idx / cols; st(idx, i, idx - i * cols, v[u]); }
+            if (idx < total) { const int i = fast_div(idx, inv); st(idx, i, idx - i * cols, v[u]); }
         }
     }
 }

@@ -43,6 +43,7 @@ class EngineConfig:
     train_visual_proj: bool = True      # FREEZE_VISUAL_PROJ False
     precision: str = "fp32"             # GEMMs of the step: "fp32" (FFMA, exact comparator) | "bf16x3" (tcgen05, split operands,
                                         # fp32-grade products: the reference itself runs TF32, adapter.py:23) | "bf16" (tcgen05)
+    overlap: bool = True                # run the feature branch of the step on a side stream next to the GP branch
     seed: int = 0
     rank: int = 0
     world: int = 1
@@ -98,6 +99,7 @@ class GPAdapterEngine:
         # ---- device scalars
         self.rng_state = torch.tensor([int(cfg.seed), 0], dtype=torch.int64, device=dev)
         self.adam_step = torch.ones(1, dtype=torch.int64, device=dev)
+        self._side_stream = torch.cuda.Stream(dev)
         self._alloc_train(cfg.batch_size)
         self._graph = None
 
@@ -209,19 +211,53 @@ class GPAdapterEngine:
                                                         float(alpha), out_ptr, ldc, _lib.stream_ptr(self.dev)), "tc_gemm_store_splitk")
 
     # ------------------------------------------------------------------ one training step (launch only)
+    # The step is a small dependency graph with two independent branches on either side of the logit GEMM:
+    #   features:   cast -> projection GEMM -> row normalise -> casts            | d f_hat GEMM -> normalise adjoint -> dW GEMM -> L2
+    #   prototypes: GP forward (Gram + algebra) -> prototypes -> casts           | d P_hat GEMM -> prototype adjoint -> GP adjoint -> KL
+    # The feature branch (few, latency-bound launches) runs on a side stream next to the GP branch (one-wave kernels that leave
+    # issue slots free); inside the captured CUDA graph this becomes two parallel chains.
     def _launch_step(self):
-        lib, cfg = self.lib, self.cfg
-        st = _lib.stream_ptr(self.dev)
-        ck = _lib.check
-        B, Cn, T, D, S = self.B, self.C, self.T, self.D, self.S_local
-        S_tot = cfg.S_train
-        per_sample = cfg.loss_mode == "per_sample"
-        SC = (S if per_sample else 1) * Cn
+        cfg = self.cfg
+        main = torch.cuda.current_stream(self.dev)
+        side = self._side_stream if cfg.overlap else None
         self.flat_g.zero_()
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._fwd_features()
+        else:
+            self._fwd_features()
+        self._fwd_prototypes()
+        if side is not None:
+            main.wait_stream(side)
+        self._logits_and_loss()
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._bwd_features()
+        else:
+            self._bwd_features()
+        self._bwd_prototypes()
+        if side is not None:
+            main.wait_stream(side)
+        if cfg.world > 1:
+            torch.distributed.all_reduce(self.flat_g)         # ONE fused all-reduce: gradients + loss
+        if not getattr(self, "skip_update", False):
+            self._launch_update()
+
+    def _dims(self):
+        per_sample = self.cfg.loss_mode == "per_sample"
+        S = self.S_local
+        SC = (S if per_sample else 1) * self.C
+        alpha = self.cfg.logit_scale * (1.0 if per_sample else 1.0 / S)
+        return per_sample, S, SC, alpha
+
+    def _fwd_features(self):
+        """visual projection + normalisation (adapter.py:419-420)"""
+        lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
+        B, D = self.B, self.D
         W = self._ptr(self.flat_p, "W")
-        # visual projection + normalisation (adapter.py:419-420)
-        tcm = cfg.precision != "fp32"
-        if tcm:
+        if cfg.precision != "fp32":
             ma, mb = self.tc_ma, self.tc_mb
             self._cast2(self.in_feat.data_ptr(), B, D, D, self.fb, D, ma, self.fTb if cfg.train_visual_proj else None, self.Bp, mb)
             self._cast(W, D, D, D, self.Wb, D, mb)
@@ -229,23 +265,36 @@ class GPAdapterEngine:
         else:
             ck(lib.clipgp_gemm_f32(self.in_feat.data_ptr(), D, 1, W, 1, D, self.Y.data_ptr(), D, B, D, D, 1.0, 0, st), "gemm(proj)")
         ck(lib.clipgp_rownorm_forward(self.Y.data_ptr(), B, D, self.f_hat.data_ptr(), self.f_inv.data_ptr(), None, st), "rownorm")
-        # GP weights + unit prototypes (adapter.py:404, 424-425)
+        if cfg.precision != "fp32":
+            self._cast2(self.f_hat.data_ptr(), B, D, D, self.fhb, D, self.tc_ma, self.fhTb, self.Bp, self.tc_mb)
+
+    def _fwd_prototypes(self):
+        """GP weights + unit prototypes (adapter.py:404, 424-425)"""
+        lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
+        Cn, T, D = self.C, self.T, self.D
+        per_sample, S, SC, _ = self._dims()
         ck(lib.clipgp_gp_forward(C.byref(self.gp_args), st), "gp_forward")
         ck(lib.clipgp_proto_forward(self.w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, self.P_hat.data_ptr(),
                                     self.P_norm.data_ptr(), None, None if per_sample else self.P_mean.data_ptr(), None, 0, st), "proto_forward")
+        if cfg.precision != "fp32":
+            Bmat = self.P_hat if per_sample else self.P_mean
+            self._cast2(Bmat.data_ptr(), SC, D, D, self.Pb, D, self.tc_mb, self.PTb if cfg.train_visual_proj else None, self.SCp, self.tc_mb)
+
+    def _logits_and_loss(self):
+        """logits (adapter.py:426) -> cross-entropy + gradient (adapter.py:427-428)"""
+        lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
+        B, Cn, D = self.B, self.C, self.D
+        per_sample, S, SC, alpha = self._dims()
         Bmat = self.P_hat if per_sample else self.P_mean
-        # logits (adapter.py:426) -> cross-entropy + gradient (adapter.py:427-428)
-        alpha = cfg.logit_scale * (1.0 if per_sample else 1.0 / S)
+        tcm = cfg.precision != "fp32"
         if tcm:
-            self._cast2(self.f_hat.data_ptr(), B, D, D, self.fhb, D, ma, self.fhTb, self.Bp, mb)
-            self._cast2(Bmat.data_ptr(), SC, D, D, self.Pb, D, mb, self.PTb if cfg.train_visual_proj else None, self.SCp, mb)
             self._tc(self.fhb, self.Pb, alpha, self.logits.data_ptr(), SC)
         else:
             ck(lib.clipgp_gemm_f32(self.f_hat.data_ptr(), D, 1, Bmat.data_ptr(), 1, D, self.logits.data_ptr(), SC, B, SC, D,
                                    alpha, 0, st), "gemm(logits)")
         if per_sample:
             rows, rpl = B * S, S
-            loss_scale = 1.0 / (B * S_tot)
+            loss_scale = 1.0 / (B * cfg.S_train)
         else:
             rows, rpl = B, 1
             loss_scale = 1.0 / (B * cfg.world)
@@ -258,49 +307,56 @@ class GPAdapterEngine:
                                            self.loss.data_ptr(), loss_scale, st), "softmax_ce_stats")
             ck(lib.clipgp_softmax_grad_bf16_dual(self.logits.data_ptr(), self.sm_stats.data_ptr(), self.in_lab.data_ptr(), B, rpl, Cn,
                                                  loss_scale, _lib.ptr(self.dlb) if cfg.train_visual_proj else None, self.dlb.stride(0),
-                                                 self.SCp, ma, self.dlTb.data_ptr(), self.dlTb.stride(0), self.Bp, ma, st), "softmax_grad")
+                                                 self.SCp, self.tc_ma, self.dlTb.data_ptr(), self.dlTb.stride(0), self.Bp, self.tc_ma, st),
+               "softmax_grad")
         else:
             ck(lib.clipgp_softmax_ce(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, None, self.loss.data_ptr(),
                                      loss_scale, self.logits.data_ptr(), Cn, loss_scale, st), "softmax_ce")
-        # adjoints of the logit GEMM: dP_hat = scale * dlogits^T f_hat ; df_hat = scale * dlogits P_hat
+
+    def _bwd_features(self):
+        """df_hat = scale * dlogits P_hat -> normalisation adjoint -> dW = dY^T f (+ L2 regulariser, adapter.py:468-476)"""
+        lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
+        if not cfg.train_visual_proj:
+            return
+        B, D = self.B, self.D
+        per_sample, S, SC, alpha = self._dims()
+        Bmat = self.P_hat if per_sample else self.P_mean
+        W = self._ptr(self.flat_p, "W")
+        tcm = cfg.precision != "fp32"
         if tcm:
+            # dlogits [B, SC] and P_hat^T [D, SC] (K = samples x classes; split over K inside the GEMM)
+            self._tc(self.dlb, self.PTb, alpha, self.df_hat.data_ptr(), D)
+        else:
+            ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), SC, 1, Bmat.data_ptr(), D, 1, self.df_hat.data_ptr(), D, B, D, SC,
+                                   alpha, 0, st), "gemm(df)")
+        ck(lib.clipgp_rownorm_backward(self.df_hat.data_ptr(), self.f_hat.data_ptr(), self.f_inv.data_ptr(), B, D,
+                                       self.dY.data_ptr(), st), "rownorm_bwd")
+        if tcm:
+            self._cast2(self.dY.data_ptr(), B, D, D, None, 0, 0, self.dYTb, self.Bp, self.tc_ma)
+            self._tc(self.dYTb, self.fTb, 1.0, self._ptr(self.flat_g, "W"), D)
+        else:
+            ck(lib.clipgp_gemm_f32(self.dY.data_ptr(), 1, D, self.in_feat.data_ptr(), D, 1, self._ptr(self.flat_g, "W"), D, D, D, B,
+                                   1.0, 0, st), "gemm(dW)")
+        coef = float(cfg.l2_lambda) / float(cfg.shots) / cfg.world
+        ck(lib.clipgp_l2_identity(W, D, coef, self._ptr(self.flat_g, "W"), self.loss.data_ptr(), st), "l2_identity")
+
+    def _bwd_prototypes(self):
+        """dP_hat = scale * dlogits^T f_hat -> prototype + GP adjoints (dkl_scalar = gp_beta: adapter.py:462-465)"""
+        lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
+        B, Cn, T, D = self.B, self.C, self.T, self.D
+        per_sample, S, SC, alpha = self._dims()
+        if cfg.precision != "fp32":
             # K-major operands: dlogits^T [SC, B] and f_hat^T [D, B] (K = batch)
             self._tc(self.dlTb, self.fhTb, alpha, self.dP.data_ptr(), D)
         else:
             ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), 1, SC, self.f_hat.data_ptr(), D, 1, self.dP.data_ptr(), D, SC, D, B,
                                    alpha, 0, st), "gemm(dP)")
-        if cfg.train_visual_proj:
-            if tcm:
-                # dlogits [B, SC] and P_hat^T [D, SC] (K = samples x classes; split over K inside the GEMM)
-                self._tc(self.dlb, self.PTb, alpha, self.df_hat.data_ptr(), D)
-            else:
-                ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), SC, 1, Bmat.data_ptr(), D, 1, self.df_hat.data_ptr(), D, B, D, SC,
-                                       alpha, 0, st), "gemm(df)")
-            ck(lib.clipgp_rownorm_backward(self.df_hat.data_ptr(), self.f_hat.data_ptr(), self.f_inv.data_ptr(), B, D,
-                                           self.dY.data_ptr(), st), "rownorm_bwd")
-            # dW = dY^T f (+ L2 regulariser, adapter.py:468-476)
-            if tcm:
-                self._cast2(self.dY.data_ptr(), B, D, D, None, 0, 0, self.dYTb, self.Bp, ma)
-                self._tc(self.dYTb, self.fTb, 1.0, self._ptr(self.flat_g, "W"), D)
-            else:
-                ck(lib.clipgp_gemm_f32(self.dY.data_ptr(), 1, D, self.in_feat.data_ptr(), D, 1, self._ptr(self.flat_g, "W"), D, D, D, B,
-                                       1.0, 0, st), "gemm(dW)")
-            coef = float(cfg.l2_lambda) / float(cfg.shots) / cfg.world
-            ck(lib.clipgp_l2_identity(W, D, coef, self._ptr(self.flat_g, "W"), self.loss.data_ptr(), st), "l2_identity")
-        # prototype + GP adjoints (dkl_scalar = gp_beta: adapter.py:462-465)
-        if per_sample:
-            ck(lib.clipgp_proto_backward(self.dP.data_ptr(), Cn * D, 1.0, self.P_hat.data_ptr(), self.P_norm.data_ptr(),
-                                         self.E.data_ptr(), S, Cn, T, D, self.dw.data_ptr(), st), "proto_backward")
-        else:
-            # mean over samples happened on unit rows: every sample receives dP_mean (the 1/S is inside alpha)
-            ck(lib.clipgp_proto_backward(self.dP.data_ptr(), 0, 1.0, self.P_hat.data_ptr(), self.P_norm.data_ptr(),
-                                         self.E.data_ptr(), S, Cn, T, D, self.dw.data_ptr(), st), "proto_backward")
+        # per-sample: dense [S,C,D] gradient; logit-mean: the mean over samples happened on unit rows, every sample receives
+        # dP_mean (the 1/S is inside alpha)
+        ck(lib.clipgp_proto_backward(self.dP.data_ptr(), Cn * D if per_sample else 0, 1.0, self.P_hat.data_ptr(), self.P_norm.data_ptr(),
+                                     self.E.data_ptr(), S, Cn, T, D, self.dw.data_ptr(), st), "proto_backward")
         ck(lib.clipgp_gp_backward(C.byref(self.gp_args), C.byref(self.gp_bwd_args), st), "gp_backward")
         ck(lib.clipgp_sum_accumulate(self.kl.data_ptr(), Cn, float(cfg.gp_beta) / cfg.world, self.loss.data_ptr(), st), "kl_sum")
-        if cfg.world > 1:
-            torch.distributed.all_reduce(self.flat_g)         # ONE fused all-reduce: gradients + loss
-        if not getattr(self, "skip_update", False):
-            self._launch_update()
 
     def _launch_update(self):
         lib, cfg, st = self.lib, self.cfg, _lib.stream_ptr(self.dev)
