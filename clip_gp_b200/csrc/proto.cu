@@ -38,20 +38,29 @@ __global__ void __launch_bounds__(kProtoThreads) proto_forward_kernel(
 #pragma unroll
         for (int g = 0; g < G; ++g) acc[s][g] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* Ec = reinterpret_cast<const float4*>(E + (size_t)c * T * D);
-    for (int t = 0; t < T; ++t) {
-        float4 e[G];
+    // TB template rows are fetched before any is consumed: TB*G 16-byte loads in flight per thread hide the HBM latency
+    constexpr int TB = (G == 1) ? 8 : (G == 2 ? 4 : 2);
+    for (int t0 = 0; t0 < T; t0 += TB) {
+        float4 e[TB][G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int col = tid + g * kProtoThreads;
-            e[g] = (col < D4) ? __ldg(Ec + (size_t)t * D4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int s = 0; s < SB; ++s) {
-            const float wv = ws[s][t];
+        for (int u = 0; u < TB; ++u)
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                acc[s][g].x = fmaf(wv, e[g].x, acc[s][g].x); acc[s][g].y = fmaf(wv, e[g].y, acc[s][g].y);
-                acc[s][g].z = fmaf(wv, e[g].z, acc[s][g].z); acc[s][g].w = fmaf(wv, e[g].w, acc[s][g].w);
+                const int col = tid + g * kProtoThreads;
+                e[u][g] = (col < D4 && t0 + u < T) ? __ldg(Ec + (size_t)(t0 + u) * D4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            if (t0 + u < T) {
+#pragma unroll
+                for (int s = 0; s < SB; ++s) {
+                    const float wv = ws[s][t0 + u];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        acc[s][g].x = fmaf(wv, e[u][g].x, acc[s][g].x); acc[s][g].y = fmaf(wv, e[u][g].y, acc[s][g].y);
+                        acc[s][g].z = fmaf(wv, e[u][g].z, acc[s][g].z); acc[s][g].w = fmaf(wv, e[u][g].w, acc[s][g].w);
+                    }
+                }
             }
         }
     }
@@ -231,16 +240,36 @@ __global__ void __launch_bounds__(kProtoThreads) proto_backward_kernel(
         __syncthreads();
     }
     const float4* Ec = reinterpret_cast<const float4*>(E + (size_t)c * T * D);
+    // each warp walks its template rows with the next row's loads (up to 4 x 16 bytes per lane) already in flight
+    constexpr int EP = 4;
+    float4 nxt[EP];
+    auto fetch = [&](int t, int col0) {
+#pragma unroll
+        for (int u = 0; u < EP; ++u) {
+            const int col = col0 + lane + 32 * u;
+            nxt[u] = (t < T && col < D4) ? __ldg(Ec + (size_t)t * D4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    fetch(warp, 0);
     for (int t = warp; t < T; t += nwarps) {
         float part[SB];
 #pragma unroll
         for (int s = 0; s < SB; ++s) part[s] = 0.f;
-        for (int col = lane; col < D4; col += 32) {
-            const float4 e = __ldg(Ec + (size_t)t * D4 + col);
+        for (int col0 = 0; col0 < D4; col0 += 32 * EP) {
+            float4 e[EP];
 #pragma unroll
-            for (int s = 0; s < SB; ++s) {
-                const float4 v = reinterpret_cast<const float4*>(g + (size_t)s * D)[col];
-                part[s] += e.x * v.x + e.y * v.y + e.z * v.z + e.w * v.w;
+            for (int u = 0; u < EP; ++u) e[u] = nxt[u];
+            if (col0 + 32 * EP < D4) fetch(t, col0 + 32 * EP); else fetch(t + nwarps, 0);
+#pragma unroll
+            for (int u = 0; u < EP; ++u) {
+                const int col = col0 + lane + 32 * u;
+                if (col < D4) {
+#pragma unroll
+                    for (int s = 0; s < SB; ++s) {
+                        const float4 v = reinterpret_cast<const float4*>(g + (size_t)s * D)[col];
+                        part[s] += e[u].x * v.x + e[u].y * v.y + e[u].z * v.z + e[u].w * v.w;
+                    }
+                }
             }
         }
 #pragma unroll
@@ -323,14 +352,29 @@ extern "C" int clipgp_proto_backward(const float* dP, int64_t dP_stride_s, float
     CLIPGP_REQUIRE(dP && E && dw, "proto_backward: NULL pointer");
     CLIPGP_REQUIRE((P_hat == nullptr) == (norm == nullptr), "proto_backward: P_hat and norm go together");
     CLIPGP_REQUIRE(dP_stride_s == 0 || dP_stride_s >= C * D, "proto_backward: dP_stride_s must be 0 (broadcast over samples) or >= C*D");
-    constexpr int SB = 8;
-    const size_t smem = sizeof(float) * SB * (size_t)D;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        CLIPGP_CUDA(cudaFuncSetAttribute(proto_backward_kernel<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    // samples per CTA: E[c] is streamed once per chunk of SB samples and the FMA / shared-memory work grows with SB, so split S
+    // into ceil(S/8) equal chunks (S = 10 -> 2 x 5 instead of 8 + 2)
+    const int chunks = (int)((S + 7) / 8);
+    const int SB = (int)((S + chunks - 1) / chunks);
+    const size_t smem = sizeof(float) * 8 * (size_t)D;
+    dim3 grid((unsigned)C, (unsigned)chunks);
+#define LAUNCH_BWD(SBV)                                                                                                          \
+    do {                                                                                                                         \
+        static size_t smem_set = 0;                                                                                              \
+        if (smem > smem_set) {                                                                                                   \
+            CLIPGP_CUDA(cudaFuncSetAttribute(proto_backward_kernel<SBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            smem_set = smem;                                                                                                     \
+        }                                                                                                                        \
+        proto_backward_kernel<SBV><<<grid, kProtoThreads, smem, (cudaStream_t)stream>>>(dP, dP_stride_s, dP_scale, P_hat, norm, E, S, C, \
+                                                                                        (int)T, (int)D, dw);                     \
+    } while (0)
+    switch (SB) {
+        case 1: case 2: case 3: case 4: LAUNCH_BWD(4); break;
+        case 5: LAUNCH_BWD(5); break;
+        case 6: LAUNCH_BWD(6); break;
+        case 7: LAUNCH_BWD(7); break;
+        default: LAUNCH_BWD(8); break;
     }
-    dim3 grid((unsigned)C, (unsigned)((S + SB - 1) / SB));
-    proto_backward_kernel<SB><<<grid, kProtoThreads, smem, (cudaStream_t)stream>>>(dP, dP_stride_s, dP_scale, P_hat, norm, E, S, C, (int)T, (int)D, dw);
+#undef LAUNCH_BWD
     return check_launch("proto_backward_kernel");
 }
