@@ -44,6 +44,8 @@ def parse():
                     help="GEMMs of the train step: fp32 FFMA | tcgen05 split-bf16 (fp32-grade) | tcgen05 bf16")
     ap.add_argument("--no-fullbatch", action="store_true", help="skip the B = N_train full-batch (tensor-bound) leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other-precision timings of the step")
+    ap.add_argument("--no-graph-collectives", action="store_true",
+                    help="N > 1: launch the step eagerly instead of capturing it (NCCL all-reduces included) in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="also print the per-kernel time table")
     return ap.parse_args()
@@ -193,7 +195,7 @@ def run_ours(args):
     torch.manual_seed(1)
     gpw = GaussianProcessTemplateWeighter(wl["E"].to(dev), _Cfg(shp.kernel, shp.d), lengthscale=ls).to(dev)
     cfg = EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world,
-                       precision=args.precision)
+                       precision=args.precision, graph_collectives=not args.no_graph_collectives)
     eng = GPAdapterEngine(gpw, cfg)
     f_all = wl["f_train"].to(dev)
     y_all = wl["y_train"].to(dev)
@@ -279,9 +281,10 @@ def run_ours(args):
                 train_variants[prec] = {"ms_per_step": ms_total / args.steps, "steps_per_s": args.steps / (ms_total * 1e-3)}
                 continue
             ev = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank,
-                                                   world=world, precision=prec))
+                                                   world=world, precision=prec, graph_collectives=not args.no_graph_collectives))
             msv = time_steps(ev, 10, 3)
             train_variants[prec] = {"ms_per_step": msv / 10, "steps_per_s": 10 / (msv * 1e-3)}
+            ev._graph = None
             del ev
 
     # ---------------- full-batch leg (B = N_train = C * shots): the tensor-bound form of the same step
@@ -291,7 +294,7 @@ def run_ours(args):
         fullbatch = {"B": Bf, "note": "per-sample MC cross-entropy over the whole cached training set; logits [B, S*C] materialised in fp32"}
         for prec in ("bf16", "bf16x3"):
             ef = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=Bf, shots=shp.shots, seed=1234, rank=rank,
-                                                   world=world, precision=prec))
+                                                   world=world, precision=prec, graph_collectives=not args.no_graph_collectives))
             msf = time_steps(ef, 5, 3) / 5
             kt = profile_step_kernels(ef, f_all, y_all, shp, flush, reps=2, B=Bf)
             entry = {"ms_per_step": msf, "steps_per_s": 1e3 / msf, "img_per_s": Bf * 1e3 / msf}
@@ -307,6 +310,7 @@ def run_ours(args):
                                         "per_gemm": {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} for k, v in big}}
                 entry["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in kt.items()}
             fullbatch[prec] = entry
+            ef._graph = None
             del ef
         torch.cuda.empty_cache()
 
@@ -361,9 +365,18 @@ def run_ours(args):
     _, out = metrics.aece_pass(conf_g, cor_g, 10)
     aece, _ = metrics.aece_from_bins(out, n_eval, 10)
 
-    if rank != 0:
+    def shutdown():
+        # captured graphs hold NCCL work: release them before the process group goes away
+        eng._graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(dev)
         if world > 1:
+            torch.distributed.barrier()
             torch.distributed.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return
     pk = peaks()
     steps_per_s = args.steps / (ms_total * 1e-3)
@@ -422,8 +435,7 @@ def run_ours(args):
     if args.profile_kernels:
         for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["ms"]):
             print(f"# {k:28s} {v['ms']*1e3:9.1f} us/step  ({v['calls']} launches)", file=sys.stderr)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    shutdown()
 
 
 def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):

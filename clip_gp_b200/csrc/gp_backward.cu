@@ -134,7 +134,7 @@ __device__ float kernel_adjoint_block(const float* dK, int ld, float* Wm, const 
 // over Z with the 4x4 register tiles of kernel_adjoint_block.  One CTA per (aliased) class.
 __global__ void __launch_bounds__(kThreads) gp_kernel_adjoint_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int c = blockIdx.x, tid = threadIdx.x;
+    const int c = (int)a.c_begin + blockIdx.x, tid = threadIdx.x;
     const int T = (int)a.T, n = (int)a.n, d = (int)a.d;
     const int ldn = n | 1, dp = (d + 3) & ~3;
     const float* ks = a.Ksave + (size_t)c * (1 + n * n + n * T + T * T);
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) gp_kernel_adjoint_kernel(const clipg
 // only_unaliased != 0: classes served by the warp path (alias flag set) are skipped.
 __global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b, const int only_unaliased) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int c = blockIdx.x, tid = threadIdx.x;
+    const int c = (int)a.c_begin + blockIdx.x, tid = threadIdx.x;
     const int T = (int)a.T, n = (int)a.n, d = (int)a.d, S = (int)a.S;
     if (only_unaliased && a.Ksave[(size_t)c * (1 + n * n + n * T + T * T)] != 0.f) return;
     const Dims D = make_dims(T, n, d);
@@ -433,7 +433,8 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
     CLIPGP_REQUIRE(a->C >= 0 && a->T >= 1 && a->T <= CLIPGP_GP_MAX_T && a->n >= 1 && a->n <= CLIPGP_GP_MAX_T + 1 &&
                        a->d >= 1 && a->S >= 1, "gp_backward: unsupported shape");
     CLIPGP_REQUIRE(a->kernel_type >= 0 && a->kernel_type <= 2, "gp_backward: Unsupported kernel: %d", a->kernel_type);
-    if (a->C == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(a->c_begin >= 0 && a->c_count >= 0 && a->c_begin + a->c_count <= a->C, "gp_backward: class shard outside [0, C)");
+    if (a->C == 0 || gp_grid(a) == 0) return CLIPGP_OK;
     CLIPGP_REQUIRE(a->Z && a->X && a->var_mean && a->chol_var && a->w && a->L && a->A && a->R && a->Ksave,
                    "gp_backward: forward tensors missing (Z, X, var_mean, chol_var, w, L, A, R, Ksave)");
     CLIPGP_REQUIRE(a->eps || a->rng_state, "gp_backward: need eps or rng_state");
@@ -456,7 +457,7 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
     if (warp_path) {
         int rc;
         if (a->x_is_z_prefix != 2) {
-            gp::gp_backward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b, 1);
+            gp::gp_backward_kernel<<<gp_grid(a), gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b, 1);
             rc = check_launch("gp_backward_kernel(unaliased)");
             if (rc != CLIPGP_OK) return rc;
         }
@@ -469,9 +470,9 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
             CLIPGP_CUDA(cudaFuncSetAttribute(gp::gp_kernel_adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
             sm2_set = sm2;
         }
-        gp::gp_kernel_adjoint_kernel<<<(unsigned)a->C, gp::kThreads, sm2, (cudaStream_t)stream>>>(*a, *b);
+        gp::gp_kernel_adjoint_kernel<<<gp_grid(a), gp::kThreads, sm2, (cudaStream_t)stream>>>(*a, *b);
         return check_launch("gp_kernel_adjoint_kernel");
     }
-    gp::gp_backward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b, 0);
+    gp::gp_backward_kernel<<<gp_grid(a), gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b, 0);
     return check_launch("gp_backward_kernel");
 }

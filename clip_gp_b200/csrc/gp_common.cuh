@@ -5,6 +5,10 @@
 #include "common.cuh"
 
 namespace clipgp {
+
+// Classes one launch covers: [c_begin, c_begin + c_count) of the C classes the tensors are laid out for (c_count == 0: all).
+inline unsigned gp_grid(const clipgp_gp_args* a) { return (unsigned)(a->c_count > 0 ? a->c_count : a->C - a->c_begin); }
+
 namespace gp {
 
 constexpr int kThreads = 128;  // threads per class CTA

@@ -15,7 +15,7 @@ namespace gp {
 // (the register-resident warp kernel of gp_warp_forward.cu continues from it); un-aliased classes run the whole path here.
 __global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_args a, const int gram_only) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int c = blockIdx.x, tid = threadIdx.x;
+    const int c = (int)a.c_begin + blockIdx.x, tid = threadIdx.x;
     const int T = (int)a.T, n = (int)a.n, d = (int)a.d, S = (int)a.S;
     const Dims D = make_dims(T, n, d);
     const FwdLayout Y = make_fwd_layout(D);
@@ -276,6 +276,8 @@ static int gp_check_args(const clipgp_gp_args* a, const char* who) {
     CLIPGP_REQUIRE(a->d >= 1 && a->S >= 1, "%s: need d >= 1 and S >= 1", who);
     CLIPGP_REQUIRE(!a->x_is_z_prefix || a->n >= a->T, "%s: x_is_z_prefix needs n >= T", who);
     CLIPGP_REQUIRE(a->kernel_type >= 0 && a->kernel_type <= 2, "%s: Unsupported kernel: %d", who, a->kernel_type);
+    CLIPGP_REQUIRE(a->c_begin >= 0 && a->c_count >= 0 && a->c_begin + a->c_count <= a->C, "%s: class shard [%lld, +%lld) outside [0, %lld)",
+                   who, (long long)a->c_begin, (long long)a->c_count, (long long)a->C);
     if (a->C == 0) return CLIPGP_OK;
     CLIPGP_REQUIRE(a->Z && a->X && a->var_mean && a->chol_var && a->w, "%s: NULL tensor", who);
     if (a->kernel_type != CLIPGP_KERNEL_LINEAR) CLIPGP_REQUIRE(a->raw_lengthscale, "%s: raw_lengthscale is NULL", who);
@@ -306,7 +308,7 @@ static bool use_warp_path(const clipgp_gp_args* a) {
 extern "C" int clipgp_gp_forward(const clipgp_gp_args* a, void* stream) {
     int rc = gp_check_args(a, "gp_forward");
     if (rc != CLIPGP_OK) return rc;
-    if (a->C == 0) return CLIPGP_OK;
+    if (a->C == 0 || gp_grid(a) == 0) return CLIPGP_OK;
     const bool warp_path = use_warp_path(a);
     size_t smem = (size_t)clipgp_gp_smem_bytes(a->T, a->n, a->d, 0);
     CLIPGP_REQUIRE(smem > 0 && smem <= 227 * 1024, "gp_forward: needs %zu bytes of shared memory (> 227 KB); reduce d", smem);
@@ -323,11 +325,11 @@ extern "C" int clipgp_gp_forward(const clipgp_gp_args* a, void* stream) {
             const gp::Dims D = gp::make_dims((int)a->T, (int)a->n, (int)a->d);
             smem = sizeof(float) * (D.f_nn + (size_t)((a->d + 3) & ~3) + (size_t)gp::pad4((int)a->n) * gp::KCP) + 16;
         }
-        gp::gp_forward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 1);
+        gp::gp_forward_kernel<<<gp_grid(a), gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 1);
         rc = check_launch("gp_forward_kernel(gram)");
         if (rc != CLIPGP_OK) return rc;
         return clipgp_gp_forward_warp_launch(a, (cudaStream_t)stream);
     }
-    gp::gp_forward_kernel<<<(unsigned)a->C, gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 0);
+    gp::gp_forward_kernel<<<gp_grid(a), gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 0);
     return check_launch("gp_forward_kernel");
 }

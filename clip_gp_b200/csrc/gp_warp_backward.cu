@@ -31,7 +31,7 @@ struct BwdSmem {
 __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b) {
     extern __shared__ __align__(16) unsigned char smw[];
     BwdSmem& s = *reinterpret_cast<BwdSmem*>(smw);
-    const int lane = lane_id(), wid = warp_id(), tid = threadIdx.x, c = blockIdx.x;
+    const int lane = lane_id(), wid = warp_id(), tid = threadIdx.x, c = (int)a.c_begin + blockIdx.x;
     const int T = (int)a.T, n = T + 1, S = (int)a.S;
     float* ks = a.Ksave + (size_t)c * ksave_stride(n, T);
     if (ks[0] == 0.f) return;                      // un-aliased class: handled by the block kernel (uniform per CTA)
@@ -259,6 +259,6 @@ int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_
                                          cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    gpw::gp_backward_warp_kernel<<<(unsigned)a->C, gpw::NT, sizeof(gpw::BwdSmem), st>>>(*a, *b);
+    gpw::gp_backward_warp_kernel<<<gp_grid(a), gpw::NT, sizeof(gpw::BwdSmem), st>>>(*a, *b);
     return check_launch("gp_backward_warp_kernel");
 }

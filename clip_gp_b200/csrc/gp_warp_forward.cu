@@ -26,7 +26,7 @@ struct FwdSmem {
 __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_args a) {
     extern __shared__ __align__(16) unsigned char smw[];
     FwdSmem& s = *reinterpret_cast<FwdSmem*>(smw);
-    const int lane = lane_id(), wid = warp_id(), tid = threadIdx.x, c = blockIdx.x;
+    const int lane = lane_id(), wid = warp_id(), tid = threadIdx.x, c = (int)a.c_begin + blockIdx.x;
     const int T = (int)a.T, n = T + 1, S = (int)a.S;
     const float* ks = a.Ksave + (size_t)c * ksave_stride(n, T);
     if (ks[0] == 0.f) return;                      // un-aliased class: finished by the block kernel (uniform per CTA)
@@ -180,6 +180,6 @@ int clipgp_gp_forward_warp_launch(const clipgp_gp_args* a, cudaStream_t st) {
                                          cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    gpw::gp_forward_warp_kernel<<<(unsigned)a->C, gpw::NT, sizeof(gpw::FwdSmem), st>>>(*a);
+    gpw::gp_forward_warp_kernel<<<gp_grid(a), gpw::NT, sizeof(gpw::FwdSmem), st>>>(*a);
     return check_launch("gp_forward_warp_kernel");
 }

@@ -43,8 +43,11 @@ class EngineConfig:
     train_visual_proj: bool = True      # FREEZE_VISUAL_PROJ False
     precision: str = "fp32"             # GEMMs of the step: "fp32" (FFMA, exact comparator) | "bf16x3" (tcgen05, split operands,
                                         # fp32-grade products: the reference itself runs TF32, adapter.py:23) | "bf16" (tcgen05)
-    graph_collectives: bool = False     # world > 1: capture the step (NCCL all-reduce included) in the CUDA graph as well.  Off by
-                                        # default: measured 1880 -> 2005 steps/s at 2 GPUs, but process-group teardown hung afterwards
+    graph_collectives: bool = False     # world > 1: capture the step (its NCCL all-reduces included) in the CUDA graph as well
+                                        # (1886 -> 2088 steps/s at 2 GPUs).  The owner must drop the graph (engine._graph = None)
+                                        # before destroying the process group, otherwise NCCL teardown hangs; bench.py does
+    shard_classes: bool = True          # world > 1: the per-class GP kernels run on this rank's class shard only (w and dw cross
+                                        # NVLink as two 1.3 MB all-reduces); the MC samples of the logit path stay sharded as before
     overlap: bool = True                # run the feature branch of the step on a side stream next to the GP branch
     seed: int = 0
     rank: int = 0
@@ -69,6 +72,8 @@ class GPAdapterEngine:
         if cfg.S_train < cfg.world:
             raise ValueError(f"S_train={cfg.S_train} < world={cfg.world}: shard the batch instead")
         self.s_offset, self.S_local = dist.sample_split(cfg.S_train, cfg.rank, cfg.world)
+        self.class_sharded = bool(cfg.shard_classes and cfg.world > 1)
+        self.c_lo, self.c_hi = dist.shard_range(self.C, cfg.rank, cfg.world) if self.class_sharded else (0, self.C)
         self.E = gpw._templates.detach().contiguous()
         self.X = gpw._templates_red.detach().contiguous()
         self.Z = gpw.variational_strategy.inducing_points.detach().clone().contiguous()
@@ -132,7 +137,12 @@ class GPAdapterEngine:
         self.Y = torch.empty(B, D, **f32)
         self.f_hat = torch.empty(B, D, **f32)
         self.f_inv = torch.empty(B, **f32)
-        self.w = torch.empty(S, Cn, T, **f32)
+        # class-sharded GP: w / dw hold ALL S_train samples (this rank fills its classes / its samples, an all-reduce completes them)
+        Sg = self.cfg.S_train if self.class_sharded else S
+        self.w_all = torch.zeros(Sg, Cn, T, **f32)
+        self.dw_all = torch.zeros(Sg, Cn, T, **f32)
+        so = self.s_offset if self.class_sharded else 0
+        self.w = self.w_all[so:so + S]
         self.kl = torch.empty(Cn, **f32)
         self.Lsave = torch.empty(Cn, n, n, dtype=torch.float64, device=dev)
         self.Asave = torch.empty(Cn, n, T, **f32)
@@ -146,13 +156,14 @@ class GPAdapterEngine:
         self.dP = torch.empty((S if self.cfg.loss_mode == "per_sample" else 1), Cn, D, **f32)
         self.df_hat = torch.empty(B, D, **f32)
         self.dY = torch.empty(B, D, **f32)
-        self.dw = torch.empty(S, Cn, T, **f32)
+        self.dw = self.dw_all[so:so + S]
         if self.cfg.precision != "fp32":
             self._alloc_tc()
         a = GpArgs()
         a.kernel_type = KERNEL_IDS[self.kernel_type]
         a.x_is_z_prefix = 2     # the engine never writes the frozen template rows of Z (only z_last is scattered back)
-        a.C, a.T, a.n, a.d, a.S = Cn, T, n, d, S
+        a.C, a.T, a.n, a.d, a.S = Cn, T, n, d, Sg
+        a.c_begin, a.c_count = self.c_lo, self.c_hi - self.c_lo
         a.Z, a.X = self.Z.data_ptr(), self.X.data_ptr()
         a.raw_lengthscale = self._ptr(self.flat_p, "ls") if "ls" in self.offsets else None
         a.raw_outputscale = self._ptr(self.flat_p, "os") if "os" in self.offsets else None
@@ -161,15 +172,17 @@ class GPAdapterEngine:
         a.mean_x = self.mean_x.data_ptr()
         a.eps = None
         a.rng_state = self.rng_state.data_ptr()
-        a.s_offset, a.S_total = self.s_offset, self.cfg.S_train
-        a.w, a.kl, a.L, a.A, a.R, a.status = (self.w.data_ptr(), self.kl.data_ptr(), self.Lsave.data_ptr(),
+        a.s_offset, a.S_total = (0 if self.class_sharded else self.s_offset), self.cfg.S_train
+        a.w, a.kl, a.L, a.A, a.R, a.status = (self.w_all.data_ptr(), self.kl.data_ptr(), self.Lsave.data_ptr(),
                                               self.Asave.data_ptr(), self.Rsave.data_ptr(), self.status.data_ptr())
         a.Ksave = self.Ksave.data_ptr()
         self.gp_args = a
         b = GpBwdArgs()
-        b.dw = self.dw.data_ptr()
+        b.dw = self.dw_all.data_ptr()
         b.dkl = None
-        b.dkl_scalar = float(self.cfg.gp_beta) / self.cfg.world
+        # KL term: every rank holds all classes (pre-divided by the world size) or only its class shard (full weight)
+        self.kl_weight = float(self.cfg.gp_beta) / (1 if self.class_sharded else self.cfg.world)
+        b.dkl_scalar = self.kl_weight
         b.dZ_last = self._ptr(self.flat_g, "z_last")
         b.draw_lengthscale = self._ptr(self.flat_g, "ls") if "ls" in self.offsets else None
         b.draw_outputscale = self._ptr(self.flat_g, "os") if "os" in self.offsets else None
@@ -275,7 +288,11 @@ class GPAdapterEngine:
         lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
         Cn, T, D = self.C, self.T, self.D
         per_sample, S, SC, _ = self._dims()
+        if self.class_sharded:
+            self.w_all.zero_()
         ck(lib.clipgp_gp_forward(C.byref(self.gp_args), st), "gp_forward")
+        if self.class_sharded:
+            torch.distributed.all_reduce(self.w_all)          # every rank wrote its classes (all samples); the sum completes w
         ck(lib.clipgp_proto_forward(self.w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, self.P_hat.data_ptr(),
                                     self.P_norm.data_ptr(), None, None if per_sample else self.P_mean.data_ptr(), None, 0, st), "proto_forward")
         if cfg.precision != "fp32":
@@ -355,10 +372,15 @@ class GPAdapterEngine:
                                    alpha, 0, st), "gemm(dP)")
         # per-sample: dense [S,C,D] gradient; logit-mean: the mean over samples happened on unit rows, every sample receives
         # dP_mean (the 1/S is inside alpha)
+        if self.class_sharded:
+            self.dw_all.zero_()
         ck(lib.clipgp_proto_backward(self.dP.data_ptr(), Cn * D if per_sample else 0, 1.0, self.P_hat.data_ptr(), self.P_norm.data_ptr(),
                                      self.E.data_ptr(), S, Cn, T, D, self.dw.data_ptr(), st), "proto_backward")
+        if self.class_sharded:
+            torch.distributed.all_reduce(self.dw_all)         # every rank wrote its samples (all classes); rows of other ranks are zero
         ck(lib.clipgp_gp_backward(C.byref(self.gp_args), C.byref(self.gp_bwd_args), st), "gp_backward")
-        ck(lib.clipgp_sum_accumulate(self.kl.data_ptr(), Cn, float(cfg.gp_beta) / cfg.world, self.loss.data_ptr(), st), "kl_sum")
+        ck(lib.clipgp_sum_accumulate(self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight, self.loss.data_ptr(), st),
+           "kl_sum")
 
     def _launch_update(self):
         lib, cfg, st = self.lib, self.cfg, _lib.stream_ptr(self.dev)
@@ -420,6 +442,7 @@ class GPAdapterEngine:
         w = torch.empty(S, Cn, T, **f32)
         a = GpArgs.from_buffer_copy(self.gp_args)
         a.S, a.s_offset, a.S_total = S, 0, S
+        a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = None
@@ -489,6 +512,7 @@ class GPAdapterEngine:
         w = torch.empty(S, Cn, T, **f32)
         a = GpArgs.from_buffer_copy(self.gp_args)
         a.S, a.s_offset, a.S_total = S, 0, S
+        a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = None

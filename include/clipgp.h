@@ -100,7 +100,11 @@ typedef struct clipgp_gp_args {
     float* R;                     /* out [C,T,T] saved: lower Cholesky factor of Sigma */
     int32_t* status;              /* out [C]: 0 ok; k>0: Sigma needed k jitter retries; <0: not positive definite */
     float* Ksave;                 /* out [C, 1 + n*n + n*T + T*T] saved kernel blocks: [alias flag | K_ZZ (no jitter) | K_ZX | K_XX];
-                                     K_ZX / K_XX are written only when the alias flag is 0.  Required by clipgp_gp_backward */
+                                     K_ZX / K_XX are written only when the alias flag is 0.  Required by clipgp_gp_backward
+                                     (which uses the K_ZX / K_XX part of aliased classes as scratch) */
+    int64_t c_begin, c_count;     /* class shard: only classes [c_begin, c_begin + c_count) are processed (c_count == 0: through C-1);
+                                     every pointer still addresses the full C-class tensors, so multi-GPU class sharding needs no
+                                     re-layout and the Philox draws do not depend on the shard */
 } clipgp_gp_args;
 
 /* Dynamic shared memory the forward / backward kernel needs for (T, n, d); 0 if unsupported. */

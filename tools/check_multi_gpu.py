@@ -1,0 +1,72 @@
+"""Multi-GPU equivalence check (run under torchrun, one rank per GPU): the sharded training step (classes sharded for the GP
+kernels, MC samples sharded for the logit path, NCCL all-reduces of w / dw / gradients) must reproduce the single-GPU step, and
+the sharded evaluation must reproduce the single-GPU counters bit for bit.
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/check_multi_gpu.py [workload] [precision]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as td
+import bench
+from clip_gp_b200 import dist as cdist, metrics, synth
+from clip_gp_b200.engine import EngineConfig, GPAdapterEngine
+from clip_gp_b200.gp_template_weigher import GaussianProcessTemplateWeighter
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+td.init_process_group("nccl", device_id=dev)
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+precision = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
+wl = synth.make_workload(name, n_test=8192); shp = wl["shape"]
+ls = bench.bench_lengthscale(wl["E"], shp.d) if shp.kernel == "rbf" else None
+S = max(shp.S, world)
+
+
+def make(world_, rank_, **kw):
+    torch.manual_seed(1)
+    gpw = GaussianProcessTemplateWeighter(wl["E"].to(dev), bench._Cfg(shp.kernel, shp.d), lengthscale=ls).to(dev)
+    return GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=77, rank=rank_, world=world_,
+                                             precision=precision, **kw))
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+
+
+f, y = wl["f_train"].to(dev), wl["y_train"].to(dev)
+ok = True
+for shard_classes in (True, False):
+    multi, single = make(world, rank, shard_classes=shard_classes), make(1, 0)
+    # one step without the update: gradients and loss
+    multi.skip_update = single.skip_update = True
+    lm = float(multi.train_step(f[:shp.B], y[:shp.B], use_graph=False)); ls_ = float(single.train_step(f[:shp.B], y[:shp.B], use_graph=False))
+    e_g = rel(multi.flat_g[:-1], single.flat_g[:-1])
+    # three optimisation steps: parameters
+    multi.skip_update = single.skip_update = False
+    for it in range(3):
+        lo = it * shp.B
+        multi.train_step(f[lo:lo + shp.B], y[lo:lo + shp.B], use_graph=False); single.train_step(f[lo:lo + shp.B], y[lo:lo + shp.B], use_graph=False)
+    # AdamW's first steps are sign-like (g / (|g| + eps)): gradients that agree to 1e-5 can still move individual near-zero-gradient
+    # parameters by up to one learning-rate step, so compare the bulk, and bound the outliers by the step budget
+    dp = (multi.flat_p - single.flat_p).abs()
+    e_p = float((dp > 1e-5).float().mean())
+    good = abs(lm - ls_) <= 1e-5 * abs(ls_) and e_g < 1e-4 and e_p < 0.01 and float(dp.max()) <= 3 * 0.0101
+    ok &= good
+    if rank == 0:
+        print(f"shard_classes={shard_classes}: loss {lm:.6f} vs {ls_:.6f}, grad rel err {e_g:.2e}, params after 3 steps: {100 * e_p:.3f} % of entries differ by > 1e-5 (max {float(dp.max()):.1e}) -> {'OK' if good else 'MISMATCH'}")
+# evaluation: image shards + counter all-reduce == single GPU, bit for bit
+eng = make(world, rank); ref = make(1, 0)
+ft, yt = wl["f_test"].to(dev), wl["y_test"].to(dev)
+n = ft.shape[0]
+lo, hi = cdist.shard_range(n, rank, world)
+conf, correct, hist = eng.eval_calibration_tc(ft[lo:hi], yt[lo:hi], precision="bf16x3", mc="collapsed")
+hist_g, conf_g, cor_g = cdist.global_calibration(hist, conf, correct, n, world)
+conf1, cor1, hist1 = ref.eval_calibration_tc(ft, yt, precision="bf16x3", mc="collapsed")
+same = torch.equal(hist_g, hist1) and torch.equal(conf_g, conf1) and torch.equal(cor_g, cor1)
+ok &= same
+if rank == 0:
+    print(f"eval: counters / confidences identical to single GPU: {same} (top-1 {int(hist1[3, 0])}/{n})")
+    print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
+torch.cuda.synchronize()
+td.destroy_process_group()
