@@ -157,14 +157,17 @@ def algorithmic_bytes(shp, S, kernel_name):
     C, T, D, d, n, B = shp.C, shp.T, shp.D, shp.d, shp.T + 1, shp.B
     f = 4
     table = {
-        # reads Z [C,n,d], X [C,T,d] (alias check), lengthscale, Lq, m; writes w, L (fp64), A, R, kl
-        "gp_forward": f * (C * n * d + C * T * d + C * d + C * n * n + C * n + S * C * T + C * n * T + C * T * T) + 8 * C * n * n,
-        # reads the saved L/A/R, w, dw, Z and X twice (r^2 pass + adjoint pass), Lq, m; writes all parameter gradients
-        "gp_backward": f * (2 * (C * n * d + C * T * d) + C * d + 2 * C * n * n + 2 * C * n + 2 * S * C * T + C * n * T + C * T * T + 2 * C * d) + 8 * C * n * n,
+        # warp path (test inputs alias the frozen inducing rows, so X is never read).  Gram kernel: reads Z [C,n,d] + lengthscales,
+        # writes the K_ZZ block; algebra kernel: reads K_ZZ, Lq, m, writes w [S,C,T] and the saved L (fp64), A, R, KL
+        "gp_forward": f * (C * n * d + C * d + C * n * n) + f * (2 * C * n * n + C * n + S * C * T + C * n * T + C * T * T + C) + 8 * C * n * n,
+        # algebra kernel: reads R, w, dw, A, Lq, m, L (fp64), writes dLq, dm and the dK block (write, read, write);
+        # kernel-adjoint kernel: reads dK, K_ZZ, Z, lengthscales, writes the length-scale / learnable-row / output-scale gradients
+        "gp_backward": f * (C * T * T + 2 * S * C * T + C * n * T + C * n * n + C * n) + 8 * C * n * n + f * (4 * C * n * n + C * n)
+                       + f * (2 * C * n * n + C * n * d + C * d + 2 * C * d + C),
         # reads E [C,T,D] + w; writes P_hat [S,C,D] + norms
         "proto_forward": f * (C * T * D + S * C * T + S * C * D + S * C),
-        # reads dP, P_hat [S,C,D], E [C,T,D]; writes dw
-        "proto_backward": f * (2 * S * C * D + C * T * D + S * C * T + S * C),
+        # reads dP, P_hat [S,C,D], E [C,T,D] once per sample chunk (ceil(S/8) chunks); writes dw
+        "proto_backward": f * (2 * S * C * D + ((S + 7) // 8) * C * T * D + S * C * T + S * C),
     }
     return table.get(kernel_name)
 
@@ -314,7 +317,11 @@ def run_ours(args):
             del ef
         torch.cuda.empty_cache()
 
-    # ---------------- eval leg: MC-averaged logits + acc/ECE/AECE over this rank's shard of the test features
+    # ---------------- eval leg (on the INITIAL parameters: a fresh engine, so that accuracy / ECE / AECE do not depend on how many
+    # optimisation steps the timing loops above happened to run, and are identical for every GPU count): MC-averaged logits + acc/ECE/AECE over this rank's shard of the test features
+    eng_train = eng
+    eng = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world,
+                                            precision=args.precision))
     n_eval = args.eval_n
     f_te, y_te = wl["f_test"][:n_eval], wl["y_test"][:n_eval]
     from clip_gp_b200 import dist as cdist
@@ -368,6 +375,7 @@ def run_ours(args):
     def shutdown():
         # captured graphs hold NCCL work: release them before the process group goes away
         eng._graph = None
+        eng_train._graph = None
         import gc
         gc.collect()
         torch.cuda.synchronize(dev)
@@ -410,7 +418,10 @@ def run_ours(args):
                    "l2_flush": "256 MB device buffer written between timed steps", "precision": {"fp32": "fp32 (FFMA GEMMs, fp64 K_ZZ Cholesky)",
                                  "bf16x3": "tcgen05 GEMMs on split-bf16 operands (fp32-grade products; the reference's GPU path is TF32), fp32 everywhere else, fp64 K_ZZ Cholesky",
                                  "bf16": "tcgen05 bf16 GEMMs, fp32 everywhere else, fp64 K_ZZ Cholesky"}[args.precision],
-                   "cuda_graph": eng._graph is not None, "two_stream_overlap": bool(eng.cfg.overlap), "loss_last": loss_last},
+                   "cuda_graph": eng_train._graph is not None, "two_stream_overlap": bool(eng_train.cfg.overlap),
+                   "multi_gpu": (f"GP kernels class-sharded ({shp.C} classes / {world} ranks, w and dw all-reduced), logit path sample-sharded, "
+                                 "gradients + loss all-reduced; step captured in a CUDA graph incl. NCCL") if world > 1 else None,
+                   "loss_last": loss_last},
         "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": shp.B * shp.D * 4 + shp.B * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches_per_step) * args.steps,
         "gpu_launches_per_step": int(launches_per_step),
@@ -444,9 +455,9 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
     lib = eng.lib
     names = ["clipgp_gemm_f32", "clipgp_rownorm_forward", "clipgp_gp_forward", "clipgp_proto_forward", "clipgp_softmax_ce",
              "clipgp_rownorm_backward", "clipgp_l2_identity", "clipgp_proto_backward", "clipgp_gp_backward", "clipgp_sum_accumulate",
-             "clipgp_adamw_step", "clipgp_increment", "clipgp_tc_gemm_store", "clipgp_tc_gemm_store_splitk", "clipgp_cast_bf16", "clipgp_cast_bf16_transpose", "clipgp_cast_bf16_dual",
+             "clipgp_adamw_step", "clipgp_adamw_step_lrptr", "clipgp_increment", "clipgp_tc_gemm_store", "clipgp_tc_gemm_store_splitk", "clipgp_cast_bf16", "clipgp_cast_bf16_transpose", "clipgp_cast_bf16_dual",
              "clipgp_softmax_ce_stats", "clipgp_softmax_grad_bf16_dual", "clipgp_increment2"]
-    multi = ("gemm_f32", "adamw_step", "increment", "tc_gemm_store", "tc_gemm_store_splitk", "cast_bf16", "cast_bf16_transpose", "cast_bf16_dual")
+    multi = ("gemm_f32", "adamw_step", "adamw_step_lrptr", "increment", "tc_gemm_store", "tc_gemm_store_splitk", "cast_bf16", "cast_bf16_transpose", "cast_bf16_dual")
     seg = getattr(eng, "tc_seg", 1)
     B = B or shp.B
     records = []

@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) l2_identity_kernel(const float* __restric
 // update to elements with mask != 0 semantics-free (mask multiplies the gradient first, gp_template_weigher.py:76-79).
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                                                    float wd, const int64_t* __restrict__ step_ptr) {
+                                                    float wd, const int64_t* __restrict__ step_ptr, const float* __restrict__ lr_ptr) {
+    if (lr_ptr) lr = *lr_ptr;                       // device-resident learning rate: schedules advance without re-capturing the graph
     const float t = (float)(*step_ptr);
     const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     const float step_size = lr / bc1;
@@ -358,7 +359,19 @@ extern "C" int clipgp_adamw_step(float* p, const float* g, float* m, float* v, i
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step);
+    adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, nullptr);
+    return check_launch("adamw_kernel");
+}
+
+extern "C" int clipgp_adamw_step_lrptr(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1,
+                                       float beta2, float eps, float weight_decay, const int64_t* step, void* stream) {
+    CLIPGP_REQUIRE(n >= 0, "adamw_step_lrptr: n < 0");
+    if (n == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(p && g && m && v && step && lr_dev, "adamw_step_lrptr: NULL pointer");
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, step, lr_dev);
     return check_launch("adamw_kernel");
 }
 

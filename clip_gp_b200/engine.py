@@ -106,6 +106,7 @@ class GPAdapterEngine:
         # ---- device scalars
         self.rng_state = torch.tensor([int(cfg.seed), 0], dtype=torch.int64, device=dev)
         self.adam_step = torch.ones(1, dtype=torch.int64, device=dev)
+        self.lr_dev = torch.tensor([cfg.lr, cfg.gp_lr], dtype=torch.float32, device=dev)   # [visual_proj group, gp_weighter group]
         self._side_stream = torch.cuda.Stream(dev)
         self._alloc_train(cfg.batch_size)
         self._graph = None
@@ -388,16 +389,32 @@ class GPAdapterEngine:
         oW, nW = self.offsets["W"]
         b1, b2 = cfg.betas
         if cfg.train_visual_proj:
-            ck(lib.clipgp_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
-                                     nW, cfg.lr, b1, b2, cfg.adam_eps, cfg.weight_decay, self.adam_step.data_ptr(), st), "adamw(W)")
+            ck(lib.clipgp_adamw_step_lrptr(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                                           nW, self.lr_dev.data_ptr(), b1, b2, cfg.adam_eps, cfg.weight_decay, self.adam_step.data_ptr(), st),
+               "adamw(W)")
         rest = self.n_params - nW
-        ck(lib.clipgp_adamw_step(self.flat_p.data_ptr() + 4 * nW, self.flat_g.data_ptr() + 4 * nW, self.flat_m.data_ptr() + 4 * nW,
-                                 self.flat_v.data_ptr() + 4 * nW, rest, cfg.gp_lr, b1, b2, cfg.adam_eps, cfg.weight_decay,
-                                 self.adam_step.data_ptr(), st), "adamw(gp)")
+        ck(lib.clipgp_adamw_step_lrptr(self.flat_p.data_ptr() + 4 * nW, self.flat_g.data_ptr() + 4 * nW, self.flat_m.data_ptr() + 4 * nW,
+                                       self.flat_v.data_ptr() + 4 * nW, rest, self.lr_dev.data_ptr() + 4, b1, b2, cfg.adam_eps,
+                                       cfg.weight_decay, self.adam_step.data_ptr(), st), "adamw(gp)")
         self.Z[:, self.n - 1, :].copy_(self.p("z_last").view(self.C, self.d))
         ck(lib.clipgp_increment2(self.adam_step.data_ptr(), self.rng_state.data_ptr() + 8, 1, st), "increment2")
 
     # ------------------------------------------------------------------ public API
+    def set_lr(self, lr: Optional[float] = None, gp_lr: Optional[float] = None) -> None:
+        """Learning rates of the two parameter groups (adapter.py:298-309) for the next steps.  They live in device memory, so a
+        scheduler (CosineAnnealingLR stepped per epoch in the reference, adapter.py:1054-1056) needs no graph re-capture."""
+        if lr is not None:
+            self.cfg.lr = float(lr)
+        if gp_lr is not None:
+            self.cfg.gp_lr = float(gp_lr)
+        self.lr_dev.copy_(torch.tensor([self.cfg.lr, self.cfg.gp_lr], dtype=torch.float32), non_blocking=False)
+
+    def cosine_lr(self, epoch: int, max_epoch: int, base_lr: float, base_gp_lr: float, eta_min: float = 0.0) -> None:
+        """torch CosineAnnealingLR(T_max=max_epoch, eta_min) evaluated in closed form at `epoch` (utils/optimization.py:232-238)."""
+        import math
+        f = 0.5 * (1.0 + math.cos(math.pi * epoch / max_epoch))
+        self.set_lr(eta_min + (base_lr - eta_min) * f, eta_min + (base_gp_lr - eta_min) * f)
+
     def train_step(self, features: torch.Tensor, labels: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
         """One optimisation step on a [B,D] feature batch (host or device tensors).  Returns the device scalar loss."""
         if features.shape[0] != self.B:

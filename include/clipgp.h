@@ -190,6 +190,10 @@ int clipgp_l2_identity(const float* W, int64_t D, float coef, float* dW, float* 
  * `step` is a DEVICE int64 (1-based) so captured CUDA graphs advance it with clipgp_increment. */
 int clipgp_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                       float weight_decay, const int64_t* step, void* stream);
+/* Same update with the learning rate read from DEVICE memory (lr_dev[0]): per-epoch / per-step schedules
+ * (utils/optimization.py:218-281, stepped at adapter.py:1054-1056) advance inside a captured CUDA graph. */
+int clipgp_adamw_step_lrptr(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
+                            float eps, float weight_decay, const int64_t* step, void* stream);
 int clipgp_increment(int64_t* counter, int64_t by, void* stream);
 /* out[0] += scale * sum(x[0..n))   (e.g. gp_beta * sum_c KL_c, adapter.py:462-465). */
 int clipgp_sum_accumulate(const float* x, int64_t n, float scale, float* out, void* stream);

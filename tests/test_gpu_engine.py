@@ -172,3 +172,24 @@ def test_tensor_core_eval_modes(precision, mc):
         assert abs(res["top1_count"] - om.top1_count(logits_ref, y)) <= fragile
         assert res["ece"] == pytest.approx(e_ref, abs=0.5)          # percentage points
     assert sum(res["calibration"]["bin_count"]) == len(y)
+
+
+def test_device_resident_learning_rate_follows_the_schedule():
+    """set_lr / cosine_lr change the step size of a CAPTURED graph (the rate lives in device memory): a zero rate freezes the
+    parameters, the cosine rate at epoch e equals torch's CosineAnnealingLR (utils/optimization.py:232-238)."""
+    wl, shp, eng, orc, cfg = build("rbf")
+    f, y = wl["f_train"].cuda(), wl["y_train"].cuda()
+    eng.train_step(f[: shp.B], y[: shp.B], use_graph=True)              # captures the graph with lr = cfg.lr
+    p0 = eng.flat_p.clone()
+    eng.set_lr(0.0, 0.0)
+    eng.train_step(f[: shp.B], y[: shp.B], use_graph=True)
+    assert torch.equal(eng.flat_p, p0)
+    eng.cosine_lr(epoch=25, max_epoch=100, base_lr=0.01, base_gp_lr=1e-3)
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.01)
+    sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=100)
+    for _ in range(25):
+        opt.step(); sch.step()
+    assert float(eng.lr_dev[0]) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-6)
+    assert float(eng.lr_dev[1]) == pytest.approx(0.1 * opt.param_groups[0]["lr"], rel=1e-6)
+    eng.train_step(f[: shp.B], y[: shp.B], use_graph=True)
+    assert not torch.equal(eng.flat_p, p0)
