@@ -51,6 +51,16 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel_base):
+    """DRAM bytes per launch (read + write) of the kernels behind one C-ABI call, from the committed `ncu --set full` capture
+    (profiles/r1_ncu_traffic.json; bench.py itself never runs under a profiler)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel_base, {}).get("dram_bytes")
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -398,7 +408,8 @@ def run_ours(args):
         if ab is not None:
             ach = ab / dur / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": None, "algorithmic_bytes": ab, "avg_launch_us": dur * 1e6, "share_of_step": ktimes[dom]["ms"] / sum(v["ms"] for v in ktimes.values()),
+                    "traffic": ncu_traffic(base), "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, DRAM read + write per launch)",
+                    "algorithmic_bytes": ab, "avg_launch_us": dur * 1e6, "share_of_step": ktimes[dom]["ms"] / sum(v["ms"] for v in ktimes.values()),
                     "peak_source": pk["source"]}
         else:
             C_, D_, B_ = shp.C, shp.D, shp.B

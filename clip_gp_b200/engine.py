@@ -449,6 +449,11 @@ class GPAdapterEngine:
         # the capture did not execute anything; state is still the snapshot
         self._graph = g
 
+    def _eval_ksave(self):
+        if getattr(self, "_ksave_eval", None) is None:
+            self._ksave_eval = torch.empty_like(self.Ksave)
+        return self._ksave_eval.data_ptr()
+
     @torch.no_grad()
     def eval_prototypes(self, S: Optional[int] = None) -> torch.Tensor:
         """(1/S) sum_s p_hat_s [C,D] with the current parameters (collapsed form of adapter.py:243-249)."""
@@ -462,7 +467,7 @@ class GPAdapterEngine:
         a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
-        a.Ksave = None
+        a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path
         Pm = torch.empty(Cn, D, **f32)
         with torch.cuda.device(self.dev):
             _lib.check(lib.clipgp_gp_forward(C.byref(a), st), "gp_forward(eval)")
@@ -532,7 +537,7 @@ class GPAdapterEngine:
         a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
-        a.Ksave = None
+        a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path
         P_hat = torch.empty(S, Cn, D, **f32)
         seg = 3 if split else 1
         Bop = torch.empty(Cn, S * seg * D, dtype=torch.bfloat16, device=self.dev)
