@@ -16,6 +16,7 @@
 // warps 2..5 = epilogue.  Roofline: tensor pipe (bf16) for large M; HBM/latency for M = 128.
 #include <cuda.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,9 +26,13 @@ namespace tc {
 constexpr int BM = 128, BN = 256, BK = 64, UK = 16;
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 192;
+constexpr int THREADS = 192;        // TMA warp + MMA warp + 4 epilogue warps (long-K configuration)
+constexpr int THREADS_WIDE = 320;   // ... + 8 epilogue warps (short-K store configuration: the epilogue is the bottleneck there)
 constexpr int ACC_COLS = BN;       // fp32 accumulator columns per tile
 constexpr int TMEM_COLS = 512;     // two accumulator stages
+constexpr int CST_BYTES = 32 * 32 * 4;             // one 32 x 32 fp32 staging tile of the TMA-store epilogue
+// staging: long-K config = 4 stages + 4 warps x 1 tile (212 KB); short-K config = 3 stages + 8 warps x 2 tiles (212 KB); the
+// 227 KB limit (static barriers / histogram included) rules out 4 stages with more staging
 
 constexpr int EPI_STORE = 0, EPI_ROWSTATS = 1, EPI_TIP = 2;
 
@@ -37,6 +42,8 @@ struct Params {
     int n_per_item;             // consecutive n tiles one work item covers (num_n for ROWSTATS, 1 for STORE)
     int k_splits, kb_per_split; // EPI_STORE only: the K blocks are split over k_splits work items that accumulate atomically
     int mode;
+    int tma_store;              // C is written by TMA from swizzled shared-memory staging tiles (full-line stores)
+    int stages, cbufs;          // operand ring depth (3 or 4) and staging tiles per epilogue warp (1 or 2)
     float alpha;
     float* C; long long ldc;    // STORE target / optional logits copy in ROWSTATS
     const long long* labels; float* conf; int* pred; unsigned char* correct;
@@ -73,6 +80,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -122,8 +134,9 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN 
 __device__ __forceinline__ unsigned long long conf_to_fx(float c) { return (unsigned long long)((double)c * 1099511627776.0); }
 
 // ------------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                             const __grid_constant__ CUtensorMap map_b, const Params p) {
+__global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_b,
+                                                             const __grid_constant__ CUtensorMap map_c, const Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
@@ -135,10 +148,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], (blockDim.x >> 5) - 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
     }
     if (p.mode == EPI_ROWSTATS) {
         for (int i = threadIdx.x; i < CLIPGP_MAX_BINS; i += blockDim.x) { s_cnt[i] = 0; s_cor[i] = 0; s_fx[i] = 0ull; }
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                         mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
                         tma_load_2d(sa, &map_a, &full_bar[stage], (kb * BK) % p.Ka, m_blk * BM);
                         tma_load_2d(sa + A_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                                       (kb > kb0 || k != 0) ? 1u : 0u);
                         umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
                         if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
@@ -209,6 +223,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     } else {
         // ===================================================== epilogue (4 warps; thread <-> TMEM lane <-> row)
         const int q = warp & 3;
+        // eight epilogue warps: warps q and q+4 share the TMEM lane quadrant and split the 256 accumulator columns in halves
+        const int n_epi = (blockDim.x >> 5) - 2;
+        const int c_lo = (n_epi == 8) ? ((warp - 2) >> 2) * (BN / 2) : 0;
+        const int c_hi = (n_epi == 8) ? c_lo + BN / 2 : BN;
+        int cbuf = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             const int mg = item / p.k_splits;
@@ -221,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                 fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
                     const int col0 = n_blk * BN + c0;
                     if (col0 >= p.N) break;                              // warp-uniform
                     uint32_t r[32];
@@ -246,6 +265,26 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                             }
                             atomicAdd(orow + cur, p.tip_alpha * sum);
                         }
+                    } else if (p.C != nullptr && p.tma_store) {
+                        // stage the 32 x 32 chunk in shared memory in the 128-byte-swizzled layout of the output tensor map
+                        // (lane = row; 16-byte chunk index XOR (row & 7): the four 8-lane phases of each vector store hit
+                        // disjoint banks), then one TMA store writes full 128-byte lines; rows / columns past M / N are clipped
+                        unsigned char* stg = smem + p.stages * STAGE_BYTES + ((warp - 2) * p.cbufs + cbuf) * CST_BYTES;
+                        if (lane == 0) {                                  // the previous store from this tile has been read
+                            if (p.cbufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 v = make_float4(p.alpha * __uint_as_float(r[j]), p.alpha * __uint_as_float(r[j + 1]),
+                                                         p.alpha * __uint_as_float(r[j + 2]), p.alpha * __uint_as_float(r[j + 3]));
+                            *reinterpret_cast<float4*>(stg + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4)) = v;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) tma_store_2d(&map_c, stg, col0, m_blk * BM + q * 32);
+                        if (p.cbufs == 2) cbuf ^= 1;
                     } else if (p.C != nullptr && row < p.M) {
                         float* dst = p.C + (long long)row * p.ldc + col0;
                         if (p.k_splits > 1) {
@@ -313,6 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             }
         }
     }
+    if (p.tma_store && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging tiles drained
     fence_before();
     __syncthreads();
     if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
@@ -360,6 +400,21 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     return CLIPGP_OK;
 }
 
+// fp32 row-major [rows, cols] (row pitch ld elements) -> 2D tensor map with a 32 x 32 box, 128B swizzle (one box row = 128 bytes)
+static int make_map_c(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver"); return CLIPGP_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc_gemm: cuTensorMapEncodeTiled(C) failed (CUresult %d)", (int)r); return CLIPGP_ERR_CUDA; }
+    return CLIPGP_OK;
+}
+
 static int launch(const void* A, long long M, long long Ka, const void* B, long long N, long long K, Params& p, cudaStream_t st,
                   bool allow_split_k = false) {
     CLIPGP_REQUIRE(M >= 1 && N >= 1 && K >= 1 && Ka >= 1, "tc_gemm: empty problem");
@@ -391,14 +446,29 @@ static int launch(const void* A, long long M, long long Ka, const void* B, long 
         }
     }
     const int items = p.num_m * (p.num_n / p.n_per_item) * p.k_splits;
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    // TMA-store epilogue for materialised outputs (store mode, or the optional logits copy of the row-statistics mode)
+    CUtensorMap mc = ma;
+    p.tma_store = 0;
+    static const bool no_tma_store = (getenv("CLIPGP_TC_NO_TMA_STORE") != nullptr);
+    if (!no_tma_store && p.C != nullptr && p.mode != EPI_TIP && p.k_splits == 1 && (p.ldc % 4) == 0 &&
+        ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0)) {
+        rc = make_map_c(&mc, p.C, M, N, p.ldc);
+        if (rc != CLIPGP_OK) return rc;
+        p.tma_store = 1;
+    }
+    // short-K materialised outputs are epilogue bound: 3-stage ring, 8 epilogue warps, double-buffered staging tiles
+    const bool wide = p.tma_store && p.mode == EPI_STORE && p.kb_per_split <= 8;      // K <= 512 (measured: K = 1024 prefers 4 stages)
+    p.stages = wide ? 3 : STAGES;
+    p.cbufs = wide ? 2 : 1;
+    const int threads = wide ? THREADS_WIDE : THREADS;
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 4 * CST_BYTES + 1024;      // both configurations need the same 212 KB
     static bool attr_set = false;
     if (!attr_set) {
         CLIPGP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int grid = items < num_sms() ? items : num_sms();
-    tc_gemm_kernel<<<grid, THREADS, smem, st>>>(ma, mb, p);
+    tc_gemm_kernel<<<grid, threads, smem, st>>>(ma, mb, mc, p);
     return check_launch("tc_gemm_kernel");
 }
 
