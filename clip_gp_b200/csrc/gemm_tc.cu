@@ -41,6 +41,8 @@ struct Params {
     int num_m, num_n, num_k;
     int n_per_item;             // consecutive n tiles one work item covers (num_n for ROWSTATS, 1 for STORE)
     int k_splits, kb_per_split; // EPI_STORE only: the K blocks are split over k_splits work items that accumulate atomically
+    int full_items, tail_split, tail_kb;   // work items >= full_items are the tiles of the last, partial wave, each split over
+                                           // tail_split work items (tail_kb K blocks each) so that the wave fills all SMs
     int mode;
     int tma_store;              // C is written by TMA from swizzled shared-memory staging tiles (full-line stores)
     int stages, cbufs;          // operand ring depth (3 or 4) and staging tiles per epilogue warp (1 or 2)
@@ -131,6 +133,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // N >> 3 in [17,23), M >> 4 in [24,29).
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// Work item -> (m block, first n block, K-block range, accumulate-atomically flag).
+struct Item { int m_blk, n_first, kb0, kb1, atomic; };
+__device__ __forceinline__ Item decode_item(const Params& p, int item) {
+    Item it;
+    const int groups = p.num_n / p.n_per_item;
+    if (item < p.full_items) {
+        const int ks = item % p.k_splits, mg = item / p.k_splits;
+        it.m_blk = mg / groups; it.n_first = (mg - it.m_blk * groups) * p.n_per_item;
+        it.kb0 = ks * p.kb_per_split; it.kb1 = min(p.num_k, it.kb0 + p.kb_per_split);
+        it.atomic = p.k_splits > 1;
+    } else {
+        const int r = item - p.full_items;
+        const int tile = p.full_items + r / p.tail_split, ks = r - (r / p.tail_split) * p.tail_split;
+        it.m_blk = tile / groups; it.n_first = (tile - it.m_blk * groups) * p.n_per_item;
+        it.kb0 = ks * p.tail_kb; it.kb1 = min(p.num_k, it.kb0 + p.tail_kb);
+        it.atomic = 1;
+    }
+    return it;
+}
+
 __device__ __forceinline__ unsigned long long conf_to_fx(float c) { return (unsigned long long)((double)c * 1099511627776.0); }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -165,19 +187,17 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
     fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    const int groups = p.num_n / p.n_per_item;              // work items per (m block, k split)
-    const int num_items = p.num_m * groups * p.k_splits;
+    const int num_items = p.full_items + (p.num_m * (p.num_n / p.n_per_item) * p.k_splits - p.full_items) * p.tail_split;
 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                const int ks = item % p.k_splits, mg = item / p.k_splits;
-                const int m_blk = mg / groups, n_first = (mg - m_blk * groups) * p.n_per_item;
-                const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_k, kb0 + p.kb_per_split);
+                const Item it = decode_item(p, item);
+                const int m_blk = it.m_blk, kb0 = it.kb0, kb1 = it.kb1;
                 for (int nn = 0; nn < p.n_per_item; ++nn) {
-                    const int n_blk = n_first + nn;
+                    const int n_blk = it.n_first + nn;
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         unsigned char* sa = smem + stage * STAGE_BYTES;
@@ -196,8 +216,8 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-                const int ks = item % p.k_splits;
-                const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_k, kb0 + p.kb_per_split);
+                const Item it = decode_item(p, item);
+                const int kb0 = it.kb0, kb1 = it.kb1;
                 for (int nn = 0; nn < p.n_per_item; ++nn) {
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     fence_after();
@@ -230,8 +250,8 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
         int cbuf = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            const int mg = item / p.k_splits;
-            const int m_blk = mg / groups, n_first = (mg - m_blk * groups) * p.n_per_item;
+            const Item it = decode_item(p, item);
+            const int m_blk = it.m_blk, n_first = it.n_first;
             const int row = m_blk * BM + q * 32 + lane;
             float run_m = -FLT_MAX, run_s = 0.f; int run_am = 0x7fffffff;
             for (int nn = 0; nn < p.n_per_item; ++nn) {
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                             }
                             atomicAdd(orow + cur, p.tip_alpha * sum);
                         }
-                    } else if (p.C != nullptr && p.tma_store) {
+                    } else if (p.C != nullptr && p.tma_store && !it.atomic) {
                         // stage the 32 x 32 chunk in shared memory in the 128-byte-swizzled layout of the output tensor map
                         // (lane = row; 16-byte chunk index XOR (row & 7): the four 8-lane phases of each vector store hit
                         // disjoint banks), then one TMA store writes full 128-byte lines; rows / columns past M / N are clipped
@@ -287,7 +307,7 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                         if (p.cbufs == 2) cbuf ^= 1;
                     } else if (p.C != nullptr && row < p.M) {
                         float* dst = p.C + (long long)row * p.ldc + col0;
-                        if (p.k_splits > 1) {
+                        if (it.atomic) {
                             if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
                                 for (int j = 0; j < 32; j += 4)        // vector reduction: one L2 atomic per 16 bytes
@@ -445,7 +465,24 @@ static int launch(const void* A, long long M, long long Ka, const void* B, long 
             }
         }
     }
-    const int items = p.num_m * (p.num_n / p.n_per_item) * p.k_splits;
+    p.full_items = p.num_m * (p.num_n / p.n_per_item) * p.k_splits; p.tail_split = 1; p.tail_kb = p.num_k;
+    if (p.mode == EPI_STORE && allow_split_k && p.k_splits == 1) {
+        // tail wave: tiles % SMs work items would occupy a whole extra round of the persistent grid (d P_hat of the full-batch
+        // step: 158 tiles on 148 SMs = 2 rounds).  Split the K range of just those tiles over the idle SMs (stream-K for the tail).
+        const int tiles = p.num_m * p.num_n, sms = num_sms();
+        const int tail = tiles % sms;
+        if (tiles > sms && tail > 0 && tail * 2 <= sms && p.num_k >= 8) {
+            int want = sms / tail;
+            if (want > p.num_k / 2) want = p.num_k / 2;
+            if (want > 1) {
+                p.tail_kb = (p.num_k + want - 1) / want;
+                p.tail_split = (p.num_k + p.tail_kb - 1) / p.tail_kb;
+                p.full_items = tiles - tail;
+                CLIPGP_CUDA(cudaMemset2DAsync(p.C, sizeof(float) * p.ldc, 0, sizeof(float) * N, M, st));
+            }
+        }
+    }
+    const int items = p.full_items + (p.num_m * (p.num_n / p.n_per_item) * p.k_splits - p.full_items) * p.tail_split;
     // TMA-store epilogue for materialised outputs (store mode, or the optional logits copy of the row-statistics mode)
     CUtensorMap mc = ma;
     p.tma_store = 0;

@@ -65,16 +65,20 @@ def softmax_ce_operands(logits: torch.Tensor, labels: torch.Tensor, S: int, grad
     return loss, out, outT
 
 
-def gemm_store(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """C = alpha * A @ B^T for bf16 A [M,Ka], B [N,K] (K % Ka == 0: A wraps along K)."""
+def gemm_store(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None,
+               split_k: bool = False) -> torch.Tensor:
+    """C = alpha * A @ B^T for bf16 A [M,Ka], B [N,K] (K % Ka == 0: A wraps along K).  split_k: the training-step entry that may
+    split K over work items (skinny outputs, tail wave) and accumulate with vector reductions (non-deterministic last bits)."""
     dev = _lib.require_cuda(A, B)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_contiguous() and B.is_contiguous()
     M, Ka = A.shape
     N, K = B.shape
     C = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    fn = lib.clipgp_tc_gemm_store_splitk if split_k else lib.clipgp_tc_gemm_store
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().clipgp_tc_gemm_store(A.data_ptr(), M, Ka, B.data_ptr(), N, K, float(alpha), C.data_ptr(),
-                                                    C.stride(0), _lib.stream_ptr(dev)), "clipgp_tc_gemm_store")
+        _lib.check(fn(A.data_ptr(), M, Ka, B.data_ptr(), N, K, float(alpha), C.data_ptr(), C.stride(0), _lib.stream_ptr(dev)),
+                   "clipgp_tc_gemm_store")
     return C
 
 

@@ -123,3 +123,18 @@ def test_two_phase_softmax_ce_operands(B, S, C, mode):
     tol = (2.0 ** -15 if mode else 2.0 ** -8) * float(gref.abs().max()) + 1e-9
     assert float((_unsplit(out, SC, SCp, mode) - gref).abs().max()) <= tol
     assert float((_unsplit(outT, B, Bp, mode) - gref.t()).abs().max()) <= tol
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 512, 1536), (128, 10000, 512), (10000, 512, 384), (10000, 512, 2048), (128, 512, 30000),
+                                   (512, 512, 384), (19000, 256, 1024), (77, 40, 72)])
+def test_split_k_and_tail_wave_gemm(M, N, K):
+    """The training-step GEMM entry (K split over work items for skinny outputs; tail-wave tiles split over the idle SMs; TMA-store
+    epilogue for the rest) against the deterministic entry: same products, fp32 summation order only."""
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    Ab, Bb = tc.cast_bf16(_rand(M, K, g)), tc.cast_bf16(_rand(N, K, g))
+    ref = 0.25 * (Ab.double() @ Bb.double().t())
+    for _ in range(2):                                   # twice into the same buffer: the entry zeroes what it accumulates into
+        C = tc.gemm_store(Ab, Bb, alpha=0.25, split_k=True, out=torch.full((M, N), 7.0, device="cuda"))
+        assert float((C.double() - ref).abs().max()) < 2e-4 * float(ref.abs().max())
+    C0 = tc.gemm_store(Ab, Bb, alpha=0.25)
+    assert float((C0.double() - ref).abs().max()) < 1e-4 * float(ref.abs().max())
