@@ -290,6 +290,9 @@ class GaussianProcessTemplateWeighter(nn.Module):
         Chunked so C*T = 32 000 points never materialise the 4 GB distance matrix.
         torch.median over an even count returns the LOWER middle element -> k = (m-1)//2 smallest."""
         flat = F.normalize(templates_red.reshape(-1, templates_red.shape[-1]), p=2, dim=-1)
+        if flat.is_cuda:
+            from . import ops
+            return ops.median_pairwise_distance(flat)      # exact radix select, no N x N matrix (csrc/setup.cu)
         parts = []
         for i in range(0, flat.shape[0], chunk):
             pd = torch.cdist(flat[i:i + chunk], flat)

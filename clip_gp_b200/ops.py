@@ -332,3 +332,36 @@ class TipCacheLogits(torch.autograd.Function):
 
 def tip_logits(feats, keys, labels_tr, clip_logits, beta: float, alpha: float, num_classes: int):
     return TipCacheLogits.apply(feats, keys, labels_tr, clip_logits, beta, alpha, num_classes)
+
+
+# ----------------------------------------------------------------------------------------------- GP setup
+@torch.no_grad()
+def median_pairwise_distance(X: torch.Tensor) -> float:
+    """Lower median (torch.median) of the positive pairwise Euclidean distances between the rows of X [N,d]
+    (gp_template_weigher.py:103-107 with X = unit-normalised reduced templates), by an exact three-pass radix select over the
+    distance bit patterns: the N x N matrix (4 GB at the ImageNet shape) is never materialised."""
+    dev = _lib.require_cuda(X)
+    X = X.detach().float().contiguous()
+    N, d = X.shape
+    lib, st = _lib.load(), _lib.stream_ptr(dev)
+    sq = torch.empty(N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.clipgp_row_sqnorm(X.data_ptr(), N, d, sq.data_ptr(), st), "clipgp_row_sqnorm")
+        prefix, prefix_bits, k = 0, 0, None
+        for shift, bits in ((21, 11), (10, 11), (0, 10)):
+            hist = torch.zeros(1 << bits, dtype=torch.int64, device=dev)
+            pos = torch.zeros(1, dtype=torch.int64, device=dev) if k is None else None
+            _lib.check(lib.clipgp_pairdist_radix_hist(X.data_ptr(), sq.data_ptr(), N, d, shift + bits, prefix, 1 if prefix_bits else 0,
+                                                      shift, 1 << bits, hist.data_ptr(), _lib.ptr(pos), st), "clipgp_pairdist_radix_hist")
+            h = hist.cpu()
+            if k is None:
+                m = int(pos.item())
+                if m == 0:
+                    raise RuntimeError("median_pairwise_distance: no positive pairwise distance")
+                k = (m - 1) // 2                           # torch.median returns the lower middle element
+            cum = torch.cumsum(h, 0)
+            b = int(torch.searchsorted(cum, torch.tensor(k, dtype=torch.int64), right=True))
+            k -= int(cum[b - 1]) if b > 0 else 0
+            prefix = (prefix << bits) | b
+            prefix_bits += bits
+    return float(torch.tensor([prefix], dtype=torch.int64).to(torch.int32).view(torch.float32).item())

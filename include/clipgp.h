@@ -271,6 +271,20 @@ int clipgp_tip_backward(float* e, int64_t lda, const int64_t* labels_tr, int64_t
 int clipgp_tc_tip_logits(const void* F_bf16, int64_t M, const void* keys_bf16, int64_t N_tr, int64_t K, const int32_t* key_class,
                          float beta, float alpha, float* out, int64_t ldo, void* stream);
 
+/* ================================================================================================
+ * One-time GP setup — gp_template_weigher.py:103-107 (median-heuristic RBF length-scale):
+ *     pdist = torch.cdist(flat, flat);  ls = pdist[pdist > 0].median()       flat = unit rows [N = C*T, d]
+ * without the N x N matrix: exact radix select over the bit patterns of the distances.  One call = one histogram pass that
+ * recomputes all pairwise distances sqrt(max(|a|^2 + |b|^2 - 2 a.b, 0)), i != j, tile by tile:
+ *   hist[b] += #{ordered pairs with dist > 0, (bits >> prefix_shift) == prefix (if use_prefix), ((bits >> shift) & (nbins-1)) == b}
+ *   positives[0] += #{ordered pairs with dist > 0}   (when positives != NULL)
+ * hist (uint64 [nbins], nbins a power of two <= 4096) and positives are ACCUMULATED into: zero them first.
+ * ================================================================================================ */
+int clipgp_row_sqnorm(const float* X, int64_t N, int64_t d, float* sq, void* stream);
+int clipgp_pairdist_radix_hist(const float* X, const float* sqnorm, int64_t N, int64_t d, int prefix_shift, uint32_t prefix,
+                               int use_prefix, int shift, int nbins, unsigned long long* hist, unsigned long long* positives,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -203,3 +203,35 @@ def test_module_drop_in_surface(kernel):
     with pytest.raises(ValueError):
         cfg.adapter.gp_kernel_type = "periodic"
         GaussianProcessTemplateWeighter(text_embeddings=wl["E"], cfg=cfg)
+
+
+@pytest.mark.parametrize("N,d", [(40, 16), (333, 32), (2048, 64), (3001, 256)])
+def test_median_lengthscale_radix_select(N, d):
+    """gp_template_weigher.py:103-107 without the N x N matrix: the three-pass radix select returns the element of the positive
+    OFF-DIAGONAL pairwise distances whose rank is the lower median.  The reference's `pdist > 0` also keeps those diagonal entries
+    that torch's matmul-form cdist leaves at a rounding-noise value (~3e-4) instead of 0, which moves its rank by at most N/2 of
+    ~N^2 (7e-7 relative at the ImageNet shape, profiles/r1_setup_kernels.txt); the oracle must therefore sit within N ranks."""
+    g = torch.Generator().manual_seed(N + d)
+    X = torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=-1)
+    X[5] = X[3]                                            # an exact duplicate: its zero distance must not be counted
+    got = ops.median_pairwise_distance(X.cuda())
+    D = torch.cdist(X.double(), X.double())
+    off = ~torch.eye(N, dtype=torch.bool)
+    pos = D[off & (D > 1e-7)]
+    k = (pos.numel() - 1) // 2
+    below = int((pos < got - 1e-7).sum()); not_above = int((pos <= got + 1e-7).sum())
+    # `got` is the k-th smallest up to the fp32 evaluation of the distances; the duplicated row may contribute two rounding-noise
+    # "positive" distances at the bottom of the list (the matmul form |a|^2+|b|^2-2ab does not return an exact 0 for it)
+    assert below - 2 <= k < not_above + 2
+    ref = ogp.median_lengthscale(X.view(1, N, d))
+    assert abs(int((pos < ref).sum()) - k) <= N + 2
+
+
+def test_module_uses_the_setup_kernel_for_the_rbf_lengthscale():
+    wl = synth.make_workload("small"); shp = wl["shape"]
+    cfg = _Cfg(); cfg.adapter.gp_kernel_type = "rbf"
+    gpw = GaussianProcessTemplateWeighter(text_embeddings=wl["E"].cuda(), cfg=cfg)
+    st = ogp.build_state(wl["E"], "rbf", 32)
+    ls = float(gpw.covar_module.base_kernel.lengthscale.flatten()[0])
+    ls_ref = float(torch.nn.functional.softplus(st.kernel.raw_lengthscale).flatten()[0])
+    assert ls == pytest.approx(ls_ref, rel=1e-3)           # N = 296 points: the diagonal-noise rank ambiguity is ~1/N
