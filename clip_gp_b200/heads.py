@@ -205,3 +205,60 @@ def gp_pretrain(gp_weighter: GaussianProcessTemplateWeighter, feats_hat: torch.T
                 acc = metrics.compute_accuracy(logits.detach(), labels)[0]
             print(f"[GP] epoch {ep + 1}/{epochs} loss={hist[-1]:.4f} CE={float(ce):.4f} KL={float(kl):.4f} acc={acc:.2f}")
     return hist
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def template_accuracy_scores(text_embeddings: torch.Tensor, features: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """S[k,m] = zero-shot accuracy of template m on the cached features of class k (adapter.py:103-115).
+
+    One tcgen05 GEMM per template ([N,D] x [K,D]^T on split-bf16 operands, fp32-grade products) whose epilogue reduces every logits
+    row to its arg-max and the hit flag `pred == label` (the row-statistics epilogue of the eval path): the [N,K] logits of the
+    M zero-shot passes never reach HBM.  The logit scale is a positive factor and does not move the arg-max."""
+    from . import _lib, tc
+    dev = _lib.require_cuda(text_embeddings)
+    K, M, D = text_embeddings.shape
+    f_hat = ops.row_normalize(features.to(dev).float().contiguous())
+    fb = tc.cast_bf16(f_hat, tc.SPLIT_A)
+    labels_i64 = labels.to(dev, torch.int64).contiguous()
+    counts_k = torch.bincount(labels_i64, minlength=K).to(torch.float32).clamp_min(1)
+    scores = torch.zeros(K, M, dtype=torch.float32, device=dev)
+    for m in range(M):
+        prot = ops.row_normalize(text_embeddings[:, m, :].to(dev).float().contiguous())
+        _, correct, _, _ = tc.logits_calibration(fb, tc.cast_bf16(prot, tc.SPLIT_B), 1.0, labels_i64, want_conf=True)
+        sums_k = torch.zeros(K, dtype=torch.float32, device=dev)
+        sums_k.index_add_(0, labels_i64, correct.to(torch.float32))
+        scores[:, m] = sums_k / counts_k
+    return scores
+
+
+@torch.no_grad()
+def get_template_weights(config: Any, text_embeddings: torch.Tensor, features: Optional[torch.Tensor], labels: Optional[torch.Tensor],
+                         logit_scale=100.0) -> torch.Tensor:
+    """Per-class template weights [K,M], rows sum to 1 — `_get_template_weights`, adapter.py:48-142 (the `prefit_on_full_set`
+    image pipeline is outside the cached-feature path).  Methods (config.adapter.template_init_method): "uniform",
+    "val_weighted", "top3", "minmax"."""
+    adapter_cfg = getattr(config, "adapter", config)
+    method = str(getattr(adapter_cfg, "template_init_method", "uniform")).lower()
+    E = text_embeddings
+    K, M = int(E.shape[0]), int(E.shape[1])
+    if M == 0:
+        return torch.empty(K, 0, device=E.device, dtype=E.dtype)
+    if method == "uniform" or features is None or labels is None:
+        return torch.full((K, M), 1.0 / float(M), device=E.device, dtype=E.dtype)
+    scores = template_accuracy_scores(E, features, labels)
+    if method == "top3":
+        top_k = min(3, M)
+        _, top_idx = torch.topk(scores.mean(dim=0), k=top_k, largest=True)
+        keep = torch.zeros(M, dtype=scores.dtype, device=scores.device)
+        keep[top_idx] = 1.0
+        scores = scores * keep.view(1, -1)
+        zero_rows = scores.sum(dim=1) <= 1e-12
+        if bool(zero_rows.any()):
+            scores[zero_rows] = (keep / float(top_k)).view(1, -1).expand(int(zero_rows.sum().item()), -1)
+    elif method == "minmax":
+        s_min = scores.min(dim=1, keepdim=True).values
+        s_max = scores.max(dim=1, keepdim=True).values
+        rng = s_max - s_min
+        scores = torch.where(rng.le(1e-12), torch.full_like(scores, 1.0 / float(M)), (scores - s_min) / rng.clamp_min(1e-12))
+    return torch.softmax(torch.log(scores.clamp_min(1e-12)), dim=1).to(device=E.device, dtype=E.dtype)

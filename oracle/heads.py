@@ -126,3 +126,43 @@ def tip_search(feats_hat, labels, keys, cache_vals, clip_logits, init_beta, init
             if acc > best_acc:
                 best_acc, best_beta, best_alpha = acc, float(beta), float(alpha)
     return best_beta, best_alpha, best_acc
+
+
+# ---------------------------------------------------------------- template-weight initialisation (trainers/adapter.py)
+@torch.no_grad()
+def template_weights(method, text_embeddings, features, labels, logit_scale, temperature: float = 1.0):
+    """_get_template_weights, adapter.py:48-142 (without the prefit_on_full_set image pipeline): per-class template weights [K,M].
+
+    zero-shot accuracy of every template per class (:107-115) -> optional top3 (:116-129) / minmax (:130-137) transform ->
+    softmax(log(clamp(S, 1e-12)) / temperature) (:138-139).  "uniform" (or missing features) returns 1/M (:99-100)."""
+    E = text_embeddings
+    K, M = int(E.shape[0]), int(E.shape[1])
+    method = str(method).lower()
+    if method == "uniform" or features is None or labels is None:
+        return torch.full((K, M), 1.0 / float(M), dtype=E.dtype)
+    feats = F.normalize(features, p=2, dim=-1)
+    labels = labels.to(torch.int64)
+    counts_k = torch.bincount(labels, minlength=K).to(feats.dtype).clamp_min(1)
+    scores = torch.zeros(K, M, dtype=feats.dtype)
+    for m in range(M):
+        prot_m = F.normalize(E[:, m, :], p=2, dim=-1)
+        preds = (logit_scale * (feats @ prot_m.t())).argmax(dim=1)
+        corr = (preds == labels).to(feats.dtype)
+        sums_k = torch.zeros(K, dtype=feats.dtype)
+        sums_k.index_add_(0, labels, corr)
+        scores[:, m] = sums_k / counts_k
+    if method == "top3":
+        top_k = min(3, M)
+        _, top_idx = torch.topk(scores.mean(dim=0), k=top_k, largest=True)
+        keep = torch.zeros(M, dtype=scores.dtype)
+        keep[top_idx] = 1.0
+        scores = scores * keep.view(1, -1)
+        zero_rows = scores.sum(dim=1) <= 1e-12
+        if bool(zero_rows.any()):
+            scores[zero_rows] = (keep / float(top_k)).view(1, -1).expand(int(zero_rows.sum()), -1)
+    elif method == "minmax":
+        s_min = scores.min(dim=1, keepdim=True).values
+        s_max = scores.max(dim=1, keepdim=True).values
+        rng = s_max - s_min
+        scores = torch.where(rng.le(1e-12), torch.full_like(scores, 1.0 / float(M)), (scores - s_min) / rng.clamp_min(1e-12))
+    return torch.softmax(torch.log(scores.clamp_min(1e-12)) / max(temperature, 1e-6), dim=1), scores

@@ -87,3 +87,26 @@ def test_tip_hyperparameter_search_matches_oracle():
     bb, ba, acc = oh.tip_search(f, y, keys, oh.tip_cache_vals(lab, C), clip, 2.0, 20.0)
     b2, a2, acc2 = heads.tip_search(f.cuda(), y.cuda(), keys.cuda(), lab.cuda(), clip.cuda(), C, 2.0, 20.0)
     assert (b2, a2) == (bb, ba) and acc2 == pytest.approx(acc)
+
+
+@pytest.mark.parametrize("method", ["uniform", "val_weighted", "top3", "minmax"])
+def test_template_weight_initialisation(method):
+    """_get_template_weights (adapter.py:48-142): zero-shot accuracy of every template per class from the tcgen05 GEMM + arg-max
+    epilogue, then the reference's top3 / minmax / log-softmax post-processing, against the line-by-line oracle."""
+    from clip_gp_b200 import heads, synth
+    from oracle import heads as oh
+    wl = synth.make_workload("small"); shp = wl["shape"]
+    cfg = type("Cfg", (), {"adapter": type("A", (), {"template_init_method": method})()})()
+    E, f, y = wl["E"], wl["f_train"], wl["y_train"]
+    ref = oh.template_weights(method, E, f, y, 100.0)
+    w = heads.get_template_weights(cfg, E.cuda(), f.cuda(), y.cuda(), 100.0)
+    assert w.shape == (shp.C, shp.T)
+    assert torch.allclose(w.sum(-1).cpu(), torch.ones(shp.C), atol=1e-5)
+    if method == "uniform":
+        assert torch.equal(w.cpu(), ref)
+        return
+    w_ref, scores_ref = ref
+    scores = heads.template_accuracy_scores(E.cuda(), f.cuda(), y.cuda()).cpu()
+    if method == "val_weighted":
+        assert torch.equal(scores, scores_ref)            # integer hit counts / class counts: bit-exact
+    assert torch.allclose(w.cpu(), w_ref, atol=1e-6)
