@@ -491,9 +491,17 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
             fn = getattr(lib, n)
             return Wrap(fn, n) if n in names else fn
 
-    if eng.cfg.world > 1:
-        return {}
     eng.lib = Proxy()
+    real_allreduce = torch.distributed.all_reduce
+    if eng.cfg.world > 1:
+        def timed_allreduce(t, *a, **kw):                  # NCCL collectives of the step, timed like the kernels
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = real_allreduce(t, *a, **kw)
+            e1.record()
+            records.append((f"nccl_all_reduce[{t.numel() * t.element_size() / 1e6:.1f}MB]", e0, e1, None))
+            return r
+        torch.distributed.all_reduce = timed_allreduce
     out = {}
     overlap_was = eng.cfg.overlap
     eng.cfg.overlap = False          # serialise the two branches of the step so that the per-kernel events do not overlap
@@ -508,7 +516,7 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
             for name, e0, e1, fl in records:
                 short = name.replace("clipgp_", "")
                 k = seen.get(short, 0); seen[short] = k + 1
-                key = f"{short}({k})" if short in multi else short
+                key = f"{short}({k})" if (short in multi or short.startswith("nccl_")) else short
                 d = out.setdefault(key, {"ms": 0.0, "calls": 0})
                 d["ms"] += e0.elapsed_time(e1) / reps
                 d["calls"] = 1
@@ -516,6 +524,7 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
     finally:
         eng.lib = lib
         eng.cfg.overlap = overlap_was
+        torch.distributed.all_reduce = real_allreduce
     return out
 
 
