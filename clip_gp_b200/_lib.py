@@ -34,6 +34,7 @@ class GpArgs(C.Structure):
         ("w", C.c_void_p), ("kl", C.c_void_p), ("L", C.c_void_p), ("A", C.c_void_p), ("R", C.c_void_p),
         ("status", C.c_void_p), ("Ksave", C.c_void_p),
         ("c_begin", c_i64), ("c_count", c_i64),
+        ("eps_save", C.c_void_p),
     ]
 
 

@@ -212,6 +212,73 @@ __device__ __forceinline__ void chol_rev_block(const T* __restrict__ L, const T*
     __syncthreads();
 }
 
+// Adjoint of L = chol(A) in solve form, by the whole CTA (same output convention as chol_rev_block):
+//     P = Phi(L^T dL)  (lower triangle, halved diagonal),   Y = L^-T P L^-1,   dA = (Y + Y^T) / 2.
+// The product is spread over the warps (4-row register tiles); each of the two triangular sweeps runs with lane = column (rows)
+// 0..31 in warp 0 and, for a 33 x 33 factor, column (row) 32 in warp 1.  About half the instructions of the level-2 reverse
+// sweep.  L must be zero above its diagonal; P is an m x m scratch matrix (row stride LD); G holds dL on entry.
+template <typename T>
+__device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ G, T* __restrict__ P, int m) {
+    const int lane = lane_id(), wid = warp_id();
+    __syncthreads();
+    {   // P = Phi(L^T G): P[i][j] = sum_{k >= i} L[k][i] G[k][j], i >= j   (lane = column j)
+        const int lj = lane < m ? lane : m - 1;
+        for (int i0 = 4 * wid; i0 < m; i0 += 4 * NW) {
+            T acc0 = (T)0, acc1 = (T)0, acc2 = (T)0, acc3 = (T)0;
+            for (int k = i0; k < m; ++k) {
+                const T g = (k >= lj) ? G[k * LD + lj] : (T)0;         // dL is lower triangular: nothing above the diagonal
+                const T* l = L + k * LD + i0;
+                acc0 += l[0] * g; acc1 += l[1] * g; acc2 += l[2] * g; acc3 += l[3] * g;
+            }
+            const T accs[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int i = i0 + x;
+                if (i < m && lane < m) P[i * LD + lane] = (lane < i) ? accs[x] : (lane == i ? (T)0.5 * accs[x] : (T)0);
+            }
+        }
+        if (m == 33 && wid == 1) {                                      // column 32: zeros above the diagonal, one entry on it
+            P[lane * LD + 32] = (T)0;
+            if (lane == 0) P[32 * LD + 32] = (T)0.5 * L[32 * LD + 32] * G[32 * LD + 32];
+        }
+    }
+    __syncthreads();
+    // X = L^-T P: back substitution down the rows, lane = column
+    if (wid < 2) {
+        const int col = (wid == 0) ? lane : 32;
+        if (col < m && (wid == 0 || lane == 0)) {
+            for (int i = m - 1; i >= 0; --i) {
+                T s0 = P[i * LD + col], s1 = (T)0;
+                int k = i + 1;
+                for (; k + 1 < m; k += 2) { s0 -= L[k * LD + i] * P[k * LD + col]; s1 -= L[(k + 1) * LD + i] * P[(k + 1) * LD + col]; }
+                if (k < m) s0 -= L[k * LD + i] * P[k * LD + col];
+                P[i * LD + col] = (s0 + s1) * invd[i];
+            }
+        }
+    }
+    __syncthreads();
+    // Y = X L^-1: y_i = (x_i - sum_{k > i} y_k L[k][i]) / L[i][i], i descending, lane = row
+    if (wid < 2) {
+        const int row = (wid == 0) ? lane : 32;
+        if (row < m && (wid == 0 || lane == 0)) {
+            T* xr = P + row * LD;
+            for (int i = m - 1; i >= 0; --i) {
+                T s0 = xr[i], s1 = (T)0;
+                int k = i + 1;
+                for (; k + 1 < m; k += 2) { s0 -= xr[k] * L[k * LD + i]; s1 -= xr[k + 1] * L[(k + 1) * LD + i]; }
+                if (k < m) s0 -= xr[k] * L[k * LD + i];
+                xr[i] = (s0 + s1) * invd[i];
+            }
+        }
+    }
+    __syncthreads();
+    each_block(m, m, [&](int idx, int i, int j) {
+        if (i > j) G[i * LD + j] = P[i * LD + j] + P[j * LD + i];
+        else if (i == j) G[i * LD + i] = P[i * LD + i];
+    });
+    __syncthreads();
+}
+
 // Offsets of the per-class record in Ksave ([alias flag | K_ZZ n*n | K_ZX n*T | K_XX T*T]).  For aliased classes the
 // K_ZX / K_XX part is unused by the forward pass; the adjoint uses it as scratch for d loss / d K_ZZ (n*n <= n*T + T*T for T >= 2).
 __device__ __forceinline__ size_t ksave_stride(int n, int T) { return (size_t)1 + (size_t)n * n + (size_t)n * T + (size_t)T * T; }

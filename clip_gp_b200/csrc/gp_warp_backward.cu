@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
             float e = 0.f;
             if (lane < T) {
                 if (a.eps) e = a.eps[(size_t)c * a.eps_sc + (size_t)lane * a.eps_st + (size_t)sidx * a.eps_ss];
+                else if (a.eps_save) e = a.eps_save[off + lane];           // drawn and stored by the forward kernel
                 else e = philox_normal(seed, step, ((uint64_t)c * T + lane) * (uint64_t)a.S_total + (uint64_t)(a.s_offset + sidx));
             }
             if (cnt == 0) continue;                             // warp-uniform
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
             }
         }
     }
-    chol_rev_block<float>(R, s.vecT, G, T, reinterpret_cast<float*>(&s.slot));
+    chol_adj_block<float>(R, s.vecT, G, reinterpret_cast<float*>(s.RC), T);      // RC is free until P2 stages Lq there
     each_block(T, T, [&](int idx, int i, int j) {               // G <- dSigma, full symmetric
         if (i > j) { const float v = 0.5f * G[i * LD + j]; G[i * LD + j] = v; G[j * LD + i] = v; }
     });
@@ -239,12 +240,12 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
             if (lane == 0) Gd[32 * LD + 32] = -v;
         }
     }
-    chol_rev_block<double>(Ld, s.invd, Gd, n, &s.slot);
-    each_block(n, n, [&](int idx, int i, int j) {
-        float v = (float)gp::sym_from_rev<double>(Gd, LD, i, j);
-        if (j < T) v += (float)s.RA[i * LD + j];
-        dKt[idx] += v;                                          // same thread wrote dKt[idx] (the dSigma block) in P1
+    __syncthreads();
+    each_block(n, n, [&](int idx, int i, int j) {              // dK_ZX leaves RA for the output block: RA becomes the adjoint's scratch
+        if (j < T) dKt[idx] += (float)s.RA[i * LD + j];         // (the same thread wrote dKt[idx], the dSigma block, in P1)
     });
+    chol_adj_block<double>(Ld, s.invd, Gd, s.RA, n);
+    each_block(n, n, [&](int idx, int i, int j) { dKt[idx] += (float)gp::sym_from_rev<double>(Gd, LD, i, j); });
 }
 
 }  // namespace gpw

@@ -148,7 +148,10 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         float e = 0.f;
         if (lane < T) {
             if (a.eps) e = a.eps[(size_t)c * a.eps_sc + (size_t)lane * a.eps_st + (size_t)sidx * a.eps_ss];
-            else e = philox_normal(seed, step, ((uint64_t)c * T + lane) * (uint64_t)a.S_total + (uint64_t)(a.s_offset + sidx));
+            else {
+                e = philox_normal(seed, step, ((uint64_t)c * T + lane) * (uint64_t)a.S_total + (uint64_t)(a.s_offset + sidx));
+                if (a.eps_save) a.eps_save[((size_t)sidx * a.C + c) * T + lane] = e;
+            }
         }
         float f0 = 0.f, f1 = 0.f;
         int k = 0;

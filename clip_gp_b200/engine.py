@@ -165,6 +165,8 @@ class GPAdapterEngine:
         a.x_is_z_prefix = 2     # the engine never writes the frozen template rows of Z (only z_last is scattered back)
         a.C, a.T, a.n, a.d, a.S = Cn, T, n, d, Sg
         a.c_begin, a.c_count = self.c_lo, self.c_hi - self.c_lo
+        self.eps_save = torch.empty(Sg, Cn, T, **f32)       # base noise of the step: drawn once (forward), re-read by the adjoint
+        a.eps_save = self.eps_save.data_ptr()
         a.Z, a.X = self.Z.data_ptr(), self.X.data_ptr()
         a.raw_lengthscale = self._ptr(self.flat_p, "ls") if "ls" in self.offsets else None
         a.raw_outputscale = self._ptr(self.flat_p, "os") if "os" in self.offsets else None
@@ -465,6 +467,7 @@ class GPAdapterEngine:
         a = GpArgs.from_buffer_copy(self.gp_args)
         a.S, a.s_offset, a.S_total = S, 0, S
         a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
+        a.eps_save = None
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path
@@ -535,6 +538,7 @@ class GPAdapterEngine:
         a = GpArgs.from_buffer_copy(self.gp_args)
         a.S, a.s_offset, a.S_total = S, 0, S
         a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
+        a.eps_save = None
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path

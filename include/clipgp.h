@@ -105,6 +105,9 @@ typedef struct clipgp_gp_args {
     int64_t c_begin, c_count;     /* class shard: only classes [c_begin, c_begin + c_count) are processed (c_count == 0: through C-1);
                                      every pointer still addresses the full C-class tensors, so multi-GPU class sharding needs no
                                      re-layout and the Philox draws do not depend on the shard */
+    float* eps_save;              /* optional [S,C,T] (layout of w): with the counter RNG, the warp-path forward kernel stores the base
+                                     noise it drew and the warp-path adjoint reads it back instead of regenerating the Philox
+                                     stream (the general kernels ignore it and regenerate) */
 } clipgp_gp_args;
 
 /* Dynamic shared memory the forward / backward kernel needs for (T, n, d); 0 if unsupported. */
