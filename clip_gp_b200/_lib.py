@@ -71,6 +71,7 @@ _SIGNATURES = {
     "clipgp_gemm_f32": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, c_i64, c_i64,
                                   C.c_float, C.c_int, C.c_void_p]),
     "clipgp_rownorm_forward": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "clipgp_rownorm_cast": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
     "clipgp_rownorm_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p]),
     "clipgp_softmax_ce": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_float,
                                     C.c_void_p, c_i64, C.c_float, C.c_void_p]),

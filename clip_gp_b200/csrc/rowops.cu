@@ -27,6 +27,39 @@ __global__ void __launch_bounds__(256) rownorm_fwd_kernel(const float* __restric
     if (lane == 0 && inv_norm) inv_norm[row] = inv;
 }
 
+// F.normalize fused with the bf16 operand cast of the next GEMM: out[r, g*seg_stride + k] in the layouts of cast_bf16_kernel
+// (mode 0 plain, 1 A-split, 2 B-split).  The fp32 unit rows are written only if y != NULL.  One warp per row, 16-byte reads.
+__global__ void __launch_bounds__(256) rownorm_cast_kernel(const float* __restrict__ x, int64_t R, int D, float* __restrict__ y,
+                                                           float* __restrict__ inv_norm, __nv_bfloat16* __restrict__ out, int64_t out_ld,
+                                                           int64_t seg_stride, int mode) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const int D4 = D >> 2;
+    float q = 0.f;
+    for (int k = lane; k < D4; k += 32) { const float4 v = __ldg(xr + k); q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+    q = warp_sum(q);
+    const float inv = 1.f / fmaxf(sqrtf(q), 1e-12f);
+    for (int k = lane; k < D4; k += 32) {
+        float4 v = __ldg(xr + k);
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        if (y) reinterpret_cast<float4*>(y + row * D)[k] = v;
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        uint2 hi; hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+        __nv_bfloat16* o = out + row * out_ld + 4 * k;
+        *reinterpret_cast<uint2*>(o) = hi;
+        if (mode != 0) {
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+            uint2 lo; lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+            *reinterpret_cast<uint2*>(o + seg_stride) = (mode == 1) ? hi : lo;
+            *reinterpret_cast<uint2*>(o + 2 * seg_stride) = (mode == 1) ? lo : hi;
+        }
+    }
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+}
+
 // dx = (dy - y <y, dy>) * inv_norm
 __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                           const float* __restrict__ inv_norm, int64_t R, int D,
@@ -137,6 +170,29 @@ __global__ void __launch_bounds__(256) sum_accumulate_kernel(const float* __rest
 // mode 1 (A side): out[r, 3K] = [hi | hi | lo];  mode 2 (B side): out[r, 3K] = [hi | lo | hi].
 // out row r, segment g, column k lives at out[r*out_ld + g*seg_stride + k] (seg_stride = K for the layouts above;
 // callers that interleave MC samples along K pass their own strides).
+// Vector form (K, ldx, out_ld, seg_stride multiples of 4; 16-byte aligned x, 8-byte aligned out): one 16-byte read and up to
+// three 8-byte writes per thread and step.
+__global__ void __launch_bounds__(256) cast_bf16_vec4_kernel(const float* __restrict__ x, int64_t R, int K, int64_t ldx,
+                                                             __nv_bfloat16* __restrict__ out, int64_t out_ld, int64_t seg_stride, int mode) {
+    const int K4 = K >> 2;
+    const int64_t total = R * (int64_t)K4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K4; const int k = (int)(i - r * K4) << 2;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ldx + k));
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        uint2 hi; hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+        __nv_bfloat16* o = out + r * out_ld + k;
+        *reinterpret_cast<uint2*>(o) = hi;
+        if (mode != 0) {
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+            uint2 lo; lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+            *reinterpret_cast<uint2*>(o + seg_stride) = (mode == 1) ? hi : lo;
+            *reinterpret_cast<uint2*>(o + 2 * seg_stride) = (mode == 1) ? lo : hi;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, int64_t R, int K, int64_t ldx,
                                                         __nv_bfloat16* __restrict__ out, int64_t out_ld, int64_t seg_stride, int mode) {
     const int64_t total = R * (int64_t)K;
@@ -320,6 +376,21 @@ extern "C" int clipgp_rownorm_forward(const float* x, int64_t R, int64_t D, floa
     return check_launch("rownorm_fwd_kernel");
 }
 
+extern "C" int clipgp_rownorm_cast(const float* x, int64_t R, int64_t D, float* y, float* inv_norm, void* out_bf16, int64_t out_ld,
+                                   int64_t seg_stride, int mode, void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && D >= 4 && (D % 4) == 0 && D < (1ll << 31), "rownorm_cast: D must be a positive multiple of 4");
+    CLIPGP_REQUIRE(mode >= 0 && mode <= 2, "rownorm_cast: mode must be 0, 1 or 2");
+    if (R == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(x && out_bf16, "rownorm_cast: NULL pointer");
+    CLIPGP_REQUIRE(((out_ld | seg_stride) & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7u) == 0 &&
+                       (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15u) == 0),
+                   "rownorm_cast: operands must be 16-byte (fp32) / 8-byte (bf16) aligned with strides that are multiples of 4");
+    const int64_t blocks = (R + 7) / 8;
+    rownorm_cast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)D, y, inv_norm, (__nv_bfloat16*)out_bf16, out_ld,
+                                                                           seg_stride, mode);
+    return check_launch("rownorm_cast_kernel");
+}
+
 extern "C" int clipgp_rownorm_backward(const float* dy, const float* y, const float* inv_norm, int64_t R, int64_t D, float* dx,
                                        void* stream) {
     CLIPGP_REQUIRE(R >= 0 && D >= 1 && D < (1ll << 31), "rownorm_backward: bad shape");
@@ -397,8 +468,14 @@ extern "C" int clipgp_cast_bf16(const float* x, int64_t R, int64_t K, int64_t ld
     CLIPGP_REQUIRE(mode >= 0 && mode <= 2, "cast_bf16: mode must be 0 (plain), 1 (A split) or 2 (B split)");
     if (R == 0) return CLIPGP_OK;
     CLIPGP_REQUIRE(x && out, "cast_bf16: NULL pointer");
-    int64_t blocks = (R * K + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 16;
+    if (((K | ldx | out_ld | seg_stride) & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0) {
+        int64_t blocks = (R * (K / 4) + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        cast_bf16_vec4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)K, ldx, (__nv_bfloat16*)out, out_ld, seg_stride, mode);
+        return check_launch("cast_bf16_vec4_kernel");
+    }
+    int64_t blocks = (R * K + 255) / 256;
     if (blocks > cap) blocks = cap;
     cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)K, ldx, (__nv_bfloat16*)out, out_ld, seg_stride, mode);
     return check_launch("cast_bf16_kernel");

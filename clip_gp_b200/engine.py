@@ -571,8 +571,9 @@ class GPAdapterEngine:
         seg = 3 if split else 1
         fhat_b = torch.empty(N, seg * D, dtype=torch.bfloat16, device=self.dev)
         with torch.cuda.device(self.dev):
-            _lib.check(lib.clipgp_rownorm_forward(Y.data_ptr(), N, D, Y.data_ptr(), None, None, st), "rownorm")      # adapter.py:240
-            _lib.check(lib.clipgp_cast_bf16(Y.data_ptr(), N, D, D, fhat_b.data_ptr(), seg * D, D, 1 if split else 0, st), "cast_bf16(f_hat)")
+            # adapter.py:240 fused with the operand cast: the fp32 unit rows are never written
+            _lib.check(lib.clipgp_rownorm_cast(Y.data_ptr(), N, D, None, None, fhat_b.data_ptr(), seg * D, D, 1 if split else 0, st),
+                       "rownorm_cast")
         conf, correct, hist, logits = tc.logits_calibration(fhat_b, Bop, self.cfg.logit_scale * mc_scale, labels, n_bins,
                                                             want_conf=True, want_logits=want_logits)
         self.last_eval_logits = logits

@@ -175,6 +175,10 @@ int clipgp_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, in
 
 /* F.normalize(x, dim=-1) (adapter.py:240): y = x / max(|x|, 1e-12); inv_norm [R]; optional bf16 copy of y. */
 int clipgp_rownorm_forward(const float* x, int64_t R, int64_t D, float* y, float* inv_norm, void* y_bf16, void* stream);
+/* F.normalize fused with the operand cast of the next tensor-core GEMM: out_bf16[r*out_ld + g*seg_stride + k] in the layouts of
+ * clipgp_cast_bf16 (mode 0 / 1 / 2); y (fp32 unit rows) and inv_norm may be NULL.  D % 4 == 0. */
+int clipgp_rownorm_cast(const float* x, int64_t R, int64_t D, float* y, float* inv_norm, void* out_bf16, int64_t out_ld,
+                        int64_t seg_stride, int mode, void* stream);
 /* dx = (dy - y <y,dy>) * inv_norm. */
 int clipgp_rownorm_backward(const float* dy, const float* y, const float* inv_norm, int64_t R, int64_t D, float* dx,
                             void* stream);

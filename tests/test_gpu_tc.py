@@ -138,3 +138,23 @@ def test_split_k_and_tail_wave_gemm(M, N, K):
         assert float((C.double() - ref).abs().max()) < 2e-4 * float(ref.abs().max())
     C0 = tc.gemm_store(Ab, Bb, alpha=0.25)
     assert float((C0.double() - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("R,D", [(7, 64), (300, 512), (1025, 128)])
+@pytest.mark.parametrize("mode", [tc.PLAIN, tc.SPLIT_A, tc.SPLIT_B])
+def test_fused_rownorm_cast(R, D, mode):
+    """F.normalize fused with the operand cast == row-normalise kernel followed by the cast kernel, bit for bit."""
+    from clip_gp_b200 import _lib, ops
+    g = torch.Generator().manual_seed(R + D + mode)
+    x = _rand(R, D, g, 3.0)
+    ref = tc.cast_bf16(ops.row_normalize(x), mode)
+    seg = 3 if mode else 1
+    out = torch.empty(R, seg * D, dtype=torch.bfloat16, device="cuda")
+    inv = torch.empty(R, dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().clipgp_rownorm_cast(x.data_ptr(), R, D, None, inv.data_ptr(), out.data_ptr(), seg * D, D, mode,
+                                               _lib.stream_ptr(x.device)), "rownorm_cast")
+    # the fused kernel sums the squares four at a time, so the norm (and a few last bits of the unit rows) may differ by an ulp
+    assert float((out.float() - ref.float()).abs().max()) <= 2.0 ** -7 * float(ref.float().abs().max())
+    assert torch.allclose(inv, 1.0 / x.norm(dim=-1), rtol=1e-6)
+    hi = out[:, :D].float()
+    assert float((hi - torch.nn.functional.normalize(x, dim=-1)).abs().max()) <= 2.0 ** -8
