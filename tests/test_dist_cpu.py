@@ -79,6 +79,56 @@ def _worker(rank, world, port, q):
         cd.allreduce_sum_(local)
         full = grads(0, S, 1.0)
         assert float((local - full).abs().max()) < 1e-5 * float(full.abs().max()) + 1e-7
+        # ---------------- hybrid sharding of the engine: classes sharded for the GP, MC samples for the logit path.
+        # Each rank computes w for its classes (all samples), an all-reduce completes w; the CE share of its samples gives dw rows,
+        # a second all-reduce completes dw; the GP adjoint then runs on the rank's classes only; gradients are summed.
+        import copy
+        import dataclasses
+        c_lo, c_hi = cd.shard_range(shp.C, rank, world)
+
+        def class_slice(st):
+            kw = {}
+            for fld in dataclasses.fields(st):
+                v = getattr(st, fld.name)
+                if fld.name == "kernel":
+                    kp = copy.copy(v)
+                    for nm in ("raw_lengthscale", "raw_outputscale", "raw_variance"):
+                        t = getattr(kp, nm)
+                        if t is not None:
+                            setattr(kp, nm, t[c_lo:c_hi].clone().requires_grad_(True))
+                    kw[fld.name] = kp
+                elif torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == shp.C and fld.name not in ("pca_W",):
+                    kw[fld.name] = v[c_lo:c_hi].clone()
+                else:
+                    kw[fld.name] = v
+            return type(st)(**kw)
+
+        st = ogp.build_state(wl["E"], "rbf", shp.d)
+        st.var_mean, st.chol_var = synth.trained_like_q(shp.C, shp.T + 1, 5)
+        sl = class_slice(st)
+        sl.var_mean.requires_grad_(True); sl.chol_var.requires_grad_(True)
+        eps_all = philox.eps_tensor(7, 0, shp.C, shp.T, S)                    # class / sample sharding never changes the draws
+        w_own, _ = ogp.gp_weights(sl, eps_all[c_lo:c_hi])                     # [S, C_local, T], all samples
+        w_full = torch.zeros(S, shp.C, shp.T)
+        w_full[:, c_lo:c_hi] = w_own.detach()
+        cd.allreduce_sum_(w_full)
+        w_leaf = w_full[off:off + cnt].clone().requires_grad_(True)           # this rank's samples, all classes
+        Wp = torch.eye(shp.D, requires_grad=True)
+        protos = torch.einsum("skm,kmd->skd", w_leaf, st.templates)
+        ce = oh.adapter_mc_ce(f, y, Wp, protos, 100.0) * (cnt / S) if cnt > 0 else Wp.sum() * 0.0
+        l2 = (Wp - torch.eye(shp.D)).pow(2).sum() * (0.5 / shp.shots) / world
+        (ce + l2).backward()
+        dw_full = torch.zeros(S, shp.C, shp.T)
+        if cnt > 0:
+            dw_full[off:off + cnt] = w_leaf.grad
+        cd.allreduce_sum_(dw_full)
+        kl_own = ogp.kl_divergence(sl.var_mean, sl.chol_var).sum() * 0.01       # full weight: the class shard owns its KL terms
+        ((w_own * dw_full[:, c_lo:c_hi]).sum() + kl_own).backward()
+        g_m = torch.zeros(shp.C, shp.T + 1); g_m[c_lo:c_hi] = sl.var_mean.grad
+        g_L = torch.zeros(shp.C, shp.T + 1, shp.T + 1); g_L[c_lo:c_hi] = sl.chol_var.grad
+        hybrid = torch.cat([Wp.grad.reshape(-1), g_m.reshape(-1), g_L.reshape(-1)])
+        cd.allreduce_sum_(hybrid)
+        assert float((hybrid - full).abs().max()) < 1e-5 * float(full.abs().max()) + 1e-7
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
