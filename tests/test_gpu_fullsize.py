@@ -1,0 +1,185 @@
+"""GPU: BASELINE.json's configurations at FULL size.  The CPU oracle cannot run them whole in seconds, so each test combines
+(1) size-independent properties of the outputs and (2) exact-path parity with the oracle on a subset that the oracle can afford:
+the GP is independent per class (subset of classes), logits / cache affinities are independent per image (subset of rows)."""
+import copy
+import dataclasses
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from clip_gp_b200 import dist as cd
+from clip_gp_b200 import metrics as gm
+from clip_gp_b200 import ops, synth, tc
+from clip_gp_b200.engine import EngineConfig, GPAdapterEngine
+from clip_gp_b200.gp_template_weigher import GaussianProcessTemplateWeighter
+from oracle import gp as ogp
+from oracle import heads as oh
+from oracle import metrics as om
+from oracle import philox
+from tests.helpers import oracle_grads, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+class _Cfg:
+    def __init__(self, kernel, pca):
+        self.adapter = type("A", (), {"gp_pca_dim": pca, "gp_kernel_type": kernel})()
+
+
+def _class_subset(st, idx):
+    """Oracle GPState restricted to the classes `idx` (the GP never couples classes)."""
+    C = st.templates.shape[0]
+    kw = {}
+    for fld in dataclasses.fields(st):
+        v = getattr(st, fld.name)
+        if fld.name == "kernel":
+            kp = copy.copy(v)
+            for nm in ("raw_lengthscale", "raw_outputscale", "raw_variance"):
+                t = getattr(kp, nm)
+                if t is not None:
+                    setattr(kp, nm, t[idx].clone())
+            kw[fld.name] = kp
+        elif torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == C and fld.name != "pca_W":
+            kw[fld.name] = v[idx].clone()
+        else:
+            kw[fld.name] = v
+    return type(st)(**kw)
+
+
+def _engine(name, kernel, S, precision="bf16x3", lengthscale=None, **kw):
+    wl = synth.make_workload(name, n_test=kw.pop("n_test", None)); shp = wl["shape"]
+    torch.manual_seed(0)
+    # built on the CPU like the oracle (same SVD -> same PCA basis), then moved
+    gpw = GaussianProcessTemplateWeighter(wl["E"], _Cfg(kernel, shp.d), lengthscale=lengthscale).cuda()
+    m, Lq = synth.trained_like_q(shp.C, shp.T + 1, 5)
+    gpw.variational_strategy._maybe_init()
+    q = gpw.variational_strategy._variational_distribution
+    with torch.no_grad():
+        q.variational_mean.copy_(m); q.chol_variational_covar.copy_(Lq)
+    eng = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=11, precision=precision, **kw))
+    # the oracle twin (same PCA, same parameters)
+    st = ogp.build_state(wl["E"], kernel, shp.d, lengthscale=lengthscale)
+    st.inducing_points = gpw.variational_strategy.inducing_points.detach().cpu().clone()
+    st.templates_red = gpw._templates_red.detach().cpu().clone()
+    st.var_mean, st.chol_var = m.clone(), Lq.clone()
+    raw_ls, raw_os, raw_var = gpw._kernel_raw()
+    if raw_ls is not None: st.kernel.raw_lengthscale = raw_ls.detach().cpu().clone()
+    if raw_os is not None: st.kernel.raw_outputscale = raw_os.detach().cpu().clone()
+    if raw_var is not None: st.kernel.raw_variance = raw_var.detach().cpu().clone()
+    return wl, shp, eng, st
+
+
+def test_cfg2_train_step_full_size_subset_parity():
+    """ImageNet shape (C=1000, T=32, D=512, d=256, S=10, B=128): one engine step; the template weights and the GP parameter
+    gradients of a handful of classes against float64 autograd through the oracle, driven by the engine's own dw."""
+    wl, shp, eng, st = _engine("cfg2", "rbf", 10, lengthscale=1.4146)
+    f, y = wl["f_train"][: shp.B].cuda(), wl["y_train"][: shp.B].cuda()
+    eng.skip_update = True
+    loss = eng.train_step(f, y, use_graph=False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and int(eng.status.abs().max()) == 0
+    w = eng.w.cpu()                                                    # [S, C, T]
+    assert float((w.sum(-1) - 1).abs().max()) < 1e-5 and float(w.min()) >= 0.0
+    assert torch.isfinite(eng.flat_g).all()
+    idx = torch.tensor([0, 1, 17, 500, 998, 999])
+    sub = _class_subset(st, idx)
+    eps = philox.eps_tensor(11, 0, shp.C, shp.T, 10)[idx]
+    dw = eng.dw.cpu()[:, idx]
+    dkl = torch.full((len(idx),), eng.cfg.gp_beta)
+    w_ref, _, G, _ = oracle_grads(sub, eps, dw, dkl, torch.float64)
+    n = shp.T + 1
+    assert rel_err(w[:, idx], w_ref) < 1e-3
+    assert rel_err(eng.g("m").view(shp.C, n).cpu()[idx], G["m"]) < 2e-3
+    assert rel_err(eng.g("Lq").view(shp.C, n, n).cpu()[idx], G["chol"]) < 2e-3
+    assert rel_err(eng.g("ls").view(shp.C, -1).cpu()[idx], G["ls"].view(len(idx), -1)) < 2e-3
+    assert rel_err(eng.g("os").cpu()[idx], G["os"]) < 2e-3
+    assert rel_err(eng.g("z_last").view(shp.C, -1).cpu()[idx], G["Z"][:, -1]) < 2e-2
+
+
+def test_cfg3_eval_full_size_properties():
+    """50 000 ImageNet-shaped test features: tensor-core eval (split operands, fused calibration) against the exact fp32 path of
+    the same engine; counters are shard-invariant bit for bit; a row subset of the logits against the oracle."""
+    wl, shp, eng, st = _engine("cfg3", "rbf", 10, lengthscale=1.4146)
+    f, y = wl["f_test"].cuda(), wl["y_test"].cuda()
+    N = f.shape[0]
+    assert N == 50000
+    conf, correct, hist = eng.eval_calibration_tc(f, y, precision="bf16x3", mc="collapsed")
+    cnt = gm.counters_from_hist(hist, N)
+    ece, bins = gm.ece_from_counters(cnt)
+    assert sum(bins["bin_count"]) == N and int(hist[3, 0]) == int(correct.sum())
+    # exact-mode comparator (fp32 FFMA GEMMs, logits materialised): same top-1 up to near-ties, same ECE to 1e-3
+    ref = eng.evaluate(f, y, precision="fp32")
+    logits = eng.eval_logits(f)
+    top2 = logits.topk(2, dim=1).values
+    fragile = int(((top2[:, 0] - top2[:, 1]) < 1e-3).sum())
+    assert abs(ref["top1_count"] - cnt.top1) <= fragile
+    assert ece == pytest.approx(ref["ece"], rel=1e-3, abs=1e-3)
+    # shards: 8 contiguous image shards, integer counters summed == single pass, bit for bit
+    tot = torch.zeros_like(hist)
+    for r in range(8):
+        lo, hi = cd.shard_range(N, r, 8)
+        _, _, h = eng.eval_calibration_tc(f[lo:hi], y[lo:hi], precision="bf16x3", mc="collapsed")
+        tot += h
+    assert torch.equal(tot, hist)
+    # oracle on a row subset: MC-averaged logits (adapter.py:243-249) with the same Philox noise
+    rows = torch.arange(0, N, 997)
+    eps = philox.eps_tensor(11, 0, shp.C, shp.T, 10)
+    protos, _ = ogp.sample_prototypes(st, eps)
+    lg_ref = oh.adapter_logits(wl["f_test"][rows], torch.eye(shp.D), protos, 100.0)
+    assert float((logits[rows.cuda()].cpu() - lg_ref).abs().max()) < 1e-3 * float(lg_ref.abs().max())
+
+
+def test_cfg4_tip_adapter_full_size():
+    """Tip-Adapter-F shape: 16 000 cache keys, D=1024, C=1000, B=128: exact fp32 kernels and the fused tcgen05 form against the
+    oracle's one-hot formulation (tip_adapter.py:250-251) on the whole batch; key gradient on a sample of keys."""
+    g = torch.Generator().manual_seed(4)
+    B, N_tr, C, D = 128, 16000, 1000, 1024
+    mu = torch.randn(C, D, generator=g)
+    lab = torch.arange(C).repeat_interleave(16)
+    keys = F.normalize(mu[lab] + 2.0 * torch.randn(N_tr, D, generator=g), dim=-1)
+    yb = torch.randint(0, C, (B,), generator=g)
+    f = F.normalize(mu[yb] + 2.0 * torch.randn(B, D, generator=g), dim=-1)
+    clip = 100.0 * f @ F.normalize(mu, dim=-1).t()
+    dout = torch.randn(B, C, generator=g)
+    kr = keys.clone().requires_grad_(True)
+    ref = oh.tip_logits(f, kr, oh.tip_cache_vals(lab, C), clip, 2.0, 20.0)
+    ref.backward(dout)
+    kd = keys.cuda().requires_grad_(True)
+    out = ops.tip_logits(f.cuda(), kd, lab.cuda(), clip.cuda(), 2.0, 20.0, C)
+    out.backward(dout.cuda())
+    assert rel_err(out, ref) < 1e-5
+    pick = torch.arange(0, N_tr, 37)
+    assert rel_err(kd.grad.cpu()[pick], kr.grad[pick]) < 1e-4
+    from clip_gp_b200 import _lib
+    o3 = clip.cuda().clone()
+    fa, kb, li = tc.cast_bf16(f.cuda(), tc.SPLIT_A), tc.cast_bf16(keys.cuda(), tc.SPLIT_B), lab.to(torch.int32).cuda().contiguous()
+    _lib.check(_lib.load().clipgp_tc_tip_logits(fa.data_ptr(), B, kb.data_ptr(), N_tr, 3 * D, li.data_ptr(), 2.0, 20.0, o3.data_ptr(), C,
+                                                _lib.stream_ptr(o3.device)), "clipgp_tc_tip_logits")
+    assert rel_err(o3, ref) < 1e-3
+    assert int((o3.argmax(1).cpu() == ref.argmax(1)).sum()) >= B - 1
+
+
+def test_cfg5_matern_T64_S100_full_size():
+    """SUN397 shape (C=397, T=64, n=65, S=100, Matern-1/2): forward of all classes on the general block kernel; properties for all,
+    oracle parity for a few classes; the MC-mean prototypes that initialise TaskRes (taskres.py:281-285) are unit rows."""
+    wl = synth.make_workload("cfg5"); shp = wl["shape"]
+    st = ogp.build_state(wl["E"], "matern", shp.d)
+    st.var_mean, st.chol_var = synth.trained_like_q(shp.C, shp.T + 1, 3)
+    S = 100
+    eps = torch.randn(shp.C, shp.T, S, generator=torch.Generator().manual_seed(5))
+    dev = "cuda"
+    n = shp.T + 1
+    mean_x = ogp.residual_mean(st.f0, st.cls_bias, st.tmp_bias, n + shp.T)[:, n:].contiguous()
+    w, kl, status = ops.gp_weights(st.inducing_points.to(dev), st.templates_red.to(dev), st.kernel.raw_lengthscale.to(dev), None, None,
+                                   st.var_mean.to(dev), st.chol_var.to(dev), mean_x.to(dev), eps.to(dev), "matern", S)
+    assert w.shape == (S, shp.C, shp.T) and int(status.abs().max()) == 0
+    assert float((w.sum(-1) - 1).abs().max()) < 1e-5 and float(w.min()) >= 0.0
+    idx = torch.tensor([0, 7, 200, 396])
+    w_ref, _ = ogp.gp_weights(_class_subset(st, idx), eps[idx])
+    assert rel_err(w[:, idx], w_ref) < 1e-3
+    assert rel_err(kl.cpu()[idx], ogp.kl_divergence(st.var_mean[idx], st.chol_var[idx])) < 1e-5
+    _, _, base = ops.prototypes_reduced(w, st.templates.to(dev), want_mean_raw=True)
+    assert float((base.norm(dim=-1) - 1).abs().max()) < 1e-5
+    P_ref = torch.einsum("skm,kmd->skd", w_ref, st.templates[idx]).mean(0)
+    assert rel_err(base[idx.to(dev)], F.normalize(P_ref, dim=-1)) < 1e-3
