@@ -247,17 +247,25 @@ __global__ void __launch_bounds__(256) cast_bf16_t_kernel(const float* __restric
 // the transposed copy outT[k, r] (operand of the adjoint GEMM that contracts over r).  Modes as cast_bf16_kernel
 // (0 plain, 1 A-split [hi|hi|lo], 2 B-split [hi|lo|hi]); either output may be NULL.  32 x 32 tiles through shared memory keep
 // both global writes contiguous.
+// Element transforms of the dual-layout producer.  `col(k)` is evaluated once per thread and column (the column of a thread is
+// fixed while it walks the rows of a tile), `apply(v, r, ctx)` once per element.
 struct IdentityOp {
-    __device__ __forceinline__ float operator()(float v, int64_t, int64_t) const { return v; }
+    struct Ctx {};
+    __device__ __forceinline__ Ctx col(int64_t) const { return Ctx(); }
+    __device__ __forceinline__ float apply(float v, int64_t, const Ctx&) const { return v; }
 };
 // dlogits = grad_scale * (softmax(x) - onehot) from per-row statistics (max, 1/sum); logits viewed as [B, S*C], row (b, s).
 struct SoftmaxGradOp {
     const float2* stats; const int64_t* labels; int S, C; float grad_scale;
-    __device__ __forceinline__ float operator()(float v, int64_t r, int64_t k) const {
-        const int sidx = (int)(k / C), j = (int)(k - (int64_t)sidx * C);
-        const float2 st = stats[r * S + sidx];
+    struct Ctx { int sidx, j; };
+    __device__ __forceinline__ Ctx col(int64_t k) const {
+        Ctx c; c.sidx = (int)(k / C); c.j = (int)(k - (int64_t)c.sidx * C);
+        return c;
+    }
+    __device__ __forceinline__ float apply(float v, int64_t r, const Ctx& c) const {
+        const float2 st = __ldg(stats + r * S + c.sidx);
         const float p = __expf(v - st.x) * st.y;
-        return grad_scale * (p - (j == (int)labels[r] ? 1.f : 0.f));
+        return grad_scale * (p - (c.j == (int)__ldg(labels + r) ? 1.f : 0.f));
     }
 };
 
@@ -292,19 +300,30 @@ __global__ void __launch_bounds__(256) cast_dual_kernel(const float* __restrict_
     const int64_t r0 = (int64_t)blockIdx.y * 64, k0 = (int64_t)blockIdx.x * 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t k = k0 + 2 * tx;
+    const typename Op::Ctx c0 = op.col(k < K ? k : 0), c1 = op.col(k + 1 < K ? k + 1 : 0);
+    // the row loads of the whole tile column are issued before any is transformed (8 x 8 bytes in flight per thread)
+    float2 xin[8];
+    const bool pair = vec && k + 1 < K;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = r0 + ty + 8 * i;
+        xin[i] = make_float2(0.f, 0.f);
+        if (r < R) {
+            if (pair) xin[i] = __ldg(reinterpret_cast<const float2*>(x + r * ldx + k));
+            else { if (k < K) xin[i].x = __ldg(x + r * ldx + k); if (k + 1 < K) xin[i].y = __ldg(x + r * ldx + k + 1); }
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = ty + 8 * i;
         const int64_t r = r0 + rr;
         float v0 = 0.f, v1 = 0.f;
         if (r < R) {
-            if (vec && k + 1 < K) {
-                const float2 xv = *reinterpret_cast<const float2*>(x + r * ldx + k);
-                v0 = op(xv.x, r, k); v1 = op(xv.y, r, k + 1);
-                if (out) store_split2(out + r * out_ld + k, seg_stride, mode, v0, v1);
-            } else {
-                if (k < K) { v0 = op(x[r * ldx + k], r, k); if (out) store_split(out + r * out_ld + k, seg_stride, mode, v0); }
-                if (k + 1 < K) { v1 = op(x[r * ldx + k + 1], r, k + 1); if (out) store_split(out + r * out_ld + k + 1, seg_stride, mode, v1); }
+            if (k < K) v0 = op.apply(xin[i].x, r, c0);
+            if (k + 1 < K) v1 = op.apply(xin[i].y, r, c1);
+            if (out) {
+                if (pair) store_split2(out + r * out_ld + k, seg_stride, mode, v0, v1);
+                else { if (k < K) store_split(out + r * out_ld + k, seg_stride, mode, v0); if (k + 1 < K) store_split(out + r * out_ld + k + 1, seg_stride, mode, v1); }
             }
         }
         tile[rr][2 * tx] = v0; tile[rr][2 * tx + 1] = v1;
@@ -339,11 +358,27 @@ __global__ void __launch_bounds__(256) softmax_stats_kernel(const float* __restr
     float my_loss = 0.f;
     if (row < R) {
         const float* x = logits + row * ld;
-        float m = -FLT_MAX;
-        for (int j = lane; j < C; j += 32) m = fmaxf(m, x[j]);
-        m = warp_max(m);
-        float sum = 0.f;
-        for (int j = lane; j < C; j += 32) sum += expf(x[j] - m);
+        float m = -FLT_MAX, sum = 0.f;
+        if (C <= 1024 && (C & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15u) == 0) {
+            // the row (<= 1024 classes) is read ONCE, 16 bytes per load, and stays in registers for both reductions
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            const int C4 = C >> 2;
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = lane + 32 * u;
+                v[u] = (j < C4) ? __ldg(x4 + j) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+            }
+            m = warp_max(m);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (lane + 32 * u < C4) sum += expf(v[u].x - m) + expf(v[u].y - m) + expf(v[u].z - m) + expf(v[u].w - m);
+        } else {
+            for (int j = lane; j < C; j += 32) m = fmaxf(m, x[j]);
+            m = warp_max(m);
+            for (int j = lane; j < C; j += 32) sum += expf(x[j] - m);
+        }
         sum = warp_sum(sum);
         my_loss = m + logf(sum) - x[(int)labels[row / rows_per_label]];
         if (lane == 0) stats[row] = make_float2(m, 1.f / sum);
