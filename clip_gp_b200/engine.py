@@ -300,7 +300,8 @@ class GPAdapterEngine:
                                     self.P_norm.data_ptr(), None, None if per_sample else self.P_mean.data_ptr(), None, 0, st), "proto_forward")
         if cfg.precision != "fp32":
             Bmat = self.P_hat if per_sample else self.P_mean
-            self._cast2(Bmat.data_ptr(), SC, D, D, self.Pb, D, self.tc_mb, self.PTb if cfg.train_visual_proj else None, self.SCp, self.tc_mb)
+            # only the row-major operand is on the critical path (logit GEMM); the transposed copy feeds d f_hat on the feature branch
+            self._cast(Bmat.data_ptr(), SC, D, D, self.Pb, D, self.tc_mb)
 
     def _logits_and_loss(self):
         """logits (adapter.py:426) -> cross-entropy + gradient (adapter.py:427-428)"""
@@ -347,6 +348,7 @@ class GPAdapterEngine:
         tcm = cfg.precision != "fp32"
         if tcm:
             # dlogits [B, SC] and P_hat^T [D, SC] (K = samples x classes; split over K inside the GEMM)
+            self._cast2(Bmat.data_ptr(), SC, D, D, None, 0, 0, self.PTb, self.SCp, self.tc_mb)
             self._tc(self.dlb, self.PTb, alpha, self.df_hat.data_ptr(), D)
         else:
             ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), SC, 1, Bmat.data_ptr(), D, 1, self.df_hat.data_ptr(), D, B, D, SC,
@@ -361,6 +363,8 @@ class GPAdapterEngine:
                                    1.0, 0, st), "gemm(dW)")
         coef = float(cfg.l2_lambda) / float(cfg.shots) / cfg.world
         ck(lib.clipgp_l2_identity(W, D, coef, self._ptr(self.flat_g, "W"), self.loss.data_ptr(), st), "l2_identity")
+        if cfg.world == 1 and not getattr(self, "skip_update", False):
+            self._adamw_w()                                   # dW is complete here: update W next to the GP adjoint
 
     def _bwd_prototypes(self):
         """dP_hat = scale * dlogits^T f_hat -> prototype + GP adjoints (dkl_scalar = gp_beta: adapter.py:462-465)"""
@@ -385,15 +389,21 @@ class GPAdapterEngine:
         ck(lib.clipgp_sum_accumulate(self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight, self.loss.data_ptr(), st),
            "kl_sum")
 
+    def _adamw_w(self):
+        lib, cfg, st = self.lib, self.cfg, _lib.stream_ptr(self.dev)
+        _, nW = self.offsets["W"]
+        b1, b2 = cfg.betas
+        _lib.check(lib.clipgp_adamw_step_lrptr(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+                                               nW, self.lr_dev.data_ptr(), b1, b2, cfg.adam_eps, cfg.weight_decay, self.adam_step.data_ptr(),
+                                               st), "adamw(W)")
+
     def _launch_update(self):
         lib, cfg, st = self.lib, self.cfg, _lib.stream_ptr(self.dev)
         ck = _lib.check
         oW, nW = self.offsets["W"]
         b1, b2 = cfg.betas
-        if cfg.train_visual_proj:
-            ck(lib.clipgp_adamw_step_lrptr(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
-                                           nW, self.lr_dev.data_ptr(), b1, b2, cfg.adam_eps, cfg.weight_decay, self.adam_step.data_ptr(), st),
-               "adamw(W)")
+        if cfg.train_visual_proj and cfg.world > 1:
+            self._adamw_w()                                   # multi-GPU: after the gradient all-reduce
         rest = self.n_params - nW
         ck(lib.clipgp_adamw_step_lrptr(self.flat_p.data_ptr() + 4 * nW, self.flat_g.data_ptr() + 4 * nW, self.flat_m.data_ptr() + 4 * nW,
                                        self.flat_v.data_ptr() + 4 * nW, rest, self.lr_dev.data_ptr() + 4, b1, b2, cfg.adam_eps,
