@@ -188,32 +188,6 @@ __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ 
     __syncthreads();
 }
 
-// In-place lower Cholesky of the n x n matrix A (row-major, leading dim ld); only the lower triangle is read
-// or written.  invd[j] = 1 / L[j][j].  Returns true (uniformly) when a pivot was not strictly positive.
-template <typename T>
-__device__ bool block_cholesky(T* __restrict__ A, int n, int ld, T* __restrict__ invd) {
-    bool fail = false;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        // every thread derives the pivot itself (broadcast read); column j below the diagonal is scaled on the fly
-        const T ajj = A[j * ld + j];
-        if (!(ajj > (T)0)) fail = true;
-        const T inv = (T)1 / sqrt(ajj);
-        // trailing update with the scaled column: A[i][k] -= (A[i][j] inv) (A[k][j] inv), j < k <= i
-        for (int i = j + 1 + warp; i < n; i += nwarps) {
-            const T lij = A[i * ld + j] * inv;
-            for (int k = j + 1 + lane; k <= i; k += 32) A[i * ld + k] -= lij * (A[k * ld + j] * inv);
-        }
-        __syncthreads();
-        // column j is final now; later columns never touch it again, so no second barrier is needed here
-        for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) A[i * ld + j] *= inv;
-        if (threadIdx.x == 0) { A[j * ld + j] = ajj * inv; invd[j] = inv; }
-    }
-    __syncthreads();
-    return fail;
-}
-
 // Left-looking lower Cholesky executed by ONE warp (call from a single warp; lanes own rows lane, lane+32, lane+64),
 // in place on the lower triangle, __syncwarp only.  invd[j] = 1 / L[j][j].  Returns true (warp-uniformly) when a
 // pivot was not strictly positive.  n <= 96.
@@ -311,47 +285,6 @@ __device__ void trsm_lowerT_left(const T* __restrict__ L, int ldl, const T* __re
             for (int k = i + 1; k < n; ++k) s -= L[k * ldl + i] * B[k * ldb + c];
             B[i * ldb + c] = s * invd[i];
         }
-    }
-    __syncthreads();
-}
-
-// Solve Y L = X in place (X is [nrow][n]); one thread per row:  y_i = (x_i - sum_{k>i} y_k L[k][i]) / L[i][i].
-template <typename T>
-__device__ void trsm_lower_right(const T* __restrict__ L, int ldl, const T* __restrict__ invd, T* __restrict__ X,
-                                 int ldx, int n, int nrow) {
-    for (int r = threadIdx.x; r < nrow; r += blockDim.x) {
-        for (int i = n - 1; i >= 0; --i) {
-            T s = X[r * ldx + i];
-            for (int k = i + 1; k < n; ++k) s -= X[r * ldx + k] * L[k * ldl + i];
-            X[r * ldx + i] = s * invd[i];
-        }
-    }
-    __syncthreads();
-}
-
-// Adjoint of L = chol(A).  In: L (lower), invd, dL (lower triangle used).  Out: dA (full symmetric) written to
-// `W` ([n][ld]); `dL` is destroyed only if it aliases W (allowed: W may be the same buffer as dL).
-//   P = Phi(L^T dL);  X = L^-T P;  Y = X L^-1;  dA = (Y + Y^T) / 2.
-template <typename T>
-__device__ void cholesky_adjoint(const T* __restrict__ L, int ldl, const T* __restrict__ invd, const T* dL, T* W,
-                                 int ld, int n, T* __restrict__ scratch /* [n][ld] */) {
-    __syncthreads();
-    // scratch = Phi(L^T dL)  (lower, halved diagonal, zero upper)
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-        const int i = idx / n, j = idx - i * n;
-        T s = (T)0;
-        if (i >= j) {
-            for (int k = i; k < n; ++k) s += L[k * ldl + i] * dL[k * ld + j];
-            if (i == j) s *= (T)0.5;
-        }
-        scratch[i * ld + j] = s;
-    }
-    __syncthreads();
-    trsm_lowerT_left(L, ldl, invd, scratch, ld, n, n);   // X = L^-T P
-    trsm_lower_right(L, ldl, invd, scratch, ld, n, n);   // Y = X L^-1
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-        const int i = idx / n, j = idx - i * n;
-        W[i * ld + j] = (T)0.5 * (scratch[i * ld + j] + scratch[j * ld + i]);
     }
     __syncthreads();
 }

@@ -7,7 +7,7 @@
 //   * "lane = column" accesses A[k*LD + lane] are contiguous, the other operand of a product is a broadcast read.
 // A CTA is ONE class with NW = 4 warps (31 KB of shared memory, 7 classes resident per SM, so the 1000 classes of the ImageNet
 // shape are one wave on 148 SMs): the matrix products and staging copies are spread over the four warps, the inherently
-// sequential factorisations run in warp 0 (or, for the Cholesky adjoint, with the rank-1 updates split across the warps).
+// sequential factorisations and triangular sweeps run in warp 0 (+ warp 1 for the 33rd row / column).
 #pragma once
 #include "gp_common.cuh"
 
@@ -49,36 +49,6 @@ __device__ __forceinline__ void stage_block(int rows, int cols, LD_ ld, ST_ st) 
         for (int u = 0; u < 4; ++u) {
             const int idx = base + NT * u;
             if (idx < total) { const int i = fast_div(idx, inv); st(idx, i, idx - i * cols, v[u]); }
-        }
-    }
-}
-
-// Lane-strided walk over the elements of a dense row-major [rows, cols] array: f(idx, i, j), idx = i*cols + j.
-template <typename F>
-__device__ __forceinline__ void each(int rows, int cols, F f) {
-    const int total = rows * cols;
-    int i = 0, j = lane_id();
-    while (j >= cols) { j -= cols; ++i; }
-    for (int idx = lane_id(); idx < total; idx += 32) {
-        f(idx, i, j);
-        j += 32;
-        while (j >= cols) { j -= cols; ++i; }
-    }
-}
-
-// Same walk, four elements per lane in flight: `ld(idx)` is evaluated for all four before `st(idx, i, j, v)` consumes any, so
-// the global loads of a staging copy overlap instead of being serialised by their dependent shared-memory stores.
-template <typename V, typename LD_, typename ST_>
-__device__ __forceinline__ void stage(int rows, int cols, LD_ ld, ST_ st) {
-    const int total = rows * cols;
-    for (int base = lane_id(); base < total; base += 128) {
-        V v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int idx = base + 32 * u; if (idx < total) v[u] = ld(idx); }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = base + 32 * u;
-            if (idx < total) { const int i = idx / cols; st(idx, i, idx - i * cols, v[u]); }
         }
     }
 }
@@ -168,55 +138,12 @@ __device__ __forceinline__ float sparsemax_lanes(float f, int T) {
     return valid ? fmaxf(z - tau, 0.f) : 0.f;
 }
 
-// Adjoint of L = chol(A) by the whole CTA: Murray's level-2 reverse sweep (gp::warp_cholesky_rev holds the single-warp form and
-// the output convention: strict lower triangle = SUM of the sensitivities of A_ij and A_ji, diagonal = sensitivity of A_ii).
-// Per column j: warp 0 finishes the pivot terms, then -- concurrently -- warp 0 updates row j (r_bar) while warps 1..3 apply the
-// rank-1 update of the trailing rows (B_bar), each on its third of the columns k < j.  `slot` = one shared T for the pivot adjoint.
-template <typename T>
-__device__ __forceinline__ void chol_rev_block(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ G, int n, T* slot) {
-    const int lane = lane_id(), wid = warp_id();
-    for (int j = n - 1; j >= 0; --j) {
-        __syncthreads();
-        if (wid == 0) {
-            const T inv = invd[j];
-            T part = (T)0;
-            for (int i = j + 1 + lane; i < n; i += 32) part += L[i * LD + j] * G[i * LD + j];
-            part = warp_sum(part);
-            const T db = (G[j * LD + j] - part * inv) * inv;            // (d_bar - c^T c_bar / d) / d
-            __syncwarp();
-            for (int i = j + 1 + lane; i < n; i += 32) G[i * LD + j] *= inv;   // c_bar /= d
-            if (lane == 0) *slot = db;
-        }
-        __syncthreads();
-        const T db = *slot;
-        if (wid == 0) {
-            for (int k = lane; k < j; k += 32) {                        // r_bar -= d_bar r + c_bar^T B
-                T s0 = G[j * LD + k] - db * L[j * LD + k], s1 = (T)0;
-                int i = j + 1;
-                for (; i + 1 < n; i += 2) { s0 -= G[i * LD + j] * L[i * LD + k]; s1 -= G[(i + 1) * LD + j] * L[(i + 1) * LD + k]; }
-                if (i < n) s0 -= G[i * LD + j] * L[i * LD + k];
-                G[j * LD + k] = s0 + s1;
-            }
-            if (lane == 0) G[j * LD + j] = db * (T)0.5;
-        } else {
-            const int per = (j + NW - 2) / (NW - 1);
-            const int k0 = (wid - 1) * per, k1 = min(j, k0 + per);
-            for (int i = j + 1 + lane; i < n; i += 32) {                // B_bar -= c_bar r
-                const T cbi = G[i * LD + j];
-                T* gi = G + i * LD;
-                const T* rj = L + j * LD;
-                for (int k = k0; k < k1; ++k) gi[k] -= cbi * rj[k];
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// Adjoint of L = chol(A) in solve form, by the whole CTA (same output convention as chol_rev_block):
+// Adjoint of L = chol(A) in solve form, by the whole CTA (output convention of gp::warp_cholesky_rev: strict lower triangle = SUM of the
+// sensitivities of A_ij and A_ji, diagonal = sensitivity of A_ii):
 //     P = Phi(L^T dL)  (lower triangle, halved diagonal),   Y = L^-T P L^-1,   dA = (Y + Y^T) / 2.
 // The product is spread over the warps (4-row register tiles); each of the two triangular sweeps runs with lane = column (rows)
-// 0..31 in warp 0 and, for a 33 x 33 factor, column (row) 32 in warp 1.  About half the instructions of the level-2 reverse
-// sweep.  L must be zero above its diagonal; P is an m x m scratch matrix (row stride LD); G holds dL on entry.
+// 0..31 in warp 0 and, for a 33 x 33 factor, column (row) 32 in warp 1.  About half the instructions of Murray's level-2 reverse
+// sweep (gp::warp_cholesky_rev, which the general block kernel still uses).  L must be zero above its diagonal; P is an m x m scratch matrix (row stride LD); G holds dL on entry.
 template <typename T>
 __device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ G, T* __restrict__ P, int m) {
     const int lane = lane_id(), wid = warp_id();

@@ -22,7 +22,6 @@ struct BwdSmem {
     double RB[NN];       // P1: R | dR->dSigma (fp32 halves);  P2: dBm | dSigma;  P3: L (fp64)
     double RC[NN];       // P2: Lq | H (fp32 halves);  P3: dL -> chol adjoint (fp64)
     double invd[34];
-    double slot;         // pivot adjoint of the Cholesky reverse sweeps
     float Af[NN];
     float mvec[36];
     float vecT[32];      // P1: 1 / R_ii;  P2: dmu
