@@ -12,123 +12,6 @@
 namespace clipgp {
 namespace gp {
 
-// One Gram block's contribution to the kernel adjoints, from the kernel values the forward pass saved.
-//   dK   : [nA][ld] float (smem) upstream gradient of K(A rows, B rows)
-//   Wm   : [nA][ld] float (smem) in: K values of the block; out: W = d loss / d raw  (raw = r^2 or <a,b>)
-//   q    : [d] accumulates sum_ij W_ij (u_ik - u_jk)^2 (rbf / matern; u = z / lengthscale), evaluated in expanded form
-//          sum_i r_i u_ik^2 + sum_j c_j u_jk^2 - 2 sum_i u_ik (W U_B)_ik  with 4x4 register tiles for W U_B
-//   dzl  : [d] accumulates the gradient of one designated row (rowA as an A row and/or rowB as a B row; -1 = none)
-//   rs/cs: [>= nA] / [>= nB] scratch for the row / column sums of W
-// Returns this thread's partial of d loss / d amp (outputscale or variance).
-__device__ float kernel_adjoint_block(const float* dK, int ld, float* Wm, const float* gA, int nA, const float* gB,
-                                      int nB, int d, int kt, float amp, const float* invls, float* tileA, float* tileB,
-                                      float* q, float* dzl, int rowA, int rowB, float* rs, float* cs) {
-    float damp = 0.f;
-    const float inv_amp = 1.f / amp;
-    for (int idx = threadIdx.x; idx < nA * nB; idx += blockDim.x) {
-        const int i = idx / nB, j = idx - i * nB;
-        const float kv = Wm[i * ld + j];
-        const float g = dK[i * ld + j];
-        float wv;
-        if (kt == CLIPGP_KERNEL_RBF) {
-            damp += g * kv * inv_amp;              // dK/d os = exp(-r2/2) = K / os
-            wv = -0.5f * g * kv;                   // dK/d r2 = -K/2
-        } else if (kt == CLIPGP_KERNEL_MATERN12) {
-            const float rr = -logf(kv);            // K = exp(-r)
-            wv = (kv < 1.f && rr > 0.f) ? (-0.5f * g * kv / rr) : 0.f;   // r2 <= 1e-30 (K == 1): clamp kills the gradient
-        } else {
-            damp += g * kv * inv_amp;              // dK/d v = <a,b> = K / v
-            wv = g * amp;                          // dK/d dot = v
-        }
-        Wm[i * ld + j] = wv;
-    }
-    __syncthreads();
-    const bool same = (gA == gB);
-    const bool dot = (kt == CLIPGP_KERNEL_LINEAR);
-    if (!dot) {
-        for (int i = threadIdx.x; i < nA; i += blockDim.x) { float t = 0.f; for (int j = 0; j < nB; ++j) t += Wm[i * ld + j]; rs[i] = t; }
-        for (int j = threadIdx.x; j < nB; j += blockDim.x) { float t = 0.f; for (int i = 0; i < nA; ++i) t += Wm[i * ld + j]; cs[j] = t; }
-    }
-    const int pA = pad4(nA), pB = pad4(nB);
-    constexpr int KQ = KC / 4;
-    const int vtiles = (pA >> 2) * KQ;
-    for (int k0 = 0; k0 < d; k0 += KC) {
-        __syncthreads();
-        load_chunk(tileA, gA, nA, pA, d, k0, dot ? nullptr : invls);
-        if (!same) load_chunk(tileB, gB, nB, pB, d, k0, dot ? nullptr : invls);
-        __syncthreads();
-        const float* tB = same ? tileA : tileB;
-        if (!dot) {
-            for (int tile = threadIdx.x; tile < vtiles; tile += blockDim.x) {
-                const int it = tile / KQ, kq = tile - it * KQ;
-                const int i0 = it * 4;
-                float v[4][4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) v[x][y] = 0.f;
-                const float* w0 = Wm + (i0 + 0 < nA ? i0 + 0 : 0) * ld;
-                const float* w1 = Wm + (i0 + 1 < nA ? i0 + 1 : 0) * ld;
-                const float* w2 = Wm + (i0 + 2 < nA ? i0 + 2 : 0) * ld;
-                const float* w3 = Wm + (i0 + 3 < nA ? i0 + 3 : 0) * ld;
-                const float* ub = tB + kq * 4;
-                for (int j = 0; j < nB; ++j) {
-                    const float w[4] = {w0[j], w1[j], w2[j], w3[j]};
-                    const float u[4] = {ub[j * KCP], ub[j * KCP + 1], ub[j * KCP + 2], ub[j * KCP + 3]};
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) v[x][y] = fmaf(w[x], u[y], v[x][y]);
-                }
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int k = k0 + kq * 4 + y;
-                    if (k < d) {
-                        float accq = 0.f;
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            const int i = i0 + x;
-                            if (i < nA) { const float ua = tileA[i * KCP + kq * 4 + y]; accq += ua * (rs[i] * ua - 2.f * v[x][y]); }
-                        }
-                        atomicAdd(&q[k], accq);
-                    }
-                }
-            }
-            if (threadIdx.x < KC && k0 + threadIdx.x < d) {            // column term sum_j c_j u_jk^2
-                const int kk = threadIdx.x;
-                float accq = 0.f;
-                for (int j = 0; j < nB; ++j) { const float uj = tB[j * KCP + kk]; accq = fmaf(cs[j] * uj, uj, accq); }
-                atomicAdd(&q[k0 + kk], accq);
-            }
-        }
-        if ((rowA >= 0 || rowB >= 0) && threadIdx.x >= blockDim.x - KC) {   // the one learnable row: O(nA + nB) per column
-            const int kk = threadIdx.x - (blockDim.x - KC);
-            const int k = k0 + kk;
-            if (k < d) {
-                float dz = 0.f;
-                if (rowA >= 0) {
-                    const float ui = tileA[rowA * KCP + kk];
-                    for (int j = 0; j < nB; ++j) {
-                        const float uj = tB[j * KCP + kk];
-                        dz = fmaf(Wm[rowA * ld + j], dot ? uj : (ui - uj), dz);
-                    }
-                }
-                if (rowB >= 0) {
-                    const float uj = tB[rowB * KCP + kk];
-                    for (int i = 0; i < nA; ++i) {
-                        const float ui = tileA[i * KCP + kk];
-                        dz = fmaf(Wm[i * ld + rowB], dot ? ui : (uj - ui), dz);
-                    }
-                }
-                if (!dot) dz *= 2.f * invls[k];
-                dzl[k] += dz;
-            }
-        }
-    }
-    __syncthreads();
-    return damp;
-}
-
 // Kernel-adjoint stage of the warp path (gp_warp_backward.cu): d loss / d K block (scratch part of the class record in
 // Ksave) -> gradients of the length-scales, the output-scale / variance and the learnable inducing row, by one streamed pass
 // over Z with the 4x4 register tiles of kernel_adjoint_block.  One CTA per (aliased) class.
@@ -426,7 +309,8 @@ __global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_a
 
 using namespace clipgp;
 
-int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, cudaStream_t st);   // gp_warp_backward.cu
+int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, cudaStream_t st, int fuse);   // gp_warp_backward.cu
+extern "C" int clipgp_gp_warp_fused_adjoint_ok(int64_t n, int64_t d);
 
 extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, void* stream) {
     CLIPGP_REQUIRE(a && b, "gp_backward: NULL args");
@@ -461,8 +345,11 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
             rc = check_launch("gp_backward_kernel(unaliased)");
             if (rc != CLIPGP_OK) return rc;
         }
-        rc = clipgp_gp_backward_warp_launch(a, b, (cudaStream_t)stream);
-        if (rc != CLIPGP_OK) return rc;
+        // the kernel adjoint runs inside the same CTA when its buffers fit the algebra kernel's shared memory (d <= ~1000)
+        static const bool no_fuse = (getenv("CLIPGP_GP_NO_FUSED_ADJOINT") != nullptr);
+        const int fuse = (!no_fuse && clipgp_gp_warp_fused_adjoint_ok(a->n, a->d)) ? 1 : 0;
+        rc = clipgp_gp_backward_warp_launch(a, b, (cudaStream_t)stream, fuse);
+        if (rc != CLIPGP_OK || fuse) return rc;
         const int n = (int)a->n, d = (int)a->d, ldn = n | 1, dp = (d + 3) & ~3, np = (n + 3) & ~3;
         const size_t sm2 = sizeof(float) * ((size_t)2 * n * ldn + 3 * dp + 2 * np + (size_t)gp::pad4(n) * gp::KCP) + 16;
         static size_t sm2_set = 48 * 1024;

@@ -27,7 +27,8 @@ struct BwdSmem {
     float vecT[32];      // P1: 1 / R_ii;  P2: dmu
 };
 
-__global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b) {
+__global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b,
+                                                                 const int fuse_kernel_adjoint) {
     extern __shared__ __align__(16) unsigned char smw[];
     BwdSmem& s = *reinterpret_cast<BwdSmem*>(smw);
     const int lane = lane_id(), wid = warp_id(), tid = threadIdx.x, c = (int)a.c_begin + blockIdx.x;
@@ -244,7 +245,52 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         if (j < T) dKt[idx] += (float)s.RA[i * LD + j];         // (the same thread wrote dKt[idx], the dSigma block, in P1)
     });
     chol_adj_block<double>(Ld, s.invd, Gd, s.RA, n);
-    each_block(n, n, [&](int idx, int i, int j) { dKt[idx] += (float)gp::sym_from_rev<double>(Gd, LD, i, j); });
+
+    // =========================== P4: kernel adjoint (same CTA; d < 0 skips it: the stand-alone kernel then runs) ===========================
+    const int d = (int)a.d;
+    if (!fuse_kernel_adjoint) {
+        each_block(n, n, [&](int idx, int i, int j) { dKt[idx] += (float)gp::sym_from_rev<double>(Gd, LD, i, j); });
+        return;
+    }
+    // d loss / d K block and the kernel values into RA (the adjoint's scratch is dead); then RB + RC (L and dL are dead, the two
+    // regions are contiguous) hold the streamed chunk tile and the per-feature accumulators of gp::kernel_adjoint_block
+    // (one Gram-shaped pass over Z with 4x4 register tiles)
+    float* dK = reinterpret_cast<float*>(s.RA);
+    float* Wm = dK + NN;
+    each_block(n, n, [&](int idx, int i, int j) {
+        dK[i * LD + j] = dKt[idx] + (float)gp::sym_from_rev<double>(Gd, LD, i, j);
+        Wm[i * LD + j] = ks[1 + idx];
+    });
+    __syncthreads();
+    const int dp = (d + 3) & ~3;
+    float* invls = reinterpret_cast<float*>(s.RB);            // RB | RC: 2 * NN doubles = 17 KB
+    float* qls = invls + dp;
+    float* dzl = qls + dp;
+    float* rs = dzl + dp;
+    float* cs = rs + 36;
+    float* tileA = cs + 36;
+    const int kt = a.kernel_type;
+    if (kt != CLIPGP_KERNEL_LINEAR)
+        for (int k = tid; k < d; k += NT) invls[k] = 1.f / softplusf(a.raw_lengthscale[(size_t)c * d + k]);
+    float amp = 1.f;
+    if (kt == CLIPGP_KERNEL_RBF) amp = softplusf(a.raw_outputscale[c]);
+    if (kt == CLIPGP_KERNEL_LINEAR) amp = softplusf(a.raw_variance[c]);
+    for (int k = tid; k < d; k += NT) { qls[k] = 0.f; dzl[k] = 0.f; }
+    __syncthreads();
+    const float* Zc = a.Z + (size_t)c * n * d;
+    const float damp = gp::kernel_adjoint_block(dK, LD, Wm, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileA, qls, dzl, n - 1, n - 1, rs, cs);
+    __shared__ float red[32];
+    const float damp_tot = block_sum(damp, red);
+    if (tid == 0) {
+        if (kt == CLIPGP_KERNEL_RBF && b.draw_outputscale) b.draw_outputscale[c] = damp_tot * sigmoidf_(a.raw_outputscale[c]);
+        if (kt == CLIPGP_KERNEL_LINEAR && b.draw_variance) b.draw_variance[c] = damp_tot * sigmoidf_(a.raw_variance[c]);
+    }
+    __syncthreads();
+    for (int k = tid; k < d; k += NT) {
+        if (kt != CLIPGP_KERNEL_LINEAR && b.draw_lengthscale)
+            b.draw_lengthscale[(size_t)c * d + k] = -2.f * qls[k] * invls[k] * sigmoidf_(a.raw_lengthscale[(size_t)c * d + k]);
+        if (b.dZ_last) b.dZ_last[(size_t)c * d + k] = dzl[k];
+    }
 }
 
 }  // namespace gpw
@@ -252,13 +298,20 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
 
 using namespace clipgp;
 
-int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, cudaStream_t st) {
+// Shared memory the fused kernel-adjoint stage needs in RB + RC (floats): inverse length-scales, two per-feature accumulators,
+// row / column sums and one [pad4(n)][KCP] chunk tile.
+extern "C" int clipgp_gp_warp_fused_adjoint_ok(int64_t n, int64_t d) {
+    const size_t need = 3 * (size_t)((d + 3) & ~3) + 72 + (size_t)gp::pad4((int)n) * gp::KCP;
+    return need * sizeof(float) <= 2 * sizeof(double) * gpw::NN ? 1 : 0;
+}
+
+int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, cudaStream_t st, int fuse) {
     static bool attr_set = false;
     if (!attr_set) {
         CLIPGP_CUDA(cudaFuncSetAttribute(gpw::gp_backward_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    gpw::gp_backward_warp_kernel<<<gp_grid(a), gpw::NT, sizeof(gpw::BwdSmem), st>>>(*a, *b);
+    gpw::gp_backward_warp_kernel<<<gp_grid(a), gpw::NT, sizeof(gpw::BwdSmem), st>>>(*a, *b, fuse);
     return check_launch("gp_backward_warp_kernel");
 }
