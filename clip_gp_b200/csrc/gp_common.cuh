@@ -100,11 +100,11 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_n, bool sym, int
     ti = row; tj = row + left;
 }
 
-template <bool DOT>
-__device__ __forceinline__ void gram_chunk(float (&acc)[kMaxTiles][16], const float* __restrict__ tA,
-                                           const float* __restrict__ tB, const int (&tis)[kMaxTiles], const int (&tjs)[kMaxTiles]) {
+template <bool DOT, int MT>
+__device__ __forceinline__ void gram_chunk(float (&acc)[MT][16], const float* __restrict__ tA,
+                                           const float* __restrict__ tB, const int (&tis)[MT], const int (&tjs)[MT]) {
 #pragma unroll
-    for (int t = 0; t < kMaxTiles; ++t) {
+    for (int t = 0; t < MT; ++t) {
         if (tis[t] >= 0) {
             const int ti = tis[t], tj = tjs[t];
             const float* pa = tA + (ti * 4) * KCP;
@@ -135,7 +135,9 @@ __device__ __forceinline__ float kernel_value(int kernel_type, float acc, float 
 // Full Gram block K(A rows, B rows) -> out[i*ldo + j] (type OutT), i < nA, j < nB.
 //   gA/gB: global row-major [nA,d] / [nB,d]; if gB == gA the second tile load is skipped.
 //   raw_out (optional, float [nA][ldr]): the un-transformed accumulator (r^2 or dot), needed by the adjoint.
-template <typename OutT>
+//   MT: 4x4 register tiles per thread (MT * blockDim.x must cover the tiles; MT = 1 keeps the register footprint small when the
+//   block is called from the warp-path algebra kernel, n <= 33 -> 45 symmetric tiles).
+template <typename OutT, int MT = kMaxTiles>
 __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ raw_out, int ldr,
                            const float* __restrict__ gA, int nA, const float* __restrict__ gB, int nB, int d,
                            int kernel_type, float amp, const float* __restrict__ inv_ls, float* tileA, float* tileB) {
@@ -144,11 +146,11 @@ __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ 
     const int pA = pad4(nA), pB = pad4(nB);
     const int tiles_m = pA >> 2, tiles_n = pB >> 2;
     const bool dot = (kernel_type == CLIPGP_KERNEL_LINEAR);
-    float acc[kMaxTiles][16];
-    int tis[kMaxTiles], tjs[kMaxTiles];
+    float acc[MT][16];
+    int tis[MT], tjs[MT];
     const int ntiles = num_tiles(tiles_m, tiles_n, sym);
 #pragma unroll
-    for (int t = 0; t < kMaxTiles; ++t) {
+    for (int t = 0; t < MT; ++t) {
         const int tile = threadIdx.x + t * blockDim.x;
         tis[t] = -1; tjs[t] = 0;
         if (tile < ntiles) tile_coords(tile, tiles_n, sym, tis[t], tjs[t]);
@@ -160,11 +162,11 @@ __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ 
         load_chunk(tileA, gA, nA, pA, d, k0, dot ? nullptr : inv_ls);
         if (!same) load_chunk(tileB, gB, nB, pB, d, k0, dot ? nullptr : inv_ls);
         __syncthreads();
-        if (dot) gram_chunk<true>(acc, tileA, same ? tileA : tileB, tis, tjs);
-        else gram_chunk<false>(acc, tileA, same ? tileA : tileB, tis, tjs);
+        if (dot) gram_chunk<true, MT>(acc, tileA, same ? tileA : tileB, tis, tjs);
+        else gram_chunk<false, MT>(acc, tileA, same ? tileA : tileB, tis, tjs);
     }
 #pragma unroll
-    for (int t = 0; t < kMaxTiles; ++t) {
+    for (int t = 0; t < MT; ++t) {
         if (tis[t] >= 0) {
             const int ti = tis[t], tj = tjs[t];
 #pragma unroll

@@ -294,7 +294,7 @@ extern "C" int64_t clipgp_gp_smem_bytes(int64_t T, int64_t n, int64_t d, int bac
     return backward ? (int64_t)gp::make_bwd_layout(D).total : (int64_t)gp::make_fwd_layout(D).total;
 }
 
-int clipgp_gp_forward_warp_launch(const clipgp_gp_args* a, cudaStream_t st);   // gp_warp_forward.cu
+int clipgp_gp_forward_warp_launch(const clipgp_gp_args* a, cudaStream_t st, int fuse_gram);   // gp_warp_forward.cu
 extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
 
 static bool use_warp_path(const clipgp_gp_args* a) {
@@ -321,6 +321,11 @@ extern "C" int clipgp_gp_forward(const clipgp_gp_args* a, void* stream) {
         // two-kernel fast path: (1) block-per-class streamed Gram -> K_ZZ saved; (2) warp-per-class register-resident
         // factorisations / sampling / sparsemax from the saved block.  Classes whose test inputs do not alias the inducing
         // rows (x_is_z_prefix == 1 and the device check fails) are completed by kernel (1) itself.
+        // aliasing guaranteed by the caller: the algebra kernel computes the Gram block itself (one launch) when its scratch fits
+        static const bool no_fuse = (getenv("CLIPGP_GP_NO_FUSED_GRAM") != nullptr);
+        if (a->x_is_z_prefix == 2 && !no_fuse && a->d <= 1088 && (size_t)gp::pad4((int)a->n) * gp::KCP <= 2 * 1092) {
+            return clipgp_gp_forward_warp_launch(a, (cudaStream_t)stream, 1);
+        }
         if (a->x_is_z_prefix == 2) {
             const gp::Dims D = gp::make_dims((int)a->T, (int)a->n, (int)a->d);
             smem = sizeof(float) * (D.f_nn + (size_t)((a->d + 3) & ~3) + (size_t)gp::pad4((int)a->n) * gp::KCP) + 16;
@@ -328,7 +333,7 @@ extern "C" int clipgp_gp_forward(const clipgp_gp_args* a, void* stream) {
         gp::gp_forward_kernel<<<gp_grid(a), gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 1);
         rc = check_launch("gp_forward_kernel(gram)");
         if (rc != CLIPGP_OK) return rc;
-        return clipgp_gp_forward_warp_launch(a, (cudaStream_t)stream);
+        return clipgp_gp_forward_warp_launch(a, (cudaStream_t)stream, 0);
     }
     gp::gp_forward_kernel<<<gp_grid(a), gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 0);
     return check_launch("gp_forward_kernel");
