@@ -35,6 +35,8 @@ class GpArgs(C.Structure):
         ("status", C.c_void_p), ("Ksave", C.c_void_p),
         ("c_begin", c_i64), ("c_count", c_i64),
         ("eps_save", C.c_void_p),
+        ("proto_E", C.c_void_p), ("proto_D", c_i64), ("proto_P_hat", C.c_void_p), ("proto_norm", C.c_void_p),
+        ("proto_bf16", C.c_void_p), ("proto_bf16_ld", c_i64), ("proto_bf16_seg", c_i64), ("proto_bf16_mode", C.c_int32),
     ]
 
 
@@ -62,6 +64,7 @@ _SIGNATURES = {
     "clipgp_gp_smem_bytes": (c_i64, [c_i64, c_i64, c_i64, C.c_int]),
     "clipgp_gp_forward": (C.c_int, [C.POINTER(GpArgs), C.c_void_p]),
     "clipgp_gp_warp_path_ok": (C.c_int, [c_i64, c_i64, c_i64]),
+    "clipgp_gp_fused_proto_ok": (C.c_int, [c_i64, c_i64, c_i64, c_i64, c_i64]),
     "clipgp_gp_backward": (C.c_int, [C.POINTER(GpArgs), C.POINTER(GpBwdArgs), C.c_void_p]),
     "clipgp_proto_forward": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, c_i64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

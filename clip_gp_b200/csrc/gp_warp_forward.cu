@@ -20,6 +20,7 @@ struct FwdSmem {
     float mvec[36];
     float invdR[32];
     float mu[32];
+    float red[40];       // fused prototype stage: partial sums of squares [10 samples][4 warps]
     int flag[4];
 };
 
@@ -166,6 +167,10 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     if (a.R) each_block(T, T, [&](int idx, int i, int j) { a.R[(size_t)c * T * T + idx] = (j <= i) ? R[i * LD + j] : 0.f; });
 
     // ---- f_s = mu + R eps_s ; w_s = sparsemax(f_s)   (one sample per warp at a time, lane = template)
+    // fused prototype stage: the weights also stay in shared memory, [S][32] floats in the (dead, saved) L / A regions
+    float* wsm = (a.proto_E != nullptr && a.proto_P_hat != nullptr && a.proto_D <= 4 * NT && S * 32 <= 4 * NN)
+                     ? reinterpret_cast<float*>(s.Ld) : nullptr;
+    __syncthreads();                                // the saves above have read L / A / R's neighbours; Sigma (in Ad) is dead
     uint64_t seed = 0, step = 0;
     if (a.eps == nullptr) { seed = a.rng_state[0]; step = a.rng_state[1]; }
     const float* Rrow = R + lt * LD;
@@ -189,6 +194,75 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         float wv = sparsemax_lanes(f0 + f1 + mu, T);
         if (st < 0) wv = 0.f;
         if (lane < T) a.w[((size_t)sidx * a.C + c) * T + lane] = wv;
+        if (wsm) wsm[sidx * 32 + lane] = wv;        // lanes >= T hold 0
+    }
+    if (!wsm) return;
+
+    // ---- fused prototype stage: P[s,c,:] = sum_t w[s,t] E[c,t,:] -> unit rows (+ the bf16 operand of the logit GEMM).
+    // Thread = one 16-byte column group (D <= 512); PS samples per pass over E[c] (64 KB at T=32, D=512; a second pass hits L2).
+    __syncthreads();
+    constexpr int PS = 10;
+    const int D = (int)a.proto_D, D4 = D >> 2;
+    const int col = tid;
+    const float4* Ec = reinterpret_cast<const float4*>(a.proto_E + (size_t)c * T * D);
+    for (int s0 = 0; s0 < S; s0 += PS) {
+        const int sb = min(PS, S - s0);
+        float4 acc[PS];
+#pragma unroll
+        for (int u = 0; u < PS; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t0 = 0; t0 < T; t0 += 4) {
+            float4 e[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                e[q] = (col < D4 && t0 + q < T) ? __ldg(Ec + (size_t)(t0 + q) * D4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float* wt = wsm + s0 * 32 + t0 + q;             // w[s0 + u][t0 + q]: broadcast reads (0 beyond T)
+#pragma unroll
+                for (int u = 0; u < PS; ++u) {
+                    if (u < sb) {
+                        const float wv = wt[u * 32];
+                        acc[u].x = fmaf(wv, e[q].x, acc[u].x); acc[u].y = fmaf(wv, e[q].y, acc[u].y);
+                        acc[u].z = fmaf(wv, e[q].z, acc[u].z); acc[u].w = fmaf(wv, e[q].w, acc[u].w);
+                    }
+                }
+            }
+        }
+        // row norms across the CTA, then the outputs straight from the accumulators
+#pragma unroll
+        for (int u = 0; u < PS; ++u) {
+            float q = acc[u].x * acc[u].x + acc[u].y * acc[u].y + acc[u].z * acc[u].z + acc[u].w * acc[u].w;
+            q = warp_sum(q);
+            if (lane == 0) s.red[u * NW + wid] = q;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PS; ++u) {
+            if (u < sb) {
+                const float nrm = sqrtf(s.red[u * NW] + s.red[u * NW + 1] + s.red[u * NW + 2] + s.red[u * NW + 3]);
+                const float inv = 1.f / fmaxf(nrm, 1e-12f);
+                const size_t row = (size_t)(s0 + u) * a.C + c;
+                if (tid == 0 && a.proto_norm) a.proto_norm[row] = nrm;
+                if (col < D4) {
+                    const float4 h = make_float4(acc[u].x * inv, acc[u].y * inv, acc[u].z * inv, acc[u].w * inv);
+                    reinterpret_cast<float4*>(a.proto_P_hat + row * D)[col] = h;
+                    if (a.proto_bf16) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.proto_bf16) + row * a.proto_bf16_ld + 4 * col;
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(h.x, h.y), h1 = __floats2bfloat162_rn(h.z, h.w);
+                        uint2 hi; hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        *reinterpret_cast<uint2*>(o) = hi;
+                        if (a.proto_bf16_mode != 0) {
+                            const __nv_bfloat162 l0 = __floats2bfloat162_rn(h.x - __low2float(h0), h.y - __high2float(h0));
+                            const __nv_bfloat162 l1 = __floats2bfloat162_rn(h.z - __low2float(h1), h.w - __high2float(h1));
+                            uint2 lo; lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+                            *reinterpret_cast<uint2*>(o + a.proto_bf16_seg) = (a.proto_bf16_mode == 1) ? hi : lo;
+                            *reinterpret_cast<uint2*>(o + 2 * a.proto_bf16_seg) = (a.proto_bf16_mode == 1) ? lo : hi;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                // `red` is reused by the next sample chunk
     }
 }
 
@@ -200,6 +274,12 @@ using namespace clipgp;
 // Fast-path eligibility (the general kernel handles everything else).
 extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d) {
     return (T >= 2 && T <= 32 && n == T + 1 && d >= 4 && (d % 4) == 0) ? 1 : 0;
+}
+
+// The fused prototype stage runs on the warp path when D <= 512 (one 16-byte column group per thread), S <= 136 (the weights of
+// the class stay in the dead L / A regions) and the class set is not sharded (every class of w is produced by this launch).
+extern "C" int clipgp_gp_fused_proto_ok(int64_t T, int64_t n, int64_t d, int64_t D, int64_t S) {
+    return (clipgp_gp_warp_path_ok(T, n, d) && D >= 4 && (D % 4) == 0 && D <= 4 * gpw::NT && S * 32 <= 4 * gpw::NN) ? 1 : 0;
 }
 
 int clipgp_gp_forward_warp_launch(const clipgp_gp_args* a, cudaStream_t st, int fuse_gram) {

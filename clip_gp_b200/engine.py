@@ -48,6 +48,7 @@ class EngineConfig:
                                         # before destroying the process group, otherwise NCCL teardown hangs; bench.py does
     shard_classes: bool = True          # world > 1: the per-class GP kernels run on this rank's class shard only (w and dw cross
                                         # NVLink as two 1.3 MB all-reduces); the MC samples of the logit path stay sharded as before
+    fuse_prototypes: bool = True        # build the prototypes inside the GP forward kernel's CTA when the sizes allow it
     overlap: bool = True                # run the feature branch of the step on a side stream next to the GP branch
     seed: int = 0
     rank: int = 0
@@ -167,6 +168,15 @@ class GPAdapterEngine:
         a.c_begin, a.c_count = self.c_lo, self.c_hi - self.c_lo
         self.eps_save = torch.empty(Sg, Cn, T, **f32)       # base noise of the step: drawn once (forward), re-read by the adjoint
         a.eps_save = self.eps_save.data_ptr()
+        # fused prototype stage: the GP forward kernel's CTA of class c also builds the unit prototypes of class c and the bf16
+        # operand rows of the logit GEMM (no grid-wide barrier, no separate prototype / cast launches)
+        self.fused_proto = bool(self.cfg.fuse_prototypes and self.cfg.loss_mode == "per_sample" and not self.class_sharded and
+                                self.lib.clipgp_gp_fused_proto_ok(T, n, d, D, S))
+        if self.fused_proto:
+            a.proto_E, a.proto_D = self.E.data_ptr(), D
+            a.proto_P_hat, a.proto_norm = self.P_hat.data_ptr(), self.P_norm.data_ptr()
+            if self.cfg.precision != "fp32":
+                a.proto_bf16, a.proto_bf16_ld, a.proto_bf16_seg, a.proto_bf16_mode = self.Pb.data_ptr(), self.Pb.stride(0), D, self.tc_mb
         a.Z, a.X = self.Z.data_ptr(), self.X.data_ptr()
         a.raw_lengthscale = self._ptr(self.flat_p, "ls") if "ls" in self.offsets else None
         a.raw_outputscale = self._ptr(self.flat_p, "os") if "os" in self.offsets else None
@@ -296,6 +306,8 @@ class GPAdapterEngine:
         ck(lib.clipgp_gp_forward(C.byref(self.gp_args), st), "gp_forward")
         if self.class_sharded:
             torch.distributed.all_reduce(self.w_all)          # every rank wrote its classes (all samples); the sum completes w
+        if self.fused_proto:
+            return                                            # prototypes and their GEMM operand came out of the GP kernel
         ck(lib.clipgp_proto_forward(self.w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, self.P_hat.data_ptr(),
                                     self.P_norm.data_ptr(), None, None if per_sample else self.P_mean.data_ptr(), None, 0, st), "proto_forward")
         if cfg.precision != "fp32":
@@ -478,6 +490,7 @@ class GPAdapterEngine:
         a.S, a.s_offset, a.S_total = S, 0, S
         a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
         a.eps_save = None
+        a.proto_E = a.proto_P_hat = a.proto_norm = a.proto_bf16 = None
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path
@@ -549,6 +562,7 @@ class GPAdapterEngine:
         a.S, a.s_offset, a.S_total = S, 0, S
         a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
         a.eps_save = None
+        a.proto_E = a.proto_P_hat = a.proto_norm = a.proto_bf16 = None
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path

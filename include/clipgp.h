@@ -108,13 +108,26 @@ typedef struct clipgp_gp_args {
     float* eps_save;              /* optional [S,C,T] (layout of w): with the counter RNG, the warp-path forward kernel stores the base
                                      noise it drew and the warp-path adjoint reads it back instead of regenerating the Philox
                                      stream (the general kernels ignore it and regenerate) */
+    /* Optional fused prototype stage of the warp-path forward kernel (all NULL / 0: off).  The CTA that produced w[:, c, :] also
+     * builds the unit prototypes of class c (gp_template_weigher.py:221 + F.normalize, adapter.py:425), i.e. what
+     * clipgp_proto_forward + clipgp_cast_bf16 would do, without a grid-wide barrier in between: */
+    const float* proto_E;         /* [C,T,D] text bank (D % 4 == 0, D <= 1024) */
+    int64_t proto_D;
+    float* proto_P_hat;           /* out [S,C,D] unit prototypes (fp32) */
+    float* proto_norm;            /* out [S,C]   |P_raw| */
+    void* proto_bf16;             /* out, optional: bf16 operand rows (s*C + c) with the layouts of clipgp_cast_bf16 */
+    int64_t proto_bf16_ld, proto_bf16_seg;
+    int32_t proto_bf16_mode;
 } clipgp_gp_args;
 
 /* Dynamic shared memory the forward / backward kernel needs for (T, n, d); 0 if unsupported. */
 int64_t clipgp_gp_smem_bytes(int64_t T, int64_t n, int64_t d, int backward);
 
 int clipgp_gp_forward(const clipgp_gp_args* args, void* stream);
-/* 1 if (T, n, d) is served by the warp-per-class register-resident fast path (T <= 32, n == T+1, d % 4 == 0). */
+/* 1 if the fused prototype stage (clipgp_gp_args.proto_*) can run for these sizes (warp path, D <= 512, S <= 136); the caller must
+ * also pass x_is_z_prefix == 2 and process all classes in one launch.  Otherwise use clipgp_proto_forward. */
+int clipgp_gp_fused_proto_ok(int64_t T, int64_t n, int64_t d, int64_t D, int64_t S);
+/* 1 if (T, n, d) is served by the warp-per-class fast path (2 <= T <= 32, n == T+1, d % 4 == 0). */
 int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
 
 /* Adjoint of clipgp_gp_forward.  `fwd` must be the argument block of the forward call (same inputs, with
