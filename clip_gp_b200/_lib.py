@@ -46,6 +46,8 @@ class GpBwdArgs(C.Structure):
         ("dw", C.c_void_p), ("dkl", C.c_void_p), ("dkl_scalar", C.c_float),
         ("dZ_last", C.c_void_p), ("draw_lengthscale", C.c_void_p), ("draw_outputscale", C.c_void_p),
         ("draw_variance", C.c_void_p), ("dvar_mean", C.c_void_p), ("dchol_var", C.c_void_p), ("dmean_x", C.c_void_p),
+        ("proto_dP", C.c_void_p), ("proto_dP_stride_s", c_i64), ("proto_dP_scale", C.c_float), ("proto_norm", C.c_void_p),
+        ("proto_E", C.c_void_p), ("proto_EEt", C.c_void_p), ("proto_D", c_i64), ("dw_out", C.c_void_p),
     ]
 
 
@@ -65,6 +67,7 @@ _SIGNATURES = {
     "clipgp_gp_forward": (C.c_int, [C.POINTER(GpArgs), C.c_void_p]),
     "clipgp_gp_warp_path_ok": (C.c_int, [c_i64, c_i64, c_i64]),
     "clipgp_gp_fused_proto_ok": (C.c_int, [c_i64, c_i64, c_i64, c_i64, c_i64]),
+    "clipgp_gp_fused_proto_bwd_ok": (C.c_int, [c_i64, c_i64, c_i64, c_i64, c_i64]),
     "clipgp_gp_backward": (C.c_int, [C.POINTER(GpArgs), C.POINTER(GpBwdArgs), C.c_void_p]),
     "clipgp_proto_forward": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, c_i64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

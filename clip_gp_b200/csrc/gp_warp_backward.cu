@@ -14,6 +14,8 @@
 // 7 classes per SM.
 #include "gp_warp.cuh"
 
+extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
+
 namespace clipgp {
 namespace gpw {
 
@@ -39,6 +41,69 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     const float dkl = b.dkl ? b.dkl[c] : b.dkl_scalar;
     const int lt = lane < T ? lane : T - 1;        // clamped lane for row-per-lane walks
 
+    // =========================== P0 (optional): prototype adjoint -> dw of this class ===========================
+    // dwsm [S][32] lives at the end of RC until P2 stages Lq there; it replaces the global dw read of P1.
+    float* dwsm = nullptr;
+    if (b.proto_dP != nullptr) {
+        const int D = (int)b.proto_D, D4 = D >> 2;
+        float* gbuf = reinterpret_cast<float*>(s.RA);                 // [S][D] upstream gradient rows (RA | RB | start of RC)
+        float* abuf = reinterpret_cast<float*>(s.RA) + 3 * 2 * NN - 2 * S * 32;   // [S][32]  a[s][t]
+        dwsm = abuf + S * 32;                                         // [S][32]  (last S*32 floats of RC)
+        float* Gc = s.Af;                                             // [T][T] = E[c] E[c]^T (Af is dead until P2)
+        for (int sidx = 0; sidx < S; ++sidx) {
+            const float4* src = reinterpret_cast<const float4*>(b.proto_dP + (size_t)sidx * b.proto_dP_stride_s + (size_t)c * D);
+            for (int col = tid; col < D4; col += NT) {
+                float4 v = __ldg(src + col);
+                v.x *= b.proto_dP_scale; v.y *= b.proto_dP_scale; v.z *= b.proto_dP_scale; v.w *= b.proto_dP_scale;
+                reinterpret_cast<float4*>(gbuf + (size_t)sidx * D)[col] = v;
+            }
+        }
+        for (int idx = tid; idx < T * T; idx += NT) Gc[idx] = __ldg(b.proto_EEt + (size_t)c * T * T + idx);
+        __syncthreads();
+        // a[s][t] = <g_s, E[c,t,:]>: warp = template row (the next row's loads in flight), lanes over the 16-byte column groups
+        const float4* Ec = reinterpret_cast<const float4*>(b.proto_E + (size_t)c * T * D);
+        constexpr int PSB = 12;
+        for (int t = wid; t < T; t += NW) {
+            float part[PSB];
+#pragma unroll
+            for (int u = 0; u < PSB; ++u) part[u] = 0.f;
+            for (int col = lane; col < D4; col += 32) {
+                const float4 e = __ldg(Ec + (size_t)t * D4 + col);
+#pragma unroll
+                for (int u = 0; u < PSB; ++u) {
+                    if (u < S) {
+                        const float4 v = reinterpret_cast<const float4*>(gbuf + (size_t)u * D)[col];
+                        part[u] += e.x * v.x + e.y * v.y + e.z * v.z + e.w * v.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PSB; ++u) {
+                if (u < S) {
+                    const float tot = warp_sum(part[u]);
+                    if (lane == 0) abuf[u * 32 + t] = tot;
+                }
+            }
+        }
+        __syncthreads();
+        // dw[s][t] = (a[s][t] - q_s (w_s G)[t] / |P_s|) / |P_s|,  q_s = <w_s, a_s> / |P_s|   (one sample per warp, lane = template)
+        for (int sidx = wid; sidx < S; sidx += NW) {
+            const size_t off = ((size_t)sidx * a.C + c) * T;
+            const float wv = lane < T ? a.w[off + lane] : 0.f;
+            const float av = lane < T ? abuf[sidx * 32 + lane] : 0.f;
+            const float invn = 1.f / fmaxf(__ldg(b.proto_norm + (size_t)sidx * a.C + c), 1e-12f);
+            const float q = warp_sum(wv * av) * invn;
+            float wg = 0.f;
+            for (int k = 0; k < T; ++k) wg = fmaf(__shfl_sync(FULL, wv, k), Gc[k * T + lt], wg);
+            const float dwv = (av - q * wg * invn) * invn;
+            if (lane < T) {
+                dwsm[sidx * 32 + lane] = dwv;
+                if (b.dw_out) b.dw_out[off + lane] = dwv;
+            }
+        }
+        __syncthreads();
+    }
+
     // =========================== P1 ===========================
     float* R = reinterpret_cast<float*>(s.RB);
     float* G = R + NN;
@@ -60,7 +125,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
             const size_t off = ((size_t)sidx * a.C + c) * T;
             const float wv = lane < T ? a.w[off + lane] : 0.f;
             const bool sup = wv > 0.f;
-            const float g = sup ? b.dw[off + lane] : 0.f;
+            const float g = sup ? (dwsm ? dwsm[sidx * 32 + lane] : b.dw[off + lane]) : 0.f;
             const int cnt = __popc(__ballot_sync(FULL, sup));
             const float vhat = warp_sum(g) / (float)max(cnt, 1);
             const float df = sup ? g - vhat : 0.f;              // entmax sparsemax backward
@@ -297,6 +362,12 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
 }  // namespace clipgp
 
 using namespace clipgp;
+
+// Fused prototype adjoint: S gradient rows of D floats plus two [S][32] tables must fit RA | RB | RC, S <= 12 register accumulators.
+extern "C" int clipgp_gp_fused_proto_bwd_ok(int64_t T, int64_t n, int64_t d, int64_t D, int64_t S) {
+    return (clipgp_gp_warp_path_ok(T, n, d) && D >= 4 && (D % 4) == 0 && S >= 1 && S <= 12 &&
+            (size_t)S * (size_t)(D + 64) * sizeof(float) <= 3 * sizeof(double) * gpw::NN) ? 1 : 0;
+}
 
 // Shared memory the fused kernel-adjoint stage needs in RB + RC (floats): inverse length-scales, two per-feature accumulators,
 // row / column sums and one [pad4(n)][KCP] chunk tile.

@@ -201,6 +201,15 @@ class GPAdapterEngine:
         b.draw_outputscale = self._ptr(self.flat_g, "os") if "os" in self.offsets else None
         b.draw_variance = self._ptr(self.flat_g, "var") if "var" in self.offsets else None
         b.dvar_mean, b.dchol_var, b.dmean_x = self._ptr(self.flat_g, "m"), self._ptr(self.flat_g, "Lq"), None
+        # fused prototype adjoint: the GP adjoint kernel's CTA of class c derives dw[:, c, :] from dP_hat itself
+        self.fused_proto_bwd = bool(self.cfg.fuse_prototypes and self.cfg.loss_mode == "per_sample" and not self.class_sharded and
+                                    self.lib.clipgp_gp_fused_proto_bwd_ok(T, n, d, D, S))
+        if self.fused_proto_bwd:
+            if getattr(self, "EEt", None) is None:
+                self.EEt = torch.bmm(self.E, self.E.transpose(1, 2)).contiguous()       # [C,T,T], frozen text bank: one-time setup
+            b.proto_dP, b.proto_dP_stride_s, b.proto_dP_scale = self.dP.data_ptr(), Cn * D, 1.0
+            b.proto_norm, b.proto_E, b.proto_EEt, b.proto_D = self.P_norm.data_ptr(), self.E.data_ptr(), self.EEt.data_ptr(), D
+            b.dw_out = self.dw_all.data_ptr()
         self.gp_bwd_args = b
 
     # ------------------------------------------------------------------ tensor-core operand buffers
@@ -393,8 +402,9 @@ class GPAdapterEngine:
         # dP_mean (the 1/S is inside alpha)
         if self.class_sharded:
             self.dw_all.zero_()
-        ck(lib.clipgp_proto_backward(self.dP.data_ptr(), Cn * D if per_sample else 0, 1.0, self.P_hat.data_ptr(), self.P_norm.data_ptr(),
-                                     self.E.data_ptr(), S, Cn, T, D, self.dw.data_ptr(), st), "proto_backward")
+        if not self.fused_proto_bwd:
+            ck(lib.clipgp_proto_backward(self.dP.data_ptr(), Cn * D if per_sample else 0, 1.0, self.P_hat.data_ptr(), self.P_norm.data_ptr(),
+                                         self.E.data_ptr(), S, Cn, T, D, self.dw.data_ptr(), st), "proto_backward")
         if self.class_sharded:
             torch.distributed.all_reduce(self.dw_all)         # every rank wrote its samples (all classes); rows of other ranks are zero
         ck(lib.clipgp_gp_backward(C.byref(self.gp_args), C.byref(self.gp_bwd_args), st), "gp_backward")

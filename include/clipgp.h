@@ -148,7 +148,23 @@ typedef struct clipgp_gp_bwd_args {
     float* dvar_mean;
     float* dchol_var;
     float* dmean_x;
+    /* Optional fused prototype adjoint of the warp path (proto_dP == NULL: off, `dw` is the upstream gradient as above).  The CTA
+     * of class c derives dw[:, c, :] itself from the gradient of the UNIT prototypes, i.e. what clipgp_proto_backward does, without a
+     * grid-wide barrier in between and without reading P_hat:
+     *     a[s,t] = <dP_hat[s,c,:], E[c,t,:]>,  q_s = <w_s, a_s> / |P_s|,  dw[s,t] = (a[s,t] - q_s (w_s G_c)[t] / |P_s|) / |P_s|
+     * with G_c = E[c] E[c]^T (frozen, [C,T,T], supplied by the caller).  Needs S * (D + 64) * 4 <= 26208 bytes of shared memory. */
+    const float* proto_dP;        /* [S,C,D] gradient of the unit prototypes (sample stride proto_dP_stride_s elements, 0 = broadcast) */
+    int64_t proto_dP_stride_s;
+    float proto_dP_scale;
+    const float* proto_norm;      /* [S,C] |P_raw| from the forward pass */
+    const float* proto_E;         /* [C,T,D] */
+    const float* proto_EEt;       /* [C,T,T] */
+    int64_t proto_D;
+    float* dw_out;                /* optional [S,C,T]: the derived dw (for inspection) */
 } clipgp_gp_bwd_args;
+
+/* 1 if the fused prototype adjoint can run for these sizes (warp path and the shared-memory bound above). */
+int clipgp_gp_fused_proto_bwd_ok(int64_t T, int64_t n, int64_t d, int64_t D, int64_t S);
 
 int clipgp_gp_backward(const clipgp_gp_args* fwd, const clipgp_gp_bwd_args* bwd, void* stream);
 
