@@ -63,25 +63,67 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         // a[s][t] = <g_s, E[c,t,:]>: warp = template row (the next row's loads in flight), lanes over the 16-byte column groups
         const float4* Ec = reinterpret_cast<const float4*>(b.proto_E + (size_t)c * T * D);
         constexpr int PSB = 12;
-        for (int t = wid; t < T; t += NW) {
-            float part[PSB];
+        if (D4 <= 128) {
+            // D <= 512: a lane owns at most four column groups of a row; the next row's loads are issued before this row is consumed
+            float4 nxt[4];
+            auto fetch = [&](int t) {
 #pragma unroll
-            for (int u = 0; u < PSB; ++u) part[u] = 0.f;
-            for (int col = lane; col < D4; col += 32) {
-                const float4 e = __ldg(Ec + (size_t)t * D4 + col);
+                for (int u = 0; u < 4; ++u) {
+                    const int col = lane + 32 * u;
+                    nxt[u] = (t < T && col < D4) ? __ldg(Ec + (size_t)t * D4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            fetch(wid);
+            for (int t = wid; t < T; t += NW) {
+                float4 e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e[u] = nxt[u];
+                fetch(t + NW);
+                float part[PSB];
+#pragma unroll
+                for (int u = 0; u < PSB; ++u) part[u] = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = lane + 32 * q;
+                    if (col < D4) {
+#pragma unroll
+                        for (int u = 0; u < PSB; ++u) {
+                            if (u < S) {
+                                const float4 v = reinterpret_cast<const float4*>(gbuf + (size_t)u * D)[col];
+                                part[u] += e[q].x * v.x + e[q].y * v.y + e[q].z * v.z + e[q].w * v.w;
+                            }
+                        }
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < PSB; ++u) {
                     if (u < S) {
-                        const float4 v = reinterpret_cast<const float4*>(gbuf + (size_t)u * D)[col];
-                        part[u] += e.x * v.x + e.y * v.y + e.z * v.z + e.w * v.w;
+                        const float tot = warp_sum(part[u]);
+                        if (lane == 0) abuf[u * 32 + t] = tot;
                     }
                 }
             }
+        } else {
+            for (int t = wid; t < T; t += NW) {
+                float part[PSB];
 #pragma unroll
-            for (int u = 0; u < PSB; ++u) {
-                if (u < S) {
-                    const float tot = warp_sum(part[u]);
-                    if (lane == 0) abuf[u * 32 + t] = tot;
+                for (int u = 0; u < PSB; ++u) part[u] = 0.f;
+                for (int col = lane; col < D4; col += 32) {
+                    const float4 e = __ldg(Ec + (size_t)t * D4 + col);
+#pragma unroll
+                    for (int u = 0; u < PSB; ++u) {
+                        if (u < S) {
+                            const float4 v = reinterpret_cast<const float4*>(gbuf + (size_t)u * D)[col];
+                            part[u] += e.x * v.x + e.y * v.y + e.z * v.z + e.w * v.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PSB; ++u) {
+                    if (u < S) {
+                        const float tot = warp_sum(part[u]);
+                        if (lane == 0) abuf[u * 32 + t] = tot;
+                    }
                 }
             }
         }
