@@ -162,23 +162,27 @@ def run_reference(args):
 
 
 # ======================================================================================================= our arm
-def algorithmic_bytes(shp, S, kernel_name):
+def algorithmic_bytes(shp, S, kernel_name, eng=None):
     """Algorithmic HBM bytes per launch of the step's kernels (DESIGN.md section 'kernels')."""
     C, T, D, d, n, B = shp.C, shp.T, shp.D, shp.d, shp.T + 1, shp.B
     f = 4
-    table = {
-        # warp path (test inputs alias the frozen inducing rows, so X is never read).  Gram kernel: reads Z [C,n,d] + lengthscales,
-        # writes the K_ZZ block; algebra kernel: reads K_ZZ, Lq, m, writes w [S,C,T] and the saved L (fp64), A, R, KL
-        "gp_forward": f * (C * n * d + C * d + C * n * n) + f * (2 * C * n * n + C * n + S * C * T + C * n * T + C * T * T + C) + 8 * C * n * n,
-        # algebra kernel: reads R, w, dw, A, Lq, m, L (fp64), writes dLq, dm and the dK block (write, read, write);
-        # kernel-adjoint kernel: reads dK, K_ZZ, Z, lengthscales, writes the length-scale / learnable-row / output-scale gradients
-        "gp_backward": f * (C * T * T + 2 * S * C * T + C * n * T + C * n * n + C * n) + 8 * C * n * n + f * (4 * C * n * n + C * n)
-                       + f * (2 * C * n * n + C * n * d + C * d + 2 * C * d + C),
-        # reads E [C,T,D] + w; writes P_hat [S,C,D] + norms
-        "proto_forward": f * (C * T * D + S * C * T + S * C * D + S * C),
-        # reads dP, P_hat [S,C,D], E [C,T,D] once per sample chunk (ceil(S/8) chunks); writes dw
-        "proto_backward": f * (2 * S * C * D + ((S + 7) // 8) * C * T * D + S * C * T + S * C),
-    }
+    seg = getattr(eng, "tc_seg", 0) if eng is not None and eng.cfg.precision != "fp32" else 0
+    # warp path (test inputs alias the frozen inducing rows, so X is never read).  Gram: reads Z [C,n,d] + lengthscales, writes the K_ZZ
+    # record; algebra: reads Lq, m, writes w [S,C,T], the base noise, the saved L (fp64), A, R, KL
+    gp_fwd = f * (C * n * d + C * d + C * n * n) + f * (C * n * n + C * n + 2 * S * C * T + C * n * T + C * T * T + C) + 8 * C * n * n
+    # algebra adjoint: reads R, w, eps, dw, A, Lq, m, L (fp64), writes dLq, dm and the dK scratch block (write, add, read);
+    # kernel adjoint: reads dK, K_ZZ, Z, lengthscales, writes the length-scale / learnable-row / output-scale gradients
+    gp_bwd = f * (C * T * T + 3 * S * C * T + C * n * T + C * n * n + C * n) + 8 * C * n * n + f * (4 * C * n * n + C * n) \
+        + f * (C * n * n + C * n * d + C * d + 2 * C * d + C)
+    # prototypes: reads E [C,T,D] (+ w); writes P_hat [S,C,D], norms and (tensor-core step) the bf16 operand rows
+    proto_fwd = f * (C * T * D + S * C * T + S * C * D + S * C)
+    # prototype adjoint: reads dP_hat [S,C,D], E (once per chunk of <= 8 samples), P_hat; writes dw
+    proto_bwd = f * (2 * S * C * D + ((S + 7) // 8) * C * T * D + S * C * T + S * C)
+    if eng is not None and getattr(eng, "fused_proto", False):
+        gp_fwd += f * (C * T * D + S * C * D + S * C) + 2 * seg * S * C * D      # fused prototype stage (w stays on chip)
+    if eng is not None and getattr(eng, "fused_proto_bwd", False):
+        gp_bwd += f * (S * C * D + C * T * D + C * T * T + S * C + S * C * T)       # dP_hat, E, E E^T, norms in; dw out (inspection copy)
+    table = {"gp_forward": gp_fwd, "gp_backward": gp_bwd, "proto_forward": proto_fwd, "proto_backward": proto_bwd}
     return table.get(kernel_name)
 
 
@@ -403,7 +407,7 @@ def run_ours(args):
     roof = None
     if dom is not None:
         base = dom.split("(")[0]
-        ab = algorithmic_bytes(shp, eng.S_local, base)
+        ab = algorithmic_bytes(shp, eng_train.S_local, base, eng_train)
         dur = ktimes[dom]["ms"] * 1e-3 / max(1, ktimes[dom]["calls"])
         if ab is not None:
             ach = ab / dur / 1e9
@@ -430,8 +434,9 @@ def run_ours(args):
                                  "bf16x3": "tcgen05 GEMMs on split-bf16 operands (fp32-grade products; the reference's GPU path is TF32), fp32 everywhere else, fp64 K_ZZ Cholesky",
                                  "bf16": "tcgen05 bf16 GEMMs, fp32 everywhere else, fp64 K_ZZ Cholesky"}[args.precision],
                    "cuda_graph": eng_train._graph is not None, "two_stream_overlap": bool(eng_train.cfg.overlap),
-                   "multi_gpu": (f"GP kernels class-sharded ({shp.C} classes / {world} ranks, w and dw all-reduced), logit path sample-sharded, "
-                                 "gradients + loss all-reduced; step captured in a CUDA graph incl. NCCL") if world > 1 else None,
+                   "multi_gpu": (f"MC samples sharded over {world} ranks (same Philox stream), ONE all-reduce of the flat gradient buffer + loss; "
+                                 "step captured in a CUDA graph incl. NCCL" + ("; GP kernels class-sharded" if eng_train.class_sharded else ""))
+                   if world > 1 else None,
                    "loss_last": loss_last},
         "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": shp.B * shp.D * 4 + shp.B * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches_per_step) * args.steps,

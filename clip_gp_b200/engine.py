@@ -46,8 +46,9 @@ class EngineConfig:
     graph_collectives: bool = False     # world > 1: capture the step (its NCCL all-reduces included) in the CUDA graph as well
                                         # (1886 -> 2088 steps/s at 2 GPUs).  The owner must drop the graph (engine._graph = None)
                                         # before destroying the process group, otherwise NCCL teardown hangs; bench.py does
-    shard_classes: bool = True          # world > 1: the per-class GP kernels run on this rank's class shard only (w and dw cross
-                                        # NVLink as two 1.3 MB all-reduces); the MC samples of the logit path stay sharded as before
+    shard_classes: bool = False         # world > 1: additionally run the per-class GP kernels on this rank's class shard only (w and dw
+                                        # cross NVLink as two 1.3 MB all-reduces).  Off by default: it rules out the per-class fusion of
+                                        # the prototype stages into the GP kernels, which is worth more (2 GPUs: 1876 vs ~2200 steps/s)
     fuse_prototypes: bool = True        # build the prototypes inside the GP forward kernel's CTA when the sizes allow it
     overlap: bool = True                # run the feature branch of the step on a side stream next to the GP branch
     seed: int = 0
