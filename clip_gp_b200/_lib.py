@@ -103,6 +103,7 @@ _SIGNATURES = {
     "clipgp_softmax_grad_bf16_dual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, C.c_float, C.c_void_p, c_i64,
                                                 c_i64, C.c_int, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
     "clipgp_increment2": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
+    "clipgp_step_epilogue": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_row_sqnorm": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p]),
     "clipgp_pairdist_radix_hist": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),

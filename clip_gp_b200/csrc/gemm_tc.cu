@@ -478,7 +478,10 @@ static int launch(const void* A, long long M, long long Ka, const void* B, long 
                 p.tail_kb = (p.num_k + want - 1) / want;
                 p.tail_split = (p.num_k + p.tail_kb - 1) / p.tail_kb;
                 p.full_items = tiles - tail;
-                CLIPGP_CUDA(cudaMemset2DAsync(p.C, sizeof(float) * p.ldc, 0, sizeof(float) * N, M, st));
+                // the tail tiles accumulate atomically: zero the rows they cover (from the first tail tile's row block to M; the few
+                // whole-K tiles that share that row block are stored afterwards, so zeroing them too is harmless)
+                const long long row0 = (long long)(p.full_items / p.num_n) * BM;
+                CLIPGP_CUDA(cudaMemset2DAsync(p.C + row0 * p.ldc, sizeof(float) * p.ldc, 0, sizeof(float) * N, M - row0, st));
             }
         }
     }

@@ -394,6 +394,18 @@ __global__ void __launch_bounds__(256) softmax_stats_kernel(const float* __restr
     }
 }
 
+// End of the optimisation step in one launch: the learnable inducing row (z_last [C,d], part of the flat parameter buffer, just
+// updated by AdamW) is scattered into Z[:, n-1, :], and the two device counters (AdamW step, RNG draw index) advance.
+__global__ void __launch_bounds__(256) step_epilogue_kernel(const float* __restrict__ z_last, float* __restrict__ Z, int64_t C, int n, int d,
+                                                            int64_t* a, int64_t* b, int64_t by) {
+    const int64_t total = C * (int64_t)d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = i / d; const int k = (int)(i - c * d);
+        Z[(c * n + (n - 1)) * d + k] = z_last[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *a += by; *b += by; }
+}
+
 __global__ void increment2_kernel(int64_t* a, int64_t* b, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) { *a += by; *b += by; } }
 
 __global__ void increment_kernel(int64_t* p, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) *p += by; }
@@ -587,4 +599,15 @@ extern "C" int clipgp_increment2(int64_t* a, int64_t* b, int64_t by, void* strea
     CLIPGP_REQUIRE(a && b, "increment2: NULL pointer");
     increment2_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a, b, by);
     return check_launch("increment2_kernel");
+}
+
+extern "C" int clipgp_step_epilogue(const float* z_last, float* Z, int64_t C, int64_t n, int64_t d, int64_t* counter_a,
+                                    int64_t* counter_b, int64_t by, void* stream) {
+    CLIPGP_REQUIRE(C >= 0 && n >= 1 && d >= 1 && n < (1ll << 31) && d < (1ll << 31), "step_epilogue: bad shape");
+    CLIPGP_REQUIRE(z_last && Z && counter_a && counter_b, "step_epilogue: NULL pointer");
+    int64_t blocks = (C * d + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1184) blocks = 1184;
+    step_epilogue_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z_last, Z, C, (int)n, (int)d, counter_a, counter_b, by);
+    return check_launch("step_epilogue_kernel");
 }

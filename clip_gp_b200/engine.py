@@ -431,8 +431,8 @@ class GPAdapterEngine:
         ck(lib.clipgp_adamw_step_lrptr(self.flat_p.data_ptr() + 4 * nW, self.flat_g.data_ptr() + 4 * nW, self.flat_m.data_ptr() + 4 * nW,
                                        self.flat_v.data_ptr() + 4 * nW, rest, self.lr_dev.data_ptr() + 4, b1, b2, cfg.adam_eps,
                                        cfg.weight_decay, self.adam_step.data_ptr(), st), "adamw(gp)")
-        self.Z[:, self.n - 1, :].copy_(self.p("z_last").view(self.C, self.d))
-        ck(lib.clipgp_increment2(self.adam_step.data_ptr(), self.rng_state.data_ptr() + 8, 1, st), "increment2")
+        ck(lib.clipgp_step_epilogue(self._ptr(self.flat_p, "z_last"), self.Z.data_ptr(), self.C, self.n, self.d, self.adam_step.data_ptr(),
+                                    self.rng_state.data_ptr() + 8, 1, st), "step_epilogue")
 
     # ------------------------------------------------------------------ public API
     def set_lr(self, lr: Optional[float] = None, gp_lr: Optional[float] = None) -> None:

@@ -266,6 +266,10 @@ int clipgp_softmax_grad_bf16_dual(const float* logits, const float* stats, const
                                   float grad_scale, void* out, int64_t out_ld, int64_t seg_stride, int mode, void* outT,
                                   int64_t outT_ld, int64_t segT_stride, int modeT, void* stream);
 int clipgp_increment2(int64_t* a, int64_t* b, int64_t by, void* stream);
+/* End of an optimisation step in one launch: Z[:, n-1, :] <- z_last [C,d] (the learnable inducing row lives in the flat parameter
+ * buffer; gp_template_weigher.py:72-79 freezes the other rows) and both device counters += by. */
+int clipgp_step_epilogue(const float* z_last, float* Z, int64_t C, int64_t n, int64_t d, int64_t* counter_a, int64_t* counter_b,
+                         int64_t by, void* stream);
 
 /* C[M,N] (fp32, row stride ldc) = alpha * A B^T.  Deterministic (one accumulator per output tile). */
 int clipgp_tc_gemm_store(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K, float alpha,
