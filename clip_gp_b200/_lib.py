@@ -102,6 +102,8 @@ _SIGNATURES = {
                                           C.c_void_p]),
     "clipgp_softmax_grad_bf16_dual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, C.c_float, C.c_void_p, c_i64,
                                                 c_i64, C.c_int, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
+    "clipgp_softmax_ce_bf16_dual": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
+                                              c_i64, c_i64, C.c_int, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
     "clipgp_increment2": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_step_epilogue": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_row_sqnorm": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p]),

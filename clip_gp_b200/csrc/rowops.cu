@@ -406,6 +406,112 @@ __global__ void __launch_bounds__(256) step_epilogue_kernel(const float* __restr
     if (blockIdx.x == 0 && threadIdx.x == 0) { *a += by; *b += by; }
 }
 
+// Softmax cross-entropy of the tensor-core step in ONE launch: a CTA owns 64 batch rows of one MC sample s, i.e. the block
+// logits[b0 .. b0+64, s*C .. (s+1)*C).  Phase 1: one warp per row reduces max / sum exp (row in registers, C <= 1024) and the CTA adds
+// its share of the loss.  Phase 2: the block is streamed again (it is L2 resident: 256 KB per CTA) in 64 x 64 tiles that write
+// dlogits = grad_scale (softmax - onehot) as both bf16 operands: row-major out[b, s*C + j] and transposed outT[s*C + j, b].
+__global__ void __launch_bounds__(256) softmax_ce_fused_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int64_t B,
+                                                               int S, int C, float* loss_sum, float loss_scale, float grad_scale,
+                                                               __nv_bfloat16* __restrict__ out, int64_t out_ld, int64_t seg_stride, int mode,
+                                                               __nv_bfloat16* __restrict__ outT, int64_t outT_ld, int64_t segT_stride, int modeT,
+                                                               int vec) {
+    __shared__ float tile[64][65];
+    __shared__ float s_m[64], s_inv[64];
+    __shared__ int s_lab[64];
+    __shared__ float s_part[8];
+    const int sidx = blockIdx.y;
+    const int64_t b0 = (int64_t)blockIdx.x * 64;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t K = (int64_t)S * C;
+    const float* base = logits + (int64_t)sidx * C;           // column offset of this sample inside a [B, S*C] row
+    // ---- phase 1: row statistics + loss (8 rows per warp)
+    float wloss = 0.f;
+    for (int rr = warp; rr < 64; rr += 8) {
+        const int64_t b = b0 + rr;
+        if (b >= B) { if (lane == 0) { s_m[rr] = 0.f; s_inv[rr] = 0.f; s_lab[rr] = -1; } continue; }
+        const float* x = base + b * K;
+        float m = -FLT_MAX, sum = 0.f;
+        if (vec && C <= 1024 && (C & 3) == 0 && (K & 3) == 0) {
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            const int C4 = C >> 2;
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = lane + 32 * u;
+                v[u] = (j < C4) ? __ldg(x4 + j) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+            }
+            m = warp_max(m);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (lane + 32 * u < C4) sum += expf(v[u].x - m) + expf(v[u].y - m) + expf(v[u].z - m) + expf(v[u].w - m);
+        } else {
+            for (int j = lane; j < C; j += 32) m = fmaxf(m, x[j]);
+            m = warp_max(m);
+            for (int j = lane; j < C; j += 32) sum += expf(x[j] - m);
+        }
+        sum = warp_sum(sum);
+        const int lab = (int)labels[b];
+        if (lane == 0) { s_m[rr] = m; s_inv[rr] = 1.f / sum; s_lab[rr] = lab; wloss += m + logf(sum) - x[lab]; }
+    }
+    if (lane == 0) s_part[warp] = wloss;
+    __syncthreads();
+    if (threadIdx.x == 0 && loss_sum) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += s_part[k];
+        atomicAdd(loss_sum, t * loss_scale);
+    }
+    // ---- phase 2: dlogits into both operand layouts, 64 x 64 tiles (thread = column pair, eight rows)
+    const int tx = lane, ty = warp;
+    for (int j0 = 0; j0 < C; j0 += 64) {
+        const int j = j0 + 2 * tx;
+        const int64_t k = (int64_t)sidx * C + j;               // column in the [B, S*C] matrix
+        const bool pair = vec && j + 1 < C;
+        float2 xin[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t b = b0 + ty + 8 * i;
+            xin[i] = make_float2(0.f, 0.f);
+            if (b < B) {
+                if (pair) xin[i] = __ldg(reinterpret_cast<const float2*>(logits + b * K + k));
+                else { if (j < C) xin[i].x = __ldg(logits + b * K + k); if (j + 1 < C) xin[i].y = __ldg(logits + b * K + k + 1); }
+            }
+        }
+        __syncthreads();                                       // the previous tile has been written out
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = ty + 8 * i;
+            const int64_t b = b0 + rr;
+            float v0 = 0.f, v1 = 0.f;
+            if (b < B) {
+                const float m = s_m[rr], inv = s_inv[rr];
+                const int lab = s_lab[rr];
+                if (j < C) v0 = grad_scale * (__expf(xin[i].x - m) * inv - (j == lab ? 1.f : 0.f));
+                if (j + 1 < C) v1 = grad_scale * (__expf(xin[i].y - m) * inv - (j + 1 == lab ? 1.f : 0.f));
+                if (out) {
+                    if (pair) store_split2(out + b * out_ld + k, seg_stride, mode, v0, v1);
+                    else { if (j < C) store_split(out + b * out_ld + k, seg_stride, mode, v0); if (j + 1 < C) store_split(out + b * out_ld + k + 1, seg_stride, mode, v1); }
+                }
+            }
+            tile[rr][2 * tx] = v0; tile[rr][2 * tx + 1] = v1;
+        }
+        __syncthreads();
+        if (outT) {
+            const int64_t b = b0 + 2 * tx;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int jj = j0 + ty + 8 * i;
+                if (jj < C) {
+                    const float v0 = tile[2 * tx][ty + 8 * i], v1 = tile[2 * tx + 1][ty + 8 * i];
+                    __nv_bfloat16* o = outT + ((int64_t)sidx * C + jj) * outT_ld + b;
+                    if (vec && b + 1 < B) store_split2(o, segT_stride, modeT, v0, v1);
+                    else { if (b < B) store_split(o, segT_stride, modeT, v0); if (b + 1 < B) store_split(o + 1, segT_stride, modeT, v1); }
+                }
+            }
+        }
+    }
+}
+
 __global__ void increment2_kernel(int64_t* a, int64_t* b, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) { *a += by; *b += by; } }
 
 __global__ void increment_kernel(int64_t* p, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) *p += by; }
@@ -610,4 +716,21 @@ extern "C" int clipgp_step_epilogue(const float* z_last, float* Z, int64_t C, in
     if (blocks > 1184) blocks = 1184;
     step_epilogue_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z_last, Z, C, (int)n, (int)d, counter_a, counter_b, by);
     return check_launch("step_epilogue_kernel");
+}
+
+extern "C" int clipgp_softmax_ce_bf16_dual(const float* logits, const int64_t* labels, int64_t B, int64_t S, int64_t C, float* loss_sum,
+                                           float loss_scale, float grad_scale, void* out, int64_t out_ld, int64_t seg_stride, int mode,
+                                           void* outT, int64_t outT_ld, int64_t segT_stride, int modeT, void* stream) {
+    const int64_t K = S * C;
+    int rc = check_dual("softmax_ce_bf16_dual", B, K, K, logits, out, outT, mode, modeT);
+    if (rc != CLIPGP_OK) return rc;
+    if (B == 0 || K == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(labels && S >= 1 && S <= 65535 && C >= 1 && C < (1ll << 31), "softmax_ce_bf16_dual: bad input");
+    dim3 grid((unsigned)((B + 63) / 64), (unsigned)S);
+    const int vec = dual_vec_ok(logits, K, out, out_ld, seg_stride, outT, outT_ld, segT_stride) && (C % 2 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(logits) & 15u) == 0);
+    softmax_ce_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, labels, B, (int)S, (int)C, loss_sum, loss_scale, grad_scale,
+                                                                   (__nv_bfloat16*)out, out_ld, seg_stride, mode, (__nv_bfloat16*)outT, outT_ld,
+                                                                   segT_stride, modeT, vec);
+    return check_launch("softmax_ce_fused_kernel");
 }

@@ -348,12 +348,19 @@ class GPAdapterEngine:
         if tcm:
             # two-phase softmax cross-entropy: row statistics + loss, then dlogits straight into the bf16 operands of the two
             # adjoint GEMMs (dlogits [B, SC] and dlogits^T [SC, B]); no fp32 dlogits
-            ck(lib.clipgp_softmax_ce_stats(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, self.sm_stats.data_ptr(),
-                                           self.loss.data_ptr(), loss_scale, st), "softmax_ce_stats")
-            ck(lib.clipgp_softmax_grad_bf16_dual(self.logits.data_ptr(), self.sm_stats.data_ptr(), self.in_lab.data_ptr(), B, rpl, Cn,
-                                                 loss_scale, _lib.ptr(self.dlb) if cfg.train_visual_proj else None, self.dlb.stride(0),
-                                                 self.SCp, self.tc_ma, self.dlTb.data_ptr(), self.dlTb.stride(0), self.Bp, self.tc_ma, st),
-               "softmax_grad")
+            dlb_ptr = _lib.ptr(self.dlb) if cfg.train_visual_proj else None
+            if ((B + 63) // 64) * rpl >= 296:
+                # large batches: one launch, a CTA owns 64 batch rows of one sample (>= two CTAs per SM; second read from L2)
+                ck(lib.clipgp_softmax_ce_bf16_dual(self.logits.data_ptr(), self.in_lab.data_ptr(), B, rpl, Cn, self.loss.data_ptr(), loss_scale,
+                                                   loss_scale, dlb_ptr, self.dlb.stride(0), self.SCp, self.tc_ma, self.dlTb.data_ptr(),
+                                                   self.dlTb.stride(0), self.Bp, self.tc_ma, st), "softmax_ce_bf16_dual")
+            else:
+                # minibatches: two launches with full-GPU grids (row statistics, then 64 x 64 tiles over the whole [B, S*C] matrix)
+                ck(lib.clipgp_softmax_ce_stats(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, self.sm_stats.data_ptr(),
+                                               self.loss.data_ptr(), loss_scale, st), "softmax_ce_stats")
+                ck(lib.clipgp_softmax_grad_bf16_dual(self.logits.data_ptr(), self.sm_stats.data_ptr(), self.in_lab.data_ptr(), B, rpl, Cn,
+                                                     loss_scale, dlb_ptr, self.dlb.stride(0), self.SCp, self.tc_ma, self.dlTb.data_ptr(),
+                                                     self.dlTb.stride(0), self.Bp, self.tc_ma, st), "softmax_grad")
         else:
             ck(lib.clipgp_softmax_ce(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, None, self.loss.data_ptr(),
                                      loss_scale, self.logits.data_ptr(), Cn, loss_scale, st), "softmax_ce")

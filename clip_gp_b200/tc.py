@@ -41,7 +41,7 @@ def cast_bf16_dual(x: torch.Tensor, mode: int = PLAIN, modeT: int = PLAIN):
     return out, outT
 
 
-def softmax_ce_operands(logits: torch.Tensor, labels: torch.Tensor, S: int, grad_scale: float, mode: int = PLAIN):
+def softmax_ce_operands(logits: torch.Tensor, labels: torch.Tensor, S: int, grad_scale: float, mode: int = PLAIN, fused: bool = True):
     """logits [B, S*C] (row (b,s) uses labels[b]) -> (mean CE over the B*S rows, dlogits bf16 [B, seg*SCp], dlogits^T bf16 [S*C, seg*Bp])
     with dlogits = grad_scale * (softmax - onehot): the two-phase tensor-core form of F.cross_entropy + its gradient."""
     dev = _lib.require_cuda(logits, labels)
@@ -55,6 +55,12 @@ def softmax_ce_operands(logits: torch.Tensor, labels: torch.Tensor, S: int, grad
     out = torch.zeros(B, seg * SCp, dtype=torch.bfloat16, device=dev)
     outT = torch.zeros(SC, seg * Bp, dtype=torch.bfloat16, device=dev)
     lib = _lib.load()
+    if fused:       # one launch (the form the engine uses)
+        with torch.cuda.device(dev):
+            _lib.check(lib.clipgp_softmax_ce_bf16_dual(logits.data_ptr(), labels.data_ptr(), B, S, Cn, loss.data_ptr(), 1.0 / (B * S),
+                                                       float(grad_scale), out.data_ptr(), out.stride(0), SCp, mode, outT.data_ptr(),
+                                                       outT.stride(0), Bp, mode, _lib.stream_ptr(dev)), "clipgp_softmax_ce_bf16_dual")
+        return loss, out, outT
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
         _lib.check(lib.clipgp_softmax_ce_stats(logits.data_ptr(), Cn, labels.data_ptr(), B * S, S, Cn, stats.data_ptr(), loss.data_ptr(),

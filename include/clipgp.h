@@ -265,6 +265,11 @@ int clipgp_softmax_ce_stats(const float* logits, int64_t ld, const int64_t* labe
 int clipgp_softmax_grad_bf16_dual(const float* logits, const float* stats, const int64_t* labels, int64_t B, int64_t S, int64_t C,
                                   float grad_scale, void* out, int64_t out_ld, int64_t seg_stride, int mode, void* outT,
                                   int64_t outT_ld, int64_t segT_stride, int modeT, void* stream);
+/* Both phases in one launch (a CTA owns 64 batch rows of one MC sample; the second read of its logits block comes from L2):
+ * loss_sum[0] += loss_scale * sum CE, and dlogits = grad_scale (softmax - onehot) in both bf16 operand layouts as above. */
+int clipgp_softmax_ce_bf16_dual(const float* logits, const int64_t* labels, int64_t B, int64_t S, int64_t C, float* loss_sum,
+                                float loss_scale, float grad_scale, void* out, int64_t out_ld, int64_t seg_stride, int mode, void* outT,
+                                int64_t outT_ld, int64_t segT_stride, int modeT, void* stream);
 int clipgp_increment2(int64_t* a, int64_t* b, int64_t by, void* stream);
 /* End of an optimisation step in one launch: Z[:, n-1, :] <- z_last [C,d] (the learnable inducing row lives in the flat parameter
  * buffer; gp_template_weigher.py:72-79 freezes the other rows) and both device counters += by. */

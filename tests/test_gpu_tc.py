@@ -106,16 +106,17 @@ def test_dual_layout_cast(R, K, mode, modeT):
     assert float((_unsplit(out, K, Kp, mode) - x).abs().max()) <= tol * float(x.abs().max())
 
 
-@pytest.mark.parametrize("B,S,C", [(16, 3, 12), (48, 4, 37), (128, 10, 1000), (130, 1, 1000)])
+@pytest.mark.parametrize("B,S,C", [(16, 3, 12), (48, 4, 37), (128, 10, 1000), (130, 1, 1000), (200, 2, 1500)])
 @pytest.mark.parametrize("mode", [tc.PLAIN, tc.SPLIT_A])
-def test_two_phase_softmax_ce_operands(B, S, C, mode):
+@pytest.mark.parametrize("fused", [True, False])
+def test_two_phase_softmax_ce_operands(B, S, C, mode, fused):
     """Loss and dlogits (both operand layouts) of the tensor-core step against torch cross_entropy + autograd."""
     g = torch.Generator().manual_seed(B + S + C)
     logits = (8.0 * torch.randn(B, S * C, generator=g)).cuda().requires_grad_(True)
     y = torch.randint(0, C, (B,), generator=g).cuda()
     ref = torch.nn.functional.cross_entropy(logits.view(B * S, C), y.repeat_interleave(S), reduction="mean")
     ref.backward()
-    loss, out, outT = tc.softmax_ce_operands(logits.detach(), y, S, 1.0 / (B * S), mode)
+    loss, out, outT = tc.softmax_ce_operands(logits.detach(), y, S, 1.0 / (B * S), mode, fused=fused)
     assert float(loss) == pytest.approx(float(ref), rel=1e-5)
     SC = S * C
     SCp, Bp = (SC + 7) // 8 * 8, (B + 7) // 8 * 8
