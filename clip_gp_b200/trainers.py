@@ -199,7 +199,10 @@ class AdapterTrainer(BaseTrainer):
                                 gp_beta=float(getattr(a, "gp_beta", 1.0)), l2_lambda=float(getattr(a, "l2_lambda", 0.5)), shots=self.shots,
                                 lr=float(_get(cfg, "optim.lr", 0.01)), gp_lr=float(getattr(a, "gp_lr", 1e-3)),
                                 weight_decay=float(_get(cfg, "optim.weight_decay", 0.0)), loss_mode="per_sample" if int(getattr(a, "gp_num_mc_samples_train", 1) or 1) > 1 else "logit_mean",
-                                train_visual_proj=not bool(getattr(a, "freeze_visual_proj", False)), seed=int(_get(cfg, "seed", 0) or 0))
+                                train_visual_proj=not bool(getattr(a, "freeze_visual_proj", False)), seed=int(_get(cfg, "seed", 0) or 0),
+                                # GEMMs of the step: split-bf16 tensor-core path by default (fp32-grade products; the reference's own
+                                # GPU path is TF32, adapter.py:23); "fp32" = FFMA comparator, "bf16" = stated tolerance
+                                precision=str(getattr(a, "clipgp_precision", "bf16x3")))
             self.engine = GPAdapterEngine(self.model.gp_weighter, ecfg, self.model.visual_proj.weight)
         else:
             params = [p for p in self.model.visual_proj.parameters()]
@@ -228,7 +231,14 @@ class AdapterTrainer(BaseTrainer):
         self.build_model()
         self.zero_shot()
         last = None
+        cfg = self.config
+        sched = str(_get(cfg, "optim.lr_scheduler", "cosine") or "constant").lower()
+        base_lr, base_gp_lr = float(_get(cfg, "optim.lr", 0.01)), float(getattr(cfg.adapter, "gp_lr", 1e-3))
         for self.epoch in range(self.max_epoch):
+            if self.use_gp and sched == "cosine":
+                # CosineAnnealingLR(T_max=max_epoch) stepped once per epoch (utils/optimization.py:232-238, adapter.py:1054-1056);
+                # the rates live in device memory, so the captured step graph is not re-captured
+                self.engine.cosine_lr(self.epoch, self.max_epoch, base_lr, base_gp_lr)
             for batch in self._epoch_batches():
                 last = self.forward_backward(batch)
             if last is not None and ((self.epoch + 1) % 10 == 0 or self.epoch == 0):
