@@ -37,6 +37,7 @@ class GpArgs(C.Structure):
         ("eps_save", C.c_void_p),
         ("proto_E", C.c_void_p), ("proto_D", c_i64), ("proto_P_hat", C.c_void_p), ("proto_norm", C.c_void_p),
         ("proto_bf16", C.c_void_p), ("proto_bf16_ld", c_i64), ("proto_bf16_seg", c_i64), ("proto_bf16_mode", C.c_int32),
+        ("proto_mean_hat", C.c_void_p),
     ]
 
 

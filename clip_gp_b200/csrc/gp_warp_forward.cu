@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
 
     // ---- f_s = mu + R eps_s ; w_s = sparsemax(f_s)   (one sample per warp at a time, lane = template)
     // fused prototype stage: the weights also stay in shared memory, [S][32] floats in the (dead, saved) L / A regions
-    float* wsm = (a.proto_E != nullptr && a.proto_P_hat != nullptr && a.proto_D <= 4 * NT && S * 32 <= 4 * NN)
+    float* wsm = (a.proto_E != nullptr && (a.proto_P_hat != nullptr || a.proto_mean_hat != nullptr) && a.proto_D <= 4 * NT && S * 32 <= 4 * NN)
                      ? reinterpret_cast<float*>(s.Ld) : nullptr;
     __syncthreads();                                // the saves above have read L / A / R's neighbours; Sigma (in Ad) is dead
     uint64_t seed = 0, step = 0;
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     const int D = (int)a.proto_D, D4 = D >> 2;
     const int col = tid;
     const float4* Ec = reinterpret_cast<const float4*>(a.proto_E + (size_t)c * T * D);
+    float4 msum = make_float4(0.f, 0.f, 0.f, 0.f);       // sum over the samples of this thread's unit-prototype columns
     for (int s0 = 0; s0 < S; s0 += PS) {
         const int sb = min(PS, S - s0);
         float4 acc[PS];
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
                 if (tid == 0 && a.proto_norm) a.proto_norm[row] = nrm;
                 if (col < D4) {
                     const float4 h = make_float4(acc[u].x * inv, acc[u].y * inv, acc[u].z * inv, acc[u].w * inv);
-                    reinterpret_cast<float4*>(a.proto_P_hat + row * D)[col] = h;
+                    msum.x += h.x; msum.y += h.y; msum.z += h.z; msum.w += h.w;
+                    if (a.proto_P_hat) reinterpret_cast<float4*>(a.proto_P_hat + row * D)[col] = h;
                     if (a.proto_bf16) {
                         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.proto_bf16) + row * a.proto_bf16_ld + 4 * col;
                         const __nv_bfloat162 h0 = __floats2bfloat162_rn(h.x, h.y), h1 = __floats2bfloat162_rn(h.z, h.w);
@@ -263,6 +265,10 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
             }
         }
         __syncthreads();                                // `red` is reused by the next sample chunk
+    }
+    if (a.proto_mean_hat && col < D4) {
+        const float is = 1.f / (float)S;
+        reinterpret_cast<float4*>(a.proto_mean_hat + (size_t)c * D)[col] = make_float4(msum.x * is, msum.y * is, msum.z * is, msum.w * is);
     }
 }
 

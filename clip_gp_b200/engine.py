@@ -508,15 +508,19 @@ class GPAdapterEngine:
         a.S, a.s_offset, a.S_total = S, 0, S
         a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
         a.eps_save = None
-        a.proto_E = a.proto_P_hat = a.proto_norm = a.proto_bf16 = None
+        a.proto_E = a.proto_P_hat = a.proto_norm = a.proto_bf16 = a.proto_mean_hat = None
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path
         Pm = torch.empty(Cn, D, **f32)
+        fused = bool(self.cfg.fuse_prototypes and lib.clipgp_gp_fused_proto_ok(T, n, self.d, D, S))
+        if fused:       # the class's CTA also averages its unit prototypes: no separate prototype pass
+            a.proto_E, a.proto_D, a.proto_mean_hat = self.E.data_ptr(), D, Pm.data_ptr()
         with torch.cuda.device(self.dev):
             _lib.check(lib.clipgp_gp_forward(C.byref(a), st), "gp_forward(eval)")
-            _lib.check(lib.clipgp_proto_forward(w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, None, None, None,
-                                                Pm.data_ptr(), None, 1, st), "proto_forward(eval)")
+            if not fused:
+                _lib.check(lib.clipgp_proto_forward(w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, None, None, None,
+                                                    Pm.data_ptr(), None, 1, st), "proto_forward(eval)")
         self.last_eval_w = w
         return Pm
 
@@ -580,7 +584,7 @@ class GPAdapterEngine:
         a.S, a.s_offset, a.S_total = S, 0, S
         a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
         a.eps_save = None
-        a.proto_E = a.proto_P_hat = a.proto_norm = a.proto_bf16 = None
+        a.proto_E = a.proto_P_hat = a.proto_norm = a.proto_bf16 = a.proto_mean_hat = None
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path

@@ -118,6 +118,8 @@ typedef struct clipgp_gp_args {
     void* proto_bf16;             /* out, optional: bf16 operand rows (s*C + c) with the layouts of clipgp_cast_bf16 */
     int64_t proto_bf16_ld, proto_bf16_seg;
     int32_t proto_bf16_mode;
+    float* proto_mean_hat;        /* out, optional [C,D]: (1/S) sum_s P_hat[s,c,:], the collapsed prototype of the logit-mean eval
+                                     (adapter.py:243-249); proto_P_hat may then be NULL */
 } clipgp_gp_args;
 
 /* Dynamic shared memory the forward / backward kernel needs for (T, n, d); 0 if unsupported. */
