@@ -458,6 +458,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(wl, shp, S, ls)
+        line["torch_eager_gpu"] = torch_eager_gpu(wl, shp, S, ls, dev)
     print(json.dumps(line), flush=True)
     if args.profile_kernels:
         for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["ms"]):
@@ -552,6 +553,42 @@ def cpu_baseline(wl, shp, S, ls, budget_s=20.0):
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} full steps (fwd + autograd bwd + AdamW) of the same {shp.name} workload on the host CPU, torch {torch.__version__}"}
+
+
+def torch_eager_gpu(wl, shp, S, ls, dev, steps=20):
+    """Second comparator of BASELINE.md section 4: the restated reference step (oracle: torch ops + autograd + torch AdamW) run
+    eagerly by torch ON THE SAME B200, TF32 matmuls allowed as in the reference (adapter.py:23) -- i.e. the reference's GPU path
+    without gpytorch's Python overhead.  Reported next to the CPU baseline; not the product path."""
+    try:
+        from oracle import gp as ogp
+        from oracle.train_step import OracleAdapter, state_to_device
+        torch.backends.cuda.matmul.allow_tf32 = True
+        st = state_to_device(ogp.build_state(wl["E"], shp.kernel, shp.d, lengthscale=ls), dev)
+        g = torch.Generator(device=dev).manual_seed(1)
+        st.var_mean = 1e-3 * torch.randn(shp.C, shp.T + 1, generator=g, device=dev)
+        orc = OracleAdapter(st, shp.D, shots=shp.shots)
+        f, y = wl["f_train"].to(dev), wl["y_train"].to(dev)
+        nb = f.shape[0] // shp.B
+
+        def one(it):
+            lo = (it % nb) * shp.B
+            return orc.step(f[lo:lo + shp.B], y[lo:lo + shp.B], torch.randn(shp.C, shp.T, S, generator=g, device=dev))
+
+        for it in range(3):
+            one(it)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(steps):
+            one(3 + it)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "kind": "port",
+                "sample": f"{steps} steps of the oracle restatement of the reference step, torch {torch.__version__} eager on the same GPU, "
+                          "TF32 matmuls, fp64 Cholesky of K_ZZ via cuSOLVER (loss read back every step, as the reference logs it)"}
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 if __name__ == "__main__":

@@ -13,11 +13,25 @@ from . import gp as ogp
 from . import heads
 
 
+def state_to_device(st: ogp.GPState, device) -> ogp.GPState:
+    """Copy of the oracle state on `device` (bench.py's torch-eager GPU comparator: the same restated reference step, run by
+    torch on the GPU as the reference itself would)."""
+    import copy
+    s2 = copy.deepcopy(st)
+    for k in ("templates", "templates_red", "inducing_points", "var_mean", "chol_var", "f0", "cls_bias", "tmp_bias", "pca_mean", "pca_W"):
+        setattr(s2, k, getattr(s2, k).detach().to(device))
+    for k in ("raw_lengthscale", "raw_outputscale", "raw_variance"):
+        v = getattr(s2.kernel, k)
+        if v is not None:
+            setattr(s2.kernel, k, v.detach().to(device))
+    return s2
+
+
 class OracleAdapter:
     def __init__(self, st: ogp.GPState, D: int, scale=100.0, gp_beta=0.01, l2_lambda=0.5, shots=16, lr=0.01, gp_lr=1e-3,
                  weight_decay=0.0, loss_mode="per_sample"):
         self.st = st
-        self.W = torch.eye(D, requires_grad=True)
+        self.W = torch.eye(D, device=st.templates.device, requires_grad=True)
         self.scale, self.gp_beta, self.l2_lambda, self.shots = scale, gp_beta, l2_lambda, shots
         self.loss_mode = loss_mode
         self.gp_params = [st.inducing_points, st.var_mean, st.chol_var]
