@@ -259,6 +259,21 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                 mbar_wait(&tmem_full[acc], acc_phase);
                 fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+                // EPI_TIP: per-warp class tile [32 rows][32 class slots] (slot index rotated by the row: conflict-free column walks)
+                float* tip_tile = reinterpret_cast<float*>(smem + p.stages * STAGE_BYTES + (warp - 2) * CST_BYTES);
+                int tip_cur = -1, tip_first = 0; float tip_sum = 0.f;
+                if (p.mode == EPI_TIP) {
+                    tip_first = __ldg(p.key_class + min(n_blk * BN, p.N - 1));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(tip_tile)[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __syncwarp();
+                }
+                auto tip_flush = [&](int cls, float sum) {
+                    if (cls < 0 || row >= p.M) return;
+                    const int slot = cls - tip_first;
+                    if (slot >= 0 && slot < 32) tip_tile[lane * 32 + ((slot + lane) & 31)] += sum;
+                    else atomicAdd(p.C + (long long)row * p.ldc + cls, p.tip_alpha * sum);
+                };
 #pragma unroll 1
                 for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
                     const int col0 = n_blk * BN + c0;
@@ -267,23 +282,28 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                     tmem_ld32(taddr + (uint32_t)c0, r);
                     const int ncols = min(32, p.N - col0);
                     if (p.mode == EPI_TIP) {
-                        // cache_logits[b, class(j)] += exp(-beta (1 - aff[b,j])): run-length sums over equal classes (keys are
-                        // sorted by class on the host, so a 32-column chunk flushes only a few atomics per row)
-                        if (row < p.M) {
-                            float* orow = p.C + (long long)row * p.ldc;
-                            int cur = p.key_class[col0];
-                            float sum = 0.f;
-                            const float bl = p.beta * 1.4426950408889634f;
-#pragma unroll 4
-                            for (int j = 0; j < 32; ++j) {
-                                if (j < ncols) {
-                                    const int cls = p.key_class[col0 + j];
-                                    const float e = exp2f(bl * (p.alpha * __uint_as_float(r[j]) - 1.f));
-                                    if (cls != cur) { atomicAdd(orow + cur, p.tip_alpha * sum); cur = cls; sum = 0.f; }
-                                    sum += e;
+                        // cache_logits[b, class(j)] += exp(-beta (1 - aff[b,j])): run-length sums over equal classes, carried across
+                        // the chunks of the tile; a finished run goes to this row's slot of the warp's 32 x 32 class tile in shared
+                        // memory (classes tip_first .. tip_first + 31; keys are sorted by class on the host, so a 256-key tile
+                        // spans few classes) and the tile leaves with 32 row-contiguous reductions after the accumulator is
+                        // released.  Classes outside the window (unsorted keys, 1-shot caches) fall back to a direct atomic.
+                        // The chunk's 32 key classes come from one coalesced load (lane = column); run boundaries become a ballot
+                        // mask, so the element loop carries no memory-dependent branch.
+                        const float bl = p.beta * 1.4426950408889634f;
+                        const int my_cls = (lane < ncols) ? __ldg(p.key_class + col0 + lane) : -2;
+                        const int prev_cls = __shfl_up_sync(0xffffffffu, my_cls, 1);
+                        const unsigned bmask = __ballot_sync(0xffffffffu, lane < ncols && my_cls != (lane == 0 ? tip_cur : prev_cls));
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < ncols) {                             // warp-uniform
+                                float e;
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(bl * (p.alpha * __uint_as_float(r[j]) - 1.f)));
+                                if ((bmask >> j) & 1u) {                 // warp-uniform: a new class starts at column j
+                                    tip_flush(tip_cur, tip_sum);
+                                    tip_cur = __shfl_sync(0xffffffffu, my_cls, j); tip_sum = 0.f;
                                 }
+                                tip_sum += e;
                             }
-                            atomicAdd(orow + cur, p.tip_alpha * sum);
                         }
                     } else if (p.C != nullptr && p.tma_store && !it.atomic) {
                         // stage the 32 x 32 chunk in shared memory in the 128-byte-swizzled layout of the output tensor map
@@ -355,6 +375,19 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (p.mode == EPI_TIP) {
+                    tip_flush(tip_cur, tip_sum);
+                    __syncwarp();
+                    const int row0 = m_blk * BM + q * 32;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {                     // lane = class slot: one contiguous reduction per row
+                        const float v = tip_tile[rr * 32 + ((lane + rr) & 31)];
+                        if (v != 0.f && row0 + rr < p.M)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p.C + (long long)(row0 + rr) * p.ldc + tip_first + lane),
+                                         "f"(p.tip_alpha * v) : "memory");
+                    }
+                    __syncwarp();
+                }
             }
             if (p.mode == EPI_ROWSTATS && row < p.M) {
                 const float cf = 1.0f / run_s;

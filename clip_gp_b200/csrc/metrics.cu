@@ -150,17 +150,41 @@ __global__ void __launch_bounds__(256) ece_hist_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------------
 // AECE: exact prefix sums at rank edges by 5-level (8 bits each) radix select over key40 = conf_bits<<8|correct.
 // Elements with equal key have equal (conf, correct), so a rank cut inside a run of equal keys is exact.
+//
+// Multi-CTA: every CTA histograms its slice of the images into shared memory (warp-aggregated: confidences share their
+// leading bytes, so a plain atomicAdd per element serialises on one or two counters), merges the non-empty counters into the
+// level's global histogram, and after a grid barrier every CTA derives the same digit choice from it.  The grid is at most
+// one CTA per SM, so all CTAs are co-resident and the spin barrier cannot deadlock.
 // ---------------------------------------------------------------------------------------------------
-static constexpr int kQ = 8;  // edges resolved per sweep
+static constexpr int kQ = 10;        // edges resolved per sweep (the default n_bins = 10 has 9 interior edges: one sweep)
+static constexpr int kLevels = 5;
+
+struct AeceBin { unsigned int cnt, cor; unsigned long long fx; };
+struct AeceWs {                      // zero-initialised by the launcher
+    unsigned long long tot_fx, tot_cor;
+    unsigned int barrier, pad[3];
+    // followed by AeceBin hist[sweeps][kLevels][kQ][256]
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& target) {
+    target += gridDim.x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned int v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(1024) aece_select_kernel(const float* __restrict__ conf,
                                                            const uint8_t* __restrict__ correct, int64_t N,
-                                                           const int64_t* __restrict__ edges, int n_bins,
+                                                           const int64_t* __restrict__ edges, int n_bins, AeceWs* ws,
                                                            unsigned long long* out_conf_fx, int64_t* out_correct,
                                                            int64_t* out_count) {
-    __shared__ unsigned int h_cnt[kQ][256];
-    __shared__ unsigned int h_cor[kQ][256];
-    __shared__ unsigned long long h_fx[kQ][256];
+    __shared__ AeceBin h[kQ][256];
     __shared__ unsigned long long q_prefix[kQ], q_fx_less[kQ], slot_prefix[kQ];
     __shared__ long long q_rank[kQ], q_cnt_less[kQ], q_cor_less[kQ];
     __shared__ int q_slot[kQ], q_edge[kQ];
@@ -171,31 +195,37 @@ __global__ void __launch_bounds__(1024) aece_select_kernel(const float* __restri
     __shared__ unsigned long long tot_fx;
     __shared__ unsigned long long tot_cor;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gfirst = (int64_t)blockIdx.x * blockDim.x;         // warp-uniform trip counts: i - lane is the same for a warp
+    AeceBin* ghist = reinterpret_cast<AeceBin*>(ws + 1);
+    unsigned int bar_target = 0;
     if (tid == 0) { tot_fx = 0ull; tot_cor = 0ull; }
     __syncthreads();
     {   // totals (prefix sum at rank N)
         unsigned long long fx = 0ull, cor = 0ull;
-        for (int64_t i = tid; i < N; i += blockDim.x) { fx += conf_to_fx(conf[i]); cor += correct[i]; }
+        for (int64_t i = gfirst + tid; i < N; i += gstride) { fx += conf_to_fx(conf[i]); cor += correct[i]; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             fx += __shfl_xor_sync(0xffffffffu, fx, o);
             cor += __shfl_xor_sync(0xffffffffu, cor, o);
         }
-        if ((tid & 31) == 0) { atomicAdd(&tot_fx, fx); atomicAdd(&tot_cor, cor); }
+        if (lane == 0) { atomicAdd(&tot_fx, fx); atomicAdd(&tot_cor, cor); }
     }
     __syncthreads();
+    if (tid == 0) { atomicAdd(&ws->tot_fx, tot_fx); atomicAdd(&ws->tot_cor, tot_cor); }
+    grid_barrier(&ws->barrier, bar_target);
     if (tid <= n_bins) {
         long long e = edges[tid];
         e = e < 0 ? 0 : (e > N ? N : e);
         e_clamped[tid] = e;
         if (e <= 0) { F_fx[tid] = 0ull; F_cor[tid] = 0; }
-        else if (e >= N) { F_fx[tid] = tot_fx; F_cor[tid] = (long long)tot_cor; }
+        else if (e >= N) { F_fx[tid] = __ldcg(&ws->tot_fx); F_cor[tid] = (long long)__ldcg(&ws->tot_cor); }
     }
     __syncthreads();
 
-    int next_edge = 0;  // uniform across the block (same shared inputs)
-    while (true) {
+    int next_edge = 0;  // uniform across the grid (same inputs)
+    for (int sweep = 0;; ++sweep) {
         // gather up to kQ interior edges that still need a select
         if (tid == 0) {
             int c = 0, k = next_edge;
@@ -213,42 +243,88 @@ __global__ void __launch_bounds__(1024) aece_select_kernel(const float* __restri
         if (nq == 0) break;
         next_edge = scan_pos;
 
-        for (int level = 0; level < 5; ++level) {
+        for (int level = 0; level < kLevels; ++level) {
             const int shift = 32 - 8 * level;
             const int ns = n_slots;
-            for (int i = tid; i < ns * 256; i += blockDim.x) {
-                (&h_cnt[0][0])[i] = 0u; (&h_cor[0][0])[i] = 0u; (&h_fx[0][0])[i] = 0ull;
-            }
+            AeceBin* gl = ghist + ((size_t)sweep * kLevels + level) * kQ * 256;
+            for (int i = tid; i < ns * 256; i += blockDim.x) { (&h[0][0])[i].cnt = 0u; (&h[0][0])[i].cor = 0u; (&h[0][0])[i].fx = 0ull; }
             __syncthreads();
-            for (int64_t i = tid; i < N; i += blockDim.x) {
-                const float cf = conf[i];
-                const unsigned int cr = correct[i];
+            for (int64_t i0 = gfirst + (tid - lane); i0 < N; i0 += gstride) {
+                const int64_t i = i0 + lane;
+                const bool valid = i < N;
+                const float cf = valid ? conf[i] : 0.f;
+                const unsigned int cr = valid ? correct[i] : 0u;
                 const unsigned long long key = ((unsigned long long)__float_as_uint(cf) << 8) | cr;
                 const unsigned long long hi = (level == 0) ? 0ull : (key >> (shift + 8));
                 const int digit = (int)((key >> shift) & 255ull);
-                for (int u = 0; u < ns; ++u) {
-                    if (hi == slot_prefix[u]) {
-                        atomicAdd(&h_cnt[u][digit], 1u);
-                        atomicAdd(&h_cor[u][digit], cr);
-                        atomicAdd(&h_fx[u][digit], conf_to_fx(cf));
+                int slot = -1;
+                for (int u = 0; u < ns; ++u) if (hi == slot_prefix[u]) slot = u;      // the slot prefixes are distinct
+                const bool in = valid && slot >= 0;
+                const unsigned int gid = in ? (unsigned int)(slot * 256 + digit) : (0x80000000u | (unsigned int)lane);
+                const unsigned int m = __match_any_sync(0xffffffffu, gid);
+                if (in) {
+                    const unsigned long long fx = conf_to_fx(cf);                      // <= 2^40: two 20-bit halves sum in 32 bits
+                    const unsigned int scor = __reduce_add_sync(m, cr);
+                    const unsigned int slo = __reduce_add_sync(m, (unsigned int)(fx & 0xFFFFFull));
+                    const unsigned int shi = __reduce_add_sync(m, (unsigned int)(fx >> 20));
+                    if (lane == __ffs(m) - 1) {
+                        atomicAdd(&h[slot][digit].cnt, (unsigned int)__popc(m));
+                        if (scor) atomicAdd(&h[slot][digit].cor, scor);
+                        atomicAdd(&h[slot][digit].fx, ((unsigned long long)shi << 20) + slo);
                     }
                 }
             }
             __syncthreads();
-            if (tid < nq) {
-                const int u = q_slot[tid];
-                const long long r = q_rank[tid];
-                long long cum = 0, cumcor = 0;
-                unsigned long long cumfx = 0ull;
-                int sel = 255;
-                for (int b = 0; b < 256; ++b) {
-                    const long long c = h_cnt[u][b];
-                    if (cum + c > r) { sel = b; break; }
-                    cum += c; cumcor += h_cor[u][b]; cumfx += h_fx[u][b];
+            if (gridDim.x > 1) {
+                for (int i = tid; i < ns * 256; i += blockDim.x) {
+                    const AeceBin v = (&h[0][0])[i];
+                    if (v.cnt) {
+                        atomicAdd(&gl[i].cnt, v.cnt);
+                        if (v.cor) atomicAdd(&gl[i].cor, v.cor);
+                        atomicAdd(&gl[i].fx, v.fx);
+                    }
                 }
-                q_cnt_less[tid] += cum; q_cor_less[tid] += cumcor; q_fx_less[tid] += cumfx;
-                q_rank[tid] = r - cum;
-                q_prefix[tid] = (q_prefix[tid] << 8) | (unsigned long long)sel;
+                grid_barrier(&ws->barrier, bar_target);
+            }
+            if (wid < nq) {                        // one warp per edge: 8 digits per lane, warp scan, the owning lane walks its 8
+                const int u = q_slot[wid];
+                const long long r = q_rank[wid];
+                unsigned int c8[8], o8[8];
+                unsigned long long f8[8];
+                long long csum = 0, osum = 0;
+                unsigned long long fsum = 0ull;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int bidx = u * 256 + lane * 8 + j;
+                    if (gridDim.x > 1) { c8[j] = __ldcg(&gl[bidx].cnt); o8[j] = __ldcg(&gl[bidx].cor); f8[j] = __ldcg(&gl[bidx].fx); }
+                    else { const AeceBin v = (&h[0][0])[bidx]; c8[j] = v.cnt; o8[j] = v.cor; f8[j] = v.fx; }
+                    csum += c8[j]; osum += o8[j]; fsum += f8[j];
+                }
+                long long cinc = csum, oinc = osum;
+                unsigned long long finc = fsum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long c2 = __shfl_up_sync(0xffffffffu, cinc, o), o2 = __shfl_up_sync(0xffffffffu, oinc, o);
+                    const unsigned long long f2 = __shfl_up_sync(0xffffffffu, finc, o);
+                    if (lane >= o) { cinc += c2; oinc += o2; finc += f2; }
+                }
+                const bool mine = (cinc - csum <= r) && (r < cinc);
+                const unsigned int found = __ballot_sync(0xffffffffu, mine);
+                if (mine || (found == 0u && lane == 31)) {
+                    long long cum = mine ? cinc - csum : cinc, cumcor = mine ? oinc - osum : oinc;
+                    unsigned long long cumfx = mine ? finc - fsum : finc;
+                    int sel = 255;
+                    if (mine) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (cum + (long long)c8[j] > r) { sel = lane * 8 + j; break; }
+                            cum += c8[j]; cumcor += o8[j]; cumfx += f8[j];
+                        }
+                    }
+                    q_cnt_less[wid] += cum; q_cor_less[wid] += cumcor; q_fx_less[wid] += cumfx;
+                    q_rank[wid] = r - cum;
+                    q_prefix[wid] = (q_prefix[wid] << 8) | (unsigned long long)sel;
+                }
             }
             __syncthreads();
             if (tid == 0) {   // dedupe prefixes -> histogram slots for the next level
@@ -273,7 +349,7 @@ __global__ void __launch_bounds__(1024) aece_select_kernel(const float* __restri
         }
         __syncthreads();
     }
-    if (tid < n_bins) {
+    if (blockIdx.x == 0 && tid < n_bins) {
         const long long lo = e_clamped[tid], hi = e_clamped[tid + 1];
         if (hi > lo) {
             out_conf_fx[tid] = F_fx[tid + 1] - F_fx[tid];
@@ -342,6 +418,18 @@ extern "C" int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64
     CLIPGP_REQUIRE(n_bins >= 1 && n_bins < CLIPGP_MAX_BINS, "aece_bins: n_bins must be in [1,%d)", CLIPGP_MAX_BINS);
     CLIPGP_REQUIRE(edges && out_conf_fx && out_correct && out_count, "aece_bins: NULL pointer");
     CLIPGP_REQUIRE(N == 0 || (conf && correct), "aece_bins: NULL input");
-    aece_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(conf, correct, N, edges, n_bins, out_conf_fx, out_correct, out_count);
-    return check_launch("aece_select_kernel");
+    // one CTA per 4096 images, at most one per SM (co-resident: the kernel synchronises the grid); stream-ordered zeroed workspace
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (N + 4095) / 4096;
+    blocks = blocks < 1 ? 1 : (blocks > (int64_t)num_sms() ? (int64_t)num_sms() : blocks);
+    const int sweeps = (n_bins - 1 + kQ - 1) / kQ + 1;
+    const size_t ws_bytes = sizeof(AeceWs) + (size_t)sweeps * kLevels * kQ * 256 * sizeof(AeceBin);
+    void* ws = nullptr;
+    CLIPGP_CUDA(cudaMallocAsync(&ws, ws_bytes, st));
+    CLIPGP_CUDA(cudaMemsetAsync(ws, 0, blocks > 1 ? ws_bytes : sizeof(AeceWs), st));
+    aece_select_kernel<<<(unsigned)blocks, 1024, 0, st>>>(conf, correct, N, edges, n_bins, reinterpret_cast<AeceWs*>(ws), out_conf_fx,
+                                                         out_correct, out_count);
+    const int rc = check_launch("aece_select_kernel");
+    CLIPGP_CUDA(cudaFreeAsync(ws, st));
+    return rc;
 }

@@ -101,16 +101,24 @@ def aece_edges(n: int, n_bins: int) -> torch.Tensor:
     return edges
 
 
+_EDGE_CACHE: Dict[tuple, tuple] = {}
+
+
 def aece_pass(conf: torch.Tensor, correct: torch.Tensor, n_bins: int = 10):
     """Exact equal-count binning of (conf, correct) on the device.  Returns (edges CPU, out[3, nb] int64 device)
     with rows conf_fx, correct, count.  No host sync."""
     dev = _lib.require_cuda(conf, correct)
     lib = _lib.load()
     n = conf.numel()
-    edges = aece_edges(n, n_bins)
+    key = (n, n_bins, str(dev))
+    if key not in _EDGE_CACHE:                              # the rank edges depend on (N, n_bins) only: one H2D copy per shape
+        if len(_EDGE_CACHE) > 64:
+            _EDGE_CACHE.clear()
+        e = aece_edges(n, n_bins)
+        _EDGE_CACHE[key] = (e, e.to(dev))
+    edges, edges_d = _EDGE_CACHE[key]
     nb = edges.numel() - 1
     out = torch.zeros(3, nb, dtype=torch.int64, device=dev)
-    edges_d = edges.to(dev)
     with torch.cuda.device(dev):
         _lib.check(lib.clipgp_aece_bins(_lib.ptr(conf), _lib.ptr(correct), n, _lib.ptr(edges_d), nb, out[0].data_ptr(),
                                         out[1].data_ptr(), out[2].data_ptr(), _lib.stream_ptr(dev)), "clipgp_aece_bins")

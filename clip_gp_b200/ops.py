@@ -290,8 +290,10 @@ class TipCacheLogits(torch.autograd.Function):
     Differentiable w.r.t. the cache keys (Tip-Adapter-F's nn.Linear weight) and clip_logits."""
 
     @staticmethod
-    def forward(ctx, feats, keys, labels_tr, clip_logits, beta: float, alpha: float, num_classes: int):
+    def forward(ctx, feats, keys, labels_tr, clip_logits, beta: float, alpha: float, num_classes: int, precision: str = "fp32"):
         dev = _lib.require_cuda(feats, keys, labels_tr)
+        if precision not in ("fp32", "bf16x3", "bf16"):
+            raise ValueError(f"tip_logits: unknown precision {precision!r}")
         lib = _lib.load()
         feats, keys = _c(feats), _c(keys)
         labels_tr = labels_tr.to(torch.int64).contiguous()
@@ -301,19 +303,26 @@ class TipCacheLogits(torch.autograd.Function):
         aff = torch.empty(B, N_tr, dtype=torch.float32, device=dev)
         out = torch.empty(B, num_classes, dtype=torch.float32, device=dev)
         if B and N_tr:
-            _gemm(feats, D, 1, keys, 1, D, aff, B, N_tr, D, 1.0)
+            if precision == "fp32" or D % 8:
+                precision = "fp32"
+                _gemm(feats, D, 1, keys, 1, D, aff, B, N_tr, D, 1.0)
+            else:       # tcgen05 affinity GEMM on bf16 / split-bf16 operands (the key matrix is re-cast every step: it is the trainable weight)
+                from . import tc
+                split = precision == "bf16x3"
+                tc.gemm_store(tc.cast_bf16(feats, tc.SPLIT_A if split else tc.PLAIN), tc.cast_bf16(keys, tc.SPLIT_B if split else tc.PLAIN),
+                              1.0, out=aff, split_k=True)
         with torch.cuda.device(dev):
             _lib.check(lib.clipgp_tip_forward(aff.data_ptr(), N_tr, labels_tr.data_ptr(), B, N_tr, num_classes, float(beta), float(alpha),
                                               _lib.ptr(clip_logits), num_classes, out.data_ptr(), num_classes, 1, _lib.stream_ptr(dev)),
                        "clipgp_tip_forward")
         ctx.save_for_backward(aff, feats, labels_tr)
-        ctx.consts = (float(beta), float(alpha))
+        ctx.consts = (float(beta), float(alpha), precision)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         e, feats, labels_tr = ctx.saved_tensors
-        beta, alpha = ctx.consts
+        beta, alpha, precision = ctx.consts
         dev = e.device
         dout = _c(dout)
         B, N_tr = e.shape
@@ -325,13 +334,53 @@ class TipCacheLogits(torch.autograd.Function):
                 _lib.check(_lib.load().clipgp_tip_backward(G.data_ptr(), N_tr, labels_tr.data_ptr(), B, N_tr, dout.data_ptr(), dout.shape[1],
                                                            beta, alpha, _lib.stream_ptr(dev)), "clipgp_tip_backward")
             dkeys = torch.empty(N_tr, D, dtype=torch.float32, device=dev)
-            _gemm(G, 1, N_tr, feats, D, 1, dkeys, N_tr, D, B, 1.0)      # dkeys = G^T f
+            if precision == "fp32":
+                _gemm(G, 1, N_tr, feats, D, 1, dkeys, N_tr, D, B, 1.0)      # dkeys = G^T f
+            else:       # K-major operands of the contraction over the batch: G^T [N_tr, B] and f^T [D, B]
+                from . import tc
+                split = precision == "bf16x3"
+                tc.gemm_store(tc.cast_bf16_transpose(G, tc.SPLIT_A if split else tc.PLAIN),
+                              tc.cast_bf16_transpose(feats, tc.SPLIT_B if split else tc.PLAIN), 1.0, out=dkeys, split_k=True)
         dclip = dout if ctx.needs_input_grad[3] else None
-        return None, dkeys, None, dclip, None, None, None
+        return None, dkeys, None, dclip, None, None, None, None
 
 
-def tip_logits(feats, keys, labels_tr, clip_logits, beta: float, alpha: float, num_classes: int):
-    return TipCacheLogits.apply(feats, keys, labels_tr, clip_logits, beta, alpha, num_classes)
+@torch.no_grad()
+def tip_affinity(feats, keys, precision: str = "fp32") -> torch.Tensor:
+    """aff = feats @ keys^T [B, N_tr] (tip_adapter.py:69), materialised once so that a (beta, alpha) grid can re-use it."""
+    dev = _lib.require_cuda(feats, keys)
+    feats, keys = _c(feats), _c(keys)
+    B, D = feats.shape
+    N_tr = keys.shape[0]
+    aff = torch.empty(B, N_tr, dtype=torch.float32, device=dev)
+    if B and N_tr:
+        if precision == "fp32" or D % 8:
+            _gemm(feats, D, 1, keys, 1, D, aff, B, N_tr, D, 1.0)
+        else:
+            from . import tc
+            split = precision == "bf16x3"
+            tc.gemm_store(tc.cast_bf16(feats, tc.SPLIT_A if split else tc.PLAIN), tc.cast_bf16(keys, tc.SPLIT_B if split else tc.PLAIN), 1.0, out=aff)
+    return aff
+
+
+@torch.no_grad()
+def tip_logits_from_affinity(aff, labels_tr, clip_logits, beta: float, alpha: float, num_classes: int) -> torch.Tensor:
+    """clip_logits + alpha * exp(-(beta - beta * aff)) @ one_hot(labels_tr) from a saved affinity (left untouched)."""
+    dev = _lib.require_cuda(aff, labels_tr)
+    B, N_tr = aff.shape
+    labels_tr = labels_tr.to(torch.int64).contiguous()
+    clip_logits = _c(clip_logits) if clip_logits is not None else None
+    out = torch.empty(B, num_classes, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().clipgp_tip_forward(aff.data_ptr(), aff.stride(0), labels_tr.data_ptr(), B, N_tr, num_classes, float(beta),
+                                                  float(alpha), _lib.ptr(clip_logits), num_classes, out.data_ptr(), num_classes, 0,
+                                                  _lib.stream_ptr(dev)), "clipgp_tip_forward")
+    return out
+
+
+def tip_logits(feats, keys, labels_tr, clip_logits, beta: float, alpha: float, num_classes: int, precision: str = "fp32"):
+    """precision: "fp32" (FFMA GEMMs, exact comparator), "bf16x3" (tcgen05 on split-bf16 operands, fp32-grade products) or "bf16"."""
+    return TipCacheLogits.apply(feats, keys, labels_tr, clip_logits, beta, alpha, num_classes, precision)
 
 
 # ----------------------------------------------------------------------------------------------- GP setup (SURVEY 8f f2)

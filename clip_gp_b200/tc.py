@@ -23,6 +23,21 @@ def cast_bf16(x: torch.Tensor, mode: int = PLAIN) -> torch.Tensor:
     return out
 
 
+def cast_bf16_transpose(x: torch.Tensor, mode: int = PLAIN) -> torch.Tensor:
+    """fp32 [R,K] -> bf16 [K, Rp] (or the split [K, 3*Rp] layouts), Rp = R padded to 8: the K-major operand of a contraction over R."""
+    dev = _lib.require_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        x = x.float().contiguous()
+    R, K = x.shape
+    Rp = (R + 7) // 8 * 8
+    out = torch.zeros(K, Rp * (3 if mode else 1), dtype=torch.bfloat16, device=dev) if Rp != R else \
+        torch.empty(K, Rp * (3 if mode else 1), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().clipgp_cast_bf16_transpose(x.data_ptr(), R, K, x.stride(0), out.data_ptr(), out.stride(0), Rp, mode,
+                                                          _lib.stream_ptr(dev)), "clipgp_cast_bf16_transpose")
+    return out
+
+
 def _pad8(v: int) -> int:
     return (v + 7) // 8 * 8
 

@@ -374,6 +374,7 @@ class TipAdapterTrainer(BaseTrainer, _GPInitMixin):
         f_tr = ops.row_normalize(self.features_train)
         self.cache_keys, self.cache_labels = heads.tip_build_cache(f_tr.detach(), self.labels_train)
         self.best_beta, self.best_alpha = float(getattr(a, "tip_adapter_init_beta", 2.0)), float(getattr(a, "tip_adapter_init_alpha", 20.0))
+        prec = str(getattr(a, "clipgp_precision", "bf16x3"))                 # GEMM path of the affinity and key-gradient contractions
         if bool(getattr(a, "tip_adapter_trainable", False)):                 # Tip-Adapter-F, tip_adapter.py:227-296
             keys = torch.nn.Parameter(self.cache_keys.clone())
             opt = torch.optim.AdamW([keys], lr=float(getattr(a, "tip_adapter_lr", 1e-3)), eps=float(getattr(a, "tip_adapter_eps", 1e-4)))
@@ -383,7 +384,8 @@ class TipAdapterTrainer(BaseTrainer, _GPInitMixin):
             for self.epoch in range(epochs):
                 for feats, labels in self._epoch_batches():
                     f_hat = ops.row_normalize(feats)
-                    tip = ops.tip_logits(f_hat, keys, self.cache_labels, self._clip_logits(f_hat).detach(), self.best_beta, self.best_alpha, self.num_classes)
+                    tip = ops.tip_logits(f_hat, keys, self.cache_labels, self._clip_logits(f_hat).detach(), self.best_beta, self.best_alpha,
+                                         self.num_classes, prec)
                     loss = ops.cross_entropy(tip, labels)
                     opt.zero_grad()
                     loss.backward()
@@ -394,6 +396,6 @@ class TipAdapterTrainer(BaseTrainer, _GPInitMixin):
             fv = ops.row_normalize(self.dm.features_val.to(self.device).float())
             yv = self.dm.labels_val.to(self.device)
             self.best_beta, self.best_alpha, _ = heads.tip_search(fv, yv, self.cache_keys, self.cache_labels, self._clip_logits(fv), self.num_classes,
-                                                                  self.best_beta, self.best_alpha)
+                                                                  self.best_beta, self.best_alpha, precision=prec)
         self._tip_adapter_best_beta, self._tip_adapter_best_alpha = self.best_beta, self.best_alpha
         return self.test()

@@ -74,6 +74,50 @@ def test_tip_cache_logits_forward_backward(B, N_tr, C, D):
     assert rel_err(o3, ref) < 1e-3
 
 
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 3e-2)])
+def test_tip_cache_logits_tensor_core_precisions(precision, tol):
+    """Tip-Adapter-F step on the tcgen05 GEMMs (affinity and key gradient) against the oracle; bf16 carries a stated tolerance."""
+    g = torch.Generator().manual_seed(11)
+    B, N_tr, C, D = 128, 1600, 100, 256
+    mu = torch.randn(C, D, generator=g)
+    lab = torch.arange(C).repeat_interleave(16)
+    keys = F.normalize(mu[lab] + 2.0 * torch.randn(N_tr, D, generator=g), dim=-1)
+    yb = torch.randint(0, C, (B,), generator=g)
+    f = F.normalize(mu[yb] + 2.0 * torch.randn(B, D, generator=g), dim=-1)
+    clip = 5.0 * torch.randn(B, C, generator=g)
+    dout = torch.randn(B, C, generator=g)
+    kr = keys.clone().requires_grad_(True)
+    ref = oh.tip_logits(f, kr, oh.tip_cache_vals(lab, C), clip, 2.0, 20.0)
+    ref.backward(dout)
+    kd = keys.cuda().requires_grad_(True)
+    out = ops.tip_logits(f.cuda(), kd, lab.cuda(), clip.cuda(), 2.0, 20.0, C, precision)
+    out.backward(dout.cuda())
+    assert rel_err(out, ref) < tol and rel_err(kd.grad, kr.grad) < tol
+    with pytest.raises(ValueError):
+        ops.tip_logits(f.cuda(), kd, lab.cuda(), clip.cuda(), 2.0, 20.0, C, "fp8")
+
+
+@pytest.mark.parametrize("N_tr,C,sort", [(600, 300, True), (777, 40, False), (4096, 4096, True)])
+def test_tip_fused_epilogue_class_windows(N_tr, C, sort):
+    """Fused tcgen05 Tip epilogue outside its fast case: more than 32 classes per 256-key tile (few-shot caches) and unsorted keys
+    go through the direct-reduction fallback; results equal the one-hot formulation."""
+    from clip_gp_b200 import _lib
+    g = torch.Generator().manual_seed(N_tr)
+    B, D = 150, 128
+    lab = torch.randint(0, C, (N_tr,), generator=g) if C < N_tr else torch.arange(C)
+    if sort:
+        lab = lab.sort().values
+    keys = F.normalize(torch.randn(N_tr, D, generator=g), dim=-1)
+    f = F.normalize(torch.randn(B, D, generator=g), dim=-1)
+    clip = 5.0 * torch.randn(B, C, generator=g)
+    ref = oh.tip_logits(f, keys, oh.tip_cache_vals(lab, C), clip, 5.0, 10.0)
+    o3 = clip.cuda().clone()
+    fa, kb, li = tc.cast_bf16(f.cuda(), tc.SPLIT_A), tc.cast_bf16(keys.cuda(), tc.SPLIT_B), lab.to(torch.int32).cuda().contiguous()
+    _lib.check(_lib.load().clipgp_tc_tip_logits(fa.data_ptr(), B, kb.data_ptr(), N_tr, 3 * D, li.data_ptr(), 5.0, 10.0, o3.data_ptr(), C,
+                                                _lib.stream_ptr(o3.device)), "clipgp_tc_tip_logits")
+    assert rel_err(o3, ref) < 1e-3
+
+
 def test_tip_hyperparameter_search_matches_oracle():
     from clip_gp_b200 import heads
     g = torch.Generator().manual_seed(7)
@@ -87,6 +131,9 @@ def test_tip_hyperparameter_search_matches_oracle():
     bb, ba, acc = oh.tip_search(f, y, keys, oh.tip_cache_vals(lab, C), clip, 2.0, 20.0)
     b2, a2, acc2 = heads.tip_search(f.cuda(), y.cuda(), keys.cuda(), lab.cuda(), clip.cuda(), C, 2.0, 20.0)
     assert (b2, a2) == (bb, ba) and acc2 == pytest.approx(acc)
+    # image chunks + tensor-core affinity: same arg-max pair (the grid shares ONE affinity per chunk)
+    b3, a3, acc3 = heads.tip_search(f.cuda(), y.cuda(), keys.cuda(), lab.cuda(), clip.cuda(), C, 2.0, 20.0, precision="bf16x3", chunk=64)
+    assert (b3, a3) == (bb, ba) and acc3 == pytest.approx(acc)
 
 
 @pytest.mark.parametrize("method", ["uniform", "val_weighted", "top3", "minmax"])

@@ -82,6 +82,25 @@ def test_aece_is_the_sorted_partition():
         assert float(o[0, i]) / gm.FX_SCALE == pytest.approx(float(sc[lo:hi].sum().item()), rel=1e-9)
 
 
+@pytest.mark.parametrize("N,n_bins", [(1000003, 25), (4097, 10), (37, 10)])
+def test_aece_multi_cta_multi_sweep(N, n_bins):
+    """Grid-wide radix select: many CTAs, more interior edges than one sweep resolves, saturated confidences (conf == 1 runs)."""
+    g = torch.Generator().manual_seed(N)
+    conf = torch.rand(N, generator=g).pow(0.05)           # piled up against 1.0 like real softmax confidences
+    conf[torch.rand(N, generator=g) < 0.3] = 1.0
+    conf = conf.cuda()
+    correct = (torch.rand(N, generator=g) < 0.7).to(torch.uint8).cuda()
+    edges, out = gm.aece_pass(conf, correct, n_bins)
+    order = torch.argsort(conf.double() * 4 + correct.double() * 1e-9)
+    sc, sa = conf[order].double(), correct[order].double()
+    o = out.cpu()
+    for i in range(edges.numel() - 1):
+        lo, hi = int(edges[i]), int(edges[i + 1])
+        assert int(o[2, i]) == hi - lo
+        assert int(o[1, i]) == int(sa[lo:hi].sum().item())
+        assert float(o[0, i]) / gm.FX_SCALE == pytest.approx(float(sc[lo:hi].sum().item()), rel=1e-9, abs=1e-9)
+
+
 def test_counters_are_shard_invariant():
     g = torch.Generator().manual_seed(9)
     lg = 3.0 * torch.randn(3001, 100, generator=g).cuda()
