@@ -62,8 +62,9 @@ _SIGNATURES = {
                                                  C.c_void_p, C.c_void_p]),
     "clipgp_ece_hist": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "clipgp_aece_workspace_bytes": (c_i64, [C.c_int]),
     "clipgp_aece_bins": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_gp_smem_bytes": (c_i64, [c_i64, c_i64, c_i64, C.c_int]),
     "clipgp_gp_forward": (C.c_int, [C.POINTER(GpArgs), C.c_void_p]),
     "clipgp_gp_warp_path_ok": (C.c_int, [c_i64, c_i64, c_i64]),

@@ -155,6 +155,16 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
 
 __device__ __forceinline__ unsigned long long conf_to_fx(float c) { return (unsigned long long)((double)c * 1099511627776.0); }
 
+// EPI_TIP: a finished run of equal-class keys leaves the registers: into the row's slot of the warp's class tile when the class
+// lies in the tile's 32-class window, else straight to the output row.  Out of line on purpose: it is called from 33 places of
+// the unrolled epilogue and runs two or three times per 32 columns.
+__device__ __noinline__ void tip_flush_run(float* tip_tile, int lane, int cls, int tip_first, float sum, float* orow, float tip_alpha) {
+    if (cls < 0 || orow == nullptr) return;
+    const int slot = cls - tip_first;
+    if (slot >= 0 && slot < 32) tip_tile[lane * 32 + ((slot + lane) & 31)] += sum;
+    else atomicAdd(orow + cls, tip_alpha * sum);
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b,
@@ -268,12 +278,6 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                     for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(tip_tile)[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     __syncwarp();
                 }
-                auto tip_flush = [&](int cls, float sum) {
-                    if (cls < 0 || row >= p.M) return;
-                    const int slot = cls - tip_first;
-                    if (slot >= 0 && slot < 32) tip_tile[lane * 32 + ((slot + lane) & 31)] += sum;
-                    else atomicAdd(p.C + (long long)row * p.ldc + cls, p.tip_alpha * sum);
-                };
 #pragma unroll 1
                 for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
                     const int col0 = n_blk * BN + c0;
@@ -289,20 +293,30 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                         // released.  Classes outside the window (unsorted keys, 1-shot caches) fall back to a direct atomic.
                         // The chunk's 32 key classes come from one coalesced load (lane = column); run boundaries become a ballot
                         // mask, so the element loop carries no memory-dependent branch.
-                        const float bl = p.beta * 1.4426950408889634f;
+                        const float bl = p.beta * 1.4426950408889634f, bla = bl * p.alpha;
                         const int my_cls = (lane < ncols) ? __ldg(p.key_class + col0 + lane) : -2;
                         const int prev_cls = __shfl_up_sync(0xffffffffu, my_cls, 1);
                         const unsigned bmask = __ballot_sync(0xffffffffu, lane < ncols && my_cls != (lane == 0 ? tip_cur : prev_cls));
+                        float* orow = row < p.M ? p.C + (long long)row * p.ldc : nullptr;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < ncols) {                             // warp-uniform
-                                float e;
-                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(bl * (p.alpha * __uint_as_float(r[j]) - 1.f)));
-                                if ((bmask >> j) & 1u) {                 // warp-uniform: a new class starts at column j
-                                    tip_flush(tip_cur, tip_sum);
-                                    tip_cur = __shfl_sync(0xffffffffu, my_cls, j); tip_sum = 0.f;
+                        for (int j4 = 0; j4 < 32; j4 += 4) {             // four columns at a time: a group without a boundary is 4 FFMA + 4 EX2 + 4 FADD
+                            float e4[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e4[u]) : "f"(fmaf(bla, __uint_as_float(r[j4 + u]), -bl)));
+                                if (ncols < 32 && j4 + u >= ncols) e4[u] = 0.f;
+                            }
+                            const unsigned bits = (bmask >> j4) & 0xFu;  // warp-uniform
+                            if (bits == 0u) tip_sum += (e4[0] + e4[1]) + (e4[2] + e4[3]);
+                            else {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if ((bits >> u) & 1u) {               // a new class starts at column j4 + u
+                                        tip_flush_run(tip_tile, lane, tip_cur, tip_first, tip_sum, orow, p.tip_alpha);
+                                        tip_cur = __shfl_sync(0xffffffffu, my_cls, j4 + u); tip_sum = 0.f;
+                                    }
+                                    tip_sum += e4[u];
                                 }
-                                tip_sum += e;
                             }
                         }
                     } else if (p.C != nullptr && p.tma_store && !it.atomic) {
@@ -376,7 +390,7 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 if (p.mode == EPI_TIP) {
-                    tip_flush(tip_cur, tip_sum);
+                    tip_flush_run(tip_tile, lane, tip_cur, tip_first, tip_sum, row < p.M ? p.C + (long long)row * p.ldc : nullptr, p.tip_alpha);
                     __syncwarp();
                     const int row0 = m_blk * BM + q * 32;
 #pragma unroll 4

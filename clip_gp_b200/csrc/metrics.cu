@@ -74,6 +74,35 @@ __global__ void __launch_bounds__(256) calib_rows_kernel(const float* __restrict
         const float* x = logits + row * ld;
         float m = -FLT_MAX;
         int am = 0x7fffffff;
+        float s = 0.f;
+        if (VEC && C <= 1024) {
+            // the whole row in registers: eight 16-byte loads in flight per lane, one pass over HBM, sum-exp from registers
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            const int C4 = (int)(C >> 2);
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = lane + 32 * u;
+                v[u] = (j < C4) ? __ldg(x4 + j) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int base = (lane + 32 * u) << 2;
+                if (v[u].x > m) { m = v[u].x; am = base; }
+                if (v[u].y > m) { m = v[u].y; am = base + 1; }
+                if (v[u].z > m) { m = v[u].z; am = base + 2; }
+                if (v[u].w > m) { m = v[u].w; am = base + 3; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float om = __shfl_xor_sync(0xffffffffu, m, o);
+                int oa = __shfl_xor_sync(0xffffffffu, am, o);
+                if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (lane + 32 * u < C4) s += expf(v[u].x - m) + expf(v[u].y - m) + expf(v[u].z - m) + expf(v[u].w - m);
+        } else {
         if (VEC) {
             const float4* x4 = reinterpret_cast<const float4*>(x);
             const int C4 = (int)(C >> 2);
@@ -97,7 +126,6 @@ __global__ void __launch_bounds__(256) calib_rows_kernel(const float* __restrict
             int oa = __shfl_xor_sync(0xffffffffu, am, o);
             if (om > m || (om == m && oa < am)) { m = om; am = oa; }
         }
-        float s = 0.f;
         if (VEC) {
             const float4* x4 = reinterpret_cast<const float4*>(x);
             const int C4 = (int)(C >> 2);
@@ -107,6 +135,7 @@ __global__ void __launch_bounds__(256) calib_rows_kernel(const float* __restrict
             }
         } else {
             for (int j = lane; j < C; j += 32) s += expf(__ldg(x + j) - m);
+        }
         }
         s = warp_sum(s);
         if (lane == 0) {
@@ -412,8 +441,16 @@ extern "C" int clipgp_ece_hist(const float* conf, const uint8_t* correct, int64_
     return check_launch("ece_hist_kernel");
 }
 
+static size_t aece_ws_bytes(int n_bins) {
+    const int sweeps = (n_bins - 1 + kQ - 1) / kQ + 1;
+    return sizeof(AeceWs) + (size_t)sweeps * kLevels * kQ * 256 * sizeof(AeceBin);
+}
+
+extern "C" int64_t clipgp_aece_workspace_bytes(int n_bins) { return (int64_t)aece_ws_bytes(n_bins < 1 ? 1 : n_bins); }
+
 extern "C" int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64_t N, const int64_t* edges, int n_bins,
-                                unsigned long long* out_conf_fx, int64_t* out_correct, int64_t* out_count, void* stream) {
+                                unsigned long long* out_conf_fx, int64_t* out_correct, int64_t* out_count, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
     CLIPGP_REQUIRE(N >= 0, "aece_bins: N < 0");
     CLIPGP_REQUIRE(n_bins >= 1 && n_bins < CLIPGP_MAX_BINS, "aece_bins: n_bins must be in [1,%d)", CLIPGP_MAX_BINS);
     CLIPGP_REQUIRE(edges && out_conf_fx && out_correct && out_count, "aece_bins: NULL pointer");
@@ -422,14 +459,15 @@ extern "C" int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64
     cudaStream_t st = (cudaStream_t)stream;
     int64_t blocks = (N + 4095) / 4096;
     blocks = blocks < 1 ? 1 : (blocks > (int64_t)num_sms() ? (int64_t)num_sms() : blocks);
-    const int sweeps = (n_bins - 1 + kQ - 1) / kQ + 1;
-    const size_t ws_bytes = sizeof(AeceWs) + (size_t)sweeps * kLevels * kQ * 256 * sizeof(AeceBin);
-    void* ws = nullptr;
-    CLIPGP_CUDA(cudaMallocAsync(&ws, ws_bytes, st));
+    const size_t ws_bytes = aece_ws_bytes(n_bins);
+    void* ws = workspace;
+    CLIPGP_REQUIRE(ws == nullptr || (size_t)workspace_bytes >= ws_bytes, "aece_bins: workspace too small (%lld < %lld bytes)",
+                   (long long)workspace_bytes, (long long)ws_bytes);
+    if (ws == nullptr) CLIPGP_CUDA(cudaMallocAsync(&ws, ws_bytes, st));
     CLIPGP_CUDA(cudaMemsetAsync(ws, 0, blocks > 1 ? ws_bytes : sizeof(AeceWs), st));
     aece_select_kernel<<<(unsigned)blocks, 1024, 0, st>>>(conf, correct, N, edges, n_bins, reinterpret_cast<AeceWs*>(ws), out_conf_fx,
                                                          out_correct, out_count);
     const int rc = check_launch("aece_select_kernel");
-    CLIPGP_CUDA(cudaFreeAsync(ws, st));
+    if (workspace == nullptr) CLIPGP_CUDA(cudaFreeAsync(ws, st));
     return rc;
 }

@@ -119,9 +119,11 @@ def aece_pass(conf: torch.Tensor, correct: torch.Tensor, n_bins: int = 10):
     edges, edges_d = _EDGE_CACHE[key]
     nb = edges.numel() - 1
     out = torch.zeros(3, nb, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(lib.clipgp_aece_workspace_bytes(nb)), dtype=torch.uint8, device=dev)     # torch's caching allocator: no driver call
     with torch.cuda.device(dev):
         _lib.check(lib.clipgp_aece_bins(_lib.ptr(conf), _lib.ptr(correct), n, _lib.ptr(edges_d), nb, out[0].data_ptr(),
-                                        out[1].data_ptr(), out[2].data_ptr(), _lib.stream_ptr(dev)), "clipgp_aece_bins")
+                                        out[1].data_ptr(), out[2].data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
+                   "clipgp_aece_bins")
     return edges, out
 
 

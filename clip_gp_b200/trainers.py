@@ -376,22 +376,22 @@ class TipAdapterTrainer(BaseTrainer, _GPInitMixin):
         self.best_beta, self.best_alpha = float(getattr(a, "tip_adapter_init_beta", 2.0)), float(getattr(a, "tip_adapter_init_alpha", 20.0))
         prec = str(getattr(a, "clipgp_precision", "bf16x3"))                 # GEMM path of the affinity and key-gradient contractions
         if bool(getattr(a, "tip_adapter_trainable", False)):                 # Tip-Adapter-F, tip_adapter.py:227-296
-            keys = torch.nn.Parameter(self.cache_keys.clone())
-            opt = torch.optim.AdamW([keys], lr=float(getattr(a, "tip_adapter_lr", 1e-3)), eps=float(getattr(a, "tip_adapter_eps", 1e-4)))
             epochs = int(getattr(a, "tip_adapter_epochs", 20))
             nb = max(1, self.features_train.shape[0] // min(self.batch_size, self.features_train.shape[0]))
-            sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, epochs * nb)
-            for self.epoch in range(epochs):
-                for feats, labels in self._epoch_batches():
-                    f_hat = ops.row_normalize(feats)
-                    tip = ops.tip_logits(f_hat, keys, self.cache_labels, self._clip_logits(f_hat).detach(), self.best_beta, self.best_alpha,
-                                         self.num_classes, prec)
-                    loss = ops.cross_entropy(tip, labels)
-                    opt.zero_grad()
-                    loss.backward()
-                    opt.step()
-                    sched.step()
-            self.cache_keys = keys.detach()
+            # the step runs in the fused engine (tip_engine.py): AdamW(lr, eps) with torch's default weight decay and the per-step
+            # CosineAnnealingLR over epochs * len(loader) steps (tip_adapter.py:231-235).  The reference's "best epoch" bookkeeping
+            # keeps a reference to the live state_dict (:289-292), i.e. the final weights are always the last epoch's: same here.
+            from .tip_engine import TipAdapterEngine
+            eng = TipAdapterEngine(self.cache_keys, self.cache_labels, self.num_classes, min(self.batch_size, self.features_train.shape[0]),
+                                   self.best_beta, self.best_alpha, lr=float(getattr(a, "tip_adapter_lr", 1e-3)),
+                                   eps=float(getattr(a, "tip_adapter_eps", 1e-4)), total_steps=epochs * nb, precision=prec)
+            with torch.no_grad():
+                for self.epoch in range(epochs):
+                    for feats, labels in self._epoch_batches():
+                        f_hat = ops.row_normalize(feats)
+                        eng.train_step(f_hat, self._clip_logits(f_hat), labels)
+            self.tip_engine = eng
+            self.cache_keys = eng.keys
         if self.dm.features_val is not None:                                  # tip_adapter.py:298-304
             fv = ops.row_normalize(self.dm.features_val.to(self.device).float())
             yv = self.dm.labels_val.to(self.device)

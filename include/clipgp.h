@@ -65,9 +65,13 @@ int clipgp_ece_hist(const float* conf, const uint8_t* correct, int64_t N, const 
  * (conf_bits<<8 | correct), then prefix sums at those ranks.
  *   edges [n_bins+1] int64 DEVICE (torch.linspace(0,N,n_bins+1).round().long(), edges[0]=0, edges[-1]=N)
  *   out_conf_fx [n_bins] uint64 (2^-40 fixed point), out_correct [n_bins] int64, out_count [n_bins] int64
- *   — overwritten.  Single CTA; intended for N up to a few million. */
+ *   — overwritten.  One CTA per 4096 images (at most one per SM) with grid-wide barriers between the levels; the per-level
+ *   histograms live in `workspace` (device, >= clipgp_aece_workspace_bytes(n_bins) bytes, contents irrelevant on entry).
+ *   workspace == NULL: a stream-ordered allocation (cudaMallocAsync / cudaFreeAsync) is made for the call. */
+int64_t clipgp_aece_workspace_bytes(int n_bins);
 int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64_t N, const int64_t* edges, int n_bins,
-                     unsigned long long* out_conf_fx, int64_t* out_correct, int64_t* out_count, void* stream);
+                     unsigned long long* out_conf_fx, int64_t* out_correct, int64_t* out_count, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 
 /* ================================================================================================
  * GP template weighter — trainers/gp_template_weigher.py:166-222 + gpytorch VariationalStrategy

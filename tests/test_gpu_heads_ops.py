@@ -118,6 +118,37 @@ def test_tip_fused_epilogue_class_windows(N_tr, C, sort):
     assert rel_err(o3, ref) < 1e-3
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16x3", 1e-3)])
+def test_tip_engine_matches_reference_loop(precision, tol):
+    """TipAdapterEngine (fused, graph-captured Tip-Adapter-F step) against the reference formulation on the CPU: nn.Linear keys,
+    AdamW(lr, eps=1e-4), per-step CosineAnnealingLR (tip_adapter.py:229-269), several steps incl. a smaller last batch."""
+    from clip_gp_b200.tip_engine import TipAdapterEngine
+    g = torch.Generator().manual_seed(21)
+    N_tr, C, D, steps = 320, 20, 64, 5
+    mu = torch.randn(C, D, generator=g)
+    lab = torch.arange(C).repeat_interleave(16)
+    keys = F.normalize(mu[lab] + 2.0 * torch.randn(N_tr, D, generator=g), dim=-1)
+    batches = []
+    for i in range(steps):
+        B = 48 if i != 3 else 24
+        yb = torch.randint(0, C, (B,), generator=g)
+        f = F.normalize(mu[yb] + 2.0 * torch.randn(B, D, generator=g), dim=-1)
+        batches.append((f, 100.0 * f @ F.normalize(mu, dim=-1).t(), yb))
+    w = keys.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([w], lr=1e-2, eps=1e-4)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, steps)
+    vals = oh.tip_cache_vals(lab, C)
+    ref_losses = []
+    for f, clip, yb in batches:
+        loss = F.cross_entropy(oh.tip_logits(f, w, vals, clip, 2.0, 20.0), yb)
+        opt.zero_grad(); loss.backward(); opt.step(); sched.step()
+        ref_losses.append(float(loss))
+    eng = TipAdapterEngine(keys.cuda(), lab.cuda(), C, 48, 2.0, 20.0, lr=1e-2, eps=1e-4, total_steps=steps, precision=precision)
+    losses = [float(eng.train_step(f.cuda(), clip.cuda(), yb.cuda())) for f, clip, yb in batches]
+    assert losses == pytest.approx(ref_losses, rel=max(tol, 1e-4), abs=2e-6)
+    assert rel_err(eng.keys, w) < tol
+
+
 def test_tip_hyperparameter_search_matches_oracle():
     from clip_gp_b200 import heads
     g = torch.Generator().manual_seed(7)

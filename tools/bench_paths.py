@@ -97,6 +97,21 @@ if "tip" in want:
     ms = timeit(tip_step)
     line("Tip-Adapter-F train step cfg4 (fp32 FFMA affinity, autograd, torch AdamW)", ms, 5 * N_tr * D * 4,
          flops=6.0 * B * N_tr * D, note="bytes: keys r + grad w/r + Adam m,v r/w lower bound")
+    for prec in ("bf16x3", "bf16"):
+        def tip_step_tc():
+            out = ops.tip_logits(f, kd, labd, clip, 2.0, 20.0, C, prec)
+            loss = ops.cross_entropy(out, ybd)
+            opt.zero_grad(); loss.backward(); opt.step()
+        ms = timeit(tip_step_tc)
+        line(f"Tip-Adapter-F train step cfg4 (tcgen05 {prec} affinity + key-gradient GEMMs, torch AdamW)", ms, 5 * N_tr * D * 4,
+             flops=6.0 * B * N_tr * D)
+    from clip_gp_b200.tip_engine import TipAdapterEngine
+    for prec in ("bf16x3", "bf16", "fp32"):
+        eng = TipAdapterEngine(keys, labd, C, B, 2.0, 20.0, total_steps=1000, precision=prec)
+        eng.train_step(f, clip, ybd)
+        ms = timeit(lambda: eng.train_step(f, clip, ybd))
+        line(f"Tip-Adapter-F train step cfg4, fused engine ({prec}, CUDA graph, own AdamW)", ms, 5 * N_tr * D * 4, flops=6.0 * B * N_tr * D)
+        del eng
     ms = timeit(lambda: ops.tip_logits(f, keys, labd, clip, 2.0, 20.0, C))
     line("Tip logits forward B=128, fp32 FFMA affinity + cache kernel", ms, N_tr * D * 4, flops=2.0 * B * N_tr * D)
     lib = _lib.load()
