@@ -610,7 +610,16 @@ class GPAdapterEngine:
         lib, st = self.lib, _lib.stream_ptr(self.dev)
         f = features.to(self.dev, non_blocking=True).float().contiguous()
         N, D = f.shape
-        Bop, mc_scale = self.eval_operands_tc(S, precision, mc)
+        # the prototype chain (GP forward -> unit prototypes -> operand cast; latency bound) runs on a side stream next to the feature
+        # chain (cast -> projection GEMM -> normalise; bandwidth / tensor bound); they meet at the logit GEMM
+        cur = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_eval_stream", None) is None:
+            self._eval_stream = torch.cuda.Stream(self.dev)
+        side = self._eval_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            Bop, mc_scale = self.eval_operands_tc(S, precision, mc)
+        Bop.record_stream(cur)
         Wb = tc.cast_bf16(self.p("W").view(D, D), tc.SPLIT_B if split else tc.PLAIN)
         fb = tc.cast_bf16(f, tc.SPLIT_A if split else tc.PLAIN)
         Y = tc.gemm_store(fb, Wb, 1.0)                                              # adapter.py:239
@@ -620,10 +629,34 @@ class GPAdapterEngine:
             # adapter.py:240 fused with the operand cast: the fp32 unit rows are never written
             _lib.check(lib.clipgp_rownorm_cast(Y.data_ptr(), N, D, None, None, fhat_b.data_ptr(), seg * D, D, 1 if split else 0, st),
                        "rownorm_cast")
+        cur.wait_stream(side)
         conf, correct, hist, logits = tc.logits_calibration(fhat_b, Bop, self.cfg.logit_scale * mc_scale, labels, n_bins,
                                                             want_conf=True, want_logits=want_logits)
         self.last_eval_logits = logits
         return conf, correct, hist
+
+    @torch.no_grad()
+    def eval_graph(self, features: torch.Tensor, labels: torch.Tensor, S=None, n_bins=10, precision="bf16x3", mc="collapsed"):
+        """Capture the tensor-core eval pass over a fixed (features, labels) device shard in one CUDA graph and return a callable
+        that replays it: () -> (conf, correct, hist), static output tensors.  The graph reads the engine's parameter buffers in
+        place, so it stays valid across training steps (the reference evaluates the same cached test features after every step,
+        adapter.py:363-380); ~15 launches and their allocations collapse into one replay."""
+        f = features.to(self.dev).float().contiguous()
+        y = labels.to(self.dev).to(torch.int64).contiguous()
+        from . import metrics as _m
+        _m._boundaries(n_bins, self.dev)                        # host-to-device copies must happen before the capture
+        for _ in range(2):                                      # warm-up: kernel attributes, tensor-map encoder, side stream
+            self.eval_calibration_tc(f, y, S=S, n_bins=n_bins, precision=precision, mc=mc)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.eval_calibration_tc(f, y, S=S, n_bins=n_bins, precision=precision, mc=mc)
+
+        def replay():
+            g.replay()
+            return out
+        replay.graph, replay.inputs = g, (f, y)
+        return replay
 
     # ------------------------------------------------------------------ sync back to the nn.Module
     @torch.no_grad()

@@ -31,9 +31,16 @@ class CalibrationCounters:
                                    self.bin_correct + other.bin_correct, self.bin_conf_fx + other.bin_conf_fx)
 
 
+_BOUNDARY_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
 def _boundaries(n_bins: int, device) -> torch.Tensor:
-    # metrics.py:75  torch.linspace(0, 1, n_bins + 1) in fp32 (0.7 and 0.9 round down)
-    return torch.linspace(0, 1, n_bins + 1, dtype=torch.float32).to(device)
+    """torch.linspace(0, 1, n_bins + 1) in fp32 (metrics.py:70) on the device; cached, so that a captured CUDA graph (engine.eval_graph)
+    sees no host-to-device copy."""
+    key = (int(n_bins), str(device))
+    if key not in _BOUNDARY_CACHE:
+        _BOUNDARY_CACHE[key] = torch.linspace(0, 1, n_bins + 1, dtype=torch.float32).to(device)
+    return _BOUNDARY_CACHE[key]
 
 
 def _prep(logits: torch.Tensor, labels: torch.Tensor):

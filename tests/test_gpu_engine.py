@@ -193,3 +193,21 @@ def test_device_resident_learning_rate_follows_the_schedule():
     assert float(eng.lr_dev[1]) == pytest.approx(0.1 * opt.param_groups[0]["lr"], rel=1e-6)
     eng.train_step(f[: shp.B], y[: shp.B], use_graph=True)
     assert not torch.equal(eng.flat_p, p0)
+
+
+def test_eval_graph_replays_track_the_parameters():
+    """engine.eval_graph: the captured eval pass (two-stream GP / feature chains + fused calibration GEMM) equals the eager pass, and a
+    replay after a training step sees the updated parameters (the graph reads the engine's buffers in place)."""
+    wl, shp, eng, _, _ = build("rbf", precision="bf16x3")
+    f, y = wl["f_test"].cuda(), wl["y_test"].cuda()
+    replay = eng.eval_graph(f, y, precision="bf16x3", mc="collapsed")
+    conf_e, cor_e, hist_e = eng.eval_calibration_tc(f, y, precision="bf16x3", mc="collapsed")
+    conf_g, cor_g, hist_g = replay()
+    assert torch.equal(hist_g, hist_e) and torch.equal(conf_g, conf_e) and torch.equal(cor_g, cor_e)
+    for it in range(3):
+        eng.train_step(wl["f_train"][:shp.B].cuda(), wl["y_train"][:shp.B].cuda())
+    conf_e, cor_e, hist_e = eng.eval_calibration_tc(f, y, precision="bf16x3", mc="collapsed")
+    before = hist_g.clone()
+    conf_g, cor_g, hist_g = replay()
+    assert torch.equal(hist_g, hist_e) and torch.equal(conf_g, conf_e)
+    assert not torch.equal(before[1], hist_g[1])              # the confidences moved with the parameters
