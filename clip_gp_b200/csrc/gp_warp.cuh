@@ -53,6 +53,36 @@ __device__ __forceinline__ void stage_block(int rows, int cols, LD_ ld, ST_ st) 
     }
 }
 
+// init - sum_{k0 <= k < k1} a[k * SA] * b[k * SB].  The sequential sweeps below (Cholesky columns, triangular substitutions) are
+// latency bound: one warp, a dependent chain per column.  Eight operand pairs are loaded before any is consumed and the products
+// go to four accumulators, so a step costs about one shared-memory round trip per EIGHT terms instead of per two.
+template <typename T, int SA, int SB>
+__device__ __forceinline__ T dot_sub(T init, const T* a, const T* b, int k0, int k1) {
+    T s0 = init, s1 = (T)0, s2 = (T)0, s3 = (T)0;
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+        T x[8], y[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { x[u] = a[(k + u) * SA]; y[u] = b[(k + u) * SB]; }
+        s0 -= x[0] * y[0]; s1 -= x[1] * y[1]; s2 -= x[2] * y[2]; s3 -= x[3] * y[3];
+        s0 -= x[4] * y[4]; s1 -= x[5] * y[5]; s2 -= x[6] * y[6]; s3 -= x[7] * y[7];
+    }
+    if (k + 4 <= k1) {
+        T x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { x[u] = a[(k + u) * SA]; y[u] = b[(k + u) * SB]; }
+        s0 -= x[0] * y[0]; s1 -= x[1] * y[1]; s2 -= x[2] * y[2]; s3 -= x[3] * y[3];
+        k += 4;
+    }
+    if (k + 2 <= k1) {
+        const T x0 = a[k * SA], y0 = b[k * SB], x1 = a[(k + 1) * SA], y1 = b[(k + 1) * SB];
+        s0 -= x0 * y0; s1 -= x1 * y1;
+        k += 2;
+    }
+    if (k < k1) s2 -= a[k * SA] * b[k * SB];
+    return (s0 + s1) + (s2 + s3);
+}
+
 // Left-looking lower Cholesky of an n x n matrix (n <= 33) by one warp, in place on the lower triangle.  Lane i owns row i;
 // when n == 33 the extra row 32 is carried by lane j-1 (idle in column j >= 1, because its own row is above the diagonal), so
 // the warp makes ONE pass per column instead of two.  invd[j] = 1 / L[j][j].  Returns true (uniformly) on a non-positive pivot.
@@ -64,16 +94,8 @@ __device__ __forceinline__ bool chol33(T* __restrict__ A, int n, T* __restrict__
         int i = lane;
         if (n == 33 && lane == j - 1) i = 32;
         const bool active = (i >= j) && (i < n);
-        T acc = (T)0;
-        {
-            const T* ri = A + (active ? i : j) * LD;
-            const T* rj = A + j * LD;
-            T a0 = ri[j], a1 = (T)0;
-            int k = 0;
-            for (; k + 1 < j; k += 2) { a0 -= ri[k] * rj[k]; a1 -= ri[k + 1] * rj[k + 1]; }
-            if (k < j) a0 -= ri[k] * rj[k];
-            acc = a0 + a1;
-        }
+        const T* ri = A + (active ? i : j) * LD;
+        const T acc = dot_sub<T, 1, 1>(ri[j], ri, A + j * LD, 0, j);
         // the pivot is the accumulator of row j: lane j for j < 32, lane 31 (carrying row 32) for j == 32
         const T sj = __shfl_sync(FULL, acc, j < 32 ? j : 31);
         if (!(sj > (T)0)) fail = true;
@@ -87,18 +109,45 @@ __device__ __forceinline__ bool chol33(T* __restrict__ A, int n, T* __restrict__
     return fail;
 }
 
+// Right-looking Cholesky of an m x m fp32 matrix (m <= 32) by one warp with the matrix in REGISTERS: lane i holds row i, the
+// column loop is fully unrolled, L[k][j] reaches the other rows by shuffle.  One column costs a pivot broadcast, one MUFU and
+// 2 (31 - j) independent SHFL / FFMA (about 1.3 k instructions in total) instead of ~150 dependent instructions around a
+// shared-memory dot product: measured 24 k -> 2 k cycles for a 32 x 32 factor (tools/gp_phase_ts.py).  Rows >= m are padded with
+// the identity.  In place on the lower triangle of A (row stride LD); invd[j] = 1 / L[j][j]; returns true (uniformly) on a
+// non-positive pivot.
+__device__ __forceinline__ bool chol32_regs(float* __restrict__ A, int m, float* __restrict__ invd) {
+    const int lane = lane_id();
+    float a[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a[k] = (lane < m && k <= lane) ? A[lane * LD + k] : (k == lane ? 1.f : 0.f);
+    bool fail = false;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float d = __shfl_sync(FULL, a[j], j);
+        if (!(d > 0.f)) fail = true;
+        const float inv = rsqrtf(d);
+        const float lij = (lane == j) ? d * inv : a[j] * inv;          // L[i][j], meaningful for i >= j
+        a[j] = lij;
+        if (lane == j) invd[j] = inv;
+#pragma unroll
+        for (int k = j + 1; k < 32; ++k) a[k] = fmaf(-lij, __shfl_sync(FULL, lij, k), a[k]);   // A[i][k] -= L[i][j] L[k][j] (used for i >= k)
+    }
+    if (lane < m) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+            if (k <= lane) A[lane * LD + k] = a[k];
+    }
+    __syncwarp();
+    return fail;
+}
+
 // X <- L^-1 X (forward substitution), X is [n][ncol] with lane = column; two partial sums shorten the dependent chain.
 template <typename T>
 __device__ __forceinline__ void trsm_lower_cols(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ X, int n, int ncol) {
     const int lane = lane_id();
     if (lane < ncol) {
         for (int i = 0; i < n; ++i) {
-            const T* Li = L + i * LD;
-            T s0 = X[i * LD + lane], s1 = (T)0;
-            int k = 0;
-            for (; k + 1 < i; k += 2) { s0 -= Li[k] * X[k * LD + lane]; s1 -= Li[k + 1] * X[(k + 1) * LD + lane]; }
-            if (k < i) s0 -= Li[k] * X[k * LD + lane];
-            X[i * LD + lane] = (s0 + s1) * invd[i];
+            X[i * LD + lane] = dot_sub<T, 1, LD>(X[i * LD + lane], L + i * LD, X + lane, 0, i) * invd[i];
         }
     }
     __syncwarp();
@@ -110,11 +159,7 @@ __device__ __forceinline__ void trsm_lowerT_cols(const T* __restrict__ L, const 
     const int lane = lane_id();
     if (lane < ncol) {
         for (int i = n - 1; i >= 0; --i) {
-            T s0 = X[i * LD + lane], s1 = (T)0;
-            int k = i + 1;
-            for (; k + 1 < n; k += 2) { s0 -= L[k * LD + i] * X[k * LD + lane]; s1 -= L[(k + 1) * LD + i] * X[(k + 1) * LD + lane]; }
-            if (k < n) s0 -= L[k * LD + i] * X[k * LD + lane];
-            X[i * LD + lane] = (s0 + s1) * invd[i];
+            X[i * LD + lane] = dot_sub<T, LD, LD>(X[i * LD + lane], L + i, X + lane, i + 1, n) * invd[i];
         }
     }
     __syncwarp();
@@ -175,11 +220,7 @@ __device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T*
         const int col = (wid == 0) ? lane : 32;
         if (col < m && (wid == 0 || lane == 0)) {
             for (int i = m - 1; i >= 0; --i) {
-                T s0 = P[i * LD + col], s1 = (T)0;
-                int k = i + 1;
-                for (; k + 1 < m; k += 2) { s0 -= L[k * LD + i] * P[k * LD + col]; s1 -= L[(k + 1) * LD + i] * P[(k + 1) * LD + col]; }
-                if (k < m) s0 -= L[k * LD + i] * P[k * LD + col];
-                P[i * LD + col] = (s0 + s1) * invd[i];
+                P[i * LD + col] = dot_sub<T, LD, LD>(P[i * LD + col], L + i, P + col, i + 1, m) * invd[i];
             }
         }
     }
@@ -190,11 +231,7 @@ __device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T*
         if (row < m && (wid == 0 || lane == 0)) {
             T* xr = P + row * LD;
             for (int i = m - 1; i >= 0; --i) {
-                T s0 = xr[i], s1 = (T)0;
-                int k = i + 1;
-                for (; k + 1 < m; k += 2) { s0 -= xr[k] * L[k * LD + i]; s1 -= xr[k + 1] * L[(k + 1) * LD + i]; }
-                if (k < m) s0 -= xr[k] * L[k * LD + i];
-                xr[i] = (s0 + s1) * invd[i];
+                xr[i] = dot_sub<T, 1, LD>(xr[i], xr, L + i, i + 1, m) * invd[i];
             }
         }
     }

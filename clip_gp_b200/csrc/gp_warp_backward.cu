@@ -19,6 +19,13 @@ extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
 namespace clipgp {
 namespace gpw {
 
+#ifdef CLIPGP_PHASE_TS
+__device__ long long g_phase_ts_bwd[64];
+#define GPB_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_ts_bwd[i] = clock64(); } while (0)
+#else
+#define GPB_TS(i) do { } while (0)
+#endif
+
 struct BwdSmem {
     double RA[NN];       // P2..P3: dA -> dK_ZX (fp64)
     double RB[NN];       // P1: R | dR->dSigma (fp32 halves);  P2: dBm | dSigma;  P3: L (fp64)
@@ -41,6 +48,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     const float dkl = b.dkl ? b.dkl[c] : b.dkl_scalar;
     const int lt = lane < T ? lane : T - 1;        // clamped lane for row-per-lane walks
 
+    GPB_TS(0);
     // =========================== P0 (optional): prototype adjoint -> dw of this class ===========================
     // dwsm [S][32] lives at the end of RC until P2 stages Lq there; it replaces the global dw read of P1.
     float* dwsm = nullptr;
@@ -60,6 +68,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         }
         for (int idx = tid; idx < T * T; idx += NT) Gc[idx] = __ldg(b.proto_EEt + (size_t)c * T * T + idx);
         __syncthreads();
+        GPB_TS(1);
         // a[s][t] = <g_s, E[c,t,:]>: warp = template row (the next row's loads in flight), lanes over the 16-byte column groups
         const float4* Ec = reinterpret_cast<const float4*>(b.proto_E + (size_t)c * T * D);
         constexpr int PSB = 12;
@@ -128,6 +137,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
             }
         }
         __syncthreads();
+        GPB_TS(2);
         // dw[s][t] = (a[s][t] - q_s (w_s G)[t] / |P_s|) / |P_s|,  q_s = <w_s, a_s> / |P_s|   (one sample per warp, lane = template)
         for (int sidx = wid; sidx < S; sidx += NW) {
             const size_t off = ((size_t)sidx * a.C + c) * T;
@@ -146,6 +156,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         __syncthreads();
     }
 
+    GPB_TS(3);
     // =========================== P1 ===========================
     float* R = reinterpret_cast<float*>(s.RB);
     float* G = R + NN;
@@ -185,6 +196,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
             }
         }
     }
+    GPB_TS(4);
     chol_adj_block<float>(R, s.vecT, G, reinterpret_cast<float*>(s.RC), T);      // RC is free until P2 stages Lq there
     each_block(T, T, [&](int idx, int i, int j) {               // G <- dSigma, full symmetric
         if (i > j) { const float v = 0.5f * G[i * LD + j]; G[i * LD + j] = v; G[j * LD + i] = v; }
@@ -196,6 +208,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         if (lane < T) s.vecT[lane] = dmu;                       // 1 / R_ii is dead
     }
 
+    GPB_TS(5);
     // =========================== P2 ===========================
     float* Lq = reinterpret_cast<float*>(s.RC);
     float* H = Lq + NN;
@@ -309,6 +322,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     }
     __syncthreads();
 
+    GPB_TS(6);
     // =========================== P3 (fp64) ===========================
     double* Ld = s.RB;
     double* Gd = s.RC;
@@ -319,8 +333,10 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     __syncthreads();
     for (int i = tid; i < n; i += NT) s.invd[i] = 1.0 / Ld[i * LD + i];
     __syncthreads();
+    GPB_TS(7);
     if (wid == 0) trsm_lowerT_cols<double>(Ld, s.invd, s.RA, n, T);   // RA <- dK_ZX = L^-T dA
     __syncthreads();
+    GPB_TS(8);
     // dL = -tril(dK_ZX A^T)  (lane = column j < 32: row j of A)
     {
         const float* arow = s.Af + min(lane, n - 1) * LD;
@@ -351,8 +367,10 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     each_block(n, n, [&](int idx, int i, int j) {              // dK_ZX leaves RA for the output block: RA becomes the adjoint's scratch
         if (j < T) dKt[idx] += (float)s.RA[i * LD + j];         // (the same thread wrote dKt[idx], the dSigma block, in P1)
     });
+    GPB_TS(9);
     chol_adj_block<double>(Ld, s.invd, Gd, s.RA, n);
 
+    GPB_TS(10);
     // =========================== P4: kernel adjoint (same CTA; d < 0 skips it: the stand-alone kernel then runs) ===========================
     const int d = (int)a.d;
     if (!fuse_kernel_adjoint) {
@@ -385,7 +403,9 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     for (int k = tid; k < d; k += NT) { qls[k] = 0.f; dzl[k] = 0.f; }
     __syncthreads();
     const float* Zc = a.Z + (size_t)c * n * d;
+    GPB_TS(11);
     const float damp = gp::kernel_adjoint_block(dK, LD, Wm, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileA, qls, dzl, n - 1, n - 1, rs, cs);
+    GPB_TS(12);
     __shared__ float red[32];
     const float damp_tot = block_sum(damp, red);
     if (tid == 0) {
@@ -404,6 +424,12 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
 }  // namespace clipgp
 
 using namespace clipgp;
+
+#ifdef CLIPGP_PHASE_TS
+extern "C" int clipgp_debug_phase_ts_bwd(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, gpw::g_phase_ts_bwd, sizeof(long long) * 64);
+}
+#endif
 
 // Fused prototype adjoint: S gradient rows of D floats plus two [S][32] tables must fit RA | RB | RC, S <= 12 register accumulators.
 extern "C" int clipgp_gp_fused_proto_bwd_ok(int64_t T, int64_t n, int64_t d, int64_t D, int64_t S) {

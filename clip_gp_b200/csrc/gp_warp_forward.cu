@@ -10,6 +10,14 @@
 namespace clipgp {
 namespace gpw {
 
+// Phase timestamps of class 0 (debug builds with -DCLIPGP_PHASE_TS only; read back with clipgp_debug_phase_ts).
+#ifdef CLIPGP_PHASE_TS
+__device__ long long g_phase_ts[64];
+#define GPW_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_ts[i] = clock64(); } while (0)
+#else
+#define GPW_TS(i) do { } while (0)
+#endif
+
 struct FwdSmem {
     double Ld[NN];       // K_ZZ + jI -> L (fp64)
     double Ad[NN];       // K_ZX -> A (fp64); afterwards reused as float Sigma [T][LD]
@@ -36,6 +44,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     const float* K = ks + 1;
     const int lt = lane < T ? lane : T - 1;
 
+    GPW_TS(0);
     if (fuse_gram) {
         // ---- K_ZZ by this CTA: scratch in regions that are written only later (K0: Af, inverse length-scales: Bm, chunk tile: Ad)
         const int d = (int)a.d, kt = a.kernel_type;
@@ -50,6 +59,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         __syncthreads();
         const float* Zc = a.Z + (size_t)c * n * d;
         gp::gram_block<float, 1>(K0, LD, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tile, tile);
+        GPW_TS(1);
         if (tid == 0) ks[0] = 1.f;
         // hand-over record for the adjoint (and the K_XX read of the Sigma stage below) + the fp64 operands
         each_block(n, n, [&](int idx, int i, int j) {
@@ -74,12 +84,15 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     if (tid < 3) s.Lq[33 * LD + tid] = 0.f;
     __syncthreads();
 
+    GPW_TS(2);
     // ---- warp 0: L = chol64(K_ZZ + 1e-4 I), A = L^-1 K_ZX;  warp 1 meanwhile: KL(q(u) || N(0,I))
     if (wid == 0) {
         const bool f = chol33<double>(s.Ld, n, s.invd);
         if (lane == 0) s.flag[0] = f ? 1 : 0;
         __syncwarp();
+        GPW_TS(20);
         trsm_lower_cols<double>(s.Ld, s.invd, s.Ad, n, T);
+        GPW_TS(21);
     } else if (wid == 1 && a.kl) {
         float part = 0.f;                          // 1/2 (|Lq|_F^2 + |m|^2 - n - sum log Lq_ii^2)
         for (int i = lane; i < n; i += 32) {
@@ -92,6 +105,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         if (lane == 0) a.kl[c] = 0.5f * (part - (float)n);
     }
     __syncthreads();
+    GPW_TS(3);
     const bool failL = s.flag[0] != 0;
     each_block(n, T, [&](int idx, int i, int j) { s.Af[i * LD + j] = (float)s.Ad[i * LD + j]; });
     __syncthreads();
@@ -120,6 +134,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     }
     __syncthreads();
 
+    GPW_TS(4);
     // ---- Sigma = K_XX + 1e-4 I + Bm^T Bm - A^T A (lower triangle), lane = column u, four rows t per pass
     float* Sig = reinterpret_cast<float*>(s.Ad);
     for (int t0 = 4 * wid; t0 < T; t0 += 4 * NW) {
@@ -140,6 +155,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     }
     __syncthreads();
 
+    GPW_TS(5);
     // ---- R = chol32(Sigma), psd_safe_cholesky retries with total diagonal jitter 1e-6, 1e-5, 1e-4
     float* R = s.Lq;                                // Lq is dead (its zeros above the diagonal stay in place)
     int retries = 0;
@@ -148,8 +164,10 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         const float jit = attempt == 0 ? 0.f : (attempt == 1 ? 1e-6f : (attempt == 2 ? 1e-5f : 1e-4f));
         each_block(T, T, [&](int idx, int t, int u) { if (u <= t) R[t * LD + u] = Sig[t * LD + u] + (t == u ? jit : 0.f); });
         __syncthreads();
+        GPW_TS(22 + 2 * attempt);
         if (wid == 0) {
-            const bool f = chol33<float>(R, T, s.invdR);
+            const bool f = chol32_regs(R, T, s.invdR);
+            GPW_TS(23 + 2 * attempt);
             if (lane == 0) s.flag[1] = f ? 1 : 0;
         }
         __syncthreads();
@@ -161,6 +179,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     const int st = failL ? -2 : (failR ? -1 : retries);
     if (tid == 0 && a.status) a.status[c] = st;
 
+    GPW_TS(6);
     // ---- saved factors for the adjoint
     if (a.L) each_block(n, n, [&](int idx, int i, int j) { a.L[(size_t)c * n * n + idx] = (j <= i) ? s.Ld[i * LD + j] : 0.0; });
     if (a.A) each_block(n, T, [&](int idx, int i, int j) { a.A[(size_t)c * n * T + idx] = s.Af[i * LD + j]; });
@@ -171,6 +190,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     float* wsm = (a.proto_E != nullptr && (a.proto_P_hat != nullptr || a.proto_mean_hat != nullptr) && a.proto_D <= 4 * NT && S * 32 <= 4 * NN)
                      ? reinterpret_cast<float*>(s.Ld) : nullptr;
     __syncthreads();                                // the saves above have read L / A / R's neighbours; Sigma (in Ad) is dead
+    GPW_TS(7);
     uint64_t seed = 0, step = 0;
     if (a.eps == nullptr) { seed = a.rng_state[0]; step = a.rng_state[1]; }
     const float* Rrow = R + lt * LD;
@@ -196,6 +216,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         if (lane < T) a.w[((size_t)sidx * a.C + c) * T + lane] = wv;
         if (wsm) wsm[sidx * 32 + lane] = wv;        // lanes >= T hold 0
     }
+    GPW_TS(8);
     if (!wsm) return;
 
     // ---- fused prototype stage: P[s,c,:] = sum_t w[s,t] E[c,t,:] -> unit rows (+ the bf16 operand of the logit GEMM).
@@ -266,6 +287,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         }
         __syncthreads();                                // `red` is reused by the next sample chunk
     }
+    GPW_TS(9);
     if (a.proto_mean_hat && col < D4) {
         const float is = 1.f / (float)S;
         reinterpret_cast<float4*>(a.proto_mean_hat + (size_t)c * D)[col] = make_float4(msum.x * is, msum.y * is, msum.z * is, msum.w * is);
@@ -278,6 +300,12 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
 using namespace clipgp;
 
 // Fast-path eligibility (the general kernel handles everything else).
+#ifdef CLIPGP_PHASE_TS
+extern "C" int clipgp_debug_phase_ts(long long* out, int which) {
+    return (int)cudaMemcpyFromSymbol(out, gpw::g_phase_ts, sizeof(long long) * 64);
+}
+#endif
+
 extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d) {
     return (T >= 2 && T <= 32 && n == T + 1 && d >= 4 && (d % 4) == 0) ? 1 : 0;
 }
