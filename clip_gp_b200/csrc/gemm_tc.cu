@@ -52,6 +52,9 @@ struct Params {
     const float* boundaries; int n_bins;
     long long* bin_count; unsigned long long* bin_conf_fx; long long* bin_correct; long long* top1;
     const int* key_class; float beta; float tip_alpha;   // EPI_TIP: class of every key (column), exp(-beta(1-aff)), alpha
+    int norm_cols;              // EPI_ROWSTATS: the first norm_cols columns (a multiple of BN) are not classes but the projected feature
+                                // y = f W^T; their squared sum gives 1 / max(|y|, 1e-12), which scales the class columns that follow
+                                // (F.normalize of the projection, adapter.py:239-240, without materialising it)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -264,6 +267,7 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
             const int m_blk = it.m_blk, n_first = it.n_first;
             const int row = m_blk * BM + q * 32 + lane;
             float run_m = -FLT_MAX, run_s = 0.f; int run_am = 0x7fffffff;
+            float sumsq = 0.f, sc = p.alpha;                     // EPI_ROWSTATS with norm columns: |f W^T|^2 of this row, then alpha / |f W^T|
             for (int nn = 0; nn < p.n_per_item; ++nn) {
                 const int n_blk = n_first + nn;
                 mbar_wait(&tmem_full[acc], acc_phase);
@@ -364,22 +368,27 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                                 if (j < ncols) dst[j] = p.alpha * __uint_as_float(r[j]);
                         }
                     }
-                    if (p.mode == EPI_ROWSTATS) {
+                    if (p.mode == EPI_ROWSTATS && col0 < p.norm_cols) {
+                        // projection columns: accumulate the squared norm; the last chunk fixes the scale of the class columns
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sumsq = fmaf(__uint_as_float(r[j]), __uint_as_float(r[j]), sumsq);
+                        if (col0 + 32 >= p.norm_cols) sc = p.alpha / fmaxf(sqrtf(sumsq), 1e-12f);
+                    } else if (p.mode == EPI_ROWSTATS) {
                         // chunk max / arg-max (lowest index on ties), then one rescale of the running sum
                         float cm = -FLT_MAX; int cam = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float v = p.alpha * __uint_as_float(r[j]);
+                            const float v = sc * __uint_as_float(r[j]);
                             if (j < ncols && v > cm) { cm = v; cam = j; }
                         }
                         if (cm > run_m) {
                             run_s *= exp2f((run_m - cm) * 1.4426950408889634f);
-                            run_m = cm; run_am = col0 + cam;
+                            run_m = cm; run_am = col0 - p.norm_cols + cam;
                         }
                         float s = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float v = p.alpha * __uint_as_float(r[j]);
+                            const float v = sc * __uint_as_float(r[j]);
                             if (j < ncols) s += exp2f((v - run_m) * 1.4426950408889634f);
                         }
                         run_s += s;
@@ -597,6 +606,25 @@ extern "C" int clipgp_tc_logits_calibration(const void* A_bf16, int64_t M, int64
     p.bin_count = reinterpret_cast<long long*>(bin_count); p.bin_conf_fx = bin_conf_fx;
     p.bin_correct = reinterpret_cast<long long*>(bin_correct); p.top1 = reinterpret_cast<long long*>(top1);
     return tc::launch(A_bf16, M, Ka, B_bf16, N, K, p, (cudaStream_t)stream);
+}
+
+extern "C" int clipgp_tc_proj_logits_calibration(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N_total, int64_t K,
+                                                 int64_t norm_cols, float alpha, const int64_t* labels, float* conf, int32_t* pred,
+                                                 uint8_t* correct, const float* boundaries, int n_bins, int64_t* bin_count,
+                                                 unsigned long long* bin_conf_fx, int64_t* bin_correct, int64_t* top1, void* stream) {
+    if (M == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(norm_cols > 0 && norm_cols % tc::BN == 0 && norm_cols < N_total,
+                   "tc_proj_logits_calibration: norm_cols (%lld) must be a positive multiple of %d below N_total", (long long)norm_cols, tc::BN);
+    CLIPGP_REQUIRE(n_bins >= 0 && n_bins <= CLIPGP_MAX_BINS, "tc_proj_logits_calibration: n_bins must be in [0,%d]", CLIPGP_MAX_BINS);
+    CLIPGP_REQUIRE(bin_count == nullptr || (boundaries && bin_conf_fx && bin_correct && n_bins >= 1), "tc_proj_logits_calibration: histogram outputs incomplete");
+    CLIPGP_REQUIRE(labels != nullptr || (correct == nullptr && top1 == nullptr && bin_count == nullptr), "tc_proj_logits_calibration: labels is NULL");
+    tc::Params p = {};
+    p.mode = tc::EPI_ROWSTATS; p.alpha = alpha; p.C = nullptr; p.ldc = 0; p.norm_cols = (int)norm_cols;
+    p.labels = reinterpret_cast<const long long*>(labels); p.conf = conf; p.pred = pred; p.correct = correct;
+    p.boundaries = boundaries; p.n_bins = n_bins;
+    p.bin_count = reinterpret_cast<long long*>(bin_count); p.bin_conf_fx = bin_conf_fx;
+    p.bin_correct = reinterpret_cast<long long*>(bin_correct); p.top1 = reinterpret_cast<long long*>(top1);
+    return tc::launch(A_bf16, M, Ka, B_bf16, N_total, K, p, (cudaStream_t)stream);
 }
 
 extern "C" int clipgp_tc_tip_logits(const void* F_bf16, int64_t M, const void* keys_bf16, int64_t N_tr, int64_t K,

@@ -50,6 +50,7 @@ class EngineConfig:
                                         # cross NVLink as two 1.3 MB all-reduces).  Off by default: it rules out the per-class fusion of
                                         # the prototype stages into the GP kernels, which is worth more (2 GPUs: 1876 vs ~2200 steps/s)
     fuse_prototypes: bool = True        # build the prototypes inside the GP forward kernel's CTA when the sizes allow it
+    fuse_eval_projection: bool = True   # tensor-core eval: projection + normalisation + logits + calibration in ONE GEMM (B = [W ; P W])
     overlap: bool = True                # run the feature branch of the step on a side stream next to the GP branch
     seed: int = 0
     rank: int = 0
@@ -617,6 +618,30 @@ class GPAdapterEngine:
             self._eval_stream = torch.cuda.Stream(self.dev)
         side = self._eval_stream
         side.wait_stream(cur)
+        fuse_proj = (mc == "collapsed" and not want_logits and D % 256 == 0 and self.cfg.fuse_eval_projection)
+        if fuse_proj:
+            # ONE GEMM for projection + normalisation + logits (clipgp_tc_proj_logits_calibration): B = [W ; Q], Q = mean_s p_hat_s W, so
+            # that f . Q_c = (f W^T) . p_c; the epilogue divides by |f W^T|.  The projected / normalised features are never written.
+            mA, mB = (tc.SPLIT_A, tc.SPLIT_B) if split else (tc.PLAIN, tc.PLAIN)
+            seg = 3 if split else 1
+            W = self.p("W").view(D, D)
+            Bop = torch.empty(D + self.C, seg * D, dtype=torch.bfloat16, device=self.dev)
+            with torch.cuda.device(self.dev):
+                _lib.check(lib.clipgp_cast_bf16(W.data_ptr(), D, D, D, Bop.data_ptr(), seg * D, D, mB, st), "cast_bf16(W)")
+            WT = tc.cast_bf16_transpose(W, mB)                                          # K-major operand of Q = P W
+            with torch.cuda.stream(side):
+                WT.record_stream(side); Bop.record_stream(side)
+                side.wait_stream(cur)
+                Pm = self.eval_prototypes(S)
+                Q = tc.gemm_store(tc.cast_bf16(Pm, mA), WT, 1.0)
+                with torch.cuda.device(self.dev):
+                    _lib.check(lib.clipgp_cast_bf16(Q.data_ptr(), self.C, D, D, Bop.data_ptr() + 2 * D * seg * D, seg * D, D, mB,
+                                                    _lib.stream_ptr(self.dev)), "cast_bf16(Q)")
+            fb = tc.cast_bf16(f, mA)
+            cur.wait_stream(side)
+            conf, correct, hist = tc.proj_logits_calibration(fb, Bop, D, self.cfg.logit_scale, labels, n_bins)
+            self.last_eval_logits = None
+            return conf, correct, hist
         with torch.cuda.stream(side):
             Bop, mc_scale = self.eval_operands_tc(S, precision, mc)
         Bop.record_stream(cur)

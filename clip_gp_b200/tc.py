@@ -124,3 +124,24 @@ def logits_calibration(A: torch.Tensor, B: torch.Tensor, alpha: float, labels: t
             b.data_ptr(), n_bins, hist[0].data_ptr(), hist[1].data_ptr(), hist[2].data_ptr(), hist[3].data_ptr(),
             _lib.ptr(logits), N, _lib.stream_ptr(dev)), "clipgp_tc_logits_calibration")
     return conf, correct, hist, logits
+
+
+def proj_logits_calibration(A: torch.Tensor, B: torch.Tensor, norm_cols: int, alpha: float, labels: torch.Tensor, n_bins: int = 10):
+    """One GEMM for projection + normalisation + logits + calibration: A = raw features [M,Ka] bf16, B = [W ; Q] [norm_cols + C, K]
+    bf16 (clipgp_tc_proj_logits_calibration).  Returns (conf, correct, hist[4,n_bins]) like logits_calibration."""
+    from .metrics import _boundaries
+    dev = _lib.require_cuda(A, B, labels)
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_contiguous() and B.is_contiguous()
+    M, Ka = A.shape
+    N, K = B.shape
+    labels = labels.to(torch.int64).contiguous()
+    conf = torch.empty(M, dtype=torch.float32, device=dev)
+    correct = torch.empty(M, dtype=torch.uint8, device=dev)
+    hist = torch.zeros(4, max(n_bins, 1), dtype=torch.int64, device=dev)
+    b = _boundaries(n_bins, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().clipgp_tc_proj_logits_calibration(
+            A.data_ptr(), M, Ka, B.data_ptr(), N, K, int(norm_cols), float(alpha), labels.data_ptr(), conf.data_ptr(), None,
+            correct.data_ptr(), b.data_ptr(), n_bins, hist[0].data_ptr(), hist[1].data_ptr(), hist[2].data_ptr(), hist[3].data_ptr(),
+            _lib.stream_ptr(dev)), "clipgp_tc_proj_logits_calibration")
+    return conf, correct, hist

@@ -316,6 +316,16 @@ int clipgp_tip_forward(float* affinity, int64_t lda, const int64_t* labels_tr, i
 int clipgp_tip_backward(float* e, int64_t lda, const int64_t* labels_tr, int64_t B, int64_t N_tr, const float* dout, int64_t ldd,
                         float beta, float alpha, void* stream);
 
+/* The eval pass of the Adapter head in ONE GEMM (adapter.py:239-249): B = [W ; Q] with W [norm_cols = D, K] the visual projection and
+ * Q = (mean_s p_hat_s) W [C, K] the prototypes pulled back through it, A = the RAW features.  The epilogue of a row block first sums
+ * the squares of the D projection columns (|f W^T|^2), then treats the remaining N_total - norm_cols columns as class logits
+ * alpha * (f . Q_c) / max(|f W^T|, 1e-12) with the calibration reduction of clipgp_tc_logits_calibration.  The projected and the
+ * normalised features are never written.  norm_cols must be a multiple of 256 (the tile width); pred / labels index classes. */
+int clipgp_tc_proj_logits_calibration(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N_total, int64_t K,
+                                      int64_t norm_cols, float alpha, const int64_t* labels, float* conf, int32_t* pred, uint8_t* correct,
+                                      const float* boundaries, int n_bins, int64_t* bin_count, unsigned long long* bin_conf_fx,
+                                      int64_t* bin_correct, int64_t* top1, void* stream);
+
 /* Tensor-core fused form for evaluation: out[b, key_class[j]] += alpha * exp(-beta (1 - f_b . key_j)) for every key j, computed in
  * the epilogue of the tcgen05 affinity GEMM ([M,K] x [N_tr,K]^T, bf16 or split operands): the [M, N_tr] affinity never reaches
  * HBM.  `out` [M, C] must already hold clip_logits; key_class [N_tr] int32 (sorting the cache by class minimises atomics). */

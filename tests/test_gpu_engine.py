@@ -211,3 +211,31 @@ def test_eval_graph_replays_track_the_parameters():
     conf_g, cor_g, hist_g = replay()
     assert torch.equal(hist_g, hist_e) and torch.equal(conf_g, conf_e)
     assert not torch.equal(before[1], hist_g[1])              # the confidences moved with the parameters
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_fused_projection_eval_matches_the_three_kernel_form(precision):
+    """clipgp_tc_proj_logits_calibration (B = [W ; P W], norm from the projection columns) against the cast -> projection GEMM ->
+    normalise -> logits GEMM form of the same engine, with a non-trivial visual projection; D = 256 so that the fused path is taken."""
+    from clip_gp_b200 import metrics as gm
+    synth.CONFIGS["d256"] = synth.WorkloadShape("d256", C=37, T=8, D=256, d=32, S=4, shots=4, B=48, N_test=3000, kernel="rbf", noise=5.0)
+    wl, shp, eng, _, _ = build("rbf", name="d256", precision=precision)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        eng.p("W").add_(0.05 * torch.randn(shp.D * shp.D, generator=g).cuda())
+    f, y = wl["f_test"].cuda(), wl["y_test"].cuda()
+    assert eng.cfg.fuse_eval_projection
+    conf_f, cor_f, hist_f = eng.eval_calibration_tc(f, y, precision=precision, mc="collapsed")
+    eng.cfg.fuse_eval_projection = False
+    conf_u, cor_u, hist_u = eng.eval_calibration_tc(f, y, precision=precision, mc="collapsed")
+    N = f.shape[0]
+    tol = 1e-3 if precision == "bf16x3" else 3e-2
+    assert float((conf_f - conf_u).abs().max()) < tol
+    assert int((cor_f != cor_u).sum()) <= (0 if precision == "bf16x3" else N // 100) + int(((conf_f - conf_u).abs() > 0).sum() > 0) * 3
+    assert int(hist_f[0].sum()) == N
+    ece_f, _ = gm.ece_from_counters(gm.counters_from_hist(hist_f, N))
+    ece_u, _ = gm.ece_from_counters(gm.counters_from_hist(hist_u, N))
+    assert ece_f == pytest.approx(ece_u, abs=0.05 if precision == "bf16x3" else 0.5)
+    # and against the exact fp32 path
+    ref = eng.evaluate(f, y, precision="fp32")
+    assert abs(ref["top1_count"] - int(hist_f[3, 0])) <= (3 if precision == "bf16x3" else N // 100)
