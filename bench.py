@@ -456,6 +456,15 @@ def run_ours(args):
                     "traffic": ncu_traffic(base), "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, DRAM read + write per launch)",
                     "algorithmic_bytes": ab, "avg_launch_us": dur * 1e6, "share_of_step": ktimes[dom]["ms"] / sum(v["ms"] for v in ktimes.values()),
                     "peak_source": pk["source"]}
+            try:        # what actually limits the kernel (committed ncu capture): issue slots and one class's dependent chain, not bytes
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json"))).get(base, {})
+                if "issue_active_pct" in prof:
+                    roof["limiter"] = {"issue_slots_active_pct": prof["issue_active_pct"], "warps_active_pct": prof["warps_active_pct"],
+                                       "warp_instructions_M": prof["inst_executed_M"],
+                                       "note": "per-class dependent chain (Cholesky factorisations / adjoints, triangular sweeps) at 7 classes per SM; "
+                                               "per-phase cycles in profiles/r1_gp_phase_cycles.txt"}
+            except Exception:
+                pass
         else:
             C_, D_, B_ = shp.C, shp.D, shp.B
             fl = ktimes[dom].get("flops") or 2.0 * B_ * eng.S_local * C_ * D_
