@@ -88,6 +88,8 @@ _SIGNATURES = {
                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "clipgp_adamw_step_lrptr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_void_p, C.c_float, C.c_float,
                                           C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "clipgp_adamw_step_cast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_float, C.c_float,
+                                         C.c_float, C.c_float, C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p]),
     "clipgp_increment": (C.c_int, [C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_sum_accumulate": (C.c_int, [C.c_void_p, c_i64, C.c_float, C.c_void_p, C.c_void_p]),
     "clipgp_tip_forward": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, c_i64, C.c_float, C.c_float, C.c_void_p, c_i64,

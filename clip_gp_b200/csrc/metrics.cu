@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) ece_hist_kernel(const float* __restrict__
 // Multi-CTA: every CTA histograms its slice of the images into shared memory (warp-aggregated: confidences share their
 // leading bytes, so a plain atomicAdd per element serialises on one or two counters), merges the non-empty counters into the
 // level's global histogram, and after a grid barrier every CTA derives the same digit choice from it.  The grid is at most
-// one CTA per SM, so all CTAs are co-resident and the spin barrier cannot deadlock.
+// one CTA per SM and is launched cooperatively, so all CTAs are co-resident and the spin barrier cannot deadlock.
 // ---------------------------------------------------------------------------------------------------
 static constexpr int kQ = 10;        // edges resolved per sweep (the default n_bins = 10 has 9 interior edges: one sweep)
 static constexpr int kLevels = 5;
@@ -465,8 +465,17 @@ extern "C" int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64
                    (long long)workspace_bytes, (long long)ws_bytes);
     if (ws == nullptr) CLIPGP_CUDA(cudaMallocAsync(&ws, ws_bytes, st));
     CLIPGP_CUDA(cudaMemsetAsync(ws, 0, blocks > 1 ? ws_bytes : sizeof(AeceWs), st));
-    aece_select_kernel<<<(unsigned)blocks, 1024, 0, st>>>(conf, correct, N, edges, n_bins, reinterpret_cast<AeceWs*>(ws), out_conf_fx,
-                                                         out_correct, out_count);
+    // cooperative launch: the runtime places the whole grid or nothing, so the in-kernel grid barrier cannot wait for CTAs that
+    // another stream's kernels keep off the SMs; a grid the device cannot hold at once falls back to one CTA (no barrier needed)
+    AeceWs* wsp = reinterpret_cast<AeceWs*>(ws);
+    void* kargs[] = {(void*)&conf, (void*)&correct, (void*)&N, (void*)&edges, (void*)&n_bins, (void*)&wsp, (void*)&out_conf_fx,
+                     (void*)&out_correct, (void*)&out_count};
+    cudaError_t le = cudaErrorUnknown;
+    if (blocks > 1) le = cudaLaunchCooperativeKernel((const void*)aece_select_kernel, dim3((unsigned)blocks), dim3(1024), kargs, 0, st);
+    if (le != cudaSuccess) {
+        (void)cudaGetLastError();
+        aece_select_kernel<<<1, 1024, 0, st>>>(conf, correct, N, edges, n_bins, wsp, out_conf_fx, out_correct, out_count);
+    }
     const int rc = check_launch("aece_select_kernel");
     if (workspace == nullptr) CLIPGP_CUDA(cudaFreeAsync(ws, st));
     return rc;

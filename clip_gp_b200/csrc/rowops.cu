@@ -157,6 +157,41 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     }
 }
 
+// AdamW on a [R, K] weight (K % 4 == 0) that also emits the updated weight as the bf16 operand of the next step's tensor-core GEMM
+// (layouts of clipgp_cast_bf16): the trainable Tip-Adapter-F keys are re-cast every step, this saves that pass over the weight.
+__global__ void __launch_bounds__(256) adamw_cast_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, int64_t n4, int K4, const float* __restrict__ lr_ptr, float b1,
+                                                         float b2, float eps, float wd, const int64_t* __restrict__ step_ptr,
+                                                         __nv_bfloat16* __restrict__ out, int64_t out_ld, int64_t seg_stride, int mode) {
+    const float lr = *lr_ptr;
+    const float t = (float)(*step_ptr);
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 gi = reinterpret_cast<const float4*>(g)[i];
+        float4 pi = reinterpret_cast<float4*>(p)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+#define CLIPGP_ADAMW1(c)                                                        \
+        mi.c = b1 * mi.c + (1.f - b1) * gi.c;                                   \
+        vi.c = b2 * vi.c + (1.f - b2) * gi.c * gi.c;                            \
+        pi.c = pi.c * decay - step_size * mi.c / (sqrtf(vi.c) * inv_sqrt_bc2 + eps);
+        CLIPGP_ADAMW1(x) CLIPGP_ADAMW1(y) CLIPGP_ADAMW1(z) CLIPGP_ADAMW1(w)
+#undef CLIPGP_ADAMW1
+        reinterpret_cast<float4*>(p)[i] = pi; reinterpret_cast<float4*>(m)[i] = mi; reinterpret_cast<float4*>(v)[i] = vi;
+        const int64_t r = i / K4; const int k = (int)(i - r * K4) << 2;
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(pi.x, pi.y), h1 = __floats2bfloat162_rn(pi.z, pi.w);
+        uint2 hi; hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+        __nv_bfloat16* o = out + r * out_ld + k;
+        *reinterpret_cast<uint2*>(o) = hi;
+        if (mode != 0) {
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(pi.x - __low2float(h0), pi.y - __high2float(h0));
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(pi.z - __low2float(h1), pi.w - __high2float(h1));
+            uint2 lo; lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+            *reinterpret_cast<uint2*>(o + seg_stride) = (mode == 1) ? hi : lo;
+            *reinterpret_cast<uint2*>(o + 2 * seg_stride) = (mode == 1) ? lo : hi;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) sum_accumulate_kernel(const float* __restrict__ x, int64_t n, float scale, float* out) {
     __shared__ float red[32];
     float q = 0.f;
@@ -644,6 +679,25 @@ extern "C" int clipgp_adamw_step_lrptr(float* p, const float* g, float* m, float
     if (blocks > cap) blocks = cap;
     adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, step, lr_dev);
     return check_launch("adamw_kernel");
+}
+
+extern "C" int clipgp_adamw_step_cast(float* p, const float* g, float* m, float* v, int64_t R, int64_t K, const float* lr_dev, float beta1,
+                                      float beta2, float eps, float weight_decay, const int64_t* step, void* out_bf16, int64_t out_ld,
+                                      int64_t seg_stride, int mode, void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && K >= 4 && (K % 4) == 0 && K < (1ll << 31), "adamw_step_cast: K must be a positive multiple of 4");
+    CLIPGP_REQUIRE(mode >= 0 && mode <= 2, "adamw_step_cast: mode must be 0, 1 or 2");
+    if (R == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(p && g && m && v && step && lr_dev && out_bf16, "adamw_step_cast: NULL pointer");
+    CLIPGP_REQUIRE(((out_ld | seg_stride) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7u) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15u) == 0,
+                   "adamw_step_cast: misaligned buffers / strides");
+    const int64_t n4 = R * (K / 4);
+    int64_t blocks = (n4 + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    adamw_cast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, (int)(K / 4), lr_dev, beta1, beta2, eps, weight_decay, step,
+                                                                         (__nv_bfloat16*)out_bf16, out_ld, seg_stride, mode);
+    return check_launch("adamw_cast_kernel");
 }
 
 extern "C" int clipgp_increment(int64_t* counter, int64_t by, void* stream) {

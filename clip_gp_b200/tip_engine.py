@@ -53,6 +53,7 @@ class TipAdapterEngine:
         self.steps_done = 0
         self.loss = torch.zeros(1, **f32)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._kb_valid = False                                  # bf16 operand of the keys: cast once, then maintained by the AdamW kernel
         self._per_batch = {}                                    # batch size -> (buffers, captured graph): the last partial batch of an epoch
         self._use(self.B)
 
@@ -101,7 +102,8 @@ class TipAdapterEngine:
             mA, mB = _MODE[self.precision]
             ck(lib.clipgp_cast_bf16_dual(self.in_feat.data_ptr(), B, D, D, self.fa.data_ptr(), self.fa.stride(0), D, mA,
                                          self.fT.data_ptr(), self.fT.stride(0), Bp, mB, st), "cast_bf16_dual(f)")
-            ck(lib.clipgp_cast_bf16(self.keys.data_ptr(), N_tr, D, D, self.kb.data_ptr(), self.kb.stride(0), D, mB, st), "cast_bf16(keys)")
+            if not self._kb_valid:      # afterwards the AdamW kernel keeps the bf16 operand of the keys up to date
+                ck(lib.clipgp_cast_bf16(self.keys.data_ptr(), N_tr, D, D, self.kb.data_ptr(), self.kb.stride(0), D, mB, st), "cast_bf16(keys)")
             ck(lib.clipgp_tc_gemm_store_splitk(self.fa.data_ptr(), B, self.fa.shape[1], self.kb.data_ptr(), N_tr, self.kb.shape[1], 1.0,
                                                self.aff.data_ptr(), N_tr, st), "tc_gemm(affinity)")
         ck(lib.clipgp_tip_forward(self.aff.data_ptr(), N_tr, self.key_labels.data_ptr(), B, N_tr, C, self.beta, self.alpha,
@@ -120,9 +122,22 @@ class TipAdapterEngine:
             ck(lib.clipgp_tc_gemm_store_splitk(self.GT.data_ptr(), N_tr, self.GT.shape[1], self.fT.data_ptr(), D, self.fT.shape[1], 1.0,
                                                self.dkeys.data_ptr(), D, st), "tc_gemm(dkeys)")
         b1, b2 = self.betas
-        ck(lib.clipgp_adamw_step_lrptr(self.keys.data_ptr(), self.dkeys.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.keys.numel(),
-                                       self.lr_dev.data_ptr(), b1, b2, self.eps, self.weight_decay, self.adam_step.data_ptr(), st), "adamw(keys)")
+        if self.precision == "fp32":
+            ck(lib.clipgp_adamw_step_lrptr(self.keys.data_ptr(), self.dkeys.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.keys.numel(),
+                                           self.lr_dev.data_ptr(), b1, b2, self.eps, self.weight_decay, self.adam_step.data_ptr(), st),
+               "adamw(keys)")
+        else:       # update + bf16 operand of the updated keys for the next step's affinity GEMM, one pass
+            ck(lib.clipgp_adamw_step_cast(self.keys.data_ptr(), self.dkeys.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), N_tr, D,
+                                          self.lr_dev.data_ptr(), b1, b2, self.eps, self.weight_decay, self.adam_step.data_ptr(),
+                                          self.kb.data_ptr(), self.kb.stride(0), D, _MODE[self.precision][1], st), "adamw_cast(keys)")
         ck(lib.clipgp_increment(self.adam_step.data_ptr(), 1, st), "increment")
+        self._kb_valid = self.precision != "fp32"
+
+    def _recast_keys(self):
+        if self.precision != "fp32":
+            _lib.check(self.lib.clipgp_cast_bf16(self.keys.data_ptr(), self.N_tr, self.D, self.D, self.kb.data_ptr(), self.kb.stride(0), self.D,
+                                                 _MODE[self.precision][1], _lib.stream_ptr(self.dev)), "cast_bf16(keys)")
+            self._kb_valid = True
 
     def _capture(self):
         snap = (self.keys.clone(), self.m.clone(), self.v.clone(), self.adam_step.clone())
@@ -134,6 +149,7 @@ class TipAdapterEngine:
         torch.cuda.synchronize(self.dev)
         for dst, src in zip((self.keys, self.m, self.v, self.adam_step), snap):
             dst.copy_(src)
+        self._recast_keys()                                     # the warm-up step left the operand of the UPDATED keys behind
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._launch_step()

@@ -236,6 +236,12 @@ int clipgp_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, f
  * (utils/optimization.py:218-281, stepped at adapter.py:1054-1056) advance inside a captured CUDA graph. */
 int clipgp_adamw_step_lrptr(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
                             float eps, float weight_decay, const int64_t* step, void* stream);
+/* clipgp_adamw_step_lrptr on a [R, K] weight that also writes the UPDATED weight as the bf16 operand of the next tensor-core GEMM
+ * (layouts / modes of clipgp_cast_bf16 below): the trainable cache keys of Tip-Adapter-F (tip_adapter.py:229-233) need no separate
+ * cast pass per step. */
+int clipgp_adamw_step_cast(float* p, const float* g, float* m, float* v, int64_t R, int64_t K, const float* lr_dev, float beta1,
+                           float beta2, float eps, float weight_decay, const int64_t* step, void* out_bf16, int64_t out_ld,
+                           int64_t seg_stride, int mode, void* stream);
 int clipgp_increment(int64_t* counter, int64_t by, void* stream);
 /* out[0] += scale * sum(x[0..n))   (e.g. gp_beta * sum_c KL_c, adapter.py:462-465). */
 int clipgp_sum_accumulate(const float* x, int64_t n, float scale, float* out, void* stream);
