@@ -49,6 +49,8 @@ class GpBwdArgs(C.Structure):
         ("draw_variance", C.c_void_p), ("dvar_mean", C.c_void_p), ("dchol_var", C.c_void_p), ("dmean_x", C.c_void_p),
         ("proto_dP", C.c_void_p), ("proto_dP_stride_s", c_i64), ("proto_dP_scale", C.c_float), ("proto_norm", C.c_void_p),
         ("proto_E", C.c_void_p), ("proto_EEt", C.c_void_p), ("proto_D", c_i64), ("dw_out", C.c_void_p),
+        ("tl_Z", C.c_void_p), ("tl_Z_ld", c_i64), ("tl_dlT", C.c_void_p), ("tl_dlT_ld", c_i64), ("tl_seg", c_i64), ("tl_B", c_i64),
+        ("tl_mode", C.c_int), ("tl_scale", C.c_float),
     ]
 
 

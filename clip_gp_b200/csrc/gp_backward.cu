@@ -336,6 +336,11 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
     // warp path (T <= 32, aliased test inputs): dense algebra warp-per-class, then the streamed kernel adjoint; classes whose
     // inputs are not aliased (x_is_z_prefix == 1 and the forward pass's device check failed) go through the block kernel
     static const bool block_only = (getenv("CLIPGP_GP_BLOCK_ONLY") != nullptr);
+    if (b->tl_Z != nullptr) {
+        CLIPGP_REQUIRE(b->tl_dlT && b->proto_EEt && b->proto_norm && b->tl_B >= 1 && a->S >= 1 && a->S <= 12 && (b->tl_mode == 0 || b->tl_mode == 1) &&
+                       b->tl_Z_ld >= a->C * a->T && b->tl_dlT_ld >= b->tl_B && clipgp_gp_warp_path_ok(a->T, a->n, a->d) && a->x_is_z_prefix != 0,
+                       "gp_backward: template-logit adjoint needs the warp path, S <= 12, dlogits^T / EEt / norms and consistent strides");
+    }
     const bool warp_path = !block_only && clipgp_gp_warp_path_ok(a->T, a->n, a->d) && a->x_is_z_prefix != 0 &&
                            ((reinterpret_cast<uintptr_t>(a->Z) & 15u) == 0);
     if (warp_path) {

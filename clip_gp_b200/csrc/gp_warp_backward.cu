@@ -52,12 +52,59 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     // =========================== P0 (optional): prototype adjoint -> dw of this class ===========================
     // dwsm [S][32] lives at the end of RC until P2 stages Lq there; it replaces the global dw read of P1.
     float* dwsm = nullptr;
-    if (b.proto_dP != nullptr) {
+    float* abuf = reinterpret_cast<float*>(s.RA) + 3 * 2 * NN - 2 * S * 32;   // [S][32]  a[s][t]  (the last 2 S 32 floats of RA | RB | RC)
+    float* Gc = s.Af;                                                         // [T][T] = E[c] E[c]^T (Af is dead until P2)
+    if (b.tl_Z != nullptr) {
+        // ---- small-batch form: a[s][t] = scale * sum_b dlogits[b,s,c] Zt[b,c,t] from the per-template cosines (see clipgp.h)
+        constexpr int BC = 128, SMAX = 12;
+        float* dls = reinterpret_cast<float*>(s.RA);                  // [S][BC]   dlogits of this class, one batch chunk
+        float* Zs = dls + SMAX * BC;                                  // [BC][32]  per-template cosines of the chunk
+        dwsm = abuf + S * 32;
+        for (int idx = tid; idx < T * T; idx += NT) Gc[idx] = __ldg(b.proto_EEt + (size_t)c * T * T + idx);
+        const __nv_bfloat16* dlT = reinterpret_cast<const __nv_bfloat16*>(b.tl_dlT);
+        const int Bt = (int)b.tl_B;
+        float acc[3] = {0.f, 0.f, 0.f};                               // samples wid, wid + 4, wid + 8 (S <= 12), lane = template
+        for (int b0 = 0; b0 < Bt; b0 += BC) {
+            const int bc = min(BC, Bt - b0);
+            __syncthreads();
+            for (int idx = tid; idx < S * BC; idx += NT) {
+                const int sidx = idx / BC, bb = idx - sidx * BC;
+                float v = 0.f;
+                if (bb < bc) {
+                    const __nv_bfloat16* row = dlT + ((size_t)sidx * a.C + c) * b.tl_dlT_ld + b0 + bb;
+                    v = __bfloat162float(row[0]);
+                    if (b.tl_mode == 1) v += __bfloat162float(row[2 * b.tl_seg]);
+                }
+                dls[idx] = v;
+            }
+            for (int idx = tid; idx < BC * 32; idx += NT) {
+                const int bb = idx >> 5, t = idx & 31;
+                Zs[idx] = (bb < bc && t < T) ? __ldg(b.tl_Z + (size_t)(b0 + bb) * b.tl_Z_ld + (size_t)c * T + t) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 2
+            for (int bb = 0; bb < BC; bb += 4) {
+                const float z0 = Zs[bb * 32 + lane], z1 = Zs[(bb + 1) * 32 + lane], z2 = Zs[(bb + 2) * 32 + lane], z3 = Zs[(bb + 3) * 32 + lane];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int sidx = wid + 4 * u;
+                    if (sidx < S) {
+                        const float4 dv = *reinterpret_cast<const float4*>(dls + sidx * BC + bb);
+                        acc[u] = fmaf(dv.x, z0, fmaf(dv.y, z1, fmaf(dv.z, z2, fmaf(dv.w, z3, acc[u]))));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int sidx = wid + 4 * u;
+            if (sidx < S) abuf[sidx * 32 + lane] = b.tl_scale * acc[u];
+        }
+        __syncthreads();
+    } else if (b.proto_dP != nullptr) {
         const int D = (int)b.proto_D, D4 = D >> 2;
         float* gbuf = reinterpret_cast<float*>(s.RA);                 // [S][D] upstream gradient rows (RA | RB | start of RC)
-        float* abuf = reinterpret_cast<float*>(s.RA) + 3 * 2 * NN - 2 * S * 32;   // [S][32]  a[s][t]
         dwsm = abuf + S * 32;                                         // [S][32]  (last S*32 floats of RC)
-        float* Gc = s.Af;                                             // [T][T] = E[c] E[c]^T (Af is dead until P2)
         for (int sidx = 0; sidx < S; ++sidx) {
             const float4* src = reinterpret_cast<const float4*>(b.proto_dP + (size_t)sidx * b.proto_dP_stride_s + (size_t)c * D);
             for (int col = tid; col < D4; col += NT) {
@@ -137,6 +184,8 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
             }
         }
         __syncthreads();
+    }
+    if (dwsm != nullptr) {
         GPB_TS(2);
         // dw[s][t] = (a[s][t] - q_s (w_s G)[t] / |P_s|) / |P_s|,  q_s = <w_s, a_s> / |P_s|   (one sample per warp, lane = template)
         for (int sidx = wid; sidx < S; sidx += NW) {

@@ -50,6 +50,11 @@ class EngineConfig:
                                         # cross NVLink as two 1.3 MB all-reduces).  Off by default: it rules out the per-class fusion of
                                         # the prototype stages into the GP kernels, which is worth more (2 GPUs: 1876 vs ~2200 steps/s)
     fuse_prototypes: bool = True        # build the prototypes inside the GP forward kernel's CTA when the sizes allow it
+    template_logit_adjoint: bool = False  # small batches: a[s,t] of the prototype adjoint from Zt = f_hat E^T (one tensor-core GEMM) and
+                                        # dlogits^T instead of the d P_hat GEMM + a 64 KB stream over E[c] per class (clipgp.h, tl_*).
+                                        # Measured at cfg2: GP adjoint 220 -> 194 us and no d P_hat GEMM, but the Zt GEMM (36 us, 125 CTAs
+                                        # of 212 KB shared memory, 98 MB of split-bf16 text bank) cannot hide next to the one-wave GP
+                                        # kernels: step 0.428 -> 0.442 ms.  Off by default; wins when the GEMM has a free slot.
     fuse_eval_projection: bool = True   # tensor-core eval: projection + normalisation + logits + calibration in ONE GEMM (B = [W ; P W])
     overlap: bool = True                # run the feature branch of the step on a side stream next to the GP branch
     seed: int = 0
@@ -212,6 +217,18 @@ class GPAdapterEngine:
             b.proto_dP, b.proto_dP_stride_s, b.proto_dP_scale = self.dP.data_ptr(), Cn * D, 1.0
             b.proto_norm, b.proto_E, b.proto_EEt, b.proto_D = self.P_norm.data_ptr(), self.E.data_ptr(), self.EEt.data_ptr(), D
             b.dw_out = self.dw_all.data_ptr()
+        # small-batch form of the same adjoint (needs the bf16 dlogits^T operand of the tensor-core step)
+        self.tl_adjoint = bool(self.fused_proto_bwd and self.cfg.template_logit_adjoint and self.cfg.precision != "fp32" and B <= 256 and
+                               S <= 12 and D % 8 == 0)
+        if self.tl_adjoint:
+            seg = self.tc_seg
+            if getattr(self, "Eb", None) is None:           # frozen text bank as the K-major B operand [C*T, seg*D]: one-time setup
+                self.Eb = torch.empty(Cn * T, seg * D, dtype=torch.bfloat16, device=self.dev)
+                self._cast(self.E.data_ptr(), Cn * T, D, D, self.Eb, D, self.tc_mb)
+            self.Zt = torch.empty(B, Cn * T, dtype=torch.float32, device=self.dev)
+            b.tl_Z, b.tl_Z_ld = self.Zt.data_ptr(), Cn * T
+            b.tl_dlT, b.tl_dlT_ld, b.tl_seg = self.dlTb.data_ptr(), self.dlTb.stride(0), self.Bp
+            b.tl_B, b.tl_mode, b.tl_scale = B, (1 if seg == 3 else 0), float(self._dims()[3])
         self.gp_bwd_args = b
 
     # ------------------------------------------------------------------ tensor-core operand buffers
@@ -269,13 +286,26 @@ class GPAdapterEngine:
         self._fwd_prototypes()
         if side is not None:
             main.wait_stream(side)
-        self._logits_and_loss()
+        self._logits()
+        tl_done = None
+        if self.tl_adjoint and cfg.precision != "fp32":
+            if side is not None:
+                side.wait_stream(main)                       # after the logit GEMM, next to the softmax kernels
+                with torch.cuda.stream(side):
+                    self._template_logits()
+                    tl_done = torch.cuda.Event()
+                    tl_done.record(side)
+            else:
+                self._template_logits()
+        self._loss()
         if side is not None:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self._bwd_features()
         else:
             self._bwd_features()
+        if tl_done is not None:
+            main.wait_event(tl_done)
         self._bwd_prototypes()
         if side is not None:
             main.wait_stream(side)
@@ -305,7 +335,15 @@ class GPAdapterEngine:
             ck(lib.clipgp_gemm_f32(self.in_feat.data_ptr(), D, 1, W, 1, D, self.Y.data_ptr(), D, B, D, D, 1.0, 0, st), "gemm(proj)")
         ck(lib.clipgp_rownorm_forward(self.Y.data_ptr(), B, D, self.f_hat.data_ptr(), self.f_inv.data_ptr(), None, st), "rownorm")
         if cfg.precision != "fp32":
-            self._cast2(self.f_hat.data_ptr(), B, D, D, self.fhb, D, self.tc_ma, self.fhTb, self.Bp, self.tc_mb)
+            self._cast2(self.f_hat.data_ptr(), B, D, D, self.fhb, D, self.tc_ma, None if self.tl_adjoint else self.fhTb, self.Bp, self.tc_mb)
+
+    def _template_logits(self):
+        """Zt = f_hat E_flat^T [B, C*T]: the per-template cosines the GP adjoint contracts with dlogits^T (clipgp.h, tl_*).  Independent
+        of the GP; launched on the feature stream AFTER the logit GEMM so that its 125 tiles (212 KB of shared memory each) neither
+        push the GP forward CTAs off the SMs nor delay the logit GEMM, and run next to the softmax kernels instead."""
+        _lib.check(self.lib.clipgp_tc_gemm_store(self.fhb.data_ptr(), self.B, self.fhb.shape[1], self.Eb.data_ptr(), self.Eb.shape[0],
+                                                 self.Eb.shape[1], 1.0, self.Zt.data_ptr(), self.Zt.stride(0), _lib.stream_ptr(self.dev)),
+                   "tc_gemm_store(Zt)")
 
     def _fwd_prototypes(self):
         """GP weights + unit prototypes (adapter.py:404, 424-425)"""
@@ -326,8 +364,8 @@ class GPAdapterEngine:
             # only the row-major operand is on the critical path (logit GEMM); the transposed copy feeds d f_hat on the feature branch
             self._cast(Bmat.data_ptr(), SC, D, D, self.Pb, D, self.tc_mb)
 
-    def _logits_and_loss(self):
-        """logits (adapter.py:426) -> cross-entropy + gradient (adapter.py:427-428)"""
+    def _logits(self):
+        """logits (adapter.py:426)"""
         lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
         B, Cn, D = self.B, self.C, self.D
         per_sample, S, SC, alpha = self._dims()
@@ -338,6 +376,13 @@ class GPAdapterEngine:
         else:
             ck(lib.clipgp_gemm_f32(self.f_hat.data_ptr(), D, 1, Bmat.data_ptr(), 1, D, self.logits.data_ptr(), SC, B, SC, D,
                                    alpha, 0, st), "gemm(logits)")
+
+    def _loss(self):
+        """cross-entropy + gradient of the logits (adapter.py:427-428)"""
+        lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
+        B, Cn, D = self.B, self.C, self.D
+        per_sample, S, SC, alpha = self._dims()
+        tcm = cfg.precision != "fp32"
         if per_sample:
             rows, rpl = B * S, S
             loss_scale = 1.0 / (B * cfg.S_train)
@@ -403,7 +448,8 @@ class GPAdapterEngine:
         per_sample, S, SC, alpha = self._dims()
         if cfg.precision != "fp32":
             # K-major operands: dlogits^T [SC, B] and f_hat^T [D, B] (K = batch)
-            self._tc(self.dlTb, self.fhTb, alpha, self.dP.data_ptr(), D)
+            if not self.tl_adjoint:
+                self._tc(self.dlTb, self.fhTb, alpha, self.dP.data_ptr(), D)
         else:
             ck(lib.clipgp_gemm_f32(self.logits.data_ptr(), 1, SC, self.f_hat.data_ptr(), D, 1, self.dP.data_ptr(), D, SC, D, B,
                                    alpha, 0, st), "gemm(dP)")

@@ -167,6 +167,20 @@ typedef struct clipgp_gp_bwd_args {
     const float* proto_EEt;       /* [C,T,T] */
     int64_t proto_D;
     float* dw_out;                /* optional [S,C,T]: the derived dw (for inspection) */
+    /* Small-batch source of a[s,t] for the fused prototype adjoint (tl_Z == NULL: off, a comes from proto_dP as above):
+     *     a[s,t] = tl_scale * sum_b dlogits[b,s,c] Zt[b,c,t],     Zt [B, C*T] = f_hat E_flat^T  (per-template cosines)
+     * which is the same number as <dP_hat[s,c,:], E[c,t,:]> with dP_hat = scale dlogits^T f_hat, contracted in the other order.
+     * Zt is ONE tensor-core GEMM on the feature branch (it does not depend on the GP), dlogits^T are the bf16 operand rows the
+     * softmax kernel writes anyway, so the d P_hat GEMM leaves the critical path and the class CTA reads B*T*4 + S*B*6 bytes
+     * instead of T*D*4 (24 KB instead of 64 KB at B = 128, T = 32, D = 512) for S*B*T instead of S*T*D multiply-adds. */
+    const float* tl_Z;            /* [B, C*T] fp32, row stride tl_Z_ld */
+    int64_t tl_Z_ld;
+    const void* tl_dlT;           /* bf16 [S*C, tl_dlT_ld], row s*C + c; tl_mode 0: [v], 1: segments [hi|hi|lo] of tl_seg elements */
+    int64_t tl_dlT_ld;
+    int64_t tl_seg;
+    int64_t tl_B;
+    int tl_mode;
+    float tl_scale;
 } clipgp_gp_bwd_args;
 
 /* 1 if the fused prototype adjoint can run for these sizes (warp path and the shared-memory bound above). */

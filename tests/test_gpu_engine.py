@@ -239,3 +239,21 @@ def test_fused_projection_eval_matches_the_three_kernel_form(precision):
     # and against the exact fp32 path
     ref = eng.evaluate(f, y, precision="fp32")
     assert abs(ref["top1_count"] - int(hist_f[3, 0])) <= (3 if precision == "bf16x3" else N // 100)
+
+
+def test_template_logit_adjoint_matches_the_default_step():
+    """EngineConfig.template_logit_adjoint: a[s,t] = scale * sum_b dlogits[b,s,c] (f_hat . E[c,t]) from the per-template cosine GEMM and
+    the bf16 dlogits^T operand (clipgp_gp_bwd_args.tl_*) gives the same gradients as the d P_hat GEMM + stream over E[c]."""
+    wl, shp, eng0, _, _ = build("rbf", name="t32", precision="bf16x3")
+    _, _, eng1, _, _ = build("rbf", name="t32", precision="bf16x3")
+    eng1.cfg.template_logit_adjoint = True
+    eng1._alloc_train(shp.B)
+    assert eng1.tl_adjoint and not eng0.tl_adjoint
+    f, y = wl["f_train"][:shp.B].cuda(), wl["y_train"][:shp.B].cuda()
+    for e in (eng0, eng1):
+        e.skip_update = True
+        e.train_step(f, y, use_graph=False)
+    torch.cuda.synchronize()
+    assert float(eng0.loss) == pytest.approx(float(eng1.loss), rel=1e-6)
+    for name in ("m", "Lq", "ls", "z_last"):
+        assert rel_err(eng1.g(name), eng0.g(name)) < 2e-4, name
