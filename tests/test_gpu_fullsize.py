@@ -183,3 +183,44 @@ def test_cfg5_matern_T64_S100_full_size():
     assert float((base.norm(dim=-1) - 1).abs().max()) < 1e-5
     P_ref = torch.einsum("skm,kmd->skd", w_ref, st.templates[idx]).mean(0)
     assert rel_err(base[idx.to(dev)], F.normalize(P_ref, dim=-1)) < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_cfg1_whole_step_and_eval_against_the_oracle(precision):
+    """BASELINE configs[0] at full size (Caltech101 shape: C=100, T=8, D=1024, 4-shot, S=4, RBF) — small enough for the CPU oracle to
+    run WHOLE: loss, every gradient of one optimisation step, and the MC-averaged eval logits / accuracy / ECE / AECE."""
+    from oracle.train_step import OracleAdapter
+    wl, shp, eng, st = _engine("cfg1", "rbf", 4, precision=precision, lengthscale=1.3)
+    assert (shp.C, shp.T, shp.D, shp.S, shp.shots) == (100, 8, 1024, 4, 4)
+    cfg = eng.cfg
+    orc = OracleAdapter(st, shp.D, scale=cfg.logit_scale, gp_beta=cfg.gp_beta, l2_lambda=cfg.l2_lambda, shots=cfg.shots, lr=cfg.lr,
+                        gp_lr=cfg.gp_lr, loss_mode="per_sample")
+    f, y = wl["f_train"][: shp.B], wl["y_train"][: shp.B]
+    eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, 4)
+    loss_ref = orc.loss(f, y, eps)
+    loss_ref.backward()
+    eng.skip_update = True
+    loss = eng.train_step(f.cuda(), y.cuda(), use_graph=False)
+    n = shp.T + 1
+    tol = 1e-3 if precision == "fp32" else 2e-3
+    assert float(loss) == pytest.approx(float(loss_ref), rel=1e-3)
+    assert int(eng.status.abs().max()) == 0
+    assert rel_err(eng.g("W").view(shp.D, shp.D), orc.W.grad) < tol
+    assert rel_err(eng.g("m").view(shp.C, n), orc.st.var_mean.grad) < tol
+    assert rel_err(eng.g("Lq").view(shp.C, n, n), orc.st.chol_var.grad) < tol
+    assert rel_err(eng.g("ls").view(shp.C, 1, -1), orc.st.kernel.raw_lengthscale.grad) < tol
+    assert rel_err(eng.g("os"), orc.st.kernel.raw_outputscale.grad) < tol
+    # eval over the whole test split: exact path vs oracle logits and the reference-pinned metrics oracle
+    ft, yt = wl["f_test"], wl["y_test"]
+    eps_e = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, 4)
+    protos, _ = ogp.sample_prototypes(st, eps_e)
+    lg_ref = oh.adapter_logits(ft, torch.eye(shp.D), protos, cfg.logit_scale)
+    res = eng.evaluate(ft.cuda(), yt.cuda(), precision="fp32" if precision == "fp32" else "bf16x3")
+    top1_ref = int((lg_ref.argmax(1) == yt).sum())
+    top2 = lg_ref.topk(2, dim=1).values
+    fragile = int(((top2[:, 0] - top2[:, 1]) < 1e-3 * float(lg_ref.abs().max())).sum())
+    assert abs(res["top1_count"] - top1_ref) <= fragile
+    assert res["ece"] == pytest.approx(om.compute_ece(lg_ref, yt), rel=1e-3, abs=2e-2)
+    # AECE re-ranks the confidences: with 200 images per bin, one near-tie swapped across a rank edge moves it by 0.05 pp; the split
+    # operands perturb confidences by ~1e-5, the exact path reproduces the order
+    assert res["aece"] == pytest.approx(om.compute_aece(lg_ref, yt), rel=1e-3, abs=2e-2 if precision == "fp32" else 0.25)
