@@ -414,9 +414,17 @@ extern "C" int clipgp_calibration_from_logits(const float* logits, int64_t ld_lo
     const int threads = 256;
     const int64_t rows_per_block = threads / 32;
     int64_t blocks = (N + rows_per_block - 1) / rows_per_block;
-    const int64_t cap = (int64_t)num_sms() * 8;
-    if (blocks > cap) blocks = cap;
     const bool vec = (C % 4 == 0) && (ld_logits % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15u) == 0);
+    // exactly one resident wave (the register-resident row keeps 5 CTAs per SM: a grid of 8 per SM ran 1.6 waves with an idle tail)
+    static int occ_vec = 0, occ_scalar = 0;
+    int& occ = vec ? occ_vec : occ_scalar;
+    if (occ == 0) {
+        if (vec) CLIPGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, calib_rows_kernel<true>, threads, 0));
+        else CLIPGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, calib_rows_kernel<false>, threads, 0));
+        if (occ < 1) occ = 1;
+    }
+    const int64_t cap = (int64_t)num_sms() * occ;
+    if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
     if (vec)
         calib_rows_kernel<true><<<(unsigned)blocks, threads, 0, st>>>(logits, ld_logits, labels, N, C, conf, pred, correct,
