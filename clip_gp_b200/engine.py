@@ -520,6 +520,64 @@ class GPAdapterEngine:
                 self._launch_step()
         return self.loss
 
+    def train_steps_host(self, f_host: torch.Tensor, y_host: torch.Tensor, batches, use_graph: bool = True) -> torch.Tensor:
+        """Run one optimisation step per (lo, hi) row range of PINNED host tensors and return the per-step losses (host tensor).
+        The reference moves every batch to the device and reads the loss back synchronously (adapter.py:729-746, 355-361); here the
+        next batch's host-to-device copy runs on a copy stream while the current step computes (two staging buffers), and each step's
+        loss is copied to pinned host memory asynchronously; the only host synchronisation is the one at the end."""
+        batches = list(batches)
+        if not batches:
+            return torch.empty(0)
+        B = batches[0][1] - batches[0][0]
+        if any(hi - lo != B for lo, hi in batches):
+            raise ValueError("train_steps_host: all batches must have the same size (drop_last, utils/data_manager.py:79)")
+        if not (f_host.is_pinned() and y_host.is_pinned()):
+            raise ValueError("train_steps_host: host tensors must be pinned (tensor.pin_memory())")
+        if B != self.B:
+            self._alloc_train(B)
+            self._graph = None
+        dev = self.dev
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            cp = self._copy_stream
+            if getattr(self, "_stage", None) is None or self._stage[0][0].shape[0] != B:
+                self._stage = [(torch.empty_like(self.in_feat), torch.empty_like(self.in_lab)) for _ in range(2)]
+            losses = torch.empty(len(batches), dtype=torch.float32).pin_memory()
+            if use_graph and self._graph is None and (self.cfg.world == 1 or self.cfg.graph_collectives):
+                self._capture()
+            loaded = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+            def prefetch(i):
+                lo, hi = batches[i]
+                sf, sy = self._stage[i % 2]
+                with torch.cuda.stream(cp):
+                    if i >= 2:
+                        cp.wait_event(consumed[i % 2])         # step i - 2 has copied this staging buffer into the step's input
+                    sf.copy_(f_host[lo:hi], non_blocking=True)
+                    sy.copy_(y_host[lo:hi], non_blocking=True)
+                    loaded[i % 2].record(cp)
+
+            cp.wait_stream(main)
+            prefetch(0)
+            for i in range(len(batches)):
+                if i + 1 < len(batches):
+                    prefetch(i + 1)
+                sf, sy = self._stage[i % 2]
+                main.wait_event(loaded[i % 2])
+                self.in_feat.copy_(sf, non_blocking=True)
+                self.in_lab.copy_(sy, non_blocking=True)
+                consumed[i % 2].record(main)
+                if use_graph and self._graph is not None:
+                    self._graph.replay()
+                else:
+                    self._launch_step()
+                losses[i:i + 1].copy_(self.loss.view(1), non_blocking=True)
+            main.synchronize()
+        return losses
+
     def _capture(self):
         # warm-up outside capture (sets kernel attributes), with all state restored afterwards
         snap = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.Z.clone(), self.adam_step.clone(),

@@ -257,3 +257,18 @@ def test_template_logit_adjoint_matches_the_default_step():
     assert float(eng0.loss) == pytest.approx(float(eng1.loss), rel=1e-6)
     for name in ("m", "Lq", "ls", "z_last"):
         assert rel_err(eng1.g(name), eng0.g(name)) < 2e-4, name
+
+
+def test_host_batch_pipeline_matches_step_by_step():
+    """train_steps_host (copy-stream prefetch + asynchronous loss read-back) == the same batches through train_step one by one."""
+    wl, shp, eng_a, _, _ = build("rbf", precision="bf16x3")
+    _, _, eng_b, _, _ = build("rbf", precision="bf16x3")
+    f, y = wl["f_train"].pin_memory(), wl["y_train"].pin_memory()
+    nb = min(5, f.shape[0] // shp.B)
+    batches = [(i * shp.B, (i + 1) * shp.B) for i in range(nb)]
+    ref = [float(eng_a.train_step(f[lo:hi].cuda(), y[lo:hi].cuda())) for lo, hi in batches]
+    losses = eng_b.train_steps_host(f, y, batches)
+    assert losses.tolist() == pytest.approx(ref, rel=1e-5)
+    assert rel_err(eng_b.flat_p, eng_a.flat_p) < 1e-5
+    with pytest.raises(ValueError):
+        eng_b.train_steps_host(wl["f_train"], wl["y_train"], batches)          # pageable host memory
