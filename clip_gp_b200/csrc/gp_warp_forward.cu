@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         if (lane == 0) s.flag[0] = f ? 1 : 0;
         __syncwarp();
         GPW_TS(20);
-        trsm_lower_cols<double>(s.Ld, s.invd, s.Ad, n, T);
+        if (n == 33) trsm_lower_cols33<double>(s.Ld, s.invd, s.Ad, T);
+        else trsm_lower_cols<double>(s.Ld, s.invd, s.Ad, n, T);
         GPW_TS(21);
     } else if (wid == 1 && a.kl) {
         float part = 0.f;                          // 1/2 (|Lq|_F^2 + |m|^2 - n - sum log Lq_ii^2)
