@@ -1,5 +1,7 @@
+"""The calibration pass (softmax max / arg-max + ECE histogram) over fp32 logits [50 000, 1000] a few times, for ncu:
+    ncu --set full -k regex:calib_rows python tools/prof_calib.py"""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from clip_gp_b200 import metrics as gm
 g = torch.Generator().manual_seed(0)
