@@ -40,19 +40,29 @@ def inv_softplus(y: float | torch.Tensor) -> torch.Tensor:
 # distances (gpytorch.kernels.kernel.sq_dist / dist)
 # ----------------------------------------------------------------------------------------
 def sq_dist(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
-    """gpytorch ``sq_dist`` for inputs that require grad (no diagonal zero-fill):
-    subtract x1's row mean from both inputs, expand |a|^2 - 2ab + |b|^2 as one matmul,
-    clamp at 0."""
+    """gpytorch ``sq_dist``: subtract x1's row mean from both inputs, expand |a|^2 - 2ab + |b|^2 as one matmul, clamp at 0.
+
+    gpytorch has a second branch, ``x1_eq_x2 and not x1.requires_grad and not x2.requires_grad``, that re-uses x1's norms and
+    forces the diagonal to exactly 0.  The reference's parameters always require grad (inducing points, length-scales), so the
+    branch is taken exactly when autograd is disabled (``torch.no_grad()`` evaluation, e.g. adapter.py:362, taskres.py:280):
+    here it is keyed on ``torch.is_grad_enabled()``.  It matters for Matern-1/2 only: the expansion leaves ~1e-6 noise on the
+    diagonal, and sqrt turns that into a 1e-3 deficit of K_ii in grad mode (pinned by tests/golden/ref_gp.npz)."""
+    x1_eq_x2 = (x1.shape == x2.shape) and torch.equal(x1, x2) and not torch.is_grad_enabled()
     adjustment = x1.mean(-2, keepdim=True)
     x1 = x1 - adjustment
-    x2 = x2 - adjustment
     x1_norm = x1.pow(2).sum(dim=-1, keepdim=True)
     x1_pad = torch.ones_like(x1_norm)
-    x2_norm = x2.pow(2).sum(dim=-1, keepdim=True)
-    x2_pad = torch.ones_like(x2_norm)
+    if x1_eq_x2:
+        x2, x2_norm, x2_pad = x1, x1_norm, x1_pad
+    else:
+        x2 = x2 - adjustment
+        x2_norm = x2.pow(2).sum(dim=-1, keepdim=True)
+        x2_pad = torch.ones_like(x2_norm)
     x1_ = torch.cat([-2.0 * x1, x1_norm, x1_pad], dim=-1)
     x2_ = torch.cat([x2, x2_pad, x2_norm], dim=-1)
     res = x1_.matmul(x2_.transpose(-2, -1))
+    if x1_eq_x2:
+        res.diagonal(dim1=-2, dim2=-1).fill_(0)
     return res.clamp_min(0)
 
 

@@ -1,0 +1,150 @@
+"""CPU: oracle/gp.py against tests/golden/ref_gp.npz — vectors produced by running the reference's OWN
+trainers/gp_template_weigher.py (unmodified) on the gpytorch/entmax stand-ins of oracle/_shim
+(tests/golden/make_ref_golden.py).  This is what pins the oracle: every reference-held line on the GP path (PCA, f0
+prior, mean-module tail, [:, :, :T] slice, batch == K branch, einsum) was executed, not restated."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp as ogp
+from tests.helpers import rel_err
+
+KERNELS = ["rbf", "matern", "linear"]
+CASES = ["tiny", "t32", "t1", "lowrank"]
+PCA_DIM = {"tiny": 16, "t32": 48, "t1": 8, "lowrank": 256}
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_gp.npz"))
+
+
+def T_(G, key):
+    return torch.from_numpy(G[key])
+
+
+def state_from_golden(G, case, kernel, dtype=torch.float32):
+    """Oracle GPState holding the reference module's buffers and (perturbed) parameters."""
+    key = f"{case}/{kernel}"
+    E = T_(G, f"{case}/E")
+    kp = ogp.KernelParams(kernel)
+    for name in ("raw_lengthscale", "raw_outputscale", "raw_variance"):
+        if f"{key}/param/{name}" in G:
+            setattr(kp, name, T_(G, f"{key}/param/{name}").to(dtype))
+    st = ogp.GPState(templates=E.to(dtype), templates_red=T_(G, f"{key}/templates_red").to(dtype),
+                     inducing_points=T_(G, f"{key}/param/Z").to(dtype), var_mean=T_(G, f"{key}/param/m").to(dtype),
+                     chol_var=T_(G, f"{key}/param/chol").to(dtype), kernel=kp, f0=T_(G, f"{key}/f0").to(dtype),
+                     cls_bias=T_(G, f"{key}/param/cls_bias").to(dtype), tmp_bias=T_(G, f"{key}/param/tmp_bias").to(dtype),
+                     pca_mean=T_(G, f"{key}/pca_mean").to(dtype), pca_W=T_(G, f"{key}/pca_W").to(dtype))
+    return st
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_setup_matches_reference(G, case, kernel):
+    """gp_template_weigher.py:22-111: PCA (columns up to sign), reduced templates, inducing points, f0, RBF median length-scale."""
+    key = f"{case}/{kernel}"
+    E = T_(G, f"{case}/E")
+    st = ogp.build_state(E, kernel, PCA_DIM[case])
+    W_ref = T_(G, f"{key}/pca_W")
+    assert st.pca_W.shape == W_ref.shape                                   # red_dim = min(gp_pca_dim, rank)
+    sign = torch.sign((st.pca_W * W_ref).sum(0))
+    assert rel_err(st.pca_W * sign, W_ref) < 1e-3
+    assert rel_err(st.pca_mean, T_(G, f"{key}/pca_mean")) < 1e-5
+    assert rel_err(st.templates_red * sign, T_(G, f"{key}/templates_red")) < 1e-3
+    assert rel_err(st.inducing_points * sign, T_(G, f"{key}/Z0")) < 1e-3
+    assert rel_err(st.f0, T_(G, f"{key}/f0")) < 1e-5
+    if kernel == "rbf":
+        assert rel_err(st.kernel.raw_lengthscale, T_(G, f"{key}/raw_lengthscale0")) < 1e-5
+        assert rel_err(ogp.softplus(st.kernel.raw_lengthscale), T_(G, f"{key}/lengthscale0")) < 1e-5
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_forward_matches_reference(G, case, kernel):
+    key = f"{case}/{kernel}"
+    st = state_from_golden(G, case, kernel)
+    eps = T_(G, f"{key}/eps")
+    protos, aux = ogp.sample_prototypes(st, eps)
+    assert rel_err(aux["mu"], T_(G, f"{key}/mu")) < 1e-3
+    assert rel_err(aux["Sigma"], T_(G, f"{key}/Sigma")) < 1e-3
+    assert rel_err(aux["w"], T_(G, f"{key}/w")) < 1e-3
+    assert rel_err(protos, T_(G, f"{key}/protos")) < 1e-3
+    assert rel_err(ogp.kl_divergence(st.var_mean, st.chol_var), T_(G, f"{key}/kl")) < 1e-5
+    # support pattern of sparsemax is identical
+    assert torch.equal(aux["w"] > 0, T_(G, f"{key}/w") > 0)
+    # eval mode from a fresh Cholesky cache gives the train-mode result.  Under no_grad gpytorch's sq_dist switches to its
+    # zero-diagonal branch (oracle.gp.sq_dist): the REFERENCE's own two modes differ for Matern-1/2 (up to 3e-3 elementwise)
+    with torch.no_grad():
+        protos_ng, _ = ogp.sample_prototypes(st, eps)
+    assert rel_err(protos_ng, T_(G, f"{key}/eval_mode/protos")) < 1e-3
+    assert rel_err(protos_ng, T_(G, f"{key}/nograd/protos")) < 1e-3
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_visual_batch_branch_matches_reference(G, case, kernel):
+    """gp_template_weigher.py:198-203,215: a visual batch with shape[0] == K adds one test row (Nx = T+1) that is sliced off."""
+    key = f"{case}/{kernel}"
+    st = state_from_golden(G, case, kernel)
+    with torch.no_grad():                                                  # the golden call ran under no_grad (eval, adapter.py:362-376)
+        protos, aux = ogp.sample_prototypes(st, T_(G, f"{key}/vis/eps"), visual_embeddings=T_(G, f"{key}/vis/features"))
+    assert aux["mu"].shape[1] == st.templates_red.shape[1] + 1
+    assert rel_err(aux["w"], T_(G, f"{key}/vis/w")) < 1e-3
+    assert rel_err(protos, T_(G, f"{key}/vis/protos")) < 1e-3
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_gradients_match_reference(G, case, kernel):
+    """Autograd through the oracle (fp32, like the reference) against autograd through the reference module."""
+    key = f"{case}/{kernel}"
+    st = state_from_golden(G, case, kernel)
+    params = {"Z": st.inducing_points, "m": st.var_mean, "chol": st.chol_var, "cls_bias": st.cls_bias, "tmp_bias": st.tmp_bias}
+    for name in ("raw_lengthscale", "raw_outputscale", "raw_variance"):
+        if getattr(st.kernel, name) is not None:
+            params[name] = getattr(st.kernel, name)
+    for p in params.values():
+        p.requires_grad_(True)
+    protos, aux = ogp.sample_prototypes(st, T_(G, f"{key}/eps"))
+    kl = ogp.kl_divergence(st.var_mean, st.chol_var)
+    loss = (protos * T_(G, f"{key}/dP")).sum() + (kl * T_(G, f"{key}/dkl")).sum()
+    grads = torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+    T = st.templates_red.shape[1]
+    for (name, p), g in zip(params.items(), grads):
+        g = torch.zeros_like(p) if g is None else g
+        ref = T_(G, f"{key}/grad/{name}")
+        if name == "Z":
+            g = g.clone(); g[:, :T] = 0                                     # the reference's hook masks the template rows (:72-79)
+            assert float(ref[:, :T].abs().max()) == 0.0
+        if name in ("cls_bias", "tmp_bias"):
+            # the mean module shifts f by a per-class constant; sparsemax is shift invariant -> exactly-zero gradient up to rounding
+            assert float(ref.abs().max()) < 1e-4 and float(g.abs().max()) < 1e-4
+            continue
+        # fp32 autograd on both sides, different op order inside sq_dist / solves: gate 2e-3 elementwise (floor 1% of the tensor max)
+        assert rel_err(g, ref) < 5e-3, name
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_first_call_initialisation(G, case):
+    """gpytorch initialises q(u) on the first call: m = 1e-3 * randn_like (drawn BEFORE the base noise), chol = I."""
+    key = f"{case}/rbf"
+    m = T_(G, f"{key}/first_call/m"); chol = T_(G, f"{key}/first_call/chol")
+    assert float(m.abs().max()) < 1e-2 and float(m.abs().max()) > 0
+    assert torch.equal(chol, torch.eye(chol.shape[-1]).expand_as(chol))
+    st = state_from_golden(G, case, "rbf")
+    st.inducing_points = T_(G, f"{key}/Z0"); st.var_mean = m; st.chol_var = chol
+    st.kernel.raw_lengthscale = T_(G, f"{key}/raw_lengthscale0"); st.kernel.raw_outputscale = torch.zeros(m.shape[0])
+    st.cls_bias = torch.zeros_like(st.cls_bias); st.tmp_bias = torch.zeros_like(st.tmp_bias)
+    protos, aux = ogp.sample_prototypes(st, T_(G, f"{key}/first_call/eps"))
+    assert rel_err(aux["w"], T_(G, f"{key}/first_call/w")) < 1e-3
+    assert rel_err(protos, T_(G, f"{key}/first_call/protos")) < 1e-3
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_initialize_from_weights_is_noop_unless_single_template(G, case):
+    changed = bool(G[f"{case}/rbf/init_from_weights/changed"])
+    T = G[f"{case}/E"].shape[1]
+    assert changed == (T == 1)
