@@ -313,8 +313,10 @@ class GaussianProcessTemplateWeighter(nn.Module):
         return (q.variational_mean._version, q.chol_variational_covar._version)
 
     def _kl(self) -> torch.Tensor:
+        # re-use the KL by-product of the last launch only while q(u) is unchanged AND (under autograd) that launch's graph is
+        # still alive: a backward through w or kl frees it (the hooks below flag that), and then a fresh launch is needed
         if self._last is not None and self._last[1] == self._versions() and (
-                self._last[0].requires_grad or not torch.is_grad_enabled()):
+                not torch.is_grad_enabled() or (self._last[0].requires_grad and not self._last[2]["consumed"])):
             return self._last[0]
         # q(u) changed since the last launch: evaluate the kernel once for its KL by-product
         self._launch(num_samples=1, eps=torch.zeros(self.num_classes, self.num_templates, 1, device=self._templates.device))
@@ -328,7 +330,12 @@ class GaussianProcessTemplateWeighter(nn.Module):
         w, kl, status = ops.gp_weights(vs.inducing_points, self._templates_red, raw_ls, raw_os, raw_var,
                                        q.variational_mean, q.chol_variational_covar, mean_x, eps, self.kernel_type,
                                        num_samples, rng_state=self._rng_state if eps is None else None)
-        self._last = (kl, self._versions())
+        flag = {"consumed": False}
+        if kl.requires_grad:
+            def _mark(_g, flag=flag):
+                flag["consumed"] = True
+            w.register_hook(_mark); kl.register_hook(_mark)
+        self._last = (kl, self._versions(), flag)
         self.last_status = status
         return w
 

@@ -68,9 +68,17 @@ class GPWeightsFunction(torch.autograd.Function):
             a.eps = eps.data_ptr()
             a.eps_sc, a.eps_st, a.eps_ss = eps.stride(0), eps.stride(1), eps.stride(2)
             a.rng_state = None
-        else:
+        rng_snap = eps_save = None
+        else_branch = eps is None
+        if else_branch:
+            # counter RNG: the adjoint must see the forward's draw even if the caller advances its (seed, step) counter before
+            # backward runs -> private snapshot of the state + the drawn noise itself (warp path re-reads it, general path
+            # regenerates from the snapshot)
             a.eps = None
-            a.rng_state = rng_state.data_ptr()
+            rng_snap = rng_state.detach().clone()
+            a.rng_state = rng_snap.data_ptr()
+            eps_save = torch.empty(S, Cn, T, dtype=torch.float32, device=dev)
+            a.eps_save = eps_save.data_ptr()
         a.s_offset, a.S_total = int(s_offset), int(S_total if S_total else S)
         a.w, a.kl, a.L, a.A, a.R, a.status = (w.data_ptr(), kl.data_ptr(), Lf.data_ptr(), Af.data_ptr(), Rf.data_ptr(),
                                               status.data_ptr())
@@ -79,7 +87,10 @@ class GPWeightsFunction(torch.autograd.Function):
             _lib.check(lib.clipgp_gp_forward(C.byref(a), _lib.stream_ptr(dev)), "clipgp_gp_forward")
         ctx.kernel_type = kernel_type
         ctx.args = a
-        ctx.keep = (Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, rng_state, w, Lf, Af, Rf)
+        # inputs and outputs go through save_for_backward so that autograd's version counters catch an in-place update
+        # (optimizer.step(), a hand-written copy_) between forward and backward; kernel-private buffers ride on ctx
+        ctx.save_for_backward(Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, w)
+        ctx.keep = (rng_snap, eps_save, Lf, Af, Rf)
         ctx.ksave = Ksave
         ctx.status = status
         ctx.mark_non_differentiable(status)
@@ -88,7 +99,7 @@ class GPWeightsFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dw, dkl, _dstatus):
         a = ctx.args
-        (Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, rng_state, w, Lf, Af, Rf) = ctx.keep
+        (Z, X, raw_ls, raw_os, raw_var, var_mean, chol_var, mean_x, eps, w) = ctx.saved_tensors
         dev = Z.device
         lib = _lib.load()
         Cn, n, d = Z.shape

@@ -31,7 +31,7 @@ class OracleAdapter:
     def __init__(self, st: ogp.GPState, D: int, scale=100.0, gp_beta=0.01, l2_lambda=0.5, shots=16, lr=0.01, gp_lr=1e-3,
                  weight_decay=0.0, loss_mode="per_sample"):
         self.st = st
-        self.W = torch.eye(D, device=st.templates.device, requires_grad=True)
+        self.W = torch.eye(D, dtype=st.templates.dtype, device=st.templates.device, requires_grad=True)
         self.scale, self.gp_beta, self.l2_lambda, self.shots = scale, gp_beta, l2_lambda, shots
         self.loss_mode = loss_mode
         self.gp_params = [st.inducing_points, st.var_mean, st.chol_var]
@@ -46,6 +46,7 @@ class OracleAdapter:
                                       {"params": self.gp_params, "lr": gp_lr, "weight_decay": weight_decay}])
 
     def loss(self, feats, labels, eps):
+        feats, eps = feats.to(self.W.dtype), eps.to(self.W.dtype)          # float64 twin: state_to(st, torch.float64)
         protos, aux = ogp.sample_prototypes(self.st, eps)
         kl = ogp.kl_divergence(self.st.var_mean, self.st.chol_var)
         if self.loss_mode == "per_sample":
@@ -64,5 +65,6 @@ class OracleAdapter:
 
     @torch.no_grad()
     def eval_logits(self, feats, eps):
+        feats, eps = feats.to(self.W.dtype), eps.to(self.W.dtype)
         protos, _ = ogp.sample_prototypes(self.st, eps)
         return heads.adapter_logits(feats, self.W, protos, self.scale)

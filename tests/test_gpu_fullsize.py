@@ -17,7 +17,7 @@ from oracle import gp as ogp
 from oracle import heads as oh
 from oracle import metrics as om
 from oracle import philox
-from tests.helpers import oracle_grads, rel_err
+from tests.helpers import assert_parity, max_err, oracle_grad_pair, oracle_grads, oracle_pair, rel_err, state_to, within
 
 pytestmark = pytest.mark.gpu
 
@@ -87,14 +87,18 @@ def test_cfg2_train_step_full_size_subset_parity():
     eps = philox.eps_tensor(11, 0, shp.C, shp.T, 10)[idx]
     dw = eng.dw.cpu()[:, idx]
     dkl = torch.full((len(idx),), eng.cfg.gp_beta)
-    w_ref, _, G, _ = oracle_grads(sub, eps, dw, dkl, torch.float64)
+    G32, G = oracle_grad_pair(sub, eps, dw, dkl)                      # reference arithmetic (fp32) / exact (float64)
+    w32, _, w64, _ = oracle_pair(sub, eps)
     n = shp.T + 1
-    assert rel_err(w[:, idx], w_ref) < 1e-3
-    assert rel_err(eng.g("m").view(shp.C, n).cpu()[idx], G["m"]) < 2e-3
-    assert rel_err(eng.g("Lq").view(shp.C, n, n).cpu()[idx], G["chol"]) < 2e-3
-    assert rel_err(eng.g("ls").view(shp.C, -1).cpu()[idx], G["ls"].view(len(idx), -1)) < 2e-3
-    assert rel_err(eng.g("os").cpu()[idx], G["os"]) < 2e-3
-    assert rel_err(eng.g("z_last").view(shp.C, -1).cpu()[idx], G["Z"][:, -1]) < 2e-2
+    assert_parity(w[:, idx], w32, w64, name="w")
+    assert rel_err(w[:, idx], w64) < 1e-3
+    got = {"m": eng.g("m").view(shp.C, n).cpu()[idx], "chol": eng.g("Lq").view(shp.C, n, n).cpu()[idx],
+           "ls": eng.g("ls").view(shp.C, 1, -1).cpu()[idx], "os": eng.g("os").cpu()[idx]}
+    for k_, g_ in got.items():
+        assert_parity(g_, G32[k_], G[k_], rtol=3e-3, name="d" + k_)     # bf16x3 GEMMs feed dw: 3e-3 (the reference's GPU path is TF32)
+        assert max_err(g_, G[k_]) < 2e-3, k_
+    assert_parity(eng.g("z_last").view(shp.C, -1).cpu()[idx], G32["Z"][:, -1], G["Z"][:, -1], rtol=3e-3, name="dz_last")
+    assert max_err(eng.g("z_last").view(shp.C, -1).cpu()[idx], G["Z"][:, -1]) < 2e-2
 
 
 def test_cfg3_eval_full_size_properties():
@@ -148,9 +152,9 @@ def test_cfg4_tip_adapter_full_size():
     kd = keys.cuda().requires_grad_(True)
     out = ops.tip_logits(f.cuda(), kd, lab.cuda(), clip.cuda(), 2.0, 20.0, C)
     out.backward(dout.cuda())
-    assert rel_err(out, ref) < 1e-5
+    assert within(out, ref, 1e-5)
     pick = torch.arange(0, N_tr, 37)
-    assert rel_err(kd.grad.cpu()[pick], kr.grad[pick]) < 1e-4
+    assert within(kd.grad.cpu()[pick], kr.grad[pick], 1e-4)
     from clip_gp_b200 import _lib
     o3 = clip.cuda().clone()
     fa, kb, li = tc.cast_bf16(f.cuda(), tc.SPLIT_A), tc.cast_bf16(keys.cuda(), tc.SPLIT_B), lab.to(torch.int32).cuda().contiguous()
@@ -176,13 +180,15 @@ def test_cfg5_matern_T64_S100_full_size():
     assert w.shape == (S, shp.C, shp.T) and int(status.abs().max()) == 0
     assert float((w.sum(-1) - 1).abs().max()) < 1e-5 and float(w.min()) >= 0.0
     idx = torch.tensor([0, 7, 200, 396])
-    w_ref, _ = ogp.gp_weights(_class_subset(st, idx), eps[idx])
-    assert rel_err(w[:, idx], w_ref) < 1e-3
-    assert rel_err(kl.cpu()[idx], ogp.kl_divergence(st.var_mean[idx], st.chol_var[idx])) < 1e-5
+    w_ref, _, w64, _ = oracle_pair(_class_subset(st, idx), eps[idx])
+    assert_parity(w[:, idx], w_ref, w64, name="w")
+    assert rel_err(w[:, idx], w64) < 2e-3
+    assert within(kl.cpu()[idx], ogp.kl_divergence(st.var_mean[idx], st.chol_var[idx]), 1e-5)
     _, _, base = ops.prototypes_reduced(w, st.templates.to(dev), want_mean_raw=True)
     assert float((base.norm(dim=-1) - 1).abs().max()) < 1e-5
     P_ref = torch.einsum("skm,kmd->skd", w_ref, st.templates[idx]).mean(0)
-    assert rel_err(base[idx.to(dev)], F.normalize(P_ref, dim=-1)) < 1e-3
+    P_64 = torch.einsum("skm,kmd->skd", w64, st.templates[idx].double()).mean(0)
+    assert_parity(base[idx.to(dev)], F.normalize(P_ref, dim=-1), F.normalize(P_64, dim=-1), name="mean prototypes")
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
@@ -197,19 +203,24 @@ def test_cfg1_whole_step_and_eval_against_the_oracle(precision):
                         gp_lr=cfg.gp_lr, loss_mode="per_sample")
     f, y = wl["f_train"][: shp.B], wl["y_train"][: shp.B]
     eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, 4)
+    orc64 = OracleAdapter(state_to(st, dtype=torch.float64), shp.D, scale=cfg.logit_scale, gp_beta=cfg.gp_beta, l2_lambda=cfg.l2_lambda,
+                          shots=cfg.shots, lr=cfg.lr, gp_lr=cfg.gp_lr, loss_mode="per_sample")
     loss_ref = orc.loss(f, y, eps)
     loss_ref.backward()
+    orc64.loss(f, y, eps).backward()
     eng.skip_update = True
     loss = eng.train_step(f.cuda(), y.cuda(), use_graph=False)
     n = shp.T + 1
     tol = 1e-3 if precision == "fp32" else 2e-3
     assert float(loss) == pytest.approx(float(loss_ref), rel=1e-3)
     assert int(eng.status.abs().max()) == 0
-    assert rel_err(eng.g("W").view(shp.D, shp.D), orc.W.grad) < tol
-    assert rel_err(eng.g("m").view(shp.C, n), orc.st.var_mean.grad) < tol
-    assert rel_err(eng.g("Lq").view(shp.C, n, n), orc.st.chol_var.grad) < tol
-    assert rel_err(eng.g("ls").view(shp.C, 1, -1), orc.st.kernel.raw_lengthscale.grad) < tol
-    assert rel_err(eng.g("os"), orc.st.kernel.raw_outputscale.grad) < tol
+    for name, g32, g64 in (("W", orc.W.grad, orc64.W.grad), ("m", orc.st.var_mean.grad, orc64.st.var_mean.grad),
+                           ("Lq", orc.st.chol_var.grad, orc64.st.chol_var.grad),
+                           ("ls", orc.st.kernel.raw_lengthscale.grad, orc64.st.kernel.raw_lengthscale.grad),
+                           ("os", orc.st.kernel.raw_outputscale.grad, orc64.st.kernel.raw_outputscale.grad)):
+        got = eng.g(name).view(g32.shape)
+        assert_parity(got, g32, g64, rtol=2e-3, name="d" + name)
+        assert max_err(got, g64) < tol, name
     # eval over the whole test split: exact path vs oracle logits and the reference-pinned metrics oracle
     ft, yt = wl["f_test"], wl["y_test"]
     eps_e = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, 4)

@@ -6,7 +6,7 @@ import torch.nn.functional as F
 
 from clip_gp_b200 import ops, tc
 from oracle import heads as oh
-from tests.helpers import rel_err
+from tests.helpers import max_err, rel_err, within
 
 pytestmark = pytest.mark.gpu
 
@@ -21,8 +21,8 @@ def test_matmul_nt_forward_backward(M, N, K):
     Ad, Bd = A.cuda().requires_grad_(True), B.cuda().requires_grad_(True)
     C = ops.matmul_nt(Ad, Bd, 0.7)
     C.backward(dC.cuda())
-    assert rel_err(C, (0.7 * A @ B.t())) < 1e-5
-    assert rel_err(Ad.grad, Ar.grad) < 1e-5 and rel_err(Bd.grad, Br.grad) < 1e-5
+    assert within(C, (0.7 * A @ B.t()), 1e-5)
+    assert within(Ad.grad, Ar.grad, 1e-5) and within(Bd.grad, Br.grad, 1e-5)
 
 
 def test_adapter_head_loss_and_grads_match_oracle():
@@ -42,10 +42,10 @@ def test_adapter_head_loss_and_grads_match_oracle():
     loss = ops.cross_entropy(logits, y.cuda(), rows_per_label=S)
     loss.backward()
     assert float(loss) == pytest.approx(float(ref), rel=1e-5)
-    assert rel_err(Wd.grad, Wr.grad) < 1e-4 and rel_err(Pd.grad, Pr.grad) < 1e-4
+    assert within(Wd.grad, Wr.grad, 1e-4) and within(Pd.grad, Pr.grad, 1e-4)
     # logit-mean form (adapter.py:247-249)
     lm = ops.matmul_nt(f_hat, p_hat, 30.0).view(B, S, C).mean(1)
-    assert rel_err(lm, oh.adapter_logits(f, W, P, 30.0)) < 1e-5
+    assert within(lm, oh.adapter_logits(f, W, P, 30.0), 1e-5)
 
 
 @pytest.mark.parametrize("B,N_tr,C,D", [(16, 48, 12, 64), (128, 1600, 100, 1024), (33, 407, 37, 128)])
@@ -62,7 +62,7 @@ def test_tip_cache_logits_forward_backward(B, N_tr, C, D):
     kd = keys.cuda().requires_grad_(True)
     out = ops.tip_logits(f.cuda(), kd, lab.cuda(), clip.cuda(), 2.0, 20.0, C)
     out.backward(dout.cuda())
-    assert rel_err(out, ref) < 1e-5 and rel_err(kd.grad, kr.grad) < 1e-4
+    assert within(out, ref, 1e-5) and within(kd.grad, kr.grad, 1e-4)
     # fused tensor-core evaluation form (affinity never materialised); split operands -> fp32-grade
     order = torch.argsort(lab, stable=True)
     ks, ls = keys[order].cuda(), lab[order].cuda()
@@ -92,7 +92,12 @@ def test_tip_cache_logits_tensor_core_precisions(precision, tol):
     kd = keys.cuda().requires_grad_(True)
     out = ops.tip_logits(f.cuda(), kd, lab.cuda(), clip.cuda(), 2.0, 20.0, C, precision)
     out.backward(dout.cuda())
-    assert rel_err(out, ref) < tol and rel_err(kd.grad, kr.grad) < tol
+    # logits: elementwise; key gradient: norm-wise (bf16: the stated tolerance) and, for the split operands, elementwise with the
+    # floor at 1e-2 of the tensor's largest entry: every entry is a sum over the batch with cancellation, and small entries carry
+    # the 2^-16 product rounding of the large terms (norm-wise the split path is at 1e-6)
+    assert rel_err(out, ref) < tol and max_err(kd.grad, kr.grad) < tol
+    if precision == "bf16x3":
+        assert within(kd.grad, kr.grad, 1e-4)
     with pytest.raises(ValueError):
         ops.tip_logits(f.cuda(), kd, lab.cuda(), clip.cuda(), 2.0, 20.0, C, "fp8")
 
@@ -146,7 +151,7 @@ def test_tip_engine_matches_reference_loop(precision, tol):
     eng = TipAdapterEngine(keys.cuda(), lab.cuda(), C, 48, 2.0, 20.0, lr=1e-2, eps=1e-4, total_steps=steps, precision=precision)
     losses = [float(eng.train_step(f.cuda(), clip.cuda(), yb.cuda())) for f, clip, yb in batches]
     assert losses == pytest.approx(ref_losses, rel=max(tol, 1e-4), abs=2e-6)
-    assert rel_err(eng.keys, w) < tol
+    assert within(eng.keys, w, max(tol, 5e-5))
 
 
 def test_tip_hyperparameter_search_matches_oracle():

@@ -4,7 +4,7 @@ import torch
 import torch.nn.functional as F
 
 from clip_gp_b200 import ops
-from tests.helpers import rel_err
+from tests.helpers import rel_err, within
 
 pytestmark = pytest.mark.gpu
 
@@ -21,16 +21,16 @@ def test_prototypes_forward_backward(S, C, T, D):
     wd = w.cuda().requires_grad_(True)
     P = ops.prototypes(wd, E.cuda())
     P.backward(dP.cuda())
-    assert rel_err(P, ref) < 1e-5 and rel_err(wd.grad, wr.grad) < 1e-5
+    assert within(P, ref, 1e-5) and within(wd.grad, wr.grad, 1e-5)
     P_hat, mh, mr = ops.prototypes_reduced(w.cuda(), E.cuda(), want_hat=True, want_mean_hat=True, want_mean_raw=True)
     ph = F.normalize(ref.detach(), dim=-1)
-    assert rel_err(P_hat, ph) < 1e-5 and rel_err(mh, ph.mean(0)) < 1e-5
-    assert rel_err(mr, F.normalize(ref.detach().mean(0), dim=-1)) < 1e-5
+    assert within(P_hat, ph, 1e-5) and within(mh, ph.mean(0), 1e-5)
+    assert within(mr, F.normalize(ref.detach().mean(0), dim=-1), 1e-5)
     # TaskRes residual branch (taskres.py:109-113)
     x = 0.1 * torch.randn(C, D, generator=g)
     t = ph + 0.5 * x.unsqueeze(0); t = t / t.norm(dim=-1, keepdim=True)
     T_hat, tm, _ = ops.prototypes_reduced(w.cuda(), E.cuda(), residual=x.cuda(), alpha=0.5, want_hat=True, want_mean_hat=True)
-    assert rel_err(T_hat, t) < 1e-5 and rel_err(tm, t.mean(0)) < 1e-5
+    assert within(T_hat, t, 1e-5) and within(tm, t.mean(0), 1e-5)
 
 
 def test_bad_shapes_raise():
