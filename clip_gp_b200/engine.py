@@ -113,6 +113,10 @@ class GPAdapterEngine:
         self.mean_x = gpw.mean_module.test_mean(T).detach().contiguous()      # per-class constant: no effect on w
         # ---- device scalars
         self.rng_state = torch.tensor([int(cfg.seed), 0], dtype=torch.int64, device=dev)
+        # evaluation draws from its OWN counter stream (the reference draws fresh, independent noise for every eval call,
+        # adapter.py:242-249): a different key, advanced once per eval pass, never touched by the captured train graph
+        self.eval_rng_state = torch.tensor([(int(cfg.seed) ^ 0x5DEECE66D) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
+        self.eval_eps = None            # optional explicit base noise [C, >=T, S] for evaluation (parity tests)
         self.adam_step = torch.ones(1, dtype=torch.int64, device=dev)
         self.lr_dev = torch.tensor([cfg.lr, cfg.gp_lr], dtype=torch.float32, device=dev)   # [visual_proj group, gp_weighter group]
         self._side_stream = torch.cuda.Stream(dev)
@@ -596,6 +600,19 @@ class GPAdapterEngine:
         # the capture did not execute anything; state is still the snapshot
         self._graph = g
 
+    def _eval_noise(self, a: GpArgs, S: int):
+        """Point a copy of the GP arguments at the evaluation noise: explicit `self.eval_eps` (kept alive by the caller) or the
+        evaluation counter stream, which is advanced by one step per call (a device-side increment, so a captured eval graph
+        draws fresh noise on every replay)."""
+        if self.eval_eps is not None:
+            e = self.eval_eps
+            if e.shape[0] != self.C or e.shape[1] < self.T or e.shape[2] != S or e.dtype != torch.float32 or e.device != self.dev:
+                raise ValueError(f"eval_eps must be a float32 [C, >=T, S={S}] tensor on {self.dev}; got {tuple(e.shape)} {e.dtype} {e.device}")
+            a.eps, a.eps_sc, a.eps_st, a.eps_ss, a.rng_state = e.data_ptr(), e.stride(0), e.stride(1), e.stride(2), None
+            return False
+        a.eps, a.rng_state = None, self.eval_rng_state.data_ptr()
+        return True
+
     def _eval_ksave(self):
         if getattr(self, "_ksave_eval", None) is None:
             self._ksave_eval = torch.empty_like(self.Ksave)
@@ -617,6 +634,7 @@ class GPAdapterEngine:
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path
+        bump = self._eval_noise(a, S)
         Pm = torch.empty(Cn, D, **f32)
         fused = bool(self.cfg.fuse_prototypes and lib.clipgp_gp_fused_proto_ok(T, n, self.d, D, S))
         if fused:       # the class's CTA also averages its unit prototypes: no separate prototype pass
@@ -626,6 +644,8 @@ class GPAdapterEngine:
             if not fused:
                 _lib.check(lib.clipgp_proto_forward(w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, None, None, None,
                                                     Pm.data_ptr(), None, 1, st), "proto_forward(eval)")
+        if bump:
+            self.eval_rng_state[1:2].add_(1)
         self.last_eval_w = w
         return Pm
 
@@ -693,6 +713,7 @@ class GPAdapterEngine:
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path
+        bump = self._eval_noise(a, S)
         P_hat = torch.empty(S, Cn, D, **f32)
         seg = 3 if split else 1
         Bop = torch.empty(Cn, S * seg * D, dtype=torch.bfloat16, device=self.dev)
@@ -703,6 +724,8 @@ class GPAdapterEngine:
             for s_ in range(S):     # row c of the operand = [p_hat_1c | ... | p_hat_Sc] (each optionally [hi|lo|hi])
                 _lib.check(lib.clipgp_cast_bf16(P_hat[s_].data_ptr(), Cn, D, D, Bop.data_ptr() + 2 * s_ * seg * D, S * seg * D, D,
                                                 2 if split else 0, st), "cast_bf16(P)")
+        if bump:
+            self.eval_rng_state[1:2].add_(1)
         return Bop, 1.0 / S
 
     @torch.no_grad()

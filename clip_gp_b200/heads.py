@@ -190,28 +190,61 @@ def tip_search(feats_hat, labels, keys, key_labels, clip_logits, num_classes: in
 
 # ---------------------------------------------------------------------------------------------------- GP pre-training
 def gp_pretrain(gp_weighter: GaussianProcessTemplateWeighter, feats_hat: torch.Tensor, labels: torch.Tensor, epochs: int,
-                gp_lr: float, beta_kl: float, num_samples: int, weight_decay: float = 0.0, scale: float = 100.0, log_every: int = 10):
-    """Full-batch ELBO optimisation of the weighter (taskres.py:254-280; identical in clip_adapter.py / tip_adapter.py):
-    CE(mean_s 100 f . normalize(protos_s), y) + beta * sum KL, AdamW + cosine annealing.  Returns the loss history."""
+                gp_lr: float, beta_kl: float, num_samples: int, weight_decay: float = 0.0, scale: float = 100.0, log_every: int = 10,
+                precision: str = "bf16x3", seed: int = 0):
+    """Full-batch ELBO optimisation of the weighter (taskres.py:254-280; identical in clip_adapter.py:257-279 and
+    tip_adapter.py:122-146): CE(mean_s 100 f . normalize(protos_s), y) + beta * sum KL, AdamW(gp_lr) + CosineAnnealingLR(epochs),
+    one step per epoch on ALL few-shot features.
+
+    Runs on the fused engine (engine.py) in its collapsed ``logit_mean`` form: the MC mean is taken over unit prototypes, so the
+    step is ONE [N_tr, D] x [C, D]^T tcgen05 GEMM forward and one backward instead of the reference's [N_tr, S, C] einsum, with
+    the engine's own AdamW and the device-resident cosine rate; no autograd graph, no torch.optim.  The features are unit rows
+    already and the visual projection is the frozen identity, exactly the reference's setting.  Returns the loss history."""
+    from .engine import EngineConfig, GPAdapterEngine
+    if float(weight_decay) != 0.0:
+        # the reference's AdamW decays every gp_weighter tensor that has a gradient, including the hook-masked template rows of
+        # the inducing points; the engine keeps those rows frozen (K_ZX = K_ZZ[:, :T] aliasing), so decay is not drop-in
+        raise NotImplementedError("gp_pretrain: weight_decay > 0 is not supported by the fused engine (it would move the frozen "
+                                  "template rows of the inducing points, gp_template_weigher.py:72-79)")
+    N = int(feats_hat.shape[0])
+    S = max(1, int(num_samples))
+    cfg = EngineConfig(S_train=S, S_eval=S, batch_size=N, logit_scale=float(scale), gp_beta=float(beta_kl), l2_lambda=0.0, shots=1,
+                       lr=0.0, gp_lr=float(gp_lr), weight_decay=0.0, loss_mode="logit_mean", train_visual_proj=False,
+                       precision=precision, seed=int(seed))
+    eng = GPAdapterEngine(gp_weighter, cfg)
+    f = feats_hat.detach().float().contiguous()
+    y = labels.to(torch.int64).contiguous()
+    losses = torch.empty(int(epochs), dtype=torch.float32, device=f.device)
+    for ep in range(int(epochs)):
+        eng.cosine_lr(ep, int(epochs), 0.0, float(gp_lr))                    # scheduler.step() after every epoch (taskres.py:276)
+        losses[ep:ep + 1].copy_(eng.train_step(f, y))
+    eng.export_to_module(gp_weighter)
+    hist = losses.tolist()                                                   # one host read for the whole loop
+    if log_every:
+        for ep, l in enumerate(hist):
+            if ep == 0 or (ep + 1) % log_every == 0:
+                print(f"[GP] epoch {ep + 1}/{epochs} loss={l:.4f}")
+    eng._graph = None
+    return hist
+
+
+def gp_pretrain_autograd(gp_weighter: GaussianProcessTemplateWeighter, feats_hat: torch.Tensor, labels: torch.Tensor, epochs: int,
+                         gp_lr: float, beta_kl: float, num_samples: int, weight_decay: float = 0.0, scale: float = 100.0):
+    """The same loop on the autograd surface (ops.py) with torch.optim — the comparator of tools/bench_paths.py and the route for
+    weight_decay > 0.  Materialises the [N_tr, S*C] logits exactly like the reference."""
     opt = torch.optim.AdamW(gp_weighter.parameters(), lr=gp_lr, weight_decay=weight_decay)
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, epochs)
     hist = []
     for ep in range(epochs):
         gp_weighter.train()
         prot = gp_weighter.sample_prototypes(num_samples=max(1, num_samples))
-        logits = _cosine_logits(feats_hat, prot, scale)
-        ce = ops.cross_entropy(logits, labels)
-        kl = gp_weighter.variational_strategy.kl_divergence().sum()
-        loss = ce + beta_kl * kl
+        loss = ops.cross_entropy(_cosine_logits(feats_hat, prot, scale), labels) + \
+            beta_kl * gp_weighter.variational_strategy.kl_divergence().sum()
         opt.zero_grad()
         loss.backward()
         opt.step()
         sched.step()
         hist.append(float(loss.detach()))
-        if log_every and ((ep == 0) or ((ep + 1) % log_every == 0)):
-            with torch.no_grad():
-                acc = metrics.compute_accuracy(logits.detach(), labels)[0]
-            print(f"[GP] epoch {ep + 1}/{epochs} loss={hist[-1]:.4f} CE={float(ce):.4f} KL={float(kl):.4f} acc={acc:.2f}")
     return hist
 
 

@@ -254,13 +254,19 @@ class NoiseBook:
       every batch makes the MC-averaged eval a deterministic function the CUDA path can reproduce with one pass);
     * the remaining train-mode calls (logging-only passes of adapter.py:339,357) get an unrelated stream."""
 
-    def __init__(self, C, T):
+    def __init__(self, C, T, sequential=False):
         self.C, self.T = C, T
         self.seed, self.step, self.in_loss, self.log = TR["seed"], 0, False, []
         self.eps_eval = {}
+        self.sequential = sequential    # trainers without compute_loss: EVERY train-mode draw (S == S_train) is a step of the stream
 
     def __call__(self, shape, idx):
         C, Nx, S = shape
+        if self.sequential and S == TR["S_train"]:
+            assert Nx == self.T, shape
+            self.log.append(("loss", self.step, shape))
+            self.step += 1
+            return philox.eps_tensor(self.seed, self.step - 1, C, Nx, S)
         if self.in_loss:
             assert Nx == self.T, shape
             self.log.append(("loss", self.step, shape))
@@ -274,19 +280,42 @@ class NoiseBook:
         return philox.eps_tensor(self.seed + 5000, idx, C, Nx, S)
 
 
-def run_reference_trainer(ref_mod, cfg, world, pretrain_epochs_attr=None, init_hook=None):
+class RecordingLoader:
+    """Wraps the few-shot train DataLoader: same attributes, but every pass over it is recorded (the shuffle order is the one
+    piece of host-side randomness a replay needs)."""
+
+    def __init__(self, loader, passes):
+        self._loader, self._passes = loader, passes
+
+    def __iter__(self):
+        cur = []
+        self._passes.append(cur)
+        for batch in self._loader:
+            cur.append((batch["img"].clone(), batch["label"].clone()))
+            yield batch
+
+    def __len__(self):
+        return len(self._loader)
+
+    def __getattr__(self, name):
+        return getattr(self._loader, name)
+
+
+def run_reference_trainer(ref_mod, cfg, world, pretrain_epochs_attr=None, init_hook=None, sequential=False, bs_train=None):
     """Instantiate the reference trainer on the fake data manager, run its own train(), return (trainer, record)."""
     register = _fake_clip.install([ref_adapter, ref_taskres, ref_clipad, ref_tip, ref_utrainer], world["E"], world["classnames"],
                                   ref_utrainer._get_templates)
     with contextlib.redirect_stdout(io.StringIO()):
         register(cfg)
     dm = _fake_clip.FakeDataManager(world["classnames"], world["f_tr"], world["y_tr"], world["f_te"], world["y_te"], world["f_va"],
-                                    world["y_va"], TR["bs_train"], TR["bs_test"])
+                                    world["y_va"], bs_train or TR["bs_train"], TR["bs_test"])
     out_dir = tempfile.mkdtemp(prefix="refgolden_")
     cfg.output_dir = out_dir
     trainer = ref_mod.Trainer(cfg, dm)
-    book = NoiseBook(TR["K"], TR["M"])
-    rec = {"batches_f": [], "batches_y": [], "losses": [], "lrs": []}
+    book = NoiseBook(TR["K"], TR["M"], sequential=sequential)
+    rec = {"batches_f": [], "batches_y": [], "losses": [], "lrs": [], "passes": []}
+    if sequential:
+        trainer.train_loader_x = RecordingLoader(trainer.train_loader_x, rec["passes"])
     # instance-level wrappers (the reference classes stay untouched): record each step's batch / loss, flag the loss pass
     orig_fb = trainer.forward_backward
 
@@ -332,10 +361,30 @@ def run_reference_trainer(ref_mod, cfg, world, pretrain_epochs_attr=None, init_h
             orig_bm()
             init_hook(trainer, rec)
         trainer.build_model = bm
+    # the head trainers create their weighter inside train(): a recording factory (the reference CLASS is untouched) triggers
+    # gpytorch's first-call initialisation of q(u) right away and keeps the state the pre-training loop starts from
+    real_cls = ref_gpw.GaussianProcessTemplateWeighter
+
+    def factory(*a, **k):
+        gp = real_cls(*a, **k)
+        gp.train()
+        with torch.no_grad():
+            gp.sample_prototypes(1)
+        gp.variational_strategy._clear_cache()
+        rec["gp_before"] = {}
+        _gp_state(rec["gp_before"], "s", gp)
+        return gp
+    if sequential:
+        for m_ in (ref_taskres, ref_clipad, ref_tip):
+            m_.GaussianProcessTemplateWeighter = factory
     torch.manual_seed(1234); np.random.seed(1234)
     log = io.StringIO()
-    with eps_hook(book) as h, contextlib.redirect_stdout(log):
-        trainer.train()
+    try:
+        with eps_hook(book) as h, contextlib.redirect_stdout(log):
+            trainer.train()
+    finally:
+        for m_ in (ref_taskres, ref_clipad, ref_tip):
+            m_.GaussianProcessTemplateWeighter = real_cls
     rec["stdout"] = log.getvalue()
     rec["noise_log"] = book.log
     rec["book"] = book
@@ -397,6 +446,124 @@ def adapter_trainer_goldens(out):
     return out
 
 
+def _gp_state(out, key, gp):
+    for n_, p_ in gp_param_dict(gp).items():
+        out[f"{key}/{n_}"] = np_(p_)
+    out[f"{key}/templates_red"] = np_(gp._templates_red); out[f"{key}/pca_W"] = np_(gp._pca_W); out[f"{key}/pca_mean"] = np_(gp._pca_mean)
+    out[f"{key}/f0"] = np_(gp.mean_module.f0); out[f"{key}/templates"] = np_(gp._templates)
+
+
+def _zero_shot_from_stdout(text):
+    import re
+    m = re.search(r"Zero-Shot accuracy on test: ([0-9.]+)", text)
+    return float(m.group(1)) if m else float("nan")
+
+
+def head_trainer_goldens(out):
+    """TaskRes / CLIP-Adapter / Tip-Adapter(-F): the reference's whole train() (GP pre-training loop included) per variant."""
+    world = trainer_world()
+    BS = 8                                                   # 40 few-shot features -> 5 full batches (no drop_last loss)
+    # ---------------------------------------------------------------- TaskRes (taskres.py:197-398)
+    for use_gp in (False, True):
+        key = f"taskres/{'gp' if use_gp else 'plain'}"
+        cfg = trainer_config("TaskRes", "rbf", use_gp=use_gp, taskres_optimizer="adam", taskres_lr=2e-3, taskres_epochs=5,
+                             taskres_residual_scale=0.5, template_init_method="uniform")
+        cfg.optim.max_epoch = 4                              # GP pre-training epochs (taskres.py:257); main loop: clip_adapter_epochs = 3
+        trainer, rec = run_reference_trainer(ref_taskres, cfg, world, sequential=True, bs_train=BS)
+        out[f"{key}/zero_shot_acc"] = np.float64(_zero_shot_from_stdout(rec["stdout"]))
+        passes = rec["passes"]
+        first_epoch_pass = 0
+        if use_gp:
+            out[f"{key}/pretrain_f"] = np.concatenate([np_(f) for f, _ in passes[0]]); out[f"{key}/pretrain_y"] = np.concatenate([np_(y) for _, y in passes[0]])
+            first_epoch_pass = 1
+            _gp_state(out, f"{key}/gp_after_pretrain", trainer.model.gp_weighter)
+            out.update({f"{key}/gp_before_pretrain/{k_[2:]}": v_ for k_, v_ in rec["gp_before"].items()})
+            assert "GP weighting failed" not in rec["stdout"], rec["stdout"][-2000:]
+        out[f"{key}/base_text_features"] = np_(trainer.model.taskres_learner.base_text_features)
+        out[f"{key}/batches_f"] = np.stack([np_(b) for b in rec["batches_f"]]); out[f"{key}/batches_y"] = np.stack([np_(b) for b in rec["batches_y"]])
+        out[f"{key}/losses"] = np.array(rec["losses"]); out[f"{key}/lrs"] = np.array(rec["lrs"])
+        out[f"{key}/final/residuals"] = np_(trainer.model.taskres_learner.text_feature_residuals)
+        if use_gp:
+            out[f"{key}/eps_eval"] = np_(rec["book"].eps_eval[TR["M"]])
+        pack_metrics(out, f"{key}/final_metrics", rec["metrics_json"]["metrics"])
+        print(f"  {key}: zs {out[f'{key}/zero_shot_acc']:.2f} losses {np.round(rec['losses'][:3], 4).tolist()}..{rec['losses'][-1]:.4f} "
+              f"final {rec['metrics_json']['metrics']}"[:260])
+    # ---------------------------------------------------------------- CLIP-Adapter (clip_adapter.py:230-355)
+    for use_gp in (False, True):
+        key = f"clip_adapter/{'gp' if use_gp else 'plain'}"
+        cfg = trainer_config("CLIP-Adapter", "linear", use_gp=use_gp, clip_adapter_optimizer="adam", clip_adapter_lr=1e-3,
+                             clip_adapter_epochs=3, clip_adapter_ratio=0.2, clip_adapter_reduction=4)
+        cfg.optim.max_epoch = 4
+
+        def init_hook(trainer, rec):
+            rec["fc1"] = trainer.model.adapter.fc1.weight.detach().clone(); rec["fc2"] = trainer.model.adapter.fc2.weight.detach().clone()
+            rec["clip_weights0"] = trainer.model.clip_weights.detach().clone()
+        trainer, rec = run_reference_trainer(ref_clipad, cfg, world, sequential=True, bs_train=BS, init_hook=init_hook)
+        out[f"{key}/zero_shot_acc"] = np.float64(_zero_shot_from_stdout(rec["stdout"]))
+        out[f"{key}/init/fc1"] = np_(rec["fc1"]); out[f"{key}/init/fc2"] = np_(rec["fc2"]); out[f"{key}/init/clip_weights"] = np_(rec["clip_weights0"])
+        passes = rec["passes"]
+        if use_gp:
+            out[f"{key}/pretrain_f"] = np.concatenate([np_(f) for f, _ in passes[0]]); out[f"{key}/pretrain_y"] = np.concatenate([np_(y) for _, y in passes[0]])
+            _gp_state(out, f"{key}/gp_after_pretrain", trainer.model.gp_weighter)
+            out.update({f"{key}/gp_before_pretrain/{k_[2:]}": v_ for k_, v_ in rec["gp_before"].items()})
+            out[f"{key}/eps_eval"] = np_(rec["book"].eps_eval[TR["M"]])
+            assert "GP weighting failed" not in rec["stdout"], rec["stdout"][-2000:]
+        out[f"{key}/clip_weights"] = np_(trainer.model.clip_weights)
+        out[f"{key}/batches_f"] = np.stack([np_(b) for b in rec["batches_f"]]); out[f"{key}/batches_y"] = np.stack([np_(b) for b in rec["batches_y"]])
+        out[f"{key}/losses"] = np.array(rec["losses"]); out[f"{key}/lrs"] = np.array(rec["lrs"])
+        out[f"{key}/final/fc1"] = np_(trainer.model.adapter.fc1.weight); out[f"{key}/final/fc2"] = np_(trainer.model.adapter.fc2.weight)
+        pack_metrics(out, f"{key}/final_metrics", rec["metrics_json"]["metrics"])
+        print(f"  {key}: zs {out[f'{key}/zero_shot_acc']:.2f} losses {np.round(rec['losses'][:3], 4).tolist()}..{rec['losses'][-1]:.4f}")
+    # ---------------------------------------------------------------- Tip-Adapter / Tip-Adapter-F (tip_adapter.py:82-362)
+    for use_gp in (False, True):
+        for trainable in (False, True):
+            key = f"tip/{'gp' if use_gp else 'plain'}/{'F' if trainable else 'cache'}"
+            cfg = trainer_config("Tip-Adapter", "matern", use_gp=use_gp, tip_adapter_trainable=trainable, tip_adapter_lr=1e-3,
+                                 tip_adapter_eps=1e-4, tip_adapter_epochs=3, tip_adapter_init_alpha=20.0, tip_adapter_init_beta=2.0)
+            cfg.optim.max_epoch = 4
+            captured = {}
+            trainer_holder = {}
+
+            def init_hook(trainer, rec, captured=captured):
+                orig = trainer._compute_final_metrics_tip_adapter
+
+                def wrapped(adapter=None, beta=None, alpha=None):
+                    if adapter is not None:
+                        captured["adapter_w"] = adapter.weight.detach().clone()
+                    gpw = getattr(trainer, "gp_weighter", None)
+                    if gpw is not None:
+                        gpw.variational_strategy._clear_cache()
+                    return orig(adapter=adapter, beta=beta, alpha=alpha)
+                trainer._compute_final_metrics_tip_adapter = wrapped
+            trainer, rec = run_reference_trainer(ref_tip, cfg, world, sequential=True, bs_train=BS, init_hook=init_hook)
+            out[f"{key}/zero_shot_acc"] = np.float64(_zero_shot_from_stdout(rec["stdout"]))
+            passes = rec["passes"]
+            pi = 0
+            if use_gp:
+                out[f"{key}/pretrain_f"] = np.concatenate([np_(f) for f, _ in passes[0]]); out[f"{key}/pretrain_y"] = np.concatenate([np_(y) for _, y in passes[0]])
+                _gp_state(out, f"{key}/gp_after_pretrain", trainer.gp_weighter)
+                out.update({f"{key}/gp_before_pretrain/{k_[2:]}": v_ for k_, v_ in rec["gp_before"].items()})
+                out[f"{key}/eps_eval"] = np_(rec["book"].eps_eval[TR["M"]])
+                assert "GP weighting failed" not in rec["stdout"], rec["stdout"][-2000:]
+                pi = 1
+            out[f"{key}/clip_weights"] = np_(trainer.clip_weights)                     # [D,K]
+            out[f"{key}/cache_keys"] = np_(trainer.cache_keys); out[f"{key}/cache_vals"] = np_(trainer.cache_vals)
+            # pass `pi` built the cache (tip_adapter.py:43-50); the following passes are the Tip-Adapter-F epochs.  The trainable
+            # nn.Linear SHARES STORAGE with cache_keys (`adapter.weight = nn.Parameter(self.cache_keys)`, :230), so after
+            # training `trainer.cache_keys` holds the trained weights: the initial keys are re-derived from the recorded pass
+            cf = torch.cat([f for f, _ in passes[pi]]); cy = torch.cat([y for _, y in passes[pi]])
+            out[f"{key}/cache_keys0"] = np_(cf / cf.norm(dim=-1, keepdim=True)); out[f"{key}/cache_labels0"] = np_(cy)
+            if trainable:
+                ep_passes = passes[pi + 1:pi + 1 + 3]
+                out[f"{key}/batches_f"] = np.stack([np_(f) for ps in ep_passes for f, _ in ps]); out[f"{key}/batches_y"] = np.stack([np_(y) for ps in ep_passes for _, y in ps])
+                out[f"{key}/final/adapter_w"] = np_(captured["adapter_w"])
+            out[f"{key}/best_beta"] = np.float64(trainer._tip_adapter_best_beta); out[f"{key}/best_alpha"] = np.float64(trainer._tip_adapter_best_alpha)
+            pack_metrics(out, f"{key}/final_metrics", rec["metrics_json"]["metrics"])
+            print(f"  {key}: zs {out[f'{key}/zero_shot_acc']:.2f} beta {trainer._tip_adapter_best_beta} alpha {trainer._tip_adapter_best_alpha} "
+                  f"final acc {rec['metrics_json']['metrics']['top1_acc']:.2f} ece {rec['metrics_json']['metrics']['ece']:.3f}")
+    return out
+
+
 def main():
     torch.set_num_threads(4)
     which = sys.argv[1:] or ["gp", "train"]
@@ -407,6 +574,7 @@ def main():
     if "train" in which:
         out = {}
         adapter_trainer_goldens(out)
+        head_trainer_goldens(out)
         np.savez_compressed(os.path.join(HERE, "ref_train.npz"), **out)
         print("wrote ref_train.npz:", len(out), "arrays,", os.path.getsize(os.path.join(HERE, "ref_train.npz")) // 1024, "KiB")
 

@@ -134,3 +134,13 @@ def oracle_grad_pair(st, eps, dw, dkl):
     _, _, G32, _ = oracle_grads(st, eps, dw, dkl, torch.float32)
     _, _, G64, _ = oracle_grads(st, eps, dw, dkl, torch.float64)
     return G32, G64
+
+
+def fix_eval_noise(eng, S=None, seed=None, step=0):
+    """Give a GPAdapterEngine explicit evaluation noise (the counter stream of oracle/philox.py) so that repeated eval calls of a
+    test see the same draw; returns the CPU tensor [C, T, S] for the oracle side."""
+    from oracle import philox
+    S = int(S or eng.cfg.S_eval)
+    eps = philox.eps_tensor(int(eng.cfg.seed if seed is None else seed), step, eng.C, eng.T, S)
+    eng.eval_eps = eps.to(eng.dev)
+    return eps

@@ -11,7 +11,7 @@ from oracle import gp as ogp
 from oracle import metrics as om
 from oracle import philox
 from oracle.train_step import OracleAdapter
-from tests.helpers import assert_parity, max_err, rel_err, state_to, within
+from tests.helpers import assert_parity, fix_eval_noise, max_err, rel_err, state_to, within
 
 pytestmark = pytest.mark.gpu
 
@@ -137,7 +137,7 @@ def test_adamw_update_and_graph_replay_match_eager():
 def test_eval_matches_oracle_logit_mean_and_metrics():
     wl, shp, eng, orc, cfg = build("rbf", S=6)
     f, y = wl["f_test"], wl["y_test"]
-    eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, 6)
+    eps = fix_eval_noise(eng, 6)
     logits_ref = orc.eval_logits(f, eps)                       # materialised [B,S,C] mean (adapter.py:247-249)
     logits = eng.eval_logits(f.cuda(), S=6)                    # collapsed: one GEMM against mean_s p_hat_s
     assert float((logits.cpu() - logits_ref).abs().max()) < 1e-3 * float(logits_ref.abs().max())
@@ -157,7 +157,7 @@ def test_tensor_core_eval_modes(precision, mc):
     (1e-3 relative on logits, identical top-1 / bin counts up to boundary ties); bf16 meets its stated tolerance."""
     wl, shp, eng, orc, cfg = build("rbf", S=6)
     f, y = wl["f_test"], wl["y_test"]
-    eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, 6)
+    eps = fix_eval_noise(eng, 6)
     logits_ref = orc.eval_logits(f, eps)
     conf, correct, hist = eng.eval_calibration_tc(f.cuda(), y.cuda(), S=6, precision=precision, mc=mc, want_logits=True)
     logits = eng.last_eval_logits.cpu()
@@ -211,6 +211,7 @@ def test_eval_graph_replays_track_the_parameters():
     replay after a training step sees the updated parameters (the graph reads the engine's buffers in place)."""
     wl, shp, eng, _, _ = build("rbf", precision="bf16x3")
     f, y = wl["f_test"].cuda(), wl["y_test"].cuda()
+    fix_eval_noise(eng)
     replay = eng.eval_graph(f, y, precision="bf16x3", mc="collapsed")
     conf_e, cor_e, hist_e = eng.eval_calibration_tc(f, y, precision="bf16x3", mc="collapsed")
     conf_g, cor_g, hist_g = replay()
@@ -236,6 +237,7 @@ def test_fused_projection_eval_matches_the_three_kernel_form(precision):
         eng.p("W").add_(0.05 * torch.randn(shp.D * shp.D, generator=g).cuda())
     f, y = wl["f_test"].cuda(), wl["y_test"].cuda()
     assert eng.cfg.fuse_eval_projection
+    fix_eval_noise(eng)
     conf_f, cor_f, hist_f = eng.eval_calibration_tc(f, y, precision=precision, mc="collapsed")
     eng.cfg.fuse_eval_projection = False
     conf_u, cor_u, hist_u = eng.eval_calibration_tc(f, y, precision=precision, mc="collapsed")
