@@ -219,6 +219,8 @@ def gp_pretrain(gp_weighter: GaussianProcessTemplateWeighter, feats_hat: torch.T
         eng.cosine_lr(ep, int(epochs), 0.0, float(gp_lr))                    # scheduler.step() after every epoch (taskres.py:276)
         losses[ep:ep + 1].copy_(eng.train_step(f, y))
     eng.export_to_module(gp_weighter)
+    if getattr(gp_weighter, "rng", None) == "philox" and int(gp_weighter._rng_state[0]) == int(seed):
+        gp_weighter._rng_state[1] += int(epochs)                             # the engine consumed steps 0 .. epochs-1 of this stream
     hist = losses.tolist()                                                   # one host read for the whole loop
     if log_every:
         for ep, l in enumerate(hist):

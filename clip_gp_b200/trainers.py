@@ -537,8 +537,17 @@ class TipAdapterTrainer(BaseTrainer, _GPInitMixin):
 
     def build_model(self):
         self.clip_weights = F.normalize(F.normalize(self.text_embeddings, dim=-1).mean(dim=1), dim=-1)    # [K,D] (transpose of the reference's [D,K])
-        self.gp_weighter = None
+        self.gp_weighter = getattr(self, "gp_weighter", None)
         self.model = None
+
+    def zero_shot(self) -> Dict[str, Any]:
+        """tip_adapter.py:206-221: CLIP logits on the test features (MC-averaged GP logits once the weighter is trained)."""
+        with torch.no_grad():
+            res = metrics.evaluate_calibration(self._clip_logits(ops.row_normalize(self.features_test)), self.labels_test)
+        self.zero_shot_metrics = {"top1_acc": res["top1_acc"], "ece": res["ece"], "aece": res["aece"],
+                                  "calibration": res["calibration"], "adaptive_calibration": res["adaptive_calibration"]}
+        print("Zero-Shot accuracy on test: " + str(round(res["top1_acc"], 2)))
+        return self.zero_shot_metrics
 
     def _clip_logits(self, feats_hat):
         if self.gp_weighter is not None:
