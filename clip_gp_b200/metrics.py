@@ -158,15 +158,22 @@ def aece_from_bins(out: torch.Tensor, n: int, n_bins_requested: int) -> Tuple[fl
 # reference-named entry points
 # ------------------------------------------------------------------------------------------------
 def compute_accuracy(logits: torch.Tensor, labels: torch.Tensor, topk: Tuple[int, ...] = (1,)) -> List[float]:
-    """utils/metrics.py:9-36.  Only top-1 is used by the reference trainers; k > 1 is not implemented."""
-    if any(k != 1 for k in topk):
-        raise NotImplementedError("clip_gp_b200.metrics.compute_accuracy implements top-1 only")
+    """utils/metrics.py:9-36: top-k accuracies in percent.  Top-1 (the only one the reference trainers use) comes from the fused
+    calibration pass (arg-max with first-index tie break, as `topk`'s largest-first order); k > 1 counts the rows whose label logit
+    is beaten by fewer than k others (ties resolved in favour of the label, the documented-undefined case of torch.topk)."""
     n = labels.size(0)
     if n == 0:
         return [0.0] * len(topk)
-    _, _, hist = calibration_pass(logits, labels, n_bins=1, want_conf=False)
-    top1 = int(hist[3, 0].item())
-    return [top1 * (100.0 / n)] * len(topk)
+    out = []
+    for k in topk:
+        if k == 1:
+            _, _, hist = calibration_pass(logits, labels, n_bins=1, want_conf=False)
+            out.append(int(hist[3, 0].item()) * (100.0 / n))
+        else:
+            lab = labels.to(logits.device, torch.int64).view(-1, 1)
+            rank = (logits > logits.gather(1, lab)).sum(dim=1)               # streaming compare + row sum: no sort
+            out.append(float((rank < int(k)).sum().item()) * (100.0 / n))
+    return out
 
 
 def compute_ece_with_bins(logits, labels, n_bins: int = 10) -> Tuple[float, Dict[str, list]]:

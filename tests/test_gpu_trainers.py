@@ -86,3 +86,46 @@ def test_gp_adapter_training_reduces_loss(tmp_path):
             losses.append(float(tr.forward_backward(batch)["loss"]))
     assert sum(losses[-3:]) / 3 < sum(losses[:3]) / 3
     assert int(tr.engine.status.abs().max()) == 0
+
+
+def test_engine_export_state_dict_round_trip():
+    """engine.export_to_module -> module.state_dict() -> a fresh module (reference checkpoint flow, utils/trainer.py:347-414):
+    the reloaded module reproduces the trained engine's prototypes bit for bit given the same base noise."""
+    from clip_gp_b200.engine import EngineConfig, GPAdapterEngine
+    from clip_gp_b200.gp_template_weigher import GaussianProcessTemplateWeighter
+    wl = synth.make_workload("small"); shp = wl["shape"]
+    cfg = NS(adapter=NS(gp_pca_dim=shp.d, gp_kernel_type="rbf"))
+    torch.manual_seed(0)
+    gpw = GaussianProcessTemplateWeighter(wl["E"], cfg, lengthscale=1.3).cuda()
+    eng = GPAdapterEngine(gpw, EngineConfig(S_train=4, S_eval=4, batch_size=shp.B, shots=shp.shots, seed=5))
+    for it in range(3):
+        eng.train_step(wl["f_train"][it * shp.B:(it + 1) * shp.B].cuda(), wl["y_train"][it * shp.B:(it + 1) * shp.B].cuda())
+    proj = torch.nn.Linear(shp.D, shp.D, bias=False).cuda()
+    eng.export_to_module(gpw, proj)
+    sd = {k: v.detach().cpu().clone() for k, v in gpw.state_dict().items()}
+    fresh = GaussianProcessTemplateWeighter(wl["E"], cfg, lengthscale=9.9).cuda()       # different init on purpose
+    missing = fresh.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    eps = torch.randn(shp.C, shp.T, 4, generator=torch.Generator().manual_seed(3)).cuda()
+    with torch.no_grad():
+        assert torch.equal(fresh.sample_prototypes(4, eps=eps), gpw.sample_prototypes(4, eps=eps))
+    assert torch.equal(proj.weight, eng.p("W").view(shp.D, shp.D))
+    assert int(fresh.variational_strategy.variational_params_initialized) == 1           # no re-initialisation of q(u) after a reload
+    # the reloaded module drives a new engine to the same next step
+    eng2 = GPAdapterEngine(fresh, EngineConfig(S_train=4, S_eval=4, batch_size=shp.B, shots=shp.shots, seed=5), proj.weight)
+    eng2.rng_state.copy_(eng.rng_state)
+    eng.skip_update = eng2.skip_update = True
+    f, y = wl["f_train"][:shp.B].cuda(), wl["y_train"][:shp.B].cuda()
+    assert float(eng2.train_step(f, y, use_graph=False)) == pytest.approx(float(eng.train_step(f, y, use_graph=False)), rel=1e-6)
+
+
+def test_topk_accuracy_matches_torch_topk():
+    from clip_gp_b200 import metrics as gm
+    g = torch.Generator().manual_seed(4)
+    logits = torch.randn(500, 37, generator=g); labels = torch.randint(0, 37, (500,), generator=g)
+    got = gm.compute_accuracy(logits.cuda(), labels.cuda(), topk=(1, 3, 5))
+    ref = []
+    for k in (1, 3, 5):                                                     # utils/metrics.py:20-34
+        pred = logits.topk(k, 1, True, True)[1].t()
+        ref.append(float(pred.eq(labels.view(1, -1).expand_as(pred))[:k].reshape(-1).float().sum() * 100.0 / 500))
+    assert got == pytest.approx(ref, abs=1e-5)                              # the reference accumulates the percentage in fp32
