@@ -8,8 +8,12 @@ One "step" = one GP-Adapter optimisation step over one batch of cached features 
 prototypes, projection, logits for every MC sample, per-sample CE, all adjoints, L2 regulariser, AdamW.
 `value` = steps/s with inputs resident in HBM (CUDA events around each step, L2 flushed between steps, max over
 ranks); `e2e` = the same step driven from pinned HOST batches (H2D copy of the batch and D2H read of the loss inside
-the timed region).  N > 1: the S MC samples are sharded over ranks (strong scaling of one optimisation step; S=10 over 8 ranks
-splits 2,2,1,1,1,1,1,1), gradients + loss go through ONE NCCL all-reduce; eval images are sharded over ranks.
+the timed region).  N > 1 (weak scaling): data parallel over the batch -- every rank steps its OWN 128-image batch with all S
+MC samples, the global batch is N * 128, gradients + loss go through ONE NCCL all-reduce inside the captured step; `value`
+counts 128-image batch-steps per second over all ranks (= N x optimisation steps/s; identical to steps/s at N = 1).  The north
+star's S-sharded form of ONE batch (strong scaling of a latency-bound step) is timed next to it (`train_sample_sharded`), and
+so is the full-batch step with the batch split over the ranks.  Eval images are sharded over ranks, the eval GP forward over
+classes.
 `--impl reference` times the CPU oracle (the restated reference path: torch CPU + autograd + AdamW) on the host cores.
 """
 from __future__ import annotations
@@ -140,12 +144,27 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
+def workload_string(name, shp, S):
+    """`config.workload` of BOTH arms (the driver compares them verbatim)."""
+    return (f"{name}: GP-Adapter optimisation step on cached features, C={shp.C} T={shp.T} D={shp.D} d={shp.d} S={S} B={shp.B} "
+            f"shots={shp.shots} kernel={shp.kernel}; per-sample MC cross-entropy + KL + L2, AdamW")
+
+
 def bench_lengthscale(E, d):
-    """Median-heuristic length-scale (gp_template_weigher.py:103-107) on the templates of the first 64 classes; the full
-    C*T = 32 000-point cdist is one-time setup outside the step and both arms use this same value."""
+    """REFERENCE ARM ONLY (CPU oracle): median-heuristic length-scale (gp_template_weigher.py:103-107) on the templates of the
+    first 64 classes; the full C*T = 32 000-point cdist is one-time setup outside the step."""
     from oracle import gp as ogp
     _, _, tr, _, _ = ogp.pca_setup(E, d)
     return ogp.median_lengthscale(tr[:64])
+
+
+def product_lengthscale(gpw):
+    """PRODUCT ARM: the same quantity from the repo's own setup kernel (csrc/setup.cu, exact radix select of the pairwise
+    distances; no oracle import on this arm), on the same 64-class subset so that both arms start from the same value."""
+    import torch.nn.functional as F
+    from clip_gp_b200 import ops
+    tr = gpw._templates_red[:64]
+    return float(ops.median_pairwise_distance(F.normalize(tr.reshape(-1, tr.shape[-1]), p=2, dim=-1).contiguous()))
 
 
 class _Cfg:
@@ -190,8 +209,9 @@ def run_reference(args):
     v = args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: C={shp.C} T={shp.T} D={shp.D} d={shp.d} S={S} B={shp.B} {shp.kernel} (CPU oracle of the reference path)"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_string(args.workload, shp, S),
+                       "arm": "CPU oracle port of the reference path (torch CPU + autograd + torch AdamW) on all host cores"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{args.steps} full optimisation steps (fwd + autograd bwd + AdamW) of the same workload"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -239,17 +259,28 @@ def run_ours(args):
     if world > 1:
         torch.distributed.barrier()
     from clip_gp_b200 import _lib, metrics, synth
+    from clip_gp_b200.dist import sample_split as cdist_sample_split
     from clip_gp_b200.engine import EngineConfig, GPAdapterEngine
     from clip_gp_b200.gp_template_weigher import GaussianProcessTemplateWeighter
 
     wl = synth.make_workload(args.workload)
     shp = wl["shape"]
-    S = shp.S                                            # S=10 over 8 ranks splits 2,2,1,1,1,1,1,1
-    ls = bench_lengthscale(wl["E"], shp.d) if shp.kernel == "rbf" else None
+    S = shp.S
     torch.manual_seed(1)
-    gpw = GaussianProcessTemplateWeighter(wl["E"].to(dev), _Cfg(shp.kernel, shp.d), lengthscale=ls).to(dev)
-    cfg = EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world,
-                       precision=args.precision, graph_collectives=not args.no_graph_collectives)
+    gpw = GaussianProcessTemplateWeighter(wl["E"].to(dev), _Cfg(shp.kernel, shp.d), lengthscale=1.0).to(dev)
+    ls = None
+    if shp.kernel == "rbf":
+        ls = product_lengthscale(gpw)
+        gpw.covar_module.base_kernel.initialize(lengthscale=ls)
+
+    def engine_config(**kw):
+        base = dict(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world, precision=args.precision,
+                    graph_collectives=not args.no_graph_collectives, shard="batch")
+        base.update(kw)
+        return EngineConfig(**base)
+
+    # N > 1: data parallel over the batch (every rank its own B-image batch, all S samples; ONE gradient all-reduce per step)
+    cfg = engine_config()
     eng = GPAdapterEngine(gpw, cfg)
     f_all = wl["f_train"].to(dev)
     y_all = wl["y_train"].to(dev)
@@ -259,7 +290,7 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
 
     def batch(it):
-        lo = (it % nb) * shp.B
+        lo = ((it * world + rank) % nb) * shp.B            # rank r takes batch it * world + r of the (shared) few-shot set
         return lo, lo + shp.B
 
     def sync_all():
@@ -272,14 +303,15 @@ def run_ours(args):
         between steps outside the events, max over ranks).  Returns total ms."""
         Bsz = e.B
         nbb = max(1, f_all.shape[0] // Bsz)
+        dp = world if e.batch_sharded else 1
         for it in range(max(warmup, 3)):
-            lo = (it % nbb) * Bsz
+            lo = ((it * dp + (rank if dp > 1 else 0)) % nbb) * Bsz
             e.train_step(f_all[lo:lo + Bsz], y_all[lo:lo + Bsz])
         sync_all()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         sync_all()
         for it in range(steps):
-            lo = ((warmup + it) % nbb) * Bsz
+            lo = (((warmup + it) * dp + (rank if dp > 1 else 0)) % nbb) * Bsz
             flush.fill_(0.0)                               # L2 flush between timed iterations (outside the events)
             e.in_feat.copy_(f_all[lo:lo + Bsz]); e.in_lab.copy_(y_all[lo:lo + Bsz])
             evs[it][0].record()
@@ -346,24 +378,37 @@ def run_ours(args):
             if prec == args.precision:
                 train_variants[prec] = {"ms_per_step": ms_total / args.steps, "steps_per_s": args.steps / (ms_total * 1e-3)}
                 continue
-            ev = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank,
-                                                   world=world, precision=prec, graph_collectives=not args.no_graph_collectives))
+            ev = GPAdapterEngine(gpw, engine_config(precision=prec))
             msv = time_steps(ev, 10, 3)
-            train_variants[prec] = {"ms_per_step": msv / 10, "steps_per_s": 10 / (msv * 1e-3)}
+            train_variants[prec] = {"ms_per_step": msv / 10, "steps_per_s": world * 10 / (msv * 1e-3)}
             ev._graph = None
             del ev
+
+    # ---------------- N > 1: the north star's S-sharded form of ONE 128-image batch (strong scaling of a latency-bound step)
+    train_sample_sharded = None
+    if world > 1 and S >= world:
+        es = GPAdapterEngine(gpw, engine_config(shard="samples"))
+        mss = time_steps(es, 10, 3) / 10
+        train_sample_sharded = {"ms_per_step": mss, "steps_per_s": 1e3 / mss, "scaling": "strong",
+                                "split": [cdist_sample_split(S, r, world)[1] for r in range(world)],
+                                "note": "MC samples of one batch sharded over the ranks (same Philox stream), ONE all-reduce of the flat gradient "
+                                        "buffer; the per-class GP chain is replicated on every rank, so this form cannot beat one GPU"}
+        es._graph = None
+        del es
 
     # ---------------- full-batch leg (B = N_train = C * shots): the tensor-bound form of the same step
     fullbatch = None
     if not args.no_fullbatch and args.precision != "fp32":
-        Bf = f_all.shape[0]
-        fullbatch = {"B": Bf, "note": "per-sample MC cross-entropy over the whole cached training set; logits [B, S*C] materialised in fp32"}
+        Btot = f_all.shape[0]
+        Bf = Btot // world                                   # N > 1: the 16 000 cached training features are split over the ranks
+        fullbatch = {"B": Btot, "B_per_rank": Bf, "scaling": "strong",
+                     "note": "per-sample MC cross-entropy over the whole cached training set (batch rows split over the ranks, gradient "
+                             "all-reduce); logits [B, S*C] materialised in fp32"}
         for prec in ("bf16", "bf16x3"):
-            ef = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=Bf, shots=shp.shots, seed=1234, rank=rank,
-                                                   world=world, precision=prec, graph_collectives=not args.no_graph_collectives))
+            ef = GPAdapterEngine(gpw, engine_config(batch_size=Bf, precision=prec))
             msf = time_steps(ef, 5, 3) / 5
-            kt = profile_step_kernels(ef, f_all, y_all, shp, flush, reps=2, B=Bf)
-            entry = {"ms_per_step": msf, "steps_per_s": 1e3 / msf, "img_per_s": Bf * 1e3 / msf}
+            kt = profile_step_kernels(ef, f_all[rank * Bf:(rank + 1) * Bf], y_all[rank * Bf:(rank + 1) * Bf], shp, flush, reps=2, B=Bf)
+            entry = {"ms_per_step": msf, "steps_per_s": 1e3 / msf, "img_per_s": Btot * 1e3 / msf}
             gem = {k: v for k, v in kt.items() if k.startswith("tc_gemm_store") and v.get("flops")}
             if gem:
                 # the three logit contractions: logits, d P_hat, d f_hat  (2*B*S*C*D algorithmic flops each)
@@ -383,8 +428,7 @@ def run_ours(args):
     # ---------------- eval leg (on the INITIAL parameters: a fresh engine, so that accuracy / ECE / AECE do not depend on how many
     # optimisation steps the timing loops above happened to run, and are identical for every GPU count): MC-averaged logits + acc/ECE/AECE over this rank's shard of the test features
     eng_train = eng
-    eng = GPAdapterEngine(gpw, EngineConfig(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world,
-                                            precision=args.precision))
+    eng = GPAdapterEngine(gpw, engine_config())
     n_eval = args.eval_n
     f_te, y_te = wl["f_test"][:n_eval], wl["y_test"][:n_eval]
     from clip_gp_b200 import dist as cdist
@@ -417,7 +461,35 @@ def run_ours(args):
     # the whole pass (GP forward -> prototypes | cast -> projection -> normalise | logits + calibration) is one captured CUDA graph over
     # the rank's resident test shard, as a trainer that evaluates after every step (adapter.py:363-380) would hold it
     eval_replay = eng.eval_graph(f_sh, y_sh, precision="bf16x3", mc="collapsed")
-    eval_ms, (conf, correct, hist) = time_eval(eval_replay)
+    # the whole metric -- logits + accuracy + ECE histogram, counter all-reduce, (conf, hit) all-gather, AECE rank-select -- as ONE graph
+    eval_pass = eng.eval_metrics_graph(f_sh, y_sh, n_eval, precision="bf16x3", mc="collapsed")
+    eval_ms, _ = time_eval(eval_pass)
+    eval_graph_only_ms, _ = time_eval(eval_replay)
+
+    # e2e eval: pinned HOST features of this rank's shard in, metrics out (H2D of the shard + D2H of counters inside the timed region)
+    f_host_sh, y_host_sh = f_te[sl].contiguous().pin_memory(), y_te[sl].contiguous().pin_memory()
+    f_static, y_static = eval_pass.inputs
+
+    def eval_e2e_once():
+        f_static.copy_(f_host_sh, non_blocking=True)
+        y_static.copy_(y_host_sh, non_blocking=True)
+        _, _, hg, aout = eval_pass()
+        cnt_ = metrics.counters_from_hist(hg, n_eval)                      # D2H: 32 integer counters
+        return cnt_, metrics.ece_from_counters(cnt_)[0], metrics.aece_from_bins(aout, n_eval, 10)[0]
+
+    for _ in range(2):
+        eval_e2e_once()
+    sync_all()
+    t0 = time.perf_counter()
+    E2E_REPS = 5
+    for _ in range(E2E_REPS):
+        eval_e2e_once()
+    sync_all()
+    tt = torch.tensor([(time.perf_counter() - t0) / E2E_REPS], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    eval_e2e_s = float(tt.item())
+    cnt, ece, aece = eval_e2e_once()                           # the reported metrics: ONE pass (counters and AECE bins of the same draw)
     eval_variants = {}
     for nm, fn in (("bf16x3_collapsed_eager_launches", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16x3", mc="collapsed")),
                    ("fp32_ffma_collapsed", eval_fp32),
@@ -433,16 +505,26 @@ def run_ours(args):
     gemm_ms, _ = time_eval(lambda: _tc.logits_calibration(fb, Bop, 100.0 * mcs, y_sh, 10), reps=5)
     gemm_flops = 2.0 * f_sh.shape[0] * shp.C * shp.D * S
     # global metrics: all-reduce only the integer counters; AECE needs the gathered confidences
-    hist_g, conf_g, cor_g = cdist.global_calibration(hist, conf, correct, n_eval, world)
-    cnt = metrics.counters_from_hist(hist_g, n_eval)
-    ece, _ = metrics.ece_from_counters(cnt)
-    _, out = metrics.aece_pass(conf_g, cor_g, 10)
-    aece, _ = metrics.aece_from_bins(out, n_eval, 10)
+    # calibration check on a set whose bins err in both directions (on the plain synthetic set every bin is over-confident and
+    # ECE == AECE to rounding, so an AECE rank-edge bug could hide): rank 0, single pass, small
+    calib_check = None
+    if rank == 0:
+        with torch.no_grad():
+            Pm0 = torch.nn.functional.normalize(wl["E"].mean(1), dim=-1)
+        f_mx, y_mx = synth.make_mixed_calibration_set(wl["mu"], Pm0, 20000, 7, shp.noise)
+        eng1 = GPAdapterEngine(gpw, engine_config(world=1, rank=0))
+        r_mx = eng1.evaluate(f_mx.to(dev), y_mx.to(dev), precision="bf16x3")
+        calib_check = {"n_images": 20000, "top1_acc": r_mx["top1_acc"], "ece": r_mx["ece"], "aece": r_mx["aece"],
+                       "bin_gap_signs": [int((a_ > c_) - (a_ < c_)) for a_, c_ in zip(r_mx["calibration"]["bin_acc"], r_mx["calibration"]["bin_conf"])],
+                       "set": "synth.make_mixed_calibration_set: half over-confident noisy features, half under-confident 4-way ambiguous features"}
+        del eng1
 
     def shutdown():
         # captured graphs hold NCCL work: release them before the process group goes away
         eng._graph = None
         eng_train._graph = None
+        eval_replay.release()
+        eval_pass.release()
         import gc
         gc.collect()
         torch.cuda.synchronize(dev)
@@ -454,9 +536,10 @@ def run_ours(args):
         shutdown()
         return
     pk = peaks()
-    steps_per_s = args.steps / (ms_total * 1e-3)
+    steps_per_s = world * args.steps / (ms_total * 1e-3)      # 128-image batch-steps per second over all ranks
     # dominant kernel of the step -> roofline
-    dom = max(ktimes, key=lambda k: ktimes[k]["ms"]) if ktimes else None
+    own = {k: v for k, v in ktimes.items() if not k.startswith("nccl_")}       # collectives are not this repo's kernels
+    dom = max(own, key=lambda k: own[k]["ms"]) if own else None
     roof = None
     if dom is not None:
         base = dom.split("(")[0]
@@ -487,23 +570,24 @@ def run_ours(args):
                              "fp32 FFMA GEMM (exact mode) reported against the bf16 tensor peak")}
     line = {
         "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: C={shp.C} T={shp.T} D={shp.D} d={shp.d} S={S} B={shp.B} shots={shp.shots} kernel={shp.kernel}, "
-                               f"per-sample MC cross-entropy + KL + L2, AdamW; MC samples sharded over {world} rank(s)",
+        "config": {"workload": workload_string(args.workload, shp, S),
+                   "global_batch": world * shp.B, "parallelism": f"dp{world}" if world > 1 else "single GPU",
+                   "value_counts": "128-image batch-steps per second summed over the ranks (one optimisation step consumes one batch per rank)",
                    "l2_flush": "256 MB device buffer written between timed steps", "precision": {"fp32": "fp32 (FFMA GEMMs, fp64 K_ZZ Cholesky)",
                                  "bf16x3": "tcgen05 GEMMs on split-bf16 operands (fp32-grade products; the reference's GPU path is TF32), fp32 everywhere else, fp64 K_ZZ Cholesky",
                                  "bf16": "tcgen05 bf16 GEMMs, fp32 everywhere else, fp64 K_ZZ Cholesky"}[args.precision],
                    "cuda_graph": eng_train._graph is not None, "two_stream_overlap": bool(eng_train.cfg.overlap),
-                   "multi_gpu": (f"MC samples sharded over {world} ranks (same Philox stream), ONE all-reduce of the flat gradient buffer + loss; "
-                                 "step captured in a CUDA graph incl. NCCL" + ("; GP kernels class-sharded" if eng_train.class_sharded else ""))
+                   "multi_gpu": (f"data parallel over the batch: {world} ranks x {shp.B} images, all {S} MC samples on every rank (same Philox "
+                                 "draw), ONE all-reduce of the flat gradient buffer + loss (7.6 MB); step captured in a CUDA graph incl. NCCL")
                    if world > 1 else None,
                    "loss_last": loss_last},
-        "e2e": {"value": args.steps / e2e_pipe_s, "unit": UNIT, "h2d_bytes_per_step": shp.B * shp.D * 4 + shp.B * 8, "d2h_bytes_per_step": 4,
+        "e2e": {"value": world * args.steps / e2e_pipe_s, "unit": UNIT, "h2d_bytes_per_step": shp.B * shp.D * 4 + shp.B * 8, "d2h_bytes_per_step": 4,
                 "api": "GPAdapterEngine.train_steps_host: per step H2D of the batch from pinned host memory (copy stream, double buffered) + "
                        "asynchronous D2H of the loss into pinned memory, one host synchronisation at the end of the timed region",
-                "synchronous_value": args.steps / e2e_s,
+                "synchronous_value": world * args.steps / e2e_s,
                 "synchronous_api": "GPAdapterEngine.train_step(host batch) + loss.item() every step (blocking read-back, as the reference logs)"},
         "gpu_launches": int(launches_per_step) * args.steps,
         "gpu_launches_per_step": int(launches_per_step),
@@ -511,11 +595,19 @@ def run_ours(args):
         "roofline": roof,
         "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in ktimes.items()},
         "train_variants": train_variants,
+        "train_sample_sharded": train_sample_sharded,
         "train_fullbatch": fullbatch,
-        "eval": {"metric": "eval_img_per_s (projection + MC-averaged logits + acc/ECE histogram, device resident)",
-                 "value": n_eval / (eval_ms * 1e-3), "unit": "img/s", "n_images": n_eval, "ms": eval_ms, "S_eval": S,
-                 "top1_acc": cnt.top1 * 100.0 / n_eval, "ece": ece, "aece": aece,
-                 "form": "one CUDA graph (engine.eval_graph): GP forward + prototypes on a side stream next to cast / projection / normalise, then the tcgen05 split-bf16 (bf16x3) collapsed logit-mean GEMM [N,D]x[C,D]^T with the calibration epilogue",
+        "eval": {"metric": "eval_img_per_s (projection + MC-averaged logits + accuracy + ECE histogram + AECE rank-select, device resident)",
+                 "value": n_eval / (eval_ms * 1e-3), "unit": "img/s", "n_images": n_eval, "ms": eval_ms, "S_eval": S, "scaling": "strong",
+                 "graph_only_ms": eval_graph_only_ms,
+                 "e2e": {"value": n_eval / eval_e2e_s, "unit": "img/s", "ms": eval_e2e_s * 1e3,
+                         "h2d_bytes_per_pass": int(f_host_sh.numel() * 4 + y_host_sh.numel() * 8), "d2h_bytes_per_pass": 32 * 8 + 10 * 3 * 8,
+                         "api": "pinned host features of the rank's shard -> H2D -> eval graph replay -> counter all-reduce -> AECE select -> "
+                                "D2H of the counters (accuracy / ECE / AECE on the host)"},
+                 "top1_acc": cnt.top1 * 100.0 / n_eval, "ece": ece, "aece": aece, "calibration_check": calib_check,
+                 "multi_gpu": (f"images sharded over {world} ranks; the eval GP forward runs on C/{world} classes per rank and one 2 MB "
+                               "all-reduce completes the mean prototypes; counters: one all-reduce, AECE: all-gather of (conf, hit)") if world > 1 else None,
+                 "form": "one CUDA graph (engine.eval_metrics_graph; graph_only_ms = engine.eval_graph without the AECE / collective tail): GP forward + prototypes on a side stream next to cast / projection / normalise, then the tcgen05 split-bf16 (bf16x3) collapsed logit-mean GEMM [N,D]x[C,D]^T with the calibration epilogue",
                  "variants": eval_variants},
         "roofline_eval_gemm": {"kernel": "tc_gemm_kernel (EPI_ROWSTATS), materialised MC logits [N,D]x[S*C,D]^T accumulated over s in TMEM",
                                "bound": "tensor", "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

@@ -72,6 +72,21 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return r;
 }
 
+// Ask the memory system to bring [p, p + bytes) into L2 (one `cp.async.bulk.prefetch.L2` per 32 KB, issued by the calling thread;
+// no register or shared-memory cost, nothing to wait for).  The per-class GP kernels call it at the top of a class CTA for the
+// operands of their LATER streaming phases (text bank rows, inducing points, saved factors): the DRAM latency of those streams
+// then overlaps the sequential factorisation phases instead of being paid chunk by chunk when the phase starts.
+__device__ __forceinline__ void l2_prefetch(const void* p, size_t bytes) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uintptr_t end = (a + bytes + 15) & ~(uintptr_t)15;
+    a &= ~(uintptr_t)15;
+    while (a < end) {
+        const unsigned n = (unsigned)((end - a) < 32768 ? (end - a) : 32768);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
+        a += n;
+    }
+}
+
 __device__ __forceinline__ float softplusf(float x) {
     // torch.nn.functional.softplus (beta=1, threshold=20)
     return x > 20.f ? x : log1pf(expf(x));

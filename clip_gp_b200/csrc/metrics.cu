@@ -5,6 +5,7 @@
 // pass over a row for sum-exp hits L1/L2), everything else is O(N).
 #include <float.h>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace clipgp {
@@ -467,6 +468,11 @@ extern "C" int clipgp_aece_bins(const float* conf, const uint8_t* correct, int64
     cudaStream_t st = (cudaStream_t)stream;
     int64_t blocks = (N + 4095) / 4096;
     blocks = blocks < 1 ? 1 : (blocks > (int64_t)num_sms() ? (int64_t)num_sms() : blocks);
+    {
+        static int forced = -2;
+        if (forced == -2) { const char* e = getenv("CLIPGP_AECE_BLOCKS"); forced = e ? atoi(e) : -1; }
+        if (forced > 0) blocks = forced;
+    }
     const size_t ws_bytes = aece_ws_bytes(n_bins);
     void* ws = workspace;
     CLIPGP_REQUIRE(ws == nullptr || (size_t)workspace_bytes >= ws_bytes, "aece_bins: workspace too small (%lld < %lld bytes)",

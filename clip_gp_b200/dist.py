@@ -40,6 +40,10 @@ def gather_variable(t: torch.Tensor, counts: List[int]) -> torch.Tensor:
         return t
     world = td.get_world_size()
     mx = max(counts)
+    if min(counts) == mx:                                   # equal shards (the usual case): ONE collective into one tensor, no padding
+        out = torch.empty(world * mx, dtype=t.dtype, device=t.device)
+        td.all_gather_into_tensor(out, t.contiguous())
+        return out
     pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
     pad[: t.numel()] = t
     bufs = [torch.empty(mx, dtype=t.dtype, device=t.device) for _ in range(world)]

@@ -60,6 +60,13 @@ class EngineConfig:
     seed: int = 0
     rank: int = 0
     world: int = 1
+    shard: str = "samples"              # world > 1, what the ranks split in a training step:
+                                        #   "samples": the S MC samples of ONE batch (north star; strong scaling of a latency-bound step)
+                                        #   "batch":   data parallel -- every rank takes its own [B, D] batch and all S samples, the global
+                                        #              batch is world * B (weak scaling when B is fixed per rank, strong when the caller
+                                        #              splits a fixed batch); loss / gradients are means over the global batch
+    shard_eval_classes: bool = True     # world > 1: the eval GP forward runs on this rank's C / world classes only and the [C, D] mean
+                                        # prototypes are completed by one 2 MB all-reduce (instead of replicating the per-class chain)
 
 
 class GPAdapterEngine:
@@ -77,9 +84,15 @@ class GPAdapterEngine:
         Cn, T, D, n, d = self.C, self.T, self.D, self.n, self.d
         # MC samples of this rank: an even split, the first S % world ranks take one more (S=10 over 8 ranks
         # is 2,2,1,1,1,1,1,1); every rank draws its slice [s_offset, s_offset + S_local) of the same Philox stream
-        if cfg.S_train < cfg.world:
-            raise ValueError(f"S_train={cfg.S_train} < world={cfg.world}: shard the batch instead")
-        self.s_offset, self.S_local = dist.sample_split(cfg.S_train, cfg.rank, cfg.world)
+        if cfg.shard not in ("samples", "batch"):
+            raise ValueError(f"unknown shard mode {cfg.shard!r}")
+        self.batch_sharded = bool(cfg.shard == "batch" and cfg.world > 1)
+        if self.batch_sharded:
+            self.s_offset, self.S_local = 0, cfg.S_train
+        else:
+            if cfg.S_train < cfg.world:
+                raise ValueError(f"S_train={cfg.S_train} < world={cfg.world}: use EngineConfig(shard='batch')")
+            self.s_offset, self.S_local = dist.sample_split(cfg.S_train, cfg.rank, cfg.world)
         self.class_sharded = bool(cfg.shard_classes and cfg.world > 1)
         self.c_lo, self.c_hi = dist.shard_range(self.C, cfg.rank, cfg.world) if self.class_sharded else (0, self.C)
         self.E = gpw._templates.detach().contiguous()
@@ -387,14 +400,16 @@ class GPAdapterEngine:
         B, Cn, D = self.B, self.C, self.D
         per_sample, S, SC, alpha = self._dims()
         tcm = cfg.precision != "fp32"
+        # mean over the (global) batch and the S_train samples; every rank contributes its share and the all-reduce sums them
+        dp = cfg.world if self.batch_sharded else 1
         if per_sample:
             rows, rpl = B * S, S
-            loss_scale = 1.0 / (B * cfg.S_train)
+            loss_scale = 1.0 / (B * cfg.S_train * dp)
         else:
             rows, rpl = B, 1
             loss_scale = 1.0 / (B * cfg.world)
-            if cfg.world > 1:
-                raise NotImplementedError("logit_mean loss is not S-sharded (it is not a sum over samples)")
+            if cfg.world > 1 and not self.batch_sharded:
+                raise NotImplementedError("logit_mean loss is not S-sharded (it is not a sum over samples); use shard='batch'")
         if tcm:
             # two-phase softmax cross-entropy: row statistics + loss, then dlogits straight into the bf16 operands of the two
             # adjoint GEMMs (dlogits [B, SC] and dlogits^T [SC, B]); no fp32 dlogits
@@ -628,22 +643,31 @@ class GPAdapterEngine:
         w = torch.empty(S, Cn, T, **f32)
         a = GpArgs.from_buffer_copy(self.gp_args)
         a.S, a.s_offset, a.S_total = S, 0, S
-        a.c_begin, a.c_count = 0, 0                             # evaluation: every rank needs the prototypes of all classes
+        a.c_begin, a.c_count = 0, 0
         a.eps_save = None
         a.proto_E = a.proto_P_hat = a.proto_norm = a.proto_bf16 = a.proto_mean_hat = None
         a.w, a.kl = w.data_ptr(), None
         a.L = a.A = a.R = None
         a.Ksave = self._eval_ksave()                            # hand-over buffer of the two-kernel fast path
         bump = self._eval_noise(a, S)
-        Pm = torch.empty(Cn, D, **f32)
         fused = bool(self.cfg.fuse_prototypes and lib.clipgp_gp_fused_proto_ok(T, n, self.d, D, S))
+        # multi-GPU: this rank's CTAs cover its class shard only; the all-reduce below completes the [C, D] matrix on every rank
+        # (the draws are keyed by (seed, step, c, t, s), so the shard does not change them)
+        shard = bool(fused and self.cfg.world > 1 and self.cfg.shard_eval_classes)
+        Pm = torch.zeros(Cn, D, **f32) if shard else torch.empty(Cn, D, **f32)
+        if shard:
+            lo, hi = dist.shard_range(Cn, self.cfg.rank, self.cfg.world)
+            a.c_begin, a.c_count = lo, max(hi - lo, 0)
         if fused:       # the class's CTA also averages its unit prototypes: no separate prototype pass
             a.proto_E, a.proto_D, a.proto_mean_hat = self.E.data_ptr(), D, Pm.data_ptr()
         with torch.cuda.device(self.dev):
-            _lib.check(lib.clipgp_gp_forward(C.byref(a), st), "gp_forward(eval)")
+            if not shard or a.c_count > 0:
+                _lib.check(lib.clipgp_gp_forward(C.byref(a), st), "gp_forward(eval)")
             if not fused:
                 _lib.check(lib.clipgp_proto_forward(w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, None, None, None,
                                                     Pm.data_ptr(), None, 1, st), "proto_forward(eval)")
+        if shard:
+            torch.distributed.all_reduce(Pm)
         if bump:
             self.eval_rng_state[1:2].add_(1)
         self.last_eval_w = w
@@ -804,10 +828,49 @@ class GPAdapterEngine:
         with torch.cuda.graph(g):
             out = self.eval_calibration_tc(f, y, S=S, n_bins=n_bins, precision=precision, mc=mc)
 
+        holder = [g]
+        del g
+
         def replay():
-            g.replay()
+            holder[0].replay()
             return out
-        replay.graph, replay.inputs = g, (f, y)
+        replay.inputs = (f, y)
+        replay.release = holder.clear          # a captured graph that holds NCCL work must be dropped before the process group goes away
+        return replay
+
+    @torch.no_grad()
+    def eval_metrics_graph(self, features: torch.Tensor, labels: torch.Tensor, n_total: int, S=None, n_bins=10,
+                           precision="bf16x3", mc="collapsed"):
+        """The WHOLE evaluation metric of this rank's image shard as one captured CUDA graph: the tensor-core eval pass
+        (eval_calibration_tc) -> all-reduce of the integer calibration counters -> all-gather of the (confidence, hit) pairs ->
+        AECE rank-select over the global set.  Returns a callable () -> (conf, correct, hist_global [4, n_bins] int64,
+        aece_bins [3, nb] int64) with static outputs; `.inputs` are the static (features, labels) to copy new data into,
+        `.release()` drops the graph (before the process group is destroyed).  `n_total` = images over all ranks."""
+        from . import metrics as _m
+        f = features.to(self.dev).float().contiguous()
+        y = labels.to(self.dev).to(torch.int64).contiguous()
+        world = self.cfg.world
+        _m._boundaries(n_bins, self.dev)
+
+        def whole():
+            conf, correct, hist = self.eval_calibration_tc(f, y, S=S, n_bins=n_bins, precision=precision, mc=mc)
+            hg, cg, og = dist.global_calibration(hist, conf, correct, n_total, world)
+            _, aout = _m.aece_pass(cg, og, n_bins)
+            return conf, correct, hg, aout
+        for _ in range(2):                                      # warm-up: kernel attributes, edge cache, NCCL channels
+            whole()
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = whole()
+        holder = [g]
+        del g
+
+        def replay():
+            holder[0].replay()
+            return out
+        replay.inputs = (f, y)
+        replay.release = holder.clear
         return replay
 
     # ------------------------------------------------------------------ sync back to the nn.Module

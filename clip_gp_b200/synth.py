@@ -94,3 +94,30 @@ def trained_like_q(C: int, n: int, seed: int):
     m = 0.5 * torch.randn(C, n, generator=g)
     Lq = torch.eye(n).repeat(C, 1, 1) + 0.1 * torch.randn(C, n, n, generator=g).tril()
     return m, Lq
+
+
+def make_mixed_calibration_set(mu: torch.Tensor, prototypes: torch.Tensor, N: int, seed: int, noise: float = 6.0,
+                               delta: float = 0.05):
+    """A test set whose reliability diagram errs in BOTH directions, so that ECE (equal-width bins) and AECE (equal-mass bins)
+    differ.  Half of the images are the usual noisy features (over-confident at logit scale 100).  The other half are placed
+    exactly between FOUR class prototypes: f is the combination of unit rows P_y, P_j1..3 with f . P_y = 1 and f . P_jk = 1 - delta
+    (a 4 x 4 Gram solve per image), so the classifier is right but only ~60-75 % confident (under-confident).  On make_test_set
+    alone every bin errs the same way and both metrics collapse to |mean conf - acc|.  `prototypes` [C, D]: the unit class
+    prototypes the evaluated model uses (or close to them)."""
+    g = torch.Generator().manual_seed(seed + 29)
+    C, D = mu.shape
+    n_a = N // 2
+    n_b = N - n_a
+    f_a, y_a = make_test_set(mu, n_a, seed + 31, noise)
+    P = F.normalize(prototypes.detach().float().cpu(), dim=-1)
+    y_b = torch.randint(0, C, (n_b,), generator=g)
+    offs = torch.stack([torch.randperm(C - 1, generator=g)[:3] + 1 for _ in range(n_b)])           # three distinct other classes
+    idx = torch.cat([y_b[:, None], (y_b[:, None] + offs) % C], dim=1)                               # [n_b, 4]
+    Ps = P[idx]                                                                                     # [n_b, 4, D]
+    G = Ps @ Ps.transpose(1, 2)
+    d = delta * (0.6 + 0.8 * torch.rand(n_b, 1, generator=g))
+    t = torch.cat([torch.ones(n_b, 1), (1.0 - d).expand(n_b, 3)], dim=1)
+    coef = torch.linalg.solve(G, t.unsqueeze(-1))                                                   # f . P_i = t_i
+    f_b = F.normalize((coef * Ps).sum(1), dim=-1)
+    perm = torch.randperm(N, generator=g)
+    return torch.cat([f_a, f_b])[perm].contiguous(), torch.cat([y_a, y_b])[perm].contiguous()

@@ -55,18 +55,50 @@ for shard_classes in (True, False):
     ok &= good
     if rank == 0:
         print(f"shard_classes={shard_classes}: loss {lm:.6f} vs {ls_:.6f}, grad rel err {e_g:.2e}, params after 3 steps: {100 * e_p:.3f} % of entries differ by > 1e-5 (max {float(dp.max()):.1e}) -> {'OK' if good else 'MISMATCH'}")
+# data parallel over the batch: rank r steps rows [r B, (r+1) B) of a world*B batch == one GPU stepping the whole world*B batch
+multi = make(world, rank, shard="batch")
+torch.manual_seed(1)
+gpw1 = GaussianProcessTemplateWeighter(wl["E"].to(dev), bench._Cfg(shp.kernel, shp.d), lengthscale=ls).to(dev)
+single = GPAdapterEngine(gpw1, EngineConfig(S_train=S, S_eval=S, batch_size=world * shp.B, shots=shp.shots, seed=77, precision=precision))
+multi.skip_update = single.skip_update = True
+lo = rank * shp.B
+lm = float(multi.train_step(f[lo:lo + shp.B], y[lo:lo + shp.B], use_graph=False))
+ls_ = float(single.train_step(f[:world * shp.B], y[:world * shp.B], use_graph=False))
+e_g = rel(multi.flat_g[:-1], single.flat_g[:-1])
+good = abs(lm - ls_) <= 1e-5 * abs(ls_) and e_g < 2e-4
+ok &= good
+if rank == 0:
+    print(f"shard=batch: loss {lm:.6f} vs {ls_:.6f} (single GPU, batch {world * shp.B}), grad rel err {e_g:.2e} -> {'OK' if good else 'MISMATCH'}")
+multi.skip_update = False
+for it in range(3):          # graph-captured DP steps (NCCL inside the graph) run and stay finite
+    multi.train_step(f[lo:lo + shp.B], y[lo:lo + shp.B])
+assert torch.isfinite(multi.flat_p).all()
+multi._graph = None
 # evaluation: image shards + counter all-reduce == single GPU, bit for bit
 eng = make(world, rank); ref = make(1, 0)
 ft, yt = wl["f_test"].to(dev), wl["y_test"].to(dev)
 n = ft.shape[0]
 lo, hi = cdist.shard_range(n, rank, world)
-conf, correct, hist = eng.eval_calibration_tc(ft[lo:hi], yt[lo:hi], precision="bf16x3", mc="collapsed")
+conf, correct, hist = eng.eval_calibration_tc(ft[lo:hi], yt[lo:hi], precision="bf16x3", mc="collapsed")     # class-sharded GP forward + all-reduce
 hist_g, conf_g, cor_g = cdist.global_calibration(hist, conf, correct, n, world)
 conf1, cor1, hist1 = ref.eval_calibration_tc(ft, yt, precision="bf16x3", mc="collapsed")
 same = torch.equal(hist_g, hist1) and torch.equal(conf_g, conf1) and torch.equal(cor_g, cor1)
 ok &= same
 if rank == 0:
-    print(f"eval: counters / confidences identical to single GPU: {same} (top-1 {int(hist1[3, 0])}/{n})")
+    print(f"eval (images sharded, GP forward class-sharded): counters / confidences identical to single GPU: {same} (top-1 {int(hist1[3, 0])}/{n})")
+# the captured eval graph (NCCL all-reduce of the prototypes inside) replays to the eager result of the same draw
+eng2 = make(world, rank)
+from tests.helpers import fix_eval_noise
+fix_eval_noise(eng2); fix_eval_noise(ref)
+rp = eng2.eval_graph(ft[lo:hi], yt[lo:hi], precision="bf16x3", mc="collapsed")
+cg, og, hg = rp()
+hgg, cgg, ogg = cdist.global_calibration(hg, cg, og, n, world)
+c1, o1, h1 = ref.eval_calibration_tc(ft, yt, precision="bf16x3", mc="collapsed")
+same2 = torch.equal(hgg, h1) and torch.equal(cgg, c1)
+ok &= same2
+rp.release()
+if rank == 0:
+    print(f"eval graph replay (class-sharded, in-graph NCCL) identical to single GPU: {same2}")
     print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
 torch.cuda.synchronize()
 td.destroy_process_group()
