@@ -119,6 +119,11 @@ _SIGNATURES = {
                                        C.c_void_p]),
     "clipgp_tc_gemm_store_splitk": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_float, C.c_void_p, c_i64,
                                               C.c_void_p]),
+    "clipgp_tc_gemm_tf32": (C.c_int, [C.c_void_p, C.c_int, c_i64, C.c_void_p, C.c_int, c_i64, c_i64, C.c_float, C.c_void_p, c_i64, C.c_int,
+                                      C.c_void_p]),
+    "clipgp_tc_logits_calibration_tf32": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, c_i64, C.c_float, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_tc_logits_calibration": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, c_i64, c_i64, C.c_float, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_void_p]),

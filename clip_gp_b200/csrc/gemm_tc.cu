@@ -52,6 +52,9 @@ struct Params {
     const float* boundaries; int n_bins;
     long long* bin_count; unsigned long long* bin_conf_fx; long long* bin_correct; long long* top1;
     const int* key_class; float beta; float tip_alpha;   // EPI_TIP: class of every key (column), exp(-beta(1-aff)), alpha
+    int elt;                    // operand element size: 2 = bf16 (kind::f16), 4 = fp32 read as TF32 (kind::tf32; no operand cast at all)
+    int a_mn, b_mn;             // operand given MN-major: A as [K, M] / B as [K, N] row-major (e.g. dlogits [B, S*C] as the A = dlogits^T
+                                // operand of d P_hat = dlogits^T f_hat): the transposed copy is never made, the tensor core reads it in place
     int norm_cols;              // EPI_ROWSTATS: the first norm_cols columns (a multiple of BN) are not classes but the projected feature
                                 // y = f W^T; their squared sum gives 1 / max(|y|, 1e-12), which scales the class columns that follow
                                 // (F.normalize of the projection, adapter.py:239-240, without materialising it)
@@ -132,9 +135,31 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     const uint32_t hi = 64u | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
-// cute::UMMA::InstrDescriptor for kind::f16: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major,
-// N >> 3 in [17,23), M >> 4 in [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// MN-major operands (see cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): a 128-byte line runs along M/N, a group of
+// K rows forms one swizzle atom, the stage's K groups are stacked SBO apart and consecutive 128-byte M/N blocks LBO apart (one TMA
+// box of [k rows of the stage][128 B] per M/N block, box after box).
+//   16-bit elements: SWIZZLE_128B (16-byte chunks, 8 K rows per atom: SBO = 1024 B), layout type 2;
+//   32-bit elements (TF32): the only MN-major layout the tensor core accepts is SWIZZLE_128B_BASE32B (32-byte chunks XOR-ed with
+//   the row index mod 4, i.e. 4 K rows per atom: SBO = 512 B), layout type 1, loaded with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, int elt) {
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    const uint32_t hi = (elt == 4) ? (32u | (1u << 14) | (1u << 29)) : (64u | (1u << 14) | (2u << 29));
+    return ((uint64_t)hi << 32) | lo;
+}
+// cute::UMMA::InstrDescriptor: D = F32 (1 << 4), A / B format in [7,10) / [10,13) (1 = BF16, 2 = TF32), A / B major in bit 15 / 16
+// (0 = K-major, 1 = MN-major), N >> 3 in [17,23), M >> 4 in [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int elt, int a_mn, int b_mn) {
+    const uint32_t fmt = (elt == 4) ? 2u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a_mn != 0) << 15) | ((uint32_t)(b_mn != 0) << 16) |
+           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 // Work item -> (m block, first n block, K-block range, accumulate-atomically flag).
 struct Item { int m_blk, n_first, kb0, kb1, atomic; };
@@ -209,14 +234,22 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 const Item it = decode_item(p, item);
                 const int m_blk = it.m_blk, kb0 = it.kb0, kb1 = it.kb1;
+                const int bke = 128 / p.elt;                              // K elements per 128-byte line: 64 bf16 / 32 tf32
+                const int mnb = 128 / p.elt;                              // M/N elements per 128-byte line of an MN-major operand
                 for (int nn = 0; nn < p.n_per_item; ++nn) {
                     const int n_blk = it.n_first + nn;
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         unsigned char* sa = smem + stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        tma_load_2d(sa, &map_a, &full_bar[stage], (kb * BK) % p.Ka, m_blk * BM);
-                        tma_load_2d(sa + A_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+                        if (!p.a_mn) tma_load_2d(sa, &map_a, &full_bar[stage], (kb * bke) % p.Ka, m_blk * BM);
+                        else
+                            for (int blk = 0; blk < BM / mnb; ++blk)      // one [bke k rows][128 B] box per 128-byte block of rows
+                                tma_load_2d(sa + blk * (bke * 128), &map_a, &full_bar[stage], m_blk * BM + blk * mnb, kb * bke);
+                        if (!p.b_mn) tma_load_2d(sa + A_BYTES, &map_b, &full_bar[stage], kb * bke, n_blk * BN);
+                        else
+                            for (int blk = 0; blk < BN / mnb; ++blk)
+                                tma_load_2d(sa + A_BYTES + blk * (bke * 128), &map_b, &full_bar[stage], n_blk * BN + blk * mnb, kb * bke);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -228,6 +261,13 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t idesc = make_idesc(p.elt, p.a_mn, p.b_mn);
+            const int bke = 128 / p.elt;
+            // one instruction consumes 32 bytes of K: K-major -> the next 32 bytes of every 128-byte row (descriptor + 2);
+            // MN-major -> the next 32 / elt K rows = (32 / elt) / 8 swizzle atoms of 1024 bytes (descriptor + 64 per atom)
+            const uint64_t a_step = p.a_mn ? (uint64_t)((32 / p.elt) / 8 * 64) : 2ull;
+            const uint64_t b_step = p.b_mn ? (uint64_t)((32 / p.elt) / 8 * 64) : 2ull;
+            const uint32_t lbo = (uint32_t)(bke * 128);                   // MN-major: distance between 128-byte M/N blocks
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 const Item it = decode_item(p, item);
                 const int kb0 = it.kb0, kb1 = it.kb1;
@@ -239,11 +279,14 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                         mbar_wait(&full_bar[stage], phase);
                         fence_after();
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+                        const uint64_t adesc = p.a_mn ? make_smem_desc_mn(sa, lbo, p.elt) : make_smem_desc(sa);
+                        const uint64_t bdesc = p.b_mn ? make_smem_desc_mn(sa + A_BYTES, lbo, p.elt) : make_smem_desc(sa + A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / UK; ++k)
-                            umma_bf16(tmem_d, adesc + (uint64_t)(k * (UK * 2 / 16)), bdesc + (uint64_t)(k * (UK * 2 / 16)), kIdesc,
-                                      (kb > kb0 || k != 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) {                     // 128-byte K line / 32 bytes per instruction
+                            const uint32_t accum = (kb > kb0 || k != 0) ? 1u : 0u;
+                            if (p.elt == 4) umma_tf32(tmem_d, adesc + (uint64_t)k * a_step, bdesc + (uint64_t)k * b_step, idesc, accum);
+                            else umma_bf16(tmem_d, adesc + (uint64_t)k * a_step, bdesc + (uint64_t)k * b_step, idesc, accum);
+                        }
                         umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs retire
                         if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -461,16 +504,21 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// bf16 row-major [rows, cols] -> 2D tensor map with a [box_rows, 64] box, 128B swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows) {
+// Operand tensor map (128-byte swizzle, zero OOB fill), element size `elt` (2 = bf16, 4 = fp32 consumed as TF32).
+//   K-major  operand [rows, K] row-major: box = [128 B of K][box_rows rows];
+//   MN-major operand [K, rows] row-major: box = [128 B of rows][128 / elt ... K rows of one stage] (see make_smem_desc_mn).
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long K, int box_rows, int elt, int mn_major) {
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) { set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver"); return CLIPGP_ERR_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t line = (cuuint32_t)(128 / elt);
+    cuuint64_t dims[2], strides[1];
+    cuuint32_t box[2];
+    if (!mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; strides[0] = (cuuint64_t)K * elt; box[0] = line; box[1] = (cuuint32_t)box_rows; }
+    else { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; strides[0] = (cuuint64_t)rows * elt; box[0] = line; box[1] = line; }
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const CUtensorMapSwizzle swz = (mn_major && elt == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = enc(map, elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_gemm: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return CLIPGP_ERR_CUDA; }
     return CLIPGP_OK;
@@ -496,16 +544,20 @@ static int launch(const void* A, long long M, long long Ka, const void* B, long 
     CLIPGP_REQUIRE(M >= 1 && N >= 1 && K >= 1 && Ka >= 1, "tc_gemm: empty problem");
     CLIPGP_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "tc_gemm: size too large");
     CLIPGP_REQUIRE(A && B, "tc_gemm: NULL operand");
-    CLIPGP_REQUIRE(Ka % 8 == 0 && K % 8 == 0, "tc_gemm: K (%lld) and Ka (%lld) must be multiples of 8 (16-byte TMA row pitch)", K, Ka);
-    CLIPGP_REQUIRE(K % Ka == 0 && (Ka == K || Ka % BK == 0), "tc_gemm: K must be a multiple of Ka, and Ka a multiple of %d when A wraps", BK);
+    if (p.elt == 0) p.elt = 2;
+    const int bke = 128 / p.elt, pitch = 16 / p.elt;           // K elements per 128-byte line; elements per 16 bytes (TMA row pitch)
+    CLIPGP_REQUIRE(!p.a_mn || Ka == K, "tc_gemm: an MN-major A operand cannot wrap along K");
+    CLIPGP_REQUIRE((p.a_mn ? M : Ka) % pitch == 0 && (p.b_mn ? N : K) % pitch == 0,
+                   "tc_gemm: operand row pitch must be a multiple of 16 bytes (M=%lld N=%lld K=%lld Ka=%lld, element size %d)", M, N, K, Ka, p.elt);
+    CLIPGP_REQUIRE(K % Ka == 0 && (Ka == K || Ka % bke == 0), "tc_gemm: K must be a multiple of Ka, and Ka a multiple of %d when A wraps", bke);
     CLIPGP_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) == 0, "tc_gemm: operands must be 16-byte aligned");
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, A, M, Ka, BM);
+    int rc = make_map(&ma, A, M, Ka, BM, p.elt, p.a_mn);
     if (rc != CLIPGP_OK) return rc;
-    rc = make_map(&mb, B, N, K, BN);
+    rc = make_map(&mb, B, N, K, BN, p.elt, p.b_mn);
     if (rc != CLIPGP_OK) return rc;
     p.M = (int)M; p.N = (int)N; p.K = (int)K; p.Ka = (int)Ka;
-    p.num_m = (int)((M + BM - 1) / BM); p.num_n = (int)((N + BN - 1) / BN); p.num_k = (int)((K + BK - 1) / BK);
+    p.num_m = (int)((M + BM - 1) / BM); p.num_n = (int)((N + BN - 1) / BN); p.num_k = (int)((K + bke - 1) / bke);
     p.n_per_item = (p.mode == EPI_ROWSTATS) ? p.num_n : 1;
     p.k_splits = 1; p.kb_per_split = p.num_k;
     if (p.mode == EPI_STORE && allow_split_k) {
@@ -587,6 +639,40 @@ extern "C" int clipgp_tc_gemm_store_splitk(const void* A_bf16, int64_t M, int64_
     tc::Params p = {};
     p.mode = tc::EPI_STORE; p.alpha = alpha; p.C = C; p.ldc = ldc;
     return tc::launch(A_bf16, M, Ka, B_bf16, N, K, p, (cudaStream_t)stream, true);
+}
+
+// TF32 on fp32 operands read in place (kind::tf32: 10-bit mantissa products, fp32 accumulation -- the reference's own GPU
+// arithmetic, adapter.py:23 `allow_tf32`).  a_layout / b_layout: 0 = K-major ([rows, K] row-major), 1 = MN-major ([K, rows]
+// row-major, i.e. the operand is the TRANSPOSE of a row-major tensor and is consumed without a transposed copy).
+extern "C" int clipgp_tc_gemm_tf32(const float* A, int a_layout, int64_t M, const float* B, int b_layout, int64_t N, int64_t K,
+                                   float alpha, float* C, int64_t ldc, int allow_split_k, void* stream) {
+    CLIPGP_REQUIRE(C != nullptr && ldc >= N, "tc_gemm_tf32: bad output");
+    tc::Params p = {};
+    p.mode = tc::EPI_STORE; p.alpha = alpha; p.C = C; p.ldc = ldc;
+    p.elt = 4; p.a_mn = a_layout != 0; p.b_mn = b_layout != 0;
+    return tc::launch(A, M, K, B, N, K, p, (cudaStream_t)stream, allow_split_k != 0);
+}
+
+extern "C" int clipgp_tc_logits_calibration_tf32(const float* A, int64_t M, int64_t Ka, const float* B, int64_t N, int64_t K, int64_t norm_cols,
+                                                 float alpha, const int64_t* labels, float* conf, int32_t* pred, uint8_t* correct,
+                                                 const float* boundaries, int n_bins, int64_t* bin_count,
+                                                 unsigned long long* bin_conf_fx, int64_t* bin_correct, int64_t* top1,
+                                                 float* logits_out, int64_t ld_logits, void* stream) {
+    if (M == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(norm_cols >= 0 && norm_cols % tc::BN == 0 && norm_cols < N,
+                   "tc_logits_calibration_tf32: norm_cols (%lld) must be a multiple of %d below N", (long long)norm_cols, tc::BN);
+    CLIPGP_REQUIRE(n_bins >= 0 && n_bins <= CLIPGP_MAX_BINS, "tc_logits_calibration_tf32: n_bins must be in [0,%d]", CLIPGP_MAX_BINS);
+    CLIPGP_REQUIRE(bin_count == nullptr || (boundaries && bin_conf_fx && bin_correct && n_bins >= 1), "tc_logits_calibration_tf32: histogram outputs incomplete");
+    CLIPGP_REQUIRE(labels != nullptr || (correct == nullptr && top1 == nullptr && bin_count == nullptr), "tc_logits_calibration_tf32: labels is NULL");
+    CLIPGP_REQUIRE(logits_out == nullptr || (norm_cols == 0 && ld_logits >= N), "tc_logits_calibration_tf32: bad logits_out");
+    tc::Params p = {};
+    p.mode = tc::EPI_ROWSTATS; p.alpha = alpha; p.C = logits_out; p.ldc = ld_logits; p.norm_cols = (int)norm_cols;
+    p.elt = 4;
+    p.labels = reinterpret_cast<const long long*>(labels); p.conf = conf; p.pred = pred; p.correct = correct;
+    p.boundaries = boundaries; p.n_bins = n_bins;
+    p.bin_count = reinterpret_cast<long long*>(bin_count); p.bin_conf_fx = bin_conf_fx;
+    p.bin_correct = reinterpret_cast<long long*>(bin_correct); p.top1 = reinterpret_cast<long long*>(top1);
+    return tc::launch(A, M, Ka, B, N, K, p, (cudaStream_t)stream);
 }
 
 extern "C" int clipgp_tc_logits_calibration(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K,

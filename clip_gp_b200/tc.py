@@ -145,3 +145,25 @@ def proj_logits_calibration(A: torch.Tensor, B: torch.Tensor, norm_cols: int, al
             correct.data_ptr(), b.data_ptr(), n_bins, hist[0].data_ptr(), hist[1].data_ptr(), hist[2].data_ptr(), hist[3].data_ptr(),
             _lib.stream_ptr(dev)), "clipgp_tc_proj_logits_calibration")
     return conf, correct, hist
+
+
+# ---------------------------------------------------------------------------------------------------- TF32 (fp32 operands in place)
+def gemm_tf32(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, a_t: bool = False, b_t: bool = False, out: Optional[torch.Tensor] = None,
+              split_k: bool = False) -> torch.Tensor:
+    """C = alpha * op(A) @ op(B)^T on the tensor cores in TF32, fp32 operands read in place (no cast kernels).
+
+    a_t False: A is [M, K];  a_t True: A is [K, M] (its transpose is the operand: an "MN-major" read, no transposed copy).
+    b_t False: B is [N, K];  b_t True: B is [K, N].  Examples (trainers/adapter.py:419-428 and adjoints):
+        logits = gemm_tf32(f_hat, P_hat, scale);  d f_hat = gemm_tf32(dlogits, P_hat, scale, b_t=True)
+        d P_hat = gemm_tf32(dlogits, f_hat, scale, a_t=True, b_t=True)."""
+    dev = _lib.require_cuda(A, B)
+    A, B = A.float().contiguous(), B.float().contiguous()
+    M, K = (A.shape[1], A.shape[0]) if a_t else A.shape
+    N, Kb = (B.shape[1], B.shape[0]) if b_t else B.shape
+    if K != Kb:
+        raise ValueError(f"gemm_tf32: contraction sizes differ ({K} vs {Kb})")
+    C_ = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().clipgp_tc_gemm_tf32(A.data_ptr(), int(a_t), M, B.data_ptr(), int(b_t), N, K, float(alpha), C_.data_ptr(),
+                                                   C_.stride(0), int(split_k), _lib.stream_ptr(dev)), "clipgp_tc_gemm_tf32")
+    return C_

@@ -311,6 +311,23 @@ int clipgp_tc_gemm_store(const void* A_bf16, int64_t M, int64_t Ka, const void* 
 int clipgp_tc_gemm_store_splitk(const void* A_bf16, int64_t M, int64_t Ka, const void* B_bf16, int64_t N, int64_t K, float alpha,
                                 float* C, int64_t ldc, void* stream);
 
+/* TF32 tensor-core GEMM on fp32 operands READ IN PLACE (tcgen05.mma kind::tf32, fp32 accumulation in TMEM): the arithmetic of the
+ * reference's own GPU path (trainers/adapter.py:23, `torch.backends.cuda.matmul.allow_tf32 = True`), with no operand cast kernels.
+ * C[M,N] = alpha * op(A) op(B)^T.  a_layout / b_layout: 0 = the operand is [rows, K] row-major (K-major), 1 = it is [K, rows]
+ * row-major (MN-major): the transpose of a row-major tensor is consumed as is -- e.g. d P_hat = dlogits^T f_hat
+ * (trainers/adapter.py:426 adjoint) takes dlogits [B, S*C] with a_layout = 1 and f_hat [B, D] with b_layout = 1, K = B.
+ * allow_split_k != 0: skinny outputs may split K over work items (fp32 atomic accumulation, not bit-reproducible). */
+int clipgp_tc_gemm_tf32(const float* A, int a_layout, int64_t M, const float* B, int b_layout, int64_t N, int64_t K, float alpha,
+                        float* C, int64_t ldc, int allow_split_k, void* stream);
+
+/* clipgp_tc_logits_calibration / clipgp_tc_proj_logits_calibration on fp32 operands (TF32): A [M,Ka] features, B [N,K] =
+ * [W ; prototypes] rows (norm_cols > 0: the first norm_cols rows of B are the visual projection, see
+ * clipgp_tc_proj_logits_calibration) or the class prototypes only (norm_cols = 0). */
+int clipgp_tc_logits_calibration_tf32(const float* A, int64_t M, int64_t Ka, const float* B, int64_t N, int64_t K, int64_t norm_cols,
+                                      float alpha, const int64_t* labels, float* conf, int32_t* pred, uint8_t* correct,
+                                      const float* boundaries, int n_bins, int64_t* bin_count, unsigned long long* bin_conf_fx,
+                                      int64_t* bin_correct, int64_t* top1, float* logits_out, int64_t ld_logits, void* stream);
+
 /* Logits alpha * A B^T reduced on the fly per row: max-softmax confidence, arg-max, hit flag, top-1 count and the equal-width
  * ECE histogram (utils/metrics.py:9-36,71-82) -- same outputs / accumulate semantics as clipgp_calibration_from_logits, but the
  * [M,N] logits never reach HBM unless logits_out != NULL. */

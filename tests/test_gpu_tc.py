@@ -159,3 +159,31 @@ def test_fused_rownorm_cast(R, D, mode):
     assert torch.allclose(inv, 1.0 / x.norm(dim=-1), rtol=1e-6)
     hi = out[:, :D].float()
     assert float((hi - torch.nn.functional.normalize(x, dim=-1)).abs().max()) <= 2.0 ** -8
+
+
+@pytest.mark.parametrize("a_t", [False, True])
+@pytest.mark.parametrize("b_t", [False, True])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (200, 1000, 512), (1000, 512, 1280), (128, 10000, 512), (77, 300, 100), (4096, 512, 128)])
+def test_tf32_gemm_all_operand_layouts(M, N, K, a_t, b_t):
+    """kind::tf32 on fp32 operands read in place, K-major and MN-major (transposed-in-place) operands, ragged M / N / K:
+    against a float64 product of the TF32-rounded operands (exact up to fp32 accumulation) and against the fp32 product within
+    the TF32 tolerance."""
+    if (a_t and M % 4) or (b_t and N % 4) or (not a_t and K % 4) or (not b_t and K % 4):
+        pytest.skip("row pitch must be a multiple of 16 bytes")
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g); B = torch.randn(N, K, generator=g)
+    Ad = (A.t().contiguous() if a_t else A).cuda(); Bd = (B.t().contiguous() if b_t else B).cuda()
+    C = tc.gemm_tf32(Ad, Bd, 0.5, a_t=a_t, b_t=b_t)
+    ref = 0.5 * (A.double() @ B.double().t())
+    scale = float(ref.abs().max())
+    assert float((C.cpu().double() - ref).abs().max()) < 2e-3 * scale          # TF32: 10-bit mantissa products
+    # the hardware truncates / rounds fp32 to TF32 (top 19 bits): both candidates bound the result far more tightly
+    def tf32(x, rnd):
+        xi = x.contiguous().view(torch.int32)
+        xi = ((xi + (0x1000 if rnd else 0)) & ~0x1FFF)
+        return xi.view(torch.float32)
+    errs = []
+    for rnd in (False, True):
+        r2 = 0.5 * (tf32(A, rnd).double() @ tf32(B, rnd).double().t())
+        errs.append(float((C.cpu().double() - r2).abs().max()) / scale)
+    assert min(errs) < 2e-5, errs
