@@ -44,8 +44,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--eval-n", type=int, default=50000)
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
-                    help="GEMMs of the train step: fp32 FFMA | tcgen05 split-bf16 (fp32-grade) | tcgen05 bf16")
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16x3", "bf16"],
+                    help="GEMMs of the train step and the eval pass: fp32 FFMA | tcgen05 TF32 on the fp32 tensors in place (default: the "
+                         "reference's own GPU arithmetic) | tcgen05 split-bf16 (fp32-grade) | tcgen05 bf16")
     ap.add_argument("--no-fullbatch", action="store_true", help="skip the B = N_train full-batch (tensor-bound) leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other-precision timings of the step")
     ap.add_argument("--no-graph-collectives", action="store_true",
@@ -374,7 +375,7 @@ def run_ours(args):
     # ---------------- the same step at the other GEMM precisions (short runs)
     train_variants = {}
     if not args.no_variants:
-        for prec in ("fp32", "bf16x3", "bf16"):
+        for prec in ("fp32", "tf32", "bf16x3", "bf16"):
             if prec == args.precision:
                 train_variants[prec] = {"ms_per_step": ms_total / args.steps, "steps_per_s": args.steps / (ms_total * 1e-3)}
                 continue
@@ -404,12 +405,12 @@ def run_ours(args):
         fullbatch = {"B": Btot, "B_per_rank": Bf, "scaling": "strong",
                      "note": "per-sample MC cross-entropy over the whole cached training set (batch rows split over the ranks, gradient "
                              "all-reduce); logits [B, S*C] materialised in fp32"}
-        for prec in ("bf16", "bf16x3"):
+        for prec in ("bf16", "bf16x3", "tf32"):
             ef = GPAdapterEngine(gpw, engine_config(batch_size=Bf, precision=prec))
             msf = time_steps(ef, 5, 3) / 5
             kt = profile_step_kernels(ef, f_all[rank * Bf:(rank + 1) * Bf], y_all[rank * Bf:(rank + 1) * Bf], shp, flush, reps=2, B=Bf)
             entry = {"ms_per_step": msf, "steps_per_s": 1e3 / msf, "img_per_s": Btot * 1e3 / msf}
-            gem = {k: v for k, v in kt.items() if k.startswith("tc_gemm_store") and v.get("flops")}
+            gem = {k: v for k, v in kt.items() if k.startswith("tc_gemm_") and v.get("flops")}
             if gem:
                 # the three logit contractions: logits, d P_hat, d f_hat  (2*B*S*C*D algorithmic flops each)
                 big = sorted(gem.items(), key=lambda kv: -kv[1]["flops"])[:3]
@@ -418,6 +419,8 @@ def run_ours(args):
                 entry["logit_gemms"] = {"bound": "tensor", "flops": fl, "ms": tm * 1e3, "achieved": fl / tm / 1e12, "unit": "TFLOP/s",
                                         "peak": pk_["bf16_tflops"], "frac": fl / tm / 1e12 / pk_["bf16_tflops"],
                                         "hw_flops_factor": 3 if prec == "bf16x3" else 1,
+                                        "tf32_peak_note": ("kind::tf32 runs at half the bf16 rate: frac of the TF32 peak = 2 x frac; measured library "
+                                                           "TF32 peak (torch.matmul allow_tf32, 8192^3) 687 TFLOP/s, profiles/r2_tc_gemm_bench.txt") if prec == "tf32" else None,
                                         "per_gemm": {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} for k, v in big}}
                 entry["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in kt.items()}
             fullbatch[prec] = entry
@@ -460,9 +463,10 @@ def run_ours(args):
     # headline eval: tcgen05 GEMMs with split-bf16 operands (fp32-grade products, >= the reference's TF32), collapsed MC form
     # the whole pass (GP forward -> prototypes | cast -> projection -> normalise | logits + calibration) is one captured CUDA graph over
     # the rank's resident test shard, as a trainer that evaluates after every step (adapter.py:363-380) would hold it
-    eval_replay = eng.eval_graph(f_sh, y_sh, precision="bf16x3", mc="collapsed")
+    eprec = args.precision if args.precision != "fp32" else "tf32"
+    eval_replay = eng.eval_graph(f_sh, y_sh, precision=eprec, mc="collapsed")
     # the whole metric -- logits + accuracy + ECE histogram, counter all-reduce, (conf, hit) all-gather, AECE rank-select -- as ONE graph
-    eval_pass = eng.eval_metrics_graph(f_sh, y_sh, n_eval, precision="bf16x3", mc="collapsed")
+    eval_pass = eng.eval_metrics_graph(f_sh, y_sh, n_eval, precision=eprec, mc="collapsed")
     eval_ms, _ = time_eval(eval_pass)
     eval_graph_only_ms, _ = time_eval(eval_replay)
 
@@ -491,7 +495,10 @@ def run_ours(args):
     eval_e2e_s = float(tt.item())
     cnt, ece, aece = eval_e2e_once()                           # the reported metrics: ONE pass (counters and AECE bins of the same draw)
     eval_variants = {}
-    for nm, fn in (("bf16x3_collapsed_eager_launches", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16x3", mc="collapsed")),
+    tf32_replay = eng.eval_graph(f_sh, y_sh, precision="bf16x3", mc="collapsed")
+    for nm, fn in (("bf16x3_collapsed_graph", tf32_replay),
+                   ("tf32_collapsed_eager_launches", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="tf32", mc="collapsed")),
+                   ("bf16x3_collapsed_eager_launches", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16x3", mc="collapsed")),
                    ("fp32_ffma_collapsed", eval_fp32),
                    ("bf16_collapsed", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16", mc="collapsed")),
                    ("bf16_materialised", lambda: eng.eval_calibration_tc(f_sh, y_sh, precision="bf16", mc="materialised")),
@@ -513,7 +520,7 @@ def run_ours(args):
             Pm0 = torch.nn.functional.normalize(wl["E"].mean(1), dim=-1)
         f_mx, y_mx = synth.make_mixed_calibration_set(wl["mu"], Pm0, 20000, 7, shp.noise)
         eng1 = GPAdapterEngine(gpw, engine_config(world=1, rank=0))
-        r_mx = eng1.evaluate(f_mx.to(dev), y_mx.to(dev), precision="bf16x3")
+        r_mx = eng1.evaluate(f_mx.to(dev), y_mx.to(dev), precision=eprec)
         calib_check = {"n_images": 20000, "top1_acc": r_mx["top1_acc"], "ece": r_mx["ece"], "aece": r_mx["aece"],
                        "bin_gap_signs": [int((a_ > c_) - (a_ < c_)) for a_, c_ in zip(r_mx["calibration"]["bin_acc"], r_mx["calibration"]["bin_conf"])],
                        "set": "synth.make_mixed_calibration_set: half over-confident noisy features, half under-confident 4-way ambiguous features"}
@@ -525,6 +532,7 @@ def run_ours(args):
         eng_train._graph = None
         eval_replay.release()
         eval_pass.release()
+        tf32_replay.release()
         import gc
         gc.collect()
         torch.cuda.synchronize(dev)
@@ -571,12 +579,14 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32 (fp32 operands read in place, 10-bit mantissa products, fp32 accumulate)",
+                                      "bf16x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "bf16": "bf16"}[args.precision],
         "data": "synthetic",
         "config": {"workload": workload_string(args.workload, shp, S),
                    "global_batch": world * shp.B, "parallelism": f"dp{world}" if world > 1 else "single GPU",
                    "value_counts": "128-image batch-steps per second summed over the ranks (one optimisation step consumes one batch per rank)",
                    "l2_flush": "256 MB device buffer written between timed steps", "precision": {"fp32": "fp32 (FFMA GEMMs, fp64 K_ZZ Cholesky)",
+                                 "tf32": "tcgen05 kind::tf32 GEMMs on the fp32 tensors in place (no operand casts; the reference's GPU arithmetic, adapter.py:23), fp32 everywhere else, fp64 K_ZZ Cholesky",
                                  "bf16x3": "tcgen05 GEMMs on split-bf16 operands (fp32-grade products; the reference's GPU path is TF32), fp32 everywhere else, fp64 K_ZZ Cholesky",
                                  "bf16": "tcgen05 bf16 GEMMs, fp32 everywhere else, fp64 K_ZZ Cholesky"}[args.precision],
                    "cuda_graph": eng_train._graph is not None, "two_stream_overlap": bool(eng_train.cfg.overlap),
@@ -607,7 +617,7 @@ def run_ours(args):
                  "top1_acc": cnt.top1 * 100.0 / n_eval, "ece": ece, "aece": aece, "calibration_check": calib_check,
                  "multi_gpu": (f"images sharded over {world} ranks; the eval GP forward runs on C/{world} classes per rank and one 2 MB "
                                "all-reduce completes the mean prototypes; counters: one all-reduce, AECE: all-gather of (conf, hit)") if world > 1 else None,
-                 "form": "one CUDA graph (engine.eval_metrics_graph; graph_only_ms = engine.eval_graph without the AECE / collective tail): GP forward + prototypes on a side stream next to cast / projection / normalise, then the tcgen05 split-bf16 (bf16x3) collapsed logit-mean GEMM [N,D]x[C,D]^T with the calibration epilogue",
+                 "form": "one CUDA graph (engine.eval_metrics_graph; graph_only_ms = engine.eval_graph without the AECE / collective tail): GP forward + prototypes on a side stream next to cast / projection / normalise, then ONE tcgen05 GEMM over the raw features against [W ; mean_s p_hat_s W] (projection, normalisation, collapsed logit-mean and the calibration epilogue fused), precision = " + eprec,
                  "variants": eval_variants},
         "roofline_eval_gemm": {"kernel": "tc_gemm_kernel (EPI_ROWSTATS), materialised MC logits [N,D]x[S*C,D]^T accumulated over s in TMEM",
                                "bound": "tensor", "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
@@ -628,11 +638,11 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
     """Average device time of every kernel of one step, from CUDA events around each C-ABI launch (eager mode)."""
     from clip_gp_b200 import _lib
     lib = eng.lib
-    names = ["clipgp_gemm_f32", "clipgp_rownorm_forward", "clipgp_gp_forward", "clipgp_proto_forward", "clipgp_softmax_ce",
+    names = ["clipgp_tc_gemm_tf32", "clipgp_gemm_f32", "clipgp_rownorm_forward", "clipgp_gp_forward", "clipgp_proto_forward", "clipgp_softmax_ce",
              "clipgp_rownorm_backward", "clipgp_l2_identity", "clipgp_proto_backward", "clipgp_gp_backward", "clipgp_sum_accumulate",
              "clipgp_adamw_step", "clipgp_adamw_step_lrptr", "clipgp_increment", "clipgp_tc_gemm_store", "clipgp_tc_gemm_store_splitk", "clipgp_cast_bf16", "clipgp_cast_bf16_transpose", "clipgp_cast_bf16_dual",
              "clipgp_softmax_ce_stats", "clipgp_softmax_grad_bf16_dual", "clipgp_softmax_ce_bf16_dual", "clipgp_increment2", "clipgp_step_epilogue"]
-    multi = ("gemm_f32", "adamw_step", "adamw_step_lrptr", "increment", "tc_gemm_store", "tc_gemm_store_splitk", "cast_bf16", "cast_bf16_transpose", "cast_bf16_dual")
+    multi = ("tc_gemm_tf32", "gemm_f32", "adamw_step", "adamw_step_lrptr", "increment", "tc_gemm_store", "tc_gemm_store_splitk", "cast_bf16", "cast_bf16_transpose", "cast_bf16_dual")
     seg = getattr(eng, "tc_seg", 1)
     B = B or shp.B
     records = []
@@ -647,6 +657,8 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
             rc = self.fn(*a)
             e1.record()
             fl = 2.0 * a[1] * a[4] * a[5] / seg if self.name.startswith("clipgp_tc_gemm_store") else None
+            if self.name == "clipgp_tc_gemm_tf32":
+                fl = 2.0 * a[2] * a[5] * a[6]
             records.append((self.name, e0, e1, fl))
             return rc
 

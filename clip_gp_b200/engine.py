@@ -41,8 +41,9 @@ class EngineConfig:
     adam_eps: float = 1e-8
     loss_mode: str = "per_sample"       # "per_sample" (adapter.py:422-428) | "logit_mean" (taskres.py:268-270)
     train_visual_proj: bool = True      # FREEZE_VISUAL_PROJ False
-    precision: str = "fp32"             # GEMMs of the step: "fp32" (FFMA, exact comparator) | "bf16x3" (tcgen05, split operands,
-                                        # fp32-grade products: the reference itself runs TF32, adapter.py:23) | "bf16" (tcgen05)
+    precision: str = "fp32"             # GEMMs of the step: "fp32" (FFMA, exact comparator) | "tf32" (tcgen05 kind::tf32 on the fp32
+                                        # tensors in place, no operand casts, transposed operands read in place: the reference's own GPU
+                                        # arithmetic, adapter.py:23) | "bf16x3" (tcgen05, split bf16 operands, fp32-grade products) | "bf16"
     graph_collectives: bool = False     # world > 1: capture the step (its NCCL all-reduces included) in the CUDA graph as well
                                         # (1886 -> 2088 steps/s at 2 GPUs).  The owner must drop the graph (engine._graph = None)
                                         # before destroying the process group, otherwise NCCL teardown hangs; bench.py does
@@ -183,7 +184,11 @@ class GPAdapterEngine:
         self.df_hat = torch.empty(B, D, **f32)
         self.dY = torch.empty(B, D, **f32)
         self.dw = self.dw_all[so:so + S]
-        if self.cfg.precision != "fp32":
+        if self.cfg.precision == "tf32":
+            SCt = (S if self.cfg.loss_mode == "per_sample" else 1) * Cn
+            if D % 4 or SCt % 4:
+                raise ValueError(f"precision='tf32' needs D ({D}) and S*C ({SCt}) to be multiples of 4 (16-byte TMA row pitch); use 'bf16x3'")
+        elif self.cfg.precision != "fp32":
             self._alloc_tc()
         a = GpArgs()
         a.kernel_type = KERNEL_IDS[self.kernel_type]
@@ -199,7 +204,7 @@ class GPAdapterEngine:
         if self.fused_proto:
             a.proto_E, a.proto_D = self.E.data_ptr(), D
             a.proto_P_hat, a.proto_norm = self.P_hat.data_ptr(), self.P_norm.data_ptr()
-            if self.cfg.precision != "fp32":
+            if self.cfg.precision in ("bf16x3", "bf16"):
                 a.proto_bf16, a.proto_bf16_ld, a.proto_bf16_seg, a.proto_bf16_mode = self.Pb.data_ptr(), self.Pb.stride(0), D, self.tc_mb
         a.Z, a.X = self.Z.data_ptr(), self.X.data_ptr()
         a.raw_lengthscale = self._ptr(self.flat_p, "ls") if "ls" in self.offsets else None
@@ -235,7 +240,7 @@ class GPAdapterEngine:
             b.proto_norm, b.proto_E, b.proto_EEt, b.proto_D = self.P_norm.data_ptr(), self.E.data_ptr(), self.EEt.data_ptr(), D
             b.dw_out = self.dw_all.data_ptr()
         # small-batch form of the same adjoint (needs the bf16 dlogits^T operand of the tensor-core step)
-        self.tl_adjoint = bool(self.fused_proto_bwd and self.cfg.template_logit_adjoint and self.cfg.precision != "fp32" and B <= 256 and
+        self.tl_adjoint = bool(self.fused_proto_bwd and self.cfg.template_logit_adjoint and self.cfg.precision in ("bf16x3", "bf16") and B <= 256 and
                                S <= 12 and D % 8 == 0)
         if self.tl_adjoint:
             seg = self.tc_seg
@@ -278,6 +283,11 @@ class GPAdapterEngine:
         _lib.check(self.lib.clipgp_cast_bf16_dual(src_ptr, R, K, ldx, _lib.ptr(out), out.stride(0) if out is not None else 0, Kp, mode,
                                                   _lib.ptr(outT), outT.stride(0) if outT is not None else 0, Rp, modeT,
                                                   _lib.stream_ptr(self.dev)), "cast_bf16_dual")
+
+    def _tf32(self, A_ptr, a_t, M, B_ptr, b_t, N, K, alpha, out_ptr, ldc, split_k=True):
+        """C[M,N] = alpha op(A) op(B)^T in TF32 on fp32 tensors in place (a_t / b_t: the operand is stored [K, rows])."""
+        _lib.check(self.lib.clipgp_tc_gemm_tf32(A_ptr, int(a_t), M, B_ptr, int(b_t), N, K, float(alpha), out_ptr, ldc, int(split_k),
+                                                _lib.stream_ptr(self.dev)), "tc_gemm_tf32")
 
     def _tc(self, A, Bm, alpha, out_ptr, ldc):
         _lib.check(self.lib.clipgp_tc_gemm_store_splitk(A.data_ptr(), A.shape[0], A.shape[1], Bm.data_ptr(), Bm.shape[0], Bm.shape[1],
@@ -343,7 +353,9 @@ class GPAdapterEngine:
         lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
         B, D = self.B, self.D
         W = self._ptr(self.flat_p, "W")
-        if cfg.precision != "fp32":
+        if cfg.precision == "tf32":
+            self._tf32(self.in_feat.data_ptr(), False, B, W, False, D, D, 1.0, self.Y.data_ptr(), D)         # Y = f W^T, both K-major
+        elif cfg.precision != "fp32":
             ma, mb = self.tc_ma, self.tc_mb
             self._cast2(self.in_feat.data_ptr(), B, D, D, self.fb, D, ma, self.fTb if cfg.train_visual_proj else None, self.Bp, mb)
             self._cast(W, D, D, D, self.Wb, D, mb)
@@ -351,7 +363,7 @@ class GPAdapterEngine:
         else:
             ck(lib.clipgp_gemm_f32(self.in_feat.data_ptr(), D, 1, W, 1, D, self.Y.data_ptr(), D, B, D, D, 1.0, 0, st), "gemm(proj)")
         ck(lib.clipgp_rownorm_forward(self.Y.data_ptr(), B, D, self.f_hat.data_ptr(), self.f_inv.data_ptr(), None, st), "rownorm")
-        if cfg.precision != "fp32":
+        if cfg.precision in ("bf16x3", "bf16"):
             self._cast2(self.f_hat.data_ptr(), B, D, D, self.fhb, D, self.tc_ma, None if self.tl_adjoint else self.fhTb, self.Bp, self.tc_mb)
 
     def _template_logits(self):
@@ -376,7 +388,7 @@ class GPAdapterEngine:
             return                                            # prototypes and their GEMM operand came out of the GP kernel
         ck(lib.clipgp_proto_forward(self.w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, self.P_hat.data_ptr(),
                                     self.P_norm.data_ptr(), None, None if per_sample else self.P_mean.data_ptr(), None, 0, st), "proto_forward")
-        if cfg.precision != "fp32":
+        if cfg.precision in ("bf16x3", "bf16"):
             Bmat = self.P_hat if per_sample else self.P_mean
             # only the row-major operand is on the critical path (logit GEMM); the transposed copy feeds d f_hat on the feature branch
             self._cast(Bmat.data_ptr(), SC, D, D, self.Pb, D, self.tc_mb)
@@ -387,8 +399,9 @@ class GPAdapterEngine:
         B, Cn, D = self.B, self.C, self.D
         per_sample, S, SC, alpha = self._dims()
         Bmat = self.P_hat if per_sample else self.P_mean
-        tcm = cfg.precision != "fp32"
-        if tcm:
+        if cfg.precision == "tf32":
+            self._tf32(self.f_hat.data_ptr(), False, B, Bmat.data_ptr(), False, SC, D, alpha, self.logits.data_ptr(), SC)
+        elif cfg.precision != "fp32":
             self._tc(self.fhb, self.Pb, alpha, self.logits.data_ptr(), SC)
         else:
             ck(lib.clipgp_gemm_f32(self.f_hat.data_ptr(), D, 1, Bmat.data_ptr(), 1, D, self.logits.data_ptr(), SC, B, SC, D,
@@ -399,7 +412,7 @@ class GPAdapterEngine:
         lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
         B, Cn, D = self.B, self.C, self.D
         per_sample, S, SC, alpha = self._dims()
-        tcm = cfg.precision != "fp32"
+        tcm = cfg.precision in ("bf16x3", "bf16")          # tf32: the fp32 softmax kernel writes dlogits in place, the GEMMs read it as is
         # mean over the (global) batch and the S_train samples; every rank contributes its share and the all-reduce sums them
         dp = cfg.world if self.batch_sharded else 1
         if per_sample:
@@ -439,8 +452,12 @@ class GPAdapterEngine:
         per_sample, S, SC, alpha = self._dims()
         Bmat = self.P_hat if per_sample else self.P_mean
         W = self._ptr(self.flat_p, "W")
-        tcm = cfg.precision != "fp32"
-        if tcm:
+        tcm = cfg.precision in ("bf16x3", "bf16")
+        tf = cfg.precision == "tf32"
+        if tf:
+            # d f_hat = alpha dlogits P_hat: A = dlogits [B, SC] (K-major), B operand = P_hat^T, i.e. P_hat [SC, D] read MN-major in place
+            self._tf32(self.logits.data_ptr(), False, B, Bmat.data_ptr(), True, D, SC, alpha, self.df_hat.data_ptr(), D)
+        elif tcm:
             # dlogits [B, SC] and P_hat^T [D, SC] (K = samples x classes; split over K inside the GEMM)
             self._cast2(Bmat.data_ptr(), SC, D, D, None, 0, 0, self.PTb, self.SCp, self.tc_mb)
             self._tc(self.dlb, self.PTb, alpha, self.df_hat.data_ptr(), D)
@@ -449,7 +466,10 @@ class GPAdapterEngine:
                                    alpha, 0, st), "gemm(df)")
         ck(lib.clipgp_rownorm_backward(self.df_hat.data_ptr(), self.f_hat.data_ptr(), self.f_inv.data_ptr(), B, D,
                                        self.dY.data_ptr(), st), "rownorm_bwd")
-        if tcm:
+        if tf:
+            # dW = dY^T f: both operands are [B, .] tensors contracted over the batch -> both read MN-major in place
+            self._tf32(self.dY.data_ptr(), True, D, self.in_feat.data_ptr(), True, D, B, 1.0, self._ptr(self.flat_g, "W"), D)
+        elif tcm:
             self._cast2(self.dY.data_ptr(), B, D, D, None, 0, 0, self.dYTb, self.Bp, self.tc_ma)
             self._tc(self.dYTb, self.fTb, 1.0, self._ptr(self.flat_g, "W"), D)
         else:
@@ -465,7 +485,10 @@ class GPAdapterEngine:
         lib, cfg, ck, st = self.lib, self.cfg, _lib.check, _lib.stream_ptr(self.dev)
         B, Cn, T, D = self.B, self.C, self.T, self.D
         per_sample, S, SC, alpha = self._dims()
-        if cfg.precision != "fp32":
+        if cfg.precision == "tf32":
+            # d P_hat = alpha dlogits^T f_hat (contraction over the batch): dlogits [B, SC] and f_hat [B, D] read MN-major in place
+            self._tf32(self.logits.data_ptr(), True, SC, self.f_hat.data_ptr(), True, D, B, alpha, self.dP.data_ptr(), D)
+        elif cfg.precision != "fp32":
             # K-major operands: dlogits^T [SC, B] and f_hat^T [D, B] (K = batch)
             if not self.tl_adjoint:
                 self._tc(self.dlTb, self.fhTb, alpha, self.dP.data_ptr(), D)
@@ -756,12 +779,14 @@ class GPAdapterEngine:
     def eval_calibration_tc(self, features, labels, S=None, n_bins=10, precision="bf16", mc="collapsed", want_logits=False):
         """Tensor-core eval: cast -> projection GEMM -> row normalise -> fused logits + softmax-max + histogram GEMM."""
         from . import tc
-        if precision not in ("bf16", "bf16x3"):
+        if precision not in ("bf16", "bf16x3", "tf32"):
             raise ValueError(f"unknown precision {precision}")
         split = precision == "bf16x3"
         lib, st = self.lib, _lib.stream_ptr(self.dev)
         f = features.to(self.dev, non_blocking=True).float().contiguous()
         N, D = f.shape
+        if precision == "tf32":
+            return self._eval_calibration_tf32(f, labels, S, n_bins, mc, want_logits)
         # the prototype chain (GP forward -> unit prototypes -> operand cast; latency bound) runs on a side stream next to the feature
         # chain (cast -> projection GEMM -> normalise; bandwidth / tensor bound); they meet at the logit GEMM
         cur = torch.cuda.current_stream(self.dev)
@@ -810,6 +835,82 @@ class GPAdapterEngine:
                                                             want_conf=True, want_logits=want_logits)
         self.last_eval_logits = logits
         return conf, correct, hist
+
+    def _eval_calibration_tf32(self, f, labels, S, n_bins, mc, want_logits):
+        """The eval pass in TF32 on the fp32 tensors in place: no operand casts at all.  Collapsed + D % 256 == 0: ONE GEMM over the
+        raw features against B = [W ; Q], Q = mean_s p_hat_s W (written by a small TF32 GEMM straight into the operand, W read
+        transposed in place); otherwise projection GEMM -> row normalise -> logits GEMM."""
+        from . import tc
+        lib, st = self.lib, _lib.stream_ptr(self.dev)
+        N, D = f.shape
+        Cn = self.C
+        if D % 4:
+            raise ValueError("precision='tf32' needs D % 4 == 0")
+        W = self.p("W").view(D, D)
+        cur = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_eval_stream", None) is None:
+            self._eval_stream = torch.cuda.Stream(self.dev)
+        side = self._eval_stream
+        scale = self.cfg.logit_scale
+        fuse_proj = (mc == "collapsed" and not want_logits and D % 256 == 0 and self.cfg.fuse_eval_projection)
+        if mc == "collapsed":
+            if fuse_proj:
+                Bop = torch.empty(D + Cn, D, dtype=torch.float32, device=self.dev)
+                Bop[:D].copy_(W)
+                Bop.record_stream(side)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):                   # prototype chain next to nothing: the features need no preparation
+                    Pm = self.eval_prototypes(S)
+                    tc.gemm_tf32(Pm, W, 1.0, b_t=True, out=Bop[D:])                    # Q = P_mean W  ([C, D_out] x [D_out, D_in])
+                cur.wait_stream(side)
+                conf, correct, hist, _ = tc.logits_calibration_tf32(f, Bop, scale, labels, n_bins, norm_cols=D)
+                self.last_eval_logits = None
+                return conf, correct, hist
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                Pm = self.eval_prototypes(S)
+            Pm.record_stream(cur)
+            Bmat, alpha = Pm, scale
+        else:
+            S_ = int(S or self.cfg.S_eval)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                P_hat = self._eval_unit_prototypes(S_)                                   # [S, C, D]
+                Bmat = P_hat.permute(1, 0, 2).reshape(Cn, S_ * D).contiguous()           # row c = [p_hat_1c | ... | p_hat_Sc]: A wraps along K
+            Bmat.record_stream(cur)
+            alpha = scale / S_
+        Y = tc.gemm_tf32(f, W, 1.0)                                                       # adapter.py:239
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.clipgp_rownorm_forward(Y.data_ptr(), N, D, Y.data_ptr(), None, None, st), "rownorm")
+        cur.wait_stream(side)
+        conf, correct, hist, logits = tc.logits_calibration_tf32(Y, Bmat, alpha, labels, n_bins, want_logits=want_logits)
+        self.last_eval_logits = logits
+        return conf, correct, hist
+
+    @torch.no_grad()
+    def _eval_unit_prototypes(self, S: int) -> torch.Tensor:
+        """p_hat_s [S, C, D] of one evaluation draw (materialised MC form)."""
+        lib, st = self.lib, _lib.stream_ptr(self.dev)
+        Cn, T, D = self.C, self.T, self.D
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        w = torch.empty(S, Cn, T, **f32)
+        a = GpArgs.from_buffer_copy(self.gp_args)
+        a.S, a.s_offset, a.S_total = S, 0, S
+        a.c_begin, a.c_count = 0, 0
+        a.eps_save = None
+        a.proto_E = a.proto_P_hat = a.proto_norm = a.proto_bf16 = a.proto_mean_hat = None
+        a.w, a.kl = w.data_ptr(), None
+        a.L = a.A = a.R = None
+        a.Ksave = self._eval_ksave()
+        bump = self._eval_noise(a, S)
+        P_hat = torch.empty(S, Cn, D, **f32)
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.clipgp_gp_forward(C.byref(a), st), "gp_forward(eval)")
+            _lib.check(lib.clipgp_proto_forward(w.data_ptr(), self.E.data_ptr(), S, Cn, T, D, None, 0.0, None, P_hat.data_ptr(), None,
+                                                None, None, None, 0, st), "proto_forward(eval)")
+        if bump:
+            self.eval_rng_state[1:2].add_(1)
+        return P_hat
 
     @torch.no_grad()
     def eval_graph(self, features: torch.Tensor, labels: torch.Tensor, S=None, n_bins=10, precision="bf16x3", mc="collapsed"):

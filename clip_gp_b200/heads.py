@@ -191,7 +191,7 @@ def tip_search(feats_hat, labels, keys, key_labels, clip_logits, num_classes: in
 # ---------------------------------------------------------------------------------------------------- GP pre-training
 def gp_pretrain(gp_weighter: GaussianProcessTemplateWeighter, feats_hat: torch.Tensor, labels: torch.Tensor, epochs: int,
                 gp_lr: float, beta_kl: float, num_samples: int, weight_decay: float = 0.0, scale: float = 100.0, log_every: int = 10,
-                precision: str = "bf16x3", seed: int = 0):
+                precision: str = "auto", seed: int = 0):
     """Full-batch ELBO optimisation of the weighter (taskres.py:254-280; identical in clip_adapter.py:257-279 and
     tip_adapter.py:122-146): CE(mean_s 100 f . normalize(protos_s), y) + beta * sum KL, AdamW(gp_lr) + CosineAnnealingLR(epochs),
     one step per epoch on ALL few-shot features.
@@ -208,6 +208,9 @@ def gp_pretrain(gp_weighter: GaussianProcessTemplateWeighter, feats_hat: torch.T
                                   "template rows of the inducing points, gp_template_weigher.py:72-79)")
     N = int(feats_hat.shape[0])
     S = max(1, int(num_samples))
+    if precision in ("auto", None):
+        # TF32 on the fp32 tensors in place when the row pitches allow it (the collapsed logits are [N, C]), else split-bf16
+        precision = "tf32" if (gp_weighter.dim % 4 == 0 and gp_weighter.num_classes % 4 == 0) else "bf16x3"
     cfg = EngineConfig(S_train=S, S_eval=S, batch_size=N, logit_scale=float(scale), gp_beta=float(beta_kl), l2_lambda=0.0, shots=1,
                        lr=0.0, gp_lr=float(gp_lr), weight_decay=0.0, loss_mode="logit_mean", train_visual_proj=False,
                        precision=precision, seed=int(seed))

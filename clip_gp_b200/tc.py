@@ -167,3 +167,26 @@ def gemm_tf32(A: torch.Tensor, B: torch.Tensor, alpha: float = 1.0, a_t: bool = 
         _lib.check(_lib.load().clipgp_tc_gemm_tf32(A.data_ptr(), int(a_t), M, B.data_ptr(), int(b_t), N, K, float(alpha), C_.data_ptr(),
                                                    C_.stride(0), int(split_k), _lib.stream_ptr(dev)), "clipgp_tc_gemm_tf32")
     return C_
+
+
+def logits_calibration_tf32(A: torch.Tensor, B: torch.Tensor, alpha: float, labels: torch.Tensor, n_bins: int = 10, norm_cols: int = 0,
+                            want_logits: bool = False):
+    """logits_calibration / proj_logits_calibration on fp32 operands (TF32, no casts): A [M,K] features, B [N,K] = class prototypes
+    (norm_cols = 0) or [W ; Q] (norm_cols = D: projection columns first).  Returns (conf, correct, hist[4,n_bins], logits|None)."""
+    from .metrics import _boundaries
+    dev = _lib.require_cuda(A, B, labels)
+    assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.is_contiguous() and B.is_contiguous()
+    M, Ka = A.shape
+    N, K = B.shape
+    labels = labels.to(torch.int64).contiguous()
+    conf = torch.empty(M, dtype=torch.float32, device=dev)
+    correct = torch.empty(M, dtype=torch.uint8, device=dev)
+    hist = torch.zeros(4, max(n_bins, 1), dtype=torch.int64, device=dev)
+    logits = torch.empty(M, N, dtype=torch.float32, device=dev) if want_logits else None
+    b = _boundaries(n_bins, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().clipgp_tc_logits_calibration_tf32(
+            A.data_ptr(), M, Ka, B.data_ptr(), N, K, int(norm_cols), float(alpha), labels.data_ptr(), conf.data_ptr(), None,
+            correct.data_ptr(), b.data_ptr(), n_bins, hist[0].data_ptr(), hist[1].data_ptr(), hist[2].data_ptr(), hist[3].data_ptr(),
+            _lib.ptr(logits), N, _lib.stream_ptr(dev)), "clipgp_tc_logits_calibration_tf32")
+    return conf, correct, hist, logits

@@ -329,11 +329,20 @@ class AdapterTrainer(BaseTrainer):
                             betas=tuple(_get(cfg, "optim.betas", (0.9, 0.999))), adam_eps=float(_get(cfg, "optim.eps", 1e-8)),
                             loss_mode="per_sample" if S_tr > 1 else "logit_mean",                      # adapter.py:401 vs :444-452
                             train_visual_proj=not bool(getattr(a, "freeze_visual_proj", False)), seed=int(_get(cfg, "seed", 0) or 0),
-                            # GEMMs of the step: split-bf16 tensor-core path by default (fp32-grade products; the reference's own
-                            # GPU path is TF32, adapter.py:23); "fp32" = FFMA comparator, "bf16" = stated tolerance
-                            precision=str(getattr(a, "clipgp_precision", "bf16x3")))
-        self.engine = GPAdapterEngine(self.model.gp_weighter, ecfg, self.model.visual_proj.weight)
+                            # GEMMs of the step: TF32 on the fp32 tensors in place by default (the reference's own GPU arithmetic,
+                            # adapter.py:23); "bf16x3" = split-bf16 (fp32-grade products), "fp32" = FFMA comparator, "bf16" = stated tolerance
+                            precision=self._precision())
+        try:
+            self.engine = GPAdapterEngine(self.model.gp_weighter, ecfg, self.model.visual_proj.weight)
+        except ValueError as e:
+            if ecfg.precision != "tf32" or "multiples of 4" not in str(e) or getattr(a, "clipgp_precision", None) is not None:
+                raise
+            ecfg.precision = "bf16x3"                        # row pitch not a multiple of 16 bytes (e.g. odd S*C): split-bf16 has no such rule
+            self.engine = GPAdapterEngine(self.model.gp_weighter, ecfg, self.model.visual_proj.weight)
         return self.engine
+
+    def _precision(self) -> str:
+        return str(getattr(self.config.adapter, "clipgp_precision", None) or "tf32")
 
     def forward_backward(self, batch):
         feats, labels = batch
@@ -361,8 +370,7 @@ class AdapterTrainer(BaseTrainer):
     def _compute_final_metrics(self) -> Dict[str, Any]:
         if not self.use_gp:
             return super()._compute_final_metrics()
-        prec = str(getattr(self.config.adapter, "clipgp_precision", "bf16x3"))
-        res = self.engine.evaluate(self.features_test, self.labels_test, precision=prec)
+        res = self.engine.evaluate(self.features_test, self.labels_test, precision=self.engine.cfg.precision)
         return {"top1_acc": float(res["top1_acc"]), "ece": float(res["ece"]), "aece": float(res["aece"]),
                 "calibration": res["calibration"], "adaptive_calibration": res["adaptive_calibration"]}
 
@@ -424,7 +432,7 @@ class _GPInitMixin:
                               gp_lr=float(getattr(a, "gp_lr", 1e-3)), beta_kl=float(getattr(a, "gp_beta", 1e-3)),
                               num_samples=int(getattr(a, "gp_num_mc_samples_train", 30) or 1),
                               weight_decay=float(_get(cfg, "optim.weight_decay", 0.0)),
-                              precision=str(getattr(a, "clipgp_precision", "bf16x3")), seed=int(_get(cfg, "seed", 0) or 0))
+                              precision=str(getattr(a, "clipgp_precision", None) or "auto"), seed=int(_get(cfg, "seed", 0) or 0))
             protos = gpw.mean_prototypes(int(getattr(a, "gp_num_mc_samples_eval", 100) or 1), eps=getattr(self, "eval_eps", None))
             print(f"[{tag}] Using trained GP-based template weighter for prototypes.")
             return protos

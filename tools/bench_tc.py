@@ -37,3 +37,29 @@ for name, M, N, K, Ka in cases:
     ms = timeit(lambda: tc.logits_calibration(A, B, 1.0, y, 10))
     print(f"{name} rowstats M={M} N={N} K={K}: {ms*1e3:9.1f} us  {fl/ms/1e9:8.1f} TFLOP/s  ({fl/ms/1e9/peak*100:5.1f}% of {peak})")
     del A, B, C
+
+# ---- TF32 on fp32 operands read in place (no cast kernels); the measured TF32 library peak next to it (torch.matmul, allow_tf32)
+torch.backends.cuda.matmul.allow_tf32 = True
+Xa, Xb = torch.randn(8192, 8192, device=dev), torch.randn(8192, 8192, device=dev)
+ms_lib = timeit(lambda: torch.matmul(Xa, Xb.t()))
+tf32_peak = 2.0 * 8192 ** 3 / ms_lib / 1e9
+print(f"torch.matmul TF32 8192^3: {ms_lib*1e3:.1f} us = {tf32_peak:.1f} TFLOP/s (library TF32 peak used below)")
+del Xa, Xb
+tcases = [("full-batch logits   f_hat P_hat^T  ", 16000, 10000, 512, False, False),
+          ("full-batch d f_hat  dlogits P_hat  ", 16000, 512, 10000, False, True),
+          ("full-batch d P_hat  dlogits^T f_hat", 10000, 512, 16000, True, True),
+          ("minibatch logits                   ", 128, 10000, 512, False, False),
+          ("minibatch d f_hat                  ", 128, 512, 10000, False, True),
+          ("minibatch d P_hat                  ", 10000, 512, 128, True, True),
+          ("projection                         ", 50000, 512, 512, False, False),
+          ("eval collapsed store               ", 50000, 1000, 512, False, False),
+          ("square 8192                        ", 8192, 8192, 8192, False, False)]
+for name, M, N, K, a_t, b_t in tcases:
+    A = torch.randn((K, M) if a_t else (M, K), generator=g).to(dev)
+    B = torch.randn((K, N) if b_t else (N, K), generator=g).to(dev)
+    C = torch.empty(M, N, device=dev)
+    fl = 2.0 * M * N * K
+    for sk in (False, True):
+        ms = timeit(lambda: tc.gemm_tf32(A, B, 1.0, a_t=a_t, b_t=b_t, out=C, split_k=sk))
+        print(f"tf32 {name} M={M} N={N} K={K} a_t={int(a_t)} b_t={int(b_t)} split_k={int(sk)}: {ms*1e3:9.1f} us  {fl/ms/1e9:8.1f} TFLOP/s  ({fl/ms/1e9/tf32_peak*100:5.1f}% of TF32 {tf32_peak:.0f})")
+    del A, B, C
