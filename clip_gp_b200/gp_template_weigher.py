@@ -207,9 +207,13 @@ class GaussianProcessTemplateWeighter(nn.Module):
         with torch.no_grad():
             X = text_embeddings.reshape(-1, D)
             mu = X.mean(dim=0, keepdim=True)
-            _, _, Vt = torch.linalg.svd(X - mu, full_matrices=False)
-            self.red_dim = min(self.red_dim, Vt.shape[0])
-            W = Vt[: self.red_dim].T.contiguous()
+            max_rank = min(X.shape[0], D)                                  # Vt.shape[0] of the reference's thin SVD
+            self.red_dim = min(self.red_dim, max_rank)
+            if X.is_cuda:
+                W = self._pca_axes_device(X - mu, self.red_dim)
+            else:
+                _, _, Vt = torch.linalg.svd(X - mu, full_matrices=False)
+                W = Vt[: self.red_dim].T.contiguous()
         self._pca_mean = mu.squeeze(0)
         self._pca_W = W
         with torch.no_grad():
@@ -283,6 +287,23 @@ class GaussianProcessTemplateWeighter(nn.Module):
         self._pca_mean = self._pca_mean_buf
         self._pca_W = self._pca_W_buf
         return out
+
+    @staticmethod
+    @torch.no_grad()
+    def _pca_axes_device(Xc: torch.Tensor, d: int) -> torch.Tensor:
+        """Leading d right-singular vectors of the centred [C*T, D] text bank WITHOUT the SVD of the tall matrix
+        (gp_template_weigher.py:26-37 runs torch.linalg.svd on [32 000, 512] at the ImageNet shape): the D x D
+        Gram matrix Xc^T Xc comes from the clipgp fp32 GEMM (one pass over the bank, contraction over the rows read in place),
+        its symmetric eigen-decomposition (512 x 512, a library call in one-time setup) gives the axes in descending order.
+        Axes are defined up to sign (and rotation inside degenerate eigenspaces), exactly like the SVD's; everything downstream
+        consumes inner products / distances of the projected points, which depend on the subspace only."""
+        N, D = Xc.shape
+        Xc = Xc.float().contiguous()
+        G = torch.empty(D, D, dtype=torch.float32, device=Xc.device)
+        ops._gemm(Xc, 1, D, Xc, D, 1, G, D, D, N, 1.0)                     # G[i,j] = sum_r Xc[r,i] Xc[r,j]
+        G = 0.5 * (G + G.t())
+        evals, evecs = torch.linalg.eigh(G.double())                       # ascending
+        return evecs[:, -d:].flip(-1).float().contiguous()                 # [D, d], largest variance first
 
     @staticmethod
     @torch.no_grad()

@@ -307,3 +307,26 @@ def test_module_philox_mode_backward_and_kl_cache():
     # the graph of the last launch is gone now: a new kl call must be differentiable again
     kl = a.variational_strategy.kl_divergence().sum()
     kl.backward()
+
+
+@pytest.mark.parametrize("C,T,D,d", [(40, 8, 64, 16), (100, 32, 512, 256), (5, 3, 64, 256)])
+def test_device_pca_spans_the_reference_subspace(C, T, D, d):
+    """gp_template_weigher.py:26-37 on the device (Gram matrix by the clipgp GEMM + symmetric eigen-solve) against the reference's
+    thin SVD on the CPU: same reduced dimension, same principal subspace (projector), same projected geometry."""
+    E, _ = synth.make_text_bank(C, T, D, seed=C + T)
+    X = E.reshape(-1, D)
+    Xc = X - X.mean(0, keepdim=True)
+    _, Sv, Vt = torch.linalg.svd(Xc, full_matrices=False)
+    dd = min(d, Vt.shape[0])
+    W_ref = Vt[:dd].T
+    W = GaussianProcessTemplateWeighter._pca_axes_device(Xc.cuda(), dd).cpu()
+    assert W.shape == W_ref.shape
+    assert float((W.t() @ W - torch.eye(dd)).abs().max()) < 1e-4                       # orthonormal axes
+    # compare on the numerically non-degenerate part of the spectrum (the centred bank has rank <= C*T - 1)
+    keep = int((Sv[:dd] > 1e-4 * Sv[0]).sum())
+    Pr = W_ref[:, :keep] @ W_ref[:, :keep].t()
+    Pg = W[:, :keep] @ W[:, :keep].t()
+    if keep == dd or float(Sv[keep - 1] / Sv[min(keep, len(Sv) - 1)]) > 1.01:          # a spectral gap at the cut makes the subspace unique
+        assert float((Pr - Pg).abs().max()) < 2e-3
+    Zr, Zg = Xc @ W_ref, Xc @ W
+    assert max_err(Zg @ Zg.t(), Zr @ Zr.t()) < 1e-3                                    # what the kernels consume: inner products of the reduced points
