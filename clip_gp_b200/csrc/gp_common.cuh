@@ -102,7 +102,8 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_n, bool sym, int
 
 template <bool DOT, int MT>
 __device__ __forceinline__ void gram_chunk(float (&acc)[MT][16], const float* __restrict__ tA,
-                                           const float* __restrict__ tB, const int (&tis)[MT], const int (&tjs)[MT]) {
+                                           const float* __restrict__ tB, const int (&tis)[MT], const int (&tjs)[MT],
+                                           const int kb = 0, const int ke = KC) {
 #pragma unroll
     for (int t = 0; t < MT; ++t) {
         if (tis[t] >= 0) {
@@ -110,7 +111,7 @@ __device__ __forceinline__ void gram_chunk(float (&acc)[MT][16], const float* __
             const float* pa = tA + (ti * 4) * KCP;
             const float* pb = tB + (tj * 4) * KCP;
 #pragma unroll 4
-            for (int k = 0; k < KC; ++k) {
+            for (int k = kb; k < ke; ++k) {
                 float a[4], b[4];
 #pragma unroll
                 for (int x = 0; x < 4; ++x) { a[x] = pa[x * KCP + k]; b[x] = pb[x * KCP + k]; }
@@ -137,10 +138,14 @@ __device__ __forceinline__ float kernel_value(int kernel_type, float acc, float 
 //   raw_out (optional, float [nA][ldr]): the un-transformed accumulator (r^2 or dot), needed by the adjoint.
 //   MT: 4x4 register tiles per thread (MT * blockDim.x must cover the tiles; MT = 1 keeps the register footprint small when the
 //   block is called from the warp-path algebra kernel, n <= 33 -> 45 symmetric tiles).
-template <typename OutT, int MT = kMaxTiles>
+//   KS = 2 (MT = 1 only, 2 * tiles <= blockDim.x): two adjacent lanes share one tile and take one half of every chunk's
+//   feature columns each; their partial sums meet through one shuffle per accumulator after the last chunk.  With n <= 33 the
+//   45 symmetric tiles then keep 90 of the 128 threads busy instead of 45 (the Gram phase of a class is latency bound).
+template <typename OutT, int MT = kMaxTiles, int KS = 1>
 __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ raw_out, int ldr,
                            const float* __restrict__ gA, int nA, const float* __restrict__ gB, int nB, int d,
                            int kernel_type, float amp, const float* __restrict__ inv_ls, float* tileA, float* tileB) {
+    static_assert(KS == 1 || (KS == 2 && MT == 1), "k-split needs one tile per thread");
     const bool same = (gA == gB);
     const bool sym = same && (nA == nB);
     const int pA = pad4(nA), pB = pad4(nB);
@@ -149,9 +154,10 @@ __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ 
     float acc[MT][16];
     int tis[MT], tjs[MT];
     const int ntiles = num_tiles(tiles_m, tiles_n, sym);
+    const int khalf = (KS == 2) ? (int)(threadIdx.x & 1) : 0;
 #pragma unroll
     for (int t = 0; t < MT; ++t) {
-        const int tile = threadIdx.x + t * blockDim.x;
+        const int tile = (KS == 2) ? (int)(threadIdx.x >> 1) : (int)(threadIdx.x + t * blockDim.x);
         tis[t] = -1; tjs[t] = 0;
         if (tile < ntiles) tile_coords(tile, tiles_n, sym, tis[t], tjs[t]);
 #pragma unroll
@@ -162,8 +168,14 @@ __device__ void gram_block(OutT* __restrict__ out, int ldo, float* __restrict__ 
         load_chunk(tileA, gA, nA, pA, d, k0, dot ? nullptr : inv_ls);
         if (!same) load_chunk(tileB, gB, nB, pB, d, k0, dot ? nullptr : inv_ls);
         __syncthreads();
-        if (dot) gram_chunk<true, MT>(acc, tileA, same ? tileA : tileB, tis, tjs);
-        else gram_chunk<false, MT>(acc, tileA, same ? tileA : tileB, tis, tjs);
+        const int kb = (KS == 2) ? khalf * (KC / 2) : 0, ke = (KS == 2) ? kb + KC / 2 : KC;
+        if (dot) gram_chunk<true, MT>(acc, tileA, same ? tileA : tileB, tis, tjs, kb, ke);
+        else gram_chunk<false, MT>(acc, tileA, same ? tileA : tileB, tis, tjs, kb, ke);
+    }
+    if (KS == 2) {      // both lanes of a pair end up with the full sums; the even lane writes
+#pragma unroll
+        for (int x = 0; x < 16; ++x) acc[0][x] += __shfl_xor_sync(0xffffffffu, acc[0][x], 1);
+        if (khalf) tis[0] = -1;
     }
 #pragma unroll
     for (int t = 0; t < MT; ++t) {

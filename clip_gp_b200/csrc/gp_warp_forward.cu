@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
             for (int k = tid; k < d; k += NT) invls[k] = 1.f / softplusf(a.raw_lengthscale[(size_t)c * d + k]);
         __syncthreads();
         const float* Zc = a.Z + (size_t)c * n * d;
-        gp::gram_block<float, 1>(K0, LD, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tile, tile);
+        gp::gram_block<float, 1, 2>(K0, LD, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tile, tile);      // 45 tiles x 2 k-halves = 90 threads
         GPW_TS(1);
         if (tid == 0) ks[0] = 1.f;
         // hand-over record for the adjoint (and the K_XX read of the Sigma stage below) + the fp64 operands
