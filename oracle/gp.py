@@ -1,9 +1,9 @@
 """CPU oracle: the GP template weighter (TEST INFRASTRUCTURE, see oracle/__init__.py).
 
-PARITY UNPINNED for the gpytorch/entmax arithmetic: neither package can be run in the
-build container and the reference holds no golden vectors for it.  Every function cites
-the reference call site it restates (paths relative to /root/reference) and, where the
-arithmetic lives in gpytorch / linear_operator / entmax, the library routine whose
+PINNED (tests/test_ref_golden.py) on tests/golden/ref_gp.npz: vectors produced by running the reference's own
+trainers/gp_template_weigher.py, unmodified, on the gpytorch / linear_operator / entmax stand-ins of oracle/_shim
+(tests/golden/make_ref_golden.py).  Every function cites the reference call site it restates (paths relative to
+/root/reference) and, where the arithmetic lives in gpytorch / linear_operator / entmax, the library routine whose
 published algorithm is restated.
 
 Everything is plain differentiable torch, so ``torch.autograd`` through these functions
