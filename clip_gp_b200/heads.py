@@ -20,14 +20,22 @@ from . import metrics, ops
 from .gp_template_weigher import GaussianProcessTemplateWeighter
 
 
-def _cosine_logits(feats_hat: torch.Tensor, prototypes: torch.Tensor, scale) -> torch.Tensor:
-    """scale * f_hat . normalize(p): [B,C] for 2-D prototypes, mean over samples for [S,C,D] (adapter.py:246-251)."""
+def _precision(config) -> str:
+    """GEMM path of the head modules: config.adapter.clipgp_precision, default "tf32" (tensor cores on the fp32 tensors in place, the
+    reference's own GPU arithmetic); "fp32" selects the FFMA comparator.  The split-bf16 / bf16 modes exist in the fused engines only."""
+    p = getattr(getattr(config, "adapter", config), "clipgp_precision", None) or "tf32"
+    return "tf32" if p in ("tf32", "bf16x3", "bf16") else "fp32"
+
+
+def _cosine_logits(feats_hat: torch.Tensor, prototypes: torch.Tensor, scale, precision: str = "fp32") -> torch.Tensor:
+    """scale * f_hat . normalize(p): [B,C] for 2-D prototypes, mean over samples for [S,C,D] (adapter.py:246-251).
+    The MC mean is taken over the unit prototypes BEFORE the contraction (the logits are linear in them): one [B,D] x [C,D]^T
+    product instead of the reference's [B,S,C] einsum + mean -- identical values, S times fewer flops."""
     if prototypes.dim() == 3:
         S, C, D = prototypes.shape
-        p_hat = ops.row_normalize(prototypes).reshape(S * C, D)
-        logits = ops.matmul_nt(feats_hat, p_hat, 1.0).view(feats_hat.shape[0], S, C)
-        return logits.mean(dim=1) * scale
-    return ops.matmul_nt(feats_hat, ops.row_normalize(prototypes), 1.0) * scale
+        p_bar = ops.row_normalize(prototypes).mean(dim=0)
+        return ops.matmul_nt(feats_hat, p_bar, 1.0, precision) * scale
+    return ops.matmul_nt(feats_hat, ops.row_normalize(prototypes), 1.0, precision) * scale
 
 
 class AdapterHead(nn.Module):
@@ -53,26 +61,28 @@ class AdapterHead(nn.Module):
         return self.text_embeddings.mean(dim=1)                                 # adapter.py:225 (uniform template weights)
 
     def forward_features(self, features: torch.Tensor, num_samples: Optional[int] = None) -> torch.Tensor:
-        projected = ops.matmul_nt(features, self.visual_proj.weight, 1.0)       # adapter.py:239
+        prec = _precision(self.config)
+        projected = ops.matmul_nt(features, self.visual_proj.weight, 1.0, prec)  # adapter.py:239
         f_hat = ops.row_normalize(projected)
         scale = self.logit_scale.exp()
         S = self.gp_num_mc_samples_train if self.training else self.gp_num_mc_samples_eval     # adapter.py:242
-        return _cosine_logits(f_hat, self.get_prototypes(S, projected), scale)
+        return _cosine_logits(f_hat, self.get_prototypes(S, projected), scale, prec)
 
     forward = forward_features
 
     def compute_loss(self, features, labels, num_samples: int, gp_beta: float, l2_lambda: float, shots: int):
         """Trainer.compute_loss, adapter.py:387-476."""
-        f_hat = ops.row_normalize(ops.matmul_nt(features, self.visual_proj.weight, 1.0))
+        prec = _precision(self.config)
+        f_hat = ops.row_normalize(ops.matmul_nt(features, self.visual_proj.weight, 1.0, prec))
         scale = float(self.logit_scale.exp())
         if self.gp_weighter is not None and num_samples > 1:
             protos = self.gp_weighter.sample_prototypes(num_samples)            # adapter.py:404
             S, C, D = protos.shape
             p_hat = ops.row_normalize(protos).reshape(S * C, D)
-            logits = ops.matmul_nt(f_hat, p_hat, scale).view(-1, C)             # rows (b, s)
+            logits = ops.matmul_nt(f_hat, p_hat, scale, prec).view(-1, C)       # rows (b, s)
             ce = ops.cross_entropy(logits, labels, rows_per_label=S)            # mean_s mean_b CE (adapter.py:422-428)
         else:
-            ce = ops.cross_entropy(_cosine_logits(f_hat, self.get_prototypes(num_samples), scale), labels)
+            ce = ops.cross_entropy(_cosine_logits(f_hat, self.get_prototypes(num_samples), scale, prec), labels)
         total = ce
         if self.gp_weighter is not None:
             total = total + self.gp_weighter.variational_strategy.kl_divergence().sum() * float(gp_beta)
@@ -106,22 +116,24 @@ class TaskResHead(nn.Module):
             protos = self.gp_weighter.sample_prototypes(S)                      # taskres.py:107-109
             p_hat = ops.row_normalize(protos)
             text_s = p_hat + (self.alpha * self.text_feature_residuals).unsqueeze(0)       # :111-112
-            return _cosine_logits(f_hat, text_s, scale)                         # :113-116
-        return _cosine_logits(f_hat, self.base_text_features + self.alpha * self.text_feature_residuals, scale)   # :119-121
+            return _cosine_logits(f_hat, text_s, scale, _precision(self.config))            # :113-116
+        return _cosine_logits(f_hat, self.base_text_features + self.alpha * self.text_feature_residuals, scale,
+                              _precision(self.config))                          # :119-121
 
 
 class AdapterMLP(nn.Module):
     """trainers/clip_adapter.py:16-32 (bias-free 2-layer MLP with ReLU); the linears run on the clipgp fp32 GEMM."""
 
-    def __init__(self, in_dim: int, reduction: int = 4):
+    def __init__(self, in_dim: int, reduction: int = 4, precision: str = "fp32"):
         super().__init__()
         hidden = max(1, in_dim // max(1, int(reduction)))
         self.fc1 = nn.Linear(in_dim, hidden, bias=False)
         self.fc2 = nn.Linear(hidden, in_dim, bias=False)
+        self.precision = precision
 
     def forward(self, x):
-        x = torch.relu(ops.matmul_nt(x, self.fc1.weight, 1.0))
-        return torch.relu(ops.matmul_nt(x, self.fc2.weight, 1.0))
+        x = torch.relu(ops.matmul_nt(x, self.fc1.weight, 1.0, self.precision))
+        return torch.relu(ops.matmul_nt(x, self.fc2.weight, 1.0, self.precision))
 
 
 class ClipAdapterHead(nn.Module):
@@ -132,7 +144,7 @@ class ClipAdapterHead(nn.Module):
         self.config = config
         a = getattr(config, "adapter", config)
         in_dim = int(clip_weights.shape[0])
-        self.adapter = AdapterMLP(in_dim, int(getattr(a, "clip_adapter_reduction", 4)))
+        self.adapter = AdapterMLP(in_dim, int(getattr(a, "clip_adapter_reduction", 4)), _precision(config))
         self.register_buffer("_blend_ratio", torch.tensor(float(getattr(a, "clip_adapter_ratio", 0.2))))
         self.register_buffer("clip_weights", clip_weights.detach().float().clone())
         self.logit_scale = nn.Parameter(torch.tensor(float(logit_scale)), requires_grad=False)
@@ -150,8 +162,8 @@ class ClipAdapterHead(nn.Module):
         scale = self.logit_scale.exp()
         if self.gp_weighter is not None and bool(getattr(getattr(self.config, "adapter", self.config), "use_gp", False)):
             S = max(1, self.gp_num_mc_samples_train if training else self.gp_num_mc_samples_eval)
-            return _cosine_logits(f_hat, self.gp_weighter.sample_prototypes(S), scale)       # clip_adapter.py:90-96
-        return _cosine_logits(f_hat, self.clip_weights.t().contiguous(), scale)                # :97-100 (normalize(dim=0) of [D,K])
+            return _cosine_logits(f_hat, self.gp_weighter.sample_prototypes(S), scale, _precision(self.config))   # clip_adapter.py:90-96
+        return _cosine_logits(f_hat, self.clip_weights.t().contiguous(), scale, _precision(self.config))           # :97-100 (normalize(dim=0) of [D,K])
 
     def forward(self, features):
         return self.logits_from_features(features, training=self.training)

@@ -232,7 +232,48 @@ class MatmulNT(torch.autograd.Function):
         return dA, dB, None
 
 
-def matmul_nt(A, B, alpha: float = 1.0):
+class MatmulNT_TF32(torch.autograd.Function):
+    """MatmulNT on the tensor cores: tcgen05 kind::tf32 over the fp32 tensors in place (csrc/gemm_tc.cu); the two adjoint
+    products read their operands transposed in place (MN-major), so neither direction makes a cast or a transposed copy.
+    TF32 is the reference's own GPU arithmetic (trainers/adapter.py:23, allow_tf32)."""
+
+    @staticmethod
+    def forward(ctx, A, B, alpha: float):
+        from . import tc
+        _lib.require_cuda(A, B)
+        A, B = _c(A), _c(B)
+        if B.shape[1] != A.shape[1]:
+            raise ValueError(f"matmul_nt: {tuple(A.shape)} x {tuple(B.shape)}^T")
+        out = tc.gemm_tf32(A, B, float(alpha))
+        ctx.save_for_backward(A, B)
+        ctx.alpha = float(alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, dC):
+        from . import tc
+        A, B = ctx.saved_tensors
+        dC = _c(dC)
+        dA = dB = None
+        if ctx.needs_input_grad[0]:
+            dA = tc.gemm_tf32(dC, B, ctx.alpha, b_t=True, split_k=True)              # dA = alpha dC B        (B [N,K] read as [K(=N), .])
+        if ctx.needs_input_grad[1]:
+            dB = tc.gemm_tf32(dC, A, ctx.alpha, a_t=True, b_t=True, split_k=True)    # dB = alpha dC^T A      (contraction over rows)
+        return dA, dB, None
+
+
+def tf32_ok(A, B) -> bool:
+    """Row pitches of all three products (forward and both adjoints) are multiples of 16 bytes and there is something to do."""
+    M, K = A.shape
+    N = B.shape[0]
+    return M > 0 and N > 0 and K % 4 == 0 and N % 4 == 0 and A.is_cuda
+
+
+def matmul_nt(A, B, alpha: float = 1.0, precision: str = "fp32"):
+    """alpha * A @ B^T.  precision: "fp32" (FFMA kernel, exact comparator) | "tf32" (tensor cores; falls back to fp32 when a row
+    pitch is not a multiple of 16 bytes)."""
+    if precision == "tf32" and tf32_ok(A, B):
+        return MatmulNT_TF32.apply(A, B, alpha)
     return MatmulNT.apply(A, B, alpha)
 
 

@@ -223,7 +223,7 @@ class BaseTrainer:
         unit-normalised template embeddings, re-normalised; logits 100 f_hat . w (taskres.py:203-206, tip_adapter.py:219)."""
         with torch.no_grad():
             protos = F.normalize(F.normalize(self.text_embeddings, dim=-1).mean(dim=1), dim=-1)
-            logits = ops.matmul_nt(ops.row_normalize(self.features_test), protos.contiguous(), 100.0)
+            logits = ops.matmul_nt(ops.row_normalize(self.features_test), protos.contiguous(), 100.0, heads._precision(self.config))
             res = metrics.evaluate_calibration(logits, self.labels_test)
         self.zero_shot_metrics = {"top1_acc": res["top1_acc"], "ece": res["ece"], "aece": res["aece"],
                                   "calibration": res["calibration"], "adaptive_calibration": res["adaptive_calibration"]}
@@ -562,8 +562,8 @@ class TipAdapterTrainer(BaseTrainer, _GPInitMixin):
             S = int(_get(self.config, "adapter.gp_num_mc_samples_eval", 100) or 1)
             with torch.no_grad():       # mean_s 100 f.p_hat_s == 100 f.(mean_s p_hat_s) (tip_adapter.py:211-217)
                 pm = self.gp_weighter.collapsed_prototypes(max(1, S), eps=getattr(self, "eval_eps", None))
-            return ops.matmul_nt(feats_hat, pm, 100.0)
-        return ops.matmul_nt(feats_hat, self.clip_weights, 100.0)           # tip_adapter.py:219
+            return ops.matmul_nt(feats_hat, pm, 100.0, heads._precision(self.config))
+        return ops.matmul_nt(feats_hat, self.clip_weights, 100.0, heads._precision(self.config))           # tip_adapter.py:219
 
     def model_inference(self, features):
         f_hat = ops.row_normalize(features)

@@ -25,6 +25,23 @@ def test_matmul_nt_forward_backward(M, N, K):
     assert within(Ad.grad, Ar.grad, 1e-5) and within(Bd.grad, Br.grad, 1e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(48, 36, 128), (128, 1000, 512), (130, 10000, 76), (700, 300, 1024), (33, 512, 10000), (50, 37, 128)])
+def test_matmul_nt_tf32_forward_backward(M, N, K):
+    """Tensor-core (kind::tf32) autograd product and both in-place-transposed adjoints; (50,37,128): N not a multiple of 4 -> FFMA."""
+    g = torch.Generator().manual_seed(M * N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    dC = torch.randn(M, N, generator=g)
+    Ar, Br = A.double().requires_grad_(True), B.double().requires_grad_(True)
+    (0.7 * Ar @ Br.t()).backward(dC.double())
+    Ad, Bd = A.cuda().requires_grad_(True), B.cuda().requires_grad_(True)
+    C = ops.matmul_nt(Ad, Bd, 0.7, "tf32")
+    C.backward(dC.cuda())
+    tol = 1e-5 if N % 4 else 2e-3                              # TF32: 10-bit mantissa operands, fp32 accumulate; normwise
+    assert max_err(C, 0.7 * A.double() @ B.double().t()) < tol
+    assert max_err(Ad.grad, Ar.grad) < tol and max_err(Bd.grad, Br.grad) < tol
+    assert ops.tf32_ok(Ad, Bd) == (N % 4 == 0)
+
+
 def test_adapter_head_loss_and_grads_match_oracle():
     """adapter.py:401-428 composed from clipgp ops == oracle.heads.adapter_mc_ce (autograd)."""
     g = torch.Generator().manual_seed(1)
