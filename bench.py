@@ -469,6 +469,20 @@ def run_ours(args):
     eval_pass = eng.eval_metrics_graph(f_sh, y_sh, n_eval, precision=eprec, mc="collapsed")
     eval_ms, _ = time_eval(eval_pass)
     eval_graph_only_ms, _ = time_eval(eval_replay)
+    # weak-scaling eval (N > 1): every rank holds a FULL n_eval-image set (the test set rotated by the rank's shard offset, so the
+    # ranks' images differ), the metric is global over world * n_eval images: same graph, counters all-reduced, (conf, hit) gathered,
+    # AECE rank-select over the global set.  50 000 images are 0.3 ms of work for ONE B200; this is the regime 8 of them are for.
+    eval_weak = None
+    if world > 1:
+        f_wk, y_wk = torch.roll(f_te, -lo_e, 0).to(dev), torch.roll(y_te, -lo_e, 0).to(dev)
+        weak_pass = eng.eval_metrics_graph(f_wk, y_wk, n_eval * world, precision=eprec, mc="collapsed")
+        weak_ms, wout = time_eval(weak_pass)
+        cnt_w = metrics.counters_from_hist(wout[2], n_eval * world)
+        eval_weak = {"images_total": n_eval * world, "images_per_rank": n_eval, "ms": weak_ms, "img_per_s": n_eval * world / (weak_ms * 1e-3),
+                     "top1_acc": cnt_w.top1 * 100.0 / max(1, n_eval * world), "ece": metrics.ece_from_counters(cnt_w)[0],
+                     "aece": metrics.aece_from_bins(wout[3], n_eval * world, 10)[0], "scaling": "weak"}
+        weak_pass.release()
+        del weak_pass, f_wk, y_wk
 
     # e2e eval: pinned HOST features of this rank's shard in, metrics out (H2D of the shard + D2H of counters inside the timed region)
     f_host_sh, y_host_sh = f_te[sl].contiguous().pin_memory(), y_te[sl].contiguous().pin_memory()
@@ -618,6 +632,7 @@ def run_ours(args):
                  "multi_gpu": (f"images sharded over {world} ranks; the eval GP forward runs on C/{world} classes per rank and one 2 MB "
                                "all-reduce completes the mean prototypes; counters: one all-reduce, AECE: all-gather of (conf, hit)") if world > 1 else None,
                  "form": "one CUDA graph (engine.eval_metrics_graph; graph_only_ms = engine.eval_graph without the AECE / collective tail): GP forward + prototypes on a side stream next to cast / projection / normalise, then ONE tcgen05 GEMM over the raw features against [W ; mean_s p_hat_s W] (projection, normalisation, collapsed logit-mean and the calibration epilogue fused), precision = " + eprec,
+                 "weak": eval_weak,
                  "variants": eval_variants},
         "roofline_eval_gemm": {"kernel": "tc_gemm_kernel (EPI_ROWSTATS), materialised MC logits [N,D]x[S*C,D]^T accumulated over s in TMEM",
                                "bound": "tensor", "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kThreads) gp_kernel_adjoint_kernel(const clipg
 }
 
 // only_unaliased != 0: classes served by the warp path (alias flag set) are skipped.
-__global__ void __launch_bounds__(kThreads) gp_backward_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b, const int only_unaliased) {
+__global__ void __launch_bounds__(kThreadsMax) gp_backward_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b, const int only_unaliased) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int c = (int)a.c_begin + blockIdx.x, tid = threadIdx.x;
     const int T = (int)a.T, n = (int)a.n, d = (int)a.d, S = (int)a.S;
@@ -365,6 +365,6 @@ extern "C" int clipgp_gp_backward(const clipgp_gp_args* a, const clipgp_gp_bwd_a
         gp::gp_kernel_adjoint_kernel<<<gp_grid(a), gp::kThreads, sm2, (cudaStream_t)stream>>>(*a, *b);
         return check_launch("gp_kernel_adjoint_kernel");
     }
-    gp::gp_backward_kernel<<<gp_grid(a), gp::kThreads, smem, (cudaStream_t)stream>>>(*a, *b, 0);
+    gp::gp_backward_kernel<<<gp_grid(a), gp::general_threads(a->n), smem, (cudaStream_t)stream>>>(*a, *b, 0);
     return check_launch("gp_backward_kernel");
 }

@@ -12,6 +12,16 @@ inline unsigned gp_grid(const clipgp_gp_args* a) { return (unsigned)(a->c_count 
 namespace gp {
 
 constexpr int kThreads = 128;  // threads per class CTA
+constexpr int kThreadsMax = 512;  // launch bound of the general block kernels (wide CTAs for n > 33, see general_threads)
+
+// Threads per class CTA of the general block kernels.  n <= 33: 128 (several classes per SM).  n > 33: the shared-memory footprint
+// allows one class per SM, so the only parallelism an SM sees is inside the CTA: every phase but the one-warp factorisations is
+// written against blockDim.x and spreads over 16 warps.
+inline int general_threads(long long n) {
+    static const char* e = getenv("CLIPGP_GP_WIDE_THREADS");
+    const int wide = e ? atoi(e) : 512;
+    return n > 33 ? wide : kThreads;
+}
 constexpr int KC = 32;         // feature-dim chunk streamed through shared memory
 constexpr int KCP = KC + 1;    // padded row stride of a chunk tile (conflict-free row access)
 constexpr int kMaxTiles = 3;   // 4x4 register tiles per thread: 3*128 >= ceil(65/4)^2 = 289

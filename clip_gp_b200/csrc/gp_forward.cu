@@ -13,7 +13,7 @@ namespace gp {
 
 // gram_only != 0: classes whose test inputs alias the inducing rows only get their kernel block K_ZZ computed and saved
 // (the register-resident warp kernel of gp_warp_forward.cu continues from it); un-aliased classes run the whole path here.
-__global__ void __launch_bounds__(kThreads) gp_forward_kernel(const clipgp_gp_args a, const int gram_only) {
+__global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp_args a, const int gram_only) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int c = (int)a.c_begin + blockIdx.x, tid = threadIdx.x;
     const int T = (int)a.T, n = (int)a.n, d = (int)a.d, S = (int)a.S;
@@ -335,6 +335,6 @@ extern "C" int clipgp_gp_forward(const clipgp_gp_args* a, void* stream) {
         if (rc != CLIPGP_OK) return rc;
         return clipgp_gp_forward_warp_launch(a, (cudaStream_t)stream, 0);
     }
-    gp::gp_forward_kernel<<<gp_grid(a), gp::kThreads, smem, (cudaStream_t)stream>>>(*a, 0);
+    gp::gp_forward_kernel<<<gp_grid(a), gp::general_threads(a->n), smem, (cudaStream_t)stream>>>(*a, 0);
     return check_launch("gp_forward_kernel");
 }
