@@ -8,6 +8,7 @@
 #include <stdlib.h>
 
 #include "gp_layout.cuh"
+#include "gp_block.cuh"
 
 namespace clipgp {
 namespace gp {
@@ -60,6 +61,13 @@ __global__ void __launch_bounds__(kThreads) gp_kernel_adjoint_kernel(const clipg
     }
 }
 
+#ifdef CLIPGP_PHASE_TS
+__device__ long long g_gen_ts_bwd[32];
+#define GENB_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_gen_ts_bwd[i] = clock64(); } while (0)
+#else
+#define GENB_TS(i) do { } while (0)
+#endif
+
 // only_unaliased != 0: classes served by the warp path (alias flag set) are skipped.
 __global__ void __launch_bounds__(kThreadsMax) gp_backward_kernel(const clipgp_gp_args a, const clipgp_gp_bwd_args b, const int only_unaliased) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -87,6 +95,7 @@ __global__ void __launch_bounds__(kThreadsMax) gp_backward_kernel(const clipgp_g
     const int kt = a.kernel_type;
     const float dkl = b.dkl ? b.dkl[c] : b.dkl_scalar;
 
+    GENB_TS(0);
     // ---- load persistent state
     if (kt != CLIPGP_KERNEL_LINEAR)
         for (int k = tid; k < d; k += blockDim.x) invls[k] = 1.f / softplusf(a.raw_lengthscale[(size_t)c * d + k]);
@@ -107,6 +116,7 @@ __global__ void __launch_bounds__(kThreadsMax) gp_backward_kernel(const clipgp_g
     for (int i = tid; i < n; i += blockDim.x) mvec[i] = a.var_mean[(size_t)c * n + i];
     for (int j = tid; j < T; j += blockDim.x) dmu[j] = 0.f;
 
+    GENB_TS(1);
     // =========================== B1 ===========================
     {
         float* R = reinterpret_cast<float*>(smem + Y.p_R);
@@ -151,24 +161,13 @@ __global__ void __launch_bounds__(kThreadsMax) gp_backward_kernel(const clipgp_g
                 for (int ss = 0; ss < sc; ++ss) s += dfb[ss * ldt + j];
                 dmu[j] += s;
             }
-            for (int idx = tid; idx < T * T; idx += blockDim.x) {
-                const int j = idx / T, k = idx - j * T;
-                if (k <= j) {
-                    float s = 0.f;
-                    for (int ss = 0; ss < sc; ++ss) s = fmaf(dfb[ss * ldt + j], ebuf[k * SCH + ss], s);
-                    dSig[j * ldt + k] += s;
-                }
-            }
+            block_gemm<float, 0>(T, T, sc, [&](int j, int ss) { return dfb[ss * ldt + j]; }, [&](int ss, int k) { return ebuf[k * SCH + ss]; },
+                                 [&](int j, int k, float v) { if (k <= j) dSig[j * ldt + k] += v; });
         }
         __syncthreads();
-        if ((tid >> 5) == 0) warp_cholesky_rev<float>(R, ldt, invdR, dSig, ldt, T);
-        __syncthreads();
-        for (int idx = tid; idx < T * T; idx += blockDim.x) {                // dSig <- dSigma (full, symmetric)
-            const int i = idx / T, j = idx - i * T;
-            if (i > j) { const float v = 0.5f * dSig[i * ldt + j]; dSig[i * ldt + j] = v; dSig[j * ldt + i] = v; }
-        }
-        __syncthreads();
-        (void)scrF;
+        GENB_TS(2);
+        cta_cholesky_adjoint<float>(R, ldt, invdR, dSig, scrF, ldt, T, reinterpret_cast<float*>(smem + Y.line));     // dSig <- dSigma (full, symmetric)
+        GENB_TS(3);
     }
 
     // =========================== B3 ===========================
@@ -182,39 +181,25 @@ __global__ void __launch_bounds__(kThreadsMax) gp_backward_kernel(const clipgp_g
             Lq[i * ldn + j] = (j <= i) ? a.chol_var[(size_t)c * n * n + idx] : 0.f;
         }
         __syncthreads();
-        for (int idx = tid; idx < n * T; idx += blockDim.x) {
-            const int i = idx / T, j = idx - i * T;
-            float s = 0.f;
-            for (int k = i; k < n; ++k) s = fmaf(Lq[k * ldn + i], Af[k * ldt + j], s);
-            Bm[i * ldt + j] = s;
-        }
+        // Bm = Lq^T A (Lq is stored with a zero upper triangle)
+        block_gemm<float, 1>(n, T, n, [&](int i, int k) { return Lq[k * ldn + i]; }, [&](int k, int j) { return Af[k * ldt + j]; },
+                             [&](int i, int j, float v) { Bm[i * ldt + j] = v; });
         __syncthreads();
-        for (int idx = tid; idx < n * T; idx += blockDim.x) {      // dBm = 2 Bm dSigma
-            const int i = idx / T, j = idx - i * T;
-            float s = 0.f;
-            for (int k = 0; k < T; ++k) s = fmaf(Bm[i * ldt + k], dSig[k * ldt + j], s);
-            dBm[i * ldt + j] = 2.f * s;
-        }
+        // dBm = 2 Bm dSigma
+        block_gemm<float, 0>(n, T, T, [&](int i, int k) { return Bm[i * ldt + k]; }, [&](int k, int j) { return dSig[k * ldt + j]; },
+                             [&](int i, int j, float v) { dBm[i * ldt + j] = 2.f * v; });
+        // dA = -2 A dSigma + m dmu^T  (+ Lq dBm below)
+        block_gemm<float, 0>(n, T, T, [&](int i, int k) { return Af[i * ldt + k]; }, [&](int k, int j) { return dSig[k * ldt + j]; },
+                             [&](int i, int j, float v) { dAf[i * ldt + j] = -2.f * v + mvec[i] * dmu[j]; });
         __syncthreads();
-        for (int idx = tid; idx < n * T; idx += blockDim.x) {      // dA = -2 A dSigma + Lq dBm + m dmu^T
-            const int i = idx / T, j = idx - i * T;
-            float s = 0.f;
-            for (int k = 0; k < T; ++k) s = fmaf(Af[i * ldt + k], dSig[k * ldt + j], s);
-            float s2 = 0.f;
-            for (int k = 0; k <= i; ++k) s2 = fmaf(Lq[i * ldn + k], dBm[k * ldt + j], s2);
-            const float v = -2.f * s + s2 + mvec[i] * dmu[j];
-            dAf[i * ldt + j] = v;
-            dAd[i * ldt + j] = (double)v;
-        }
-        for (int idx = tid; idx < n * n; idx += blockDim.x) {      // dLq = tril(A dBm^T) + dkl (Lq - diag(1/Lq_ii))
-            const int i = idx / n, j = idx - i * n;
-            float v = 0.f;
-            if (j <= i) {
-                for (int t = 0; t < T; ++t) v = fmaf(Af[i * ldt + t], dBm[j * ldt + t], v);
-                v += dkl * (Lq[i * ldn + j] - (i == j ? 1.f / Lq[i * ldn + i] : 0.f));
-            }
-            b.dchol_var[(size_t)c * n * n + idx] = v;
-        }
+        block_gemm<float, 2>(n, T, n, [&](int i, int k) { return Lq[i * ldn + k]; }, [&](int k, int j) { return dBm[k * ldt + j]; },
+                             [&](int i, int j, float v) { const float t = dAf[i * ldt + j] + v; dAf[i * ldt + j] = t; dAd[i * ldt + j] = (double)t; });
+        // dLq = tril(A dBm^T) + dkl (Lq - diag(1/Lq_ii))
+        block_gemm<float, 0>(n, n, T, [&](int i, int t) { return Af[i * ldt + t]; }, [&](int t, int j) { return dBm[j * ldt + t]; },
+                             [&](int i, int j, float v) {
+                                 b.dchol_var[(size_t)c * n * n + (size_t)i * n + j] =
+                                     (j <= i) ? v + dkl * (Lq[i * ldn + j] - (i == j ? 1.f / Lq[i * ldn + i] : 0.f)) : 0.f;
+                             });
         for (int i = tid; i < n; i += blockDim.x) {                // dm = A dmu + dkl m
             float s = 0.f;
             for (int j = 0; j < T; ++j) s = fmaf(Af[i * ldt + j], dmu[j], s);
@@ -225,30 +210,29 @@ __global__ void __launch_bounds__(kThreadsMax) gp_backward_kernel(const clipgp_g
         __syncthreads();
     }
 
+    GENB_TS(4);
     // =========================== B4 (fp64) ===========================
     float* dKzz = reinterpret_cast<float*>(smem + Y.p_dKzz);
     {
         double* scrD = reinterpret_cast<double*>(smem + Y.p_scrD);
         double* dLd = reinterpret_cast<double*>(smem + Y.p_dLd);
-        trsm_lowerT_left<double>(Ld, ldn, invd, dAd, ldt, n, T);   // dAd <- dK_ZX = L^-T dA
-        for (int idx = tid; idx < n * n; idx += blockDim.x) {      // dL = -tril(dK_ZX A^T)
-            const int i = idx / n, j = idx - i * n;
-            double s = 0.0;
-            if (j <= i)
-                for (int t = 0; t < T; ++t) s += dAd[i * ldt + t] * (double)Af[j * ldt + t];
-            dLd[i * ldn + j] = -s;
-        }
+        cta_trsm_lowerT_left<double>(Ld, ldn, invd, dAd, ldt, n, T, reinterpret_cast<double*>(smem + Y.line));   // dAd <- dK_ZX = L^-T dA
+        GENB_TS(5);
+        // dL = -tril(dK_ZX A^T)
+        block_gemm<double, 0>(n, n, T, [&](int i, int t) { return dAd[i * ldt + t]; }, [&](int t, int j) { return (double)Af[j * ldt + t]; },
+                              [&](int i, int j, double v) { dLd[i * ldn + j] = (j <= i) ? -v : 0.0; });
         __syncthreads();
-        if ((tid >> 5) == 0) warp_cholesky_rev<double>(Ld, ldn, invd, dLd, ldn, n);
-        __syncthreads();
+        GENB_TS(6);
+        cta_cholesky_adjoint<double>(Ld, ldn, invd, dLd, scrD, ldn, n, reinterpret_cast<double*>(smem + Y.line));    // dLd <- dK_ZZ (full, symmetric)
+        GENB_TS(7);
         for (int idx = tid; idx < n * n; idx += blockDim.x) {
             const int i = idx / n, j = idx - i * n;
-            dKzz[i * ldn + j] = (float)sym_from_rev<double>(dLd, ldn, i, j);
+            dKzz[i * ldn + j] = (float)dLd[i * ldn + j];
         }
         __syncthreads();
-        (void)scrD;
     }
 
+    GENB_TS(8);
     // =========================== B5 ===========================
     {
         float* dKzx = reinterpret_cast<float*>(smem + Y.p_dKzx);   // [n][ldt]
@@ -302,12 +286,17 @@ __global__ void __launch_bounds__(kThreadsMax) gp_backward_kernel(const clipgp_g
             if (b.dZ_last) b.dZ_last[(size_t)c * d + k] = dzl[k];
         }
     }
+    GENB_TS(9);
 }
 
 }  // namespace gp
 }  // namespace clipgp
 
 using namespace clipgp;
+
+#ifdef CLIPGP_PHASE_TS
+extern "C" int clipgp_debug_general_ts_bwd(long long* out) { return (int)cudaMemcpyFromSymbol(out, gp::g_gen_ts_bwd, sizeof(long long) * 32); }
+#endif
 
 int clipgp_gp_backward_warp_launch(const clipgp_gp_args* a, const clipgp_gp_bwd_args* b, cudaStream_t st, int fuse);   // gp_warp_backward.cu
 extern "C" int clipgp_gp_warp_fused_adjoint_ok(int64_t n, int64_t d);

@@ -285,6 +285,109 @@ __device__ __forceinline__ T sym_from_rev(const T* __restrict__ G, int ld, int i
     return i == j ? G[i * ld + i] : (T)0.5 * (i > j ? G[i * ld + j] : G[j * ld + i]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Whole-CTA (right-looking) factorisation, solves and Cholesky adjoint: one barrier per column / row, every warp busy.
+// The one-warp routines above cost ~700-1000 cycles per column whatever the arithmetic type (a dependent chain of shared-memory
+// dot products issued by one warp while the rest of the CTA waits); these spread each step's rank-1 update over the CTA
+// (rows over warps, columns over lanes).  Used by the general block kernels (n up to 65, 128-512 threads).
+
+// A = L L^T in place on the lower triangle of A [n][ld]; optionally B [n][ldb] (ncol columns) <- L^-1 B in the same sweep
+// (forward elimination of the augmented matrix [A | B]).  Step j applies the update of the UNSCALED column j
+// (a_ij a_kj / a_jj): nobody writes column j after step j-1, so the scaling l_ij = a_ij / sqrt(a_jj) is one parallel pass at the end.
+// invd[j] = 1 / L[j][j].  Returns true (uniformly) when a pivot was not strictly positive.  flag: one shared int.
+template <typename T>
+__device__ bool block_cholesky_solve(T* __restrict__ A, int n, int ld, T* __restrict__ invd, T* __restrict__ B, int ldb, int ncol,
+                                     int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = 0;
+    for (int j = 0; j + 1 < n; ++j) {
+        __syncthreads();
+        const T ip = (T)1 / A[j * ld + j];
+        const T* cj = A + j;
+        for (int i = j + 1 + warp; i < n; i += nw) {
+            const T f = A[i * ld + j] * ip;
+            T* ri = A + i * ld;
+            for (int k = j + 1 + lane; k <= i; k += 32) ri[k] -= f * cj[k * ld];
+            if (B != nullptr) {
+                T* bi = B + i * ldb;
+                const T* bj = B + j * ldb;
+                for (int c = lane; c < ncol; c += 32) bi[c] -= f * bj[c];
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const T p = A[j * ld + j];
+        if (!(p > (T)0)) *flag = 1;
+        const T dd = sqrt(p);
+        A[j * ld + j] = dd;
+        invd[j] = (T)1 / dd;
+    }
+    __syncthreads();
+    for (int i = 1 + warp; i < n; i += nw)
+        for (int k = lane; k < i; k += 32) A[i * ld + k] *= invd[k];
+    if (B != nullptr)
+        for (int i = warp; i < n; i += nw) {
+            const T s = invd[i];
+            for (int c = lane; c < ncol; c += 32) B[i * ldb + c] *= s;
+        }
+    __syncthreads();
+    return *flag != 0;
+}
+
+// Solve L^T X = B in place (B [n][ldb], ncol columns): right-looking back substitution, one barrier per row.
+template <typename T>
+__device__ void block_trsm_lowerT_left(const T* __restrict__ L, int ldl, const T* __restrict__ invd, T* __restrict__ B, int ldb,
+                                       int n, int ncol) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = n - 1; k > 0; --k) {
+        __syncthreads();
+        const T ik = invd[k];
+        const T* bk = B + k * ldb;
+        const T* lk = L + k * ldl;
+        for (int i = warp; i < k; i += nw) {
+            const T f = lk[i] * ik;
+            T* bi = B + i * ldb;
+            for (int c = lane; c < ncol; c += 32) bi[c] -= f * bk[c];
+        }
+    }
+    __syncthreads();
+    for (int i = warp; i < n; i += nw) {
+        const T s = invd[i];
+        for (int c = lane; c < ncol; c += 32) B[i * ldb + c] *= s;
+    }
+    __syncthreads();
+}
+
+// Adjoint of L = chol(A) in solve form: dA = sym(L^-T Phi(L^T dL) L^-1), Phi = lower triangle with halved diagonal.
+// In: L, invd, G = dL (lower triangle read).  Out: G = the SYMMETRIC gradient dA (full matrix).  W: scratch [n][ld].
+template <typename T>
+__device__ void block_cholesky_adjoint(const T* __restrict__ L, int ldl, const T* __restrict__ invd, T* __restrict__ G,
+                                       T* __restrict__ W, int ld, int n) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    for (int i = warp; i < n; i += nw)
+        for (int j = lane; j < n; j += 32) {
+            T s = (T)0;
+            if (j <= i) {
+                for (int k = i; k < n; ++k) s += L[k * ldl + i] * G[k * ld + j];
+                if (j == i) s *= (T)0.5;
+            }
+            W[i * ld + j] = s;
+        }
+    block_trsm_lowerT_left<T>(L, ldl, invd, W, ld, n, n);          // X = L^-T Phi
+    for (int i = warp; i < n; i += nw)
+        for (int j = lane; j < n; j += 32) G[i * ld + j] = W[j * ld + i];
+    block_trsm_lowerT_left<T>(L, ldl, invd, G, ld, n, n);          // M^T = L^-T X^T
+    for (int i = 1 + warp; i < n; i += nw)
+        for (int j = lane; j < i; j += 32) {
+            const T v = (T)0.5 * (G[i * ld + j] + G[j * ld + i]);
+            G[i * ld + j] = v; G[j * ld + i] = v;
+        }
+    __syncthreads();
+}
+
 // Solve L X = B in place (B is [n][ncol], leading dim ldb); one thread per column.
 template <typename T>
 __device__ void trsm_lower_left(const T* __restrict__ L, int ldl, const T* __restrict__ invd, T* __restrict__ B,

@@ -7,9 +7,18 @@
 #include <stdlib.h>
 
 #include "gp_layout.cuh"
+#include "gp_block.cuh"
 
 namespace clipgp {
 namespace gp {
+
+// Phase timestamps of the first class CTA (debug builds with -DCLIPGP_PHASE_TS only; tools/gp_general_ts.py)
+#ifdef CLIPGP_PHASE_TS
+__device__ long long g_gen_ts[32];
+#define GEN_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_gen_ts[i] = clock64(); } while (0)
+#else
+#define GEN_TS(i) do { } while (0)
+#endif
 
 // gram_only != 0: classes whose test inputs alias the inducing rows only get their kernel block K_ZZ computed and saved
 // (the register-resident warp kernel of gp_warp_forward.cu continues from it); un-aliased classes run the whole path here.
@@ -40,12 +49,12 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
     float* ebuf = pool + (size_t)SCH * ldt;   // [T][SCH]
     __shared__ float red[32];
     __shared__ int s_flag;
-    const int warp_id = tid >> 5;
 
     const float* Zc = a.Z + (size_t)c * n * d;
     const float* Xc = a.X + (size_t)c * T * d;
     const int kt = a.kernel_type;
 
+    GEN_TS(0);
     // ---- hyper-parameters (gpytorch Positive constraint = softplus)
     const bool compact = gram_only && a.x_is_z_prefix == 2;      // small launch: only the Gram scratch exists in smem
     float amp = 1.f;
@@ -81,7 +90,9 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
         for (int idx = tid; idx < n * n; idx += blockDim.x) { const int i = idx / n, j = idx - i * n; ks[1 + idx] = K0c[i * ldn + j]; }
         return;
     }
+    GEN_TS(1);
     gram_block<float>(K0, ldn, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB);
+    GEN_TS(2);
     if (!alias) {
         gram_block<double>(Ad, ldt, nullptr, 0, Zc, n, Xc, T, d, kt, amp, invls, tileA, tileB);
         gram_block<float>(Sig, ldt, nullptr, 0, Xc, T, Xc, T, d, kt, amp, invls, tileA, tileB);
@@ -113,31 +124,24 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
     __syncthreads();
 
     // ---- L = chol64(K_ZZ + 1e-4 I);  A = L^-1 K_ZX
-    if (warp_id == 0) {
-        const bool f = warp_cholesky<double>(Ld, n, ldn, invd);
-        if (tid == 0) s_flag = f ? 1 : 0;
-    }
-    __syncthreads();
-    const bool failL = s_flag != 0;
-    trsm_lower_left<double>(Ld, ldn, invd, Ad, ldt, n, T);
+    GEN_TS(3);
+    const bool failL = cta_cholesky_solve<double, true>(Ld, n, ldn, invd, Ad, ldt, T, reinterpret_cast<double*>(smem + Y.line), &s_flag);
+    GEN_TS(4);
     for (int idx = tid; idx < n * T; idx += blockDim.x) {
         const int i = idx / T, j = idx - i * T;
         Af[i * ldt + j] = (float)Ad[i * ldt + j];
     }
     __syncthreads();
     // ---- Bm = Lq^T A ;  mu = A^T m + mean_x
-    for (int idx = tid; idx < n * T; idx += blockDim.x) {
-        const int i = idx / T, j = idx - i * T;
-        float s = 0.f;
-        for (int k = i; k < n; ++k) s = fmaf(Lq[k * ldn + i], Af[k * ldt + j], s);
-        Bm[i * ldt + j] = s;
-    }
+    block_gemm<float, 1>(n, T, n, [&](int i, int k) { return Lq[k * ldn + i]; }, [&](int k, int j) { return Af[k * ldt + j]; },
+                         [&](int i, int j, float v) { Bm[i * ldt + j] = v; });       // Lq is stored with a zero upper triangle
     for (int j = tid; j < T; j += blockDim.x) {
         float s = 0.f;
         for (int i = 0; i < n; ++i) s = fmaf(Af[i * ldt + j], mvec[i], s);
         mu[j] = s + (a.mean_x ? a.mean_x[(size_t)c * T + j] : 0.f);
     }
     __syncthreads();
+    GEN_TS(5);
     // ---- Sigma = K_XX + 1e-4 I + Bm^T Bm - A^T A   (lower triangle; 4x4 register tiles over (i, j), k = inducing index)
     {
         const int tt = pad4(T) >> 2;
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
         }
     }
     __syncthreads();
+    GEN_TS(6);
     // ---- R = chol32(Sigma), psd_safe_cholesky: retry with total diagonal jitter 1e-6, 1e-5, 1e-4
     int retries = 0;
     bool failR = true;
@@ -183,17 +188,13 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
             if (j <= i) R[i * ldt + j] = Sig[i * ldt + j] + (i == j ? jit : 0.f);
         }
         __syncthreads();
-        if (warp_id == 0) {
-            const bool f = warp_cholesky<float>(R, T, ldt, invdR);
-            if (tid == 0) s_flag = f ? 1 : 0;
-        }
-        __syncthreads();
-        failR = s_flag != 0;
+        failR = cta_cholesky_solve<float, false>(R, T, ldt, invdR, nullptr, 0, 0, reinterpret_cast<float*>(smem + Y.line), &s_flag);
         if (!failR) break;
         ++retries;
         __syncthreads();     // everyone has read s_flag before the next attempt overwrites it
     }
     if (tid == 0 && a.status) a.status[c] = failL ? -2 : (failR ? -1 : retries);
+    GEN_TS(7);
 
     // ---- saved tensors for the adjoint
     if (a.L)
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
     }
     __syncthreads();   // pool: tiles are dead, sample buffers take over
 
+    GEN_TS(8);
     // ---- f_s = mu + R eps_s ;  w_s = sparsemax(f_s)
     uint64_t seed = 0, step = 0;
     if (a.eps == nullptr) { seed = a.rng_state[0]; step = a.rng_state[1]; }
@@ -241,12 +243,8 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
             ebuf[t * SCH + ss] = e;
         }
         __syncthreads();
-        for (int idx = tid; idx < sc * T; idx += blockDim.x) {
-            const int ss = idx / T, j = idx - ss * T;
-            float s = 0.f;
-            for (int k = 0; k <= j; ++k) s = fmaf(R[j * ldt + k], ebuf[k * SCH + ss], s);
-            fbuf[ss * ldt + j] = s + mu[j];
-        }
+        block_gemm<float, 2>(T, sc, T, [&](int j, int k) { return k <= j ? R[j * ldt + k] : 0.f; }, [&](int k, int ss) { return ebuf[k * SCH + ss]; },
+                             [&](int j, int ss, float v) { fbuf[ss * ldt + j] = v + mu[j]; });
         __syncthreads();
         for (int ss = warp; ss < sc; ss += nwarps) {
             const float f0 = lane < T ? fbuf[ss * ldt + lane] : -INFINITY;
@@ -260,12 +258,17 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
         }
         __syncthreads();
     }
+    GEN_TS(9);
 }
 
 }  // namespace gp
 }  // namespace clipgp
 
 using namespace clipgp;
+
+#ifdef CLIPGP_PHASE_TS
+extern "C" int clipgp_debug_general_ts(long long* out) { return (int)cudaMemcpyFromSymbol(out, gp::g_gen_ts, sizeof(long long) * 32); }
+#endif
 
 static int gp_check_args(const clipgp_gp_args* a, const char* who) {
     CLIPGP_REQUIRE(a != nullptr, "%s: args is NULL", who);

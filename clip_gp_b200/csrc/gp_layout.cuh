@@ -29,8 +29,11 @@ __host__ __device__ inline Dims make_dims(int T, int n, int d) {
 struct FwdLayout {
     size_t Ld, Ad, invd;                                   // double
     size_t Sig, R, AfBm, Lq, mu, mvec, invls, invdR, pool; // float
+    size_t line;                                           // exchange lines of the whole-CTA factorisations (gp_block.cuh)
     size_t total;
 };
+
+constexpr size_t kLineBytes = (36 + 8 * 68 + 4 * 64) * 8;     // Blk4<65, 64>::kCholScratch doubles (>= the 2 * 4 * 68 of the back substitution)
 
 __host__ __device__ inline FwdLayout make_fwd_layout(const Dims& D) {
     FwdLayout L;
@@ -48,6 +51,7 @@ __host__ __device__ inline FwdLayout make_fwd_layout(const Dims& D) {
     L.invdR = o; o = align16(o + 4 * (size_t)D.T);
     // pool: chunk tiles during the Gram phase, then the sample chunk buffers f [SCH][ldt] and eps [T][SCH]
     L.pool = o;  o = align16(o + 4 * maxsz(D.tiles, (size_t)SCH * D.ldt + (size_t)D.T * SCH));
+    L.line = o;  o = align16(o + kLineBytes);
     L.total = o;
     return L;
 }
@@ -60,7 +64,7 @@ __host__ __device__ inline FwdLayout make_fwd_layout(const Dims& D) {
 //   B5 (kernel adjoint)                      : dKzx | raw | tiles        (dKzz stays where B4 left it)
 struct BwdLayout {
     size_t Ld, invd, dAd;                                   // double
-    size_t Af, dSig, mvec, dmu, invls, invdR, dls, dzl, rs, cs, pool;
+    size_t Af, dSig, mvec, dmu, invls, invdR, dls, dzl, rs, cs, line, pool;
     size_t p_R, p_scrF, p_df, p_eps;                        // B1 (offsets from start of smem)
     size_t p_Lq, p_Bm, p_dBm, p_dAf;                        // B3
     size_t p_scrD, p_dLd, p_dKzz;                           // B4
@@ -84,6 +88,7 @@ __host__ __device__ inline BwdLayout make_bwd_layout(const Dims& D) {
     L.dzl = o;   o = align16(o + 4 * (size_t)(D.d > 0 ? D.d : 1));
     L.rs = o;    o = align16(o + 4 * (size_t)(D.n + 3));
     L.cs = o;    o = align16(o + 4 * (size_t)(D.n + 3));
+    L.line = o;  o = align16(o + kLineBytes);
     L.pool = o;
     size_t p = o;
     L.p_R = p;     p = align16(p + 4 * D.f_tt);
