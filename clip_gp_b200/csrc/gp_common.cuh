@@ -534,7 +534,7 @@ __device__ inline float kernel_adjoint_block(const float* dK, int ld, float* Wm,
 }
 
 // Warp-level sparsemax over T <= 64 values (lane holds elements lane and lane+32).
-// Sort-free: rank by (value desc, index asc);  support_i = k_i z_i > cumsum_i - 1.
+// Sort-free (Michelot's fixed point on the support; same support and threshold as the sorted rule k z_(k) > cumsum_k - 1).
 // Returns w0/w1 and the support size (entmax SparsemaxFunction.forward).
 __device__ __forceinline__ void warp_sparsemax(float f0, float f1, int T, float& w0, float& w1, int& ksz) {
     const int lane = threadIdx.x & 31;
@@ -542,20 +542,19 @@ __device__ __forceinline__ void warp_sparsemax(float f0, float f1, int T, float&
     float mx = fmaxf(v0 ? f0 : -INFINITY, v1 ? f1 : -INFINITY);
     mx = warp_max(mx);
     const float z0 = f0 - mx, z1 = f1 - mx;
-    int k0 = 0, k1 = 0;
-    float c0 = 0.f, c1 = 0.f;
-    for (int j = 0; j < T; ++j) {
-        const float zj = __shfl_sync(0xffffffffu, (j < 32) ? z0 : z1, j & 31);
-        const bool b0 = (zj > z0) || (zj == z0 && j <= lane);
-        const bool b1 = (zj > z1) || (zj == z1 && j <= lane + 32);
-        if (b0) { ++k0; c0 += zj; }
-        if (b1) { ++k1; c1 += zj; }
+    // support by Michelot's fixed point: tau <- (sum_S z - 1) / |S|, S <- {z > tau}, until S stops shrinking.  It ends at the support of
+    // the sort-based rule (k z_(k) > cumsum_k - 1) in a handful of warp reductions instead of a T-step rank loop.
+    bool s0 = v0, s1 = v1;
+    int cnt = T;
+    float tau;
+    for (;;) {
+        const float ssum = warp_sum((s0 ? z0 : 0.f) + (s1 ? z1 : 0.f));
+        tau = (ssum - 1.f) / (float)cnt;
+        const bool n0 = s0 && z0 > tau, n1 = s1 && z1 > tau;
+        const int c = __popc(__ballot_sync(0xffffffffu, n0)) + __popc(__ballot_sync(0xffffffffu, n1));
+        if (c == cnt) break;
+        s0 = n0; s1 = n1; cnt = c;
     }
-    const bool s0 = v0 && ((float)k0 * z0 > c0 - 1.f);
-    const bool s1 = v1 && ((float)k1 * z1 > c1 - 1.f);
-    const int cnt = __popc(__ballot_sync(0xffffffffu, s0)) + __popc(__ballot_sync(0xffffffffu, s1));
-    const float ssum = warp_sum((s0 ? z0 : 0.f) + (s1 ? z1 : 0.f));
-    const float tau = (ssum - 1.f) / (float)cnt;
     w0 = v0 ? fmaxf(z0 - tau, 0.f) : 0.f;
     w1 = v1 ? fmaxf(z1 - tau, 0.f) : 0.f;
     ksz = cnt;

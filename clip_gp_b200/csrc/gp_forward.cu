@@ -91,7 +91,14 @@ __global__ void __launch_bounds__(kThreadsMax) gp_forward_kernel(const clipgp_gp
         return;
     }
     GEN_TS(1);
-    gram_block<float>(K0, ldn, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB);
+    {   // wide CTAs (n > 33): two lanes per 4 x 4 tile, each takes half of every chunk's feature columns (153 tiles -> 306 busy threads).
+        // Aliased inputs only: with three separate blocks K_ZZ, K_ZX, K_XX must come out of the SAME accumulation order -- X repeats
+        // rows of Z, Sigma = K_XX - K_XZ K_ZZ^-1 K_ZX is of the order of the jitter (1e-4), and a 1e-7 inconsistency between the
+        // blocks is a 1e-3 error there (seen as 5e-3 on d z_last when only K_ZZ took the split order).
+        const int tsym = pad4(n) >> 2;
+        if (alias && (int)blockDim.x >= tsym * (tsym + 1)) gram_block<float, 1, 2>(K0, ldn, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB);
+        else gram_block<float>(K0, ldn, nullptr, 0, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileB);
+    }
     GEN_TS(2);
     if (!alias) {
         gram_block<double>(Ad, ldt, nullptr, 0, Zc, n, Xc, T, d, kt, amp, invls, tileA, tileB);

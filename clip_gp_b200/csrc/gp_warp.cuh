@@ -210,21 +210,22 @@ __device__ __forceinline__ void trsm_lowerT_cols(const T* __restrict__ L, const 
     __syncwarp();
 }
 
-// Sort-free sparsemax over the T <= 32 lanes (rank by value desc, index asc; entmax SparsemaxFunction.forward).
+// Sort-free sparsemax over the T <= 32 lanes (entmax SparsemaxFunction.forward: same support and threshold as the sorted rule).
 __device__ __forceinline__ float sparsemax_lanes(float f, int T) {
     const int lane = lane_id();
     const bool valid = lane < T;
     const float fm = warp_max(valid ? f : -INFINITY);
     const float z = f - fm;
-    int kk = 0; float cs = 0.f;
-    for (int j = 0; j < T; ++j) {
-        const float zj = __shfl_sync(FULL, z, j);
-        const bool before = (zj > z) || (zj == z && j <= lane);
-        if (before) { ++kk; cs += zj; }
+    bool sup = valid;
+    int cnt = T;
+    float tau;
+    for (;;) {      // Michelot's fixed point: tau <- (sum_S z - 1) / |S|, S <- {z > tau}; ends at the support of the sorted rule
+        tau = (warp_sum(sup ? z : 0.f) - 1.f) / (float)cnt;
+        const bool nsup = sup && z > tau;
+        const int c = __popc(__ballot_sync(FULL, nsup));
+        if (c == cnt) break;
+        sup = nsup; cnt = c;
     }
-    const bool sup = valid && ((float)kk * z > cs - 1.f);
-    const int cnt = __popc(__ballot_sync(FULL, sup));
-    const float tau = (warp_sum(sup ? z : 0.f) - 1.f) / (float)cnt;
     return valid ? fmaxf(z - tau, 0.f) : 0.f;
 }
 

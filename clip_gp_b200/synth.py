@@ -44,6 +44,10 @@ CONFIGS: Dict[str, WorkloadShape] = {
     # the headline per-class shape (T=32, n=33) and its neighbour (n=32) on a few classes
     "t32": WorkloadShape("t32", C=19, T=32, D=128, d=64, S=5, shots=4, B=32, N_test=500, kernel="rbf"),
     "t31": WorkloadShape("t31", C=7, T=31, D=128, d=48, S=3, shots=4, B=32, N_test=500, kernel="rbf"),
+    # n > 33: the general block kernels with wide CTAs (SUN397-like template counts; t40: partial 4 x 4 tiles); d ~ 2.5 n as in cfg5, so
+    # that K_ZZ is not rank deficient beyond the class-mean row (with d < n the fp32 noise of the REFERENCE arithmetic exceeds the gate)
+    "t64": WorkloadShape("t64", C=5, T=64, D=256, d=160, S=4, shots=4, B=32, N_test=500, kernel="rbf"),
+    "t40": WorkloadShape("t40", C=6, T=40, D=192, d=100, S=3, shots=4, B=32, N_test=500, kernel="rbf"),
 }
 
 

@@ -31,7 +31,7 @@ def run_kernel(st, eps, kernel, alias_check=True, need_grad=False, X=None):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("name", ["tiny", "small", "cfg1", "t32", "t31"])
+@pytest.mark.parametrize("name", ["tiny", "small", "cfg1", "t32", "t31", "t40", "t64"])
 def test_forward_matches_oracle(kernel, name):
     wl, st = make_state(name, kernel)
     shp = wl["shape"]
@@ -80,7 +80,7 @@ def test_selfgolden_fixture(golden_dir, kernel):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("name", ["tiny", "small", "t32", "t31"])
+@pytest.mark.parametrize("name", ["tiny", "small", "t32", "t31", "t40", "t64"])
 @pytest.mark.parametrize("alias", [True, False])
 def test_adjoint_matches_oracle_autograd(kernel, name, alias):
     wl, st = make_state(name, kernel)
