@@ -56,10 +56,13 @@ def parse():
     return ap.parse_args()
 
 
+TRAFFIC_JSON = "r2_ncu_traffic.json"
+
+
 def ncu_traffic(kernel_base):
     """DRAM bytes per launch (read + write) of the kernels behind one C-ABI call, from the committed `ncu --set full` capture
-    (profiles/r1_ncu_traffic.json; bench.py itself never runs under a profiler)."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    (profiles/r2_ncu_traffic.json; bench.py itself never runs under a profiler)."""
+    path = os.path.join(ROOT, "profiles", TRAFFIC_JSON)
     try:
         return json.load(open(path)).get(kernel_base, {}).get("dram_bytes")
     except Exception:
@@ -570,16 +573,16 @@ def run_ours(args):
         if ab is not None:
             ach = ab / dur / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": ncu_traffic(base), "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, DRAM read + write per launch)",
+                    "traffic": ncu_traffic(base), "traffic_source": "profiles/" + TRAFFIC_JSON + " (ncu --set full, DRAM read + write per launch)",
                     "algorithmic_bytes": ab, "avg_launch_us": dur * 1e6, "share_of_step": ktimes[dom]["ms"] / sum(v["ms"] for v in ktimes.values()),
                     "peak_source": pk["source"]}
             try:        # what actually limits the kernel (committed ncu capture): issue slots and one class's dependent chain, not bytes
-                prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json"))).get(base, {})
+                prof = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_JSON))).get(base, {})
                 if "issue_active_pct" in prof:
                     roof["limiter"] = {"issue_slots_active_pct": prof["issue_active_pct"], "warps_active_pct": prof["warps_active_pct"],
                                        "warp_instructions_M": prof["inst_executed_M"],
                                        "note": "per-class dependent chain (Cholesky factorisations / adjoints, triangular sweeps) at 7 classes per SM; "
-                                               "per-phase cycles in profiles/r1_gp_phase_cycles.txt"}
+                                               "per-phase cycles in profiles/r2_gp_hotspots.txt / r1_gp_phase_cycles.txt"}
             except Exception:
                 pass
         else:
