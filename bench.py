@@ -49,6 +49,8 @@ def parse():
                          "reference's own GPU arithmetic) | tcgen05 split-bf16 (fp32-grade) | tcgen05 bf16")
     ap.add_argument("--no-fullbatch", action="store_true", help="skip the B = N_train full-batch (tensor-bound) leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the other-precision timings of the step")
+    ap.add_argument("--no-peer-update", action="store_true",
+                    help="N > 1: gradient ncclAllReduce + AdamW instead of the fused NVLink peer-memory optimiser step (csrc/peer.cu)")
     ap.add_argument("--no-graph-collectives", action="store_true",
                     help="N > 1: launch the step eagerly instead of capturing it (NCCL all-reduces included) in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -279,8 +281,10 @@ def run_ours(args):
 
     def engine_config(**kw):
         base = dict(S_train=S, S_eval=S, batch_size=shp.B, shots=shp.shots, seed=1234, rank=rank, world=world, precision=args.precision,
-                    graph_collectives=not args.no_graph_collectives, shard="batch")
+                    graph_collectives=not args.no_graph_collectives, shard="batch", peer_update=world > 1 and not args.no_peer_update)
         base.update(kw)
+        if base["shard"] != "batch" or base["world"] == 1:
+            base["peer_update"] = False
         return EngineConfig(**base)
 
     # N > 1: data parallel over the batch (every rank its own B-image batch, all S samples; ONE gradient all-reduce per step)
@@ -385,7 +389,7 @@ def run_ours(args):
             ev = GPAdapterEngine(gpw, engine_config(precision=prec))
             msv = time_steps(ev, 10, 3)
             train_variants[prec] = {"ms_per_step": msv / 10, "steps_per_s": world * 10 / (msv * 1e-3)}
-            ev._graph = None
+            ev.close_peer()
             del ev
 
     # ---------------- N > 1: the north star's S-sharded form of ONE 128-image batch (strong scaling of a latency-bound step)
@@ -397,7 +401,7 @@ def run_ours(args):
                                 "split": [cdist_sample_split(S, r, world)[1] for r in range(world)],
                                 "note": "MC samples of one batch sharded over the ranks (same Philox stream), ONE all-reduce of the flat gradient "
                                         "buffer; the per-class GP chain is replicated on every rank, so this form cannot beat one GPU"}
-        es._graph = None
+        es.close_peer()
         del es
 
     # ---------------- full-batch leg (B = N_train = C * shots): the tensor-bound form of the same step
@@ -427,7 +431,7 @@ def run_ours(args):
                                         "per_gemm": {k: {"ms": round(v["ms"], 4), "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} for k, v in big}}
                 entry["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in kt.items()}
             fullbatch[prec] = entry
-            ef._graph = None
+            ef.close_peer()
             del ef
         torch.cuda.empty_cache()
 
@@ -545,11 +549,12 @@ def run_ours(args):
 
     def shutdown():
         # captured graphs hold NCCL work: release them before the process group goes away
-        eng._graph = None
-        eng_train._graph = None
         eval_replay.release()
         eval_pass.release()
         tf32_replay.release()
+        eng.close_peer()
+        eng_train.check_peer_status()
+        eng_train.close_peer()
         import gc
         gc.collect()
         torch.cuda.synchronize(dev)
@@ -607,8 +612,10 @@ def run_ours(args):
                                  "bf16x3": "tcgen05 GEMMs on split-bf16 operands (fp32-grade products; the reference's GPU path is TF32), fp32 everywhere else, fp64 K_ZZ Cholesky",
                                  "bf16": "tcgen05 bf16 GEMMs, fp32 everywhere else, fp64 K_ZZ Cholesky"}[args.precision],
                    "cuda_graph": eng_train._graph is not None, "two_stream_overlap": bool(eng_train.cfg.overlap),
-                   "multi_gpu": (f"data parallel over the batch: {world} ranks x {shp.B} images, all {S} MC samples on every rank (same Philox "
-                                 "draw), ONE all-reduce of the flat gradient buffer + loss (7.6 MB); step captured in a CUDA graph incl. NCCL")
+                   "multi_gpu": (f"data parallel over the batch: {world} ranks x {shp.B} images, all {S} MC samples on every rank (same Philox draw); "
+                                 + ("gradient reduce-scatter + AdamW on the owned 1/world slice + parameter all-gather in ONE kernel over NVLink peer "
+                                    "memory (CUDA IPC pointers, csrc/peer.cu), inside the step's CUDA graph" if eng_train.peer is not None else
+                                    "ONE ncclAllReduce of the flat gradient buffer + loss (7.6 MB) + replicated AdamW; step captured in a CUDA graph incl. NCCL"))
                    if world > 1 else None,
                    "loss_last": loss_last},
         "e2e": {"value": world * args.steps / e2e_pipe_s, "unit": UNIT, "h2d_bytes_per_step": shp.B * shp.D * 4 + shp.B * 8, "d2h_bytes_per_step": 4,

@@ -54,8 +54,31 @@ class GpBwdArgs(C.Structure):
     ]
 
 
+PEER_MAX = 8
+
+
+class PeerArgs(C.Structure):
+    """Mirror of ``clipgp_peer_args`` (include/clipgp.h)."""
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32),
+        ("g", C.c_void_p * PEER_MAX), ("p", C.c_void_p * PEER_MAX), ("flags", C.c_void_p * PEER_MAX),
+        ("m", C.c_void_p), ("v", C.c_void_p),
+        ("n", c_i64), ("n_group0", c_i64),
+        ("lr_dev", C.c_void_p),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("step", C.c_void_p), ("local", C.c_void_p), ("loss_out", C.c_void_p), ("status", C.c_void_p),
+        ("timeout_ns", C.c_uint64),
+    ]
+
+
 _SIGNATURES = {
     # name: (restype, argtypes)
+    "clipgp_peer_alloc": (C.c_int, [c_i64, C.POINTER(C.c_void_p)]),
+    "clipgp_peer_free": (C.c_int, [C.c_void_p]),
+    "clipgp_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "clipgp_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "clipgp_ipc_close": (C.c_int, [C.c_void_p]),
+    "clipgp_peer_adamw": (C.c_int, [C.POINTER(PeerArgs), C.c_void_p]),
     "clipgp_last_error": (C.c_char_p, []),
     "clipgp_version": (C.c_int, []),
     "clipgp_launch_count": (c_i64, []),

@@ -102,7 +102,9 @@ extern "C" int clipgp_gemm_f32(const float* A, int64_t sam, int64_t sak, const f
     // split-K when the output grid cannot fill the SMs (skinny adjoint GEMMs: K = S*C or B is the long axis)
     int splits = 1;
     const int64_t tiles = (int64_t)grid.x * grid.y;
-    if (tiles < num_sms() && K >= 8 * GBK) {
+    const bool deterministic = (accumulate & 2) != 0;       // bit 1: no split-K (atomic accumulation order varies from run to run)
+    accumulate &= 1;
+    if (!deterministic && tiles < num_sms() && K >= 8 * GBK) {
         splits = (int)((2 * num_sms() + tiles - 1) / tiles);
         const int max_splits = (int)(K / (4 * GBK));
         if (splits > max_splits) splits = max_splits;

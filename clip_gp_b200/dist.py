@@ -59,3 +59,71 @@ def global_calibration(hist: torch.Tensor, conf: torch.Tensor, correct: torch.Te
     allreduce_sum_(h)
     counts = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
     return h, gather_variable(conf, counts), gather_variable(correct, counts)
+
+
+# ---------------------------------------------------------------------------------------------------- NVLink peer memory
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier: lets torch view memory the library allocated with cudaMalloc."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerBlock:
+    """One cudaMalloc block per rank, mapped into every other rank's address space with CUDA IPC (one process per GPU on ONE node;
+    torch.distributed carries the 64-byte handles once).  `views(q)` are rank q's regions as seen from this process: raw device
+    pointers that kernels on THIS GPU may load / store through NVLink (csrc/peer.cu).  `local(name)` is a torch view of this rank's
+    own region, so the rest of the engine (kernel argument blocks, optimiser state) uses it like any other tensor.
+
+    layout: {name: (offset_bytes, nbytes)}; identical on every rank."""
+
+    def __init__(self, layout, device: torch.device, rank: int, world: int, group=None):
+        from . import _lib
+        import ctypes as C
+        if world > _lib.PEER_MAX:
+            raise ValueError(f"PeerBlock: world {world} > {_lib.PEER_MAX}")
+        self.lib, self.rank, self.world, self.layout, self.device = _lib.load(), rank, world, dict(layout), device
+        self.nbytes = max(o + b for o, b in layout.values())
+        base = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.clipgp_peer_alloc(self.nbytes, C.byref(base)), "peer_alloc")
+            handle = C.create_string_buffer(64)
+            _lib.check(self.lib.clipgp_ipc_export(base, handle), "ipc_export")
+        self.base = int(base.value)
+        self._carrier = _CudaArray(self.base, self.nbytes)
+        self._bytes = torch.as_tensor(self._carrier, device=device)
+        handles = [None] * world
+        torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.bases = [0] * world
+        self._mapped = []
+        with torch.cuda.device(device):
+            for q in range(world):
+                if q == rank:
+                    self.bases[q] = self.base
+                    continue
+                ptr = C.c_void_p()
+                _lib.check(self.lib.clipgp_ipc_open(handles[q], C.byref(ptr)), f"ipc_open(rank {q})")
+                self.bases[q] = int(ptr.value)
+                self._mapped.append(int(ptr.value))
+        torch.distributed.barrier(group=group)          # nobody touches a peer's block before everybody has mapped everything
+
+    def local(self, name: str, dtype: torch.dtype) -> torch.Tensor:
+        o, b = self.layout[name]
+        return self._bytes[o:o + b].view(dtype)
+
+    def ptr(self, q: int, name: str) -> int:
+        return self.bases[q] + self.layout[name][0]
+
+    def close(self):
+        """Unmap the peers' blocks and free this rank's (call on every rank, after a barrier: peers may still be reading)."""
+        import ctypes as C
+        if self.lib is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in self._mapped:
+                self.lib.clipgp_ipc_close(C.c_void_p(p))
+            self._mapped = []
+            self._bytes = None
+            self.lib.clipgp_peer_free(C.c_void_p(self.base))
+        self.lib = None

@@ -66,6 +66,9 @@ class EngineConfig:
                                         #   "batch":   data parallel -- every rank takes its own [B, D] batch and all S samples, the global
                                         #              batch is world * B (weak scaling when B is fixed per rank, strong when the caller
                                         #              splits a fixed batch); loss / gradients are means over the global batch
+    peer_update: bool = False           # world > 1, shard = "batch": replace ncclAllReduce(flat gradient) + AdamW by ONE kernel over NVLink peer
+                                        # memory (csrc/peer.cu: gradient reduce-scatter + AdamW on the owned 1/world slice + parameter
+                                        # all-gather through CUDA-IPC peer pointers).  All ranks must live on one node
     shard_eval_classes: bool = True     # world > 1: the eval GP forward runs on this rank's C / world classes only and the [C, D] mean
                                         # prototypes are completed by one 2 MB all-reduce (instead of replicating the per-class chain)
 
@@ -112,8 +115,23 @@ class GPAdapterEngine:
             self.offsets[name] = (off, sz)
             off += sz
         self.n_params = off
-        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(off + 1, dtype=torch.float32, device=dev)     # last slot: the loss (all-reduced with the grads)
+        self.peer = None
+        if cfg.peer_update and cfg.world > 1:
+            if not self.batch_sharded:
+                raise ValueError("EngineConfig.peer_update needs shard='batch'")
+            a16 = lambda x: (x + 255) & ~255
+            lay, o = {}, 0
+            for nm, nb in (("flags", 8 * 2 * _lib.PEER_MAX), ("g", 4 * (off + 1)), ("p", 4 * off)):
+                lay[nm] = (o, nb); o = a16(o + nb)
+            self.peer = dist.PeerBlock(lay, dev, cfg.rank, cfg.world)
+            self.flat_p = self.peer.local("p", torch.float32)
+            self.flat_g = self.peer.local("g", torch.float32)
+            self.peer_local = torch.zeros(2, dtype=torch.int64, device=dev)         # epoch, CTA arrival counter
+            self.peer_status = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.loss_global = torch.zeros(1, dtype=torch.float32, device=dev)
+        else:
+            self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+            self.flat_g = torch.zeros(off + 1, dtype=torch.float32, device=dev)     # last slot: the loss (all-reduced with the grads)
         self.flat_m = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(off, dtype=torch.float32, device=dev)
         W0 = torch.eye(D, device=dev) if visual_proj_weight is None else visual_proj_weight.detach().to(dev).float()
@@ -148,6 +166,14 @@ class GPAdapterEngine:
 
     @property
     def loss(self) -> torch.Tensor:
+        """Loss of the last step (device scalar; the global mean when sharded)."""
+        if self.peer is not None:
+            return self.loss_global
+        return self.flat_g[self.n_params:self.n_params + 1]
+
+    @property
+    def _loss_acc(self) -> torch.Tensor:
+        """Where this rank's kernels accumulate their loss share (slot n of the gradient buffer)."""
         return self.flat_g[self.n_params:self.n_params + 1]
 
     def _ptr(self, buf, name):
@@ -336,8 +362,13 @@ class GPAdapterEngine:
         self._bwd_prototypes()
         if side is not None:
             main.wait_stream(side)
+        if self.peer is not None and not getattr(self, "skip_update", False):
+            self._launch_peer_update()                        # reduce-scatter + AdamW + all-gather over NVLink peer memory, one kernel
+            return
         if cfg.world > 1:
             torch.distributed.all_reduce(self.flat_g)         # ONE fused all-reduce: gradients + loss
+            if self.peer is not None:
+                self.loss_global.copy_(self._loss_acc)
         if not getattr(self, "skip_update", False):
             self._launch_update()
 
@@ -429,18 +460,18 @@ class GPAdapterEngine:
             dlb_ptr = _lib.ptr(self.dlb) if cfg.train_visual_proj else None
             if ((B + 63) // 64) * rpl >= 296:
                 # large batches: one launch, a CTA owns 64 batch rows of one sample (>= two CTAs per SM; second read from L2)
-                ck(lib.clipgp_softmax_ce_bf16_dual(self.logits.data_ptr(), self.in_lab.data_ptr(), B, rpl, Cn, self.loss.data_ptr(), loss_scale,
+                ck(lib.clipgp_softmax_ce_bf16_dual(self.logits.data_ptr(), self.in_lab.data_ptr(), B, rpl, Cn, self._loss_acc.data_ptr(), loss_scale,
                                                    loss_scale, dlb_ptr, self.dlb.stride(0), self.SCp, self.tc_ma, self.dlTb.data_ptr(),
                                                    self.dlTb.stride(0), self.Bp, self.tc_ma, st), "softmax_ce_bf16_dual")
             else:
                 # minibatches: two launches with full-GPU grids (row statistics, then 64 x 64 tiles over the whole [B, S*C] matrix)
                 ck(lib.clipgp_softmax_ce_stats(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, self.sm_stats.data_ptr(),
-                                               self.loss.data_ptr(), loss_scale, st), "softmax_ce_stats")
+                                               self._loss_acc.data_ptr(), loss_scale, st), "softmax_ce_stats")
                 ck(lib.clipgp_softmax_grad_bf16_dual(self.logits.data_ptr(), self.sm_stats.data_ptr(), self.in_lab.data_ptr(), B, rpl, Cn,
                                                      loss_scale, dlb_ptr, self.dlb.stride(0), self.SCp, self.tc_ma, self.dlTb.data_ptr(),
                                                      self.dlTb.stride(0), self.Bp, self.tc_ma, st), "softmax_grad")
         else:
-            ck(lib.clipgp_softmax_ce(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, None, self.loss.data_ptr(),
+            ck(lib.clipgp_softmax_ce(self.logits.data_ptr(), Cn, self.in_lab.data_ptr(), rows, rpl, Cn, None, self._loss_acc.data_ptr(),
                                      loss_scale, self.logits.data_ptr(), Cn, loss_scale, st), "softmax_ce")
 
     def _bwd_features(self):
@@ -476,7 +507,7 @@ class GPAdapterEngine:
             ck(lib.clipgp_gemm_f32(self.dY.data_ptr(), 1, D, self.in_feat.data_ptr(), D, 1, self._ptr(self.flat_g, "W"), D, D, D, B,
                                    1.0, 0, st), "gemm(dW)")
         coef = float(cfg.l2_lambda) / float(cfg.shots) / cfg.world
-        ck(lib.clipgp_l2_identity(W, D, coef, self._ptr(self.flat_g, "W"), self.loss.data_ptr(), st), "l2_identity")
+        ck(lib.clipgp_l2_identity(W, D, coef, self._ptr(self.flat_g, "W"), self._loss_acc.data_ptr(), st), "l2_identity")
         if cfg.world == 1 and not getattr(self, "skip_update", False):
             self._adamw_w()                                   # dW is complete here: update W next to the GP adjoint
 
@@ -505,7 +536,7 @@ class GPAdapterEngine:
         if self.class_sharded:
             torch.distributed.all_reduce(self.dw_all)         # every rank wrote its samples (all classes); rows of other ranks are zero
         ck(lib.clipgp_gp_backward(C.byref(self.gp_args), C.byref(self.gp_bwd_args), st), "gp_backward")
-        ck(lib.clipgp_sum_accumulate(self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight, self.loss.data_ptr(), st),
+        ck(lib.clipgp_sum_accumulate(self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight, self._loss_acc.data_ptr(), st),
            "kl_sum")
 
     def _adamw_w(self):
@@ -515,6 +546,47 @@ class GPAdapterEngine:
         _lib.check(lib.clipgp_adamw_step_lrptr(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
                                                nW, self.lr_dev.data_ptr(), b1, b2, cfg.adam_eps, cfg.weight_decay, self.adam_step.data_ptr(),
                                                st), "adamw(W)")
+
+    def _peer_args(self):
+        a = _lib.PeerArgs()
+        cfg, pb = self.cfg, self.peer
+        a.world, a.rank = cfg.world, cfg.rank
+        for q in range(cfg.world):
+            a.g[q], a.p[q], a.flags[q] = pb.ptr(q, "g"), pb.ptr(q, "p"), pb.ptr(q, "flags")
+        a.m, a.v = self.flat_m.data_ptr(), self.flat_v.data_ptr()
+        a.n = self.n_params
+        a.n_group0 = self.offsets["W"][1] if cfg.train_visual_proj else 0
+        a.lr_dev = self.lr_dev.data_ptr()
+        a.beta1, a.beta2 = cfg.betas
+        a.eps, a.weight_decay = cfg.adam_eps, cfg.weight_decay
+        a.step, a.local = self.adam_step.data_ptr(), self.peer_local.data_ptr()
+        a.loss_out, a.status = self.loss_global.data_ptr(), self.peer_status.data_ptr()
+        a.timeout_ns = int(5e9)
+        return a
+
+    def _launch_peer_update(self):
+        lib, st = self.lib, _lib.stream_ptr(self.dev)
+        if getattr(self, "_peer_args_c", None) is None:
+            self._peer_args_c = self._peer_args()
+        _lib.check(lib.clipgp_peer_adamw(C.byref(self._peer_args_c), st), "peer_adamw")
+        _lib.check(lib.clipgp_step_epilogue(self._ptr(self.flat_p, "z_last"), self.Z.data_ptr(), self.C, self.n, self.d, self.adam_step.data_ptr(),
+                                            self.rng_state.data_ptr() + 8, 1, st), "step_epilogue")
+
+    def check_peer_status(self):
+        """Raise if a peer flag timed out inside clipgp_peer_adamw (host read: call outside the timed region)."""
+        if self.peer is not None and int(self.peer_status.item()) != 0:
+            raise RuntimeError(f"clipgp_peer_adamw: peer flag timeout (status {int(self.peer_status.item())}) on rank {self.cfg.rank}")
+
+    def close_peer(self):
+        """Drop the captured graph and unmap / free the NVLink peer block (every rank, before destroy_process_group)."""
+        self._graph = None
+        if self.peer is not None:
+            torch.cuda.synchronize(self.dev)
+            self.check_peer_status()
+            torch.distributed.barrier()
+            fp, fg = self.flat_p.clone(), self.flat_g.clone()
+            self.peer.close()
+            self.flat_p, self.flat_g, self.peer = fp, fg, None
 
     def _launch_update(self):
         lib, cfg, st = self.lib, self.cfg, _lib.stream_ptr(self.dev)

@@ -300,7 +300,8 @@ class GaussianProcessTemplateWeighter(nn.Module):
         N, D = Xc.shape
         Xc = Xc.float().contiguous()
         G = torch.empty(D, D, dtype=torch.float32, device=Xc.device)
-        ops._gemm(Xc, 1, D, Xc, D, 1, G, D, D, N, 1.0)                     # G[i,j] = sum_r Xc[r,i] Xc[r,j]
+        ops._gemm(Xc, 1, D, Xc, D, 1, G, D, D, N, 1.0, accumulate=2)       # G[i,j] = sum_r Xc[r,i] Xc[r,j]; flag 2: no split-K, so
+        #                                                                    two constructions give bit-identical axes (set-up: 16 CTAs suffice)
         G = 0.5 * (G + G.t())
         evals, evecs = torch.linalg.eigh(G.double())                       # ascending
         return evecs[:, -d:].flip(-1).float().contiguous()                 # [D, d], largest variance first

@@ -216,7 +216,8 @@ int clipgp_proto_backward(const float* dP, int64_t dP_stride_s, float dP_scale, 
  * (The tensor-core path with fused epilogues is clipgp_tc_*.)
  * ================================================================================================ */
 
-/* C[M,N] = alpha * op(A) op(B) (+ C if accumulate), fp32 FFMA.  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn];
+/* C[M,N] = alpha * op(A) op(B) (+ C if accumulate & 1), fp32 FFMA.  accumulate & 2: never split K (split-K adds partial sums with
+ * atomics, so their order -- and the last bits of C -- vary from run to run; set-up code that must be reproducible sets this bit).  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn];
  * each operand needs one unit stride.  Covers f W^T (adapter.py:239), f_hat P_hat^T (:248,:426), f keys^T
  * (tip_adapter.py:250) and their adjoints dlogits^T f_hat, dlogits P_hat. */
 int clipgp_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
@@ -382,6 +383,48 @@ int clipgp_row_sqnorm(const float* X, int64_t N, int64_t d, float* sq, void* str
 int clipgp_pairdist_radix_hist(const float* X, const float* sqnorm, int64_t N, int64_t d, int prefix_shift, uint32_t prefix,
                                int use_prefix, int shift, int nbins, unsigned long long* hist, unsigned long long* positives,
                                void* stream);
+
+/* ================================================================================================
+ * Multi-GPU optimiser step over NVLink peer memory (one process per GPU; csrc/peer.cu) — replaces, for the data-parallel
+ * GP-Adapter step, ncclAllReduce(flat gradient) + optimizer.step() (adapter.py:537-549; AdamW as utils/optimization.py:57-216):
+ * gradient reduce-scatter + AdamW on the owned 1/world slice + parameter all-gather in ONE kernel, through peer pointers.
+ *
+ * Set-up: every rank allocates one block with clipgp_peer_alloc (cudaMalloc, zeroed), exports it (64-byte CUDA IPC handle, carried
+ * to the peers by any host channel, e.g. torch.distributed.all_gather_object) and opens the peers' blocks; g / p / flags below point
+ * into those blocks (index = rank; the entry of the calling rank is its own block).
+ *   g[q]     : rank q's flat gradient buffer, n + 1 floats (slot n: its loss share), 16-byte aligned
+ *   p[q]     : rank q's flat parameter buffer, n floats, 16-byte aligned (every rank ends the call with identical parameters)
+ *   flags[q] : rank q's 2 * CLIPGP_PEER_MAX uint64 flags, zero before the first call
+ *   m, v     : LOCAL Adam moments, n floats (only the owned slice is read / written)
+ *   n_group0 : elements [0, n_group0) use lr_dev[0], the rest lr_dev[1] (visual-projection / gp_weighter groups, adapter.py:298-309)
+ *   step     : device int64, the 1-based Adam step (read, not advanced);  local: device uint64[2], zero before the first call
+ *   loss_out : optional device float: sum over ranks of slot n
+ *   status   : device int, set to 1 / 2 if a peer's "gradients ready" / "parameters written" flag did not arrive within timeout_ns
+ * Every rank must make the same sequence of calls.  The call is stream-ordered and can be captured in a CUDA graph.
+ * ================================================================================================ */
+#define CLIPGP_PEER_MAX 8
+typedef struct clipgp_peer_args {
+    int32_t world, rank;
+    const float* g[CLIPGP_PEER_MAX];
+    float* p[CLIPGP_PEER_MAX];
+    unsigned long long* flags[CLIPGP_PEER_MAX];
+    float* m;
+    float* v;
+    int64_t n, n_group0;
+    const float* lr_dev;
+    float beta1, beta2, eps, weight_decay;
+    const int64_t* step;
+    unsigned long long* local;
+    float* loss_out;
+    int32_t* status;
+    unsigned long long timeout_ns;
+} clipgp_peer_args;
+int clipgp_peer_alloc(int64_t bytes, void** out);
+int clipgp_peer_free(void* block);
+int clipgp_ipc_export(const void* block, unsigned char* handle64);
+int clipgp_ipc_open(const unsigned char* handle64, void** out);
+int clipgp_ipc_close(void* mapped);
+int clipgp_peer_adamw(const clipgp_peer_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,10 @@ def rel(a, b):
 
 f, y = wl["f_train"].to(dev), wl["y_train"].to(dev)
 ok = True
+# fp32-grade GEMM modes reproduce the single-GPU step to rounding; TF32 / bf16 products depend on how a contraction is split over the
+# ranks (10-bit / 8-bit mantissa operands), so there the comparison is at the mode's own tolerance
+exact = precision in ("fp32", "bf16x3")
+TOL_G, TOL_FRAC = (1e-4, 0.01) if exact else (2e-3, 0.25)
 for shard_classes in (True, False):
     multi, single = make(world, rank, shard_classes=shard_classes), make(1, 0)
     # one step without the update: gradients and loss
@@ -51,7 +55,7 @@ for shard_classes in (True, False):
     # parameters by up to one learning-rate step, so compare the bulk, and bound the outliers by the step budget
     dp = (multi.flat_p - single.flat_p).abs()
     e_p = float((dp > 1e-5).float().mean())
-    good = abs(lm - ls_) <= 1e-5 * abs(ls_) and e_g < 1e-4 and e_p < 0.01 and float(dp.max()) <= 3 * 0.0101
+    good = abs(lm - ls_) <= (1e-5 if exact else 1e-4) * abs(ls_) and e_g < TOL_G and e_p < TOL_FRAC and float(dp.max()) <= 3 * 0.0101
     ok &= good
     if rank == 0:
         print(f"shard_classes={shard_classes}: loss {lm:.6f} vs {ls_:.6f}, grad rel err {e_g:.2e}, params after 3 steps: {100 * e_p:.3f} % of entries differ by > 1e-5 (max {float(dp.max()):.1e}) -> {'OK' if good else 'MISMATCH'}")
@@ -65,7 +69,7 @@ lo = rank * shp.B
 lm = float(multi.train_step(f[lo:lo + shp.B], y[lo:lo + shp.B], use_graph=False))
 ls_ = float(single.train_step(f[:world * shp.B], y[:world * shp.B], use_graph=False))
 e_g = rel(multi.flat_g[:-1], single.flat_g[:-1])
-good = abs(lm - ls_) <= 1e-5 * abs(ls_) and e_g < 2e-4
+good = abs(lm - ls_) <= (1e-5 if exact else 1e-4) * abs(ls_) and e_g < 2 * TOL_G
 ok &= good
 if rank == 0:
     print(f"shard=batch: loss {lm:.6f} vs {ls_:.6f} (single GPU, batch {world * shp.B}), grad rel err {e_g:.2e} -> {'OK' if good else 'MISMATCH'}")
@@ -74,6 +78,40 @@ for it in range(3):          # graph-captured DP steps (NCCL inside the graph) r
     multi.train_step(f[lo:lo + shp.B], y[lo:lo + shp.B])
 assert torch.isfinite(multi.flat_p).all()
 multi._graph = None
+# the same data-parallel steps with the fused NVLink peer-memory optimiser step (csrc/peer.cu) instead of ncclAllReduce + AdamW
+nccl_e, peer_e = make(world, rank, shard="batch", graph_collectives=True), make(world, rank, shard="batch", peer_update=True, graph_collectives=True)
+for it in range(4):
+    b0 = ((it * world + rank) * shp.B) % (f.shape[0] - shp.B)
+    l_n = nccl_e.train_step(f[b0:b0 + shp.B], y[b0:b0 + shp.B], use_graph=it >= 2)
+    l_p = peer_e.train_step(f[b0:b0 + shp.B], y[b0:b0 + shp.B], use_graph=it >= 2)
+peer_e.check_peer_status()
+dp = (peer_e.flat_p - nccl_e.flat_p).abs()
+e_p = float((dp > 1e-5).float().mean())
+pall = [torch.empty_like(peer_e.flat_p) for _ in range(world)]
+td.all_gather(pall, peer_e.flat_p.contiguous())
+identical = all(torch.equal(pall[0], q) for q in pall)
+good = e_p < TOL_FRAC and float(dp.max()) <= 4 * 0.0101 and abs(float(l_p) - float(l_n)) <= (1e-4 if exact else 1e-3) * abs(float(l_n)) and identical
+ok &= good
+def _time(e, reps=200):
+    b0 = rank * shp.B
+    for _ in range(10):
+        e.train_step(f[b0:b0 + shp.B], y[b0:b0 + shp.B])
+    torch.cuda.synchronize(); td.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        e.train_step(f[b0:b0 + shp.B], y[b0:b0 + shp.B])
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev); td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t)
+t_n, t_p = _time(nccl_e), _time(peer_e)
+peer_e.check_peer_status()
+if rank == 0:
+    print(f"peer_update (reduce-scatter + AdamW + all-gather over NVLink peer memory, one kernel): loss {float(l_p):.6f} vs {float(l_n):.6f} (NCCL path), "
+          f"params after 4 steps: {100 * e_p:.3f} % differ by > 1e-5 (max {float(dp.max()):.1e}), identical on all ranks: {identical} -> {'OK' if good else 'MISMATCH'}")
+    print(f"    graph-replayed DP step, no L2 flush: NCCL all-reduce + AdamW {t_n * 1e3:.1f} us, peer kernel {t_p * 1e3:.1f} us")
+nccl_e._graph = None
+peer_e.close_peer()
 # evaluation: image shards + counter all-reduce == single GPU, bit for bit
 eng = make(world, rank); ref = make(1, 0)
 ft, yt = wl["f_test"].to(dev), wl["y_test"].to(dev)
