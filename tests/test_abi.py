@@ -59,6 +59,22 @@ def test_struct_layout_matches_header_field_order():
     assert fields == [f[0] for f in _lib.GpArgs._fields_]
 
 
+def test_peer_args_layout_matches_a_c_compiler(tmp_path):
+    """clipgp_peer_args (the fused NVLink optimiser step): ctypes mirror == what gcc lays out from the header."""
+    import ctypes, subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "clipgp.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(clipgp_peer_args), offsetof(clipgp_peer_args, g), offsetof(clipgp_peer_args, flags), offsetof(clipgp_peer_args, m), '
+                   'offsetof(clipgp_peer_args, lr_dev), offsetof(clipgp_peer_args, step), offsetof(clipgp_peer_args, timeout_ns)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    P = _lib.PeerArgs
+    assert got == [ctypes.sizeof(P), P.g.offset, P.flags.offset, P.m.offset, P.lr_dev.offset, P.step.offset, P.timeout_ns.offset]
+    lib = _lib.load()
+    assert lib.clipgp_peer_adamw(None, None) != 0 and b"NULL" in lib.clipgp_last_error()
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
 def test_no_cpu_fallback():
     from clip_gp_b200 import metrics
