@@ -598,6 +598,28 @@ __global__ void increment2_kernel(int64_t* a, int64_t* b, int64_t by) { if (thre
 
 __global__ void increment_kernel(int64_t* p, int64_t by) { if (threadIdx.x == 0 && blockIdx.x == 0) *p += by; }
 
+
+// out[k][r] = x[r][k] for an fp32 [R, K] matrix (row pitches ldx / out_ld): 32 x 32 tiles through shared memory, both sides coalesced.
+// Used to hand the SMALL operand of a long-K TF32 GEMM to the tensor cores K-major: an MN-major B operand (the 256-wide tile) costs
+// the tcgen05 pipeline ~35 % of its rate (tools/micro/tf32_layouts.py), a transposed copy of a [S*C, D] matrix costs microseconds.
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ x, int64_t R, int64_t K, int64_t ldx,
+                                                            float* __restrict__ out, int64_t out_ld) {
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int64_t r = r0 + ty + j, k = k0 + tx;
+        tile[ty + j][tx] = (r < R && k < K) ? x[r * ldx + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int64_t k = k0 + ty + j, r = r0 + tx;
+        if (k < K && r < R) out[k * out_ld + r] = tile[tx][ty + j];
+    }
+}
+
 }  // namespace clipgp
 
 using namespace clipgp;
@@ -843,4 +865,14 @@ extern "C" int clipgp_softmax_ce_bf16_dual(const float* logits, const int64_t* l
                                                                    (__nv_bfloat16*)out, out_ld, seg_stride, mode, (__nv_bfloat16*)outT, outT_ld,
                                                                    segT_stride, modeT, vec);
     return check_launch("softmax_ce_fused_kernel");
+}
+
+extern "C" int clipgp_transpose_f32(const float* x, int64_t R, int64_t K, int64_t ldx, float* out, int64_t out_ld, void* stream) {
+    CLIPGP_REQUIRE(R >= 0 && K >= 0 && ldx >= K && out_ld >= R, "transpose_f32: bad shape / pitches");
+    if (R == 0 || K == 0) return CLIPGP_OK;
+    CLIPGP_REQUIRE(x && out, "transpose_f32: NULL pointer");
+    const int64_t gy = (R + 31) / 32, gx = (K + 31) / 32;
+    CLIPGP_REQUIRE(gy <= 65535, "transpose_f32: too many rows for one launch");
+    transpose_f32_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(x, R, K, ldx, out, out_ld);
+    return check_launch("transpose_f32_kernel");
 }

@@ -214,6 +214,13 @@ class GPAdapterEngine:
             SCt = (S if self.cfg.loss_mode == "per_sample" else 1) * Cn
             if D % 4 or SCt % 4:
                 raise ValueError(f"precision='tf32' needs D ({D}) and S*C ({SCt}) to be multiples of 4 (16-byte TMA row pitch); use 'bf16x3'")
+            # large batches: the adjoint GEMMs take their SMALL operand (P_hat, f_hat) K-major from a transposed copy -- as the 256-wide
+            # B tile an MN-major operand costs the MMA pipeline ~35 % (d f_hat 504 -> 331 us, d P_hat 520 -> 307 us at B = 16 000), the
+            # copies ~10 us each; the big operand (dlogits, 640 MB) is still read in place.  Minibatches are latency bound: in place
+            self.tf32_kmajor_b = bool(B >= 1024 and B % 4 == 0)
+            if self.tf32_kmajor_b:
+                self.PT32 = torch.empty(D, SCt, **f32)
+                self.fhT32 = torch.empty(D, B, **f32)
         elif self.cfg.precision != "fp32":
             self._alloc_tc()
         a = GpArgs()
@@ -487,7 +494,11 @@ class GPAdapterEngine:
         tf = cfg.precision == "tf32"
         if tf:
             # d f_hat = alpha dlogits P_hat: A = dlogits [B, SC] (K-major), B operand = P_hat^T, i.e. P_hat [SC, D] read MN-major in place
-            self._tf32(self.logits.data_ptr(), False, B, Bmat.data_ptr(), True, D, SC, alpha, self.df_hat.data_ptr(), D)
+            if self.tf32_kmajor_b:
+                ck(lib.clipgp_transpose_f32(Bmat.data_ptr(), SC, D, D, self.PT32.data_ptr(), SC, st), "transpose(P_hat)")
+                self._tf32(self.logits.data_ptr(), False, B, self.PT32.data_ptr(), False, D, SC, alpha, self.df_hat.data_ptr(), D)
+            else:
+                self._tf32(self.logits.data_ptr(), False, B, Bmat.data_ptr(), True, D, SC, alpha, self.df_hat.data_ptr(), D)
         elif tcm:
             # dlogits [B, SC] and P_hat^T [D, SC] (K = samples x classes; split over K inside the GEMM)
             self._cast2(Bmat.data_ptr(), SC, D, D, None, 0, 0, self.PTb, self.SCp, self.tc_mb)
@@ -518,7 +529,11 @@ class GPAdapterEngine:
         per_sample, S, SC, alpha = self._dims()
         if cfg.precision == "tf32":
             # d P_hat = alpha dlogits^T f_hat (contraction over the batch): dlogits [B, SC] and f_hat [B, D] read MN-major in place
-            self._tf32(self.logits.data_ptr(), True, SC, self.f_hat.data_ptr(), True, D, B, alpha, self.dP.data_ptr(), D)
+            if self.tf32_kmajor_b:
+                ck(lib.clipgp_transpose_f32(self.f_hat.data_ptr(), B, D, D, self.fhT32.data_ptr(), B, st), "transpose(f_hat)")
+                self._tf32(self.logits.data_ptr(), True, SC, self.fhT32.data_ptr(), False, D, B, alpha, self.dP.data_ptr(), D)
+            else:
+                self._tf32(self.logits.data_ptr(), True, SC, self.f_hat.data_ptr(), True, D, B, alpha, self.dP.data_ptr(), D)
         elif cfg.precision != "fp32":
             # K-major operands: dlogits^T [SC, B] and f_hat^T [D, B] (K = batch)
             if not self.tl_adjoint:

@@ -275,6 +275,9 @@ int clipgp_cast_bf16(const float* x, int64_t R, int64_t K, int64_t ldx, void* ou
 
 /* Transposing form: fp32 [R,K] -> bf16 [K, R] (or the split [K, 3R] layouts) with out[k*out_ld + g*seg_stride + r]; produces the
  * K-major operands of the adjoint GEMMs (dlogits^T, f_hat^T, P_hat^T) without an fp32 transpose. */
+/* out[k][r] = x[r][k] (fp32; row pitches ldx >= K, out_ld >= R).  The small operand of a long-K TF32 GEMM is handed to the tensor
+ * cores K-major through this copy: an MN-major B operand costs the MMA pipeline ~35 % of its rate, the copy microseconds. */
+int clipgp_transpose_f32(const float* x, int64_t R, int64_t K, int64_t ldx, float* out, int64_t out_ld, void* stream);
 int clipgp_cast_bf16_transpose(const float* x, int64_t R, int64_t K, int64_t ldx, void* out, int64_t out_ld, int64_t seg_stride,
                                int mode, void* stream);
 

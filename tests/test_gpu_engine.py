@@ -115,6 +115,30 @@ def test_tensor_core_step_loss_and_gradients(precision, loss_mode, name):
     assert within(eng2.flat_g, eng.flat_g, 1e-5)            # split-K reductions: fp32 summation order varies run to run
 
 
+def test_tf32_large_batch_uses_kmajor_copies_and_matches_in_place_operands():
+    """B >= 1024: the adjoint GEMMs read P_hat / f_hat from transposed copies (K-major B operand) instead of MN-major in place.
+    Same products, same TF32 rounding of the operands: the gradients agree to accumulation order, and with the float64 oracle."""
+    wl, shp, eng, orc, cfg = build("rbf", name="tiny", precision="tf32")
+    g = torch.Generator().manual_seed(3)
+    B = 1024
+    idx = torch.randint(0, wl["f_train"].shape[0], (B,), generator=g)
+    f = (wl["f_train"][idx] + 0.05 * torch.randn(B, shp.D, generator=g)).contiguous(); y = wl["y_train"][idx].contiguous()
+    eng.skip_update = True
+    loss = eng.train_step(f.cuda(), y.cuda(), use_graph=False)
+    assert eng.tf32_kmajor_b
+    _, _, eng2, _, _ = build("rbf", name="tiny", precision="tf32")
+    eng2.skip_update = True
+    eng2._alloc_train(B); eng2.tf32_kmajor_b = False
+    loss2 = eng2.train_step(f.cuda(), y.cuda(), use_graph=False)
+    assert float(loss) == pytest.approx(float(loss2), rel=1e-6)
+    assert within(eng.flat_g, eng2.flat_g, 1e-5)
+    eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, cfg.S_train)
+    loss_ref, G = oracle_grads_pair(orc, f, y, eps)
+    assert float(loss) == pytest.approx(float(loss_ref), rel=1e-3)
+    for pn in ("W", "m", "Lq", "ls", "os"):
+        assert max_err(eng.g(pn).view(G[pn][1].shape), G[pn][1]) < 5e-3, pn
+
+
 def test_adamw_update_and_graph_replay_match_eager():
     wl, shp, eng_a, orc, cfg = build("rbf")
     _, _, eng_b, _, _ = build("rbf")
