@@ -81,8 +81,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a pipeline whose producer never arrives (a bad tensor map / descriptor, a byte count that does not match the boxes) would
+// otherwise spin for ever and take the GPU with it.  One counter increment per failed poll (a version that read %globaltimer and
+// backed off with nanosleep cost the issuing thread 4-5 % of the GEMM's rate); 2^28 failed polls are seconds, then the launch traps
+// and fails with an error instead of hanging.  The TMA producer and the epilogue warps wait this way; the single MMA-issuing thread keeps
+// the bare loop below (every instruction between a successful poll and the next tcgen05.mma is on the kernel's critical path: the
+// counter alone cost 5 % there) -- a stalled pipeline still ends, because one of the bounded waiters traps the whole grid.
+__device__ __forceinline__ void mbar_wait_issuer(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+#ifndef CLIPGP_MBAR_UNBOUNDED
+        if (++polls == (1u << 28)) __trap();
+#endif
+    }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
@@ -272,11 +286,11 @@ __global__ void __launch_bounds__(THREADS_WIDE, 1) tc_gemm_kernel(const __grid_c
                 const Item it = decode_item(p, item);
                 const int kb0 = it.kb0, kb1 = it.kb1;
                 for (int nn = 0; nn < p.n_per_item; ++nn) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    mbar_wait_issuer(&tmem_empty[acc], acc_phase ^ 1);
                     fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * ACC_COLS);
                     for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);
+                        mbar_wait_issuer(&full_bar[stage], phase);
                         fence_after();
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                         const uint64_t adesc = p.a_mn ? make_smem_desc_mn(sa, lbo, p.elt) : make_smem_desc(sa);

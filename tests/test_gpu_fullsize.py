@@ -192,6 +192,34 @@ def test_cfg5_matern_T64_S100_full_size():
     assert_parity(base[idx.to(dev)], F.normalize(P_ref, dim=-1), F.normalize(P_64, dim=-1), name="mean prototypes")
 
 
+def test_cfg5_adjoint_full_size_against_float64_autograd():
+    """The same shape through the adjoint (wide-CTA general kernels, blocked factorisations): ALL 397 classes run, the gradients of a
+    class subset are compared with float64 autograd through the oracle."""
+    wl = synth.make_workload("cfg5"); shp = wl["shape"]
+    st = ogp.build_state(wl["E"], "matern", shp.d)
+    st.var_mean, st.chol_var = synth.trained_like_q(shp.C, shp.T + 1, 3)
+    S = 20
+    g = torch.Generator().manual_seed(6)
+    eps = torch.randn(shp.C, shp.T, S, generator=g)
+    dw = torch.randn(S, shp.C, shp.T, generator=g); dkl = torch.rand(shp.C, generator=g)
+    dev, n = "cuda", shp.T + 1
+    mean_x = ogp.residual_mean(st.f0, st.cls_bias, st.tmp_bias, n + shp.T)[:, n:].contiguous()
+    t = lambda x: x.detach().clone().to(dev).requires_grad_(True)
+    Z, ls, m, chol = t(st.inducing_points), t(st.kernel.raw_lengthscale), t(st.var_mean), t(st.chol_var)
+    w, kl, status = ops.gp_weights(Z, st.templates_red.to(dev), ls, None, None, m, chol, mean_x.to(dev), eps.to(dev), "matern", S)
+    assert int(status.abs().max()) == 0
+    ((w * dw.to(dev)).sum() + (kl * dkl.to(dev)).sum()).backward()
+    assert all(bool(torch.isfinite(x.grad).all()) for x in (Z, ls, m, chol))
+    assert float(Z.grad[:, :-1].abs().max()) == 0.0 and float(chol.grad.triu(1).abs().max()) == 0.0
+    idx = torch.tensor([0, 7, 200, 396])
+    from tests.helpers import oracle_grad_pair
+    G32, G64 = oracle_grad_pair(_class_subset(st, idx), eps[idx], dw[:, idx], dkl[idx])
+    for name, got in (("m", m.grad), ("chol", chol.grad), ("ls", ls.grad)):
+        assert_parity(got[idx.to(dev)], G32[name], G64[name], rtol=2e-3, name="d" + name)
+        assert max_err(got[idx.to(dev)], G64[name]) < 1e-3, name
+    assert max_err(Z.grad[idx.to(dev), -1], G64["Z"][:, -1]) < 5e-3
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_cfg1_whole_step_and_eval_against_the_oracle(precision):
     """BASELINE configs[0] at full size (Caltech101 shape: C=100, T=8, D=1024, 4-shot, S=4, RBF) — small enough for the CPU oracle to
