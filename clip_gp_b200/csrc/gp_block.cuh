@@ -276,19 +276,17 @@ __device__ void blk4_trsm_lowerT_left(const T* __restrict__ L, int ldl, const T*
         if (K == 0) break;
         __syncthreads();
         if (owner && ti < K) {
-            T xr[4][4], l[4][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                ld4(X + W * k + c0, xr[k]);
+            for (int k = 0; k < 4; ++k) {              // one row of the block at a time: 8 live operand values next to the 16 of the tile
+                T xr[4], l[4];
+                ld4(X + W * k + c0, xr);
 #pragma unroll
-                for (int x = 0; x < 4; ++x) l[k][x] = (k0 + k < n) ? L[(k0 + k) * ldl + i0 + x] : (T)0;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
+                for (int x = 0; x < 4; ++x) l[x] = (k0 + k < n) ? L[(k0 + k) * ldl + i0 + x] : (T)0;
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) m[x][y] -= l[k][x] * xr[k][y];
+                    for (int y = 0; y < 4; ++y) m[x][y] -= l[x] * xr[y];
+            }
         }
     }
     if (owner) {

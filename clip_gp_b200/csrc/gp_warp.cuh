@@ -10,6 +10,7 @@
 // sequential factorisations and triangular sweeps run in warp 0 (+ warp 1 for the 33rd row / column).
 #pragma once
 #include "gp_common.cuh"
+#include "gp_block.cuh"
 
 namespace clipgp {
 namespace gpw {
@@ -236,7 +237,8 @@ __device__ __forceinline__ float sparsemax_lanes(float f, int T) {
 // 0..31 in warp 0 and, for a 33 x 33 factor, column (row) 32 in warp 1.  About half the instructions of Murray's level-2 reverse
 // sweep (gp::warp_cholesky_rev, which the general block kernel still uses).  L must be zero above its diagonal; P is an m x m scratch matrix (row stride LD); G holds dL on entry.
 template <typename T>
-__device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ G, T* __restrict__ P, int m) {
+__device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T* __restrict__ invd, T* __restrict__ G, T* __restrict__ P, int m,
+                                               T* __restrict__ scratch = nullptr) {
     const int lane = lane_id(), wid = warp_id();
     __syncthreads();
     {   // P = Phi(L^T G): P[i][j] = sum_{k >= i} L[k][i] G[k][j], i >= j   (lane = column j)
@@ -261,6 +263,16 @@ __device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T*
         }
     }
     __syncthreads();
+    if (scratch != nullptr) {
+        // whole-CTA blocked back substitutions (gp_block.cuh: 4 x 4 register tiles, one barrier per four rows) instead of the two
+        // one-warp sweeps below: X = L^-T P, then (X L^-1)^T = L^-T X^T on the transposed matrix; the symmetrisation below does not
+        // care which of Y, Y^T sits in P
+        gp::blk4_trsm_lowerT_left<T, 33, 33>(L, LD, invd, P, LD, m, m, scratch);
+        each_block(m, m, [&](int idx, int i, int j) {
+            if (i < j) { const T t = P[i * LD + j]; P[i * LD + j] = P[j * LD + i]; P[j * LD + i] = t; }
+        });
+        gp::blk4_trsm_lowerT_left<T, 33, 33>(L, LD, invd, P, LD, m, m, scratch);
+    } else {
     // X = L^-T P: back substitution down the rows, lane = column
     if (wid < 2) {
         const int col = (wid == 0) ? lane : 32;
@@ -284,6 +296,7 @@ __device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T*
                     xr[i] = dot_sub<T, 1, LD>(xr[i], xr, L + i, i + 1, m) * invd[i];
                 }
         }
+    }
     }
     __syncthreads();
     each_block(m, m, [&](int idx, int i, int j) {

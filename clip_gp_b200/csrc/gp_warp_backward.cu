@@ -16,6 +16,10 @@
 
 extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
 
+#ifndef BLK4_ADJ
+#define BLK4_ADJ 1      // blocked whole-CTA back substitutions inside the two Cholesky adjoints (0: the one-warp sweeps)
+#endif
+
 namespace clipgp {
 namespace gpw {
 
@@ -246,7 +250,8 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         }
     }
     GPB_TS(4);
-    chol_adj_block<float>(R, s.vecT, G, reinterpret_cast<float*>(s.RC), T);      // RC is free until P2 stages Lq there
+    chol_adj_block<float>(R, s.vecT, G, reinterpret_cast<float*>(s.RC), T,       // RC is free until P2 stages Lq there; its second half
+                          BLK4_ADJ ? reinterpret_cast<float*>(s.RC) + NN : nullptr);   // (16-byte aligned) is the exchange scratch
     each_block(T, T, [&](int idx, int i, int j) {               // G <- dSigma, full symmetric
         if (i > j) { const float v = 0.5f * G[i * LD + j]; G[i * LD + j] = v; G[j * LD + i] = v; }
     });
@@ -417,7 +422,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         if (j < T) dKt[idx] += (float)s.RA[i * LD + j];         // (the same thread wrote dKt[idx], the dSigma block, in P1)
     });
     GPB_TS(9);
-    chol_adj_block<double>(Ld, s.invd, Gd, s.RA, n);
+    chol_adj_block<double>(Ld, s.invd, Gd, s.RA, n, BLK4_ADJ ? reinterpret_cast<double*>(s.Af) : nullptr);     // Af is dead after dL
 
     GPB_TS(10);
     // =========================== P4: kernel adjoint (same CTA; d < 0 skips it: the stand-alone kernel then runs) ===========================

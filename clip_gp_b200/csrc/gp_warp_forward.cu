@@ -7,6 +7,10 @@
 // One 4-warp CTA per class, matrices in shared memory, run-time loops (see gp_warp.cuh).
 #include "gp_warp.cuh"
 
+#ifndef BLK4_FWD
+#define BLK4_FWD 1      // blocked whole-CTA fp64 factorisation + forward solve (0: the one-warp left-looking sweeps)
+#endif
+
 namespace clipgp {
 namespace gpw {
 
@@ -86,6 +90,28 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
 
     GPW_TS(2);
     // ---- warp 0: L = chol64(K_ZZ + 1e-4 I), A = L^-1 K_ZX;  warp 1 meanwhile: KL(q(u) || N(0,I))
+#if BLK4_FWD
+    // blocked whole-CTA factorisation + forward solve on 4 x 4 register tiles (gp_block.cuh): the augmented matrix [K_ZZ + jI | K_ZX] in one
+    // sweep, two barriers per four columns; scratch = Af (written only after the solve)
+    {
+        const bool f = gp::blk4_cholesky_solve<double, 33, 32>(s.Ld, n, LD, s.invd, s.Ad, LD, T, reinterpret_cast<double*>(s.Af), &s.flag[0]);
+        (void)f;
+    }
+    GPW_TS(20);
+    GPW_TS(21);
+    if (wid == 1 && a.kl) {
+        float part = 0.f;                          // 1/2 (|Lq|_F^2 + |m|^2 - n - sum log Lq_ii^2)
+        for (int i = lane; i < n; i += 32) {
+            const float* row = s.Lq + i * LD;
+            float q = 0.f;
+            for (int j = 0; j <= i; ++j) q = fmaf(row[j], row[j], q);
+            part += q - logf(row[i] * row[i]) + s.mvec[i] * s.mvec[i];
+        }
+        part = warp_sum(part);
+        if (lane == 0) a.kl[c] = 0.5f * (part - (float)n);
+    }
+    __syncthreads();
+#else
     if (wid == 0) {
         const bool f = chol33<double>(s.Ld, n, s.invd);
         if (lane == 0) s.flag[0] = f ? 1 : 0;
@@ -107,6 +133,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
     }
     __syncthreads();
     GPW_TS(3);
+#endif
     const bool failL = s.flag[0] != 0;
     each_block(n, T, [&](int idx, int i, int j) { s.Af[i * LD + j] = (float)s.Ad[i * LD + j]; });
     __syncthreads();

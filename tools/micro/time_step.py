@@ -3,6 +3,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
+from clip_gp_b200 import _lib
+if os.environ.get("CLIPGP_LIB"):        # A/B runs: another build of the library (tools/micro/ab_step.py)
+    _lib.LIB_PATH = os.path.join(ROOT, "clip_gp_b200", "lib", os.environ["CLIPGP_LIB"])
 import bench
 from clip_gp_b200 import synth
 from clip_gp_b200.engine import EngineConfig, GPAdapterEngine
