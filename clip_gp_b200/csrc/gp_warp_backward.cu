@@ -388,8 +388,12 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     for (int i = tid; i < n; i += NT) s.invd[i] = 1.0 / Ld[i * LD + i];
     __syncthreads();
     GPB_TS(7);
+#if BLK4_ADJ
+    gp::blk4_trsm_lowerT_left<double, 33, 33>(Ld, LD, s.invd, s.RA, LD, n, T, Gd);   // RA <- dK_ZX = L^-T dA (scratch: RC, written only below)
+#else
     if (wid == 0) trsm_lowerT_cols<double>(Ld, s.invd, s.RA, n, T);   // RA <- dK_ZX = L^-T dA
     __syncthreads();
+#endif
     GPB_TS(8);
     // dL = -tril(dK_ZX A^T)  (lane = column j < 32: row j of A)
     {

@@ -7,6 +7,9 @@
 // One 4-warp CTA per class, matrices in shared memory, run-time loops (see gp_warp.cuh).
 #include "gp_warp.cuh"
 
+#ifndef BLK4_FWD32
+#define BLK4_FWD32 1    // blocked whole-CTA fp32 factorisation of Sigma (0: the register-resident one-warp right-looking sweep)
+#endif
 #ifndef BLK4_FWD
 #define BLK4_FWD 1      // blocked whole-CTA fp64 factorisation + forward solve (0: the one-warp left-looking sweeps)
 #endif
@@ -193,6 +196,10 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         each_block(T, T, [&](int idx, int t, int u) { if (u <= t) R[t * LD + u] = Sig[t * LD + u] + (t == u ? jit : 0.f); });
         __syncthreads();
         GPW_TS(22 + 2 * attempt);
+#if BLK4_FWD32
+        failR = gp::blk4_cholesky_solve<float, 33, 0>(R, T, LD, s.invdR, nullptr, 0, 0, s.Bm, &s.flag[1]);      // Bm is dead after Sigma
+        GPW_TS(23 + 2 * attempt);
+#else
         if (wid == 0) {
             const bool f = chol32_regs(R, T, s.invdR);
             GPW_TS(23 + 2 * attempt);
@@ -200,6 +207,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         }
         __syncthreads();
         failR = s.flag[1] != 0;
+#endif
         if (!failR) break;
         ++retries;
         __syncthreads();                            // everyone has read the flag before the next attempt rewrites it
