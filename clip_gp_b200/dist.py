@@ -78,34 +78,51 @@ class PeerBlock:
     layout: {name: (offset_bytes, nbytes)}; identical on every rank."""
 
     def __init__(self, layout, device: torch.device, rank: int, world: int, group=None):
+        """Collective over the group.  Raises RuntimeError ON EVERY RANK if any rank could not allocate, export or map a block (CUDA IPC
+        unavailable in the container, peers on another node, ...), so that the caller can fall back to NCCL consistently."""
         from . import _lib
         import ctypes as C
         if world > _lib.PEER_MAX:
             raise ValueError(f"PeerBlock: world {world} > {_lib.PEER_MAX}")
         self.lib, self.rank, self.world, self.layout, self.device = _lib.load(), rank, world, dict(layout), device
         self.nbytes = max(o + b for o, b in layout.values())
-        base = C.c_void_p()
-        with torch.cuda.device(device):
-            _lib.check(self.lib.clipgp_peer_alloc(self.nbytes, C.byref(base)), "peer_alloc")
-            handle = C.create_string_buffer(64)
-            _lib.check(self.lib.clipgp_ipc_export(base, handle), "ipc_export")
-        self.base = int(base.value)
+        self.base, self._mapped, self._bytes, self.bases = 0, [], None, [0] * world
+        err, handle = None, C.create_string_buffer(64)
+        try:
+            import os
+            if os.environ.get("CLIPGP_PEER_DISABLE_IPC"):             # test hook: exercise the collective fall-back
+                raise RuntimeError("CUDA IPC disabled by CLIPGP_PEER_DISABLE_IPC")
+            base = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(self.lib.clipgp_peer_alloc(self.nbytes, C.byref(base)), "peer_alloc")
+                self.base = int(base.value)
+                _lib.check(self.lib.clipgp_ipc_export(base, handle), "ipc_export")
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {rank}: {e}"
+        got = [None] * world
+        torch.distributed.all_gather_object(got, (err, bytes(handle.raw)), group=group)
+        errs = [g[0] for g in got if g[0]]
+        if not errs:
+            try:
+                with torch.cuda.device(device):
+                    for q in range(world):
+                        if q == rank:
+                            self.bases[q] = self.base
+                            continue
+                        ptr = C.c_void_p()
+                        _lib.check(self.lib.clipgp_ipc_open(got[q][1], C.byref(ptr)), f"ipc_open(rank {q})")
+                        self.bases[q] = int(ptr.value)
+                        self._mapped.append(int(ptr.value))
+            except Exception as e:  # noqa: BLE001
+                err = f"rank {rank}: {e}"
+            got2 = [None] * world
+            torch.distributed.all_gather_object(got2, err, group=group)     # also the barrier: nobody touches a block before all are mapped
+            errs = [g for g in got2 if g]
+        if errs:
+            self.close()
+            raise RuntimeError("PeerBlock: CUDA IPC peer mapping failed (" + "; ".join(errs) + ")")
         self._carrier = _CudaArray(self.base, self.nbytes)
         self._bytes = torch.as_tensor(self._carrier, device=device)
-        handles = [None] * world
-        torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
-        self.bases = [0] * world
-        self._mapped = []
-        with torch.cuda.device(device):
-            for q in range(world):
-                if q == rank:
-                    self.bases[q] = self.base
-                    continue
-                ptr = C.c_void_p()
-                _lib.check(self.lib.clipgp_ipc_open(handles[q], C.byref(ptr)), f"ipc_open(rank {q})")
-                self.bases[q] = int(ptr.value)
-                self._mapped.append(int(ptr.value))
-        torch.distributed.barrier(group=group)          # nobody touches a peer's block before everybody has mapped everything
 
     def local(self, name: str, dtype: torch.dtype) -> torch.Tensor:
         o, b = self.layout[name]
@@ -125,5 +142,7 @@ class PeerBlock:
                 self.lib.clipgp_ipc_close(C.c_void_p(p))
             self._mapped = []
             self._bytes = None
-            self.lib.clipgp_peer_free(C.c_void_p(self.base))
+            if self.base:
+                self.lib.clipgp_peer_free(C.c_void_p(self.base))
+            self.base = 0
         self.lib = None

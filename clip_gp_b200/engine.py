@@ -123,7 +123,14 @@ class GPAdapterEngine:
             lay, o = {}, 0
             for nm, nb in (("flags", 8 * 2 * _lib.PEER_MAX), ("g", 4 * (off + 1)), ("p", 4 * off)):
                 lay[nm] = (o, nb); o = a16(o + nb)
-            self.peer = dist.PeerBlock(lay, dev, cfg.rank, cfg.world)
+            try:
+                self.peer = dist.PeerBlock(lay, dev, cfg.rank, cfg.world)
+            except RuntimeError as e:          # raised on every rank together: all of them take the NCCL path
+                if cfg.rank == 0:
+                    import sys
+                    print(f"[clipgp] peer_update unavailable, using ncclAllReduce + AdamW: {e}", file=sys.stderr)
+                self.peer = None
+        if self.peer is not None:
             self.flat_p = self.peer.local("p", torch.float32)
             self.flat_g = self.peer.local("g", torch.float32)
             self.peer_local = torch.zeros(2, dtype=torch.int64, device=dev)         # epoch, CTA arrival counter

