@@ -16,6 +16,9 @@
 
 extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
 
+#ifndef SPARSE_W
+#define SPARSE_W 1       // skip a[s][t] = <dP_s, E_t> where the sparsemax weight w[s][t] is zero
+#endif
 #ifndef BLK4_ADJ
 #define BLK4_ADJ 1      // blocked whole-CTA back substitutions inside the two Cholesky adjoints (0: the one-warp sweeps)
 #endif
@@ -123,6 +126,14 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         // a[s][t] = <g_s, E[c,t,:]>: warp = template row (the next row's loads in flight), lanes over the 16-byte column groups
         const float4* Ec = reinterpret_cast<const float4*>(b.proto_E + (size_t)c * T * D);
         constexpr int PSB = 12;
+        // sparsemax: a[s][t] is consumed only where w[s][t] > 0 (q_s = <w_s, a_s>, and the sparsemax adjoint masks dw by the support), and
+        // ~60 % of the weights are exact zeros: lane t keeps the S-bit mask of the samples that need a[., t]
+        unsigned need = 0xFFFu;
+#if SPARSE_W
+        need = 0u;
+        for (int u = 0; u < S; ++u)
+            if (lane < T && __ldg(a.w + ((size_t)u * a.C + c) * T + lane) > 0.f) need |= 1u << u;
+#endif
         if (D4 <= 128) {
             // D <= 512: a lane owns at most four column groups of a row; the next row's loads are issued before this row is consumed
             float4 nxt[4];
@@ -139,6 +150,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
 #pragma unroll
                 for (int u = 0; u < 4; ++u) e[u] = nxt[u];
                 fetch(t + NW);
+                const unsigned nt = __shfl_sync(FULL, need, t);      // samples whose support holds template t (warp-uniform)
                 float part[PSB];
 #pragma unroll
                 for (int u = 0; u < PSB; ++u) part[u] = 0.f;
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
                     if (col < D4) {
 #pragma unroll
                         for (int u = 0; u < PSB; ++u) {
-                            if (u < S) {
+                            if (u < S && ((nt >> u) & 1u)) {
                                 const float4 v = reinterpret_cast<const float4*>(gbuf + (size_t)u * D)[col];
                                 part[u] += e[q].x * v.x + e[q].y * v.y + e[q].z * v.z + e[q].w * v.w;
                             }
@@ -158,7 +170,8 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
 #pragma unroll
                 for (int u = 0; u < PSB; ++u) {
                     if (u < S) {
-                        const float tot = warp_sum(part[u]);
+                        float tot = 0.f;
+                        if ((nt >> u) & 1u) tot = warp_sum(part[u]);
                         if (lane == 0) abuf[u * 32 + t] = tot;
                     }
                 }

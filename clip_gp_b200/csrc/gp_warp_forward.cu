@@ -7,6 +7,9 @@
 // One 4-warp CTA per class, matrices in shared memory, run-time loops (see gp_warp.cuh).
 #include "gp_warp.cuh"
 
+#ifndef SPARSE_W
+#define SPARSE_W 1       // skip the multiply-adds of zero sparsemax weights in the prototype stage
+#endif
 #ifndef BLK4_FWD32
 #define BLK4_FWD32 1    // blocked whole-CTA fp32 factorisation of Sigma (0: the register-resident one-warp right-looking sweep)
 #endif
@@ -280,8 +283,13 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
                 for (int u = 0; u < PS; ++u) {
                     if (u < sb) {
                         const float wv = wt[u * 32];
-                        acc[u].x = fmaf(wv, e[q].x, acc[u].x); acc[u].y = fmaf(wv, e[q].y, acc[u].y);
-                        acc[u].z = fmaf(wv, e[q].z, acc[u].z); acc[u].w = fmaf(wv, e[q].w, acc[u].w);
+#if SPARSE_W
+                        if (wv != 0.f)                                    // sparsemax weights: ~60 % exact zeros; the test is uniform over the CTA
+#endif
+                        {
+                            acc[u].x = fmaf(wv, e[q].x, acc[u].x); acc[u].y = fmaf(wv, e[q].y, acc[u].y);
+                            acc[u].z = fmaf(wv, e[q].z, acc[u].z); acc[u].w = fmaf(wv, e[q].w, acc[u].w);
+                        }
                     }
                 }
             }

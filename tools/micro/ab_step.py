@@ -1,7 +1,7 @@
 """A/B the cfg2 train step between libclipgp.so and libclipgp_ts.so on the same box (kernel experiments)."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-for rnd in range(3):
+for rnd in range(4):
     for which, lib in (("main", ""), ("alt ", "libclipgp_ts.so")):
         env = dict(os.environ); env["CLIPGP_LIB"] = lib
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "micro", "time_step.py"), "tf32", "300"], capture_output=True, text=True, env=env)
