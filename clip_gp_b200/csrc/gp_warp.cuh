@@ -306,6 +306,139 @@ __device__ __forceinline__ void chol_adj_block(const T* __restrict__ L, const T*
     __syncthreads();
 }
 
+// Kernel adjoint of ONE symmetric-input Gram block K(Z, Z) for the warp path (n <= 36 rows, learnable row n - 1): the arithmetic of
+// gp::kernel_adjoint_block (q_k = sum_ij W_ij (u_ik - u_jk)^2 in expanded form with V = W U from 4 x 4 register tiles; gradient of the
+// learnable row; amplitude gradient), re-laid out so that BOTH operands of the tile product are 16-byte shared-memory loads:
+//   U chunk  [row][KV = 36]  (row stride a multiple of 4: u[j][4kq .. 4kq+3] is one LDS.128, and the loader writes with STS.128),
+//   W^T      [j][KV]         (W_T[j][i0 .. i0+3] is one LDS.128; W is NOT symmetric here: the block carries dK_ZZ + [dK_ZX | 0] + dK_XX),
+// i.e. 2 loads per 16 multiply-adds instead of 8 (kernel adjoint = the longest phase of the adjoint kernel, 86 k of 317 k cycles).
+//   dK   : [n][LD] upstream gradient;  Kv: [n][LD] kernel values (both read only)
+//   WT   : [n][KV] scratch;  tile: [pad4(n)][KV] scratch;  q, dzl: [d] accumulators (zeroed by the caller);  rs, cs: [>= n]
+constexpr int KV = 36;
+__device__ inline float kernel_adjoint_sym(const float* __restrict__ dK, const float* __restrict__ Kv, float* __restrict__ WT,
+                                           const float* __restrict__ gZ, int n, int d, int kt, float amp, const float* __restrict__ invls,
+                                           float* __restrict__ tile, float* __restrict__ q, float* __restrict__ dzl,
+                                           float* __restrict__ rs, float* __restrict__ cs) {
+    using gp::KC;
+    float damp = 0.f;
+    const float inv_amp = 1.f / amp;
+    const int tid = threadIdx.x;
+    each_block(n, n, [&](int idx, int i, int j) {
+        const float kv = Kv[i * LD + j], g = dK[i * LD + j];
+        float wv;
+        if (kt == CLIPGP_KERNEL_RBF) { damp += g * kv * inv_amp; wv = -0.5f * g * kv; }
+        else if (kt == CLIPGP_KERNEL_MATERN12) { const float rr = -logf(kv); wv = (kv < 1.f && rr > 0.f) ? (-0.5f * g * kv / rr) : 0.f; }
+        else { damp += g * kv * inv_amp; wv = g * amp; }
+        WT[j * KV + i] = wv;
+    });
+    if (tid < 3 * KV) {                                       // rows n .. n+2 of a padded 4-row tile read W_T[j][i >= n]: zero columns
+        for (int j = 0; j < n; ++j) if (tid >= n && tid < KV) WT[j * KV + tid] = 0.f;
+    }
+    __syncthreads();
+    const bool dot = (kt == CLIPGP_KERNEL_LINEAR);
+    const int rowL = n - 1;
+    if (!dot) {
+        for (int i = tid; i < n; i += NT) { float t = 0.f; for (int j = 0; j < n; ++j) t += WT[j * KV + i]; rs[i] = t; }      // row sums of W
+        for (int j = tid; j < n; j += NT) { float t = 0.f; for (int i = 0; i < n; ++i) t += WT[j * KV + i]; cs[j] = t; }      // column sums
+    }
+    const int pA = gp::pad4(n);
+    constexpr int KQ = KC / 4;
+    const int vtiles = (pA >> 2) * KQ;
+    const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(gZ) & 15u) == 0);
+    for (int k0 = 0; k0 < d; k0 += KC) {
+        __syncthreads();
+        // ---- chunk loader: columns [k0, k0 + KC) of Z (scaled by the inverse length-scales), rows >= n and columns >= d zero
+        if (vec) {
+            const int total = pA * KQ;
+            for (int base = tid; base < total; base += 4 * NT) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + u * NT;
+                    const int r = idx / KQ, k = k0 + (idx - r * KQ) * 4;
+                    v[u] = (idx < total && r < n && k < d) ? __ldg(reinterpret_cast<const float4*>(gZ + (size_t)r * d + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + u * NT;
+                    if (idx < total) {
+                        const int r = idx / KQ, qq = (idx - r * KQ) * 4, k = k0 + qq;
+                        float4 x = v[u];
+                        if (!dot && k < d) { const float4 sc = *reinterpret_cast<const float4*>(invls + k); x.x *= sc.x; x.y *= sc.y; x.z *= sc.z; x.w *= sc.w; }
+                        *reinterpret_cast<float4*>(tile + r * KV + qq) = x;
+                    }
+                }
+            }
+        } else {
+            for (int idx = tid; idx < pA * KC; idx += NT) {
+                const int r = idx / KC, k = idx - r * KC;
+                float v = 0.f;
+                if (r < n && k0 + k < d) { v = __ldg(gZ + (size_t)r * d + k0 + k); if (!dot) v *= invls[k0 + k]; }
+                tile[r * KV + k] = v;
+            }
+        }
+        __syncthreads();
+        if (!dot) {
+            for (int tl = tid; tl < vtiles; tl += NT) {
+                const int it = tl / KQ, kq = tl - it * KQ, i0 = it * 4;
+                float v[4][4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) v[x][y] = 0.f;
+                const float* wp = WT + i0;
+                const float* up = tile + kq * 4;
+#pragma unroll 3
+                for (int j = 0; j < n; ++j) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wp + j * KV);
+                    const float4 u4 = *reinterpret_cast<const float4*>(up + j * KV);
+                    const float w[4] = {w4.x, w4.y, w4.z, w4.w}, u[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) v[x][y] = fmaf(w[x], u[y], v[x][y]);
+                }
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int k = k0 + kq * 4 + y;
+                    if (k < d) {
+                        float accq = 0.f;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const int i = i0 + x;
+                            if (i < n) { const float ua = tile[i * KV + kq * 4 + y]; accq += ua * (rs[i] * ua - 2.f * v[x][y]); }
+                        }
+                        atomicAdd(&q[k], accq);
+                    }
+                }
+            }
+            if (tid < KC && k0 + tid < d) {                                // column term sum_j c_j u_jk^2
+                float accq = 0.f;
+                for (int j = 0; j < n; ++j) { const float uj = tile[j * KV + tid]; accq = fmaf(cs[j] * uj, uj, accq); }
+                atomicAdd(&q[k0 + tid], accq);
+            }
+        }
+        if (tid >= NT - KC) {                                               // the learnable row (as an A row and as a B row)
+            const int kk = tid - (NT - KC), k = k0 + kk;
+            if (k < d) {
+                float dz = 0.f;
+                const float ul = tile[rowL * KV + kk];
+                for (int j = 0; j < n; ++j) {
+                    const float uj = tile[j * KV + kk];
+                    const float wa = WT[j * KV + rowL];                     // W[rowL][j]
+                    const float wb = WT[rowL * KV + j];                     // W[j][rowL]
+                    dz = fmaf(wa, dot ? uj : (ul - uj), dz);
+                    dz = fmaf(wb, dot ? uj : (ul - uj), dz);
+                }
+                if (!dot) dz *= 2.f * invls[k];
+                dzl[k] += dz;
+            }
+        }
+    }
+    __syncthreads();
+    return damp;
+}
+
 // Offsets of the per-class record in Ksave ([alias flag | K_ZZ n*n | K_ZX n*T | K_XX T*T]).  For aliased classes the
 // K_ZX / K_XX part is unused by the forward pass; the adjoint uses it as scratch for d loss / d K_ZZ (n*n <= n*T + T*T for T >= 2).
 __device__ __forceinline__ size_t ksave_stride(int n, int T) { return (size_t)1 + (size_t)n * n + (size_t)n * T + (size_t)T * T; }

@@ -16,6 +16,9 @@
 
 extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d);
 
+#ifndef KADJ_V
+#define KADJ_V 1         // kernel adjoint with 16-byte operand loads (stride-36 chunk tile + transposed W); 0: gp::kernel_adjoint_block
+#endif
 #ifndef SPARSE_W
 #define SPARSE_W 1       // skip a[s][t] = <dP_s, E_t> where the sparsemax weight w[s][t] is zero
 #endif
@@ -475,7 +478,11 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
     __syncthreads();
     const float* Zc = a.Z + (size_t)c * n * d;
     GPB_TS(11);
+#if KADJ_V
+    const float damp = kernel_adjoint_sym(dK, Wm, tileA + gp::pad4(n) * KV, Zc, n, d, kt, amp, invls, tileA, qls, dzl, rs, cs);
+#else
     const float damp = gp::kernel_adjoint_block(dK, LD, Wm, Zc, n, Zc, n, d, kt, amp, invls, tileA, tileA, qls, dzl, n - 1, n - 1, rs, cs);
+#endif
     GPB_TS(12);
     __shared__ float red[32];
     const float damp_tot = block_sum(damp, red);
@@ -511,7 +518,7 @@ extern "C" int clipgp_gp_fused_proto_bwd_ok(int64_t T, int64_t n, int64_t d, int
 // Shared memory the fused kernel-adjoint stage needs in RB + RC (floats): inverse length-scales, two per-feature accumulators,
 // row / column sums and one [pad4(n)][KCP] chunk tile.
 extern "C" int clipgp_gp_warp_fused_adjoint_ok(int64_t n, int64_t d) {
-    const size_t need = 3 * (size_t)((d + 3) & ~3) + 72 + (size_t)gp::pad4((int)n) * gp::KCP;
+    const size_t need = 3 * (size_t)((d + 3) & ~3) + 72 + (size_t)gp::pad4((int)n) * gpw::KV + (size_t)n * gpw::KV;   // + transposed W
     return need * sizeof(float) <= 2 * sizeof(double) * gpw::NN ? 1 : 0;
 }
 
