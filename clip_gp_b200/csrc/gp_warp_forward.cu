@@ -7,6 +7,9 @@
 // One 4-warp CTA per class, matrices in shared memory, run-time loops (see gp_warp.cuh).
 #include "gp_warp.cuh"
 
+#ifndef PROTO_W4
+#define PROTO_W4 1       // prototype stage: a row's weights as three 16-byte shared-memory loads (S <= 12)
+#endif
 #ifndef SPARSE_W
 #define SPARSE_W 1       // skip the multiply-adds of zero sparsemax weights in the prototype stage
 #endif
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
 
     // ---- f_s = mu + R eps_s ; w_s = sparsemax(f_s)   (one sample per warp at a time, lane = template)
     // fused prototype stage: the weights also stay in shared memory, [S][32] floats in the (dead, saved) L / A regions
-    float* wsm = (a.proto_E != nullptr && (a.proto_P_hat != nullptr || a.proto_mean_hat != nullptr) && a.proto_D <= 4 * NT && S * 32 <= 4 * NN)
+    float* wsm = (a.proto_E != nullptr && (a.proto_P_hat != nullptr || a.proto_mean_hat != nullptr) && a.proto_D <= 4 * NT && S * 32 + 32 * 12 <= 4 * NN)
                      ? reinterpret_cast<float*>(s.Ld) : nullptr;
     __syncthreads();                                // the saves above have read L / A / R's neighbours; Sigma (in Ad) is dead
     GPW_TS(7);
@@ -253,7 +256,10 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
         float wv = sparsemax_lanes(f0 + f1 + mu, T);
         if (st < 0) wv = 0.f;
         if (lane < T) a.w[((size_t)sidx * a.C + c) * T + lane] = wv;
-        if (wsm) wsm[sidx * 32 + lane] = wv;        // lanes >= T hold 0
+        if (wsm) {
+            wsm[sidx * 32 + lane] = wv;             // lanes >= T hold 0
+            if (S <= 10) wsm[S * 32 + lane * 12 + sidx] = wv;     // [t][12] copy (S <= PS, one sample chunk): a row's weights as three 16-byte loads
+        }
     }
     GPW_TS(8);
     if (!wsm) return;
@@ -276,6 +282,25 @@ __global__ void __launch_bounds__(NT, 7) gp_forward_warp_kernel(const clipgp_gp_
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 e[q] = (col < D4 && t0 + q < T) ? __ldg(Ec + (size_t)(t0 + q) * D4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#if PROTO_W4
+            if (S <= PS) {
+                // all S weights of a template row from three broadcast 16-byte loads (the [t][12] copy) instead of S scalar loads
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4* wr = reinterpret_cast<const float4*>(wsm + S * 32 + (t0 + q) * 12);
+                    const float4 wa = wr[0], wb = wr[1], wc = wr[2];
+                    const float wv12[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+                    for (int u = 0; u < PS; ++u) {
+                        if (u < sb && wv12[u] != 0.f) {
+                            acc[u].x = fmaf(wv12[u], e[q].x, acc[u].x); acc[u].y = fmaf(wv12[u], e[q].y, acc[u].y);
+                            acc[u].z = fmaf(wv12[u], e[q].z, acc[u].z); acc[u].w = fmaf(wv12[u], e[q].w, acc[u].w);
+                        }
+                    }
+                }
+                continue;
+            }
+#endif
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float* wt = wsm + s0 * 32 + t0 + q;             // w[s0 + u][t0 + q]: broadcast reads (0 beyond T)
@@ -357,7 +382,7 @@ extern "C" int clipgp_gp_warp_path_ok(int64_t T, int64_t n, int64_t d) {
 // The fused prototype stage runs on the warp path when D <= 512 (one 16-byte column group per thread), S <= 136 (the weights of
 // the class stay in the dead L / A regions) and the class set is not sharded (every class of w is produced by this launch).
 extern "C" int clipgp_gp_fused_proto_ok(int64_t T, int64_t n, int64_t d, int64_t D, int64_t S) {
-    return (clipgp_gp_warp_path_ok(T, n, d) && D >= 4 && (D % 4) == 0 && D <= 4 * gpw::NT && S * 32 <= 4 * gpw::NN) ? 1 : 0;
+    return (clipgp_gp_warp_path_ok(T, n, d) && D >= 4 && (D % 4) == 0 && D <= 4 * gpw::NT && S * 32 + 32 * 12 <= 4 * gpw::NN) ? 1 : 0;
 }
 
 int clipgp_gp_forward_warp_launch(const clipgp_gp_args* a, cudaStream_t st, int fuse_gram) {
