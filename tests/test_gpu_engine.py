@@ -115,6 +115,23 @@ def test_tensor_core_step_loss_and_gradients(precision, loss_mode, name):
     assert within(eng2.flat_g, eng.flat_g, 1e-5)            # split-K reductions: fp32 summation order varies run to run
 
 
+@pytest.mark.parametrize("S", [10, 12, 23])
+def test_step_with_more_samples_than_one_prototype_pass(S):
+    """S = 10 is the single-pass form of the fused prototype stages (16-byte weight loads, zero-weight skipping); S = 12 / 23 take the
+    chunked passes over E[c] (10 samples per pass) and the fused adjoint's S <= 12 limit / the un-fused fallback."""
+    wl, shp, eng, orc, cfg = build("rbf", name="tiny", S=S)
+    f, y = wl["f_train"][: shp.B], wl["y_train"][: shp.B]
+    eps = philox.eps_tensor(cfg.seed, 0, shp.C, shp.T, cfg.S_train)
+    loss_ref, G = oracle_grads_pair(orc, f, y, eps)
+    eng.skip_update = True
+    loss = eng.train_step(f.cuda(), y.cuda(), use_graph=False)
+    assert float(loss) == pytest.approx(float(loss_ref), rel=1e-4)
+    for pn in ("W", "m", "Lq", "ls", "os"):
+        g32, g64 = G[pn]
+        assert_parity(eng.g(pn).view(g32.shape), g32, g64, rtol=2e-3, name=f"d{pn}")
+        assert max_err(eng.g(pn).view(g32.shape), g64) < 2e-3, pn
+
+
 def test_tf32_large_batch_uses_kmajor_copies_and_matches_in_place_operands():
     """B >= 1024: the adjoint GEMMs read P_hat / f_hat from transposed copies (K-major B operand) instead of MN-major in place.
     Same products, same TF32 rounding of the operands: the gradients agree to accumulation order, and with the float64 oracle."""
