@@ -667,7 +667,7 @@ def profile_step_kernels(eng, f_all, y_all, shp, flush, reps=5, B=None):
              "clipgp_rownorm_backward", "clipgp_l2_identity", "clipgp_proto_backward", "clipgp_gp_backward", "clipgp_sum_accumulate",
              "clipgp_adamw_step", "clipgp_adamw_step_lrptr", "clipgp_increment", "clipgp_tc_gemm_store", "clipgp_tc_gemm_store_splitk", "clipgp_cast_bf16", "clipgp_cast_bf16_transpose", "clipgp_cast_bf16_dual",
              "clipgp_softmax_ce_stats", "clipgp_softmax_grad_bf16_dual", "clipgp_softmax_ce_bf16_dual", "clipgp_increment2", "clipgp_step_epilogue",
-             "clipgp_peer_adamw", "clipgp_transpose_f32"]
+             "clipgp_peer_adamw", "clipgp_transpose_f32", "clipgp_adamw_tail"]
     multi = ("tc_gemm_tf32", "gemm_f32", "transpose_f32", "adamw_step", "adamw_step_lrptr", "increment", "tc_gemm_store", "tc_gemm_store_splitk", "cast_bf16", "cast_bf16_transpose", "cast_bf16_dual")
     seg = getattr(eng, "tc_seg", 1)
     B = B or shp.B

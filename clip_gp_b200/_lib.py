@@ -73,6 +73,9 @@ class PeerArgs(C.Structure):
 
 _SIGNATURES = {
     # name: (restype, argtypes)
+    "clipgp_adamw_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_void_p, c_i64, c_i64, c_i64, c_i64, C.c_void_p, C.c_void_p, c_i64, C.c_float, C.c_void_p, C.c_void_p, c_i64,
+                                    C.c_void_p, C.c_void_p]),
     "clipgp_transpose_f32": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, c_i64, C.c_void_p]),
     "clipgp_peer_alloc": (C.c_int, [c_i64, C.POINTER(C.c_void_p)]),
     "clipgp_peer_free": (C.c_int, [C.c_void_p]),

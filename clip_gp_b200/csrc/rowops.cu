@@ -620,6 +620,74 @@ __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restr
     }
 }
 
+
+// Tail of the single-GPU optimisation step in ONE launch (was: KL sum -> AdamW of the gp_weighter group -> scatter of the learnable
+// inducing row + counters: three dependent launches behind the adjoint kernel, ~19 us on the critical path).
+//   * AdamW (same arithmetic as adamw_kernel) over p / g / m / v [n], 16 bytes per thread and step;
+//   * elements of the z_last segment [z_off, z_off + C d) are also written to Z[c, nrows - 1, k] (gp_template_weigher.py:72-79);
+//   * the LAST CTA of the grid adds kl_scale * sum(kl) to loss[0] (one writer, fixed summation order);
+//   * whoever takes the last ticket advances the AdamW step and the RNG draw index (every CTA has read the step by then).
+__global__ void __launch_bounds__(256) adamw_tail_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr, float b1, float b2,
+                                                         float eps, float wd, int64_t* step_ptr, int64_t z_off, int64_t zn, int nrows, int d,
+                                                         float* __restrict__ Z, const float* __restrict__ kl, int64_t kl_n, float kl_scale,
+                                                         float* loss, int64_t* counter_b, int64_t by, unsigned int* ticket) {
+    __shared__ float red[32];
+    const float lr = *lr_ptr;
+    const float t = (float)(*step_ptr);
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+    const unsigned workers = gridDim.x - 1;
+    if (blockIdx.x == workers) {
+        if (kl != nullptr) {
+            float q = 0.f;
+            for (int64_t i = threadIdx.x; i < kl_n; i += blockDim.x) q += kl[i];
+            const float tot = block_sum(q, red);
+            if (threadIdx.x == 0) loss[0] += tot * kl_scale;
+        }
+    } else {
+        const int64_t n4 = n >> 2;
+        for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (int64_t)workers * blockDim.x) {
+            const float4 gi = reinterpret_cast<const float4*>(g)[i4];
+            float4 pi = reinterpret_cast<float4*>(p)[i4], mi = reinterpret_cast<float4*>(m)[i4], vi = reinterpret_cast<float4*>(v)[i4];
+#define CLIPGP_ADAMW1(c)                                                        \
+            mi.c = b1 * mi.c + (1.f - b1) * gi.c;                               \
+            vi.c = b2 * vi.c + (1.f - b2) * gi.c * gi.c;                        \
+            pi.c = pi.c * decay - step_size * mi.c / (sqrtf(vi.c) * inv_sqrt_bc2 + eps);
+            CLIPGP_ADAMW1(x) CLIPGP_ADAMW1(y) CLIPGP_ADAMW1(z) CLIPGP_ADAMW1(w)
+#undef CLIPGP_ADAMW1
+            reinterpret_cast<float4*>(p)[i4] = pi; reinterpret_cast<float4*>(m)[i4] = mi; reinterpret_cast<float4*>(v)[i4] = vi;
+            const int64_t i = i4 << 2;
+            if (Z != nullptr && i + 3 >= z_off && i < z_off + zn) {
+                const float pv[4] = {pi.x, pi.y, pi.z, pi.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t r = i + e - z_off;
+                    if (r >= 0 && r < zn) { const int64_t c = r / d; Z[(c * nrows + (nrows - 1)) * d + (r - c * d)] = pv[e]; }
+                }
+            }
+        }
+        if (blockIdx.x == 0) {
+            for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {     // n % 4 tail
+                const float gi = g[i];
+                const float mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
+                const float pi = p[i] * decay - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+                m[i] = mi; v[i] = vi; p[i] = pi;
+                const int64_t r = i - z_off;
+                if (Z != nullptr && r >= 0 && r < zn) { const int64_t c = r / d; Z[(c * nrows + (nrows - 1)) * d + (r - c * d)] = pi; }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+            *step_ptr += by; *counter_b += by;
+            *ticket = 0u;
+        }
+    }
+}
+
 }  // namespace clipgp
 
 using namespace clipgp;
@@ -875,4 +943,22 @@ extern "C" int clipgp_transpose_f32(const float* x, int64_t R, int64_t K, int64_
     CLIPGP_REQUIRE(gy <= 65535, "transpose_f32: too many rows for one launch");
     transpose_f32_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(x, R, K, ldx, out, out_ld);
     return check_launch("transpose_f32_kernel");
+}
+
+extern "C" int clipgp_adamw_tail(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
+                                 float eps, float weight_decay, int64_t* step, int64_t z_off, int64_t C, int64_t nrows, int64_t d, float* Z,
+                                 const float* kl, int64_t kl_n, float kl_scale, float* loss, int64_t* counter_b, int64_t by,
+                                 unsigned int* ticket, void* stream) {
+    CLIPGP_REQUIRE(n >= 0 && p && g && m && v && lr_dev && step && counter_b && ticket, "adamw_tail: NULL pointer / bad size");
+    CLIPGP_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15u) == 0,
+                   "adamw_tail: p / g / m / v must be 16-byte aligned");
+    CLIPGP_REQUIRE(Z == nullptr || (z_off >= 0 && C >= 0 && nrows >= 1 && d >= 1 && z_off + C * d <= n), "adamw_tail: z_last segment outside the group");
+    CLIPGP_REQUIRE(kl == nullptr || (loss != nullptr && kl_n >= 0), "adamw_tail: kl without loss");
+    int64_t blocks = ((n >> 2) + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    adamw_tail_kernel<<<(unsigned)blocks + 1u, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, weight_decay, step, z_off,
+                                                                              C * d, (int)nrows, (int)d, Z, kl, kl_n, kl_scale, loss, counter_b, by, ticket);
+    return check_launch("adamw_tail_kernel");
 }

@@ -58,6 +58,7 @@ class EngineConfig:
                                         # kernels: step 0.428 -> 0.442 ms.  Off by default; wins when the GEMM has a free slot.
     fuse_eval_projection: bool = True   # tensor-core eval: projection + normalisation + logits + calibration in ONE GEMM (B = [W ; P W])
     overlap: bool = True                # run the feature branch of the step on a side stream next to the GP branch
+    fuse_tail: bool = True              # single GPU: KL sum + AdamW of the gp_weighter group + inducing-row scatter + counters in ONE launch
     seed: int = 0
     rank: int = 0
     world: int = 1
@@ -558,8 +559,9 @@ class GPAdapterEngine:
         if self.class_sharded:
             torch.distributed.all_reduce(self.dw_all)         # every rank wrote its samples (all classes); rows of other ranks are zero
         ck(lib.clipgp_gp_backward(C.byref(self.gp_args), C.byref(self.gp_bwd_args), st), "gp_backward")
-        ck(lib.clipgp_sum_accumulate(self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight, self._loss_acc.data_ptr(), st),
-           "kl_sum")
+        if not self._fused_tail():                            # (single GPU: the KL sum rides in the fused tail kernel of _launch_update)
+            ck(lib.clipgp_sum_accumulate(self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight, self._loss_acc.data_ptr(), st),
+               "kl_sum")
 
     def _adamw_w(self):
         lib, cfg, st = self.lib, self.cfg, _lib.stream_ptr(self.dev)
@@ -610,11 +612,26 @@ class GPAdapterEngine:
             self.peer.close()
             self.flat_p, self.flat_g, self.peer = fp, fg, None
 
+    def _fused_tail(self) -> bool:
+        """Single GPU, updating step: KL sum + AdamW(gp group) + inducing-row scatter + counters are ONE launch (clipgp_adamw_tail)."""
+        return bool(self.cfg.world == 1 and self.cfg.fuse_tail and not getattr(self, "skip_update", False) and self.offsets["W"][1] % 4 == 0)
+
     def _launch_update(self):
         lib, cfg, st = self.lib, self.cfg, _lib.stream_ptr(self.dev)
         ck = _lib.check
         oW, nW = self.offsets["W"]
         b1, b2 = cfg.betas
+        if self._fused_tail():
+            if getattr(self, "_tail_ticket", None) is None:
+                self._tail_ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            rest = self.n_params - nW
+            zo, _ = self.offsets["z_last"]
+            ck(lib.clipgp_adamw_tail(self.flat_p.data_ptr() + 4 * nW, self.flat_g.data_ptr() + 4 * nW, self.flat_m.data_ptr() + 4 * nW,
+                                     self.flat_v.data_ptr() + 4 * nW, rest, self.lr_dev.data_ptr() + 4, b1, b2, cfg.adam_eps, cfg.weight_decay,
+                                     self.adam_step.data_ptr(), zo - nW, self.C, self.n, self.d, self.Z.data_ptr(),
+                                     self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight, self._loss_acc.data_ptr(),
+                                     self.rng_state.data_ptr() + 8, 1, self._tail_ticket.data_ptr(), st), "adamw_tail")
+            return
         if cfg.train_visual_proj and cfg.world > 1:
             self._adamw_w()                                   # multi-GPU: after the gradient all-reduce
         rest = self.n_params - nW

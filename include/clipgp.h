@@ -301,6 +301,13 @@ int clipgp_softmax_ce_bf16_dual(const float* logits, const int64_t* labels, int6
                                 float loss_scale, float grad_scale, void* out, int64_t out_ld, int64_t seg_stride, int mode, void* outT,
                                 int64_t outT_ld, int64_t segT_stride, int modeT, void* stream);
 int clipgp_increment2(int64_t* a, int64_t* b, int64_t by, void* stream);
+/* Tail of the single-GPU optimisation step in ONE launch (adapter.py:462-465 KL term, :537-549 optimizer.step() of the gp_weighter group,
+ * gp_template_weigher.py:72-79 learnable inducing row): AdamW over p / g / m / v [n] (16-byte aligned; arithmetic of
+ * clipgp_adamw_step_lrptr, lr_dev[0]); elements [z_off, z_off + C d) are also scattered to Z[c, nrows - 1, :]; loss[0] += kl_scale *
+ * sum(kl[0 .. kl_n)) (kl may be NULL); then *step += by and *counter_b += by.  ticket: device uint32, zero before the first call. */
+int clipgp_adamw_tail(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2, float eps,
+                      float weight_decay, int64_t* step, int64_t z_off, int64_t C, int64_t nrows, int64_t d, float* Z, const float* kl,
+                      int64_t kl_n, float kl_scale, float* loss, int64_t* counter_b, int64_t by, unsigned int* ticket, void* stream);
 /* End of an optimisation step in one launch: Z[:, n-1, :] <- z_last [C,d] (the learnable inducing row lives in the flat parameter
  * buffer; gp_template_weigher.py:72-79 freezes the other rows) and both device counters += by. */
 int clipgp_step_epilogue(const float* z_last, float* Z, int64_t C, int64_t n, int64_t d, int64_t* counter_a, int64_t* counter_b,

@@ -17,7 +17,8 @@ wl = synth.make_workload("cfg2", n_test=256); shp = wl["shape"]
 dev = torch.device("cuda", 0)
 torch.manual_seed(1)
 gpw = GaussianProcessTemplateWeighter(wl["E"].to(dev), bench._Cfg(shp.kernel, shp.d), lengthscale=1.4146).to(dev)
-eng = GPAdapterEngine(gpw, EngineConfig(S_train=shp.S, S_eval=shp.S, batch_size=shp.B, shots=shp.shots, seed=1234, precision=precision))
+eng = GPAdapterEngine(gpw, EngineConfig(S_train=shp.S, S_eval=shp.S, batch_size=shp.B, shots=shp.shots, seed=1234, precision=precision,
+                                       fuse_tail=not os.environ.get("CLIPGP_NO_FUSE_TAIL")))
 f, y = wl["f_train"].to(dev), wl["y_train"].to(dev)
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 nb = f.shape[0] // shp.B
