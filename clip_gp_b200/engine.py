@@ -58,6 +58,7 @@ class EngineConfig:
                                         # kernels: step 0.428 -> 0.442 ms.  Off by default; wins when the GEMM has a free slot.
     fuse_eval_projection: bool = True   # tensor-core eval: projection + normalisation + logits + calibration in ONE GEMM (B = [W ; P W])
     overlap: bool = True                # run the feature branch of the step on a side stream next to the GP branch
+    clear_on_side: bool = True          # clear the gradient buffer at the head of the side stream instead of in front of the GP forward
     fuse_tail: bool = True              # single GPU: KL sum + AdamW of the gp_weighter group + inducing-row scatter + counters in ONE launch
     seed: int = 0
     rank: int = 0
@@ -344,12 +345,16 @@ class GPAdapterEngine:
         cfg = self.cfg
         main = torch.cuda.current_stream(self.dev)
         side = self._side_stream if cfg.overlap else None
-        self.flat_g.zero_()
         if side is not None:
+            if not cfg.clear_on_side:
+                self.flat_g.zero_()
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                self._fwd_features()
+                if cfg.clear_on_side:
+                    self.flat_g.zero_()       # off the critical path: the GP forward does not touch the gradient buffer, and every writer of
+                self._fwd_features()          # it (loss terms, adjoint kernels, split-K GEMMs) runs after main has joined this stream again
         else:
+            self.flat_g.zero_()
             self._fwd_features()
         self._fwd_prototypes()
         if side is not None:

@@ -18,7 +18,8 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(1)
 gpw = GaussianProcessTemplateWeighter(wl["E"].to(dev), bench._Cfg(shp.kernel, shp.d), lengthscale=1.4146).to(dev)
 eng = GPAdapterEngine(gpw, EngineConfig(S_train=shp.S, S_eval=shp.S, batch_size=shp.B, shots=shp.shots, seed=1234, precision=precision,
-                                       fuse_tail=not os.environ.get("CLIPGP_NO_FUSE_TAIL")))
+                                       fuse_tail=not os.environ.get("CLIPGP_NO_FUSE_TAIL"),
+                                       clear_on_side=not os.environ.get("CLIPGP_CLEAR_ON_MAIN")))
 f, y = wl["f_train"].to(dev), wl["y_train"].to(dev)
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 nb = f.shape[0] // shp.B
