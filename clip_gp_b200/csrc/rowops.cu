@@ -84,7 +84,59 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* logits, in
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     float my_loss = 0.f;
-    if (row < R) {
+    // register-resident rows (C <= 1024, 16-byte aligned): ONE 16-byte read per 4 logits, one exp per logit, one 16-byte write -- the
+    // general path below reads the row three times and evaluates exp twice (this kernel sits on the step's critical path between the
+    // logit GEMM and the d P_hat GEMM: it is pure latency at B = 128)
+#ifdef SOFTMAX_NOVEC
+    const bool vec = false;
+#else
+    const bool vec = C <= 1024 && (C & 3) == 0 && (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(logits) & 15u) == 0) &&
+                     (!dlogits || ((ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(dlogits) & 15u) == 0));
+#endif
+    if (row < R && vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(logits + row * ld);
+        const int lab = (int)labels[row / rows_per_label];
+        const int C4 = C >> 2;
+        float4 v[8];
+        float m = -FLT_MAX;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j4 = lane + 32 * u;
+            v[u] = (j4 < C4) ? x4[j4] : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+        }
+        m = warp_max(m);
+        float s = 0.f, xl = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j4 = lane + 32 * u;
+            if (j4 < C4) {
+                if ((lab >> 2) == j4) xl = (lab & 3) == 0 ? v[u].x : ((lab & 3) == 1 ? v[u].y : ((lab & 3) == 2 ? v[u].z : v[u].w));
+                v[u].x = expf(v[u].x - m); v[u].y = expf(v[u].y - m); v[u].z = expf(v[u].z - m); v[u].w = expf(v[u].w - m);
+                s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+            }
+        }
+        s = warp_sum(s);
+        xl = warp_sum(xl);                                   // exactly one lane holds the label's logit
+        my_loss = m + logf(s) - xl;
+        if (loss_rows && lane == 0) loss_rows[row] = my_loss;
+        if (dlogits) {
+            const float gs = grad_scale / s;
+            float4* g4 = reinterpret_cast<float4*>(dlogits + row * ldd);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j4 = lane + 32 * u;
+                if (j4 < C4) {
+                    float4 o = make_float4(v[u].x * gs, v[u].y * gs, v[u].z * gs, v[u].w * gs);
+                    if ((lab >> 2) == j4) {
+                        if ((lab & 3) == 0) o.x -= grad_scale; else if ((lab & 3) == 1) o.y -= grad_scale;
+                        else if ((lab & 3) == 2) o.z -= grad_scale; else o.w -= grad_scale;
+                    }
+                    g4[j4] = o;
+                }
+            }
+        }
+    } else if (row < R) {
         const float* x = logits + row * ld;
         const int lab = (int)labels[row / rows_per_label];
         float m = -FLT_MAX;
