@@ -68,6 +68,7 @@ class PeerArgs(C.Structure):
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
         ("step", C.c_void_p), ("local", C.c_void_p), ("loss_out", C.c_void_p), ("status", C.c_void_p),
         ("timeout_ns", C.c_uint64),
+        ("kl", C.c_void_p), ("kl_n", c_i64), ("kl_scale", C.c_float),
     ]
 
 

@@ -72,6 +72,15 @@ __global__ void __launch_bounds__(256) peer_adamw_kernel(const clipgp_peer_args 
     const unsigned long long e = s_epoch;
     unsigned long long* mine = a.flags[r];
     // ---- (A) my gradients are complete (written by earlier kernels of this stream); wait for everybody's
+    if (blockIdx.x == 0 && a.kl != nullptr) {
+        // this rank's KL share joins its loss slot first (adapter.py:462-465; saves the separate reduction launch in front of this kernel)
+        __shared__ float red[32];
+        float q = 0.f;
+        for (int64_t i = tid; i < a.kl_n; i += blockDim.x) q += a.kl[i];
+        const float tot = block_sum(q, red);
+        if (tid == 0) { float* slot = const_cast<float*>(a.g[r]) + a.n; *slot += tot * a.kl_scale; __threadfence_system(); }
+        __syncthreads();
+    }
     if (blockIdx.x == 0 && tid < W) st_release_sys_u64(a.flags[tid] + r, e);
     if (tid < W && !spin_until(mine + tid, e, a.timeout_ns)) s_fail = 1;
     __syncthreads();

@@ -566,7 +566,8 @@ class GPAdapterEngine:
         if self.class_sharded:
             torch.distributed.all_reduce(self.dw_all)         # every rank wrote its samples (all classes); rows of other ranks are zero
         ck(lib.clipgp_gp_backward(C.byref(self.gp_args), C.byref(self.gp_bwd_args), st), "gp_backward")
-        if not self._fused_tail():                            # (single GPU: the KL sum rides in the fused tail kernel of _launch_update)
+        if not (self._fused_tail() or (self.peer is not None and not getattr(self, "skip_update", False))):
+            # (single GPU: the KL sum rides in the fused tail kernel of _launch_update; peer mode: in clipgp_peer_adamw)
             ck(lib.clipgp_sum_accumulate(self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight, self._loss_acc.data_ptr(), st),
                "kl_sum")
 
@@ -593,6 +594,7 @@ class GPAdapterEngine:
         a.step, a.local = self.adam_step.data_ptr(), self.peer_local.data_ptr()
         a.loss_out, a.status = self.loss_global.data_ptr(), self.peer_status.data_ptr()
         a.timeout_ns = int(5e9)
+        a.kl, a.kl_n, a.kl_scale = self.kl.data_ptr() + 4 * self.c_lo, self.c_hi - self.c_lo, self.kl_weight      # the KL sum rides in the kernel
         return a
 
     def _launch_peer_update(self):

@@ -409,6 +409,7 @@ int clipgp_pairdist_radix_hist(const float* X, const float* sqnorm, int64_t N, i
  *   n_group0 : elements [0, n_group0) use lr_dev[0], the rest lr_dev[1] (visual-projection / gp_weighter groups, adapter.py:298-309)
  *   step     : device int64, the 1-based Adam step (read, not advanced);  local: device uint64[2], zero before the first call
  *   loss_out : optional device float: sum over ranks of slot n
+ *   kl       : optional device vector whose scaled sum is added to this rank's loss slot first (the KL term of the step)
  *   status   : device int, set to 1 / 2 if a peer's "gradients ready" / "parameters written" flag did not arrive within timeout_ns
  * Every rank must make the same sequence of calls.  The call is stream-ordered and can be captured in a CUDA graph.
  * ================================================================================================ */
@@ -428,6 +429,9 @@ typedef struct clipgp_peer_args {
     float* loss_out;
     int32_t* status;
     unsigned long long timeout_ns;
+    const float* kl;                 /* optional: g[rank][n] += kl_scale * sum(kl[0 .. kl_n)) before the exchange (this rank's KL share) */
+    int64_t kl_n;
+    float kl_scale;
 } clipgp_peer_args;
 int clipgp_peer_alloc(int64_t bytes, void** out);
 int clipgp_peer_free(void* block);

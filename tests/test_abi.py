@@ -65,12 +65,12 @@ def test_peer_args_layout_matches_a_c_compiler(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "clipgp.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
                    'sizeof(clipgp_peer_args), offsetof(clipgp_peer_args, g), offsetof(clipgp_peer_args, flags), offsetof(clipgp_peer_args, m), '
-                   'offsetof(clipgp_peer_args, lr_dev), offsetof(clipgp_peer_args, step), offsetof(clipgp_peer_args, timeout_ns)); return 0; }\n')
+                   'offsetof(clipgp_peer_args, lr_dev), offsetof(clipgp_peer_args, step), offsetof(clipgp_peer_args, kl_scale)); return 0; }\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     P = _lib.PeerArgs
-    assert got == [ctypes.sizeof(P), P.g.offset, P.flags.offset, P.m.offset, P.lr_dev.offset, P.step.offset, P.timeout_ns.offset]
+    assert got == [ctypes.sizeof(P), P.g.offset, P.flags.offset, P.m.offset, P.lr_dev.offset, P.step.offset, P.kl_scale.offset]
     lib = _lib.load()
     assert lib.clipgp_peer_adamw(None, None) != 0 and b"NULL" in lib.clipgp_last_error()
 
