@@ -379,8 +379,10 @@ __device__ inline float kernel_adjoint_sym(const float* __restrict__ dK, const f
         }
         __syncthreads();
         if (!dot) {
-            for (int tl = tid; tl < vtiles; tl += NT) {
-                const int it = tl / KQ, kq = tl - it * KQ, i0 = it * 4;
+            for (int tl0 = 0; tl0 < vtiles; tl0 += NT) {              // all threads iterate together: the reduction below shuffles across the warp
+                const int tl = tl0 + tid;
+                const bool live = tl < vtiles;
+                const int it = live ? tl / KQ : 0, kq = tl & (KQ - 1), i0 = it * 4;
                 float v[4][4];
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
@@ -389,7 +391,7 @@ __device__ inline float kernel_adjoint_sym(const float* __restrict__ dK, const f
                 const float* wp = WT + i0;
                 const float* up = tile + kq * 4;
 #pragma unroll 3
-                for (int j = 0; j < n; ++j) {
+                for (int j = 0; j < (live ? n : 0); ++j) {
                     const float4 w4 = *reinterpret_cast<const float4*>(wp + j * KV);
                     const float4 u4 = *reinterpret_cast<const float4*>(up + j * KV);
                     const float w[4] = {w4.x, w4.y, w4.z, w4.w}, u[4] = {u4.x, u4.y, u4.z, u4.w};
@@ -401,15 +403,19 @@ __device__ inline float kernel_adjoint_sym(const float* __restrict__ dK, const f
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
                     const int k = k0 + kq * 4 + y;
-                    if (k < d) {
-                        float accq = 0.f;
+                    float accq = 0.f;
+                    if (live && k < d) {
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
                             const int i = i0 + x;
                             if (i < n) { const float ua = tile[i * KV + kq * 4 + y]; accq += ua * (rs[i] * ua - 2.f * v[x][y]); }
                         }
-                        atomicAdd(&q[k], accq);
                     }
+                    // lanes l, l + 8, l + 16, l + 24 hold the same feature column (tile index = row tile * 8 + column quad): one shared-memory
+                    // atomic per warp and column instead of one per tile (the atomics were 4 % of the adjoint kernel's stall samples)
+                    accq += __shfl_xor_sync(FULL, accq, 8);
+                    accq += __shfl_xor_sync(FULL, accq, 16);
+                    if (lane_id() < KQ && k < d) atomicAdd(&q[k], accq);
                 }
             }
             if (tid < KC && k0 + tid < d) {                                // column term sum_j c_j u_jk^2
