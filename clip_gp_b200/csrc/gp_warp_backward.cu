@@ -115,6 +115,11 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         const int D = (int)b.proto_D, D4 = D >> 2;
         float* gbuf = reinterpret_cast<float*>(s.RA);                 // [S][D] upstream gradient rows (RA | RB | start of RC)
         dwsm = abuf + S * 32;                                         // [S][32]  (last S*32 floats of RC)
+#if SPARSE_W
+        float wpre[12];                                               // this lane's template weight in every sample: in flight while dP is staged
+#pragma unroll
+        for (int u = 0; u < 12; ++u) wpre[u] = (u < S && lane < T) ? __ldg(a.w + ((size_t)u * a.C + c) * T + lane) : 0.f;
+#endif
         for (int sidx = 0; sidx < S; ++sidx) {
             const float4* src = reinterpret_cast<const float4*>(b.proto_dP + (size_t)sidx * b.proto_dP_stride_s + (size_t)c * D);
             for (int col = tid; col < D4; col += NT) {
@@ -134,8 +139,9 @@ __global__ void __launch_bounds__(NT, 7) gp_backward_warp_kernel(const clipgp_gp
         unsigned need = 0xFFFu;
 #if SPARSE_W
         need = 0u;
-        for (int u = 0; u < S; ++u)
-            if (lane < T && __ldg(a.w + ((size_t)u * a.C + c) * T + lane) > 0.f) need |= 1u << u;
+#pragma unroll
+        for (int u = 0; u < 12; ++u)
+            if (wpre[u] > 0.f) need |= 1u << u;
 #endif
         if (D4 <= 128) {
             // D <= 512: a lane owns at most four column groups of a row; the next row's loads are issued before this row is consumed
