@@ -181,6 +181,19 @@ class _GaussianLikelihood(nn.Module):
         self.noise_covar = _NoiseCovar(C)
 
 
+class _PriorMVN:
+    """What ``GaussianProcessTemplateWeighter.forward`` returns in place of gpytorch.distributions.MultivariateNormal:
+    the prior's mean [K,N] and dense covariance [K,N,N]."""
+
+    def __init__(self, mean: torch.Tensor, covariance_matrix: torch.Tensor):
+        self.mean = self.loc = mean
+        self.covariance_matrix = self.lazy_covariance_matrix = covariance_matrix
+
+    @property
+    def variance(self) -> torch.Tensor:
+        return self.covariance_matrix.diagonal(dim1=-2, dim2=-1)
+
+
 class GaussianProcessTemplateWeighter(nn.Module):
     """Per-class variational GP over templates -> sparsemax template weights -> prototypes.
 
@@ -376,7 +389,39 @@ class GaussianProcessTemplateWeighter(nn.Module):
             pass
 
     def forward(self, x):
-        raise NotImplementedError("the prior forward() is fused into the clipgp GP kernel; use sample_prototypes()")
+        """:167-175 -> the PRIOR over f at ``x`` [K,N,d]: mean_module(x), covar_module(x).  In the reference this is what the
+        variational strategy calls on cat[Z; X]; here that product is fused into the clipgp GP kernel (``sample_prototypes``),
+        so this method is host-side torch for callers that inspect the prior (not a hot path, differentiable by autograd).
+        Returns an object with ``mean`` [K,N], ``covariance_matrix`` [K,N,N] (also ``loc`` / ``lazy_covariance_matrix``)."""
+        mean_x = self.mean_module(x)
+        if not isinstance(mean_x, torch.Tensor):
+            raise TypeError("Mean module must return a tensor")
+        return _PriorMVN(mean_x, self._prior_covariance(x))
+
+    def _prior_covariance(self, x: torch.Tensor) -> torch.Tensor:
+        """covar_module(x) of :101-122 with gpytorch's arithmetic: squared distances as ONE product of the augmented rows
+        [-2a, |a|^2, 1] . [b, 1, |b|^2] after shifting by the row mean (with autograd off, equal inputs get an exactly-zero
+        diagonal), RBF = outputscale * exp(-r^2 / 2) on x / lengthscale, Matern-1/2 = exp(-r) on (x - mean of all rows) /
+        lengthscale with r clamped at 1e-15, linear = variance * x x^T."""
+        cm = self.covar_module
+
+        def sqd(a):
+            exact_diag = not torch.is_grad_enabled()
+            a = a - a.mean(-2, keepdim=True)
+            n2 = a.pow(2).sum(-1, keepdim=True)
+            one = torch.ones_like(n2)
+            r = torch.cat([-2.0 * a, n2, one], -1) @ torch.cat([a, one, n2], -1).transpose(-2, -1)
+            if exact_diag:
+                r.diagonal(dim1=-2, dim2=-1).fill_(0)
+            return r.clamp_min(0)
+
+        if self.kernel_type == "rbf":
+            return sqd(x / cm.base_kernel.lengthscale).div(-2).exp() * cm.outputscale.view(-1, 1, 1)
+        if self.kernel_type == "matern":
+            centre = x.reshape(-1, x.size(-1)).mean(0)
+            return torch.exp(-sqd((x - centre) / cm.lengthscale).clamp_min(1e-30).sqrt())
+        sx = x * cm.variance.sqrt()
+        return sx @ sx.transpose(-2, -1)
 
     def sample_weights(self, num_samples: int, visual_embeddings: Optional[torch.Tensor] = None,
                        eps: Optional[torch.Tensor] = None) -> torch.Tensor:

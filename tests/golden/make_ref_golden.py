@@ -191,6 +191,13 @@ def gp_goldens():
             out[f"{key}/init_from_weights/changed"] = np.array(
                 not torch.equal(m_before, gp.variational_strategy._variational_distribution.variational_mean.detach()))
             out[f"{key}/state_dict_keys"] = np.array(sorted(gp.state_dict().keys()))
+            # (5) the PRIOR gp.forward(x) (gp_template_weigher.py:167-175) at the template rows (N = T) and at the inducing rows
+            #     (N = T + 1: mean-module tail), in grad mode and under no_grad (gpytorch's exact-zero-diagonal distance branch)
+            for tag, xin in (("templates", gp._templates_red), ("inducing", gp.variational_strategy.inducing_points.detach())):
+                prior = gp.forward(xin)
+                out[f"{key}/prior/{tag}/mean"] = np_(prior.mean); out[f"{key}/prior/{tag}/covar"] = np_(prior.covariance_matrix)
+                with torch.no_grad():                              # the kernel is evaluated lazily: densify inside the block
+                    out[f"{key}/prior/{tag}/covar_nograd"] = np_(gp.forward(xin).covariance_matrix)
     return out
 
 

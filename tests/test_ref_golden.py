@@ -148,3 +148,37 @@ def test_initialize_from_weights_is_noop_unless_single_template(G, case):
     changed = bool(G[f"{case}/rbf/init_from_weights/changed"])
     T = G[f"{case}/E"].shape[1]
     assert changed == (T == 1)
+
+
+class _Cfg:
+    def __init__(self, kernel, pca):
+        self.adapter = type("A", (), {"gp_pca_dim": pca, "gp_kernel_type": kernel, "gp_prior_temp": 1.0})()
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_module_prior_forward_matches_reference(G, case, kernel):
+    """The drop-in module's forward(x) (host-side torch, gp_template_weigher.py:167-175 + ResidualMeanWithBias :225-244) against
+    the reference's own forward(): prior mean (N = T and the N = T + 1 tail) and prior covariance of all three kernel families, in
+    grad mode and under no_grad (gpytorch's exact-zero-diagonal distance branch, visible in Matern-1/2)."""
+    from clip_gp_b200.gp_template_weigher import GaussianProcessTemplateWeighter
+    key = f"{case}/{kernel}"
+    gp = GaussianProcessTemplateWeighter(T_(G, f"{case}/E"), _Cfg(kernel, PCA_DIM[case]), lengthscale=1.0)   # CPU tensors: no kernel launch
+    with torch.no_grad():
+        gp.mean_module.cls_bias.copy_(T_(G, f"{key}/param/cls_bias")); gp.mean_module.tmp_bias.copy_(T_(G, f"{key}/param/tmp_bias"))
+        for p, name in zip(gp._kernel_raw(), ("raw_lengthscale", "raw_outputscale", "raw_variance")):
+            if p is not None:
+                p.copy_(T_(G, f"{key}/param/{name}"))
+    for tag, x in (("templates", T_(G, f"{key}/templates_red")), ("inducing", T_(G, f"{key}/param/Z"))):
+        prior = gp.forward(x)
+        assert prior.mean.shape == (x.shape[0], x.shape[1]) and prior.covariance_matrix.shape == (x.shape[0], x.shape[1], x.shape[1])
+        assert rel_err(prior.mean, T_(G, f"{key}/prior/{tag}/mean")) < 1e-6
+        assert rel_err(prior.covariance_matrix, T_(G, f"{key}/prior/{tag}/covar")) < 1e-5
+        with torch.no_grad():
+            assert rel_err(gp.forward(x).covariance_matrix, T_(G, f"{key}/prior/{tag}/covar_nograd")) < 1e-5
+    if kernel == "matern" and case != "t1":      # the two branches really differ on the diagonal in the reference (n > 1)
+        assert not np.array_equal(G[f"{key}/prior/templates/covar"], G[f"{key}/prior/templates/covar_nograd"])
+    # differentiable through the kernel hyper-parameters and the mean biases
+    prior = gp.forward(T_(G, f"{key}/param/Z"))
+    (prior.mean.sum() + prior.covariance_matrix.sum()).backward()
+    assert gp.mean_module.cls_bias.grad is not None and any(p.grad is not None for p in gp._kernel_raw() if p is not None)
