@@ -72,7 +72,7 @@ def _engine(name, kernel, S, precision="bf16x3", lengthscale=None, **kw):
 
 def test_cfg2_train_step_full_size_subset_parity():
     """ImageNet shape (C=1000, T=32, D=512, d=256, S=10, B=128): one engine step; the template weights and the GP parameter
-    gradients of a handful of classes against float64 autograd through the oracle, driven by the engine's own dw."""
+    gradients of 41 classes spread over the class range against float64 autograd through the oracle, driven by the engine's own dw."""
     wl, shp, eng, st = _engine("cfg2", "rbf", 10, lengthscale=1.4146)
     f, y = wl["f_train"][: shp.B].cuda(), wl["y_train"][: shp.B].cuda()
     eng.skip_update = True
@@ -82,7 +82,7 @@ def test_cfg2_train_step_full_size_subset_parity():
     w = eng.w.cpu()                                                    # [S, C, T]
     assert float((w.sum(-1) - 1).abs().max()) < 1e-5 and float(w.min()) >= 0.0
     assert torch.isfinite(eng.flat_g).all()
-    idx = torch.tensor([0, 1, 17, 500, 998, 999])
+    idx = torch.unique(torch.cat([torch.tensor([0, 1, 17, 500, 998, 999]), torch.arange(5, shp.C, 29)]))   # 41 classes across every SM's slots
     sub = _class_subset(st, idx)
     eps = philox.eps_tensor(11, 0, shp.C, shp.T, 10)[idx]
     dw = eng.dw.cpu()[:, idx]
@@ -91,7 +91,7 @@ def test_cfg2_train_step_full_size_subset_parity():
     w32, _, w64, _ = oracle_pair(sub, eps)
     n = shp.T + 1
     assert_parity(w[:, idx], w32, w64, name="w")
-    assert rel_err(w[:, idx], w64) < 1e-3
+    assert rel_err(w[:, idx], w64) < max(1e-3, 2.0 * rel_err(w32, w64))   # vs EXACT arithmetic: no further off than the reference's own fp32 path
     got = {"m": eng.g("m").view(shp.C, n).cpu()[idx], "chol": eng.g("Lq").view(shp.C, n, n).cpu()[idx],
            "ls": eng.g("ls").view(shp.C, 1, -1).cpu()[idx], "os": eng.g("os").cpu()[idx]}
     for k_, g_ in got.items():
