@@ -80,3 +80,24 @@ def test_no_cpu_fallback():
     from clip_gp_b200 import metrics
     with pytest.raises(RuntimeError):
         metrics.compute_ece(torch.randn(8, 4), torch.zeros(8, dtype=torch.long))
+
+
+def test_gp_bwd_args_layout_matches_a_c_compiler(tmp_path):
+    """clipgp_gp_bwd_args: ctypes mirror == what gcc lays out from the header."""
+    import subprocess
+    names = ["dkl_scalar", "dZ_last", "dmean_x", "proto_dP_stride_s", "proto_dP_scale", "proto_norm", "proto_D", "dw_out", "tl_Z", "tl_dlT_ld",
+             "tl_B", "tl_mode", "tl_scale"]
+    src = tmp_path / "szb.c"
+    fmt = " ".join(["%zu"] * (len(names) + 1))
+    args = ", ".join(["sizeof(clipgp_gp_bwd_args)"] + [f"offsetof(clipgp_gp_bwd_args, {n})" for n in names])
+    src.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "clipgp.h"\nint main(void) {{ printf("{fmt}\\n", {args}); return 0; }}\n')
+    exe = tmp_path / "szb"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    B = _lib.GpBwdArgs
+    assert got == [ctypes_sizeof(B)] + [getattr(B, n).offset for n in names]
+
+
+def ctypes_sizeof(t):
+    import ctypes
+    return ctypes.sizeof(t)
