@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <float.h>
 #include <stdlib.h>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -518,10 +519,39 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// Encoded descriptors are pure functions of (base pointer, geometry, layout kind): a small cache keeps eager callers (the autograd
+// heads, the trainers' per-batch GEMMs on persistent buffers) from re-encoding three maps per launch on the host.
+struct MapKey {
+    const void* base; long long a, b, c; int kind;
+    bool operator==(const MapKey& o) const { return base == o.base && a == o.a && b == o.b && c == o.c && kind == o.kind; }
+};
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+static MapSlot g_map_cache[128];
+static std::mutex g_map_mutex;
+static unsigned map_slot(const MapKey& k) {
+    unsigned long long h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (unsigned long long)k.a * 0xC2B2AE3D27D4EB4Full; h ^= (unsigned long long)k.b * 0x165667B19E3779F9ull;
+    h ^= (unsigned long long)k.c * 0x27D4EB2F165667C5ull; h ^= (unsigned long long)k.kind * 0x85EBCA77C2B2AE63ull;
+    return (unsigned)(h >> 40) & 127u;
+}
+static bool map_lookup(const MapKey& k, CUtensorMap* out) {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    const MapSlot& sl = g_map_cache[map_slot(k)];
+    if (sl.used && sl.key == k) { *out = sl.map; return true; }
+    return false;
+}
+static void map_store(const MapKey& k, const CUtensorMap& m) {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    MapSlot& sl = g_map_cache[map_slot(k)];
+    sl.key = k; sl.map = m; sl.used = true;
+}
+
 // Operand tensor map (128-byte swizzle, zero OOB fill), element size `elt` (2 = bf16, 4 = fp32 consumed as TF32).
 //   K-major  operand [rows, K] row-major: box = [128 B of K][box_rows rows];
 //   MN-major operand [K, rows] row-major: box = [128 B of rows][128 / elt ... K rows of one stage] (see make_smem_desc_mn).
 static int make_map(CUtensorMap* map, const void* base, long long rows, long long K, int box_rows, int elt, int mn_major) {
+    const MapKey key{base, rows, K, (long long)box_rows, elt * 2 + (mn_major ? 1 : 0)};
+    if (map_lookup(key, map)) return CLIPGP_OK;
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) { set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver"); return CLIPGP_ERR_CUDA; }
     const cuuint32_t line = (cuuint32_t)(128 / elt);
@@ -535,11 +565,14 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_gemm: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return CLIPGP_ERR_CUDA; }
+    map_store(key, *map);
     return CLIPGP_OK;
 }
 
 // fp32 row-major [rows, cols] (row pitch ld elements) -> 2D tensor map with a 32 x 32 box, 128B swizzle (one box row = 128 bytes)
 static int make_map_c(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld) {
+    const MapKey key{base, rows, cols, ld, 100};
+    if (map_lookup(key, map)) return CLIPGP_OK;
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) { set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver"); return CLIPGP_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -550,6 +583,7 @@ static int make_map_c(CUtensorMap* map, const float* base, long long rows, long 
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_gemm: cuTensorMapEncodeTiled(C) failed (CUresult %d)", (int)r); return CLIPGP_ERR_CUDA; }
+    map_store(key, *map);
     return CLIPGP_OK;
 }
 

@@ -187,3 +187,18 @@ def test_tf32_gemm_all_operand_layouts(M, N, K, a_t, b_t):
         r2 = 0.5 * (tf32(A, rnd).double() @ tf32(B, rnd).double().t())
         errs.append(float((C.cpu().double() - r2).abs().max()) / scale)
     assert min(errs) < 2e-5, errs
+
+
+def test_descriptor_cache_keys_on_geometry_and_follows_the_data():
+    """The TMA descriptor cache of gemm_tc.cu is keyed on (pointer, geometry, layout): the same storage viewed with another shape
+    gets its own descriptor, and a cached descriptor reads whatever the buffer holds now."""
+    g = torch.Generator().manual_seed(5)
+    buf_a = torch.empty(256 * 512, device="cuda"); buf_b = torch.empty(384 * 512, device="cuda")
+    out = torch.empty(256 * 768, device="cuda")
+    for rnd in range(3):
+        for (M, N, K) in ((256, 384, 512), (128, 192, 1024), (64, 96, 2048), (256, 384, 512)):
+            A = buf_a[: M * K].view(M, K); B = buf_b[: N * K].view(N, K)
+            A.copy_(_rand(M, K, g).cuda() if not A.is_cuda else _rand(M, K, g)); B.copy_(_rand(N, K, g))
+            C = tc.gemm_tf32(A, B, 0.5, out=out[: M * N].view(M, N))
+            ref = 0.5 * (A.double() @ B.double().t())
+            assert float((C.double() - ref).abs().max()) < 2e-3 * float(ref.abs().max()), (rnd, M, N, K)
