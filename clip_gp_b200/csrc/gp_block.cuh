@@ -44,6 +44,12 @@ __device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
     *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
 }
 
+// rows of a [.][ld] matrix of T at p can be read / written as 16-byte vectors at column offsets that are multiples of 4
+template <typename T>
+__device__ __forceinline__ bool rows_vec16(const T* p, int ld) {
+    return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ((ld * (int)sizeof(T)) & 15) == 0;
+}
+
 template <int MAXN, int MAXB>
 struct Blk4 {
     static constexpr int NT = (MAXN + 3) / 4, NA = NT * (NT + 1) / 2, NB = MAXB / 4, NP = 4 * NT;
@@ -91,18 +97,31 @@ __device__ bool blk4_cholesky_solve(T* __restrict__ A, int n, int ld, T* __restr
     T m[4][4];
     __syncthreads();
     if (tid == 0) *flag = 0;
+    // tile rows as one 16-byte-vector access where the four columns are all inside the triangle / the column range (a scalar walk of
+    // 4-column tiles is a 4-way bank conflict: ncu, profiles/r2_gp_bank_conflicts.txt); ragged edges and diagonal tiles stay scalar
+    const bool vA = rows_vec16(A, ld), vB = rows_vec16(B, ldb);
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < 4; ++x) {
+        const int i = i0 + x;
+        T r[4] = {(T)0, (T)0, (T)0, (T)0};
+        if (owner && i < n) {
+            if (!isB) {
+                if (vA && c0 + 3 <= i) ld4(A + i * ld + c0, r);
+                else {
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = i0 + x, c = c0 + y;
-            T v = (T)0;
-            if (owner && i < n) {
-                if (!isB) { if (c <= i) v = A[i * ld + c]; }
-                else if (c < ncol) v = B[i * ldb + c];
+                    for (int y = 0; y < 4; ++y) if (c0 + y <= i) r[y] = A[i * ld + c0 + y];
+                }
+            } else {
+                if (vB && c0 + 3 < ncol) ld4(B + i * ldb + c0, r);
+                else {
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) if (c0 + y < ncol) r[y] = B[i * ldb + c0 + y];
+                }
             }
-            m[x][y] = v;
         }
+#pragma unroll
+        for (int y = 0; y < 4; ++y) m[x][y] = r[y];
+    }
     const int nblk = (n + 3) >> 2;
     BLK4_TS(0);
     for (int J = 0; J < nblk; ++J) {
@@ -199,15 +218,24 @@ __device__ bool blk4_cholesky_solve(T* __restrict__ A, int n, int ld, T* __restr
     BLK4_TS(7);
     if (owner) {
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < 4; ++x) {
+            const int i = i0 + x;
+            if (i < n) {
+                if (!isB) {
+                    if (vA && c0 + 3 <= i) st4(A + i * ld + c0, m[x]);
+                    else {
 #pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const int i = i0 + x, c = c0 + y;
-                if (i < n) {
-                    if (!isB) { if (c <= i) A[i * ld + c] = m[x][y]; }
-                    else if (c < ncol) B[i * ldb + c] = m[x][y];
+                        for (int y = 0; y < 4; ++y) if (c0 + y <= i) A[i * ld + c0 + y] = m[x][y];
+                    }
+                } else {
+                    if (vB && c0 + 3 < ncol) st4(B + i * ldb + c0, m[x]);
+                    else {
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) if (c0 + y < ncol) B[i * ldb + c0 + y] = m[x][y];
+                    }
                 }
             }
+        }
     }
     __syncthreads();
     for (int j = tid; j < n; j += blockDim.x) {
@@ -246,10 +274,20 @@ __device__ void blk4_trsm_lowerT_left(const T* __restrict__ L, int ldl, const T*
     const int ti = owner ? tid / NC : 0, tc = owner ? tid - ti * NC : 0, i0 = 4 * ti, c0 = 4 * tc;
     T m[4][4];
     __syncthreads();
+    const bool vB = rows_vec16(B, ldb) && c0 + 3 < ncol;       // whole tile rows as 16-byte vectors (see blk4_cholesky_solve)
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+    for (int x = 0; x < 4; ++x) {
+        T r[4] = {(T)0, (T)0, (T)0, (T)0};
+        if (owner && i0 + x < n) {
+            if (vB) ld4(B + (i0 + x) * ldb + c0, r);
+            else {
 #pragma unroll
-        for (int y = 0; y < 4; ++y) m[x][y] = (owner && i0 + x < n && c0 + y < ncol) ? B[(i0 + x) * ldb + c0 + y] : (T)0;
+                for (int y = 0; y < 4; ++y) if (c0 + y < ncol) r[y] = B[(i0 + x) * ldb + c0 + y];
+            }
+        }
+#pragma unroll
+        for (int y = 0; y < 4; ++y) m[x][y] = r[y];
+    }
     const int nblk = (n + 3) >> 2;
     int par = 0;
     for (int K = nblk - 1; K >= 0; --K, par ^= 1) {
@@ -291,9 +329,15 @@ __device__ void blk4_trsm_lowerT_left(const T* __restrict__ L, int ldl, const T*
     }
     if (owner) {
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < 4; ++x) {
+            if (i0 + x < n) {
+                if (vB) st4(B + (i0 + x) * ldb + c0, m[x]);
+                else {
 #pragma unroll
-            for (int y = 0; y < 4; ++y) if (i0 + x < n && c0 + y < ncol) B[(i0 + x) * ldb + c0 + y] = m[x][y];
+                    for (int y = 0; y < 4; ++y) if (c0 + y < ncol) B[(i0 + x) * ldb + c0 + y] = m[x][y];
+                }
+            }
+        }
     }
     __syncthreads();
 }
