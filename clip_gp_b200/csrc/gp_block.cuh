@@ -44,6 +44,21 @@ __device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
     *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
 }
 
+// Group g (4 elements) of a scratch row that holds `ngroups` groups and is only ever accessed through these two helpers.  float: the
+// 16-byte vector at row + 4 g.  double: the two 16-byte halves live in two planes of the row (first halves of all groups, then the second
+// halves), so the eight threads of a quarter warp that read consecutive groups touch eight consecutive vectors; a 32-byte-strided pair
+// of double2 accesses is a 2-way bank conflict (profiles/r2_gp_bank_conflicts.txt, gp_block.cuh ld4 / st4 lines).
+__device__ __forceinline__ void ld4g(const float* row, int ngroups, int g, float (&v)[4]) { (void)ngroups; ld4(row + 4 * g, v); }
+__device__ __forceinline__ void st4g(float* row, int ngroups, int g, const float (&v)[4]) { (void)ngroups; st4(row + 4 * g, v); }
+__device__ __forceinline__ void ld4g(const double* row, int ngroups, int g, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(row + 2 * g), b = *reinterpret_cast<const double2*>(row + 2 * ngroups + 2 * g);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4g(double* row, int ngroups, int g, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(row + 2 * g) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(row + 2 * ngroups + 2 * g) = make_double2(v[2], v[3]);
+}
+
 // rows of a [.][ld] matrix of T at p can be read / written as 16-byte vectors at column offsets that are multiples of 4
 template <typename T>
 __device__ __forceinline__ bool rows_vec16(const T* p, int ld) {
@@ -166,7 +181,7 @@ __device__ bool blk4_cholesky_solve(T* __restrict__ A, int n, int ld, T* __restr
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const T uc[4] = {m[0][k], m[1][k], m[2][k], m[3][k]}, gc[4] = {g[0][k], g[1][k], g[2][k], g[3][k]};
-                st4(pU + NP * k + i0, uc); st4(pG + NP * k + i0, gc);
+                st4g(pU + NP * k, NT, ti, uc); st4g(pG + NP * k, NT, ti, gc);
             }
         }
         if (MAXB > 0 && owner && isB && ti == J) {
@@ -182,7 +197,7 @@ __device__ bool blk4_cholesky_solve(T* __restrict__ A, int n, int ld, T* __restr
                         for (int y = 0; y < 4; ++y) m[x][y] -= g[x][k] * m[k][y];
                     }
 #pragma unroll
-            for (int x = 0; x < 4; ++x) st4(bR + MB * x + c0, m[x]);
+            for (int x = 0; x < 4; ++x) st4g(bR + MB * x, MB / 4, tk, m[x]);
         }
         if (J + 1 == nblk) break;
         if (J == 2) BLK4_TS(4);
@@ -192,10 +207,10 @@ __device__ bool blk4_cholesky_solve(T* __restrict__ A, int n, int ld, T* __restr
         if (owner && ti > J && (isB || tk > J)) {
             T g[4][4], u[4][4];                                                          // g[k][x], u[k][y]
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ld4(pG + NP * k + i0, g[k]);
+            for (int k = 0; k < 4; ++k) ld4g(pG + NP * k, NT, ti, g[k]);
             if (!isB) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ld4(pU + NP * k + c0, u[k]);
+                for (int k = 0; k < 4; ++k) ld4g(pU + NP * k, NT, tk, u[k]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -204,7 +219,7 @@ __device__ bool blk4_cholesky_solve(T* __restrict__ A, int n, int ld, T* __restr
                         for (int y = 0; y < 4; ++y) m[x][y] -= g[k][x] * u[k][y];
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ld4(bR + MB * k + c0, u[k]);                  // u[k][y]
+                for (int k = 0; k < 4; ++k) ld4g(bR + MB * k, MB / 4, tk, u[k]);                  // u[k][y]
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -309,7 +324,7 @@ __device__ void blk4_trsm_lowerT_left(const T* __restrict__ L, int ldl, const T*
                 for (int y = 0; y < 4; ++y) m[a][y] *= ia;
             }
 #pragma unroll
-            for (int x = 0; x < 4; ++x) st4(X + W * x + c0, m[x]);
+            for (int x = 0; x < 4; ++x) st4g(X + W * x, NC, tc, m[x]);
         }
         if (K == 0) break;
         __syncthreads();
@@ -317,7 +332,7 @@ __device__ void blk4_trsm_lowerT_left(const T* __restrict__ L, int ldl, const T*
 #pragma unroll
             for (int k = 0; k < 4; ++k) {              // one row of the block at a time: 8 live operand values next to the 16 of the tile
                 T xr[4], l[4];
-                ld4(X + W * k + c0, xr);
+                ld4g(X + W * k, NC, tc, xr);
 #pragma unroll
                 for (int x = 0; x < 4; ++x) l[x] = (k0 + k < n) ? L[(k0 + k) * ldl + i0 + x] : (T)0;
 #pragma unroll
