@@ -109,6 +109,7 @@ GP_CASES = {
     "t32": (6, 32, 96, 48, 4),        # the headline per-class shape n = 33
     "t1": (5, 1, 32, 8, 2),           # single template (n = 2)
     "lowrank": (3, 4, 40, 256, 3),    # gp_pca_dim > rank: red_dim = min(256, C*T) = 12  (gp_template_weigher.py:33-34)
+    "t64": (4, 64, 128, 48, 3),       # the cfg5 per-class shape n = 65 (general block kernels); pins the ORACLE on CPU (tests/test_ref_golden.py)
 }
 
 
