@@ -129,6 +129,40 @@ def _worker(rank, world, port, q):
         hybrid = torch.cat([Wp.grad.reshape(-1), g_m.reshape(-1), g_L.reshape(-1)])
         cd.allreduce_sum_(hybrid)
         assert float((hybrid - full).abs().max()) < 1e-5 * float(full.abs().max()) + 1e-7
+        # ---------------- batch sharding (the default multi-GPU mode): every rank its OWN batch, every loss term pre-divided by
+        # the world size, gradients summed -> the gradient of the mean loss over the world * B rows; then the fused peer step's protocol
+        # (csrc/peer.cu): reduce-scatter, AdamW on this rank's quarter-float4 slice only, all-gather == AdamW on the whole vector
+        B = shp.B
+
+        def grads_batch(f_, y_, share):
+            st = ogp.build_state(wl["E"], "rbf", shp.d)
+            st.var_mean, st.chol_var = synth.trained_like_q(shp.C, shp.T + 1, 5)
+            orc = OracleAdapter(st, shp.D, shots=shp.shots)
+            protos, _ = ogp.sample_prototypes(st, philox.eps_tensor(7, 0, shp.C, shp.T, S))       # same draws on every rank
+            ce = oh.adapter_mc_ce(f_, y_, orc.W, protos, 100.0) * share
+            kl = ogp.kl_divergence(st.var_mean, st.chol_var).sum() * 0.01 * share
+            l2 = (orc.W - torch.eye(shp.D)).pow(2).sum() * (0.5 / shp.shots) * share
+            (ce + kl + l2).backward()
+            params = torch.cat([orc.W.detach().reshape(-1), st.var_mean.detach().reshape(-1), st.chol_var.detach().reshape(-1)])
+            return torch.cat([orc.W.grad.reshape(-1), st.var_mean.grad.reshape(-1), st.chol_var.grad.reshape(-1)]), params
+
+        fa, ya = wl["f_train"][: world * B], wl["y_train"][: world * B]
+        g_loc, p0 = grads_batch(fa[rank * B:(rank + 1) * B], ya[rank * B:(rank + 1) * B], 1.0 / world)
+        g_sum = g_loc.clone()
+        cd.allreduce_sum_(g_sum)
+        g_full, _ = grads_batch(fa, ya, 1.0)
+        assert float((g_sum - g_full).abs().max()) < 1e-5 * float(g_full.abs().max()) + 1e-7
+
+        def adamw(p, g_, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, t=1):
+            m = (1 - b1) * g_; v = (1 - b2) * g_ * g_
+            return p - (lr / (1 - b1 ** t)) * m / (v.sqrt() / (1 - b2 ** t) ** 0.5 + eps)
+
+        n = g_sum.numel(); n4 = n >> 2; per = (n4 + world - 1) // world          # the slice formula of peer.cu
+        lo, hi = 4 * per * rank, (4 * min(per * (rank + 1), n4) if rank < world - 1 else n)
+        mine = torch.zeros(n)
+        mine[lo:hi] = adamw(p0[lo:hi], g_sum[lo:hi])                            # reduce-scatter + AdamW on the own slice
+        cd.allreduce_sum_(mine)                                                 # all-gather (disjoint slices)
+        assert torch.equal(mine, adamw(p0, g_sum))
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
